@@ -1,0 +1,348 @@
+/*
+ * trino_gpu.h — C ABI of libtrino_gpu.so: the B200 (sm_100a) implementation of Trino's
+ * columnar operator hot path.
+ *
+ * The reference has no FFI for this path: operators are Java classes that
+ * implement io.trino.operator.Operator / OperatorFactory.  Every entry point below is what a
+ * thin Java Operator (java/) binds through Panama/JNI, and each cites the
+ * reference interface it stands in for (paths relative to
+ * /root/reference/core/trino-main/src/main/java/io/trino/ = M/, .../trino-spi/.../spi/ = S/).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; no C++/torch types.
+ *   - every call returns TGPU_OK (0) or a negative tgpu_status; tgpu_last_error() gives text.
+ *   - a handle is used by one thread at a time (mirrors @NotThreadSafe Operator, M/operator/Driver.java:298);
+ *     distinct handles may be used concurrently.
+ *   - pages are Arrow-layout column buffers.  Host pages are copied to the device inside
+ *     add_input; pages flagged TGPU_PAGE_DEVICE already live in HBM and are consumed in place.
+ *   - there is NO CPU fallback: without a CUDA device every create call fails with TGPU_ERR_CUDA.
+ */
+#ifndef TRINO_GPU_H
+#define TRINO_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status / error codes */
+typedef enum tgpu_status {
+    TGPU_OK = 0,
+    TGPU_ERR_INVALID_ARGUMENT = -1,       /* IllegalArgumentException / checkArgument */
+    TGPU_ERR_CUDA = -2,                   /* GENERIC_INTERNAL_ERROR: device failure, no device, OOM on device */
+    TGPU_ERR_INSUFFICIENT_RESOURCES = -3, /* GENERIC_INSUFFICIENT_RESOURCES (M/operator/BigintGroupByHash.java:242, M/operator/PagesIndex.java:247) */
+    TGPU_ERR_NUMERIC_VALUE_OUT_OF_RANGE = -4, /* NUMERIC_VALUE_OUT_OF_RANGE (M/type/BigintOperators.java:52-84) */
+    TGPU_ERR_DIVISION_BY_ZERO = -5,       /* DIVISION_BY_ZERO (M/type/BigintOperators.java:96-106) */
+    TGPU_ERR_NOT_SUPPORTED = -6,          /* NOT_SUPPORTED: caller keeps the Java operator */
+    TGPU_ERR_ILLEGAL_STATE = -7           /* IllegalStateException / checkState (protocol misuse) */
+} tgpu_status;
+
+/* ------------------------------------------------------------------ columnar data model
+ * Stands in for S/Page.java:31 and the Block family (S/block/LongArrayBlock.java:36-41,
+ * IntArrayBlock, ShortArrayBlock, ByteArrayBlock, VariableWidthBlock.java:41-46,
+ * DictionaryBlock.java:37-40, RunLengthEncodedBlock.java:71-72).                       */
+typedef enum tgpu_type {
+    TGPU_INT64 = 1,    /* BIGINT, short DECIMAL, TIMESTAMP(millis)…  (LongArrayBlock)          */
+    TGPU_INT32 = 2,    /* INTEGER, DATE                              (IntArrayBlock)           */
+    TGPU_INT16 = 3,    /* SMALLINT                                   (ShortArrayBlock)         */
+    TGPU_INT8 = 4,     /* TINYINT, BOOLEAN                           (ByteArrayBlock)          */
+    TGPU_FLOAT64 = 5,  /* DOUBLE, raw IEEE bits in a LongArrayBlock (S/type/DoubleType.java:205) */
+    TGPU_UTF8 = 7,     /* VARCHAR / CHAR / VARBINARY: int32 offsets[length+1] + bytes          */
+    TGPU_DICT32 = 8,   /* DictionaryBlock: data = int32 ids[length], dictionary = value column */
+    TGPU_RLE = 9       /* RunLengthEncodedBlock: dictionary = 1-row value column, broadcast    */
+} tgpu_type;
+
+enum {
+    TGPU_COL_NULLS_BYTEMAP = 1 /* `validity` points at Java's boolean[] valueIsNull (1 byte/position,
+                                  1 = NULL) instead of an Arrow LSB bitmap (1 bit/position, 1 = valid) */
+};
+
+typedef struct tgpu_column {
+    int32_t type;                         /* tgpu_type */
+    int32_t flags;                        /* TGPU_COL_* */
+    int64_t length;                       /* positions */
+    const void* data;                     /* values; int32 ids for DICT32; bytes for UTF8; unused for RLE */
+    const int32_t* offsets;               /* UTF8 only: length+1 entries */
+    const uint8_t* validity;              /* NULL = no nulls */
+    const struct tgpu_column* dictionary; /* DICT32: dictionary values; RLE: the single value */
+} tgpu_column;
+
+enum {
+    TGPU_PAGE_DEVICE = 1 /* all buffers referenced by the page are device pointers (GPU->GPU operator
+                            chaining and the device-resident benchmark path) */
+};
+
+typedef struct tgpu_page {
+    int32_t num_columns;
+    int32_t flags;                        /* TGPU_PAGE_* */
+    int64_t num_rows;                     /* Page.getPositionCount() */
+    const tgpu_column* columns;
+} tgpu_page;
+
+typedef struct tgpu_ctx tgpu_ctx;         /* one per (process, device): stream, memory pool, error slot */
+typedef struct tgpu_op tgpu_op;           /* one Operator instance */
+typedef struct tgpu_lookup tgpu_lookup;   /* built join table: LookupSource (M/operator/join/LookupSource.java:24-68) */
+
+/* ------------------------------------------------------------------ context */
+int tgpu_ctx_create(int device, tgpu_ctx** out);
+void tgpu_ctx_destroy(tgpu_ctx* ctx);
+const char* tgpu_last_error(const tgpu_ctx* ctx);     /* message of the last failing call on ctx */
+const char* tgpu_status_name(int status);             /* Trino StandardErrorCode name */
+int tgpu_ctx_synchronize(tgpu_ctx* ctx);              /* cudaStreamSynchronize on the ctx stream */
+void* tgpu_ctx_stream(tgpu_ctx* ctx);                 /* the cudaStream_t every kernel of ctx is launched on */
+int64_t tgpu_ctx_kernel_launches(const tgpu_ctx* ctx);/* number of kernels this library launched on ctx */
+int tgpu_device_count(void);
+
+/* device memory helpers for the device-resident path (bench, GPU->GPU chaining, tests) */
+int tgpu_malloc(tgpu_ctx* ctx, size_t bytes, void** out);
+int tgpu_free(tgpu_ctx* ctx, void* ptr);
+int tgpu_memcpy_h2d(tgpu_ctx* ctx, void* dst, const void* src, size_t bytes);
+int tgpu_memcpy_d2h(tgpu_ctx* ctx, void* dst, const void* src, size_t bytes);
+int tgpu_host_alloc_pinned(size_t bytes, void** out);
+int tgpu_host_free_pinned(void* ptr);
+/* write a buffer larger than L2 (bench hygiene between timed iterations) */
+int tgpu_flush_l2(tgpu_ctx* ctx);
+/* device timing on the ctx stream (cudaEvent pair) */
+int tgpu_timer_start(tgpu_ctx* ctx);
+int tgpu_timer_stop_ms(tgpu_ctx* ctx, float* ms);
+
+/* ------------------------------------------------------------------ expressions (PageProcessor)
+ * Stands in for the compiled PageFilter/PageProjection pair produced by
+ * ExpressionCompiler.compilePageProcessor (M/sql/gen/ExpressionCompiler.java:50-85) from the
+ * RowExpression trees at M/sql/planner/LocalExecutionPlanner.java:2111-2127.
+ * A program is three-address code over per-row temporaries; operands are an input channel, an
+ * immediate, or a temporary.  Value types inside the VM: BIGINT (all integer widths are sign-extended
+ * on load), DOUBLE, BOOLEAN; every value carries a null flag (SQL three-valued logic).          */
+typedef enum tgpu_expr_op {
+    TGPU_EX_MOV = 0,
+    TGPU_EX_ADD = 1, TGPU_EX_SUB = 2, TGPU_EX_MUL = 3, TGPU_EX_DIV = 4, TGPU_EX_MOD = 5, TGPU_EX_NEG = 6,
+    TGPU_EX_EQ = 10, TGPU_EX_NE = 11, TGPU_EX_LT = 12, TGPU_EX_LE = 13, TGPU_EX_GT = 14, TGPU_EX_GE = 15,
+    TGPU_EX_AND = 20, TGPU_EX_OR = 21, TGPU_EX_NOT = 22,
+    TGPU_EX_IS_NULL = 23, TGPU_EX_IS_NOT_NULL = 24,
+    TGPU_EX_BETWEEN = 25,          /* a BETWEEN b AND c: c in operand `c` */
+    TGPU_EX_CAST_BIGINT_TO_DOUBLE = 30,
+    TGPU_EX_CAST_DOUBLE_TO_BIGINT = 31, /* Math.round semantics, range-checked (M/type/DoubleOperators.java) */
+    TGPU_EX_IN = 40                /* a IN (const list): b.imm = index into in_lists, all operands of `vtype` */
+} tgpu_expr_op;
+
+typedef enum tgpu_vtype { TGPU_V_BIGINT = 0, TGPU_V_DOUBLE = 1, TGPU_V_BOOLEAN = 2 } tgpu_vtype;
+typedef enum tgpu_operand_kind { TGPU_OPND_NONE = 0, TGPU_OPND_COLUMN = 1, TGPU_OPND_TEMP = 2, TGPU_OPND_CONST = 3, TGPU_OPND_NULL = 4 } tgpu_operand_kind;
+
+typedef struct tgpu_operand {
+    int32_t kind;                         /* tgpu_operand_kind */
+    int32_t index;                        /* channel or temp slot */
+    union { int64_t i64; double f64; } imm;
+} tgpu_operand;
+
+typedef struct tgpu_expr_insn {
+    int32_t op;                           /* tgpu_expr_op */
+    int32_t vtype;                        /* tgpu_vtype of the OPERANDS (result of comparisons is BOOLEAN) */
+    int32_t dst;                          /* temp slot written, 0..TGPU_MAX_TEMPS-1 */
+    int32_t reserved;
+    tgpu_operand a, b, c;
+} tgpu_expr_insn;
+
+#define TGPU_MAX_TEMPS 8
+#define TGPU_MAX_INSNS 64
+#define TGPU_MAX_CHANNELS 32
+
+typedef struct tgpu_in_list { int32_t count; const int64_t* values; /* raw bits for DOUBLE */ } tgpu_in_list;
+
+typedef struct tgpu_projection {
+    int32_t kind;        /* 0 = pass an input channel through (any type incl. UTF8/DICT/RLE, like InputPageProjection);
+                            1 = computed: value of temp `index` after the program ran */
+    int32_t index;       /* channel or temp */
+    int32_t vtype;       /* computed only: result type (BIGINT->INT64, DOUBLE->FLOAT64, BOOLEAN->INT8) */
+} tgpu_projection;
+
+typedef struct tgpu_expr_program {
+    int32_t num_insns;
+    const tgpu_expr_insn* insns;
+    int32_t filter_temp;                  /* temp holding the BOOLEAN filter result, or -1 = no filter.
+                                             NULL or FALSE rejects the row (M/sql/gen/columnar/ColumnarFilter.java:27-30) */
+    int32_t num_filter_insns;             /* insns [0, num_filter_insns) compute the filter and run for every row; the
+                                             remaining insns (projections) run, and may raise errors, only for selected
+                                             rows (PageProcessor filters first: M/operator/project/PageProcessor.java:126-142) */
+    int32_t num_projections;
+    const tgpu_projection* projections;
+    int32_t num_in_lists;
+    const tgpu_in_list* in_lists;
+} tgpu_expr_program;
+
+/* FilterAndProjectOperator (M/operator/FilterAndProjectOperator.java:60-95) over a PageProcessor
+ * (M/operator/project/PageProcessor.java:105-142).  Output: one page per non-empty input page.  */
+int tgpu_filter_project_create(tgpu_ctx* ctx, const tgpu_expr_program* program, tgpu_op** out);
+
+/* ------------------------------------------------------------------ hash aggregation
+ * Stands in for HashAggregationOperator (M/operator/HashAggregationOperator.java:346-498) +
+ * InMemoryHashAggregationBuilder (M/operator/aggregation/builder/InMemoryHashAggregationBuilder.java:141-300)
+ * + GroupByHash (M/operator/GroupByHash.java:82-125) + the grouped accumulators
+ * (M/operator/aggregation/GroupedAggregator.java:77-117).                                        */
+typedef enum tgpu_agg_function {
+    TGPU_AGG_COUNT_STAR = 0,  /* CountAggregation.java:36-51    -> BIGINT                       */
+    TGPU_AGG_COUNT = 1,       /* CountColumn.java               -> BIGINT (non-null inputs)     */
+    TGPU_AGG_SUM = 2,         /* DoubleSumAggregation.java:37-63 / BigintSumAggregation.java:38-59 (checked) */
+    TGPU_AGG_AVG = 3,         /* DoubleAverageAggregations.java:37-63 (DOUBLE input) / LongAverage (BIGINT input) */
+    TGPU_AGG_MIN = 4,
+    TGPU_AGG_MAX = 5
+} tgpu_agg_function;
+
+typedef enum tgpu_agg_step {   /* M/sql/planner/plan/AggregationNode.java:361-402 */
+    TGPU_STEP_SINGLE = 0,      /* raw input -> final output                                   */
+    TGPU_STEP_PARTIAL = 1,     /* raw input -> intermediate state columns                     */
+    TGPU_STEP_FINAL = 2,       /* intermediate state columns -> final output                  */
+    TGPU_STEP_INTERMEDIATE = 3 /* intermediate -> intermediate                                */
+} tgpu_agg_step;
+
+typedef struct tgpu_agg_fn {
+    int32_t function;          /* tgpu_agg_function */
+    int32_t input_channel;     /* -1 for count(*).  For FINAL/INTERMEDIATE: first channel of the state columns */
+    int32_t mask_channel;      /* -1 or a BOOLEAN channel (AggregationMask, M/operator/aggregation/AggregationMask.java:30-100) */
+    int32_t reserved;
+} tgpu_agg_fn;
+
+/* Intermediate state layout emitted by PARTIAL and consumed by FINAL (one or two flat columns per
+ * aggregate, the Arrow-side flattening of the reference's state serializers):
+ *   count/count(*) : INT64 count
+ *   sum            : value (INT64 or FLOAT64), NULL when no input rows (NullableDoubleState / NullableLongState)
+ *   avg            : INT64 count, FLOAT64 sum (LongAndDoubleState)
+ *   min/max        : value, NULL when no input rows                                            */
+typedef struct tgpu_agg_spec {
+    int32_t num_keys;
+    const int32_t* key_channels;  /* groupByChannels */
+    int32_t step;                 /* tgpu_agg_step */
+    int32_t num_aggs;
+    const tgpu_agg_fn* aggs;
+    int64_t expected_groups;      /* expectedGroups, sizes the table like arraySize(expected, 0.75) */
+    int64_t max_partial_bytes;    /* task.max-partial-aggregation-memory (PARTIAL flush threshold); 0 = never flush */
+    /* optional fused pre-stage: filter + projections evaluated in registers in the same kernel that
+       aggregates, so projected columns never reach HBM (ScanFilterAndProject -> HashAggregation chain of Q1).
+       When set, key_channels / input_channel refer to the program's projection outputs.        */
+    const tgpu_expr_program* pre;
+} tgpu_agg_spec;
+
+int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op** out);
+/* GroupByHash.getGroupCount() */
+int tgpu_agg_group_count(tgpu_op* op, int64_t* out);
+
+/* GroupByHash.getGroupIds(Page) alone (M/operator/GroupByHash.java:118-125): dense ids in
+ * first-seen order for the key columns of `page`, written to `out_group_ids` (host or device to
+ * match the page).  The table persists in the handle across calls, like the Java object.        */
+int tgpu_groupby_hash_create(tgpu_ctx* ctx, int32_t num_keys, const int32_t* key_channels, int64_t expected_groups, tgpu_op** out);
+int tgpu_groupby_hash_get_group_ids(tgpu_op* op, const tgpu_page* page, int32_t* out_group_ids);
+
+/* ------------------------------------------------------------------ hash join
+ * Build: HashBuilderOperator (M/operator/join/unspilled/HashBuilderOperator.java:253-333) over
+ * PagesIndex (M/operator/PagesIndex.java:224-256,523-542) producing a JoinHash
+ * (M/operator/join/JoinHash.java) = PagesHash (BigintPagesHash.java:62-141 / DefaultPagesHash.java:61-144)
+ * + ArrayPositionLinks (M/operator/join/ArrayPositionLinks.java:45-104).
+ * Probe: LookupJoinOperator (M/operator/join/unspilled/LookupJoinOperator.java:52-80) =
+ * JoinProbe.fillCache (JoinProbe.java:112-180) + PageJoiner (PageJoiner.java:93-258) +
+ * LookupJoinPageBuilder (LookupJoinPageBuilder.java:89-160).                                     */
+typedef enum tgpu_join_type {  /* M/operator/join/LookupJoinOperatorFactory.JoinType */
+    TGPU_JOIN_INNER = 0,
+    TGPU_JOIN_PROBE_OUTER = 1
+} tgpu_join_type;
+
+typedef struct tgpu_join_build_spec {
+    int32_t num_key_channels;
+    const int32_t* key_channels;      /* hashChannels of the build pages */
+    int32_t num_output_channels;
+    const int32_t* output_channels;   /* build columns appended to each output row */
+    int64_t expected_positions;       /* expectedPositions (sizing hint only) */
+} tgpu_join_build_spec;
+
+typedef struct tgpu_join_probe_spec {
+    int32_t join_type;                /* tgpu_join_type */
+    int32_t output_single_match;      /* outputSingleMatch (semi-join style: first match only) */
+    int32_t num_key_channels;
+    const int32_t* key_channels;      /* probeJoinChannels */
+    int32_t num_output_channels;
+    const int32_t* output_channels;   /* probeOutputChannels; output page = these, then the build output channels */
+} tgpu_join_probe_spec;
+
+int tgpu_join_build_create(tgpu_ctx* ctx, const tgpu_join_build_spec* spec, tgpu_op** out);
+/* valid after finish(): lendPartitionLookupSource (PartitionedLookupSourceFactory.java:100).  The
+ * lookup stays alive until tgpu_lookup_release, independent of the build operator handle.       */
+int tgpu_join_build_get_lookup(tgpu_op* build, tgpu_lookup** out);
+void tgpu_lookup_release(tgpu_lookup* lookup);
+int64_t tgpu_lookup_position_count(const tgpu_lookup* lookup);   /* LookupSource.getJoinPositionCount */
+int64_t tgpu_lookup_memory_bytes(const tgpu_lookup* lookup);     /* getInMemorySizeInBytes */
+int tgpu_lookup_has_duplicates(const tgpu_lookup* lookup);       /* !positionLinks.isEmpty() */
+int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec* spec, tgpu_lookup* lookup, tgpu_op** out);
+
+/* LookupSource.getJoinPosition(int[] positions, Page hashChannelsPage, Page allChannelsPage, long[] result)
+ * (M/operator/join/JoinHash.java:100-143): for every row of `keys_page` (only the key columns, in
+ * key order) the address index of the chain head or -1.  `out_positions` is int32[num_rows], host or
+ * device to match the page.  This is the index-only probe the headline metric times.            */
+int tgpu_lookup_get_join_positions(tgpu_ctx* ctx, const tgpu_lookup* lookup, const tgpu_page* keys_page, int32_t* out_positions);
+/* PositionLinks.next for every build position (ArrayPositionLinks.java:101-104); -1 terminates */
+int tgpu_lookup_copy_position_links(tgpu_ctx* ctx, const tgpu_lookup* lookup, int32_t* out_links_host);
+
+/* ------------------------------------------------------------------ partitioned output / exchange
+ * Stands in for PartitionedOutputOperator (M/operator/output/PartitionedOutputOperator.java:335-357)
+ * + PagePartitioner (M/operator/output/PagePartitioner.java:133-162,229-433) with the
+ * SystemPartitionFunction.HASH bucket function (M/sql/planner/HashBucketFunction.java:43-46,
+ * M/operator/HashGenerator.java:25-46, M/operator/BucketPartitionFunction.java:45-64).
+ * get_output returns one page per non-empty partition per input page; the partition id of the
+ * page returned last is read with tgpu_partition_last_output_partition.                          */
+typedef struct tgpu_partition_spec {
+    int32_t num_key_channels;
+    const int32_t* key_channels;          /* partitionChannels (constants not supported: TGPU_ERR_NOT_SUPPORTED) */
+    int32_t bucket_count;                 /* HashBucketFunction bucketCount */
+    const int32_t* bucket_to_partition;   /* bucket_count entries, NULL = identity */
+    int32_t null_channel;                 /* -1 or channel whose NULL rows are replicated to every partition */
+    int32_t replicates_any_row;           /* replicatesAnyRow */
+} tgpu_partition_spec;
+
+int tgpu_partition_create(tgpu_ctx* ctx, const tgpu_partition_spec* spec, tgpu_op** out);
+int tgpu_partition_last_output_partition(tgpu_op* op, int32_t* out);
+/* HashGenerator.getPartitions equivalent: partition id per row (after bucket_to_partition) */
+int tgpu_partition_get_partitions(tgpu_op* op, const tgpu_page* page, int32_t* out_partitions);
+
+/* multi-GPU exchange: one process per GPU.  Rank discovery / id distribution is the host's job
+ * (torch.distributed here, Trino's task RPC in a Java deployment); the data path is NCCL send/recv
+ * over NVLink (all-to-all with explicit counts).  Replaces PartitionedOutputBuffer + HTTP pull
+ * (M/execution/buffer/PartitionedOutputBuffer.java, M/operator/DirectExchangeClient.java).       */
+#define TGPU_COMM_ID_BYTES 128
+int tgpu_comm_get_unique_id(uint8_t id[TGPU_COMM_ID_BYTES]);
+int tgpu_comm_init(tgpu_ctx* ctx, const uint8_t id[TGPU_COMM_ID_BYTES], int rank, int world);
+int tgpu_comm_destroy(tgpu_ctx* ctx);
+/* Hash-partition a device-resident page into `world` partitions and exchange: partition p goes to
+ * rank p.  Returns the concatenation (in rank order) of what every rank sent here, as a
+ * library-owned device page.  Fixed-width columns only.                                         */
+int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out);
+
+/* ------------------------------------------------------------------ Operator protocol
+ * One-to-one with M/operator/Operator.java:21-102.                                              */
+int tgpu_op_needs_input(tgpu_op* op, int* out);                  /* needsInput() */
+int tgpu_op_add_input(tgpu_op* op, const tgpu_page* page);       /* addInput(Page): copies; caller keeps ownership */
+int tgpu_op_get_output(tgpu_op* op, tgpu_page** out);            /* getOutput(): *out = NULL when nothing is ready */
+int tgpu_op_finish(tgpu_op* op);                                 /* finish(): re-entrant (Driver.java:380-388) */
+int tgpu_op_is_finished(tgpu_op* op, int* out);                  /* isFinished() */
+int64_t tgpu_op_memory_bytes(tgpu_op* op);                       /* bytes to report through LocalMemoryContext.setBytes */
+void tgpu_op_close(tgpu_op* op);                                 /* close() */
+
+/* output pages are library-owned device pages (flags has TGPU_PAGE_DEVICE) until released */
+void tgpu_page_release(tgpu_ctx* ctx, tgpu_page* page);
+/* copy a device page into caller-provided host buffers: `host` must describe the same schema with
+ * buffers large enough (UTF8: data capacity from tgpu_page_utf8_bytes)                          */
+int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* device_page, tgpu_page* host);
+int64_t tgpu_page_utf8_bytes(tgpu_ctx* ctx, const tgpu_page* device_page, int32_t channel);
+
+/* ------------------------------------------------------------------ synthetic data (bench/tests)
+ * Counter-based generators (x_i = splitmix64(seed ^ i)) so the CPU oracle and the GPU produce
+ * identical TPC-H-shaped columns without a transfer.                            */
+int tgpu_synth_orders_keys(tgpu_ctx* ctx, int64_t n_total, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t* out_device);
+int64_t tgpu_synth_lineitem_rows(int64_t n_orders);
+int tgpu_synth_lineitem_keys(tgpu_ctx* ctx, int64_t n_orders, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t* out_device);
+int tgpu_synth_lineitem_q1(tgpu_ctx* ctx, int64_t n, int64_t first, uint64_t seed,
+                           int32_t* shipdate, int8_t* returnflag, int8_t* linestatus,
+                           double* quantity, double* extendedprice, double* discount, double* tax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRINO_GPU_H */

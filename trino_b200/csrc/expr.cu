@@ -1,0 +1,319 @@
+// expr.cu — FilterAndProjectOperator / PageProcessor on the GPU.
+//
+// Reference: PageProcessor.createWorkProcessor (M/operator/project/PageProcessor.java:105-142): evaluate
+// the filter to SelectedPositions, then every projection over the selected positions
+// (ProjectSelectedPositions.processBatch :302-336); FilterAndProjectOperator
+// (M/operator/FilterAndProjectOperator.java:60-95) wraps it.  Output rows keep input order.
+#include <cub/cub.cuh>
+
+#include "expr.cuh"
+
+namespace tg {
+
+int expr_compile(tgpu_ctx* ctx, const tgpu_expr_program* p, DProgram* out, int32_t* max_channel)
+{
+    memset(out, 0, sizeof(*out));
+    *max_channel = -1;
+    if (!p) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "expression program is null");
+    if (p->num_insns < 0 || p->num_insns > TGPU_MAX_INSNS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "expression program has %d instructions (max %d)", p->num_insns, TGPU_MAX_INSNS);
+    if (p->num_filter_insns < 0 || p->num_filter_insns > p->num_insns) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "num_filter_insns out of range");
+    if (p->filter_temp >= TGPU_MAX_TEMPS) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "filter_temp out of range");
+    if (p->num_in_lists > 8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than 8 IN lists");
+    out->num_insns = p->num_insns;
+    out->num_filter_insns = p->filter_temp >= 0 ? p->num_filter_insns : 0;
+    out->filter_temp = p->filter_temp;
+    out->num_in_lists = p->num_in_lists;
+    int off = 0;
+    for (int i = 0; i < p->num_in_lists; i++) {
+        if (off + p->in_lists[i].count > 128) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "IN lists hold more than 128 constants");
+        out->in_offset[i] = off;
+        out->in_count[i] = p->in_lists[i].count;
+        for (int k = 0; k < p->in_lists[i].count; k++) out->in_values[off + k] = p->in_lists[i].values[k];
+        off += p->in_lists[i].count;
+    }
+    auto conv = [&](const tgpu_operand& o, DOperand* d) -> int {
+        d->kind = o.kind;
+        d->index = o.index;
+        d->imm = o.imm.i64;
+        if (o.kind == TGPU_OPND_COLUMN) {
+            if (o.index < 0 || o.index >= TGPU_MAX_CHANNELS) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "operand channel %d out of range", o.index);
+            if (o.index > *max_channel) *max_channel = o.index;
+        }
+        else if (o.kind == TGPU_OPND_TEMP) {
+            if (o.index < 0 || o.index >= TGPU_MAX_TEMPS) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "operand temp %d out of range", o.index);
+        }
+        else if (o.kind < 0 || o.kind > TGPU_OPND_NULL) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "bad operand kind %d", o.kind);
+        return TGPU_OK;
+    };
+    for (int i = 0; i < p->num_insns; i++) {
+        const tgpu_expr_insn& s = p->insns[i];
+        DInsn& d = out->insns[i];
+        if (s.dst < 0 || s.dst >= TGPU_MAX_TEMPS) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "insn %d: dst temp out of range", i);
+        if (s.vtype < 0 || s.vtype > TGPU_V_BOOLEAN) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "insn %d: bad vtype", i);
+        switch (s.op) {
+            case TGPU_EX_MOV: case TGPU_EX_ADD: case TGPU_EX_SUB: case TGPU_EX_MUL: case TGPU_EX_DIV: case TGPU_EX_MOD: case TGPU_EX_NEG:
+            case TGPU_EX_EQ: case TGPU_EX_NE: case TGPU_EX_LT: case TGPU_EX_LE: case TGPU_EX_GT: case TGPU_EX_GE:
+            case TGPU_EX_AND: case TGPU_EX_OR: case TGPU_EX_NOT: case TGPU_EX_IS_NULL: case TGPU_EX_IS_NOT_NULL: case TGPU_EX_BETWEEN:
+            case TGPU_EX_CAST_BIGINT_TO_DOUBLE: case TGPU_EX_CAST_DOUBLE_TO_BIGINT:
+                break;
+            case TGPU_EX_IN:
+                if (s.b.imm.i64 < 0 || s.b.imm.i64 >= p->num_in_lists) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "insn %d: IN list index out of range", i);
+                break;
+            default:
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "insn %d: unsupported op %d", i, s.op);
+        }
+        d.op = s.op;
+        d.vtype = s.vtype;
+        d.dst = s.dst;
+        TG_TRY(conv(s.a, &d.a));
+        TG_TRY(conv(s.b, &d.b));
+        TG_TRY(conv(s.c, &d.c));
+        if (s.op == TGPU_EX_IN) d.b.kind = TGPU_OPND_CONST;
+    }
+    return TGPU_OK;
+}
+
+}  // namespace tg
+
+namespace {
+
+using namespace tg;
+
+constexpr int FP_THREADS = 256;
+
+// filter pass: one row per thread, writes 1/0 selection flags
+__global__ void __launch_bounds__(FP_THREADS) fp_filter_kernel(const DProgram* __restrict__ prog, DColumns cols, int64_t n, uint8_t* __restrict__ flags,
+                                                              unsigned int* __restrict__ err_out)
+{
+    __shared__ int64_t temps[TGPU_MAX_TEMPS * FP_THREADS];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t err = 0;
+    for (; i < n; i += stride) {
+        uint32_t nb = vm_run(prog, 0, prog->num_filter_insns, cols, i, temps + threadIdx.x, FP_THREADS, 0, &err);
+        int ft = prog->filter_temp;
+        bool sel = !((nb >> ft) & 1) && temps[ft * FP_THREADS + threadIdx.x] != 0;
+        flags[i] = sel ? 1 : 0;
+    }
+    if (err) atomicOr(err_out, err);
+}
+
+struct OutCols {
+    int32_t count;
+    int32_t temp[TGPU_MAX_CHANNELS];
+    int32_t vtype[TGPU_MAX_CHANNELS];
+    void* data[TGPU_MAX_CHANNELS];
+    uint8_t* nullmap[TGPU_MAX_CHANNELS];   // 1 byte per row, 1 = NULL
+};
+
+// projection pass: output row j <- input row sel[j] (sel == nullptr: identity)
+__global__ void __launch_bounds__(FP_THREADS) fp_project_kernel(const DProgram* __restrict__ prog, DColumns cols, const int32_t* __restrict__ sel, int64_t m,
+                                                               OutCols out, unsigned int* __restrict__ err_out, unsigned int* __restrict__ any_null)
+{
+    __shared__ int64_t temps[TGPU_MAX_TEMPS * FP_THREADS];
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint32_t err = 0, ignored = 0, nulls_seen = 0;
+    for (; j < m; j += stride) {
+        int64_t row = sel ? sel[j] : j;
+        int64_t* t = temps + threadIdx.x;
+        uint32_t nb = vm_run(prog, 0, prog->num_filter_insns, cols, row, t, FP_THREADS, 0, &ignored);
+        nb = vm_run(prog, prog->num_filter_insns, prog->num_insns, cols, row, t, FP_THREADS, nb, &err);
+        for (int c = 0; c < out.count; c++) {
+            int tp = out.temp[c];
+            bool isn = (nb >> tp) & 1;
+            int64_t v = isn ? 0 : t[tp * FP_THREADS];
+            if (out.vtype[c] == TGPU_V_BOOLEAN) ((int8_t*)out.data[c])[j] = (int8_t)v;
+            else ((int64_t*)out.data[c])[j] = v;
+            out.nullmap[c][j] = isn ? 1 : 0;
+            if (isn) nulls_seen |= 1u << c;
+        }
+    }
+    if (err) atomicOr(err_out, err);
+    if (nulls_seen) atomicOr(any_null, nulls_seen);
+}
+
+struct IotaIt {
+    __host__ __device__ int32_t operator[](int64_t i) const { return (int32_t)i; }
+};
+
+struct FilterProjectOp : tgpu_op {
+    DProgram host_prog;
+    DevBuf d_prog;
+    std::vector<tgpu_projection> projections;
+    int32_t max_channel = -1;
+    std::vector<OwnedPage*> pending;
+    size_t next_out = 0;
+    bool finishing = false;
+
+    explicit FilterProjectOp(tgpu_ctx* c) : tgpu_op(c) {}
+    ~FilterProjectOp() override { for (size_t i = next_out; i < pending.size(); i++) delete pending[i]; }
+
+    bool needs_input() override { return !finishing && next_out >= pending.size(); }
+
+    int add_input(const tgpu_page* page) override
+    {
+        pending.clear();
+        next_out = 0;
+        int64_t n = page->num_rows;
+        if (n == 0) return TGPU_OK;
+        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+        DevPage in;
+        TG_TRY(tg_ingest_page(ctx, page, &in));
+        if (max_channel >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "program reads channel %d, page has %zu", max_channel, in.cols.size());
+        DColumns cols;
+        memset(&cols, 0, sizeof(cols));
+        for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++) {
+            if ((int32_t)c <= max_channel && in.cols[c].type == TGPU_UTF8) {
+                // only pass-through is allowed for variable-width columns; computed operands were validated below
+            }
+            cols.cols[c] = tg_colref(in.cols[c]);
+        }
+        for (int i = 0; i < host_prog.num_insns; i++) {
+            const DOperand* ops[3] = {&host_prog.insns[i].a, &host_prog.insns[i].b, &host_prog.insns[i].c};
+            for (auto* o : ops)
+                if (o->kind == TGPU_OPND_COLUMN && in.cols[o->index].elem_size() == 0)
+                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "expressions over variable-width channel %d are not supported on the GPU path", o->index);
+        }
+        unsigned int* d_err = (unsigned int*)(ctx->d_scratch + 2);
+        unsigned int* d_anynull = d_err + 1;
+        TG_CUDA(ctx, cudaMemsetAsync(d_err, 0, 8, ctx->stream));
+        const DProgram* dp = d_prog.as<DProgram>();
+        int grid = tg_grid(ctx, n, FP_THREADS, 8);
+
+        int64_t m = n;
+        DevBuf sel;
+        const int32_t* d_sel = nullptr;
+        if (host_prog.filter_temp >= 0) {
+            DevBuf flags, tmp;
+            TG_TRY(flags.alloc(ctx, (size_t)n));
+            TG_TRY(sel.alloc(ctx, (size_t)n * 4));
+            TG_LAUNCH(ctx, fp_filter_kernel, grid, FP_THREADS, 0, dp, cols, n, flags.as<uint8_t>(), d_err);
+            long long* d_count = (long long*)(ctx->d_scratch + 4);
+            size_t tmp_bytes = 0;
+            cub::CountingInputIterator<int32_t> iota(0);
+            cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream);
+            TG_TRY(tmp.alloc(ctx, tmp_bytes));
+            TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream));
+            TG_TRY(tg_read_i64(ctx, d_count, &m));
+            int64_t errw = 0;
+            TG_TRY(tg_read_i64(ctx, d_err, &errw));
+            TG_TRY(raise(errw));
+            if (m == 0) return TGPU_OK;
+            if (m < n) d_sel = sel.as<int32_t>();
+        }
+
+        DevPage outp;
+        outp.rows = m;
+        outp.cols.resize(projections.size());
+        OutCols oc;
+        memset(&oc, 0, sizeof(oc));
+        std::vector<std::shared_ptr<DevBuf>> nullmaps;
+        std::vector<int> computed_at;
+        for (size_t pi = 0; pi < projections.size(); pi++) {
+            const tgpu_projection& pr = projections[pi];
+            if (pr.kind == 0) {
+                if (pr.index < 0 || pr.index >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "projection channel out of range");
+                if (!d_sel) outp.cols[pi] = in.cols[pr.index];       // InputPageProjection on all positions: the block itself
+                else TG_TRY(tg_gather_column(ctx, in.cols[pr.index], d_sel, m, false, &outp.cols[pi]));
+            }
+            else {
+                DevColumn& c = outp.cols[pi];
+                c.type = pr.vtype == TGPU_V_DOUBLE ? TGPU_FLOAT64 : pr.vtype == TGPU_V_BOOLEAN ? TGPU_INT8 : TGPU_INT64;
+                c.length = m;
+                c.own_data = std::make_shared<DevBuf>();
+                TG_TRY(c.own_data->alloc(ctx, (size_t)m * c.elem_size()));
+                c.data = c.own_data->p;
+                auto nm = std::make_shared<DevBuf>();
+                TG_TRY(nm->alloc(ctx, (size_t)m));
+                int k = oc.count++;
+                oc.temp[k] = pr.index;
+                oc.vtype[k] = pr.vtype;
+                oc.data[k] = c.own_data->p;
+                oc.nullmap[k] = nm->as<uint8_t>();
+                nullmaps.push_back(nm);
+                computed_at.push_back((int)pi);
+            }
+        }
+        if (oc.count > 0) {
+            int pgrid = tg_grid(ctx, m, FP_THREADS, 8);
+            TG_LAUNCH(ctx, fp_project_kernel, pgrid, FP_THREADS, 0, dp, cols, d_sel, m, oc, d_err, d_anynull);
+            int64_t word = 0;
+            TG_TRY(tg_read_i64(ctx, d_err, &word));
+            TG_TRY(raise(word & 0xFFFFFFFFLL));
+            uint32_t any_null = (uint32_t)((uint64_t)word >> 32);
+            for (int k = 0; k < oc.count; k++) {
+                if (!((any_null >> k) & 1)) continue;
+                DevColumn& c = outp.cols[computed_at[k]];
+                c.own_validity = std::make_shared<DevBuf>();
+                TG_TRY(c.own_validity->alloc(ctx, (size_t)((m + 7) / 8)));
+                TG_TRY(pack_nullmap(nullmaps[k]->as<uint8_t>(), m, c.own_validity->as<uint8_t>()));
+                c.validity = c.own_validity->as<uint8_t>();
+            }
+        }
+        pending.push_back(tg_make_owned_page(std::move(outp)));
+        return TGPU_OK;
+    }
+
+    int pack_nullmap(const uint8_t* nullmap, int64_t m, uint8_t* bitmap);
+
+    int raise(int64_t errbits)
+    {
+        if (errbits & TG_ERR_BIT_DIV_ZERO) return tg_fail(ctx, TGPU_ERR_DIVISION_BY_ZERO, "Division by zero");
+        if (errbits & TG_ERR_BIT_OVERFLOW) return tg_fail(ctx, TGPU_ERR_NUMERIC_VALUE_OUT_OF_RANGE, "bigint arithmetic overflow");
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override
+    {
+        *out = nullptr;
+        if (next_out < pending.size()) *out = pending[next_out++];
+        return TGPU_OK;
+    }
+    int finish() override { finishing = true; return TGPU_OK; }
+    bool is_finished() override { return finishing && next_out >= pending.size(); }
+};
+
+__global__ void fp_pack_nullmap_kernel(const uint8_t* __restrict__ is_null, int64_t n, uint8_t* __restrict__ bitmap)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nbytes = (n + 7) >> 3;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; b < nbytes; b += stride) {
+        uint32_t v = 0;
+        int64_t base = b << 3;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int64_t i = base + k;
+            if (i < n && is_null[i] == 0) v |= 1u << k;
+        }
+        bitmap[b] = (uint8_t)v;
+    }
+}
+
+int FilterProjectOp::pack_nullmap(const uint8_t* nullmap, int64_t m, uint8_t* bitmap)
+{
+    TG_LAUNCH(ctx, fp_pack_nullmap_kernel, tg_grid(ctx, (m + 7) / 8, 256, 8), 256, 0, nullmap, m, bitmap);
+    return TGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int tgpu_filter_project_create(tgpu_ctx* ctx, const tgpu_expr_program* program, tgpu_op** out)
+{
+    if (!ctx || !program || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::unique_ptr<FilterProjectOp> op(new FilterProjectOp(ctx));
+    TG_TRY(tg::expr_compile(ctx, program, &op->host_prog, &op->max_channel));
+    if (program->num_projections > TGPU_MAX_CHANNELS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than %d projections", TGPU_MAX_CHANNELS);
+    for (int i = 0; i < program->num_projections; i++) {
+        const tgpu_projection& p = program->projections[i];
+        if (p.kind == 1 && (p.index < 0 || p.index >= TGPU_MAX_TEMPS)) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "projection temp out of range");
+        op->projections.push_back(p);
+    }
+    TG_TRY(op->d_prog.alloc(ctx, sizeof(tg::DProgram)));
+    TG_CUDA(ctx, cudaMemcpyAsync(op->d_prog.p, &op->host_prog, sizeof(tg::DProgram), cudaMemcpyHostToDevice, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = op.release();
+    return TGPU_OK;
+}

@@ -1,0 +1,1392 @@
+// groupby.cu — HashAggregationOperator / GroupByHash / grouped accumulators for sm_100a.
+//
+// Reference semantics reproduced:
+//   - GroupByHash contract (M/operator/GroupByHash.java:118-125): group ids are dense, 0-based and assigned in
+//     first-appearance order over the whole input stream; a NULL key is an ordinary group
+//     (M/operator/BigintGroupByHash.java:193-200); DOUBLE keys group by IDENTICAL (NaN == NaN, -0 == +0,
+//     S/type/DoubleType.java:218-229) and the stored key is the first one seen.
+//   - accumulators (M/operator/aggregation/GroupedAggregator.java:77-117 + the @InputFunctions cited in
+//     include/trino_gpu.h): state[groupId] op= value, NULL inputs skipped, AggregationMask honoured.
+//   - output (InMemoryHashAggregationBuilder.buildResult :229-300): key columns then one column per aggregate
+//     (PARTIAL: the intermediate state columns), rows in group-id order.
+//   - HashAggregationOperator state machine (M/operator/HashAggregationOperator.java:346-498): accumulate until
+//     finish(); a PARTIAL step flushes when its memory exceeds max_partial_bytes (:351-353,478-483).
+//
+// Two device paths, chosen at run time:
+//   S (small)  : one pass, no group-id array in HBM.  Every CTA keeps a shared-memory key table of L slots and
+//                per-thread private accumulators [slot][acc][thread] (no atomics, no bank conflicts); a
+//                fixed-order in-CTA reduction and a single-CTA merge kernel fold the CTA partials into the
+//                operator state, ranking new groups by their first row so ids come out in first-seen order.
+//                The optional `pre` program (filter + projections) is evaluated in the same kernel, so
+//                projected columns never reach HBM (TPC-H Q1 shape).  Results are run-to-run deterministic.
+//   G (general): global open-addressing table {key, gid, first_row}; provisional inserts record the minimum
+//                row per new key, new groups are ranked with a prefix sum over "representative row" flags,
+//                then accumulators are updated with L2 atomics (RED.ADD.F64 / atomicAdd / atomicMin/Max).
+// Keys are packed exactly into one 64-bit word (single key of any fixed width, or several narrow keys with
+// one null bit each, <= 63 bits); other key shapes return NOT_SUPPORTED so the caller keeps the Java operator.
+#include <cub/cub.cuh>
+
+#include "expr.cuh"
+
+namespace {
+
+using namespace tg;
+
+constexpr unsigned long long EMPTY_KEY = 0x8000000000000000ULL;
+constexpr long long NO_ROW = 0x7FFFFFFFFFFFFFFFLL;
+constexpr int MAX_KEYS = 4;
+constexpr int MAX_SRCS = 16;
+constexpr int MAX_ACCS = 24;
+constexpr int S_THREADS = 256;
+constexpr int S_GMAX = 64;             // regular groups the S path can hold (+2 special)
+constexpr int S_SPECIAL_NULL = 0;      // special slot for the NULL key (single-key case)
+constexpr int S_SPECIAL_SENTINEL = 1;  // special slot for a key whose bits equal EMPTY_KEY
+
+enum AccKind {
+    ACC_ROWS = 0, ACC_NONNULL = 1, ACC_SUM_F64 = 2, ACC_SUM_I64_LO = 3, ACC_SUM_I64_HI = 4,
+    ACC_MIN_F64 = 5, ACC_MAX_F64 = 6, ACC_MIN_I64 = 7, ACC_MAX_I64 = 8, ACC_SUM_F64_FROM_I64 = 9
+};
+
+struct SrcRef {
+    int32_t is_temp;   // 0: channel of the input page, 1: VM temporary of the pre program
+    int32_t index;
+    int32_t vtype;     // temps only
+    int32_t pad;
+};
+
+struct AccDesc {
+    int32_t kind;
+    int32_t src;       // index into srcs, -1 for ACC_ROWS
+    int32_t mask;      // index into srcs of the BOOLEAN mask, or -1
+    int32_t pad;
+};
+
+struct AggPlan {
+    int32_t num_keys;
+    int32_t key_src[MAX_KEYS];
+    int32_t key_bits[MAX_KEYS];      // payload bits per key in the packed word (multi-key case)
+    int32_t key_is_double[MAX_KEYS];
+    int32_t num_srcs;
+    SrcRef srcs[MAX_SRCS];
+    int32_t num_accs;
+    AccDesc accs[MAX_ACCS];
+    int32_t has_pre;
+};
+
+// ---- order-preserving encodings so MIN/MAX are plain integer min/max ---------------------------------
+__host__ __device__ __forceinline__ unsigned long long f64_order_key(long long bits)
+{
+    unsigned long long u = (unsigned long long)bits;
+    if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;   // NaN sorts last
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__host__ __device__ __forceinline__ long long f64_from_order_key(unsigned long long k)
+{
+    return (long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
+}
+__host__ __device__ __forceinline__ unsigned long long i64_order_key(long long v) { return (unsigned long long)v ^ 0x8000000000000000ULL; }
+
+__host__ __device__ __forceinline__ unsigned long long acc_init(int kind)
+{
+    switch (kind) {
+        case ACC_MIN_F64: case ACC_MIN_I64: return 0xFFFFFFFFFFFFFFFFULL;
+        default: return 0;   // sums, counts, MAX over order keys
+    }
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long acc_combine(int kind, unsigned long long a, unsigned long long b)
+{
+    switch (kind) {
+        case ACC_SUM_F64: case ACC_SUM_F64_FROM_I64:
+            return (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b)));
+        case ACC_MIN_F64: case ACC_MIN_I64: return a < b ? a : b;
+        case ACC_MAX_F64: case ACC_MAX_I64: return a > b ? a : b;
+        default: return a + b;   // counts and the two halves of the 128-bit integer sum (carry handled by caller)
+    }
+}
+
+struct Fetched {
+    long long bits;
+    bool is_null;
+};
+
+__device__ __forceinline__ Fetched fetch_src(const SrcRef& s, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits)
+{
+    Fetched f;
+    if (s.is_temp) {
+        f.bits = temps[s.index * tstride];
+        f.is_null = (nullbits >> s.index) & 1;
+    }
+    else {
+        const ColRef& c = cols.cols[s.index];
+        f.is_null = !tg_valid(c.validity, row);
+        f.bits = tg_load_i64(c, row);
+    }
+    return f;
+}
+
+// canonical packed key of a row.  Returns the special-slot index (0 NULL key, 1 sentinel-valued key) or -1.
+__device__ __forceinline__ int pack_key(const AggPlan& plan, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits,
+                                        unsigned long long* out)
+{
+    if (plan.num_keys == 1) {
+        Fetched f = fetch_src(plan.srcs[plan.key_src[0]], cols, row, temps, tstride, nullbits);
+        if (f.is_null) return S_SPECIAL_NULL;
+        unsigned long long u = (unsigned long long)f.bits;
+        if (plan.key_is_double[0]) {
+            if ((u << 1) == 0) u = 0;
+            if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;
+        }
+        if (u == EMPTY_KEY) return S_SPECIAL_SENTINEL;
+        *out = u;
+        return -1;
+    }
+    unsigned long long pk = 0;
+    int shift = 0;
+    for (int k = 0; k < plan.num_keys; k++) {
+        Fetched f = fetch_src(plan.srcs[plan.key_src[k]], cols, row, temps, tstride, nullbits);
+        int bits = plan.key_bits[k];
+        unsigned long long field = f.is_null ? 1ULL : (((unsigned long long)f.bits & ((1ULL << bits) - 1)) << 1);
+        pk |= field << shift;
+        shift += bits + 1;
+    }
+    *out = pk;   // <= 63 bits used: can never equal EMPTY_KEY
+    return -1;
+}
+
+// one accumulator update of one row.  `p` points at the accumulator word(s); stride to the HI half is `hi_off`.
+__device__ __forceinline__ void acc_update_private(int kind, unsigned long long* p, long long hi_off, const Fetched& v)
+{
+    switch (kind) {
+        case ACC_ROWS: *p += 1; break;
+        case ACC_NONNULL: *p += 1; break;
+        case ACC_SUM_F64: *p = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), __longlong_as_double(v.bits))); break;
+        case ACC_SUM_F64_FROM_I64: *p = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), (double)v.bits)); break;
+        case ACC_SUM_I64_LO: {
+            unsigned long long old = *p, add = (unsigned long long)v.bits, nw = old + add;
+            *p = nw;
+            p[hi_off] += (unsigned long long)((v.bits < 0 ? -1LL : 0LL) + (nw < old ? 1LL : 0LL));
+            break;
+        }
+        case ACC_MIN_F64: { unsigned long long k = f64_order_key(v.bits); if (k < *p) *p = k; break; }
+        case ACC_MAX_F64: { unsigned long long k = f64_order_key(v.bits); if (k > *p) *p = k; break; }
+        case ACC_MIN_I64: { unsigned long long k = i64_order_key(v.bits); if (k < *p) *p = k; break; }
+        case ACC_MAX_I64: { unsigned long long k = i64_order_key(v.bits); if (k > *p) *p = k; break; }
+        default: break;
+    }
+}
+
+__device__ __forceinline__ bool mask_selected(const AggPlan& plan, int mask, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits)
+{
+    if (mask < 0) return true;
+    Fetched m = fetch_src(plan.srcs[mask], cols, row, temps, tstride, nullbits);
+    return !m.is_null && m.bits != 0;
+}
+
+// =====================================================================================================
+// path S
+// =====================================================================================================
+struct SmallOut {
+    unsigned long long* blk_keys;    // [grid][L]
+    long long* blk_first;            // [grid][L+2]
+    unsigned long long* blk_acc;     // [grid][L+2][A]
+    int* overflow;
+    unsigned int* err;
+};
+
+// dynamic shared memory layout:
+//   unsigned long long tkeys[L]; long long lfirst[L+2]; unsigned long long acc[(L+2)*A*T]; int64 temps[8*T] (pre only)
+__global__ void __launch_bounds__(S_THREADS) agg_small_kernel(AggPlan plan, DColumns cols, const DProgram* __restrict__ prog, int64_t n, int L,
+                                                             SmallOut out)
+{
+    extern __shared__ unsigned long long smem_u64[];
+    const int A = plan.num_accs;
+    const int T = S_THREADS;
+    unsigned long long* tkeys = smem_u64;
+    long long* lfirst = (long long*)(tkeys + L);
+    unsigned long long* acc = (unsigned long long*)(lfirst + L + 2);
+    int64_t* temps_base = (int64_t*)(acc + (size_t)(L + 2) * A * T);
+    int64_t* temps = temps_base + threadIdx.x;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < L; i += T) tkeys[i] = EMPTY_KEY;
+    for (int i = tid; i < L + 2; i += T) lfirst[i] = NO_ROW;
+    for (int s = 0; s < L + 2; s++)
+        for (int a = 0; a < A; a++) acc[((size_t)s * A + a) * T + tid] = acc_init(plan.accs[a].kind);
+    __shared__ int s_overflow;
+    if (tid == 0) s_overflow = 0;
+    __syncthreads();
+
+    unsigned long long seen = 0;
+    uint32_t err = 0, ignored = 0;
+    const long long hi_off = T;   // HI half is the next accumulator: ((s*A + a+1)*T + tid) - ((s*A + a)*T + tid)
+    int64_t stride = (int64_t)gridDim.x * T;
+    for (int64_t row = (int64_t)blockIdx.x * T + tid; row < n; row += stride) {
+        uint32_t nb = 0;
+        if (plan.has_pre) {
+            if (prog->filter_temp >= 0) {
+                nb = vm_run(prog, 0, prog->num_filter_insns, cols, row, temps, T, 0, &ignored);
+                err |= ignored;
+                int ft = prog->filter_temp;
+                bool sel = !((nb >> ft) & 1) && temps[ft * T] != 0;
+                if (!sel) continue;
+            }
+            nb = vm_run(prog, prog->num_filter_insns, prog->num_insns, cols, row, temps, T, nb, &err);
+        }
+        unsigned long long pk = 0;
+        int special = pack_key(plan, cols, row, temps, T, nb, &pk);
+        int slot;
+        if (special >= 0) slot = L + special;
+        else {
+            int h = (int)(murmur3_mix(pk) & (unsigned long long)(L - 1));
+            slot = -1;
+            for (int probe = 0; probe < L; probe++) {
+                unsigned long long cur = tkeys[h];
+                if (cur == EMPTY_KEY) cur = atomicCAS(&tkeys[h], EMPTY_KEY, pk);
+                if (cur == EMPTY_KEY || cur == pk) { slot = h; break; }
+                h = (h + 1) & (L - 1);
+            }
+            if (slot < 0) { s_overflow = 1; break; }   // more distinct keys in this CTA than L: host switches to path G
+        }
+        if (!((seen >> slot) & 1)) {
+            seen |= 1ULL << slot;
+            atomicMin(&lfirst[slot], (long long)row);   // rows of one thread ascend: its first hit is its minimum
+        }
+        int last_src = -2;
+        Fetched v;
+        v.bits = 0; v.is_null = false;
+        for (int a = 0; a < A; a++) {
+            const AccDesc& d = plan.accs[a];
+            if (d.kind == ACC_SUM_I64_HI) continue;
+            if (!mask_selected(plan, d.mask, cols, row, temps, T, nb)) continue;
+            if (d.src >= 0 && d.src != last_src) { v = fetch_src(plan.srcs[d.src], cols, row, temps, T, nb); last_src = d.src; }
+            if (d.kind != ACC_ROWS && v.is_null) continue;
+            acc_update_private(d.kind, &acc[((size_t)slot * A + a) * T + tid], hi_off, v);
+        }
+    }
+    if (err) atomicOr(out.err, err);
+    __syncthreads();
+    if (s_overflow) {
+        if (tid == 0) *out.overflow = 1;
+        return;
+    }
+
+    // fixed-order reduction of the T private copies of every (slot, acc): lane-sequential then xor tree
+    const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+    const size_t b = blockIdx.x;
+    for (int pair = warp; pair < (L + 2) * A; pair += nwarps) {
+        int s = pair / A, a = pair % A;
+        int kind = plan.accs[a].kind;
+        if (kind == ACC_SUM_I64_HI) continue;   // reduced together with its LO half
+        if (lfirst[s] == NO_ROW) continue;
+        const unsigned long long* p = &acc[((size_t)s * A + a) * T];
+        if (kind == ACC_SUM_I64_LO) {
+            const unsigned long long* ph = p + T;
+            unsigned long long lo = 0, hi = 0;
+            for (int t = lane; t < T; t += 32) { unsigned long long o = lo; lo += p[t]; hi += ph[t] + (lo < o ? 1 : 0); }
+            for (int off = 16; off > 0; off >>= 1) {
+                unsigned long long ol = __shfl_xor_sync(0xffffffffu, lo, off), oh = __shfl_xor_sync(0xffffffffu, hi, off);
+                unsigned long long o = lo; lo += ol; hi += oh + (lo < o ? 1 : 0);
+            }
+            if (lane == 0) {
+                out.blk_acc[(b * (L + 2) + s) * A + a] = lo;
+                out.blk_acc[(b * (L + 2) + s) * A + a + 1] = hi;
+            }
+        }
+        else {
+            unsigned long long r = acc_init(kind);
+            for (int t = lane; t < T; t += 32) r = acc_combine(kind, r, p[t]);
+            for (int off = 16; off > 0; off >>= 1) r = acc_combine(kind, r, __shfl_xor_sync(0xffffffffu, r, off));
+            if (lane == 0) out.blk_acc[(b * (L + 2) + s) * A + a] = r;
+        }
+    }
+    for (int s = tid; s < L + 2; s += T) {
+        out.blk_first[b * (L + 2) + s] = lfirst[s];
+        if (s < L) out.blk_keys[b * L + s] = tkeys[s];
+    }
+}
+
+// operator state shared by both paths (device resident)
+struct AggState {
+    int32_t* count;                   // [0] number of groups, [1] gid of NULL-key group or -1, [2] gid of sentinel-key group or -1
+    unsigned long long* keys;         // path S: canonical packed key per gid (cap entries)
+    unsigned long long* acc;          // [A][cap]
+    long long* keyvals;               // [num_keys][cap] raw first-seen key values
+    unsigned char* keynull;           // [num_keys][cap]
+    int64_t cap;
+};
+
+// single-CTA merge of the CTA partials of one page into the operator state (path S)
+__global__ void __launch_bounds__(256) agg_small_merge_kernel(AggPlan plan, DColumns cols, int B, int L, SmallOut part, AggState st, int* __restrict__ blk_ps)
+{
+    __shared__ unsigned long long pkeys[S_GMAX];
+    __shared__ long long pfirst[S_GMAX + 2];
+    __shared__ int pgid[S_GMAX + 2];       // gid of the page slot (existing or newly assigned)
+    __shared__ int pnew[S_GMAX + 2];
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int A = plan.num_accs;
+    for (int i = tid; i < S_GMAX; i += T) pkeys[i] = EMPTY_KEY;
+    for (int i = tid; i < S_GMAX + 2; i += T) { pfirst[i] = NO_ROW; pgid[i] = -1; pnew[i] = 0; }
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    // 1. distinct keys of the page with their minimum first row
+    const int entries = B * (L + 2);
+    for (int e = tid; e < entries; e += T) {
+        int b = e / (L + 2), s = e % (L + 2);
+        long long first = part.blk_first[(size_t)b * (L + 2) + s];
+        int ps = -1;
+        if (first != NO_ROW) {
+            if (s >= L) ps = S_GMAX + (s - L);
+            else {
+                unsigned long long key = part.blk_keys[(size_t)b * L + s];
+                int h = (int)(murmur3_mix(key) & (S_GMAX - 1));
+                for (int probe = 0; probe < S_GMAX; probe++) {
+                    unsigned long long cur = pkeys[h];
+                    if (cur == EMPTY_KEY) cur = atomicCAS(&pkeys[h], EMPTY_KEY, key);
+                    if (cur == EMPTY_KEY || cur == key) { ps = h; break; }
+                    h = (h + 1) & (S_GMAX - 1);
+                }
+                if (ps < 0) s_fail = 1;
+            }
+            if (ps >= 0) atomicMin(&pfirst[ps], first);
+        }
+        blk_ps[e] = ps;
+    }
+    __syncthreads();
+    if (s_fail) { if (tid == 0) *part.overflow = 1; return; }
+    // 2. match page slots against the state
+    const int count = st.count[0];
+    for (int ps = tid; ps < S_GMAX + 2; ps += T) {
+        if (pfirst[ps] == NO_ROW) continue;
+        int gid = -1;
+        if (ps >= S_GMAX) gid = st.count[1 + (ps - S_GMAX)];
+        else {
+            unsigned long long key = pkeys[ps];
+            for (int g = 0; g < count; g++)
+                if (st.keys[g] == key && g != st.count[1] && g != st.count[2]) { gid = g; break; }
+        }
+        pgid[ps] = gid;
+        pnew[ps] = gid < 0 ? 1 : 0;
+    }
+    __syncthreads();
+    // 3. new groups get ids in first-row order
+    int my_new = 0;
+    for (int ps = tid; ps < S_GMAX + 2; ps += T) my_new += pnew[ps];
+    __shared__ int s_total_new;
+    if (tid == 0) s_total_new = 0;
+    __syncthreads();
+    if (my_new) atomicAdd(&s_total_new, my_new);
+    __syncthreads();
+    const int total_new = s_total_new;
+    if ((int64_t)count + total_new > st.cap) { if (tid == 0) *part.overflow = 1; return; }
+    for (int ps = tid; ps < S_GMAX + 2; ps += T) {
+        if (!pnew[ps]) continue;
+        int rank = 0;
+        for (int q = 0; q < S_GMAX + 2; q++)
+            if (pnew[q] && pfirst[q] < pfirst[ps]) rank++;
+        int gid = count + rank;
+        pgid[ps] = gid;
+        long long row = pfirst[ps];
+        if (ps < S_GMAX) st.keys[gid] = pkeys[ps];
+        else { st.keys[gid] = EMPTY_KEY; st.count[1 + (ps - S_GMAX)] = gid; }
+        for (int k = 0; k < plan.num_keys; k++) {
+            const ColRef& c = cols.cols[plan.srcs[plan.key_src[k]].index];   // keys are pass-through channels
+            bool isn = !tg_valid(c.validity, row);
+            st.keyvals[(size_t)k * st.cap + gid] = isn ? 0 : tg_load_i64(c, row);
+            st.keynull[(size_t)k * st.cap + gid] = isn ? 1 : 0;
+        }
+        for (int a = 0; a < A; a++) st.acc[(size_t)a * st.cap + gid] = acc_init(plan.accs[a].kind);
+    }
+    __syncthreads();
+    // 4. fold CTA partials in CTA order (deterministic)
+    for (int pair = tid; pair < (S_GMAX + 2) * A; pair += T) {
+        int ps = pair / A, a = pair % A;
+        int kind = plan.accs[a].kind;
+        if (pfirst[ps] == NO_ROW || kind == ACC_SUM_I64_HI) continue;
+        int gid = pgid[ps];
+        unsigned long long r = st.acc[(size_t)a * st.cap + gid];
+        unsigned long long rh = kind == ACC_SUM_I64_LO ? st.acc[(size_t)(a + 1) * st.cap + gid] : 0;
+        for (int b = 0; b < B; b++) {
+            for (int s = 0; s < L + 2; s++) {
+                if (blk_ps[b * (L + 2) + s] != ps) continue;
+                size_t at = ((size_t)b * (L + 2) + s) * A + a;
+                if (kind == ACC_SUM_I64_LO) {
+                    unsigned long long o = r;
+                    r += part.blk_acc[at];
+                    rh += part.blk_acc[at + 1] + (r < o ? 1 : 0);
+                }
+                else r = acc_combine(kind, r, part.blk_acc[at]);
+            }
+        }
+        st.acc[(size_t)a * st.cap + gid] = r;
+        if (kind == ACC_SUM_I64_LO) st.acc[(size_t)(a + 1) * st.cap + gid] = rh;
+    }
+    __syncthreads();
+    if (tid == 0) st.count[0] = count + total_new;
+}
+
+// =====================================================================================================
+// path G
+// =====================================================================================================
+struct __align__(16) GSlot {
+    unsigned long long key;
+    int gid;        // -1 until the group is numbered
+    int first_row;  // minimum row of the current page that hit this provisional slot
+};
+
+struct GSpecial {
+    int gid[2];
+    int first_row[2];
+};
+
+__global__ void g_table_init_kernel(int4* table, int64_t slots)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int4 empty = make_int4(0, (int)0x80000000, -1, 0x7FFFFFFF);
+    for (; i < slots; i += stride) table[i] = empty;
+}
+
+// K1: find or provisionally insert the key of every row.  slot_of_row: slot index, or -2-special.
+// `budget` new slots may be claimed (reserve-then-claim keeps the load factor bounded); exceeding it sets *overflow.
+__global__ void __launch_bounds__(256) g_insert_kernel(AggPlan plan, DColumns cols, int64_t n, GSlot* __restrict__ table, unsigned long long mask,
+                                                      GSpecial* __restrict__ special, int* __restrict__ slot_of_row, int* __restrict__ tickets, int budget,
+                                                      int* __restrict__ overflow)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        unsigned long long pk = 0;
+        int sp = pack_key(plan, cols, row, nullptr, 0, 0, &pk);
+        if (sp >= 0) {
+            if (special->gid[sp] < 0) atomicMin(&special->first_row[sp], (int)row);
+            slot_of_row[row] = -2 - sp;
+            continue;
+        }
+        unsigned long long pos = murmur3_mix(pk) & mask;
+        bool have_ticket = false;
+        int found = -1;
+        while (true) {
+            unsigned long long cur = *((volatile unsigned long long*)&table[pos].key);
+            if (cur == EMPTY_KEY) {
+                if (!have_ticket) {
+                    if (atomicAdd(tickets, 1) >= budget) { *overflow = 1; break; }
+                    have_ticket = true;
+                }
+                cur = atomicCAS(&table[pos].key, EMPTY_KEY, pk);
+                if (cur == EMPTY_KEY) { found = (int)pos; have_ticket = false; break; }   // ticket consumed
+            }
+            if (cur == pk) { found = (int)pos; break; }
+            pos = (pos + 1) & mask;
+        }
+        if (have_ticket) atomicSub(tickets, 1);
+        slot_of_row[row] = found;   // -1 only on overflow (page is re-run after the table grows)
+        if (found >= 0 && *((volatile int*)&table[found].gid) < 0) atomicMin(&table[found].first_row, (int)row);
+    }
+}
+
+// K2: flag the representative (minimum) row of every group that is new in this page
+__global__ void g_flag_kernel(int64_t n, const GSlot* __restrict__ table, const GSpecial* __restrict__ special, const int* __restrict__ slot_of_row,
+                              unsigned char* __restrict__ flags)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        int s = slot_of_row[row];
+        bool rep;
+        if (s <= -2) { int sp = -2 - s; rep = special->gid[sp] < 0 && special->first_row[sp] == (int)row; }
+        else rep = table[s].gid < 0 && table[s].first_row == (int)row;
+        flags[row] = rep ? 1 : 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[n] = 0;
+}
+
+// K3: number the new groups (next_gid + rank of the representative row) and record their key values
+__global__ void g_assign_kernel(AggPlan plan, DColumns cols, int64_t n, GSlot* __restrict__ table, GSpecial* __restrict__ special,
+                                const int* __restrict__ slot_of_row, const unsigned char* __restrict__ flags, const int* __restrict__ rank, int next_gid, AggState st)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        if (!flags[row]) continue;
+        int gid = next_gid + rank[row];
+        int s = slot_of_row[row];
+        if (s <= -2) special->gid[-2 - s] = gid;
+        else table[s].gid = gid;
+        for (int k = 0; k < plan.num_keys; k++) {
+            const ColRef& c = cols.cols[plan.srcs[plan.key_src[k]].index];
+            bool isn = !tg_valid(c.validity, row);
+            st.keyvals[(size_t)k * st.cap + gid] = isn ? 0 : tg_load_i64(c, row);
+            st.keynull[(size_t)k * st.cap + gid] = isn ? 1 : 0;
+        }
+        for (int a = 0; a < plan.num_accs; a++) st.acc[(size_t)a * st.cap + gid] = acc_init(plan.accs[a].kind);
+    }
+}
+
+// K4: group id of every row
+__global__ void g_gid_kernel(int64_t n, const GSlot* __restrict__ table, const GSpecial* __restrict__ special, const int* __restrict__ slot_of_row,
+                             int* __restrict__ gids)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        int s = slot_of_row[row];
+        gids[row] = s <= -2 ? special->gid[-2 - s] : table[s].gid;
+    }
+}
+
+// accumulate with L2 atomics: state[acc][gid] op= value
+__global__ void __launch_bounds__(256) g_accumulate_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ gids, AggState st)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        int gid = gids[row];
+        int last_src = -2;
+        Fetched v;
+        v.bits = 0; v.is_null = false;
+        for (int a = 0; a < plan.num_accs; a++) {
+            const AccDesc& d = plan.accs[a];
+            if (d.kind == ACC_SUM_I64_HI) continue;
+            if (!mask_selected(plan, d.mask, cols, row, nullptr, 0, 0)) continue;
+            if (d.src >= 0 && d.src != last_src) { v = fetch_src(plan.srcs[d.src], cols, row, nullptr, 0, 0); last_src = d.src; }
+            if (d.kind != ACC_ROWS && v.is_null) continue;
+            unsigned long long* p = &st.acc[(size_t)a * st.cap + gid];
+            switch (d.kind) {
+                case ACC_ROWS: case ACC_NONNULL: atomicAdd(p, 1ULL); break;
+                case ACC_SUM_F64: atomicAdd((double*)p, __longlong_as_double(v.bits)); break;
+                case ACC_SUM_F64_FROM_I64: atomicAdd((double*)p, (double)v.bits); break;
+                case ACC_SUM_I64_LO: {
+                    unsigned long long add = (unsigned long long)v.bits;
+                    unsigned long long old = atomicAdd(p, add);
+                    long long carry = (v.bits < 0 ? -1LL : 0LL) + ((old + add) < old ? 1LL : 0LL);
+                    if (carry) atomicAdd(p + st.cap, (unsigned long long)carry);
+                    break;
+                }
+                case ACC_MIN_F64: atomicMin(p, f64_order_key(v.bits)); break;
+                case ACC_MAX_F64: atomicMax(p, f64_order_key(v.bits)); break;
+                case ACC_MIN_I64: atomicMin(p, i64_order_key(v.bits)); break;
+                case ACC_MAX_I64: atomicMax(p, i64_order_key(v.bits)); break;
+                default: break;
+            }
+        }
+    }
+}
+
+// re-insert numbered groups into a bigger table
+__global__ void g_rehash_kernel(const GSlot* __restrict__ old_table, int64_t old_slots, GSlot* __restrict__ table, unsigned long long mask)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < old_slots; i += stride) {
+        GSlot s = old_table[i];
+        if (s.key == EMPTY_KEY || s.gid < 0) continue;
+        unsigned long long pos = murmur3_mix(s.key) & mask;
+        while (atomicCAS(&table[pos].key, EMPTY_KEY, s.key) != EMPTY_KEY) pos = (pos + 1) & mask;
+        table[pos].gid = s.gid;
+    }
+}
+
+// forget provisional (unnumbered) claims of an aborted K1 run
+__global__ void g_reset_provisional_kernel(GSlot* __restrict__ table, int64_t slots, GSpecial* special)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < slots; i += stride)
+        if (table[i].gid < 0) table[i].first_row = 0x7FFFFFFF;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int sp = 0; sp < 2; sp++) if (special->gid[sp] < 0) special->first_row[sp] = 0x7FFFFFFF;
+    }
+}
+
+// S -> G migration: insert the S-path groups (ids already final) into the G table
+__global__ void g_migrate_kernel(AggState st, GSlot* __restrict__ table, unsigned long long mask, GSpecial* special)
+{
+    int count = st.count[0];
+    for (int g = threadIdx.x; g < count; g += blockDim.x) {
+        if (g == st.count[1]) { special->gid[0] = g; continue; }
+        if (g == st.count[2]) { special->gid[1] = g; continue; }
+        unsigned long long key = st.keys[g];
+        unsigned long long pos = murmur3_mix(key) & mask;
+        while (atomicCAS(&table[pos].key, EMPTY_KEY, key) != EMPTY_KEY) pos = (pos + 1) & mask;
+        table[pos].gid = g;
+    }
+}
+
+__global__ void relayout_state_kernel(const unsigned long long* __restrict__ old_acc, const long long* __restrict__ old_keyvals,
+                                      const unsigned char* __restrict__ old_keynull, int64_t old_cap, int64_t count, int A, int K, AggState st)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) {
+        for (int a = 0; a < A; a++) st.acc[(size_t)a * st.cap + i] = old_acc[(size_t)a * old_cap + i];
+        for (int k = 0; k < K; k++) {
+            st.keyvals[(size_t)k * st.cap + i] = old_keyvals[(size_t)k * old_cap + i];
+            st.keynull[(size_t)k * st.cap + i] = old_keynull[(size_t)k * old_cap + i];
+        }
+    }
+}
+
+// =====================================================================================================
+// output
+// =====================================================================================================
+struct OutSpec {
+    int32_t count;                   // output columns after the keys
+    int32_t kind[48];                // 0 int64 from acc a0; 1 f64 sum nullable by count a1; 2 avg = sum a0 / count a1; 3 i128 sum (a0 lo, a0+1 hi) nullable by a1;
+                                     // 4 min/max f64 decode nullable by a1; 5 min/max i64 decode nullable by a1; 6 f64 sum never null (avg partial sum)
+    int32_t a0[48], a1[48];
+    void* data[48];
+    unsigned char* nullmap[48];      // 1 = NULL
+};
+
+__global__ void agg_output_kernel(AggState st, int64_t count, OutSpec spec, unsigned int* __restrict__ err_out, unsigned int* __restrict__ any_null)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int nulls0 = 0, nulls1 = 0, err = 0;
+    for (; g < count; g += stride) {
+        for (int c = 0; c < spec.count; c++) {
+            unsigned long long x = st.acc[(size_t)spec.a0[c] * st.cap + g];
+            unsigned long long cnt = spec.a1[c] >= 0 ? st.acc[(size_t)spec.a1[c] * st.cap + g] : 1;
+            long long outv = 0;
+            bool isn = false;
+            switch (spec.kind[c]) {
+                case 0: outv = (long long)x; break;
+                case 1: isn = cnt == 0; outv = (long long)x; break;
+                case 2:
+                    isn = cnt == 0;
+                    if (!isn) outv = __double_as_longlong(__ddiv_rn(__longlong_as_double((long long)x), (double)(long long)cnt));
+                    break;
+                case 3: {
+                    isn = cnt == 0;
+                    long long hi = (long long)st.acc[(size_t)(spec.a0[c] + 1) * st.cap + g];
+                    long long lo = (long long)x;
+                    if (hi != (lo >> 63)) err |= TG_ERR_BIT_OVERFLOW;   // Math.addExact would have thrown
+                    outv = lo;
+                    break;
+                }
+                case 4: isn = cnt == 0; outv = f64_from_order_key(x); break;
+                case 5: isn = cnt == 0; outv = (long long)(x ^ 0x8000000000000000ULL); break;
+                default: outv = (long long)x; break;
+            }
+            ((long long*)spec.data[c])[g] = isn ? 0 : outv;
+            spec.nullmap[c][g] = isn ? 1 : 0;
+            if (isn) { if (c < 32) nulls0 |= 1u << c; else nulls1 |= 1u << (c - 32); }
+        }
+    }
+    if (err) atomicOr(err_out, err);
+    if (nulls0) atomicOr(any_null, nulls0);
+    if (nulls1) atomicOr(any_null + 1, nulls1);
+}
+
+// typed key column from the 64-bit first-seen key values
+__global__ void agg_key_output_kernel(const long long* __restrict__ keyvals, const unsigned char* __restrict__ keynull, int64_t count, int elem,
+                                      void* __restrict__ out, unsigned char* __restrict__ nullmap)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; g < count; g += stride) {
+        long long v = keyvals[g];
+        switch (elem) {
+            case 8: ((long long*)out)[g] = v; break;
+            case 4: ((int*)out)[g] = (int)v; break;
+            case 2: ((short*)out)[g] = (short)v; break;
+            default: ((signed char*)out)[g] = (signed char)v; break;
+        }
+        nullmap[g] = keynull[g];
+    }
+}
+
+__global__ void nullmap_pack_kernel(const unsigned char* __restrict__ is_null, int64_t n, unsigned char* __restrict__ bitmap, unsigned int* __restrict__ any)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nbytes = (n + 7) >> 3;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int seen = 0;
+    for (; b < nbytes; b += stride) {
+        unsigned int v = 0;
+        int64_t base = b << 3;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int64_t i = base + k;
+            if (i < n) { if (is_null[i] == 0) v |= 1u << k; else seen = 1; }
+        }
+        bitmap[b] = (unsigned char)v;
+    }
+    if (seen && any) atomicOr(any, 1u);
+}
+
+#endif  // __CUDACC__
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct AggFnPlan {
+    int function;
+    int in_elem_is_double;
+    int acc_main = -1, acc_count = -1;   // indices into plan.accs
+};
+
+struct AggOp : tgpu_op {
+    // spec
+    std::vector<int32_t> key_channels;       // channels of the (projected) input
+    std::vector<tgpu_agg_fn> fns;
+    int step = TGPU_STEP_SINGLE;
+    int64_t expected_groups = 0, max_partial_bytes = 0;
+    bool has_pre = false;
+    DProgram host_prog;
+    DevBuf d_prog;
+    std::vector<tgpu_projection> projections;
+    int32_t prog_max_channel = -1;
+    bool gids_only = false;                  // tgpu_groupby_hash_* handle
+
+    // resolved at the first page (needs column types)
+    bool planned = false;
+    AggPlan plan;
+    std::vector<int> key_types;
+    std::vector<AggFnPlan> fnplans;
+    std::vector<int> fn_input_types;         // tgpu_type of each aggregate's input (first state column for FINAL)
+
+    // state
+    bool use_general = false;
+    DevBuf st_count, st_keys, st_acc, st_keyvals, st_keynull;
+    int64_t st_cap = 0;
+    int64_t group_count = 0;
+    // path S scratch
+    int s_L = 0, s_grid = 0;
+    size_t s_smem = 0;
+    DevBuf blk_keys, blk_first, blk_acc, blk_ps;
+    // path G
+    DevBuf g_table, g_special;
+    int64_t g_slots = 0;
+
+    bool finishing = false, finished = false, flushing = false;
+    std::vector<OwnedPage*> pending;
+    size_t next_out = 0;
+
+    explicit AggOp(tgpu_ctx* c) : tgpu_op(c) {}
+    ~AggOp() override { for (size_t i = next_out; i < pending.size(); i++) delete pending[i]; }
+
+    AggState state() const
+    {
+        AggState s;
+        s.count = st_count.as<int32_t>();
+        s.keys = st_keys.as<unsigned long long>();
+        s.acc = st_acc.as<unsigned long long>();
+        s.keyvals = st_keyvals.as<long long>();
+        s.keynull = st_keynull.as<unsigned char>();
+        s.cap = st_cap;
+        return s;
+    }
+
+    int add_src(int is_temp, int index, int vtype)
+    {
+        for (int i = 0; i < plan.num_srcs; i++)
+            if (plan.srcs[i].is_temp == is_temp && plan.srcs[i].index == index) return i;
+        if (plan.num_srcs >= MAX_SRCS) return -1;
+        plan.srcs[plan.num_srcs] = SrcRef{is_temp, index, vtype, 0};
+        return plan.num_srcs++;
+    }
+
+    // value source of a channel of the aggregation input (a projection output when `pre` is set)
+    int src_of_channel(int ch, int* type_out, const DevPage& in)
+    {
+        if (!has_pre) {
+            if (ch < 0 || ch >= (int)in.cols.size()) return -1;
+            *type_out = in.cols[ch].type;
+            return add_src(0, ch, 0);
+        }
+        if (ch < 0 || ch >= (int)projections.size()) return -1;
+        const tgpu_projection& p = projections[ch];
+        if (p.kind == 0) {
+            if (p.index < 0 || p.index >= (int)in.cols.size()) return -1;
+            *type_out = in.cols[p.index].type;
+            return add_src(0, p.index, 0);
+        }
+        *type_out = p.vtype == TGPU_V_DOUBLE ? TGPU_FLOAT64 : p.vtype == TGPU_V_BOOLEAN ? TGPU_INT8 : TGPU_INT64;
+        return add_src(1, p.index, p.vtype);
+    }
+
+    int add_acc(int kind, int src, int mask)
+    {
+        for (int i = 0; i < plan.num_accs; i++)
+            if (plan.accs[i].kind == kind && plan.accs[i].src == src && plan.accs[i].mask == mask) return i;
+        int need = kind == ACC_SUM_I64_LO ? 2 : 1;
+        if (plan.num_accs + need > MAX_ACCS) return -1;
+        int at = plan.num_accs;
+        plan.accs[at] = AccDesc{kind, src, mask, 0};
+        if (need == 2) plan.accs[at + 1] = AccDesc{ACC_SUM_I64_HI, src, mask, 0};
+        plan.num_accs += need;
+        return at;
+    }
+
+    int make_plan(const DevPage& in)
+    {
+        memset(&plan, 0, sizeof(plan));
+        plan.has_pre = has_pre ? 1 : 0;
+        int nk = (int)key_channels.size();
+        if (nk < 1) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "global aggregation (no GROUP BY keys) stays on the Java AggregationOperator");
+        if (nk > MAX_KEYS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than %d group-by keys", MAX_KEYS);
+        plan.num_keys = nk;
+        int total_bits = 0;
+        key_types.clear();
+        for (int k = 0; k < nk; k++) {
+            int type = 0;
+            int s = src_of_channel(key_channels[k], &type, in);
+            if (s < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d out of range", key_channels[k]);
+            if (plan.srcs[s].is_temp) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "group-by keys must be pass-through channels of the fused pre-stage");
+            int bits = type == TGPU_INT64 || type == TGPU_FLOAT64 ? 64 : type == TGPU_INT32 ? 32 : type == TGPU_INT16 ? 16 : type == TGPU_INT8 ? 8 : 0;
+            if (!bits) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width group-by keys are not supported on the GPU path (pass dictionary codes)");
+            plan.key_src[k] = s;
+            plan.key_bits[k] = bits;
+            plan.key_is_double[k] = type == TGPU_FLOAT64;
+            key_types.push_back(type);
+            total_bits += bits + 1;
+        }
+        if (nk > 1 && total_bits > 63)
+            return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "group-by keys need %d bits; the GPU path packs keys into 63 bits", total_bits);
+        fnplans.clear();
+        fn_input_types.clear();
+        bool from_state = step == TGPU_STEP_FINAL || step == TGPU_STEP_INTERMEDIATE;
+        for (auto& f : fns) {
+            AggFnPlan fp;
+            fp.function = f.function;
+            int mask = -1;
+            if (f.mask_channel >= 0) {
+                int mt = 0;
+                mask = src_of_channel(f.mask_channel, &mt, in);
+                if (mask < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "mask channel out of range");
+            }
+            int type = TGPU_INT64, src = -1, src2 = -1, type2 = 0;
+            if (f.function != TGPU_AGG_COUNT_STAR || from_state) {
+                src = src_of_channel(f.input_channel, &type, in);
+                if (src < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "aggregate input channel %d out of range", f.input_channel);
+                if (type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregates over variable-width inputs are not supported");
+            }
+            bool dbl = type == TGPU_FLOAT64;
+            fp.in_elem_is_double = dbl;
+            fn_input_types.push_back(type);
+            if (!from_state) {
+                switch (f.function) {
+                    case TGPU_AGG_COUNT_STAR: fp.acc_main = add_acc(ACC_ROWS, -1, mask); break;
+                    case TGPU_AGG_COUNT: fp.acc_main = add_acc(ACC_NONNULL, src, mask); break;
+                    case TGPU_AGG_SUM:
+                        fp.acc_main = add_acc(dbl ? ACC_SUM_F64 : ACC_SUM_I64_LO, src, mask);
+                        fp.acc_count = add_acc(ACC_NONNULL, src, mask);
+                        break;
+                    case TGPU_AGG_AVG:
+                        fp.acc_main = add_acc(dbl ? ACC_SUM_F64 : ACC_SUM_F64_FROM_I64, src, mask);
+                        fp.acc_count = add_acc(ACC_NONNULL, src, mask);
+                        break;
+                    case TGPU_AGG_MIN: case TGPU_AGG_MAX:
+                        fp.acc_main = add_acc(f.function == TGPU_AGG_MIN ? (dbl ? ACC_MIN_F64 : ACC_MIN_I64) : (dbl ? ACC_MAX_F64 : ACC_MAX_I64), src, mask);
+                        fp.acc_count = add_acc(ACC_NONNULL, src, mask);
+                        break;
+                    default: return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d", f.function);
+                }
+            }
+            else {
+                // combine functions over the intermediate state columns (layout in include/trino_gpu.h)
+                switch (f.function) {
+                    case TGPU_AGG_COUNT_STAR: case TGPU_AGG_COUNT: fp.acc_main = add_acc(ACC_SUM_I64_LO, src, -1); break;
+                    case TGPU_AGG_SUM:
+                        fp.acc_main = add_acc(dbl ? ACC_SUM_F64 : ACC_SUM_I64_LO, src, -1);
+                        fp.acc_count = add_acc(ACC_NONNULL, src, -1);
+                        break;
+                    case TGPU_AGG_AVG:
+                        src2 = src_of_channel(f.input_channel + 1, &type2, in);
+                        if (src2 < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "avg state needs two channels");
+                        fp.acc_count = add_acc(ACC_SUM_I64_LO, src, -1);
+                        fp.acc_main = add_acc(ACC_SUM_F64, src2, -1);
+                        break;
+                    case TGPU_AGG_MIN: case TGPU_AGG_MAX:
+                        fp.acc_main = add_acc(f.function == TGPU_AGG_MIN ? (dbl ? ACC_MIN_F64 : ACC_MIN_I64) : (dbl ? ACC_MAX_F64 : ACC_MAX_I64), src, -1);
+                        fp.acc_count = add_acc(ACC_NONNULL, src, -1);
+                        break;
+                    default: return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d", f.function);
+                }
+            }
+            if (fp.acc_main < 0 || (fp.acc_count == -1 && false)) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
+            fnplans.push_back(fp);
+        }
+        if (plan.num_srcs >= MAX_SRCS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many distinct aggregate inputs");
+        // accumulators sorted by source so the kernels fetch every source once per row
+        // (indices are referenced by fnplans: keep positions, the kernels only cache the last source)
+        planned = true;
+        return TGPU_OK;
+    }
+
+    int alloc_state(int64_t cap)
+    {
+        int A = plan.num_accs > 0 ? plan.num_accs : 1, K = plan.num_keys;
+        DevBuf n_keys, n_acc, n_kv, n_kn;
+        TG_TRY(n_keys.alloc(ctx, (size_t)cap * 8));
+        TG_TRY(n_acc.alloc(ctx, (size_t)cap * 8 * A));
+        TG_TRY(n_kv.alloc(ctx, (size_t)cap * 8 * K));
+        TG_TRY(n_kn.alloc(ctx, (size_t)cap * K));
+        if (st_cap > 0 && group_count > 0) {
+            AggState ns;
+            ns.count = st_count.as<int32_t>();
+            ns.keys = n_keys.as<unsigned long long>();
+            ns.acc = n_acc.as<unsigned long long>();
+            ns.keyvals = n_kv.as<long long>();
+            ns.keynull = n_kn.as<unsigned char>();
+            ns.cap = cap;
+            TG_CUDA(ctx, cudaMemcpyAsync(ns.keys, st_keys.p, (size_t)std::min(cap, st_cap) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            TG_LAUNCH(ctx, relayout_state_kernel, tg_grid(ctx, group_count, 256, 8), 256, 0, st_acc.as<unsigned long long>(), st_keyvals.as<long long>(),
+                      st_keynull.as<unsigned char>(), st_cap, group_count, plan.num_accs, K, ns);
+        }
+        st_keys = std::move(n_keys);
+        st_acc = std::move(n_acc);
+        st_keyvals = std::move(n_kv);
+        st_keynull = std::move(n_kn);
+        st_cap = cap;
+        return TGPU_OK;
+    }
+
+    int init_state()
+    {
+        TG_TRY(st_count.alloc(ctx, 64));
+        int32_t init[4] = {0, -1, -1, 0};
+        TG_CUDA(ctx, cudaMemcpyAsync(st_count.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        group_count = 0;
+        st_cap = 0;
+        TG_TRY(alloc_state(S_GMAX + 2));
+        use_general = gids_only;
+        // path S configuration: the largest power-of-two L whose private accumulators fit with 2 CTAs/SM,
+        // else 1 CTA/SM; L < 4 -> go straight to path G
+        int A = plan.num_accs > 0 ? plan.num_accs : 1;
+        size_t per_slot = (size_t)A * S_THREADS * 8;
+        size_t fixed = (size_t)(has_pre ? TGPU_MAX_TEMPS * S_THREADS * 8 : 0) + 1024;
+        size_t budget2 = (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) / 2 - 2048;
+        size_t budget1 = (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) - 2048;
+        s_L = 0;
+        for (int L = 32; L >= 4; L >>= 1) {
+            size_t need = fixed + (size_t)(L + 2) * per_slot + (size_t)L * 8 + (size_t)(L + 2) * 8;
+            if (need <= budget2 || (L <= 8 && need <= budget1)) { s_L = L; s_smem = need; break; }
+        }
+        if (s_L == 0) use_general = true;
+        if (expected_groups > S_GMAX * 4) use_general = true;   // planner expects many groups: skip the S attempt
+        return TGPU_OK;
+    }
+
+    // ---- path S -----------------------------------------------------------------------------------
+    int run_small(const DevPage& in, const DColumns& cols, bool* overflowed)
+    {
+        int64_t n = in.rows;
+        int L = s_L, A = plan.num_accs;
+        int ctas_per_sm = s_smem <= ((ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) / 2 - 2048) ? 2 : 1;
+        int grid = tg_grid(ctx, n, S_THREADS * 4, ctas_per_sm);
+        if (grid != s_grid) {
+            TG_TRY(blk_keys.alloc(ctx, (size_t)grid * L * 8));
+            TG_TRY(blk_first.alloc(ctx, (size_t)grid * (L + 2) * 8));
+            TG_TRY(blk_acc.alloc(ctx, (size_t)grid * (L + 2) * (A > 0 ? A : 1) * 8));
+            TG_TRY(blk_ps.alloc(ctx, (size_t)grid * (L + 2) * 4));
+            s_grid = grid;
+        }
+        int* d_overflow = (int*)(ctx->d_scratch + 6);
+        unsigned int* d_err = (unsigned int*)(ctx->d_scratch + 6) + 1;
+        TG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 8, ctx->stream));
+        SmallOut so;
+        so.blk_keys = blk_keys.as<unsigned long long>();
+        so.blk_first = blk_first.as<long long>();
+        so.blk_acc = blk_acc.as<unsigned long long>();
+        so.overflow = d_overflow;
+        so.err = d_err;
+        static bool attr_set = false;
+        if (!attr_set || true) {
+            TG_CUDA(ctx, cudaFuncSetAttribute(agg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
+            attr_set = true;
+        }
+        TG_LAUNCH(ctx, agg_small_kernel, grid, S_THREADS, s_smem, plan, cols, has_pre ? d_prog.as<DProgram>() : nullptr, n, L, so);
+        TG_LAUNCH(ctx, agg_small_merge_kernel, 1, 256, 0, plan, cols, grid, L, so, state(), blk_ps.as<int>());
+        // one small readback per page: overflow flag + error bits, then the group count
+        int64_t word = 0;
+        TG_TRY(tg_read_i64(ctx, d_overflow, &word));
+        if ((uint32_t)(word >> 32)) TG_TRY(raise((uint32_t)(word >> 32)));
+        *overflowed = (word & 0xFFFFFFFFLL) != 0;
+        if (!*overflowed) {
+            int64_t cnt = 0;
+            TG_TRY(tg_read_i64(ctx, st_count.p, &cnt));
+            group_count = (int32_t)(cnt & 0xFFFFFFFFLL);
+        }
+        return TGPU_OK;
+    }
+
+    int raise(uint32_t errbits)
+    {
+        if (errbits & TG_ERR_BIT_DIV_ZERO) return tg_fail(ctx, TGPU_ERR_DIVISION_BY_ZERO, "Division by zero");
+        if (errbits & TG_ERR_BIT_OVERFLOW) return tg_fail(ctx, TGPU_ERR_NUMERIC_VALUE_OUT_OF_RANGE, "bigint arithmetic overflow");
+        return TGPU_OK;
+    }
+
+    // ---- path G -----------------------------------------------------------------------------------
+    int g_alloc_table(int64_t slots)
+    {
+        DevBuf nt;
+        TG_TRY(nt.alloc(ctx, (size_t)slots * sizeof(GSlot)));
+        TG_LAUNCH(ctx, g_table_init_kernel, tg_grid(ctx, slots, 1024, 8), 256, 0, nt.as<int4>(), slots);
+        if (g_slots > 0)
+            TG_LAUNCH(ctx, g_rehash_kernel, tg_grid(ctx, g_slots, 1024, 8), 256, 0, g_table.as<GSlot>(), g_slots, nt.as<GSlot>(), (unsigned long long)slots - 1);
+        g_table = std::move(nt);
+        g_slots = slots;
+        return TGPU_OK;
+    }
+
+    int switch_to_general()
+    {
+        use_general = true;
+        TG_TRY(g_special.alloc(ctx, sizeof(GSpecial)));
+        GSpecial init;
+        init.gid[0] = init.gid[1] = -1;
+        init.first_row[0] = init.first_row[1] = 0x7FFFFFFF;
+        TG_CUDA(ctx, cudaMemcpyAsync(g_special.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int64_t want = expected_groups > 0 ? expected_groups : 1024;
+        int64_t slots = 1 << 16;
+        while (slots * 3 / 4 < want + group_count) slots <<= 1;    // arraySize(expected, 0.75)
+        if (slots > (1LL << 30)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+        g_slots = 0;
+        TG_TRY(g_alloc_table(slots));
+        if (group_count > 0)
+            TG_LAUNCH(ctx, g_migrate_kernel, 1, 256, 0, state(), g_table.as<GSlot>(), (unsigned long long)g_slots - 1, g_special.as<GSpecial>());
+        return TGPU_OK;
+    }
+
+    // assigns group ids for the page into d_gids (int32[n]); updates group_count
+    int run_general_ids(const DevPage& in, const DColumns& cols, int* d_gids)
+    {
+        int64_t n = in.rows;
+        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+        DevBuf slot_of_row, flags, rank, tmp;
+        TG_TRY(slot_of_row.alloc(ctx, (size_t)n * 4));
+        TG_TRY(flags.alloc(ctx, (size_t)n + 1));
+        TG_TRY(rank.alloc(ctx, (size_t)(n + 1) * 4));
+        int* d_tickets = (int*)(ctx->d_scratch + 8);
+        int* d_overflow = d_tickets + 1;
+        int grid = tg_grid(ctx, n, 256, 8);
+        while (true) {
+            int64_t max_fill = g_slots * 3 / 4;
+            int64_t budget = max_fill - group_count;
+            TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 8, ctx->stream));
+            TG_LAUNCH(ctx, g_insert_kernel, grid, 256, 0, plan, cols, n, g_table.as<GSlot>(), (unsigned long long)g_slots - 1, g_special.as<GSpecial>(),
+                      slot_of_row.as<int>(), d_tickets, (int)std::min<int64_t>(budget, INT32_MAX), d_overflow);
+            int64_t word = 0;
+            TG_TRY(tg_read_i64(ctx, d_tickets, &word));
+            bool overflow = (word >> 32) != 0;
+            if (!overflow) break;
+            // BigintGroupByHash.tryRehash :239-290: double (here: x4) and retry the page
+            int64_t slots = g_slots * 4;
+            if (slots > (1LL << 30)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+            TG_TRY(g_alloc_table(slots));
+            TG_LAUNCH(ctx, g_reset_provisional_kernel, 1, 32, 0, g_table.as<GSlot>(), (int64_t)0, g_special.as<GSpecial>());
+        }
+        TG_LAUNCH(ctx, g_flag_kernel, grid, 256, 0, n, g_table.as<GSlot>(), g_special.as<GSpecial>(), slot_of_row.as<int>(), flags.as<unsigned char>());
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags.as<unsigned char>(), rank.as<int>(), n + 1, ctx->stream);
+        TG_TRY(tmp.alloc(ctx, tmp_bytes));
+        TG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, flags.as<unsigned char>(), rank.as<int>(), n + 1, ctx->stream));
+        TG_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, rank.as<int>() + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int32_t total_new = *(int32_t*)ctx->h_scratch;
+        if (group_count + total_new > st_cap) {
+            int64_t cap = st_cap;
+            while (cap < group_count + total_new) cap *= 2;
+            TG_TRY(alloc_state(cap));
+        }
+        if (total_new > 0)
+            TG_LAUNCH(ctx, g_assign_kernel, grid, 256, 0, plan, cols, n, g_table.as<GSlot>(), g_special.as<GSpecial>(), slot_of_row.as<int>(),
+                      flags.as<unsigned char>(), rank.as<int>(), (int)group_count, state());
+        TG_LAUNCH(ctx, g_gid_kernel, grid, 256, 0, n, g_table.as<GSlot>(), g_special.as<GSpecial>(), slot_of_row.as<int>(), d_gids);
+        group_count += total_new;
+        return TGPU_OK;
+    }
+
+    int run_general(const DevPage& in, const DColumns& cols)
+    {
+        DevBuf gids;
+        TG_TRY(gids.alloc(ctx, (size_t)in.rows * 4));
+        TG_TRY(run_general_ids(in, cols, gids.as<int>()));
+        if (plan.num_accs > 0)
+            TG_LAUNCH(ctx, g_accumulate_kernel, tg_grid(ctx, in.rows, 256, 8), 256, 0, plan, cols, in.rows, gids.as<int>(), state());
+        return TGPU_OK;
+    }
+
+    // ---- Operator protocol --------------------------------------------------------------------------
+    bool needs_input() override { return !finishing && !flushing && next_out >= pending.size(); }
+
+    int fill_cols(const DevPage& in, DColumns* cols)
+    {
+        memset(cols, 0, sizeof(*cols));
+        if (in.cols.size() > TGPU_MAX_CHANNELS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than %d channels", TGPU_MAX_CHANNELS);
+        for (size_t c = 0; c < in.cols.size(); c++) cols->cols[c] = tg_colref(in.cols[c]);
+        return TGPU_OK;
+    }
+
+    int add_input(const tgpu_page* page) override
+    {
+        if (page->num_rows == 0) return TGPU_OK;
+        DevPage in;
+        TG_TRY(tg_ingest_page(ctx, page, &in));
+        return add_device_page(in);
+    }
+
+    int add_device_page(const DevPage& in)
+    {
+        if (!planned) {
+            TG_TRY(make_plan(in));
+            TG_TRY(init_state());
+            if (use_general) TG_TRY(switch_to_general());
+        }
+        if (has_pre && prog_max_channel >= (int)in.cols.size())
+            return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "pre-stage reads channel %d, page has %zu", prog_max_channel, in.cols.size());
+        DColumns cols;
+        TG_TRY(fill_cols(in, &cols));
+        if (!use_general) {
+            bool overflowed = false;
+            TG_TRY(run_small(in, cols, &overflowed));
+            if (!overflowed) return after_page();
+            TG_TRY(switch_to_general());
+        }
+        if (has_pre) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "fused pre-stage with more than %d groups: run FilterAndProject as its own operator", S_GMAX);
+        TG_TRY(run_general(in, cols));
+        return after_page();
+    }
+
+    int after_page()
+    {
+        // InMemoryHashAggregationBuilder.updateIsFull :193-200 -> HashAggregationOperator.needsInput :346-355
+        if (step == TGPU_STEP_PARTIAL && max_partial_bytes > 0 && memory_bytes() > max_partial_bytes) flushing = true;
+        return TGPU_OK;
+    }
+
+    int64_t memory_bytes() override
+    {
+        int64_t A = plan.num_accs > 0 ? plan.num_accs : 1;
+        int64_t b = group_count * (8 + 8 * A + 9 * (int64_t)plan.num_keys);
+        if (use_general) b += (int64_t)g_table.bytes;
+        return planned ? b : 0;
+    }
+
+    int build_output(OwnedPage** out)
+    {
+        *out = nullptr;
+        if (!planned || group_count == 0) return TGPU_OK;
+        int64_t G = group_count;
+        DevPage outp;
+        outp.rows = G;
+        unsigned int* d_err = (unsigned int*)(ctx->d_scratch + 10);
+        unsigned int* d_any = d_err + 2;    // two words of per-column null flags
+        TG_CUDA(ctx, cudaMemsetAsync(d_err, 0, 16, ctx->stream));
+        int grid = tg_grid(ctx, G, 256, 8);
+        std::vector<std::shared_ptr<DevBuf>> nullmaps;
+        // key columns
+        for (int k = 0; k < plan.num_keys; k++) {
+            DevColumn c;
+            c.type = key_types[k];
+            c.length = G;
+            c.own_data = std::make_shared<DevBuf>();
+            TG_TRY(c.own_data->alloc(ctx, (size_t)G * c.elem_size()));
+            c.data = c.own_data->p;
+            auto nm = std::make_shared<DevBuf>();
+            TG_TRY(nm->alloc(ctx, (size_t)G));
+            TG_LAUNCH(ctx, agg_key_output_kernel, grid, 256, 0, st_keyvals.as<long long>() + (size_t)k * st_cap, st_keynull.as<unsigned char>() + (size_t)k * st_cap,
+                      G, c.elem_size(), c.own_data->p, nm->as<unsigned char>());
+            nullmaps.push_back(nm);
+            outp.cols.push_back(std::move(c));
+        }
+        // aggregate columns
+        OutSpec spec;
+        memset(&spec, 0, sizeof(spec));
+        bool partial_out = step == TGPU_STEP_PARTIAL || step == TGPU_STEP_INTERMEDIATE;
+        bool from_state = step == TGPU_STEP_FINAL || step == TGPU_STEP_INTERMEDIATE;
+        auto add_col = [&](int type, int kind, int a0, int a1) -> int {
+            if (spec.count >= 48) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many output columns");
+            DevColumn c;
+            c.type = type;
+            c.length = G;
+            c.own_data = std::make_shared<DevBuf>();
+            TG_TRY(c.own_data->alloc(ctx, (size_t)G * 8));
+            c.data = c.own_data->p;
+            auto nm = std::make_shared<DevBuf>();
+            TG_TRY(nm->alloc(ctx, (size_t)G));
+            int k = spec.count++;
+            spec.kind[k] = kind;
+            spec.a0[k] = a0;
+            spec.a1[k] = a1;
+            spec.data[k] = c.own_data->p;
+            spec.nullmap[k] = nm->as<unsigned char>();
+            nullmaps.push_back(nm);
+            outp.cols.push_back(std::move(c));
+            return TGPU_OK;
+        };
+        for (size_t i = 0; i < fns.size(); i++) {
+            const AggFnPlan& fp = fnplans[i];
+            bool dbl = fp.in_elem_is_double;
+            bool count_is_i128 = from_state;   // counts combined from state columns are 128-bit sums
+            switch (fp.function) {
+                case TGPU_AGG_COUNT_STAR: case TGPU_AGG_COUNT:
+                    TG_TRY(add_col(TGPU_INT64, count_is_i128 ? 3 : 0, fp.acc_main, -1));
+                    break;
+                case TGPU_AGG_SUM:
+                    TG_TRY(add_col(dbl ? TGPU_FLOAT64 : TGPU_INT64, dbl ? 1 : 3, fp.acc_main, fp.acc_count));
+                    break;
+                case TGPU_AGG_AVG:
+                    if (partial_out) {
+                        TG_TRY(add_col(TGPU_INT64, count_is_i128 ? 3 : 0, fp.acc_count, -1));
+                        TG_TRY(add_col(TGPU_FLOAT64, 6, fp.acc_main, -1));
+                    }
+                    else TG_TRY(add_col(TGPU_FLOAT64, 2, fp.acc_main, fp.acc_count));
+                    break;
+                case TGPU_AGG_MIN: case TGPU_AGG_MAX:
+                    TG_TRY(add_col(dbl ? TGPU_FLOAT64 : TGPU_INT64, dbl ? 4 : 5, fp.acc_main, fp.acc_count));
+                    break;
+                default: break;
+            }
+        }
+        if (spec.count > 0) TG_LAUNCH(ctx, agg_output_kernel, grid, 256, 0, state(), G, spec, d_err, d_any);
+        // validity bitmaps only for columns that actually hold a NULL
+        DevBuf anyflags;
+        TG_TRY(anyflags.alloc(ctx, outp.cols.size() * 4));
+        TG_CUDA(ctx, cudaMemsetAsync(anyflags.p, 0, outp.cols.size() * 4, ctx->stream));
+        std::vector<std::shared_ptr<DevBuf>> bitmaps(outp.cols.size());
+        for (size_t c = 0; c < outp.cols.size(); c++) {
+            bitmaps[c] = std::make_shared<DevBuf>();
+            TG_TRY(bitmaps[c]->alloc(ctx, (size_t)((G + 7) / 8)));
+            TG_LAUNCH(ctx, nullmap_pack_kernel, tg_grid(ctx, (G + 7) / 8, 256, 8), 256, 0, nullmaps[c]->as<unsigned char>(), G,
+                      bitmaps[c]->as<unsigned char>(), anyflags.as<unsigned int>() + c);
+        }
+        std::vector<unsigned int> h_any(outp.cols.size());
+        TG_CUDA(ctx, cudaMemcpyAsync(h_any.data(), anyflags.p, outp.cols.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        int64_t errw = 0;
+        TG_TRY(tg_read_i64(ctx, d_err, &errw));
+        TG_TRY(raise((uint32_t)(errw & 0xFFFFFFFFLL)));
+        for (size_t c = 0; c < outp.cols.size(); c++) {
+            if (!h_any[c]) continue;
+            outp.cols[c].own_validity = bitmaps[c];
+            outp.cols[c].validity = bitmaps[c]->as<uint8_t>();
+        }
+        *out = tg_make_owned_page(std::move(outp));
+        return TGPU_OK;
+    }
+
+    int reset_state()
+    {
+        // partial flush: the builder is rebuilt empty (HashAggregationOperator.getOutput :478-483)
+        planned = true;
+        g_slots = 0;
+        g_table.release();
+        TG_TRY(init_state());
+        if (use_general) TG_TRY(switch_to_general());
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override
+    {
+        *out = nullptr;
+        if (next_out < pending.size()) { *out = pending[next_out++]; return TGPU_OK; }
+        if (flushing) {
+            TG_TRY(build_output(out));
+            TG_TRY(reset_state());
+            flushing = false;
+            return TGPU_OK;
+        }
+        if (finishing && !finished) {
+            TG_TRY(build_output(out));
+            finished = true;
+        }
+        return TGPU_OK;
+    }
+
+    int finish() override { finishing = true; return TGPU_OK; }
+    bool is_finished() override { return finished && next_out >= pending.size(); }
+};
+
+int build_agg_op(tgpu_ctx* ctx, const tgpu_agg_spec* spec, AggOp** out)
+{
+    if (spec->num_keys < 0 || spec->num_aggs < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "negative counts in aggregation spec");
+    if (spec->step < TGPU_STEP_SINGLE || spec->step > TGPU_STEP_INTERMEDIATE) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "bad aggregation step");
+    std::unique_ptr<AggOp> op(new AggOp(ctx));
+    op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_keys);
+    op->fns.assign(spec->aggs, spec->aggs + spec->num_aggs);
+    op->step = spec->step;
+    op->expected_groups = spec->expected_groups;
+    op->max_partial_bytes = spec->max_partial_bytes;
+    if (spec->pre) {
+        if (spec->step == TGPU_STEP_FINAL || spec->step == TGPU_STEP_INTERMEDIATE)
+            return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a fused pre-stage only makes sense on raw input");
+        op->has_pre = true;
+        TG_TRY(tg::expr_compile(ctx, spec->pre, &op->host_prog, &op->prog_max_channel));
+        op->projections.assign(spec->pre->projections, spec->pre->projections + spec->pre->num_projections);
+        TG_TRY(op->d_prog.alloc(ctx, sizeof(DProgram)));
+        TG_CUDA(ctx, cudaMemcpyAsync(op->d_prog.p, &op->host_prog, sizeof(DProgram), cudaMemcpyHostToDevice, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = op.release();
+    return TGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op** out)
+{
+    if (!ctx || !spec || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    AggOp* op = nullptr;
+    TG_TRY(build_agg_op(ctx, spec, &op));
+    *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_agg_group_count(tgpu_op* op, int64_t* out)
+{
+    AggOp* a = dynamic_cast<AggOp*>(op);
+    if (!a || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = a->group_count;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_groupby_hash_create(tgpu_ctx* ctx, int32_t num_keys, const int32_t* key_channels, int64_t expected_groups, tgpu_op** out)
+{
+    if (!ctx || !key_channels || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    tgpu_agg_spec spec;
+    memset(&spec, 0, sizeof(spec));
+    spec.num_keys = num_keys;
+    spec.key_channels = key_channels;
+    spec.step = TGPU_STEP_SINGLE;
+    spec.expected_groups = expected_groups;
+    AggOp* op = nullptr;
+    TG_TRY(build_agg_op(ctx, &spec, &op));
+    op->gids_only = true;
+    *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_groupby_hash_get_group_ids(tgpu_op* op, const tgpu_page* page, int32_t* out_group_ids)
+{
+    AggOp* a = dynamic_cast<AggOp*>(op);
+    if (!a || !page || !out_group_ids) return TGPU_ERR_INVALID_ARGUMENT;
+    tgpu_ctx* ctx = a->ctx;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (page->num_rows == 0) return TGPU_OK;
+    DevPage in;
+    TG_TRY(tg_ingest_page(ctx, page, &in));
+    if (!a->planned) {
+        TG_TRY(a->make_plan(in));
+        TG_TRY(a->init_state());
+        TG_TRY(a->switch_to_general());
+    }
+    DColumns cols;
+    TG_TRY(a->fill_cols(in, &cols));
+    bool device = (page->flags & TGPU_PAGE_DEVICE) != 0;
+    if (device) return a->run_general_ids(in, cols, out_group_ids);
+    DevBuf gids;
+    TG_TRY(gids.alloc(ctx, (size_t)in.rows * 4));
+    TG_TRY(a->run_general_ids(in, cols, gids.as<int>()));
+    TG_CUDA(ctx, cudaMemcpyAsync(out_group_ids, gids.p, (size_t)in.rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TGPU_OK;
+}

@@ -1,0 +1,94 @@
+// hash.cuh — the reference's hash arithmetic as __host__ __device__ inlines.
+// Fused into every consumer kernel; never a pass of its own.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TG_HD __host__ __device__ __forceinline__
+#else
+#define TG_HD inline
+#endif
+
+namespace tg {
+
+constexpr uint64_t XXP1 = 0x9E3779B185EBCA87ULL, XXP2 = 0xC2B2AE3D27D4EB4FULL, XXP3 = 0x165667B19E3779F9ULL,
+                   XXP4 = 0x85EBCA77C2B2AE63ULL, XXP5 = 0x27D4EB2F165667C5ULL;
+
+TG_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+// BIGINT / INTEGER / DATE / SMALLINT / TINYINT hash code (S/type/AbstractLongType.java:121-125;
+// narrower integers are sign-extended first, S/type/AbstractIntType.java:183-187)
+TG_HD uint64_t hash_long(int64_t v) { return rotl64((uint64_t)v * XXP2, 31) * XXP1; }
+
+// DOUBLE hash code (S/type/DoubleType.java:199-206): -0.0 -> +0.0, every NaN -> canonical NaN
+// (Double.doubleToLongBits), then hash_long of the bits
+TG_HD uint64_t hash_double_bits(int64_t bits)
+{
+    uint64_t u = (uint64_t)bits;
+    if ((u << 1) == 0) u = 0;                                            // +-0.0
+    if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;  // NaN
+    return hash_long((int64_t)u);
+}
+
+// murmur3 fmix64 (M/operator/join/PagesHash.java:44-50 == fastutil HashCommon.murmurHash3 used at
+// M/operator/BigintGroupByHash.java:297-300)
+TG_HD uint64_t murmur3_mix(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+// CombineHashFunction.getHash (M/operator/scalar/CombineHashFunction.java:29-32)
+TG_HD uint64_t combine_hash(uint64_t prev, uint64_t v) { return 31 * prev + v; }
+
+// HashGenerator.processRawHash (M/operator/HashGenerator.java:41-46)
+TG_HD int32_t process_raw_hash(uint64_t raw, int32_t count)
+{
+    uint32_t x = (uint32_t)(raw ^ (raw >> 32));
+    return (int32_t)(((uint64_t)x * (uint64_t)(uint32_t)count) >> 32);
+}
+
+// XXH64 (io.airlift.slice.XxHash64, public algorithm) of a byte range, seed 0; unaligned-safe
+TG_HD uint64_t xxh64_bytes(const uint8_t* p, int64_t len)
+{
+    const uint8_t* end = p + len;
+    uint64_t h;
+    auto rd64 = [](const uint8_t* q) { uint64_t v = 0; for (int i = 7; i >= 0; i--) v = (v << 8) | q[i]; return v; };
+    auto rd32 = [](const uint8_t* q) { uint32_t v = 0; for (int i = 3; i >= 0; i--) v = (v << 8) | q[i]; return v; };
+    if (len >= 32) {
+        uint64_t v1 = XXP1 + XXP2, v2 = XXP2, v3 = 0, v4 = 0 - XXP1;
+        const uint8_t* limit = end - 32;
+        do {
+            v1 = rotl64(v1 + rd64(p) * XXP2, 31) * XXP1;
+            v2 = rotl64(v2 + rd64(p + 8) * XXP2, 31) * XXP1;
+            v3 = rotl64(v3 + rd64(p + 16) * XXP2, 31) * XXP1;
+            v4 = rotl64(v4 + rd64(p + 24) * XXP2, 31) * XXP1;
+            p += 32;
+        } while (p <= limit);
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h ^= rotl64(v1 * XXP2, 31) * XXP1; h = h * XXP1 + XXP4;
+        h ^= rotl64(v2 * XXP2, 31) * XXP1; h = h * XXP1 + XXP4;
+        h ^= rotl64(v3 * XXP2, 31) * XXP1; h = h * XXP1 + XXP4;
+        h ^= rotl64(v4 * XXP2, 31) * XXP1; h = h * XXP1 + XXP4;
+    }
+    else {
+        h = XXP5;
+    }
+    h += (uint64_t)len;
+    while (p + 8 <= end) { h ^= rotl64(rd64(p) * XXP2, 31) * XXP1; h = rotl64(h, 27) * XXP1 + XXP4; p += 8; }
+    if (p + 4 <= end) { h ^= (uint64_t)rd32(p) * XXP1; h = rotl64(h, 23) * XXP2 + XXP3; p += 4; }
+    while (p < end) { h ^= (uint64_t)(*p) * XXP5; h = rotl64(h, 11) * XXP1; p++; }
+    h ^= h >> 33; h *= XXP2; h ^= h >> 29; h *= XXP3; h ^= h >> 32;
+    return h;
+}
+
+// splitmix64: counter-based generator of the synthetic TPC-H-shaped columns
+TG_HD uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+}  // namespace tg

@@ -1,0 +1,607 @@
+// join.cu — hash join build + probe for sm_100a.
+//
+// Reference semantics reproduced (bit-exact on address indices and output row order):
+//   build : PagesIndex.addPage (M/operator/PagesIndex.java:224-256) keeps every build row; the address
+//           index of a row is its global row number.  BigintPagesHash.insertValue
+//           (M/operator/join/BigintPagesHash.java:122-141) + ArrayPositionLinks.link
+//           (M/operator/join/ArrayPositionLinks.java:45-50): rows with a NULL key are skipped; for
+//           duplicate keys the LAST inserted row is the chain head and links to the previous head, so a
+//           chain lists its rows in descending row order.
+//   probe : JoinProbe.fillCache (M/operator/join/unspilled/JoinProbe.java:112-180) ->
+//           BigintPagesHash.getAddressIndex (:184-220): chain head or -1, NULL probe keys -> -1.
+//   expand: PageJoiner.joinCurrentPosition / outerJoinCurrentPosition (PageJoiner.java:203-242) and
+//           LookupJoinPageBuilder.build (LookupJoinPageBuilder.java:119-160): output rows in probe order,
+//           within one probe row in chain order; probe columns first, then build output columns.
+//
+// B200 design: the table is an open-addressing array of 16-byte slots {int64 key, int32 head} so that one
+// probe touches exactly one 32-byte sector; the deterministic "head = highest row" of the sequential
+// reference insert order is obtained with atomicMax, and duplicate chains are materialised by a radix sort
+// of (slot,row) pairs only when duplicates exist.  Slot placement (mix(key) & mask, linear probing) is not
+// observable, only key -> head is.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long EMPTY_KEY = 0x8000000000000000ULL;   // INT64_MIN is kept out of the table
+
+struct __align__(16) JoinSlot {
+    unsigned long long key;
+    int head;
+    int pad;
+};
+
+enum KeyKind { KEY_INT = 0, KEY_DOUBLE = 1 };
+
+// canonical 64-bit join key; returns false when the row can never match (NULL, or NaN under EQUAL)
+__device__ __forceinline__ bool join_key(const ColRef& c, int kind, int64_t i, unsigned long long* out)
+{
+    if (!tg_valid(c.validity, i)) return false;
+    int64_t v = tg_load_i64(c, i);
+    if (kind == KEY_DOUBLE) {
+        unsigned long long u = (unsigned long long)v;
+        if ((u << 1) == 0) u = 0;                                            // -0.0 == +0.0
+        if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) return false;  // NaN != NaN
+        v = (int64_t)u;
+    }
+    *out = (unsigned long long)v;
+    return true;
+}
+
+__global__ void join_table_init_kernel(int4* table, int64_t slots)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int4 empty = make_int4(0, (int)0x80000000, -1, 0);
+    for (; i < slots; i += stride) table[i] = empty;
+}
+
+// one thread per build row: claim/find the key's slot, head = max(row).  *dup_flag is set when a key repeats.
+__global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, int64_t n, JoinSlot* __restrict__ table, unsigned long long mask,
+                                                         int* __restrict__ special_head, int* __restrict__ dup_flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned long long k;
+        if (!join_key(key, kind, i, &k)) continue;
+        if (k == EMPTY_KEY) {
+            int old = atomicMax(special_head, (int)i);
+            if (old >= 0) *dup_flag = 1;
+            continue;
+        }
+        unsigned long long pos = tg::murmur3_mix(k) & mask;
+        while (true) {
+            unsigned long long cur = *((volatile unsigned long long*)&table[pos].key);
+            if (cur == EMPTY_KEY) cur = atomicCAS(&table[pos].key, EMPTY_KEY, k);
+            if (cur == EMPTY_KEY || cur == k) {
+                int old = atomicMax(&table[pos].head, (int)i);
+                if (old >= 0) *dup_flag = 1;
+                break;
+            }
+            pos = (pos + 1) & mask;
+        }
+    }
+}
+
+__device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, unsigned long long mask, unsigned long long k, int special_head)
+{
+    if (k == EMPTY_KEY) return special_head;
+    unsigned long long pos = tg::murmur3_mix(k) & mask;
+    while (true) {
+        int4 s = __ldg((const int4*)&table[pos]);
+        unsigned long long sk = (unsigned long long)(unsigned int)s.x | ((unsigned long long)(unsigned int)s.y << 32);
+        if (sk == k) return s.z;
+        if (sk == EMPTY_KEY) return -1;
+        pos = (pos + 1) & mask;
+    }
+}
+
+// Index-only probe (the headline kernel).  ROWS independent lookups per thread are issued before any is
+// consumed so that each thread keeps ROWS random 16-byte sector reads in flight; consecutive probe rows with
+// the same key (TPC-H clustering) collapse in the coalescer / L1.
+// Algorithmic bytes per probe row: 8 (key) + 12 (slot) + 4 (position) = 24.
+template <int ROWS, bool INT64_NO_NULLS>
+__global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
+                                                         int special_head, int* __restrict__ out)
+{
+    int64_t tile = (int64_t)blockDim.x * ROWS;
+    int64_t tiles = (n + tile - 1) / tile;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int64_t base = t * tile + threadIdx.x;
+        unsigned long long k[ROWS];
+        bool ok[ROWS];
+        int4 s[ROWS];
+        unsigned long long pos[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            int64_t i = base + (int64_t)j * blockDim.x;
+            ok[j] = false;
+            k[j] = 0;
+            if (i < n) {
+                if (INT64_NO_NULLS) { k[j] = (unsigned long long)__ldg((const long long*)key.data + i); ok[j] = true; }
+                else ok[j] = join_key(key, kind, i, &k[j]);
+            }
+            pos[j] = tg::murmur3_mix(k[j]) & mask;
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            if (ok[j] && k[j] != EMPTY_KEY) s[j] = __ldg((const int4*)&table[pos[j]]);
+            else s[j] = make_int4(0, (int)0x80000000, -1, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            int64_t i = base + (int64_t)j * blockDim.x;
+            if (i >= n) continue;
+            int res = -1;
+            if (ok[j]) {
+                if (k[j] == EMPTY_KEY) res = special_head;
+                else {
+                    unsigned long long p = pos[j];
+                    int4 cur = s[j];
+                    while (true) {
+                        unsigned long long sk = (unsigned long long)(unsigned int)cur.x | ((unsigned long long)(unsigned int)cur.y << 32);
+                        if (sk == k[j]) { res = cur.z; break; }
+                        if (sk == EMPTY_KEY) break;
+                        p = (p + 1) & mask;
+                        cur = __ldg((const int4*)&table[p]);
+                    }
+                }
+            }
+            out[i] = res;
+        }
+    }
+}
+
+// --- duplicate chains -------------------------------------------------------------------------------
+// sort key = (slot << 32 | row) for rows that are in the table; rows with NULL keys sort last
+__global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
+                                        unsigned long long special_slot, unsigned long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned long long k;
+        unsigned long long slot = 0xFFFFFFFFULL;
+        if (join_key(key, kind, i, &k)) {
+            if (k == EMPTY_KEY) slot = special_slot;
+            else {
+                unsigned long long pos = tg::murmur3_mix(k) & mask;
+                while (table[pos].key != k) pos = (pos + 1) & mask;
+                slot = pos;
+            }
+        }
+        out[i] = (slot << 32) | (unsigned long long)(unsigned int)i;
+    }
+}
+
+// after the sort rows of one key are adjacent in ascending row order: next(row) = previous row of the key
+__global__ void join_links_kernel(const unsigned long long* __restrict__ sorted, int64_t n, int* __restrict__ links)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned long long cur = sorted[i];
+        unsigned int slot = (unsigned int)(cur >> 32);
+        int row = (int)(unsigned int)cur;
+        int next = -1;
+        if (slot != 0xFFFFFFFFu && i > 0) {
+            unsigned long long prev = sorted[i - 1];
+            if ((unsigned int)(prev >> 32) == slot) next = (int)(unsigned int)prev;
+        }
+        links[row] = next;
+    }
+}
+
+// --- expansion --------------------------------------------------------------------------------------
+__global__ void join_count_kernel(const int* __restrict__ jp, int64_t n, const int* __restrict__ links, int single_match, int outer,
+                                  int* __restrict__ counts)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int p = jp[i];
+        int c = 0;
+        if (p >= 0) {
+            c = 1;
+            if (links && !single_match) {
+                p = links[p];
+                while (p >= 0) { c++; p = links[p]; }
+            }
+        }
+        else if (outer) c = 1;
+        counts[i] = c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[n] = 0;
+}
+
+__global__ void join_fill_kernel(const int* __restrict__ jp, int64_t n, const int* __restrict__ links, int single_match, int outer,
+                                 const long long* __restrict__ offsets, int* __restrict__ out_probe, int* __restrict__ out_build)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int p = jp[i];
+        long long o = offsets[i];
+        if (p >= 0) {
+            out_probe[o] = (int)i;
+            out_build[o] = p;
+            if (links && !single_match) {
+                p = links[p];
+                while (p >= 0) { o++; out_probe[o] = (int)i; out_build[o] = p; p = links[p]; }
+            }
+        }
+        else if (outer) {
+            out_probe[o] = (int)i;
+            out_build[o] = -1;
+        }
+    }
+}
+
+int key_kind_of(int type) { return type == TGPU_FLOAT64 ? KEY_DOUBLE : KEY_INT; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// LookupSource
+// ------------------------------------------------------------------------------------------------
+struct tgpu_lookup {
+    tgpu_ctx* ctx = nullptr;
+    int refs = 1;
+    int64_t positions = 0;              // build rows (incl. NULL-key rows: PagesIndex keeps them)
+    int key_type = 0;
+    DevBuf table;                       // JoinSlot[capacity]
+    unsigned long long mask = 0;
+    int special_head = -1;
+    bool has_dups = false;
+    DevBuf links;                       // int32[positions], only when has_dups
+    DevPage store;                      // key column first, then build output columns
+    int32_t num_output = 0;
+};
+
+namespace {
+
+int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key, int* d_out)
+{
+    int64_t n = key.length;
+    if (n == 0) return TGPU_OK;
+    if (key.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width join keys are not supported on the GPU path");
+    if (key_kind_of(key.type) != key_kind_of(lk->key_type) || key.elem_size() == 0)
+        return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key type %d does not match build key type %d", key.type, lk->key_type);
+    constexpr int ROWS = 4;
+    int grid = tg_grid(ctx, n, 256 * ROWS, 8);
+    const JoinSlot* table = lk->table.as<JoinSlot>();
+    auto probe_fast = join_probe_kernel<ROWS, true>;
+    auto probe_any = join_probe_kernel<ROWS, false>;
+    if (key.type == TGPU_INT64 && !key.validity)
+        TG_LAUNCH(ctx, probe_fast, grid, 256, 0, tg_colref(key), KEY_INT, n, table, lk->mask, lk->special_head, d_out);
+    else
+        TG_LAUNCH(ctx, probe_any, grid, 256, 0, tg_colref(key), key_kind_of(key.type), n, table, lk->mask, lk->special_head, d_out);
+    return TGPU_OK;
+}
+
+// HashBuilderOperator: NEEDS_INPUT -> (finish) LOOKUP_SOURCE_BUILT -> CLOSED
+struct JoinBuildOp : tgpu_op {
+    std::vector<int32_t> key_channels, output_channels;
+    std::vector<DevPage> chunks;     // key column + output columns of every input page
+    int64_t rows = 0;
+    bool finishing = false;
+    tgpu_lookup* lookup = nullptr;
+
+    explicit JoinBuildOp(tgpu_ctx* c) : tgpu_op(c) {}
+    ~JoinBuildOp() override { if (lookup) tgpu_lookup_release(lookup); }
+
+    bool needs_input() override { return !finishing; }
+
+    int add_input(const tgpu_page* page) override
+    {
+        // HashBuilderOperator.addInput :253-277 -> PagesIndex.addPage :224-256
+        if (page->num_rows == 0) return TGPU_OK;
+        if (rows + page->num_rows > (int64_t)INT32_MAX)
+            return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of pages index cannot exceed 2 billion entries");   // PagesIndex.java:247-250
+        bool device = (page->flags & TGPU_PAGE_DEVICE) != 0;
+        DevPage p;
+        p.rows = page->num_rows;
+        auto take = [&](int32_t ch) -> int {
+            if (ch < 0 || ch >= page->num_columns) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "channel %d out of range", ch);
+            DevColumn c;
+            TG_TRY(tg_ingest_column(ctx, &page->columns[ch], device, &c));
+            p.cols.push_back(std::move(c));
+            return TGPU_OK;
+        };
+        TG_TRY(take(key_channels[0]));
+        for (int32_t ch : output_channels) TG_TRY(take(ch));
+        if (!device) TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        rows += p.rows;
+        chunks.push_back(std::move(p));
+        return TGPU_OK;
+    }
+
+    int concat(DevPage* out)
+    {
+        if (chunks.size() == 1) { *out = std::move(chunks[0]); chunks.clear(); return TGPU_OK; }
+        DevPage r;
+        r.rows = rows;
+        size_t ncols = 1 + output_channels.size();
+        r.cols.resize(ncols);
+        for (size_t c = 0; c < ncols; c++) {
+            DevColumn& d = r.cols[c];
+            d.length = rows;
+            if (chunks.empty()) { d.type = TGPU_INT64; continue; }
+            d.type = chunks[0].cols[c].type;
+            bool any_valid = false;
+            for (auto& ch : chunks) any_valid |= ch.cols[c].validity != nullptr;
+            if (d.type == TGPU_UTF8 || any_valid) {
+                // general path: gather-append through row indices is overkill here; variable-width and nullable
+                // build columns are concatenated on the host-side shim for now
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "multi-page build with nullable or variable-width columns is not supported yet");
+            }
+            int es = d.elem_size();
+            d.own_data = std::make_shared<DevBuf>();
+            TG_TRY(d.own_data->alloc(ctx, (size_t)rows * es));
+            int64_t off = 0;
+            for (auto& ch : chunks) {
+                TG_CUDA(ctx, cudaMemcpyAsync((char*)d.own_data->p + off * es, ch.cols[c].data, (size_t)ch.rows * es, cudaMemcpyDeviceToDevice, ctx->stream));
+                off += ch.rows;
+            }
+            d.data = d.own_data->p;
+        }
+        chunks.clear();
+        *out = std::move(r);
+        return TGPU_OK;
+    }
+
+    int finish() override
+    {
+        // HashBuilderOperator.finish :286-308 -> finishInput :310-333 -> PagesIndex.createLookupSourceSupplier :523-542
+        if (finishing) return TGPU_OK;   // re-entrant
+        std::unique_ptr<tgpu_lookup> lk(new tgpu_lookup());
+        lk->ctx = ctx;
+        lk->positions = rows;
+        lk->num_output = (int32_t)output_channels.size();
+        TG_TRY(concat(&lk->store));
+        if (rows == 0) {
+            lk->store.cols.resize(1 + output_channels.size());
+            lk->key_type = TGPU_INT64;
+        }
+        else lk->key_type = lk->store.cols[0].type;
+        if (lk->key_type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width join keys are not supported on the GPU path");
+        // sizing: IncrementalLoadFactorHashArraySizeSupplier.getHashArraySize :40-47 (capacity is not observable)
+        double lf = rows <= (1 << 16) ? 0.25 : rows <= (1 << 20) ? 0.5 : 0.75;
+        int64_t need = (int64_t)((double)rows / lf) + 1;
+        int64_t cap = 2;
+        while (cap < need) cap <<= 1;
+        if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
+        lk->mask = (unsigned long long)cap - 1;
+        TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
+        TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
+        int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag
+        int init[2] = {-1, 0};
+        TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        if (rows > 0) {
+            const DevColumn& key = lk->store.cols[0];
+            TG_LAUNCH(ctx, join_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(key), key_kind_of(key.type), rows,
+                      lk->table.as<JoinSlot>(), lk->mask, d_flags, d_flags + 1);
+        }
+        int64_t packed = 0;
+        TG_TRY(tg_read_i64(ctx, d_flags, &packed));
+        lk->special_head = (int)(packed & 0xFFFFFFFFLL);
+        lk->has_dups = (packed >> 32) != 0;
+        if (lk->has_dups) {
+            // ArrayPositionLinks: chains in descending row order
+            const DevColumn& key = lk->store.cols[0];
+            DevBuf keys_in, keys_out, tmp;
+            TG_TRY(keys_in.alloc(ctx, (size_t)rows * 8));
+            TG_TRY(keys_out.alloc(ctx, (size_t)rows * 8));
+            TG_LAUNCH(ctx, join_slot_of_row_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(key), key_kind_of(key.type), rows,
+                      lk->table.as<JoinSlot>(), lk->mask, (unsigned long long)cap, keys_in.as<unsigned long long>());
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys_in.as<unsigned long long>(), keys_out.as<unsigned long long>(), (int)rows, 0, 64, ctx->stream);
+            TG_TRY(tmp.alloc(ctx, tmp_bytes));
+            TG_CUDA(ctx, cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, keys_in.as<unsigned long long>(), keys_out.as<unsigned long long>(), (int)rows, 0, 64, ctx->stream));
+            TG_TRY(lk->links.alloc(ctx, (size_t)rows * 4));
+            TG_LAUNCH(ctx, join_links_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, keys_out.as<unsigned long long>(), rows, lk->links.as<int>());
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        lookup = lk.release();
+        finishing = true;
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override { *out = nullptr; return TGPU_OK; }
+    // HashBuilderOperator.isFinished: after the lookup source was handed over and released
+    bool is_finished() override { return finishing; }
+    int64_t memory_bytes() override
+    {
+        int64_t b = 0;
+        for (auto& c : chunks) b += c.memory_bytes();
+        if (lookup) b += tgpu_lookup_memory_bytes(lookup);
+        return b;
+    }
+};
+
+// LookupJoinOperator
+struct JoinProbeOp : tgpu_op {
+    tgpu_lookup* lookup;
+    int join_type = 0, single_match = 0;
+    std::vector<int32_t> key_channels, output_channels;
+    std::vector<OwnedPage*> pending;
+    size_t next_out = 0;
+    bool finishing = false;
+
+    JoinProbeOp(tgpu_ctx* c, tgpu_lookup* lk) : tgpu_op(c), lookup(lk) { lookup->refs++; }
+    ~JoinProbeOp() override
+    {
+        for (size_t i = next_out; i < pending.size(); i++) delete pending[i];
+        tgpu_lookup_release(lookup);
+    }
+
+    bool needs_input() override { return !finishing && next_out >= pending.size(); }
+
+    int add_input(const tgpu_page* page) override
+    {
+        pending.clear();
+        next_out = 0;
+        int64_t n = page->num_rows;
+        if (n == 0) return TGPU_OK;
+        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+        DevPage in;
+        TG_TRY(tg_ingest_page(ctx, page, &in));
+        if (key_channels[0] < 0 || key_channels[0] >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key channel out of range");
+        const DevColumn& key = in.cols[key_channels[0]];
+        // joinPositionCache (JoinProbe.java:112-180)
+        auto jp = std::make_shared<DevBuf>();
+        TG_TRY(jp->alloc(ctx, (size_t)(n + 1) * 4));
+        TG_TRY(lookup_positions(ctx, lookup, key, jp->as<int>()));
+        bool outer = join_type == TGPU_JOIN_PROBE_OUTER;
+        const int* links = lookup->has_dups ? lookup->links.as<int>() : nullptr;
+        // match counts -> exclusive scan -> output offsets
+        DevBuf counts, offsets, tmp;
+        TG_TRY(counts.alloc(ctx, (size_t)(n + 1) * 4));
+        TG_TRY(offsets.alloc(ctx, (size_t)(n + 1) * 8));
+        int grid = tg_grid(ctx, n, 256 * 4, 8);
+        TG_LAUNCH(ctx, join_count_kernel, grid, 256, 0, jp->as<int>(), n, links, single_match, outer ? 1 : 0, counts.as<int>());
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.as<int>(), offsets.as<long long>(), n + 1, ctx->stream);
+        TG_TRY(tmp.alloc(ctx, tmp_bytes));
+        TG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, counts.as<int>(), offsets.as<long long>(), n + 1, ctx->stream));
+        int64_t total = 0;
+        TG_TRY(tg_read_i64(ctx, offsets.as<long long>() + n, &total));
+        if (total == 0) return TGPU_OK;
+        if (total > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "join output of one probe page exceeds 2^31-1 rows");
+
+        DevPage outp;
+        outp.rows = total;
+        // every probe row produced exactly one row and there are no chains: probe rows map 1:1
+        // (LookupJoinPageBuilder.build :144-150 "outputProbeBlocksDirectly")
+        bool identity = (total == n) && (!links || single_match);
+        const int* build_idx = nullptr;
+        bool build_may_be_null = outer;
+        DevBuf out_probe, out_build;
+        if (identity) {
+            for (int32_t ch : output_channels) outp.cols.push_back(in.cols[ch]);   // shares ownership, no copy
+            build_idx = jp->as<int>();
+        }
+        else {
+            TG_TRY(out_probe.alloc(ctx, (size_t)total * 4));
+            TG_TRY(out_build.alloc(ctx, (size_t)total * 4));
+            TG_LAUNCH(ctx, join_fill_kernel, grid, 256, 0, jp->as<int>(), n, links, single_match, outer ? 1 : 0, offsets.as<long long>(),
+                      out_probe.as<int>(), out_build.as<int>());
+            for (int32_t ch : output_channels) {
+                DevColumn c;
+                TG_TRY(tg_gather_column(ctx, in.cols[ch], out_probe.as<int>(), total, false, &c));
+                outp.cols.push_back(std::move(c));
+            }
+            build_idx = out_build.as<int>();
+        }
+        for (int32_t b = 0; b < lookup->num_output; b++) {
+            DevColumn c;
+            TG_TRY(tg_gather_column(ctx, lookup->store.cols[1 + b], build_idx, total, build_may_be_null, &c));
+            outp.cols.push_back(std::move(c));
+        }
+        pending.push_back(tg_make_owned_page(std::move(outp)));
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override
+    {
+        *out = nullptr;
+        if (next_out < pending.size()) *out = pending[next_out++];
+        return TGPU_OK;
+    }
+    int finish() override { finishing = true; return TGPU_OK; }
+    bool is_finished() override { return finishing && next_out >= pending.size(); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int tgpu_join_build_create(tgpu_ctx* ctx, const tgpu_join_build_spec* spec, tgpu_op** out)
+{
+    if (!ctx || !spec || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    if (spec->num_key_channels != 1)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports exactly one fixed-width join channel (got %d)", spec->num_key_channels);
+    JoinBuildOp* op = new JoinBuildOp(ctx);
+    op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
+    op->output_channels.assign(spec->output_channels, spec->output_channels + spec->num_output_channels);
+    *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_join_build_get_lookup(tgpu_op* build, tgpu_lookup** out)
+{
+    JoinBuildOp* op = dynamic_cast<JoinBuildOp*>(build);
+    if (!op || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    if (!op->lookup) return tg_fail(op->ctx, TGPU_ERR_ILLEGAL_STATE, "lookup source is not built yet: call finish() first");
+    op->lookup->refs++;
+    *out = op->lookup;
+    return TGPU_OK;
+}
+
+extern "C" void tgpu_lookup_release(tgpu_lookup* lookup)
+{
+    if (!lookup) return;
+    if (--lookup->refs == 0) {
+        cudaSetDevice(lookup->ctx->device);
+        delete lookup;
+    }
+}
+
+extern "C" int64_t tgpu_lookup_position_count(const tgpu_lookup* lookup) { return lookup ? lookup->positions : 0; }
+
+extern "C" int64_t tgpu_lookup_memory_bytes(const tgpu_lookup* lookup)
+{
+    if (!lookup) return 0;
+    return (int64_t)lookup->table.bytes + (int64_t)lookup->links.bytes + lookup->store.memory_bytes();
+}
+
+extern "C" int tgpu_lookup_has_duplicates(const tgpu_lookup* lookup) { return lookup && lookup->has_dups ? 1 : 0; }
+
+extern "C" int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec* spec, tgpu_lookup* lookup, tgpu_op** out)
+{
+    if (!ctx || !spec || !lookup || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    if (spec->num_key_channels != 1)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports exactly one fixed-width join channel (got %d)", spec->num_key_channels);
+    if (spec->join_type != TGPU_JOIN_INNER && spec->join_type != TGPU_JOIN_PROBE_OUTER)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "join type %d needs LookupOuterOperator: keep the Java operator", spec->join_type);
+    JoinProbeOp* op = new JoinProbeOp(ctx, lookup);
+    op->join_type = spec->join_type;
+    op->single_match = spec->output_single_match;
+    op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
+    op->output_channels.assign(spec->output_channels, spec->output_channels + spec->num_output_channels);
+    *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_lookup_get_join_positions(tgpu_ctx* ctx, const tgpu_lookup* lookup, const tgpu_page* keys_page, int32_t* out_positions)
+{
+    if (!ctx || !lookup || !keys_page || !out_positions) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (keys_page->num_columns != 1) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exactly one key column expected");
+    bool device = (keys_page->flags & TGPU_PAGE_DEVICE) != 0;
+    int64_t n = keys_page->num_rows;
+    DevColumn key;
+    TG_TRY(tg_ingest_column(ctx, &keys_page->columns[0], device, &key));
+    if (device) return lookup_positions(ctx, lookup, key, out_positions);
+    DevBuf out;
+    TG_TRY(out.alloc(ctx, (size_t)n * 4));
+    TG_TRY(lookup_positions(ctx, lookup, key, out.as<int>()));
+    TG_CUDA(ctx, cudaMemcpyAsync(out_positions, out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_lookup_copy_position_links(tgpu_ctx* ctx, const tgpu_lookup* lookup, int32_t* out_links_host)
+{
+    if (!ctx || !lookup || !out_links_host) return TGPU_ERR_INVALID_ARGUMENT;
+    if (!lookup->has_dups) {
+        for (int64_t i = 0; i < lookup->positions; i++) out_links_host[i] = -1;
+        return TGPU_OK;
+    }
+    TG_CUDA(ctx, cudaMemcpyAsync(out_links_host, lookup->links.p, (size_t)lookup->positions * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TGPU_OK;
+}

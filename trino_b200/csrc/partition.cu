@@ -1,0 +1,561 @@
+// partition.cu — PagePartitioner / PartitionedOutputOperator for sm_100a, and the NCCL all-to-all exchange.
+//
+// Reference semantics reproduced:
+//   - partition id = bucketToPartition[ processRawHash(rowHash, bucketCount) ] with rowHash folded as
+//     h = 31*h + typeHash(col) and NULL -> 0 (M/operator/HashGenerator.java:25-46,
+//     M/operator/InterpretedHashGenerator.java:102-110, M/operator/BucketPartitionFunction.java:45-64)
+//   - per-partition row order of PagePartitioner.partitionPage (M/operator/output/PagePartitioner.java:133-162):
+//       column-wise strategy (:273-314, positions >= 2 x partitions): [row 0 once when replicatesAnyRow],
+//       then every NULL-channel row (replicated to all partitions, :401-416), then the partition's own rows,
+//       each list ascending; row-wise strategy (:229-271): plain ascending row order with replicated rows
+//       interleaved.  A single partition takes the whole page.
+//   - output buffers are flushed per input page here (the reference flushes at 1 MB / 32768 rows,
+//     PositionsAppenderPageBuilder.java:34,132-142); values per partition and their order are identical.
+//
+// Device path: one kernel computes row hash -> partition id, a stable radix sort of (partition, row) pairs
+// yields the per-partition position lists, and one gather per column writes partition-contiguous buffers —
+// which are exactly the send buffers of the all-to-all.
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace {
+
+using namespace tg;
+
+struct KeyCols {
+    int32_t count;
+    ColRef cols[8];
+    const int32_t* offsets[8];   // UTF8 only
+    int32_t is_utf8[8];
+    int32_t is_double[8];
+};
+
+__device__ __forceinline__ uint64_t type_hash(const KeyCols& k, int c, int64_t row)
+{
+    const ColRef& col = k.cols[c];
+    if (!tg_valid(col.validity, row)) return 0;   // NULL_HASH_CODE (S/type/TypeUtils.java:34)
+    if (k.is_utf8[c]) {
+        int32_t a = k.offsets[c][row], b = k.offsets[c][row + 1];
+        return xxh64_bytes((const uint8_t*)col.data + a, b - a);
+    }
+    int64_t v = tg_load_i64(col, row);
+    return k.is_double[c] ? hash_double_bits(v) : hash_long(v);
+}
+
+// partition id per row; rows whose null_channel is NULL get id == partition_count (replicated later)
+__global__ void __launch_bounds__(256) partition_ids_kernel(KeyCols keys, int64_t n, int32_t bucket_count, const int32_t* __restrict__ bucket_to_partition,
+                                                           ColRef null_col, int32_t has_null_col, int32_t partition_count, int32_t* __restrict__ out)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        if (has_null_col && !tg_valid(null_col.validity, row)) { out[row] = partition_count; continue; }
+        uint64_t h = 0;
+        for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
+        int32_t bucket = process_raw_hash(h, bucket_count);
+        out[row] = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
+    }
+}
+
+// first index of every partition id in the sorted id array (P+2 boundaries)
+__global__ void partition_bounds_kernel(const int32_t* __restrict__ sorted_ids, int64_t n, int32_t nbounds, long long* __restrict__ bounds)
+{
+    int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nbounds) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (sorted_ids[mid] < p) lo = mid + 1;
+        else hi = mid;
+    }
+    bounds[p] = lo;
+}
+
+// final gather index of the column-wise strategy: per partition [any-row] + nulls + own rows
+__global__ void partition_compose_kernel(const int32_t* __restrict__ sorted_rows, const long long* __restrict__ bounds, int32_t partition_count,
+                                         int32_t prepend_row0, const long long* __restrict__ out_offsets, int32_t* __restrict__ out)
+{
+    int32_t p = blockIdx.y;
+    long long nulls_begin = bounds[partition_count], nulls_end = bounds[partition_count + 1];
+    long long own_begin = bounds[p], own_end = bounds[p + 1];
+    long long n_nulls = nulls_end - nulls_begin, n_own = own_end - own_begin;
+    long long total = prepend_row0 + n_nulls + n_own;
+    long long base = out_offsets[p];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        int32_t v;
+        if (i < prepend_row0) v = 0;
+        else if (i < prepend_row0 + n_nulls) v = sorted_rows[nulls_begin + (i - prepend_row0)];
+        else v = sorted_rows[own_begin + (i - prepend_row0 - n_nulls)];
+        out[base + i] = v;
+    }
+}
+
+// row-wise strategy (tiny pages): one thread per partition walks the rows in order
+__global__ void partition_rowwise_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t partition_count, int32_t start_row, int32_t prepend_row0,
+                                         long long* __restrict__ counts, int32_t* __restrict__ out, int64_t out_stride)
+{
+    int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= partition_count) return;
+    long long c = 0;
+    int32_t* o = out + (int64_t)p * out_stride;
+    if (prepend_row0) o[c++] = 0;
+    for (int64_t i = start_row; i < n; i++) {
+        int32_t id = ids[i];
+        if (id == partition_count || id == p) o[c++] = (int32_t)i;
+    }
+    counts[p] = c;
+}
+
+__global__ void iota32_kernel(int32_t* out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (int32_t)i;
+}
+
+__global__ void shift_rows_kernel(const int32_t* __restrict__ in, int64_t n, int32_t delta, int32_t* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = in[i] + delta;
+}
+
+struct PartitionOp : tgpu_op {
+    std::vector<int32_t> key_channels;
+    int32_t bucket_count = 1, partition_count = 1;
+    std::vector<int32_t> bucket_to_partition;
+    DevBuf d_b2p;
+    int32_t null_channel = -1;
+    bool replicates_any_row = false, any_row_replicated = false;
+    std::vector<OwnedPage*> pending;
+    size_t next_out = 0;
+    int32_t last_partition = -1;
+    bool finishing = false;
+
+    explicit PartitionOp(tgpu_ctx* c) : tgpu_op(c) {}
+    ~PartitionOp() override { for (size_t i = next_out; i < pending.size(); i++) delete pending[i]; }
+
+    bool needs_input() override { return !finishing && next_out >= pending.size(); }
+
+    int key_cols(const DevPage& in, KeyCols* k)
+    {
+        memset(k, 0, sizeof(*k));
+        if (key_channels.size() > 8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than 8 partition channels");
+        k->count = (int32_t)key_channels.size();
+        for (int c = 0; c < k->count; c++) {
+            int ch = key_channels[c];
+            if (ch < 0 || ch >= (int)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition channel %d out of range", ch);
+            const DevColumn& col = in.cols[ch];
+            k->cols[c] = tg_colref(col);
+            k->offsets[c] = col.offsets;
+            k->is_utf8[c] = col.type == TGPU_UTF8;
+            k->is_double[c] = col.type == TGPU_FLOAT64;
+        }
+        return TGPU_OK;
+    }
+
+    // partition id per row into d_ids (int32[n]); NULL-channel rows get partition_count
+    int compute_ids(const DevPage& in, int32_t* d_ids, bool use_null_channel)
+    {
+        KeyCols k;
+        TG_TRY(key_cols(in, &k));
+        ColRef nullcol;
+        memset(&nullcol, 0, sizeof(nullcol));
+        int has_null = 0;
+        if (use_null_channel && null_channel >= 0) {
+            if (null_channel >= (int)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "null channel out of range");
+            if (in.cols[null_channel].validity) { nullcol = tg_colref(in.cols[null_channel]); has_null = 1; }
+        }
+        TG_LAUNCH(ctx, partition_ids_kernel, tg_grid(ctx, in.rows, 256, 8), 256, 0, k, in.rows, bucket_count,
+                  bucket_to_partition.empty() ? nullptr : d_b2p.as<int32_t>(), nullcol, has_null, partition_count, d_ids);
+        return TGPU_OK;
+    }
+
+    // stable sort of rows by partition id: sorted row list + P+2 boundaries (bounds[P]..bounds[P+1] = NULL-channel rows)
+    int sort_rows(const int32_t* d_ids, int64_t n, DevBuf* sorted_rows, DevBuf* bounds)
+    {
+        DevBuf rows_in, ids_out, tmp;
+        TG_TRY(rows_in.alloc(ctx, (size_t)n * 4));
+        TG_TRY(ids_out.alloc(ctx, (size_t)n * 4));
+        TG_TRY(sorted_rows->alloc(ctx, (size_t)n * 4));
+        TG_TRY(bounds->alloc(ctx, (size_t)(partition_count + 2) * 8));
+        TG_LAUNCH(ctx, iota32_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, rows_in.as<int32_t>(), n);
+        int bits = 1;
+        while ((1 << bits) <= partition_count) bits++;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_ids, ids_out.as<int32_t>(), rows_in.as<int32_t>(), sorted_rows->as<int32_t>(), (int)n, 0, bits, ctx->stream);
+        TG_TRY(tmp.alloc(ctx, tmp_bytes));
+        TG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, d_ids, ids_out.as<int32_t>(), rows_in.as<int32_t>(), sorted_rows->as<int32_t>(), (int)n, 0, bits, ctx->stream));
+        int nb = partition_count + 2;
+        TG_LAUNCH(ctx, partition_bounds_kernel, (nb + 127) / 128, 128, 0, ids_out.as<int32_t>(), n, nb, bounds->as<long long>());
+        return TGPU_OK;
+    }
+
+    int add_input(const tgpu_page* page) override
+    {
+        pending.clear();
+        next_out = 0;
+        int64_t n = page->num_rows;
+        if (n == 0) return TGPU_OK;   // PagePartitioner.partitionPage :135-137
+        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+        DevPage in;
+        TG_TRY(tg_ingest_page(ctx, page, &in));
+        const int P = partition_count;
+        if (P == 1) {
+            // single output partition: the whole page (:141-148)
+            if (replicates_any_row && !any_row_replicated) any_row_replicated = true;
+            OwnedPage* o = tg_make_owned_page(std::move(in));
+            o->partition = 0;
+            pending.push_back(o);
+            return TGPU_OK;
+        }
+        int prepend = 0, start_row = 0;
+        if (replicates_any_row && !any_row_replicated) { prepend = 1; start_row = 1; any_row_replicated = true; }
+        DevBuf ids;
+        TG_TRY(ids.alloc(ctx, (size_t)n * 4));
+        TG_TRY(compute_ids(in, ids.as<int32_t>(), true));
+        std::vector<long long> h_off(P + 1, 0);
+        DevBuf gather_idx;
+        int64_t idx_stride = 0;
+        bool row_wise = n < (int64_t)P * 2;   // COLUMNAR_STRATEGY_COEFFICIENT (:57,149)
+        if (row_wise) {
+            DevBuf counts;
+            TG_TRY(counts.alloc(ctx, (size_t)P * 8));
+            idx_stride = n + 1;
+            TG_TRY(gather_idx.alloc(ctx, (size_t)P * idx_stride * 4));
+            TG_LAUNCH(ctx, partition_rowwise_kernel, (P + 63) / 64, 64, 0, ids.as<int32_t>(), n, P, start_row, prepend, counts.as<long long>(),
+                      gather_idx.as<int32_t>(), idx_stride);
+            std::vector<long long> h_counts(P);
+            TG_CUDA(ctx, cudaMemcpyAsync(h_counts.data(), counts.p, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int p = 0; p < P; p++) {
+                if (h_counts[p] == 0) continue;
+                TG_TRY(emit(in, gather_idx.as<int32_t>() + (int64_t)p * idx_stride, h_counts[p], p));
+            }
+            return TGPU_OK;
+        }
+        // column-wise: rows [start_row, n) sorted by partition, NULL-channel rows in bucket P
+        DevBuf sorted_rows, bounds;
+        TG_TRY(sort_rows(ids.as<int32_t>() + start_row, n - start_row, &sorted_rows, &bounds));
+        std::vector<long long> h_bounds(P + 2);
+        TG_CUDA(ctx, cudaMemcpyAsync(h_bounds.data(), bounds.p, (size_t)(P + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        long long n_nulls = h_bounds[P + 1] - h_bounds[P];
+        if (start_row == 0 && n_nulls == 0) {
+            // common case: the sorted row list already is the per-partition gather index
+            for (int p = 0; p < P; p++) {
+                long long cnt = h_bounds[p + 1] - h_bounds[p];
+                if (cnt == 0) continue;
+                TG_TRY(emit(in, sorted_rows.as<int32_t>() + h_bounds[p], cnt, p));
+            }
+            return TGPU_OK;
+        }
+        // sorted rows are relative to start_row: shift back while composing
+        long long total = 0;
+        for (int p = 0; p < P; p++) { h_off[p] = total; total += prepend + n_nulls + (h_bounds[p + 1] - h_bounds[p]); }
+        h_off[P] = total;
+        DevBuf d_off, shifted;
+        TG_TRY(d_off.alloc(ctx, (size_t)(P + 1) * 8));
+        TG_CUDA(ctx, cudaMemcpyAsync(d_off.p, h_off.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TG_TRY(gather_idx.alloc(ctx, (size_t)total * 4));
+        const int32_t* rows_ptr = sorted_rows.as<int32_t>();
+        if (start_row) {
+            TG_TRY(shifted.alloc(ctx, (size_t)(n - start_row) * 4));
+            TG_LAUNCH(ctx, shift_rows_kernel, tg_grid(ctx, n - start_row, 1024, 8), 256, 0, sorted_rows.as<int32_t>(), n - start_row, start_row, shifted.as<int32_t>());
+            rows_ptr = shifted.as<int32_t>();
+        }
+        dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(tg_div_up(total / P + 1, 256), ctx->sm_count)), (unsigned)P);
+        TG_LAUNCH(ctx, partition_compose_kernel, grid, 256, 0, rows_ptr, bounds.as<long long>(), P, prepend, d_off.as<long long>(), gather_idx.as<int32_t>());
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_off staging buffer must outlive the copy
+        for (int p = 0; p < P; p++) {
+            long long cnt = h_off[p + 1] - h_off[p];
+            if (cnt == 0) continue;
+            TG_TRY(emit(in, gather_idx.as<int32_t>() + h_off[p], cnt, p));
+        }
+        return TGPU_OK;
+    }
+
+    int emit(const DevPage& in, const int32_t* d_idx, int64_t count, int32_t partition)
+    {
+        DevPage outp;
+        outp.rows = count;
+        outp.cols.resize(in.cols.size());
+        for (size_t c = 0; c < in.cols.size(); c++) TG_TRY(tg_gather_column(ctx, in.cols[c], d_idx, count, false, &outp.cols[c]));
+        OwnedPage* o = tg_make_owned_page(std::move(outp));
+        o->partition = partition;
+        pending.push_back(o);
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override
+    {
+        *out = nullptr;
+        if (next_out < pending.size()) {
+            *out = pending[next_out++];
+            last_partition = (*out)->partition;
+        }
+        return TGPU_OK;
+    }
+    int finish() override { finishing = true; return TGPU_OK; }
+    bool is_finished() override { return finishing && next_out >= pending.size(); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time so that libtrino_gpu.so has no link-time dependency on a particular libnccl
+// ------------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } ncclUniqueIdT;
+typedef int (*nccl_get_unique_id_t)(ncclUniqueIdT*);
+typedef int (*nccl_comm_init_rank_t)(ncclComm**, int, ncclUniqueIdT, int);
+typedef int (*nccl_comm_destroy_t)(ncclComm*);
+typedef int (*nccl_send_t)(const void*, size_t, int, int, ncclComm*, cudaStream_t);
+typedef int (*nccl_recv_t)(void*, size_t, int, int, ncclComm*, cudaStream_t);
+typedef int (*nccl_group_t)(void);
+typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, ncclComm*, cudaStream_t);
+typedef const char* (*nccl_get_error_string_t)(int);
+
+struct NcclApi {
+    void* handle = nullptr;
+    nccl_get_unique_id_t get_unique_id = nullptr;
+    nccl_comm_init_rank_t comm_init_rank = nullptr;
+    nccl_comm_destroy_t comm_destroy = nullptr;
+    nccl_send_t send = nullptr;
+    nccl_recv_t recv = nullptr;
+    nccl_group_t group_start = nullptr, group_end = nullptr;
+    nccl_all_gather_t all_gather = nullptr;
+    nccl_get_error_string_t error_string = nullptr;
+};
+
+NcclApi g_nccl;
+
+int load_nccl(tgpu_ctx* ctx)
+{
+    if (g_nccl.handle) return TGPU_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "libnccl.so.2 not found: %s", dlerror());
+    g_nccl.get_unique_id = (nccl_get_unique_id_t)dlsym(h, "ncclGetUniqueId");
+    g_nccl.comm_init_rank = (nccl_comm_init_rank_t)dlsym(h, "ncclCommInitRank");
+    g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
+    g_nccl.send = (nccl_send_t)dlsym(h, "ncclSend");
+    g_nccl.recv = (nccl_recv_t)dlsym(h, "ncclRecv");
+    g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
+    g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
+    g_nccl.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
+    g_nccl.error_string = (nccl_get_error_string_t)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end || !g_nccl.all_gather)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "libnccl is missing required symbols");
+    g_nccl.handle = h;
+    return TGPU_OK;
+}
+
+#define TG_NCCL(ctx, call)                                                                                               \
+    do {                                                                                                                 \
+        int _r = (call);                                                                                                 \
+        if (_r != 0)                                                                                                     \
+            return tg_fail((ctx), TGPU_ERR_CUDA, "%s failed: %s", #call, g_nccl.error_string ? g_nccl.error_string(_r) : "nccl error"); \
+    } while (0)
+
+constexpr int NCCL_INT8 = 0;    // ncclInt8 / ncclChar
+constexpr int NCCL_INT64 = 4;   // ncclInt64
+
+__global__ void validity_to_bytes_kernel(const uint8_t* __restrict__ validity, const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = tg_valid(validity, idx[i]) ? 0 : 1;   // 1 = NULL (byte map)
+}
+
+}  // namespace
+
+int tg_comm_destroy_internal(tgpu_ctx* ctx)
+{
+    if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
+    ctx->comm = nullptr;
+    return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int tgpu_partition_create(tgpu_ctx* ctx, const tgpu_partition_spec* spec, tgpu_op** out)
+{
+    if (!ctx || !spec || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (spec->bucket_count < 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partitionCount must be at least 1");   // HashBucketFunction.java:30
+    std::unique_ptr<PartitionOp> op(new PartitionOp(ctx));
+    op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
+    op->bucket_count = spec->bucket_count;
+    op->partition_count = spec->bucket_count;
+    if (spec->bucket_to_partition) {
+        op->bucket_to_partition.assign(spec->bucket_to_partition, spec->bucket_to_partition + spec->bucket_count);
+        int mx = 0;
+        for (int v : op->bucket_to_partition) {
+            if (v < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "negative partition in bucket_to_partition");
+            mx = std::max(mx, v);
+        }
+        op->partition_count = mx + 1;   // BucketPartitionFunction.java:35
+        TG_TRY(op->d_b2p.alloc(ctx, (size_t)spec->bucket_count * 4));
+        TG_CUDA(ctx, cudaMemcpyAsync(op->d_b2p.p, op->bucket_to_partition.data(), (size_t)spec->bucket_count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    op->null_channel = spec->null_channel;
+    op->replicates_any_row = spec->replicates_any_row != 0;
+    *out = op.release();
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_partition_last_output_partition(tgpu_op* op, int32_t* out)
+{
+    PartitionOp* p = dynamic_cast<PartitionOp*>(op);
+    if (!p || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = p->last_partition;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_partition_get_partitions(tgpu_op* op, const tgpu_page* page, int32_t* out_partitions)
+{
+    PartitionOp* p = dynamic_cast<PartitionOp*>(op);
+    if (!p || !page || !out_partitions) return TGPU_ERR_INVALID_ARGUMENT;
+    tgpu_ctx* ctx = p->ctx;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (page->num_rows == 0) return TGPU_OK;
+    DevPage in;
+    TG_TRY(tg_ingest_page(ctx, page, &in));
+    bool device = (page->flags & TGPU_PAGE_DEVICE) != 0;
+    if (device) return p->compute_ids(in, out_partitions, false);
+    DevBuf ids;
+    TG_TRY(ids.alloc(ctx, (size_t)in.rows * 4));
+    TG_TRY(p->compute_ids(in, ids.as<int32_t>(), false));
+    TG_CUDA(ctx, cudaMemcpyAsync(out_partitions, ids.p, (size_t)in.rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_comm_get_unique_id(uint8_t id[TGPU_COMM_ID_BYTES])
+{
+    TG_TRY(load_nccl(nullptr));
+    ncclUniqueIdT uid;
+    int r = g_nccl.get_unique_id(&uid);
+    if (r != 0) return tg_fail(nullptr, TGPU_ERR_CUDA, "ncclGetUniqueId failed");
+    memcpy(id, uid.internal, TGPU_COMM_ID_BYTES);
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_comm_init(tgpu_ctx* ctx, const uint8_t id[TGPU_COMM_ID_BYTES], int rank, int world)
+{
+    if (!ctx || !id) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    TG_TRY(load_nccl(ctx));
+    ncclUniqueIdT uid;
+    memcpy(uid.internal, id, TGPU_COMM_ID_BYTES);
+    TG_NCCL(ctx, g_nccl.comm_init_rank(&ctx->comm, world, uid, rank));
+    ctx->rank = rank;
+    ctx->world = world;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_comm_destroy(tgpu_ctx* ctx)
+{
+    if (!ctx) return TGPU_ERR_INVALID_ARGUMENT;
+    return tg_comm_destroy_internal(ctx);
+}
+
+extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out)
+{
+    PartitionOp* p = dynamic_cast<PartitionOp*>(partitioner);
+    if (!ctx || !p || !page || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->comm) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "tgpu_comm_init has not been called");
+    const int W = ctx->world;
+    if (p->partition_count != W) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition count %d != world size %d", p->partition_count, W);
+    if (p->null_channel >= 0 || p->replicates_any_row) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "replicating partitioners are not supported by the exchange");
+    int64_t n = page->num_rows;
+    if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+    DevPage in;
+    TG_TRY(tg_ingest_page(ctx, page, &in));
+    for (auto& c : in.cols)
+        if (c.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
+    // 1. rows sorted by destination rank
+    DevBuf ids, sorted_rows, bounds;
+    std::vector<long long> h_bounds(W + 2, 0);
+    if (n > 0) {
+        TG_TRY(ids.alloc(ctx, (size_t)n * 4));
+        TG_TRY(p->compute_ids(in, ids.as<int32_t>(), false));
+        TG_TRY(p->sort_rows(ids.as<int32_t>(), n, &sorted_rows, &bounds));
+        TG_CUDA(ctx, cudaMemcpyAsync(h_bounds.data(), bounds.p, (size_t)(W + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // 2. count matrix: every rank learns what every rank sends to whom
+    std::vector<long long> send_counts(W), matrix((size_t)W * W);
+    for (int r = 0; r < W; r++) send_counts[r] = h_bounds[r + 1] - h_bounds[r];
+    DevBuf d_send, d_matrix;
+    TG_TRY(d_send.alloc(ctx, (size_t)W * 8));
+    TG_TRY(d_matrix.alloc(ctx, (size_t)W * W * 8));
+    TG_CUDA(ctx, cudaMemcpyAsync(d_send.p, send_counts.data(), (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, g_nccl.all_gather(d_send.p, d_matrix.p, (size_t)W, NCCL_INT64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)W * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<long long> recv_counts(W), recv_off(W + 1, 0);
+    for (int r = 0; r < W; r++) { recv_counts[r] = matrix[(size_t)r * W + ctx->rank]; recv_off[r + 1] = recv_off[r] + recv_counts[r]; }
+    long long total_recv = recv_off[W];
+    if (total_recv > (long long)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "exchange output exceeds 2^31-1 rows on rank %d", ctx->rank);
+    // 3. per column: gather into destination order, then all-to-all with explicit counts
+    DevPage outp;
+    outp.rows = total_recv;
+    outp.cols.resize(in.cols.size());
+    for (size_t c = 0; c < in.cols.size(); c++) {
+        const DevColumn& src = in.cols[c];
+        int es = src.elem_size();
+        DevColumn sendcol;
+        if (n > 0) TG_TRY(tg_gather_column(ctx, src, sorted_rows.as<int32_t>(), n, false, &sendcol));
+        DevColumn& dst = outp.cols[c];
+        dst.type = src.type;
+        dst.length = total_recv;
+        dst.own_data = std::make_shared<DevBuf>();
+        TG_TRY(dst.own_data->alloc(ctx, (size_t)total_recv * es));
+        dst.data = dst.own_data->p;
+        TG_NCCL(ctx, g_nccl.group_start());
+        for (int r = 0; r < W; r++) {
+            if (send_counts[r] > 0)
+                TG_NCCL(ctx, g_nccl.send((const char*)sendcol.data + h_bounds[r] * es, (size_t)send_counts[r] * es, NCCL_INT8, r, ctx->comm, ctx->stream));
+            if (recv_counts[r] > 0)
+                TG_NCCL(ctx, g_nccl.recv((char*)dst.own_data->p + recv_off[r] * es, (size_t)recv_counts[r] * es, NCCL_INT8, r, ctx->comm, ctx->stream));
+        }
+        TG_NCCL(ctx, g_nccl.group_end());
+        // nulls travel as one byte per row (every rank takes part, a column without nulls sends "valid")
+        DevBuf send_nulls, recv_nulls;
+        TG_TRY(send_nulls.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
+        TG_TRY(recv_nulls.alloc(ctx, (size_t)std::max<long long>(total_recv, 1)));
+        if (n > 0)
+            TG_LAUNCH(ctx, validity_to_bytes_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, src.validity, sorted_rows.as<int32_t>(), n, send_nulls.as<uint8_t>());
+        TG_NCCL(ctx, g_nccl.group_start());
+        for (int r = 0; r < W; r++) {
+            if (send_counts[r] > 0) TG_NCCL(ctx, g_nccl.send(send_nulls.as<uint8_t>() + h_bounds[r], (size_t)send_counts[r], NCCL_INT8, r, ctx->comm, ctx->stream));
+            if (recv_counts[r] > 0) TG_NCCL(ctx, g_nccl.recv(recv_nulls.as<uint8_t>() + recv_off[r], (size_t)recv_counts[r], NCCL_INT8, r, ctx->comm, ctx->stream));
+        }
+        TG_NCCL(ctx, g_nccl.group_end());
+        if (total_recv > 0) {
+            tgpu_column bytemap_col;
+            memset(&bytemap_col, 0, sizeof(bytemap_col));
+            // pack the byte map into an Arrow bitmap through the ingest path of a device column
+            bytemap_col.type = TGPU_INT8;
+            bytemap_col.flags = TGPU_COL_NULLS_BYTEMAP;
+            bytemap_col.length = total_recv;
+            bytemap_col.data = recv_nulls.p;
+            bytemap_col.validity = recv_nulls.as<uint8_t>();
+            DevColumn packed;
+            TG_TRY(tg_ingest_column(ctx, &bytemap_col, true, &packed));
+            dst.own_validity = packed.own_validity;
+            dst.validity = packed.validity;
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    OwnedPage* o = tg_make_owned_page(std::move(outp));
+    *out = &o->hdr;
+    return TGPU_OK;
+}

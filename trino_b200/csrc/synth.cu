@@ -1,0 +1,120 @@
+// synth.cu — counter-based synthetic TPC-H-shaped columns generated directly in HBM.
+// MUST stay identical to the generators in oracle/oracle.cpp (tests compare them element by element).
+#include "common.cuh"
+
+namespace {
+
+__host__ __device__ inline uint64_t feistel_perm(uint64_t i, uint64_t n, uint64_t seed)
+{
+    int bits = 1;
+    while ((1ULL << bits) < n) bits++;
+    int hb = (bits + 1) / 2;
+    uint64_t hm = (1ULL << hb) - 1;
+    uint64_t x = i;
+    do {
+        uint64_t l = x >> hb, r = x & hm;
+        for (int round = 0; round < 4; round++) {
+            uint64_t f = tg::splitmix64(r ^ (seed + 0x1000003ULL * (uint64_t)round)) & hm;
+            uint64_t nl = r, nr = l ^ f;
+            l = nl; r = nr;
+        }
+        x = (l << hb) | r;
+    } while (x >= n);
+    return x;
+}
+
+__host__ __device__ inline int64_t order_key(int64_t i) { return (i / 8) * 32 + (i % 8) + 1; }
+
+__host__ __device__ inline int64_t lineitem_order_index(int64_t r)
+{
+    int64_t b = r / 28, w = r % 28;
+    int64_t acc = 0;
+    for (int64_t jj = 0; jj < 7; jj++) {
+        int64_t c = 1 + ((jj + b) % 7);
+        if (w < acc + c) return b * 7 + jj;
+        acc += c;
+    }
+    return b * 7 + 6;
+}
+
+__global__ void synth_orders_kernel(int64_t n_total, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t* __restrict__ out)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j < count; j += stride) {
+        int64_t i = shuffle ? (int64_t)feistel_perm((uint64_t)(first + j), (uint64_t)n_total, seed) : first + j;
+        out[j] = order_key(i);
+    }
+}
+
+__global__ void synth_lineitem_keys_kernel(int64_t rows, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t* __restrict__ out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < count; k += stride) {
+        int64_t r = shuffle ? (int64_t)feistel_perm((uint64_t)(first + k), (uint64_t)rows, seed) : first + k;
+        out[k] = order_key(lineitem_order_index(r));
+    }
+}
+
+__global__ void synth_q1_kernel(int64_t n, int64_t first, uint64_t seed, int32_t* __restrict__ shipdate, int8_t* __restrict__ returnflag,
+                                int8_t* __restrict__ linestatus, double* __restrict__ quantity, double* __restrict__ extendedprice,
+                                double* __restrict__ discount, double* __restrict__ tax)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        uint64_t x = tg::splitmix64(seed ^ (uint64_t)(first + k));
+        uint64_t y = tg::splitmix64(x);
+        int32_t sd = 8036 + (int32_t)(x % 2556);
+        int32_t receipt = sd + 1 + (int32_t)((y >> 40) % 30);
+        int64_t qty = 1 + (int64_t)((x >> 12) % 50);
+        int64_t retail_cents = 90000 + (int64_t)(y % 20001);
+        shipdate[k] = sd;
+        linestatus[k] = sd > 9298 ? 'O' : 'F';
+        returnflag[k] = receipt <= 9298 ? (((y >> 50) & 1) ? 'R' : 'A') : 'N';
+        quantity[k] = (double)qty;
+        extendedprice[k] = __ddiv_rn((double)(qty * retail_cents), 100.0);
+        discount[k] = __ddiv_rn((double)((y >> 20) % 11), 100.0);
+        tax[k] = __ddiv_rn((double)((y >> 30) % 9), 100.0);
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t tgpu_synth_lineitem_rows(int64_t n_orders)
+{
+    int64_t full = n_orders / 7, rem = n_orders % 7;
+    int64_t rows = full * 28;
+    for (int64_t jj = 0; jj < rem; jj++) rows += 1 + ((jj + full) % 7);
+    return rows;
+}
+
+extern "C" int tgpu_synth_orders_keys(tgpu_ctx* ctx, int64_t n_total, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t* out)
+{
+    if (!ctx || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return TGPU_OK;
+    TG_LAUNCH(ctx, synth_orders_kernel, tg_grid(ctx, count, 256, 8), 256, 0, n_total, first, count, seed, shuffle, out);
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_synth_lineitem_keys(tgpu_ctx* ctx, int64_t n_orders, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t* out)
+{
+    if (!ctx || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return TGPU_OK;
+    int64_t rows = tgpu_synth_lineitem_rows(n_orders);
+    TG_LAUNCH(ctx, synth_lineitem_keys_kernel, tg_grid(ctx, count, 256, 8), 256, 0, rows, first, count, seed, shuffle, out);
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_synth_lineitem_q1(tgpu_ctx* ctx, int64_t n, int64_t first, uint64_t seed, int32_t* shipdate, int8_t* returnflag, int8_t* linestatus,
+                                      double* quantity, double* extendedprice, double* discount, double* tax)
+{
+    if (!ctx) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return TGPU_OK;
+    TG_LAUNCH(ctx, synth_q1_kernel, tg_grid(ctx, n, 256, 8), 256, 0, n, first, seed, shipdate, returnflag, linestatus, quantity, extendedprice, discount, tax);
+    return TGPU_OK;
+}
