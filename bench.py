@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""bench.py — hash-join probe rows/s on the BASELINE.json workload (lineitem JOIN orders, synthetic SF100,
+BIGINT key), plus the Q1 GROUP-BY input rows/s, through the C ABI of libtrino_gpu.so.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's sm_100a operators
+  python bench.py --impl reference --gpus N ...            # the reference's CPU algorithm (C++ restatement, all host threads)
+  torchrun ... bench.py --gpus N ...                       # partitioned join: hash exchange over NCCL + local probe
+
+A "step" is one pass of the LookupJoinOperator over the whole probe side (N>1: PagePartitioner + all-to-all + probe).
+`value` is timed with inputs resident in HBM; `e2e` feeds HOST pages through the same operator calls and copies the
+result back to host memory inside the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+SEED_LINEITEM, SEED_ORDERS = 0x7C01, 0x7C02
+ALG_BYTES_PROBE_INDEX = 24          # 8 key + 12 table entry + 4 position
+ALG_BYTES_Q1_CODES = 38             # shipdate 4 + 4 x FLOAT64 32 + 2 INT8 key codes
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def reference_arm(args):
+    """The reference's CPU algorithm (oracle port: BigintPagesHash 3-phase batched probe + payload copy, T drivers)
+    on a bounded sample of the same workload.  Test infrastructure timed as the baseline; never on the product path."""
+    import oracle_lib as o
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    threads = o.hardware_threads()
+    sf = args.sf
+    n_orders = int(1_500_000 * sf)
+    rows = o.synth_lineitem_rows(n_orders)
+    sample = min(rows, args.cpu_sample_rows)
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, SEED_ORDERS, True)
+    payload = (okeys % 2557).astype(np.int32)
+    from trino_b200.page import Block, Page
+    t0 = time.time()
+    join = o.Join(Page(Block.bigint(okeys)), [0], force_default=2)
+    build_s = time.time() - t0
+    lkeys = o.synth_lineitem_keys(n_orders, 0, sample, SEED_LINEITEM, False)
+    times = []
+    for i in range(args.warmup + args.steps):
+        secs, pos, _ = join.probe_timed(lkeys, threads, payload)
+        if i >= args.warmup:
+            times.append(secs)
+    assert (pos >= 0).all()
+    t = float(np.mean(times))
+    value = sample / t
+    cpu = {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
+           "sample": f"{sample} of {rows} probe rows against the full {n_orders}-row build table (built in {build_s:.1f} s, untimed); {os.cpu_count()} logical CPUs"}
+    line = {"impl": "reference", "metric": "hash_join_probe_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": workload_config(args, n_orders, rows, 1), "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_orders, probe_rows, world):
+    return {"workload": f"lineitem JOIN orders hash join, synthetic SF{args.sf:g}, BIGINT join key, INNER, build payload o_orderdate (days, BIGINT), "
+                        f"probe payload l_extendedprice FLOAT64 (BASELINE.json configs[1])",
+            "build_rows_per_gpu": n_orders, "probe_rows_per_gpu": probe_rows, "probe_order": "orderkey-clustered" if not args.shuffle_probe else "shuffled",
+            "parallelism": f"hash-partitioned x{world}" if world > 1 else "single GPU",
+            "l2": "inputs (9.6 GB probe side, 4.3 GB table at SF100) are far larger than the 126 MB L2; no flush needed"}
+
+
+def device_col(ctx, nbytes):
+    return ctx.malloc(nbytes)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sf", type=float, default=100.0, help="TPC-H scale factor of the join workload per GPU")
+    ap.add_argument("--q1-sf", type=float, default=300.0, help="scale factor of the Q1 GROUP-BY side measurement (0 = skip)")
+    ap.add_argument("--shuffle-probe", action="store_true", help="variant B: uniformly shuffled probe keys")
+    ap.add_argument("--cpu-sample-rows", type=int, default=200_000_000)
+    ap.add_argument("--e2e-rows", type=int, default=0, help="probe rows fed from host per e2e step (0 = all)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank, world, local = dist_env()
+    from trino_b200 import abi
+    from trino_b200 import operators as ops
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = ops.Context(local)
+    lib = ctx.lib
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---------------- setup (untimed): synthetic columns in HBM, hash build
+    sf = args.sf
+    n_orders = int(1_500_000 * sf)                   # per GPU
+    probe_rows = lib.tgpu_synth_lineitem_rows(n_orders)
+    total_orders = n_orders * world
+    total_rows = lib.tgpu_synth_lineitem_rows(total_orders)
+    # every rank owns a contiguous range shard of the global tables
+    o_first = n_orders * rank
+    l_first = (total_rows // world) * rank
+    l_count = (total_rows // world) if rank < world - 1 else total_rows - l_first
+    d_okeys = ctx.malloc(n_orders * 8)
+    ctx.check(lib.tgpu_synth_orders_keys(ctx.h, total_orders, o_first, n_orders, SEED_ORDERS, 1, C.c_void_p(d_okeys)))
+    d_lkeys = ctx.malloc(l_count * 8)
+    d_lprice = ctx.malloc(l_count * 8)
+    ctx.check(lib.tgpu_synth_lineitem_keys(ctx.h, total_orders, l_first, l_count, SEED_LINEITEM, int(args.shuffle_probe), C.c_void_p(d_lkeys)))
+    # payload columns: o_orderdate = key % 2557 (INT32), l_extendedprice = key * 0.5 (FLOAT64); produced by the filter/project operator
+    def project(ptr, n, dtype_expr, out_type):
+        page = ops.DevicePage([ops.DeviceColumn(abi.INT64, ptr, n)], n)
+        prog = ops.PageProcessorProgram(None, [dtype_expr])
+        op = ops.FilterAndProjectOperatorFactory(ctx, prog).create_operator()
+        op.add_input(page)
+        out = op.get_output_device()
+        op.close()
+        return out
+    price_page = project(d_lkeys, l_count, ops.Call(abi.EX_MUL, ops.Call(abi.EX_CAST_BIGINT_TO_DOUBLE, ops.Col(0, abi.V_BIGINT)), ops.Const(0.5, abi.V_DOUBLE)), abi.FLOAT64)
+    d_lprice_col = price_page.column(0)
+    date_page = project(d_okeys, n_orders, ops.Call(abi.EX_MOD, ops.Col(0, abi.V_BIGINT), ops.Const(2557, abi.V_BIGINT)), abi.INT64)
+    d_odate_col = date_page.column(0)      # INT64 payload (8 B) — keeps the build payload a plain BIGINT column
+
+    build_page = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_okeys, n_orders), d_odate_col], n_orders)
+    probe_page = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_lkeys, l_count), d_lprice_col], l_count)
+
+    partitioner = None
+    if world > 1:
+        # co-locate build and probe by key: HashBucketFunction over orderkey, bucket == rank
+        idb = (C.c_uint8 * abi.COMM_ID_BYTES)()
+        if rank == 0:
+            ctx.check(lib.tgpu_comm_get_unique_id(C.cast(idb, C.c_void_p)))
+        import torch
+        t = torch.tensor(list(idb), dtype=torch.uint8, device=f"cuda:{local}")
+        dist.broadcast(t, 0)
+        idb = (C.c_uint8 * abi.COMM_ID_BYTES)(*t.cpu().tolist())
+        ctx.check(lib.tgpu_comm_init(ctx.h, C.cast(idb, C.c_void_p), rank, world))
+        partitioner = ops.PartitionedOutputOperatorFactory(ctx, [0], world).create_operator()
+        pp = abi.PP()
+        ctx.check(lib.tgpu_exchange_partitioned(ctx.h, partitioner.h, build_page.ref(), C.byref(pp)))
+        build_in = ops.DeviceOutputPage(ctx, pp)
+        build_page_local = build_in.as_device_page()
+    else:
+        build_page_local = build_page
+
+    bridge = ops.JoinBridge()
+    builder = ops.HashBuilderOperatorFactory(ctx, bridge, [0], [1], n_orders).create_operator()
+    t_build0 = time.time()
+    builder.add_input(build_page_local)
+    builder.finish()
+    ctx.synchronize()
+    build_s = time.time() - t_build0
+    lookup = bridge.lookup_source
+    probe_op = ops.LookupJoinOperatorFactory(ctx, bridge, abi.JOIN_INNER, False, [0], [0, 1]).create_operator()
+
+    out_rows_seen = [0]
+
+    def step():
+        if partitioner is not None:
+            pp = abi.PP()
+            ctx.check(lib.tgpu_exchange_partitioned(ctx.h, partitioner.h, probe_page.ref(), C.byref(pp)))
+            inp = ops.DeviceOutputPage(ctx, pp)
+            probe_op.add_input(inp.as_device_page())
+            out = probe_op.get_output_device()
+            out_rows_seen[0] = out.rows if out else 0
+            if out:
+                out.release()
+            inp.release()
+        else:
+            probe_op.add_input(probe_page)
+            out = probe_op.get_output_device()
+            out_rows_seen[0] = out.rows if out else 0
+            if out:
+                out.release()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = ctx.timer_stop_ms()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop()
+    barrier()
+    if dist is not None:
+        import torch
+        tt = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        rr = torch.tensor([float(out_rows_seen[0])], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(rr)
+        total_out = int(rr.item())
+    else:
+        total_out = out_rows_seen[0]
+    assert total_out == total_rows, f"join produced {total_out} rows, expected {total_rows} (100 % match rate)"
+    ms_per_step = ms / args.steps
+    value = total_rows / (ms_per_step * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (index-only probe), timed alone with CUDA events
+    roofline = None
+    if world == 1:
+        d_pos = ctx.malloc(l_count * 4)
+        keys_page = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_lkeys, l_count)], l_count)
+        for _ in range(3):
+            lookup.get_join_positions_device(keys_page, d_pos)
+        reps = 10
+        ctx.timer_start()
+        for _ in range(reps):
+            lookup.get_join_positions_device(keys_page, d_pos)
+        kms = ctx.timer_stop_ms() / reps
+        peak, peak_src = measured_peak()
+        achieved = ALG_BYTES_PROBE_INDEX * l_count / (kms * 1e-3) / 1e9
+        roofline = {"kernel": "join_probe_kernel<4,true>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_PROBE_INDEX, "rows_per_launch": l_count,
+                    "kernel_ms": kms, "kernel_rows_per_sec": l_count / (kms * 1e-3)}
+        ctx.free(d_pos)
+
+    # ---------------- Q1 GROUP-BY side measurement (BASELINE.json configs[2]) on rank 0 at N=1
+    q1 = None
+    if world == 1 and args.q1_sf > 0:
+        q1 = bench_q1(ctx, args)
+
+    # ---------------- end to end: host pages in, host result out, through the same operator calls
+    e2e = None
+    if world == 1:
+        e2e = bench_e2e(ctx, args, probe_op, d_lkeys, d_lprice_col.ptr, l_count)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, n_orders, probe_rows)
+
+    if rank == 0:
+        line = {"metric": "hash_join_probe_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": workload_config(args, n_orders, probe_rows, world), "gpu_launches": int(launches), "clocks": clocks,
+                "build_seconds": build_s, "output_rows_per_step": total_out}
+        if roofline:
+            line["roofline"] = roofline
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if e2e:
+            line["e2e"] = e2e
+        if q1:
+            line["groupby_q1"] = q1
+        print(json.dumps(line))
+    probe_op.close()
+    builder.close()
+    lookup.close()
+    if dist is not None:
+        dist.barrier()
+        ctx.check(lib.tgpu_comm_destroy(ctx.h))
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def bench_e2e(ctx, args, probe_op, d_keys, d_price, n):
+    """host -> device -> host through add_input / get_output / page_copy_to_host, pinned host memory"""
+    from trino_b200 import abi
+    from trino_b200 import operators as ops
+    from trino_b200.page import Block, Page
+    lib = ctx.lib
+    total = n if args.e2e_rows <= 0 else min(n, args.e2e_rows)
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        avail = 32 << 30
+    chunk = 64 << 20    # rows per host page
+    need = total * 16 + chunk * 24
+    if need > avail * 0.6:
+        total = int((avail * 0.6 - chunk * 24) // 16)
+    h_keys = ctx.pinned_empty(total, np.int64)
+    h_price = ctx.pinned_empty(total, np.float64)
+    ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(h_keys.ctypes.data), C.c_void_p(d_keys), total * 8))
+    ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(h_price.ctypes.data), C.c_void_p(d_price), total * 8))
+    # result landing zone (pinned): probe key, probe price, build payload
+    o_keys = ctx.pinned_empty(chunk, np.int64)
+    o_price = ctx.pinned_empty(chunk, np.float64)
+    o_date = ctx.pinned_empty(chunk, np.int64)
+    valid = [np.empty(chunk // 8 + 8, np.uint8) for _ in range(3)]
+    host_cols = (abi.Column * 3)()
+    for c, (arr, t) in enumerate(((o_keys, abi.INT64), (o_price, abi.FLOAT64), (o_date, abi.INT64))):
+        host_cols[c].type, host_cols[c].data, host_cols[c].validity = t, arr.ctypes.data, valid[c].ctypes.data
+
+    def one_pass():
+        rows = 0
+        for lo in range(0, total, chunk):
+            hi = min(total, lo + chunk)
+            page = Page(Block(abi.INT64, h_keys[lo:hi]), Block(abi.FLOAT64, h_price[lo:hi]))
+            probe_op.add_input(page)
+            pp = abi.PP()
+            ctx.check(lib.tgpu_op_get_output(probe_op.h, C.byref(pp)))
+            if pp:
+                m = pp.contents.num_rows
+                hp = abi.Page(3, 0, m, C.cast(host_cols, C.POINTER(abi.Column)))
+                ctx.check(lib.tgpu_page_copy_to_host(ctx.h, pp, C.byref(hp)))
+                lib.tgpu_page_release(ctx.h, pp)
+                rows += m
+        return rows
+
+    one_pass()
+    reps = 2
+    t0 = time.time()
+    for _ in range(reps):
+        rows = one_pass()
+    dt = (time.time() - t0) / reps
+    assert rows == total
+    assert (o_date[:8] == (o_keys[:8] % 2557)).all()
+    return {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": int(total * 16), "d2h_bytes_per_step": int(total * 24),
+            "rows_per_step": int(total), "host_page_rows": chunk, "timing": "wall clock around add_input(host page) + get_output + page_copy_to_host, pinned memory"}
+
+
+def bench_q1(ctx, args):
+    """TPC-H Q1 fused scan+filter+project+GROUP BY over device-resident synthetic lineitem columns"""
+    from q1 import q1_factory
+    from trino_b200 import abi
+    from trino_b200 import operators as ops
+    lib = ctx.lib
+    n = int(6_000_000 * args.q1_sf)
+    spec = [(abi.INT32, 4), (abi.INT8, 1), (abi.INT8, 1), (abi.FLOAT64, 8), (abi.FLOAT64, 8), (abi.FLOAT64, 8), (abi.FLOAT64, 8)]
+    ptrs = [ctx.malloc(n * sz) for _, sz in spec]
+    ctx.check(lib.tgpu_synth_lineitem_q1(ctx.h, n, 0, SEED_LINEITEM, *[C.c_void_p(p) for p in ptrs]))
+    page = ops.DevicePage([ops.DeviceColumn(t, p, n) for (t, _), p in zip(spec, ptrs)], n)
+    factory = q1_factory(ctx, fused=True)
+
+    def run():
+        op = factory.create_operator()
+        op.add_input(page)
+        op.finish()
+        out = op.get_output()
+        op.close()
+        return out
+
+    for _ in range(2):
+        out = run()
+    reps = 5
+    ctx.timer_start()
+    for _ in range(reps):
+        out = run()
+    ms = ctx.timer_stop_ms() / reps
+    rows = out.rows()
+    peak, peak_src = measured_peak()
+    achieved = ALG_BYTES_Q1_CODES * n / (ms * 1e-3) / 1e9
+    for p in ptrs:
+        ctx.free(p)
+    return {"metric": "groupby_input_rows_per_sec", "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "rows": n, "groups": len(rows),
+            "config": f"TPC-H Q1 GROUP-BY, synthetic SF{args.q1_sf:g} lineitem, INT8 key codes, fused filter+project+aggregate (BASELINE.json configs[2])",
+            "roofline": {"kernel": "agg_small_kernel (+merge)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_Q1_CODES, "traffic": None},
+            "result_count_order": [int(r[-1]) for r in rows]}
+
+
+def cpu_baseline(args, n_orders, probe_rows):
+    import oracle_lib as o
+    from trino_b200.page import Block, Page
+    threads = o.hardware_threads()
+    sample = min(probe_rows, args.cpu_sample_rows)
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, SEED_ORDERS, True)
+    payload = (okeys % 2557).astype(np.int32)
+    t0 = time.time()
+    join = o.Join(Page(Block.bigint(okeys)), [0], force_default=2)
+    build_s = time.time() - t0
+    lkeys = o.synth_lineitem_keys(n_orders, 0, sample, SEED_LINEITEM, int(args.shuffle_probe))
+    join.probe_timed(lkeys[: sample // 8], threads, payload)
+    secs, pos, _ = join.probe_timed(lkeys, threads, payload)
+    join.close()
+    out = {"value": sample / secs, "unit": "rows/s", "cores": threads, "kind": "port",
+           "sample": f"{sample} of {probe_rows} probe rows against the full {n_orders}-row build table (CPU build {build_s:.1f} s, untimed), "
+                     f"BigintPagesHash 3-phase batched probe on 8192-row pages + build payload copy, {threads} threads"}
+    if args.q1_sf > 0:
+        n = 60_000_000
+        cols = o.synth_lineitem_q1(n, 0, SEED_LINEITEM)
+        secs, rows = o.q1_run(cols, 10471, threads)
+        out["groupby_q1"] = {"value": n / secs, "unit": "rows/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} synthetic lineitem rows, filter -> 7 projection loops -> FlatHash group ids -> 8 accumulator passes, {threads} partial drivers + final merge"}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

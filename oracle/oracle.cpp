@@ -593,7 +593,7 @@ orc_join* orc_join_build(const tgpu_page* build, const int32_t* key_channels, in
     j->build_page.columns = j->build_cols.data();
     auto cols = views(&j->build_page, key_channels, num_keys);
     // JoinHashSupplier.getPagesHashType :162-168
-    j->bigint = num_keys == 1 && cols[0].type == TGPU_INT64 && j->n <= (1 << 20) && !force_default;
+    j->bigint = num_keys == 1 && cols[0].type == TGPU_INT64 && ((j->n <= (1 << 20) && !force_default) || force_default == 2);
     int32_t hash_size = orc_join_hash_array_size(j->n);
     j->mask = hash_size - 1;
     j->keys.assign(hash_size, -1);
@@ -711,7 +711,8 @@ int64_t orc_join_expand(const orc_join* j, const int32_t* jp, int64_t n, int32_t
     return count;
 }
 
-double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_t n, int32_t threads, int32_t* out)
+double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_t n, int32_t threads, int32_t* out,
+                            const int32_t* build_payload, int32_t* out_payload)
 {
     // T probe drivers over 8192-row pages sharing one table; 3-phase batched probe of
     // BigintPagesHash.getAddressIndex(int[], Page) :184-268 (also the shape of DefaultPagesHash :204-282)
@@ -744,6 +745,12 @@ double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_
                         if (j->values[j->keys[pos]] == in[idx]) { res[idx] = j->keys[pos]; break; }
                         pos = (pos + 1) & j->mask;
                     }
+                }
+                // PageJoiner.joinCurrentPosition :203-227 + LookupJoinPageBuilder.appendRow :89-97: one output row per
+                // match, build-side column copied row by row (probe-side columns are views: :131-151)
+                if (build_payload) {
+                    int32_t* po = out_payload + base;
+                    for (int32_t i = 0; i < cnt; i++) po[i] = res[i] >= 0 ? build_payload[res[i]] : 0;
                 }
             }
         });

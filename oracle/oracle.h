@@ -68,7 +68,8 @@ void orc_agg_minmax_bigint(const int32_t* gids, int64_t n, const int64_t* v, con
 /* ---- hash join (M/operator/join/BigintPagesHash.java, DefaultPagesHash.java, ArrayPositionLinks.java, JoinHash.java) */
 typedef struct orc_join orc_join;
 /* build over one concatenated build page; address index == row number (M/operator/SyntheticAddress.java).
- * force_default != 0 selects DefaultPagesHash even for a single BIGINT key (as JoinHashSupplier.java:162-168 does above 2^20 rows) */
+ * force_default == 1 selects DefaultPagesHash even for a single BIGINT key (as JoinHashSupplier.java:162-168 does above 2^20 rows);
+ * force_default == 2 keeps the BigintPagesHash layout at any size (the timing leg: it is the faster of the two on a CPU) */
 orc_join* orc_join_build(const tgpu_page* build, const int32_t* key_channels, int32_t num_keys, int32_t force_default);
 void orc_join_destroy(orc_join* j);
 int32_t orc_join_hash_size(const orc_join* j);
@@ -84,7 +85,9 @@ int64_t orc_join_expand(const orc_join* j, const int32_t* join_positions, int64_
                         int32_t* out_probe, int32_t* out_build, int64_t capacity);
 /* multi-threaded probe timing leg for the CPU baseline: `threads` workers each take 8192-row pages
  * (BigintPagesHash.getAddressIndex(int[],Page) 3-phase batching); returns seconds */
-double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_t n, int32_t threads, int32_t* out);
+double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_t n, int32_t threads, int32_t* out,
+                            const int32_t* build_payload, int32_t* out_payload);
+/* force BigintPagesHash layout (keys[] + values[]) regardless of size: the timing leg probes BIGINT keys */
 
 /* ---- PagePartitioner (M/operator/output/PagePartitioner.java:133-162,229-433) */
 /* partition id per row: bucketToPartition[processRawHash(rowHash, bucketCount)] */

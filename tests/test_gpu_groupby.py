@@ -1,0 +1,265 @@
+"""GPU parity: GroupByHash ids (first-seen order) and HashAggregationOperator results vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from helpers import rows_equal
+from q1 import CUTOFF, q1_gpu_rows
+from trino_b200 import abi
+from trino_b200 import operators as ops
+from trino_b200.page import Block, DictionaryBlock, Page, RunLengthEncodedBlock
+
+pytestmark = pytest.mark.gpu
+A = ops.Aggregator
+
+
+# ---------------------------------------------------------------- GroupByHash
+def test_group_ids_reference_cases(ctx):
+    # TestGroupByHash.testGetGroupIds :187-204 (MAX_GROUP_ID shortened to 60 single-row pages x 2 tries)
+    g = ops.GroupByHash(ctx, [0], 100)
+    for tries in range(2):
+        for value in range(60):
+            ids = g.get_group_ids(Page(Block.bigint([value])))
+            assert list(ids) == [value]
+            assert g.get_group_count() == (value + 1 if tries == 0 else 60)
+    g.close()
+    # testNullGroup :163-184 incl. the forced rehash
+    g = ops.GroupByHash(ctx, [0], 100)
+    assert list(g.get_group_ids(Page(Block.bigint([0, None])))) == [0, 1]
+    ids = g.get_group_ids(Page(Block.bigint(np.arange(1, 132749))))
+    assert (ids == np.arange(2, 132750)).all()
+    assert list(g.get_group_ids(Page(Block.bigint([None])))) == [1]
+    g.close()
+    # testDictionaryInputPage :133-160 / testRunLengthEncodedInputPage :111-131
+    g = ops.GroupByHash(ctx, [0], 100)
+    assert list(g.get_group_ids(Page(DictionaryBlock(Block.bigint([0, 1]), [0, 0, 1, 1])))) == [0, 0, 1, 1]
+    assert g.get_group_count() == 2
+    g.close()
+    g = ops.GroupByHash(ctx, [0], 100)
+    assert list(g.get_group_ids(Page(RunLengthEncodedBlock(Block.bigint([0]), 2)))) == [0, 0]
+    assert g.get_group_count() == 1
+    g.close()
+
+
+@pytest.mark.parametrize("card,expected", [(50, 16), (20000, 100), (300000, 10)])
+def test_group_ids_random_pages_match_oracle(ctx, card, expected):
+    rng = np.random.default_rng(card)
+    g = ops.GroupByHash(ctx, [0], expected)
+    og = o.GroupByHash(1, expected)
+    for n in (1000, 1, 65536, 300000):
+        page = Page(Block.bigint(rng.integers(-card, card, n), rng.random(n) < 0.01))
+        assert (g.get_group_ids(page) == og.get_group_ids(page, [0])).all()
+        assert g.get_group_count() == og.group_count()
+    g.close(); og.close()
+
+
+def test_group_ids_packed_multi_column_and_other_types(ctx):
+    rng = np.random.default_rng(17)
+    n = 50000
+    page = Page(Block.integer(rng.integers(0, 300, n), rng.random(n) < 0.02), Block.tinyint(rng.integers(65, 70, n)), Block.smallint(rng.integers(-3, 3, n), rng.random(n) < 0.02))
+    g = ops.GroupByHash(ctx, [0, 1, 2], 1000)
+    og = o.GroupByHash(0, 1000)
+    assert (g.get_group_ids(page) == og.get_group_ids(page, [0, 1, 2])).all()
+    g.close(); og.close()
+    # DOUBLE key: IDENTICAL semantics, INT64_MIN-valued key, NULL
+    d = Block.double([0.0, -0.0, float("nan"), 1.0, float("nan"), None, 1.0, None])
+    g = ops.GroupByHash(ctx, [0], 10)
+    og = o.GroupByHash(0, 10)
+    assert list(g.get_group_ids(Page(d))) == list(og.get_group_ids(Page(d), [0])) == [0, 0, 1, 2, 1, 3, 2, 3]
+    g.close(); og.close()
+    k = Block.bigint([-2**63, 5, -2**63, None, 5])
+    g = ops.GroupByHash(ctx, [0], 10)
+    assert list(g.get_group_ids(Page(k))) == [0, 1, 0, 2, 1]
+    g.close()
+    with pytest.raises(abi.TrinoGpuError) as e:
+        ops.GroupByHash(ctx, [0, 1], 10).get_group_ids(Page(Block.bigint([1]), Block.bigint([2])))
+    assert e.value.code == abi.ERR_NOT_SUPPORTED
+
+
+# ---------------------------------------------------------------- aggregation
+def _oracle_agg(pages, key_channels, aggs):
+    """group-id order rows: keys then aggregate values (None = NULL), sequential left fold like the reference"""
+    lib = o.load()
+    og = o.GroupByHash(0, 16)
+    state = []
+    keyrows = {}
+    for page in pages:
+        ids = og.get_group_ids(page, key_channels)
+        G = og.group_count()
+        for i, gid in enumerate(ids):
+            if gid not in keyrows:
+                keyrows[int(gid)] = tuple(page.get_block(c).flatten().get(i) for c in key_channels)
+        for ai, (fn, ch, mask) in enumerate(aggs):
+            if len(state) <= ai:
+                state.append({"sum": np.zeros(0), "cnt": np.zeros(0, np.int64), "isum": np.zeros(0, np.int64), "nn": np.zeros(0, np.uint8), "acc": np.zeros(0), "iacc": np.zeros(0, np.int64)})
+            st = state[ai]
+            for k in st:
+                if len(st[k]) < G:
+                    st[k] = np.concatenate([st[k], np.zeros(G - len(st[k]), st[k].dtype)])
+            blk = page.get_block(ch).flatten() if ch >= 0 else None
+            valid = None
+            if blk is not None and blk.nulls is not None:
+                valid = np.packbits(~blk.nulls, bitorder="little")
+            sel = None
+            if mask >= 0:
+                mb = page.get_block(mask).flatten()
+                sel = ((mb.values != 0) & (~mb.nulls if mb.nulls is not None else True)).astype(np.uint8)
+            n = page.position_count
+            P = o._p
+            ids32 = np.ascontiguousarray(ids, np.int32)
+            is_dbl = blk is not None and blk.type == abi.FLOAT64
+            vals = None if blk is None else np.ascontiguousarray(blk.values.astype(np.float64 if is_dbl else np.int64))
+            if fn == abi.AGG_COUNT_STAR:
+                lib.orc_agg_count(P(ids32), n, None, P(sel), P(st["cnt"]))
+            elif fn == abi.AGG_COUNT:
+                lib.orc_agg_count(P(ids32), n, P(valid), P(sel), P(st["cnt"]))
+            elif fn == abi.AGG_SUM and is_dbl:
+                lib.orc_agg_sum_double(P(ids32), n, P(vals), P(valid), P(sel), P(st["sum"]), P(st["nn"]))
+            elif fn == abi.AGG_SUM:
+                assert lib.orc_agg_sum_bigint(P(ids32), n, P(vals), P(valid), P(sel), P(st["isum"]), P(st["nn"])) == 0
+            elif fn == abi.AGG_AVG:
+                lib.orc_agg_avg_double(P(ids32), n, P(vals.astype(np.float64)), P(valid), P(sel), P(st["sum"]), P(st["cnt"]))
+            elif is_dbl:
+                lib.orc_agg_minmax_double(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["acc"]), P(st["nn"]))
+            else:
+                lib.orc_agg_minmax_bigint(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["iacc"]), P(st["nn"]))
+            st["dbl"] = is_dbl
+    G = og.group_count()
+    rows = []
+    for g in range(G):
+        r = list(keyrows[g])
+        for ai, (fn, ch, mask) in enumerate(aggs):
+            st = state[ai]
+            if fn in (abi.AGG_COUNT_STAR, abi.AGG_COUNT):
+                r.append(int(st["cnt"][g]))
+            elif fn == abi.AGG_SUM:
+                r.append(None if not st["nn"][g] else (float(st["sum"][g]) if st["dbl"] else int(st["isum"][g])))
+            elif fn == abi.AGG_AVG:
+                r.append(None if st["cnt"][g] == 0 else float(st["sum"][g]) / float(st["cnt"][g]))
+            else:
+                r.append(None if not st["nn"][g] else (float(st["acc"][g]) if st["dbl"] else int(st["iacc"][g])))
+        rows.append(tuple(r))
+    og.close()
+    return rows
+
+
+def _gpu_agg(ctx, pages, key_channels, aggs, step=abi.STEP_SINGLE, expected=100, max_partial=0):
+    f = ops.HashAggregationOperatorFactory(ctx, key_channels, step, [A(fn, ch, m) for fn, ch, m in aggs], expected, max_partial)
+    op = f.create_operator()
+    out = ops.drive(op, pages)
+    op.close()
+    rows = []
+    for p in out:
+        rows.extend(p.rows())
+    return rows
+
+
+AGGS = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_COUNT, 1, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_MAX, 1, -1),
+        (abi.AGG_SUM, 2, -1), (abi.AGG_AVG, 2, -1), (abi.AGG_MIN, 2, -1), (abi.AGG_MAX, 2, -1), (abi.AGG_SUM, 1, 3), (abi.AGG_COUNT_STAR, -1, 3)]
+
+
+def _agg_pages(rng, card, sizes):
+    pages = []
+    for n in sizes:
+        pages.append(Page(Block.bigint(rng.integers(0, card, n), rng.random(n) < 0.01),
+                          Block.double(rng.normal(size=n) * 100, rng.random(n) < 0.1),
+                          Block.bigint(rng.integers(-1000, 1000, n), rng.random(n) < 0.1),
+                          Block.boolean(rng.random(n) < 0.5, rng.random(n) < 0.05)))
+    return pages
+
+
+@pytest.mark.parametrize("card", [5, 40, 3000])
+def test_aggregation_matches_oracle(ctx, card):
+    # small cardinalities run the fused shared-memory path, large ones the global-table path; both must give the
+    # reference's rows in first-seen group order (DOUBLE aggregates within 1e-6 relative, everything else exact)
+    rng = np.random.default_rng(card)
+    pages = _agg_pages(rng, card, (5000, 1, 40000, 333))
+    got = _gpu_agg(ctx, pages, [0], AGGS)
+    want = _oracle_agg(pages, [0], AGGS)
+    assert rows_equal(got, want, rel=1e-6)
+    assert [r[0] for r in got] == [r[0] for r in want]
+    assert [(r[1], r[4], r[7], r[12]) for r in got] == [(r[1], r[4], r[7], r[12]) for r in want]     # counts and BIGINT sum exact
+
+
+def test_small_path_spills_into_general_path(ctx):
+    # first page has few groups (path S), the next one thousands: state must migrate without losing ids or sums
+    rng = np.random.default_rng(99)
+    pages = _agg_pages(rng, 6, (2000,)) + _agg_pages(rng, 5000, (30000,)) + _agg_pages(rng, 6, (100,))
+    got = _gpu_agg(ctx, pages, [0], AGGS, expected=16)
+    want = _oracle_agg(pages, [0], AGGS)
+    assert rows_equal(got, want, rel=1e-6)
+
+
+def test_partial_then_final_equals_single(ctx):
+    rng = np.random.default_rng(5)
+    pages = _agg_pages(rng, 30, (4000, 4000))
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_SUM, 2, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_MAX, 2, -1), (abi.AGG_COUNT, 2, -1)]
+    single = _gpu_agg(ctx, pages, [0], aggs)
+    # two PARTIAL operators (one page each) -> FINAL over the intermediate state columns
+    f = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, [A(fn, ch, m) for fn, ch, m in aggs], 100)
+    partial_pages = []
+    for p in pages:
+        op = f.create_operator()
+        partial_pages += ops.drive(op, [p])
+        op.close()
+    assert partial_pages[0].channel_count == 1 + 8      # avg carries (count, sum)
+    final_aggs = [A(abi.AGG_COUNT_STAR, 1), A(abi.AGG_SUM, 2), A(abi.AGG_AVG, 3), A(abi.AGG_SUM, 5), A(abi.AGG_MIN, 6), A(abi.AGG_MAX, 7), A(abi.AGG_COUNT, 8)]
+    ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, final_aggs, 100)
+    op = ff.create_operator()
+    out = ops.drive(op, partial_pages)
+    op.close()
+    final = [r for p in out for r in p.rows()]
+    assert rows_equal(final, single, rel=1e-9)
+
+
+def test_partial_flush_when_memory_exceeded(ctx):
+    # HashAggregationOperator.needsInput :346-355 / getOutput :478-483: a full partial builder flushes and restarts
+    rng = np.random.default_rng(6)
+    pages = _agg_pages(rng, 2000, (10000, 10000))
+    f = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, [A(abi.AGG_COUNT_STAR)], 100, max_partial_memory=1024)
+    op = f.create_operator()
+    op.add_input(pages[0])
+    assert not op.needs_input()
+    first = op.get_output()
+    assert first is not None and op.needs_input()
+    op.add_input(pages[1])
+    second = op.get_output()
+    op.finish()
+    assert op.get_output() is None and op.is_finished()
+    total = sum(r[1] for r in first.rows()) + sum(r[1] for r in second.rows())
+    assert total == 20000
+    op.close()
+
+
+def test_bigint_sum_overflow_raises(ctx):
+    page = Page(Block.bigint([1, 1]), Block.bigint([2**62, 2**62]))
+    with pytest.raises(abi.TrinoGpuError) as e:
+        _gpu_agg(ctx, [page], [0], [(abi.AGG_SUM, 1, -1)])
+    assert e.value.code == abi.ERR_NUMERIC_VALUE_OUT_OF_RANGE
+
+
+def test_empty_input_and_all_null_inputs(ctx):
+    assert _gpu_agg(ctx, [], [0], [(abi.AGG_COUNT_STAR, -1, -1)]) == []
+    page = Page(Block.bigint([7, 7, 8]), Block.double([None, None, 1.0]))
+    rows = _gpu_agg(ctx, [page], [0], [(abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_COUNT, 1, -1), (abi.AGG_MIN, 1, -1)])
+    assert rows == [(7, None, None, 0, None), (8, 1.0, 1.0, 1, 1.0)]
+
+
+# ---------------------------------------------------------------- Q1
+@pytest.mark.parametrize("fused", [True, False])
+def test_q1_matches_oracle(ctx, fused):
+    cols = o.synth_lineitem_q1(1_000_000, 0, 0x7C01)
+    _, want = o.q1_run(cols, CUTOFF, 1)
+    for page_rows in (None, 250_000):
+        got = q1_gpu_rows(ctx, cols, CUTOFF, page_rows, fused)
+        assert [(g[0], g[1], g[9]) for g in got] == [(w[0], w[1], w[9]) for w in want]      # groups, first-seen order, counts: exact
+        for g, w in zip(got, want):
+            for a, b in zip(g[2:9], w[2:9]):
+                assert abs(a - b) <= 1e-6 * abs(b)                                           # north_star: 1e-6 relative for DOUBLE
+
+
+def test_q1_fused_is_run_to_run_deterministic(ctx):
+    cols = o.synth_lineitem_q1(500_000, 0, 0x7C01)
+    a = q1_gpu_rows(ctx, cols, CUTOFF)
+    b = q1_gpu_rows(ctx, cols, CUTOFF)
+    assert a == b

@@ -1,0 +1,150 @@
+"""GPU parity: HashBuilderOperator / LookupJoinOperator through the C ABI vs the CPU oracle (bit-exact rows and order)."""
+import numpy as np
+import pytest
+
+import oracle_lib as o
+from helpers import gpu_join_rows, oracle_join_rows, reference_cases, rows_equal
+from trino_b200 import abi
+from trino_b200 import operators as ops
+from trino_b200.page import Block, DictionaryBlock, Page, RunLengthEncodedBlock
+
+pytestmark = pytest.mark.gpu
+
+
+def _build_lookup(ctx, build_pages, key=0, out=()):
+    bridge = ops.JoinBridge()
+    b = ops.HashBuilderOperatorFactory(ctx, bridge, [key], list(out)).create_operator()
+    for p in build_pages:
+        b.add_input(p)
+    b.finish()
+    return b, bridge.lookup_source
+
+
+def test_reference_join_cases(ctx):
+    for case in reference_cases()["join"]:
+        build = Page(Block.bigint(case["build"])) if case["build"] else Page(Block.bigint([]), position_count=0)
+        probe = Page(Block.bigint(case["probe"]))
+        jt = abi.JOIN_INNER if case["join_type"] == "inner" else abi.JOIN_PROBE_OUTER
+        rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], jt, case["single_match"])
+        assert rows == [tuple(r) for r in case["expected"]], case["source"]
+
+
+def test_probe_outer_sequence_case(ctx):
+    c = reference_cases()["probe_outer_sequence"]
+    b0, b1, b2 = c["build_initial"]
+    p0, p1, p2 = c["probe_initial"]
+    nb, npr = c["build_rows"], c["probe_rows"]
+    build = Page(*[Block.bigint([x + i for i in range(nb)]) for x in (b0, b1, b2)])
+    probe = Page(*[Block.bigint([x + i for i in range(npr)]) for x in (p0, p1, p2)])
+    rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1, 2], [0, 1, 2], abi.JOIN_PROBE_OUTER, False)
+    want = oracle_join_rows(build, probe, 0, 0, [0, 1, 2], [0, 1, 2], abi.JOIN_PROBE_OUTER, False)
+    assert rows == want
+    assert rows[0] == (20, 1020, 2020, 20, 30, 40) and rows[-1] == (34, 1034, 2034, None, None, None)
+
+
+@pytest.mark.parametrize("join_type,single", [(abi.JOIN_INNER, False), (abi.JOIN_PROBE_OUTER, False), (abi.JOIN_INNER, True), (abi.JOIN_PROBE_OUTER, True)])
+def test_random_duplicates_and_nulls(ctx, join_type, single):
+    rng = np.random.default_rng(42)
+    nb, npr = 5000, 20000
+    bk = rng.integers(0, 1500, nb)
+    build = Page(Block.bigint(bk, rng.random(nb) < 0.05), Block.double(rng.normal(size=nb), rng.random(nb) < 0.1), Block.integer(rng.integers(-9, 9, nb)))
+    pk = rng.integers(0, 2000, npr)
+    probe = Page(Block.double(rng.normal(size=npr)), Block.bigint(pk, rng.random(npr) < 0.05), Block.varchar(["s%d" % (i % 13) if i % 11 else None for i in range(npr)]))
+    got = gpu_join_rows(ctx, [build], [probe], 0, 1, [0, 1, 2], [1, 2], join_type, single)
+    want = oracle_join_rows(build, probe, 0, 1, [0, 1, 2], [1, 2], join_type, single)
+    assert rows_equal(got, want)
+
+
+def test_multi_page_build_and_probe_pages(ctx):
+    rng = np.random.default_rng(7)
+    chunks = [rng.integers(0, 3000, n) for n in (1000, 1, 4096, 777)]
+    build_pages = [Page(Block.bigint(c), Block.bigint(c * 10)) for c in chunks]
+    whole = np.concatenate(chunks)
+    build = Page(Block.bigint(whole), Block.bigint(whole * 10))
+    probes = [Page(Block.bigint(rng.integers(0, 3500, n))) for n in (8192, 100, 1)]
+    got = gpu_join_rows(ctx, build_pages, probes, 0, 0, [0], [0, 1], abi.JOIN_INNER, False)
+    want = []
+    for p in probes:
+        want += oracle_join_rows(build, p, 0, 0, [0], [0, 1], abi.JOIN_INNER, False)
+    assert got == want
+
+
+def test_other_key_types_and_encodings(ctx):
+    rng = np.random.default_rng(9)
+    # INTEGER keys
+    build = Page(Block.integer(rng.integers(-50, 50, 300)))
+    probe = Page(Block.integer(rng.integers(-60, 60, 1000), rng.random(1000) < 0.1))
+    assert gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], abi.JOIN_INNER, False) == oracle_join_rows(build, probe, 0, 0, [0], [0], abi.JOIN_INNER, False)
+    # DOUBLE keys: -0.0 == +0.0, NaN never matches
+    build = Page(Block.double([0.0, 1.5, float("nan"), 2.5]))
+    probe = Page(Block.double([-0.0, float("nan"), 1.5, 3.0]))
+    got = gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], abi.JOIN_PROBE_OUTER, False)
+    want = oracle_join_rows(build, probe, 0, 0, [0], [0], abi.JOIN_PROBE_OUTER, False)
+    assert rows_equal(got, want) and got[0][1] == 0.0 and got[1][1] is None
+    # dictionary / RLE probe keys are values, not encodings
+    build = Page(Block.bigint([10, 20, 30]))
+    probe = Page(DictionaryBlock(Block.bigint([20, 99, 10]), [0, 1, 2, 2, 0]))
+    assert gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], abi.JOIN_INNER, False) == [(20, 20), (10, 10), (10, 10), (20, 20)]
+    probe = Page(RunLengthEncodedBlock(Block.bigint([30]), 4))
+    assert gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], abi.JOIN_INNER, False) == [(30, 30)] * 4
+    # the INT64_MIN key lives outside the table
+    mn = -2**63
+    build = Page(Block.bigint([mn, 5, mn]))
+    probe = Page(Block.bigint([5, mn, 7]))
+    assert gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], abi.JOIN_INNER, False) == oracle_join_rows(build, probe, 0, 0, [0], [0], abi.JOIN_INNER, False)
+
+
+def test_positions_and_links_match_oracle(ctx):
+    rng = np.random.default_rng(3)
+    bk = rng.integers(0, 40000, 100000)
+    build = Page(Block.bigint(bk, rng.random(100000) < 0.01))
+    b, lk = _build_lookup(ctx, [build])
+    oj = o.Join(build, [0])
+    probe = Page(Block.bigint(rng.integers(0, 50000, 300000), rng.random(300000) < 0.01))
+    assert (lk.get_join_positions(probe) == oj.positions(probe, [0])).all()
+    assert lk.has_position_links() and oj.has_links()
+    assert (lk.position_links() == oj.links()).all()
+    assert lk.get_join_position_count() == 100000
+    oj.close(); b.close(); lk.close()
+
+
+def test_synthetic_lineitem_orders_full_match(ctx):
+    # configs[1] shape at 1/100 scale: every probe row finds its order; positions equal the oracle's
+    n_orders = 1_500_000
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, 0x7C02, True)
+    rows = o.synth_lineitem_rows(n_orders)
+    lkeys = o.synth_lineitem_keys(n_orders, 0, rows, 0x7C01, False)
+    build = Page(Block.bigint(okeys))
+    b, lk = _build_lookup(ctx, [build])
+    pos = lk.get_join_positions(Page(Block.bigint(lkeys)))
+    assert not lk.has_position_links()
+    assert (pos >= 0).all()
+    assert (okeys[pos] == lkeys).all()                      # size-independent property: matched build key == probe key
+    oj = o.Join(build, [0], force_default=True)             # DefaultPagesHash is what the reference uses above 2^20 rows
+    assert (pos[:2_000_000] == oj.positions(Page(Block.bigint(lkeys[:2_000_000])), [0])).all()
+    oj.close(); b.close(); lk.close()
+
+
+def test_operator_protocol(ctx):
+    bridge = ops.JoinBridge()
+    b = ops.HashBuilderOperatorFactory(ctx, bridge, [0], []).create_operator()
+    assert b.needs_input() and not b.is_finished()
+    b.add_input(Page(Block.bigint([1, 2])))
+    b.finish(); b.finish()                                  # finish() is re-entrant (Driver.java:380-388)
+    assert not b.needs_input() and b.is_finished()
+    with pytest.raises(abi.TrinoGpuError) as e:
+        b.add_input(Page(Block.bigint([3])))
+    assert e.value.code == abi.ERR_ILLEGAL_STATE
+    j = ops.LookupJoinOperatorFactory(ctx, bridge, abi.JOIN_INNER, False, [0], [0]).create_operator()
+    assert j.needs_input() and j.get_output() is None
+    j.add_input(Page(Block.bigint([2, 2, 9])))
+    assert not j.needs_input()
+    out = j.get_output()
+    assert out.rows() == [(2,), (2,)]
+    assert j.needs_input()
+    j.finish()
+    assert j.is_finished()
+    with pytest.raises(abi.TrinoGpuError) as e:
+        ops.HashBuilderOperatorFactory(ctx, ops.JoinBridge(), [0, 1], []).create_operator()
+    assert e.value.code == abi.ERR_NOT_SUPPORTED
+    j.close(); b.close(); bridge.lookup_source.close()

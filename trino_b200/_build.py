@@ -1,4 +1,4 @@
-"""Build recipe for libtrino_gpu.so (sm_100a) and the CPU oracle.
+"""Build recipe for libtrino_gpu.so (sm_100a).
 
 `python -m trino_b200._build` or `__graft_entry__.build()`.  nvcc cross-compiles without a GPU.
 The library is built IN-TREE (trino_b200/libtrino_gpu.so) so that it travels to the GPU box.
@@ -56,17 +56,6 @@ def build_gpu(force=False, verbose=False):
     return LIB
 
 
-def build_oracle(force=False):
-    odir = os.path.join(ROOT, "oracle")
-    lib = os.path.join(odir, "liboracle.so")
-    deps = [os.path.join(odir, "oracle.cpp"), os.path.join(odir, "oracle.h"), os.path.join(ROOT, "include", "trino_gpu.h")]
-    if not force and _newer(lib, deps):
-        return lib
-    subprocess.check_call(["make", "-C", odir, "-B", "liboracle.so"])
-    return lib
-
-
 if __name__ == "__main__":
     build_gpu(force="--force" in sys.argv, verbose=True)
-    build_oracle(force="--force" in sys.argv)
     print(LIB)

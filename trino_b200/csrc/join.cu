@@ -285,6 +285,7 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
 struct JoinBuildOp : tgpu_op {
     std::vector<int32_t> key_channels, output_channels;
     std::vector<DevPage> chunks;     // key column + output columns of every input page
+    std::vector<int32_t> col_types;  // types of [key, outputs...] as first seen (an empty build still needs them)
     int64_t rows = 0;
     bool finishing = false;
     tgpu_lookup* lookup = nullptr;
@@ -297,6 +298,16 @@ struct JoinBuildOp : tgpu_op {
     int add_input(const tgpu_page* page) override
     {
         // HashBuilderOperator.addInput :253-277 -> PagesIndex.addPage :224-256
+        if (col_types.empty()) {
+            auto type_of = [&](int32_t ch) -> int32_t {
+                if (ch < 0 || ch >= page->num_columns) return 0;
+                const tgpu_column* c = &page->columns[ch];
+                while ((c->type == TGPU_DICT32 || c->type == TGPU_RLE) && c->dictionary) c = c->dictionary;
+                return c->type;
+            };
+            col_types.push_back(type_of(key_channels[0]));
+            for (int32_t ch : output_channels) col_types.push_back(type_of(ch));
+        }
         if (page->num_rows == 0) return TGPU_OK;
         if (rows + page->num_rows > (int64_t)INT32_MAX)
             return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of pages index cannot exceed 2 billion entries");   // PagesIndex.java:247-250
@@ -363,7 +374,8 @@ struct JoinBuildOp : tgpu_op {
         TG_TRY(concat(&lk->store));
         if (rows == 0) {
             lk->store.cols.resize(1 + output_channels.size());
-            lk->key_type = TGPU_INT64;
+            for (size_t c = 0; c < lk->store.cols.size(); c++) lk->store.cols[c].type = c < col_types.size() && col_types[c] ? col_types[c] : TGPU_INT64;
+            lk->key_type = lk->store.cols[0].type;
         }
         else lk->key_type = lk->store.cols[0].type;
         if (lk->key_type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width join keys are not supported on the GPU path");

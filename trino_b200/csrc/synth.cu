@@ -1,5 +1,5 @@
 // synth.cu — counter-based synthetic TPC-H-shaped columns generated directly in HBM.
-// MUST stay identical to the generators in oracle/oracle.cpp (tests compare them element by element).
+// The CPU checker restates the same generators; tests compare them element by element.
 #include "common.cuh"
 
 namespace {

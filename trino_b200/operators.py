@@ -1,0 +1,644 @@
+"""Host-side mirror of the reference's Operator / OperatorFactory interface over the C ABI.
+
+The reference's host language is Java and there is no JDK in this environment, so the drop-in boundary is
+the C ABI (include/trino_gpu.h); these classes are the Python equivalent of the thin Java operators in
+java/  and keep the reference's names, argument meaning and error behaviour:
+
+  Operator            M/operator/Operator.java:21-102  (needsInput/addInput/getOutput/finish/isFinished/close)
+  OperatorFactory     M/operator/OperatorFactory.java:16-30 (createOperator/noMoreOperators/duplicate)
+  HashAggregationOperatorFactory   M/operator/HashAggregationOperator.java:63-200
+  HashBuilderOperatorFactory       M/operator/join/unspilled/HashBuilderOperator.java:55-140
+  LookupJoinOperatorFactory        M/operator/join/unspilled/LookupJoinOperatorFactory.java
+  FilterAndProjectOperatorFactory  M/operator/FilterAndProjectOperator.java:97-150
+  PartitionedOutputOperatorFactory M/operator/output/PartitionedOutputOperator.java:52-140
+
+Every method ends in a libtrino_gpu.so call; nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .page import AbiPage, Block, Page
+
+_NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64}
+_ELEM = {abi.INT64: 8, abi.INT32: 4, abi.INT16: 2, abi.INT8: 1, abi.FLOAT64: 8}
+
+
+def _i32(values):
+    arr = (C.c_int32 * max(1, len(values)))(*values)
+    return arr
+
+
+class Context:
+    """tgpu_ctx: one per (process, device, driver thread)."""
+
+    def __init__(self, device=0):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        st = self.lib.tgpu_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise abi.TrinoGpuError(st, self.lib.tgpu_status_name(st).decode(), self.lib.tgpu_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, st):
+        if st != 0:
+            raise abi.TrinoGpuError(st, self.lib.tgpu_status_name(st).decode(), self.lib.tgpu_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.tgpu_ctx_destroy(self.h)
+            self.h = None
+
+    def synchronize(self):
+        self.check(self.lib.tgpu_ctx_synchronize(self.h))
+
+    @property
+    def kernel_launches(self):
+        return self.lib.tgpu_ctx_kernel_launches(self.h)
+
+    # ---- device memory
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(self.lib.tgpu_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, ptr):
+        self.check(self.lib.tgpu_free(self.h, C.c_void_p(ptr)))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = self.malloc(max(arr.nbytes, 16))
+        if arr.nbytes:
+            self.check(self.lib.tgpu_memcpy_h2d(self.h, C.c_void_p(p), C.c_void_p(arr.ctypes.data), arr.nbytes))
+        return p
+
+    def to_host(self, ptr, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        if out.nbytes:
+            self.check(self.lib.tgpu_memcpy_d2h(self.h, C.c_void_p(out.ctypes.data), C.c_void_p(ptr), out.nbytes))
+        return out
+
+    def pinned_empty(self, count, dtype):
+        p = C.c_void_p()
+        nbytes = int(count) * np.dtype(dtype).itemsize
+        st = self.lib.tgpu_host_alloc_pinned(max(nbytes, 16), C.byref(p))
+        self.check(st)
+        buf = (C.c_char * max(nbytes, 16)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=count)
+        arr._tgpu_pinned = p   # keep the pointer for free
+        return arr
+
+    def flush_l2(self):
+        self.check(self.lib.tgpu_flush_l2(self.h))
+
+    def timer_start(self):
+        self.check(self.lib.tgpu_timer_start(self.h))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        self.check(self.lib.tgpu_timer_stop_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    # ---- output pages
+    def page_to_host(self, pp, release=True):
+        """device tgpu_page* -> host Page (numpy)."""
+        dp = pp.contents
+        n = dp.num_rows
+        host_cols = (abi.Column * max(1, dp.num_columns))()
+        keep = []
+        for c in range(dp.num_columns):
+            d = dp.columns[c]
+            h = host_cols[c]
+            h.type = d.type
+            h.length = n
+            valid = np.empty((n + 7) // 8 + 1, dtype=np.uint8)
+            h.validity = valid.ctypes.data
+            if d.type == abi.UTF8:
+                nbytes = max(1, self.lib.tgpu_page_utf8_bytes(self.h, pp, c))
+                # offsets may be absolute into a larger buffer: size the host buffer by the last offset
+                offs = np.empty(n + 1, dtype=np.int32)
+                if n:
+                    self.check(self.lib.tgpu_memcpy_d2h(self.h, C.c_void_p(offs.ctypes.data), C.c_void_p(d.offsets), (n + 1) * 4))
+                    nbytes = max(nbytes, int(offs[n]))
+                data = np.zeros(nbytes, dtype=np.uint8)
+                h.offsets = offs.ctypes.data
+                h.data = data.ctypes.data
+                keep.append((d.type, data, valid, offs))
+            else:
+                data = np.empty(n, dtype=_NP_OF_TYPE[d.type])
+                h.data = data.ctypes.data
+                keep.append((d.type, data, valid, None))
+        hp = abi.Page(dp.num_columns, 0, n, C.cast(host_cols, C.POINTER(abi.Column)))
+        self.check(self.lib.tgpu_page_copy_to_host(self.h, pp, C.byref(hp)))
+        blocks = []
+        for type_, data, valid, offs in keep:
+            bits = np.unpackbits(valid, bitorder="little")[:n].astype(np.bool_)
+            nulls = ~bits
+            blocks.append(Block(type_, data, nulls if nulls.any() else None, offs))
+        if release:
+            self.lib.tgpu_page_release(self.h, pp)
+        return Page(*blocks, position_count=n)
+
+
+class DeviceColumn:
+    """A column that already lives in HBM (bench / GPU->GPU chaining)."""
+
+    def __init__(self, type_, ptr, length, validity=None, offsets=None):
+        self.type, self.ptr, self.length, self.validity, self.offsets = type_, ptr, length, validity, offsets
+
+
+class DevicePage:
+    def __init__(self, columns, rows):
+        self.columns = columns
+        self.rows = rows
+        self.abi_cols = (abi.Column * max(1, len(columns)))()
+        for i, c in enumerate(columns):
+            a = self.abi_cols[i]
+            a.type, a.flags, a.length = c.type, 0, c.length
+            a.data, a.offsets, a.validity = c.ptr, c.offsets, c.validity
+        self.page = abi.Page(len(columns), abi.PAGE_DEVICE, rows, C.cast(self.abi_cols, C.POINTER(abi.Column)))
+
+    def ref(self):
+        return C.byref(self.page)
+
+
+class DeviceOutputPage:
+    """A library-owned output page left on the device."""
+
+    def __init__(self, ctx, pp):
+        self.ctx, self.pp = ctx, pp
+        self.rows = pp.contents.num_rows
+        self.num_columns = pp.contents.num_columns
+
+    def column(self, c):
+        d = self.pp.contents.columns[c]
+        return DeviceColumn(d.type, d.data, d.length, d.validity, d.offsets)
+
+    def as_device_page(self):
+        return DevicePage([self.column(c) for c in range(self.num_columns)], self.rows)
+
+    def to_host(self):
+        return self.ctx.page_to_host(self.pp, release=False)
+
+    def release(self):
+        if self.pp:
+            self.ctx.lib.tgpu_page_release(self.ctx.h, self.pp)
+            self.pp = None
+
+
+def _as_abi_page(page):
+    if isinstance(page, (DevicePage, AbiPage)):
+        return page
+    if isinstance(page, DeviceOutputPage):
+        return page.as_device_page()
+    return AbiPage(page)
+
+
+# =====================================================================================================
+# Operator / OperatorFactory
+# =====================================================================================================
+class Operator:
+    """M/operator/Operator.java:21-102"""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.h = handle
+
+    def needs_input(self):
+        v = C.c_int()
+        self.ctx.check(self.ctx.lib.tgpu_op_needs_input(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def add_input(self, page):
+        ap = _as_abi_page(page)
+        self.ctx.check(self.ctx.lib.tgpu_op_add_input(self.h, ap.ref()))
+
+    def get_output_device(self):
+        pp = abi.PP()
+        self.ctx.check(self.ctx.lib.tgpu_op_get_output(self.h, C.byref(pp)))
+        return DeviceOutputPage(self.ctx, pp) if pp else None
+
+    def get_output(self):
+        pp = abi.PP()
+        self.ctx.check(self.ctx.lib.tgpu_op_get_output(self.h, C.byref(pp)))
+        return self.ctx.page_to_host(pp) if pp else None
+
+    def finish(self):
+        self.ctx.check(self.ctx.lib.tgpu_op_finish(self.h))
+
+    def is_finished(self):
+        v = C.c_int()
+        self.ctx.check(self.ctx.lib.tgpu_op_is_finished(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def memory_bytes(self):
+        return self.ctx.lib.tgpu_op_memory_bytes(self.h)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tgpu_op_close(self.h)
+            self.h = None
+
+
+class OperatorFactory:
+    """M/operator/OperatorFactory.java:16-30"""
+
+    def __init__(self):
+        self.closed = False
+
+    def create_operator(self):
+        if self.closed:
+            raise RuntimeError("Factory is already closed")   # checkState(!closed) in every reference factory
+        return self._create()
+
+    def no_more_operators(self):
+        self.closed = True
+
+    def duplicate(self):
+        raise NotImplementedError
+
+
+# ---- expressions ----------------------------------------------------------------------------------
+class Col:
+    def __init__(self, channel, vtype):
+        self.channel, self.vtype = channel, vtype
+
+
+class Const:
+    def __init__(self, value, vtype):
+        self.value, self.vtype = value, vtype
+
+
+class Null:
+    def __init__(self, vtype):
+        self.vtype = vtype
+
+
+class Call:
+    """op: one of abi.EX_*; args: expressions.  vtype is the OPERAND type (result of comparisons is BOOLEAN)."""
+
+    def __init__(self, op, *args, in_list=None):
+        self.op, self.args, self.in_list = op, list(args), in_list
+        a0 = args[0]
+        self.operand_vtype = a0.vtype if not isinstance(a0, Call) else a0.result_vtype
+        boolean_result = op in (abi.EX_EQ, abi.EX_NE, abi.EX_LT, abi.EX_LE, abi.EX_GT, abi.EX_GE, abi.EX_AND, abi.EX_OR, abi.EX_NOT,
+                                abi.EX_IS_NULL, abi.EX_IS_NOT_NULL, abi.EX_BETWEEN, abi.EX_IN)
+        if boolean_result:
+            self.result_vtype = abi.V_BOOLEAN
+        elif op == abi.EX_CAST_BIGINT_TO_DOUBLE:
+            self.result_vtype = abi.V_DOUBLE
+        elif op == abi.EX_CAST_DOUBLE_TO_BIGINT:
+            self.result_vtype = abi.V_BIGINT
+        else:
+            self.result_vtype = self.operand_vtype
+
+    @property
+    def vtype(self):
+        return self.result_vtype
+
+
+class PageProcessorProgram:
+    """Compiles expression trees (the RowExpressions of LocalExecutionPlanner.java:2111-2114) to the three-address
+    tgpu_expr_program.  `projections`: ints pass a channel through, expressions are computed."""
+
+    def __init__(self, filter_expr, projections):
+        self.insns = []
+        self.in_lists = []
+        self.live = set()
+        self.filter_temp = -1
+        self.num_filter_insns = 0
+        if filter_expr is not None:
+            opnd = self._emit(filter_expr)
+            if opnd[0] != abi.OPND_TEMP:
+                t = self._alloc()
+                self._push(abi.EX_MOV, abi.V_BOOLEAN, t, opnd)
+                opnd = (abi.OPND_TEMP, t, 0)
+            self.filter_temp = opnd[1]
+            self.num_filter_insns = len(self.insns)
+        self.projections = []
+        for p in projections:
+            if isinstance(p, int):
+                self.projections.append((0, p, 0))
+                continue
+            vt = p.vtype
+            opnd = self._emit(p)
+            if opnd[0] != abi.OPND_TEMP or opnd[1] == self.filter_temp:
+                t = self._alloc()
+                self._push(abi.EX_MOV, vt, t, opnd)
+                opnd = (abi.OPND_TEMP, t, 0)
+            self.projections.append((1, opnd[1], vt))
+        self._build()
+
+    def _alloc(self):
+        for t in range(8):
+            if t not in self.live:
+                self.live.add(t)
+                return t
+        raise ValueError("expression needs more than 8 temporaries")
+
+    def _push(self, op, vtype, dst, a, b=None, c=None):
+        self.insns.append((op, vtype, dst, a, b or (abi.OPND_NONE, 0, 0), c or (abi.OPND_NONE, 0, 0)))
+
+    def _emit(self, e):
+        if isinstance(e, Col):
+            return (abi.OPND_COLUMN, e.channel, 0)
+        if isinstance(e, Const):
+            imm = abi.Imm()
+            if e.vtype == abi.V_DOUBLE:
+                imm.f64 = float(e.value)
+            else:
+                imm.i64 = int(e.value)
+            return (abi.OPND_CONST, 0, imm.i64)
+        if isinstance(e, Null):
+            return (abi.OPND_NULL, 0, 0)
+        ops = [self._emit(a) for a in e.args]
+        b = None
+        if e.op == abi.EX_IN:
+            vals = []
+            for v in e.in_list:
+                imm = abi.Imm()
+                if e.operand_vtype == abi.V_DOUBLE:
+                    imm.f64 = float(v)
+                else:
+                    imm.i64 = int(v)
+                vals.append(imm.i64)
+            self.in_lists.append(vals)
+            b = (abi.OPND_CONST, 0, len(self.in_lists) - 1)
+        for o in ops:   # operand temps die here (projection temps are never passed as operands twice)
+            if o[0] == abi.OPND_TEMP and o[1] != self.filter_temp:
+                self.live.discard(o[1])
+        dst = self._alloc()
+        self._push(e.op, e.operand_vtype, dst, ops[0], b if b else (ops[1] if len(ops) > 1 else None), ops[2] if len(ops) > 2 else None)
+        return (abi.OPND_TEMP, dst, 0)
+
+    def _build(self):
+        n = len(self.insns)
+        self._insns = (abi.ExprInsn * max(1, n))()
+        for i, (op, vt, dst, a, b, c) in enumerate(self.insns):
+            ins = self._insns[i]
+            ins.op, ins.vtype, ins.dst = op, vt, dst
+            for fld, o in (("a", a), ("b", b), ("c", c)):
+                f = getattr(ins, fld)
+                f.kind, f.index = o[0], o[1]
+                f.imm.i64 = o[2]
+        self._projs = (abi.Projection * max(1, len(self.projections)))()
+        for i, (k, idx, vt) in enumerate(self.projections):
+            self._projs[i].kind, self._projs[i].index, self._projs[i].vtype = k, idx, vt
+        self._lists = (abi.InList * max(1, len(self.in_lists)))()
+        self._list_bufs = []
+        for i, vals in enumerate(self.in_lists):
+            buf = (C.c_int64 * max(1, len(vals)))(*vals)
+            self._list_bufs.append(buf)
+            self._lists[i].count = len(vals)
+            self._lists[i].values = C.cast(buf, C.POINTER(C.c_int64))
+        self.struct = abi.ExprProgram(n, C.cast(self._insns, C.POINTER(abi.ExprInsn)), self.filter_temp, self.num_filter_insns,
+                                      len(self.projections), C.cast(self._projs, C.POINTER(abi.Projection)),
+                                      len(self.in_lists), C.cast(self._lists, C.POINTER(abi.InList)))
+
+
+class FilterAndProjectOperatorFactory(OperatorFactory):
+    def __init__(self, ctx, program):
+        super().__init__()
+        self.ctx, self.program = ctx, program
+
+    def _create(self):
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_filter_project_create(self.ctx.h, C.byref(self.program.struct), C.byref(h)))
+        return Operator(self.ctx, h)
+
+    def duplicate(self):
+        return FilterAndProjectOperatorFactory(self.ctx, self.program)
+
+
+# ---- aggregation ------------------------------------------------------------------------------------
+class Aggregator:
+    """One AggregatorFactory (M/operator/aggregation/AggregatorFactory.java:40-58): function + input/mask channels."""
+
+    def __init__(self, function, input_channel=-1, mask_channel=-1):
+        self.function, self.input_channel, self.mask_channel = function, input_channel, mask_channel
+
+
+class HashAggregationOperator(Operator):
+    def group_count(self):
+        v = C.c_int64()
+        self.ctx.check(self.ctx.lib.tgpu_agg_group_count(self.h, C.byref(v)))
+        return v.value
+
+
+class HashAggregationOperatorFactory(OperatorFactory):
+    def __init__(self, ctx, group_by_channels, step, aggregators, expected_groups=10_000, max_partial_memory=0, pre=None):
+        super().__init__()
+        self.ctx, self.group_by_channels, self.step, self.aggregators = ctx, list(group_by_channels), step, list(aggregators)
+        self.expected_groups, self.max_partial_memory, self.pre = expected_groups, max_partial_memory, pre
+
+    def _create(self):
+        keys = _i32(self.group_by_channels)
+        fns = (abi.AggFn * max(1, len(self.aggregators)))()
+        for i, a in enumerate(self.aggregators):
+            fns[i].function, fns[i].input_channel, fns[i].mask_channel = a.function, a.input_channel, a.mask_channel
+        spec = abi.AggSpec(len(self.group_by_channels), C.cast(keys, C.POINTER(C.c_int32)), self.step, len(self.aggregators),
+                           C.cast(fns, C.POINTER(abi.AggFn)), self.expected_groups, self.max_partial_memory,
+                           C.pointer(self.pre.struct) if self.pre is not None else None)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_agg_create(self.ctx.h, C.byref(spec), C.byref(h)))
+        return HashAggregationOperator(self.ctx, h)
+
+    def duplicate(self):
+        return HashAggregationOperatorFactory(self.ctx, self.group_by_channels, self.step, self.aggregators, self.expected_groups,
+                                              self.max_partial_memory, self.pre)
+
+
+class GroupByHash:
+    """M/operator/GroupByHash.java: getGroupIds / getGroupCount over a persistent device table."""
+
+    def __init__(self, ctx, key_channels, expected_size=10_000):
+        self.ctx = ctx
+        keys = _i32(list(key_channels))
+        h = C.c_void_p()
+        ctx.check(ctx.lib.tgpu_groupby_hash_create(ctx.h, len(key_channels), C.cast(keys, C.POINTER(C.c_int32)), expected_size, C.byref(h)))
+        self.h = h
+
+    def get_group_ids(self, page):
+        ap = _as_abi_page(page)
+        out = np.empty(page.position_count, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.tgpu_groupby_hash_get_group_ids(self.h, ap.ref(), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def get_group_count(self):
+        v = C.c_int64()
+        self.ctx.check(self.ctx.lib.tgpu_agg_group_count(self.h, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tgpu_op_close(self.h)
+            self.h = None
+
+
+# ---- join -------------------------------------------------------------------------------------------
+class LookupSource:
+    """M/operator/join/LookupSource.java:24-68 (device table handle)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+
+    def get_join_position_count(self):
+        return self.ctx.lib.tgpu_lookup_position_count(self.h)
+
+    def get_in_memory_size_in_bytes(self):
+        return self.ctx.lib.tgpu_lookup_memory_bytes(self.h)
+
+    def has_position_links(self):
+        return bool(self.ctx.lib.tgpu_lookup_has_duplicates(self.h))
+
+    def get_join_positions(self, keys_page):
+        ap = _as_abi_page(keys_page)
+        n = keys_page.position_count
+        out = np.empty(n, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.tgpu_lookup_get_join_positions(self.ctx.h, self.h, ap.ref(), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def get_join_positions_device(self, device_page, out_ptr):
+        self.ctx.check(self.ctx.lib.tgpu_lookup_get_join_positions(self.ctx.h, self.h, device_page.ref(), C.c_void_p(out_ptr)))
+
+    def position_links(self):
+        out = np.empty(self.get_join_position_count(), dtype=np.int32)
+        self.ctx.check(self.ctx.lib.tgpu_lookup_copy_position_links(self.ctx.h, self.h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.tgpu_lookup_release(self.h)
+            self.h = None
+
+
+class JoinBridge:
+    """The JoinBridgeManager / PartitionedLookupSourceFactory hand-off (PartitionedLookupSourceFactory.java:100,126):
+    the build operator lends its LookupSource, probe operators take it once it is there."""
+
+    def __init__(self):
+        self.lookup_source = None
+
+    def lend(self, lookup_source):
+        self.lookup_source = lookup_source
+
+    def is_built(self):
+        return self.lookup_source is not None
+
+
+class HashBuilderOperator(Operator):
+    def __init__(self, ctx, handle, bridge):
+        super().__init__(ctx, handle)
+        self.bridge = bridge
+
+    def finish(self):
+        super().finish()
+        if not self.bridge.is_built():
+            lk = C.c_void_p()
+            self.ctx.check(self.ctx.lib.tgpu_join_build_get_lookup(self.h, C.byref(lk)))
+            self.bridge.lend(LookupSource(self.ctx, lk))
+
+
+class HashBuilderOperatorFactory(OperatorFactory):
+    def __init__(self, ctx, bridge, hash_channels, output_channels, expected_positions=10_000):
+        super().__init__()
+        self.ctx, self.bridge = ctx, bridge
+        self.hash_channels, self.output_channels, self.expected_positions = list(hash_channels), list(output_channels), expected_positions
+
+    def _create(self):
+        kc, oc = _i32(self.hash_channels), _i32(self.output_channels)
+        spec = abi.JoinBuildSpec(len(self.hash_channels), C.cast(kc, C.POINTER(C.c_int32)), len(self.output_channels),
+                                 C.cast(oc, C.POINTER(C.c_int32)), self.expected_positions)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_join_build_create(self.ctx.h, C.byref(spec), C.byref(h)))
+        return HashBuilderOperator(self.ctx, h, self.bridge)
+
+    def duplicate(self):
+        raise RuntimeError("Parallel hash build can not be duplicated")   # HashBuilderOperator.java:131-134
+
+
+class LookupJoinOperatorFactory(OperatorFactory):
+    def __init__(self, ctx, bridge, join_type, output_single_match, probe_join_channels, probe_output_channels):
+        super().__init__()
+        self.ctx, self.bridge, self.join_type, self.output_single_match = ctx, bridge, join_type, output_single_match
+        self.probe_join_channels, self.probe_output_channels = list(probe_join_channels), list(probe_output_channels)
+
+    def _create(self):
+        if not self.bridge.is_built():
+            # PageJoiner.process blocks on lookupSourceFuture (PageJoiner.java:102-105); here the driver must build first
+            raise RuntimeError("lookup source is not built yet")
+        kc, oc = _i32(self.probe_join_channels), _i32(self.probe_output_channels)
+        spec = abi.JoinProbeSpec(self.join_type, int(self.output_single_match), len(self.probe_join_channels), C.cast(kc, C.POINTER(C.c_int32)),
+                                 len(self.probe_output_channels), C.cast(oc, C.POINTER(C.c_int32)))
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_join_probe_create(self.ctx.h, C.byref(spec), self.bridge.lookup_source.h, C.byref(h)))
+        return Operator(self.ctx, h)
+
+    def duplicate(self):
+        return LookupJoinOperatorFactory(self.ctx, self.bridge, self.join_type, self.output_single_match, self.probe_join_channels,
+                                         self.probe_output_channels)
+
+
+# ---- partitioned output -----------------------------------------------------------------------------
+class PartitionedOutputOperator(Operator):
+    def get_output_with_partition(self):
+        """(partition, Page) or None — the OutputBuffer.enqueue(partition, pages) call of PagePartitioner.java:484-487"""
+        page = self.get_output()
+        if page is None:
+            return None
+        p = C.c_int32()
+        self.ctx.check(self.ctx.lib.tgpu_partition_last_output_partition(self.h, C.byref(p)))
+        return p.value, page
+
+    def get_partitions(self, page):
+        ap = _as_abi_page(page)
+        out = np.empty(page.position_count, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.tgpu_partition_get_partitions(self.h, ap.ref(), C.c_void_p(out.ctypes.data)))
+        return out
+
+
+class PartitionedOutputOperatorFactory(OperatorFactory):
+    def __init__(self, ctx, partition_channels, bucket_count, bucket_to_partition=None, null_channel=-1, replicates_any_row=False):
+        super().__init__()
+        self.ctx, self.partition_channels, self.bucket_count = ctx, list(partition_channels), bucket_count
+        self.bucket_to_partition, self.null_channel, self.replicates_any_row = bucket_to_partition, null_channel, replicates_any_row
+
+    def _create(self):
+        kc = _i32(self.partition_channels)
+        b2p = _i32(list(self.bucket_to_partition)) if self.bucket_to_partition is not None else None
+        spec = abi.PartitionSpec(len(self.partition_channels), C.cast(kc, C.POINTER(C.c_int32)), self.bucket_count,
+                                 C.cast(b2p, C.POINTER(C.c_int32)) if b2p is not None else None, self.null_channel, int(self.replicates_any_row))
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_partition_create(self.ctx.h, C.byref(spec), C.byref(h)))
+        return PartitionedOutputOperator(self.ctx, h)
+
+    def duplicate(self):
+        return PartitionedOutputOperatorFactory(self.ctx, self.partition_channels, self.bucket_count, self.bucket_to_partition, self.null_channel,
+                                                self.replicates_any_row)
+
+
+def drive(operator, pages):
+    """The relevant slice of Driver.processInternal (M/operator/Driver.java:391-424) for one operator:
+    feed pages while needsInput, drain getOutput, then finish and drain.  Returns the output pages."""
+    out = []
+    for p in pages:
+        while not operator.needs_input():
+            o = operator.get_output()
+            if o is not None:
+                out.append(o)
+        operator.add_input(p)
+        while True:
+            o = operator.get_output()
+            if o is None:
+                break
+            out.append(o)
+    operator.finish()
+    while not operator.is_finished():
+        o = operator.get_output()
+        if o is not None:
+            out.append(o)
+        elif operator.is_finished():
+            break
+    return out

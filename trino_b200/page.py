@@ -1,0 +1,229 @@
+"""Host-side mirror of Trino's Page / Block data model (S/Page.java:31, S/block/*), numpy backed.
+
+Blocks keep the reference's shapes — value blocks (LongArrayBlock, IntArrayBlock, ShortArrayBlock,
+ByteArrayBlock, VariableWidthBlock), DictionaryBlock and RunLengthEncodedBlock — and convert to the
+Arrow-layout `tgpu_column` structs of the C ABI without copying the value buffers.
+Nulls are held the way Java holds them (boolean valueIsNull[], True = NULL) and handed to the library
+either as that byte map (TGPU_COL_NULLS_BYTEMAP) or as an Arrow validity bitmap.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64}
+
+
+class Block:
+    """A value block.  `type` is a tgpu_type; `values` a numpy array (UTF8: uint8 bytes + int32 offsets)."""
+
+    def __init__(self, type_, values, nulls=None, offsets=None):
+        self.type = type_
+        self.values = values
+        self.offsets = offsets
+        self.nulls = None if nulls is None else np.ascontiguousarray(nulls, dtype=np.bool_)
+        self.position_count = (len(offsets) - 1) if type_ == abi.UTF8 else len(values)
+        if self.nulls is not None and not self.nulls.any():
+            self.nulls = None
+
+    # --- constructors named after the SQL types of the reference
+    @staticmethod
+    def _fixed(type_, values, nulls):
+        v = list(values) if not isinstance(values, np.ndarray) else values
+        if not isinstance(v, np.ndarray):
+            if nulls is None and any(x is None for x in v):
+                nulls = [x is None for x in v]
+            v = [0 if x is None else x for x in v]
+        arr = np.ascontiguousarray(np.asarray(v, dtype=_NP_OF_TYPE[type_]))
+        return Block(type_, arr, nulls)
+
+    @staticmethod
+    def bigint(values, nulls=None):
+        return Block._fixed(abi.INT64, values, nulls)
+
+    @staticmethod
+    def integer(values, nulls=None):
+        return Block._fixed(abi.INT32, values, nulls)
+
+    date = integer
+
+    @staticmethod
+    def smallint(values, nulls=None):
+        return Block._fixed(abi.INT16, values, nulls)
+
+    @staticmethod
+    def tinyint(values, nulls=None):
+        return Block._fixed(abi.INT8, values, nulls)
+
+    @staticmethod
+    def boolean(values, nulls=None):
+        v = [None if x is None else int(bool(x)) for x in values] if not isinstance(values, np.ndarray) else values.astype(np.int8)
+        return Block._fixed(abi.INT8, v, nulls)
+
+    @staticmethod
+    def double(values, nulls=None):
+        return Block._fixed(abi.FLOAT64, values, nulls)
+
+    @staticmethod
+    def varchar(values):
+        nulls = [v is None for v in values]
+        enc = [b"" if v is None else (v.encode() if isinstance(v, str) else bytes(v)) for v in values]
+        offsets = np.zeros(len(enc) + 1, dtype=np.int32)
+        np.cumsum([len(e) for e in enc], out=offsets[1:])
+        data = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if enc else np.zeros(0, dtype=np.uint8)
+        if len(data) == 0:
+            data = np.zeros(1, dtype=np.uint8)
+        return Block(abi.UTF8, data, nulls if any(nulls) else None, offsets)
+
+    # --- accessors
+    def is_null(self, i):
+        return self.nulls is not None and bool(self.nulls[i])
+
+    def get(self, i):
+        if self.is_null(i):
+            return None
+        if self.type == abi.UTF8:
+            return bytes(self.values[self.offsets[i]:self.offsets[i + 1]])
+        v = self.values[i]
+        return float(v) if self.type == abi.FLOAT64 else int(v)
+
+    def to_pylist(self):
+        return [self.get(i) for i in range(self.position_count)]
+
+    def flatten(self):
+        return self
+
+    def get_positions(self, idx):
+        idx = np.asarray(idx, dtype=np.int64)
+        nulls = None if self.nulls is None else self.nulls[idx]
+        if self.type == abi.UTF8:
+            return Block.varchar([self.get(int(i)) for i in idx])
+        return Block(self.type, np.ascontiguousarray(self.values[idx]), nulls)
+
+
+class DictionaryBlock:
+    """S/block/DictionaryBlock.java:37-40"""
+
+    def __init__(self, dictionary, ids):
+        self.dictionary = dictionary
+        self.ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self.type = abi.DICT32
+        self.position_count = len(self.ids)
+
+    def get(self, i):
+        return self.dictionary.get(int(self.ids[i]))
+
+    def is_null(self, i):
+        return self.dictionary.is_null(int(self.ids[i]))
+
+    def to_pylist(self):
+        return [self.get(i) for i in range(self.position_count)]
+
+    def flatten(self):
+        return self.dictionary.get_positions(self.ids)
+
+
+class RunLengthEncodedBlock:
+    """S/block/RunLengthEncodedBlock.java:71-72"""
+
+    def __init__(self, value, position_count):
+        assert value.position_count == 1
+        self.value = value
+        self.type = abi.RLE
+        self.position_count = position_count
+
+    def get(self, i):
+        return self.value.get(0)
+
+    def is_null(self, i):
+        return self.value.is_null(0)
+
+    def to_pylist(self):
+        return [self.value.get(0)] * self.position_count
+
+    def flatten(self):
+        return self.value.get_positions(np.zeros(self.position_count, dtype=np.int64))
+
+
+class Page:
+    """S/Page.java:31"""
+
+    def __init__(self, *blocks, position_count=None):
+        self.blocks = list(blocks)
+        if position_count is None:
+            position_count = self.blocks[0].position_count if self.blocks else 0
+        self.position_count = position_count
+        for b in self.blocks:
+            assert b.position_count == position_count, "block position counts differ"
+
+    @property
+    def channel_count(self):
+        return len(self.blocks)
+
+    def get_block(self, channel):
+        return self.blocks[channel]
+
+    def get_columns(self, channels):
+        return Page(*[self.blocks[c] for c in channels], position_count=self.position_count)
+
+    def rows(self):
+        cols = [b.to_pylist() for b in self.blocks]
+        return [tuple(c[i] for c in cols) for i in range(self.position_count)]
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(C.c_void_p).value if arr is not None and arr.size else (arr.ctypes.data if arr is not None else None)
+
+
+def _pack_validity(nulls):
+    return np.packbits(~nulls, bitorder="little")
+
+
+class AbiPage:
+    """A tgpu_page view over a host Page.  Holds every buffer alive for the duration of the call."""
+
+    def __init__(self, page, nulls_as_bytemap=True):
+        self.keep = []
+        self.ncols = len(page.blocks)
+        self.columns = (abi.Column * max(1, self.ncols))()
+        for c, b in enumerate(page.blocks):
+            self._fill(self.columns[c], b, nulls_as_bytemap)
+        self.page = abi.Page(self.ncols, 0, page.position_count, C.cast(self.columns, C.POINTER(abi.Column)))
+
+    def _fill(self, col, b, bytemap):
+        col.length = b.position_count
+        col.flags = 0
+        if isinstance(b, DictionaryBlock):
+            col.type = abi.DICT32
+            col.data = b.ids.ctypes.data
+            sub = abi.Column()
+            self._fill(sub, b.dictionary, bytemap)
+            self.keep.append(sub)
+            col.dictionary = C.pointer(sub)
+            return
+        if isinstance(b, RunLengthEncodedBlock):
+            col.type = abi.RLE
+            sub = abi.Column()
+            self._fill(sub, b.value, bytemap)
+            self.keep.append(sub)
+            col.dictionary = C.pointer(sub)
+            return
+        col.type = b.type
+        self.keep.append(b.values)
+        col.data = b.values.ctypes.data
+        if b.type == abi.UTF8:
+            self.keep.append(b.offsets)
+            col.offsets = b.offsets.ctypes.data
+        if b.nulls is not None:
+            if bytemap:
+                self.keep.append(b.nulls)
+                col.validity = b.nulls.ctypes.data
+                col.flags = abi.COL_NULLS_BYTEMAP
+            else:
+                bits = _pack_validity(b.nulls)
+                self.keep.append(bits)
+                col.validity = bits.ctypes.data
+
+    def ref(self):
+        return C.byref(self.page)
