@@ -93,7 +93,7 @@ def _oracle_agg(pages, key_channels, aggs):
             if len(state) <= ai:
                 state.append({"sum": np.zeros(0), "cnt": np.zeros(0, np.int64), "isum": np.zeros(0, np.int64), "nn": np.zeros(0, np.uint8), "acc": np.zeros(0), "iacc": np.zeros(0, np.int64)})
             st = state[ai]
-            for k in st:
+            for k in [k for k in st if k != "dbl"]:
                 if len(st[k]) < G:
                     st[k] = np.concatenate([st[k], np.zeros(G - len(st[k]), st[k].dtype)])
             blk = page.get_block(ch).flatten() if ch >= 0 else None

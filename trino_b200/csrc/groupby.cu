@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(256) agg_small_merge_kernel(AggPlan plan, DCol
     __shared__ int s_fail;
     const int tid = threadIdx.x, T = blockDim.x;
     const int A = plan.num_accs;
+    if (*((volatile int*)part.overflow)) return;   // a CTA ran out of key slots: its partials were never written
     for (int i = tid; i < S_GMAX; i += T) pkeys[i] = EMPTY_KEY;
     for (int i = tid; i < S_GMAX + 2; i += T) { pfirst[i] = NO_ROW; pgid[i] = -1; pnew[i] = 0; }
     if (tid == 0) s_fail = 0;

@@ -87,7 +87,8 @@ class Context:
         self.check(st)
         buf = (C.c_char * max(nbytes, 16)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype, count=count)
-        arr._tgpu_pinned = p   # keep the pointer for free
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)   # freed with the process; pinned buffers live as long as the bench
         return arr
 
     def flush_l2(self):
