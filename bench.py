@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000_000)
     ap.add_argument("--e2e-rows", type=int, default=0, help="probe rows fed from host per e2e step (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128; 0 = leave the default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -169,6 +170,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = ops.Context(local)
     lib = ctx.lib
+    if args.l2_fetch:
+        ctx.check(lib.tgpu_ctx_set_l2_fetch_granularity(ctx.h, args.l2_fetch))
+    l2g = C.c_int()
+    ctx.check(lib.tgpu_ctx_get_l2_fetch_granularity(ctx.h, C.byref(l2g)))
 
     def barrier():
         if dist is not None:
@@ -320,7 +325,7 @@ def main():
         line = {"metric": "hash_join_probe_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
                 "config": workload_config(args, n_orders, probe_rows, world), "gpu_launches": int(launches), "clocks": clocks,
-                "build_seconds": build_s, "output_rows_per_step": total_out}
+                "build_seconds": build_s, "output_rows_per_step": total_out, "l2_fetch_granularity": l2g.value}
         if roofline:
             line["roofline"] = roofline
         if cpu:

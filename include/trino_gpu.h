@@ -94,6 +94,9 @@ int tgpu_ctx_synchronize(tgpu_ctx* ctx);              /* cudaStreamSynchronize o
 void* tgpu_ctx_stream(tgpu_ctx* ctx);                 /* the cudaStream_t every kernel of ctx is launched on */
 int64_t tgpu_ctx_kernel_launches(const tgpu_ctx* ctx);/* number of kernels this library launched on ctx */
 int tgpu_device_count(void);
+/* tuning knob: cudaLimitMaxL2FetchGranularity (32/64/128 bytes pulled from HBM per missing L2 sector) */
+int tgpu_ctx_set_l2_fetch_granularity(tgpu_ctx* ctx, int bytes);
+int tgpu_ctx_get_l2_fetch_granularity(tgpu_ctx* ctx, int* bytes);
 
 /* device memory helpers for the device-resident path (bench, GPU->GPU chaining, tests) */
 int tgpu_malloc(tgpu_ctx* ctx, size_t bytes, void** out);
@@ -224,6 +227,11 @@ typedef struct tgpu_agg_spec {
 } tgpu_agg_spec;
 
 int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op** out);
+/* diagnostics (needs no GPU): generate the kernel specialised for `spec` over input channels of the given tgpu_types
+ * (bit c of nullable_mask = channel c carries NULLs), compile it with NVRTC for sm_100a; returns the cubin size and
+ * the generated source (or the compiler log on failure) */
+int tgpu_jit_selftest_agg(const tgpu_agg_spec* spec, const int32_t* channel_types, int32_t num_channels, uint32_t nullable_mask,
+                          int64_t* cubin_bytes, char* source_out, int64_t source_cap);
 /* GroupByHash.getGroupCount() */
 int tgpu_agg_group_count(tgpu_op* op, int64_t* out);
 

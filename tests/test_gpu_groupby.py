@@ -118,7 +118,8 @@ def _oracle_agg(pages, key_channels, aggs):
             elif fn == abi.AGG_SUM:
                 assert lib.orc_agg_sum_bigint(P(ids32), n, P(vals), P(valid), P(sel), P(st["isum"]), P(st["nn"])) == 0
             elif fn == abi.AGG_AVG:
-                lib.orc_agg_avg_double(P(ids32), n, P(vals.astype(np.float64)), P(valid), P(sel), P(st["sum"]), P(st["cnt"]))
+                fvals = np.ascontiguousarray(vals.astype(np.float64))   # keep alive across the call
+                lib.orc_agg_avg_double(P(ids32), n, P(fvals), P(valid), P(sel), P(st["sum"]), P(st["cnt"]))
             elif is_dbl:
                 lib.orc_agg_minmax_double(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["acc"]), P(st["nn"]))
             else:

@@ -1,0 +1,52 @@
+"""The NVRTC specialisation path needs no GPU to compile: generate the fused Q1 kernel (and variants with NULL-able
+channels) and compile it for sm_100a on the CPU box.  The launch itself is covered by the -m gpu suites."""
+import ctypes as C
+
+import pytest
+
+from q1 import q1_aggregators, q1_program
+from trino_b200 import abi
+
+
+def _selftest(nullable_mask, with_pre=True, aggs=None):
+    lib = abi.load_library()
+    prog = q1_program()
+    aggs = aggs or q1_aggregators()
+    keys = (C.c_int32 * 2)(0, 1) if with_pre else (C.c_int32 * 2)(1, 2)
+    fns = (abi.AggFn * len(aggs))()
+    for i, a in enumerate(aggs):
+        fns[i].function, fns[i].input_channel, fns[i].mask_channel = a.function, a.input_channel, a.mask_channel
+    spec = abi.AggSpec(2, C.cast(keys, C.POINTER(C.c_int32)), abi.STEP_SINGLE, len(aggs), C.cast(fns, C.POINTER(abi.AggFn)), 16, 0,
+                       C.pointer(prog.struct) if with_pre else None)
+    types = (C.c_int32 * 7)(abi.INT32, abi.INT8, abi.INT8, abi.FLOAT64, abi.FLOAT64, abi.FLOAT64, abi.FLOAT64)
+    n = C.c_int64()
+    buf = C.create_string_buffer(1 << 16)
+    st = lib.tgpu_jit_selftest_agg(C.byref(spec), types, 7, nullable_mask, C.byref(n), buf, len(buf))
+    return st, n.value, buf.value.decode()
+
+
+def test_q1_kernel_compiles_and_drops_redundant_counters():
+    st, size, src = _selftest(0)
+    if st == abi.ERR_NOT_SUPPORTED:
+        pytest.skip("NVRTC not installed: " + src)
+    assert st == 0, src
+    assert size > 10_000
+    assert "A = 6" in src                      # 5 sums + count(*): the 5 non-null counters alias the row counter
+    assert "tg_agg_small_jit" in src and "vm_apply(3, 1" in src
+
+
+def test_nullable_channels_keep_their_counters():
+    st, size, src = _selftest(0b1111000)      # quantity, extendedprice, discount, tax carry NULLs
+    if st == abi.ERR_NOT_SUPPORTED:
+        pytest.skip("NVRTC not installed")
+    assert st == 0, src
+    assert "A = 11" in src
+    assert "tg_valid(cols.cols[4].validity" in src
+
+
+def test_unfused_plan_compiles_too():
+    from trino_b200.operators import Aggregator as A
+    st, size, src = _selftest(0, with_pre=False, aggs=[A(abi.AGG_SUM, 3), A(abi.AGG_MIN, 4), A(abi.AGG_MAX, 0), A(abi.AGG_COUNT_STAR), A(abi.AGG_AVG, 0)])
+    if st == abi.ERR_NOT_SUPPORTED:
+        pytest.skip("NVRTC not installed")
+    assert st == 0, src

@@ -10,12 +10,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "trino_b200", "csrc")
 LIB = os.path.join(ROOT, "trino_b200", "libtrino_gpu.so")
-SOURCES = ["core.cu", "join.cu", "groupby.cu", "expr.cu", "partition.cu", "synth.cu"]
+SOURCES = ["core.cu", "join.cu", "groupby.cu", "expr.cu", "partition.cu", "synth.cu", "jit.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",            # Java never contracts a*b+c (M/type/DoubleOperators.java:66-86)
     "-Xcompiler", "-fPIC",
+    "-I", os.path.join(ROOT, "build"),
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
 ]
@@ -36,6 +37,13 @@ def build_gpu(force=False, verbose=False):
     objs = []
     procs = []
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    # device_lib.cuh is also the prelude of every NVRTC-specialised kernel: embed it as a string literal
+    with open(os.path.join(CSRC, "device_lib.cuh")) as f:
+        text = f.read()
+    assert ')TGJIT"' not in text
+    chunks = [text[i:i + 12000] for i in range(0, len(text), 12000)]   # stay under the 64 KiB literal limit
+    with open(os.path.join(ROOT, "build", "device_lib_str.inc"), "w") as f:
+        f.write("\n".join('R"TGJIT(' + c + ')TGJIT"' for c in chunks) + "\n")
     for src in SOURCES:
         obj = os.path.join(ROOT, "build", src.replace(".cu", ".o"))
         objs.append(obj)

@@ -152,6 +152,8 @@ SIGNATURES = {
     "tgpu_ctx_stream": (VP, [VP]),
     "tgpu_ctx_kernel_launches": (C.c_int64, [VP]),
     "tgpu_device_count": (C.c_int, []),
+    "tgpu_ctx_set_l2_fetch_granularity": (C.c_int, [VP, C.c_int]),
+    "tgpu_ctx_get_l2_fetch_granularity": (C.c_int, [VP, C.POINTER(C.c_int)]),
     "tgpu_malloc": (C.c_int, [VP, C.c_size_t, C.POINTER(VP)]),
     "tgpu_free": (C.c_int, [VP, VP]),
     "tgpu_memcpy_h2d": (C.c_int, [VP, VP, VP, C.c_size_t]),
@@ -164,6 +166,7 @@ SIGNATURES = {
     "tgpu_filter_project_create": (C.c_int, [VP, C.POINTER(ExprProgram), C.POINTER(VP)]),
     "tgpu_agg_create": (C.c_int, [VP, C.POINTER(AggSpec), C.POINTER(VP)]),
     "tgpu_agg_group_count": (C.c_int, [VP, C.POINTER(C.c_int64)]),
+    "tgpu_jit_selftest_agg": (C.c_int, [C.POINTER(AggSpec), C.POINTER(C.c_int32), C.c_int32, C.c_uint32, C.POINTER(C.c_int64), C.c_char_p, C.c_int64]),
     "tgpu_groupby_hash_create": (C.c_int, [VP, C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(VP)]),
     "tgpu_groupby_hash_get_group_ids": (C.c_int, [VP, PP, VP]),
     "tgpu_join_build_create": (C.c_int, [VP, C.POINTER(JoinBuildSpec), C.POINTER(VP)]),

@@ -14,6 +14,7 @@
 
 #include "../../include/trino_gpu.h"
 #include "hash.cuh"
+#include "device_lib.cuh"
 
 struct ncclComm;
 
@@ -177,14 +178,6 @@ struct OwnedPage {
     int32_t partition = -1;
 };
 
-// compact POD view of a fixed-width column for kernels
-struct ColRef {
-    const void* data;
-    const uint8_t* validity;
-    int32_t type;
-    int32_t elem;
-};
-
 static inline ColRef tg_colref(const DevColumn& c) { return ColRef{c.data, c.validity, c.type, c.elem_size()}; }
 
 // page ingestion: host pages are staged through pinned memory and copied H2D on the ctx stream;
@@ -216,22 +209,6 @@ struct tgpu_op {
 
 // device-side helpers -------------------------------------------------------------------------
 #if defined(__CUDACC__)
-__device__ __forceinline__ bool tg_valid(const uint8_t* validity, int64_t i)
-{
-    return validity == nullptr || ((validity[i >> 3] >> (i & 7)) & 1);
-}
-
-// sign-extending load of any fixed-width integer column element / raw bits of FLOAT64
-__device__ __forceinline__ int64_t tg_load_i64(const ColRef& c, int64_t i)
-{
-    switch (c.elem) {
-        case 8: return ((const int64_t*)c.data)[i];
-        case 4: return ((const int32_t*)c.data)[i];
-        case 2: return ((const int16_t*)c.data)[i];
-        default: return ((const int8_t*)c.data)[i];
-    }
-}
-
 // streaming (read-once) 128-bit load that does not allocate in L1
 __device__ __forceinline__ int4 tg_ldg_stream(const int4* p)
 {

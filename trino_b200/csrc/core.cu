@@ -113,6 +113,23 @@ extern "C" int tgpu_ctx_synchronize(tgpu_ctx* ctx)
 extern "C" void* tgpu_ctx_stream(tgpu_ctx* ctx) { return (void*)ctx->stream; }
 extern "C" int64_t tgpu_ctx_kernel_launches(const tgpu_ctx* ctx) { return ctx->launches; }
 
+extern "C" int tgpu_ctx_set_l2_fetch_granularity(tgpu_ctx* ctx, int bytes)
+{
+    // cudaLimitMaxL2FetchGranularity: how much the L2 pulls from HBM per missing sector (32/64/128 B).  Hash probes
+    // touch one 32-byte sector per lookup; anything wider is wasted DRAM traffic for them.
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    TG_CUDA(ctx, cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_ctx_get_l2_fetch_granularity(tgpu_ctx* ctx, int* bytes)
+{
+    size_t v = 0;
+    TG_CUDA(ctx, cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+    *bytes = (int)v;
+    return TGPU_OK;
+}
+
 extern "C" int tgpu_malloc(tgpu_ctx* ctx, size_t bytes, void** out)
 {
     TG_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -40,18 +40,8 @@ struct DProgram {
     DInsn insns[TGPU_MAX_INSNS];
 };
 
-struct DColumns {
-    ColRef cols[TGPU_MAX_CHANNELS];
-};
-
-enum { TG_ERR_BIT_OVERFLOW = 1, TG_ERR_BIT_DIV_ZERO = 2 };
 
 #if defined(__CUDACC__)
-
-struct Value {
-    int64_t bits;
-    bool is_null;
-};
 
 __device__ __forceinline__ Value vm_fetch(const DOperand& o, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits)
 {
@@ -79,29 +69,6 @@ __device__ __forceinline__ Value vm_fetch(const DOperand& o, const DColumns& col
     return v;
 }
 
-__device__ __forceinline__ bool vm_cmp(int op, int vtype, int64_t a, int64_t b)
-{
-    if (vtype == TGPU_V_DOUBLE) {
-        double x = __longlong_as_double(a), y = __longlong_as_double(b);
-        switch (op) {
-            case TGPU_EX_EQ: return x == y;
-            case TGPU_EX_NE: return !(x == y);
-            case TGPU_EX_LT: return x < y;
-            case TGPU_EX_LE: return x <= y;
-            case TGPU_EX_GT: return x > y;
-            default: return x >= y;
-        }
-    }
-    switch (op) {
-        case TGPU_EX_EQ: return a == b;
-        case TGPU_EX_NE: return a != b;
-        case TGPU_EX_LT: return a < b;
-        case TGPU_EX_LE: return a <= b;
-        case TGPU_EX_GT: return a > b;
-        default: return a >= b;
-    }
-}
-
 // Runs instructions [first, last) for one row.  `temps` points at this thread's column of the shared
 // [temp][thread] array (stride tstride).  Returns the updated null bitmask; *err accumulates TG_ERR_BIT_*.
 __device__ __forceinline__ uint32_t vm_run(const DProgram* __restrict__ prog, int first, int last, const DColumns& cols, int64_t row,
@@ -111,123 +78,29 @@ __device__ __forceinline__ uint32_t vm_run(const DProgram* __restrict__ prog, in
         const DInsn& in = prog->insns[pc];
         Value a = vm_fetch(in.a, cols, row, temps, tstride, nullbits);
         Value b = vm_fetch(in.b, cols, row, temps, tstride, nullbits);
-        int64_t r = 0;
-        bool rn = false;
-        const int op = in.op;
-        const bool dbl = in.vtype == TGPU_V_DOUBLE;
-        switch (op) {
-            case TGPU_EX_MOV: r = a.bits; rn = a.is_null; break;
-            case TGPU_EX_ADD: case TGPU_EX_SUB: case TGPU_EX_MUL: case TGPU_EX_DIV: case TGPU_EX_MOD: {
-                rn = a.is_null || b.is_null;
-                if (rn) break;
-                if (dbl) {
-                    double x = __longlong_as_double(a.bits), y = __longlong_as_double(b.bits), z;
-                    if (op == TGPU_EX_ADD) z = __dadd_rn(x, y);
-                    else if (op == TGPU_EX_SUB) z = __dsub_rn(x, y);
-                    else if (op == TGPU_EX_MUL) z = __dmul_rn(x, y);
-                    else if (op == TGPU_EX_DIV) z = __ddiv_rn(x, y);
-                    else z = fmod(x, y);
-                    r = __double_as_longlong(z);
-                }
-                else {
-                    long long x = a.bits, y = b.bits, z = 0;
-                    if (op == TGPU_EX_ADD) {
-                        z = (long long)((unsigned long long)x + (unsigned long long)y);
-                        if (((x ^ z) & (y ^ z)) < 0) *err |= TG_ERR_BIT_OVERFLOW;
-                    }
-                    else if (op == TGPU_EX_SUB) {
-                        z = (long long)((unsigned long long)x - (unsigned long long)y);
-                        if (((x ^ y) & (x ^ z)) < 0) *err |= TG_ERR_BIT_OVERFLOW;
-                    }
-                    else if (op == TGPU_EX_MUL) {
-                        z = (long long)((unsigned long long)x * (unsigned long long)y);
-                        long long hi = __mul64hi(x, y);
-                        if (hi != (z >> 63)) *err |= TG_ERR_BIT_OVERFLOW;
-                    }
-                    else {
-                        if (y == 0) { *err |= TG_ERR_BIT_DIV_ZERO; }
-                        else if (y == -1) {
-                            if (op == TGPU_EX_DIV) {
-                                if (x == LLONG_MIN) *err |= TG_ERR_BIT_OVERFLOW;
-                                else z = -x;
-                            }
-                            else z = 0;
-                        }
-                        else z = op == TGPU_EX_DIV ? x / y : x % y;
-                    }
-                    r = z;
-                }
-                break;
-            }
-            case TGPU_EX_NEG:
-                rn = a.is_null;
-                if (rn) break;
-                if (dbl) r = a.bits ^ (long long)0x8000000000000000ULL;
-                else {
-                    if (a.bits == LLONG_MIN) *err |= TG_ERR_BIT_OVERFLOW;
-                    r = (long long)(0ULL - (unsigned long long)a.bits);
-                }
-                break;
-            case TGPU_EX_EQ: case TGPU_EX_NE: case TGPU_EX_LT: case TGPU_EX_LE: case TGPU_EX_GT: case TGPU_EX_GE:
-                rn = a.is_null || b.is_null;
-                if (!rn) r = vm_cmp(op, in.vtype, a.bits, b.bits) ? 1 : 0;
-                break;
-            case TGPU_EX_AND: {
-                bool af = !a.is_null && a.bits == 0, bf = !b.is_null && b.bits == 0;
-                if (af || bf) { r = 0; rn = false; }
-                else if (a.is_null || b.is_null) rn = true;
-                else r = 1;
-                break;
-            }
-            case TGPU_EX_OR: {
-                bool at = !a.is_null && a.bits != 0, bt = !b.is_null && b.bits != 0;
-                if (at || bt) { r = 1; rn = false; }
-                else if (a.is_null || b.is_null) rn = true;
-                else r = 0;
-                break;
-            }
-            case TGPU_EX_NOT: rn = a.is_null; r = a.bits == 0 ? 1 : 0; break;
-            case TGPU_EX_IS_NULL: r = a.is_null ? 1 : 0; break;
-            case TGPU_EX_IS_NOT_NULL: r = a.is_null ? 0 : 1; break;
-            case TGPU_EX_BETWEEN: {
-                // value BETWEEN min AND max  ==  value >= min AND value <= max (Kleene AND)
-                Value c = vm_fetch(in.c, cols, row, temps, tstride, nullbits);
-                bool n1 = a.is_null || b.is_null, n2 = a.is_null || c.is_null;
-                bool v1 = !n1 && vm_cmp(TGPU_EX_GE, in.vtype, a.bits, b.bits);
-                bool v2 = !n2 && vm_cmp(TGPU_EX_LE, in.vtype, a.bits, c.bits);
-                bool f1 = !n1 && !v1, f2 = !n2 && !v2;
-                if (f1 || f2) r = 0;
-                else if (n1 || n2) rn = true;
-                else r = 1;
-                break;
-            }
-            case TGPU_EX_CAST_BIGINT_TO_DOUBLE:
-                rn = a.is_null;
-                r = __double_as_longlong((double)a.bits);
-                break;
-            case TGPU_EX_CAST_DOUBLE_TO_BIGINT: {
-                rn = a.is_null;
-                if (rn) break;
-                double x = __longlong_as_double(a.bits);
-                // DoubleMath.roundToLong(x, HALF_UP): NaN / out of range is an error
-                if (!(x >= -9.2233720368547758e18 && x < 9.2233720368547758e18)) *err |= TG_ERR_BIT_OVERFLOW;
-                else r = llround(x);
-                break;
-            }
-            case TGPU_EX_IN: {
-                rn = a.is_null;
-                if (rn) break;
+        int64_t r;
+        bool rn;
+        if (in.op == TGPU_EX_IN) {
+            rn = a.is_null;
+            r = 0;
+            if (!rn) {
                 int li = (int)in.b.imm;
                 int off = prog->in_offset[li], cnt = prog->in_count[li];
                 bool hit = false;
                 for (int k = 0; k < cnt; k++) {
                     int64_t c = prog->in_values[off + k];
-                    hit |= dbl ? (__longlong_as_double(a.bits) == __longlong_as_double(c)) : (a.bits == c);
+                    hit |= in.vtype == TGPU_V_DOUBLE ? (__longlong_as_double(a.bits) == __longlong_as_double(c)) : (a.bits == c);
                 }
                 r = hit ? 1 : 0;
-                break;
             }
-            default: break;
+        }
+        else {
+            Value c;
+            c.bits = 0; c.is_null = true;
+            if (in.op == TGPU_EX_BETWEEN) c = vm_fetch(in.c, cols, row, temps, tstride, nullbits);
+            Value res = vm_apply(in.op, in.vtype, a, b, c, err);
+            r = res.bits;
+            rn = res.is_null;
         }
         temps[in.dst * tstride] = r;
         nullbits = (nullbits & ~(1u << in.dst)) | ((rn ? 1u : 0u) << in.dst);

@@ -26,7 +26,10 @@
 // one null bit each, <= 63 bits); other key shapes return NOT_SUPPORTED so the caller keeps the Java operator.
 #include <cub/cub.cuh>
 
+#include <map>
+
 #include "expr.cuh"
+#include "jit.cuh"
 
 namespace {
 
@@ -37,15 +40,11 @@ constexpr long long NO_ROW = 0x7FFFFFFFFFFFFFFFLL;
 constexpr int MAX_KEYS = 4;
 constexpr int MAX_SRCS = 16;
 constexpr int MAX_ACCS = 24;
-constexpr int S_THREADS = 256;
+constexpr int S_THREADS = TGD_S_THREADS;
+static_assert(TGD_MAX_CHANNELS == TGPU_MAX_CHANNELS, "channel limits differ");
 constexpr int S_GMAX = 64;             // regular groups the S path can hold (+2 special)
 constexpr int S_SPECIAL_NULL = 0;      // special slot for the NULL key (single-key case)
 constexpr int S_SPECIAL_SENTINEL = 1;  // special slot for a key whose bits equal EMPTY_KEY
-
-enum AccKind {
-    ACC_ROWS = 0, ACC_NONNULL = 1, ACC_SUM_F64 = 2, ACC_SUM_I64_LO = 3, ACC_SUM_I64_HI = 4,
-    ACC_MIN_F64 = 5, ACC_MAX_F64 = 6, ACC_MIN_I64 = 7, ACC_MAX_I64 = 8, ACC_SUM_F64_FROM_I64 = 9
-};
 
 struct SrcRef {
     int32_t is_temp;   // 0: channel of the input page, 1: VM temporary of the pre program
@@ -73,39 +72,16 @@ struct AggPlan {
     int32_t has_pre;
 };
 
-// ---- order-preserving encodings so MIN/MAX are plain integer min/max ---------------------------------
-__host__ __device__ __forceinline__ unsigned long long f64_order_key(long long bits)
-{
-    unsigned long long u = (unsigned long long)bits;
-    if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;   // NaN sorts last
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
-}
-__host__ __device__ __forceinline__ long long f64_from_order_key(unsigned long long k)
-{
-    return (long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
-}
-__host__ __device__ __forceinline__ unsigned long long i64_order_key(long long v) { return (unsigned long long)v ^ 0x8000000000000000ULL; }
+// which accumulators the specialised kernel really maintains: a NONNULL counter over an input that cannot be
+// NULL in this page is the row counter of the same mask, so it is dropped from the kernel and read back from the
+// ROWS accumulator when the CTA partials are merged.
+struct AccMap {
+    int32_t compact_count;
+    int32_t of_plan[MAX_ACCS];    // plan accumulator -> index in the kernel's compact accumulator space
+};
 
-__host__ __device__ __forceinline__ unsigned long long acc_init(int kind)
-{
-    switch (kind) {
-        case ACC_MIN_F64: case ACC_MIN_I64: return 0xFFFFFFFFFFFFFFFFULL;
-        default: return 0;   // sums, counts, MAX over order keys
-    }
-}
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ unsigned long long acc_combine(int kind, unsigned long long a, unsigned long long b)
-{
-    switch (kind) {
-        case ACC_SUM_F64: case ACC_SUM_F64_FROM_I64:
-            return (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a), __longlong_as_double((long long)b)));
-        case ACC_MIN_F64: case ACC_MIN_I64: return a < b ? a : b;
-        case ACC_MAX_F64: case ACC_MAX_I64: return a > b ? a : b;
-        default: return a + b;   // counts and the two halves of the 128-bit integer sum (carry handled by caller)
-    }
-}
-
 struct Fetched {
     long long bits;
     bool is_null;
@@ -155,28 +131,6 @@ __device__ __forceinline__ int pack_key(const AggPlan& plan, const DColumns& col
     return -1;
 }
 
-// one accumulator update of one row.  `p` points at the accumulator word(s); stride to the HI half is `hi_off`.
-__device__ __forceinline__ void acc_update_private(int kind, unsigned long long* p, long long hi_off, const Fetched& v)
-{
-    switch (kind) {
-        case ACC_ROWS: *p += 1; break;
-        case ACC_NONNULL: *p += 1; break;
-        case ACC_SUM_F64: *p = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), __longlong_as_double(v.bits))); break;
-        case ACC_SUM_F64_FROM_I64: *p = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)*p), (double)v.bits)); break;
-        case ACC_SUM_I64_LO: {
-            unsigned long long old = *p, add = (unsigned long long)v.bits, nw = old + add;
-            *p = nw;
-            p[hi_off] += (unsigned long long)((v.bits < 0 ? -1LL : 0LL) + (nw < old ? 1LL : 0LL));
-            break;
-        }
-        case ACC_MIN_F64: { unsigned long long k = f64_order_key(v.bits); if (k < *p) *p = k; break; }
-        case ACC_MAX_F64: { unsigned long long k = f64_order_key(v.bits); if (k > *p) *p = k; break; }
-        case ACC_MIN_I64: { unsigned long long k = i64_order_key(v.bits); if (k < *p) *p = k; break; }
-        case ACC_MAX_I64: { unsigned long long k = i64_order_key(v.bits); if (k > *p) *p = k; break; }
-        default: break;
-    }
-}
-
 __device__ __forceinline__ bool mask_selected(const AggPlan& plan, int mask, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits)
 {
     if (mask < 0) return true;
@@ -187,14 +141,6 @@ __device__ __forceinline__ bool mask_selected(const AggPlan& plan, int mask, con
 // =====================================================================================================
 // path S
 // =====================================================================================================
-struct SmallOut {
-    unsigned long long* blk_keys;    // [grid][L]
-    long long* blk_first;            // [grid][L+2]
-    unsigned long long* blk_acc;     // [grid][L+2][A]
-    int* overflow;
-    unsigned int* err;
-};
-
 // dynamic shared memory layout:
 //   unsigned long long tkeys[L]; long long lfirst[L+2]; unsigned long long acc[(L+2)*A*T]; int64 temps[8*T] (pre only)
 __global__ void __launch_bounds__(S_THREADS) agg_small_kernel(AggPlan plan, DColumns cols, const DProgram* __restrict__ prog, int64_t n, int L,
@@ -262,7 +208,7 @@ __global__ void __launch_bounds__(S_THREADS) agg_small_kernel(AggPlan plan, DCol
             if (!mask_selected(plan, d.mask, cols, row, temps, T, nb)) continue;
             if (d.src >= 0 && d.src != last_src) { v = fetch_src(plan.srcs[d.src], cols, row, temps, T, nb); last_src = d.src; }
             if (d.kind != ACC_ROWS && v.is_null) continue;
-            acc_update_private(d.kind, &acc[((size_t)slot * A + a) * T + tid], hi_off, v);
+            acc_update_private(d.kind, &acc[((size_t)slot * A + a) * T + tid], hi_off, v.bits);
         }
     }
     if (err) atomicOr(out.err, err);
@@ -318,7 +264,7 @@ struct AggState {
 };
 
 // single-CTA merge of the CTA partials of one page into the operator state (path S)
-__global__ void __launch_bounds__(256) agg_small_merge_kernel(AggPlan plan, DColumns cols, int B, int L, SmallOut part, AggState st, int* __restrict__ blk_ps)
+__global__ void __launch_bounds__(256) agg_small_merge_kernel(AggPlan plan, DColumns cols, int B, int L, SmallOut part, AggState st, int* __restrict__ blk_ps, AccMap map)
 {
     __shared__ unsigned long long pkeys[S_GMAX];
     __shared__ long long pfirst[S_GMAX + 2];
@@ -412,7 +358,7 @@ __global__ void __launch_bounds__(256) agg_small_merge_kernel(AggPlan plan, DCol
         for (int b = 0; b < B; b++) {
             for (int s = 0; s < L + 2; s++) {
                 if (blk_ps[b * (L + 2) + s] != ps) continue;
-                size_t at = ((size_t)b * (L + 2) + s) * A + a;
+                size_t at = ((size_t)b * (L + 2) + s) * map.compact_count + map.of_plan[a];
                 if (kind == ACC_SUM_I64_LO) {
                     unsigned long long o = r;
                     r += part.blk_acc[at];
@@ -721,6 +667,175 @@ __global__ void nullmap_pack_kernel(const unsigned char* __restrict__ is_null, i
 
 #endif  // __CUDACC__
 
+
+// =====================================================================================================
+// NVRTC specialisation of path S: straight-line typed code for the row program (filter + projections +
+// key packing + accumulator updates) plugged into agg_small_body<P> of device_lib.cuh.
+// =====================================================================================================
+static void appendf(std::string& s, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    s += buf;
+}
+
+static std::string gen_operand(const DOperand& o)
+{
+    char buf[128];
+    switch (o.kind) {
+        case TGPU_OPND_COLUMN: snprintf(buf, sizeof(buf), "Value{c%d, c%dn}", o.index, o.index); break;
+        case TGPU_OPND_TEMP: snprintf(buf, sizeof(buf), "Value{t%d, tn%d}", o.index, o.index); break;
+        case TGPU_OPND_CONST: snprintf(buf, sizeof(buf), "Value{(long long)0x%llxULL, false}", (unsigned long long)o.imm); break;
+        default: snprintf(buf, sizeof(buf), "Value{0, true}"); break;
+    }
+    return buf;
+}
+
+// `elems[c]` = element size of input channel c (0 = not a fixed-width column); bit c of nullable_mask = channel c has a validity bitmap
+static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* prog, const int* elems, int num_channels, int L, int min_blocks,
+                                        uint32_t nullable_mask, AccMap* map)
+{
+    std::string s;
+    bool used[TGPU_MAX_CHANNELS] = {false};
+    for (int i = 0; i < plan.num_srcs; i++)
+        if (!plan.srcs[i].is_temp) used[plan.srcs[i].index] = true;
+    // never-NULL analysis of the temporaries (straight-line program: one pass)
+    bool temp_nullable[TGPU_MAX_TEMPS];
+    for (int t = 0; t < TGPU_MAX_TEMPS; t++) temp_nullable[t] = true;
+    auto opnd_nullable = [&](const DOperand& o) {
+        switch (o.kind) {
+            case TGPU_OPND_COLUMN: return ((nullable_mask >> o.index) & 1) != 0;
+            case TGPU_OPND_TEMP: return temp_nullable[o.index];
+            case TGPU_OPND_CONST: return false;
+            default: return true;
+        }
+    };
+    if (prog) {
+        for (int i = 0; i < prog->num_insns; i++) {
+            const DInsn& in = prog->insns[i];
+            const DOperand* ops[3] = {&in.a, &in.b, &in.c};
+            for (auto* o : ops)
+                if (o->kind == TGPU_OPND_COLUMN) used[o->index] = true;
+            bool n;
+            switch (in.op) {
+                case TGPU_EX_IS_NULL: case TGPU_EX_IS_NOT_NULL: n = false; break;
+                case TGPU_EX_MOV: case TGPU_EX_NEG: case TGPU_EX_NOT: case TGPU_EX_CAST_BIGINT_TO_DOUBLE: case TGPU_EX_CAST_DOUBLE_TO_BIGINT: case TGPU_EX_IN:
+                    n = opnd_nullable(in.a); break;
+                case TGPU_EX_BETWEEN: n = opnd_nullable(in.a) || opnd_nullable(in.b) || opnd_nullable(in.c); break;
+                default: n = opnd_nullable(in.a) || opnd_nullable(in.b); break;
+            }
+            temp_nullable[in.dst] = n;
+        }
+    }
+    auto src_nullable = [&](int src) {
+        const SrcRef& r = plan.srcs[src];
+        return r.is_temp ? temp_nullable[r.index] : (((nullable_mask >> r.index) & 1) != 0);
+    };
+    // compact accumulator space
+    int compact = 0;
+    int kinds[MAX_ACCS];
+    for (int a = 0; a < plan.num_accs; a++) map->of_plan[a] = -1;
+    for (int a = 0; a < plan.num_accs; a++) {
+        const AccDesc& d = plan.accs[a];
+        if (d.kind == ACC_NONNULL && !src_nullable(d.src)) continue;   // aliased below
+        kinds[compact] = d.kind;
+        map->of_plan[a] = compact++;
+    }
+    for (int a = 0; a < plan.num_accs; a++) {
+        if (map->of_plan[a] >= 0) continue;
+        const AccDesc& d = plan.accs[a];
+        for (int r = 0; r < plan.num_accs; r++)
+            if (plan.accs[r].kind == ACC_ROWS && plan.accs[r].mask == d.mask) map->of_plan[a] = map->of_plan[r];
+    }
+    map->compact_count = compact;
+
+    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4;\n", L, compact);
+    s += "  __device__ static __forceinline__ int acc_kind(int a) {\n    switch (a) {\n";
+    for (int a = 0; a < compact; a++) appendf(s, "      case %d: return %d;\n", a, kinds[a]);
+    s += "      default: return 0;\n    }\n  }\n";
+    s += "  struct Regs {\n";
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++)
+        if (used[c]) appendf(s, "    long long c%d; bool c%dn;\n", c, c);
+    s += "  };\n";
+    for (int i = 0; i < plan.num_srcs; i++) appendf(s, "  long long v%d; bool vn%d;\n", i, i);
+    // all global loads of a row, nothing else: the body issues them for R rows back to back
+    s += "  __device__ __forceinline__ void load(const DColumns& cols, long long row, Regs& r) {\n";
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) {
+        if (!used[c]) continue;
+        appendf(s, "    r.c%d = tg_load_elem<%d>(cols.cols[%d].data, row);", c, elems[c], c);
+        if ((nullable_mask >> c) & 1) appendf(s, " r.c%dn = !tg_valid(cols.cols[%d].validity, row);\n", c, c);
+        else appendf(s, " r.c%dn = false;\n", c);
+    }
+    s += "  }\n";
+    s += "  __device__ __forceinline__ bool row(const Regs& r, unsigned long long* pk, int* special, unsigned int* err) {\n";
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++)
+        if (used[c]) appendf(s, "    const long long c%d = r.c%d; const bool c%dn = r.c%dn;\n", c, c, c, c);
+    if (prog) {
+        for (int t = 0; t < TGPU_MAX_TEMPS; t++) appendf(s, "    long long t%d = 0; bool tn%d = true;\n", t, t);
+        for (int i = 0; i < prog->num_insns; i++) {
+            const DInsn& in = prog->insns[i];
+            if (i == prog->num_filter_insns && prog->filter_temp >= 0)
+                appendf(s, "    if (tn%d || t%d == 0) return false;\n", prog->filter_temp, prog->filter_temp);
+            if (in.op == TGPU_EX_IN) {
+                int li = (int)in.b.imm;
+                appendf(s, "    { Value a = %s; bool hit = false;\n", gen_operand(in.a).c_str());
+                for (int k = 0; k < prog->in_count[li]; k++) {
+                    unsigned long long c = (unsigned long long)prog->in_values[prog->in_offset[li] + k];
+                    if (in.vtype == TGPU_V_DOUBLE) appendf(s, "      hit |= __longlong_as_double(a.bits) == __longlong_as_double((long long)0x%llxULL);\n", c);
+                    else appendf(s, "      hit |= a.bits == (long long)0x%llxULL;\n", c);
+                }
+                appendf(s, "      t%d = hit ? 1 : 0; tn%d = a.is_null; }\n", in.dst, in.dst);
+            }
+            else {
+                appendf(s, "    { Value x = vm_apply(%d, %d, %s, %s, %s, err); t%d = x.bits; tn%d = x.is_null; }\n", in.op, in.vtype,
+                        gen_operand(in.a).c_str(), gen_operand(in.b).c_str(), gen_operand(in.c).c_str(), in.dst, in.dst);
+            }
+        }
+        if (prog->num_filter_insns == prog->num_insns && prog->filter_temp >= 0)
+            appendf(s, "    if (tn%d || t%d == 0) return false;\n", prog->filter_temp, prog->filter_temp);
+    }
+    for (int i = 0; i < plan.num_srcs; i++) {
+        if (plan.srcs[i].is_temp) appendf(s, "    v%d = t%d; vn%d = tn%d;\n", i, plan.srcs[i].index, i, plan.srcs[i].index);
+        else appendf(s, "    v%d = c%d; vn%d = c%dn;\n", i, plan.srcs[i].index, i, plan.srcs[i].index);
+    }
+    if (plan.num_keys == 1) {
+        int k = plan.key_src[0];
+        appendf(s, "    if (vn%d) { *special = 0; return true; }\n    unsigned long long u = (unsigned long long)v%d;\n", k, k);
+        if (plan.key_is_double[0])
+            s += "    if ((u << 1) == 0) u = 0;\n    if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;\n";
+        s += "    if (u == TGD_EMPTY_KEY) { *special = 1; return true; }\n    *pk = u;\n";
+    }
+    else {
+        s += "    unsigned long long k = 0;\n";
+        int shift = 0;
+        for (int kk = 0; kk < plan.num_keys; kk++) {
+            int src = plan.key_src[kk], bits = plan.key_bits[kk];
+            appendf(s, "    k |= (vn%d ? 1ULL : ((((unsigned long long)v%d) & 0x%llxULL) << 1)) << %d;\n", src, src, (1ULL << bits) - 1, shift);
+            shift += bits + 1;
+        }
+        s += "    *pk = k;\n";
+    }
+    s += "    return true;\n  }\n";
+    s += "  __device__ __forceinline__ void accumulate(unsigned long long* acc, int T) {\n";
+    for (int a = 0; a < plan.num_accs; a++) {
+        const AccDesc& d = plan.accs[a];
+        if (d.kind == ACC_SUM_I64_HI) continue;
+        if (d.kind == ACC_NONNULL && !src_nullable(d.src)) continue;
+        std::string cond = "true";
+        if (d.mask >= 0) { char b[64]; snprintf(b, sizeof(b), "(!vn%d && v%d != 0)", d.mask, d.mask); cond = b; }
+        if (d.kind != ACC_ROWS && src_nullable(d.src)) { char b[64]; snprintf(b, sizeof(b), " && !vn%d", d.src); cond += b; }
+        if (d.kind == ACC_ROWS) appendf(s, "    if (%s) acc_update_private(%d, acc + %d * T, T, 0);\n", cond.c_str(), d.kind, map->of_plan[a]);
+        else appendf(s, "    if (%s) acc_update_private(%d, acc + %d * T, T, v%d);\n", cond.c_str(), d.kind, map->of_plan[a], d.src);
+    }
+    s += "  }\n};\n";
+    appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) tg_agg_small_jit(DColumns cols, long long n, SmallOut out) {\n", S_THREADS, min_blocks);
+    s += "  extern __shared__ unsigned long long smem_u64[];\n  Prog p;\n  agg_small_body(p, cols, n, out, smem_u64);\n}\n";
+    return s;
+}
+
 // =====================================================================================================
 // host side
 // =====================================================================================================
@@ -740,6 +855,10 @@ struct AggOp : tgpu_op {
     DProgram host_prog;
     DevBuf d_prog;
     std::vector<tgpu_projection> projections;
+    std::vector<tgpu_expr_insn> pre_insns;            // deep copy of the caller's program (its pointers die after create)
+    std::vector<std::vector<int64_t>> pre_in_values;
+    int32_t pre_filter_temp = -1, pre_num_filter_insns = 0;
+    tgpu_op* inner_fp = nullptr;                      // unfused FilterAndProject feeding the general path
     int32_t prog_max_channel = -1;
     bool gids_only = false;                  // tgpu_groupby_hash_* handle
 
@@ -747,6 +866,7 @@ struct AggOp : tgpu_op {
     bool planned = false;
     AggPlan plan;
     std::vector<int> key_types;
+    std::vector<int> src_channel;            // aggregation-input channel of every plan source
     std::vector<AggFnPlan> fnplans;
     std::vector<int> fn_input_types;         // tgpu_type of each aggregate's input (first state column for FINAL)
 
@@ -756,6 +876,9 @@ struct AggOp : tgpu_op {
     int64_t st_cap = 0;
     int64_t group_count = 0;
     // path S scratch
+    struct JitVariant { void* fn = nullptr; AccMap map; };
+    std::map<uint32_t, JitVariant> jit_variants;   // keyed by which channels carry a validity bitmap
+    std::vector<int> jit_elems;
     int s_L = 0, s_grid = 0;
     size_t s_smem = 0;
     DevBuf blk_keys, blk_first, blk_acc, blk_ps;
@@ -768,7 +891,11 @@ struct AggOp : tgpu_op {
     size_t next_out = 0;
 
     explicit AggOp(tgpu_ctx* c) : tgpu_op(c) {}
-    ~AggOp() override { for (size_t i = next_out; i < pending.size(); i++) delete pending[i]; }
+    ~AggOp() override
+    {
+        for (size_t i = next_out; i < pending.size(); i++) delete pending[i];
+        delete inner_fp;
+    }
 
     AggState state() const
     {
@@ -782,12 +909,15 @@ struct AggOp : tgpu_op {
         return s;
     }
 
-    int add_src(int is_temp, int index, int vtype)
+    // sources are identified by the channel of the aggregation input they stand for (a projection output when a
+    // pre-stage is fused), so the accumulator layout is the same with and without the fused pre-stage
+    int add_src(int is_temp, int index, int vtype, int agg_channel)
     {
         for (int i = 0; i < plan.num_srcs; i++)
-            if (plan.srcs[i].is_temp == is_temp && plan.srcs[i].index == index) return i;
+            if (src_channel[i] == agg_channel) return i;
         if (plan.num_srcs >= MAX_SRCS) return -1;
         plan.srcs[plan.num_srcs] = SrcRef{is_temp, index, vtype, 0};
+        src_channel.push_back(agg_channel);
         return plan.num_srcs++;
     }
 
@@ -797,17 +927,17 @@ struct AggOp : tgpu_op {
         if (!has_pre) {
             if (ch < 0 || ch >= (int)in.cols.size()) return -1;
             *type_out = in.cols[ch].type;
-            return add_src(0, ch, 0);
+            return add_src(0, ch, 0, ch);
         }
         if (ch < 0 || ch >= (int)projections.size()) return -1;
         const tgpu_projection& p = projections[ch];
         if (p.kind == 0) {
             if (p.index < 0 || p.index >= (int)in.cols.size()) return -1;
             *type_out = in.cols[p.index].type;
-            return add_src(0, p.index, 0);
+            return add_src(0, p.index, 0, ch);
         }
         *type_out = p.vtype == TGPU_V_DOUBLE ? TGPU_FLOAT64 : p.vtype == TGPU_V_BOOLEAN ? TGPU_INT8 : TGPU_INT64;
-        return add_src(1, p.index, p.vtype);
+        return add_src(1, p.index, p.vtype, ch);
     }
 
     int add_acc(int kind, int src, int mask)
@@ -826,6 +956,7 @@ struct AggOp : tgpu_op {
     int make_plan(const DevPage& in)
     {
         memset(&plan, 0, sizeof(plan));
+        src_channel.clear();
         plan.has_pre = has_pre ? 1 : 0;
         int nk = (int)key_channels.size();
         if (nk < 1) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "global aggregation (no GROUP BY keys) stays on the Java AggregationOperator");
@@ -913,6 +1044,10 @@ struct AggOp : tgpu_op {
             fnplans.push_back(fp);
         }
         if (plan.num_srcs >= MAX_SRCS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many distinct aggregate inputs");
+        // every non-null counter can fall back on the row counter of its mask when its input has no NULLs in a page
+        for (int a = 0, n0 = plan.num_accs; a < n0; a++)
+            if (plan.accs[a].kind == ACC_NONNULL && add_acc(ACC_ROWS, -1, plan.accs[a].mask) < 0)
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
         // accumulators sorted by source so the kernels fetch every source once per row
         // (indices are referenced by fnplans: keep positions, the kernels only cache the last source)
         planned = true;
@@ -959,8 +1094,16 @@ struct AggOp : tgpu_op {
         // path S configuration: the largest power-of-two L whose private accumulators fit with 2 CTAs/SM,
         // else 1 CTA/SM; L < 4 -> go straight to path G
         int A = plan.num_accs > 0 ? plan.num_accs : 1;
+        bool jit = jit_available();
+        if (jit) {
+            // the specialised kernel drops non-null counters of inputs that cannot be NULL: size for the common case
+            // (a page with more NULL-able inputs than fit falls back to the general path)
+            int opt = 0;
+            for (int a = 0; a < plan.num_accs; a++) opt += plan.accs[a].kind != ACC_NONNULL;
+            A = opt > 0 ? opt : 1;
+        }
         size_t per_slot = (size_t)A * S_THREADS * 8;
-        size_t fixed = (size_t)(has_pre ? TGPU_MAX_TEMPS * S_THREADS * 8 : 0) + 1024;
+        size_t fixed = (size_t)(has_pre && !jit ? TGPU_MAX_TEMPS * S_THREADS * 8 : 0) + 1024;
         size_t budget2 = (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) / 2 - 2048;
         size_t budget1 = (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) - 2048;
         s_L = 0;
@@ -996,13 +1139,47 @@ struct AggOp : tgpu_op {
         so.blk_acc = blk_acc.as<unsigned long long>();
         so.overflow = d_overflow;
         so.err = d_err;
-        static bool attr_set = false;
-        if (!attr_set || true) {
-            TG_CUDA(ctx, cudaFuncSetAttribute(agg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
-            attr_set = true;
+        // the kernel specialised for this row program (NVRTC, cached); the interpreter kernel when NVRTC is not there
+        AccMap map;
+        void* jit_fn = nullptr;
+        if (jit_available()) {
+            uint32_t nullable = 0;
+            int elems[TGPU_MAX_CHANNELS] = {0};
+            for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++) {
+                elems[c] = in.cols[c].elem_size();
+                if (in.cols[c].validity) nullable |= 1u << c;
+            }
+            if (jit_elems.empty()) jit_elems.assign(elems, elems + TGPU_MAX_CHANNELS);
+            for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++)
+                if (jit_elems[c] != elems[c]) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "channel %zu changed its type between pages", c);
+            auto it = jit_variants.find(nullable);
+            if (it == jit_variants.end()) {
+                JitVariant v;
+                std::string src = gen_agg_small_source(plan, has_pre ? &host_prog : nullptr, elems, (int)in.cols.size(), L, ctas_per_sm, nullable, &v.map);
+                // a generated program that does not compile is a bug, not a fallback case
+                TG_TRY(jit_get_function(ctx, src, "tg_agg_small_jit", &v.fn));
+                it = jit_variants.emplace(nullable, v).first;
+            }
+            jit_fn = it->second.fn;
+            map = it->second.map;
         }
-        TG_LAUNCH(ctx, agg_small_kernel, grid, S_THREADS, s_smem, plan, cols, has_pre ? d_prog.as<DProgram>() : nullptr, n, L, so);
-        TG_LAUNCH(ctx, agg_small_merge_kernel, 1, 256, 0, plan, cols, grid, L, so, state(), blk_ps.as<int>());
+        else {
+            map.compact_count = A;
+            for (int a = 0; a < MAX_ACCS; a++) map.of_plan[a] = a;
+        }
+        if (jit_fn) {
+            long long n_arg = n;
+            DColumns cols_arg = cols;
+            void* params[3] = {&cols_arg, &n_arg, &so};
+            size_t smem = (size_t)L * 8 + (size_t)(L + 2) * 8 + (size_t)(L + 2) * map.compact_count * S_THREADS * 8;
+            if (smem + 2048 > (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024)) { *overflowed = true; return TGPU_OK; }   // too many live accumulators for path S
+            TG_TRY(jit_launch(ctx, jit_fn, grid, S_THREADS, smem, params));
+        }
+        else {
+            TG_CUDA(ctx, cudaFuncSetAttribute(agg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
+            TG_LAUNCH(ctx, agg_small_kernel, grid, S_THREADS, s_smem, plan, cols, has_pre ? d_prog.as<DProgram>() : nullptr, n, L, so);
+        }
+        TG_LAUNCH(ctx, agg_small_merge_kernel, 1, 256, 0, plan, cols, grid, L, so, state(), blk_ps.as<int>(), map);
         // one small readback per page: overflow flag + error bits, then the group count
         int64_t word = 0;
         TG_TRY(tg_read_i64(ctx, d_overflow, &word));
@@ -1039,6 +1216,26 @@ struct AggOp : tgpu_op {
     int switch_to_general()
     {
         use_general = true;
+        if (has_pre) {
+            // the general path works on materialised projection outputs: un-fuse the pre-stage into its own
+            // FilterAndProject (the reference's own operator chain) and re-point every source at its output channel
+            std::vector<tgpu_in_list> lists(pre_in_values.size());
+            for (size_t i = 0; i < lists.size(); i++) { lists[i].count = (int32_t)pre_in_values[i].size(); lists[i].values = pre_in_values[i].data(); }
+            tgpu_expr_program prog;
+            memset(&prog, 0, sizeof(prog));
+            prog.num_insns = (int32_t)pre_insns.size();
+            prog.insns = pre_insns.data();
+            prog.filter_temp = pre_filter_temp;
+            prog.num_filter_insns = pre_num_filter_insns;
+            prog.num_projections = (int32_t)projections.size();
+            prog.projections = projections.data();
+            prog.num_in_lists = (int32_t)lists.size();
+            prog.in_lists = lists.data();
+            TG_TRY(tgpu_filter_project_create(ctx, &prog, &inner_fp));
+            for (int i = 0; i < plan.num_srcs; i++) plan.srcs[i] = SrcRef{0, src_channel[i], 0, 0};
+            plan.has_pre = 0;
+            has_pre = false;
+        }
         TG_TRY(g_special.alloc(ctx, sizeof(GSpecial)));
         GSpecial init;
         init.gid[0] = init.gid[1] = -1;
@@ -1129,17 +1326,16 @@ struct AggOp : tgpu_op {
     int add_input(const tgpu_page* page) override
     {
         if (page->num_rows == 0) return TGPU_OK;
+        if (use_general && inner_fp) return add_via_filter_project(page);
         DevPage in;
         TG_TRY(tg_ingest_page(ctx, page, &in));
-        return add_device_page(in);
-    }
-
-    int add_device_page(const DevPage& in)
-    {
         if (!planned) {
             TG_TRY(make_plan(in));
             TG_TRY(init_state());
-            if (use_general) TG_TRY(switch_to_general());
+            if (use_general) {
+                TG_TRY(switch_to_general());
+                if (inner_fp) return add_via_filter_project(page);
+            }
         }
         if (has_pre && prog_max_channel >= (int)in.cols.size())
             return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "pre-stage reads channel %d, page has %zu", prog_max_channel, in.cols.size());
@@ -1150,9 +1346,24 @@ struct AggOp : tgpu_op {
             TG_TRY(run_small(in, cols, &overflowed));
             if (!overflowed) return after_page();
             TG_TRY(switch_to_general());
+            if (inner_fp) return add_via_filter_project(page);
         }
-        if (has_pre) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "fused pre-stage with more than %d groups: run FilterAndProject as its own operator", S_GMAX);
         TG_TRY(run_general(in, cols));
+        return after_page();
+    }
+
+    int add_via_filter_project(const tgpu_page* page)
+    {
+        TG_TRY(inner_fp->add_input(page));
+        while (true) {
+            OwnedPage* o = nullptr;
+            TG_TRY(inner_fp->get_output(&o));
+            if (!o) break;
+            std::unique_ptr<OwnedPage> guard(o);
+            DColumns cols;
+            TG_TRY(fill_cols(o->page, &cols));
+            TG_TRY(run_general(o->page, cols));
+        }
         return after_page();
     }
 
@@ -1321,6 +1532,11 @@ int build_agg_op(tgpu_ctx* ctx, const tgpu_agg_spec* spec, AggOp** out)
         op->has_pre = true;
         TG_TRY(tg::expr_compile(ctx, spec->pre, &op->host_prog, &op->prog_max_channel));
         op->projections.assign(spec->pre->projections, spec->pre->projections + spec->pre->num_projections);
+        op->pre_insns.assign(spec->pre->insns, spec->pre->insns + spec->pre->num_insns);
+        for (int i = 0; i < spec->pre->num_in_lists; i++)
+            op->pre_in_values.emplace_back(spec->pre->in_lists[i].values, spec->pre->in_lists[i].values + spec->pre->in_lists[i].count);
+        op->pre_filter_temp = spec->pre->filter_temp;
+        op->pre_num_filter_insns = spec->pre->num_filter_insns;
         TG_TRY(op->d_prog.alloc(ctx, sizeof(DProgram)));
         TG_CUDA(ctx, cudaMemcpyAsync(op->d_prog.p, &op->host_prog, sizeof(DProgram), cudaMemcpyHostToDevice, ctx->stream));
         TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1389,5 +1605,44 @@ extern "C" int tgpu_groupby_hash_get_group_ids(tgpu_op* op, const tgpu_page* pag
     TG_TRY(a->run_general_ids(in, cols, gids.as<int>()));
     TG_CUDA(ctx, cudaMemcpyAsync(out_group_ids, gids.p, (size_t)in.rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return TGPU_OK;
+}
+
+// test hook (no GPU needed): generate + NVRTC-compile the specialised small-group kernel for a spec whose input
+// channels have the given tgpu_types; returns the cubin size in *cubin_bytes and the generated source length
+extern "C" int tgpu_jit_selftest_agg(const tgpu_agg_spec* spec, const int32_t* channel_types, int32_t num_channels, uint32_t nullable_mask, int64_t* cubin_bytes, char* source_out, int64_t source_cap)
+{
+    if (!spec || !channel_types || !cubin_bytes) return TGPU_ERR_INVALID_ARGUMENT;
+    tgpu_ctx fake;
+    AggOp* op = nullptr;
+    {
+        // build_agg_op touches the device only when a pre-program has to be uploaded: mimic it on the host
+        std::unique_ptr<AggOp> o(new AggOp(&fake));
+        o->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_keys);
+        o->fns.assign(spec->aggs, spec->aggs + spec->num_aggs);
+        o->step = spec->step;
+        if (spec->pre) {
+            o->has_pre = true;
+            int st = tg::expr_compile(&fake, spec->pre, &o->host_prog, &o->prog_max_channel);
+            if (st != TGPU_OK) return st;
+            o->projections.assign(spec->pre->projections, spec->pre->projections + spec->pre->num_projections);
+        }
+        op = o.release();
+    }
+    std::unique_ptr<AggOp> guard(op);
+    DevPage in;
+    in.rows = 0;
+    in.cols.resize(num_channels);
+    int elems[TGPU_MAX_CHANNELS] = {0};
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) { in.cols[c].type = channel_types[c]; elems[c] = in.cols[c].elem_size(); }
+    int st = op->make_plan(in);
+    if (st != TGPU_OK) return st;
+    AccMap map;
+    std::string src = gen_agg_small_source(op->plan, op->has_pre ? &op->host_prog : nullptr, elems, num_channels, 4, 2, nullable_mask, &map);
+    if (source_out && source_cap > 0) { strncpy(source_out, src.c_str(), (size_t)source_cap - 1); source_out[source_cap - 1] = 0; }
+    std::string cubin;
+    st = tg::jit_compile_cubin(&fake, src, &cubin);
+    if (st != TGPU_OK) { if (source_out && source_cap > 0) { strncpy(source_out, fake.err.c_str(), (size_t)source_cap - 1); source_out[source_cap - 1] = 0; } return st; }
+    *cubin_bytes = (int64_t)cubin.size();
     return TGPU_OK;
 }

@@ -154,6 +154,133 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
     }
 }
 
+
+// Fused probe + build-side gather for the common join shape (no duplicate chains, fixed-width non-null build
+// columns): the chain head is looked up and the build payload of the matching row is fetched while the slot is
+// still in flight in the same thread, so the positions never make a round trip through HBM before the gather and
+// no count/scan pass is needed when every probe row matches (FK -> PK joins).  Misses are counted; the host
+// compacts only when there are any.
+struct GatherCols {
+    int count;
+    int elem[4];
+    const void* src[4];
+    void* dst[4];
+};
+
+template <int ROWS, bool INT64_NO_NULLS>
+__global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
+                                                                int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
+{
+    int64_t tile = (int64_t)blockDim.x * ROWS;
+    int64_t tiles = (n + tile - 1) / tile;
+    unsigned int matched = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int64_t base = t * tile + threadIdx.x;
+        unsigned long long k[ROWS];
+        bool ok[ROWS];
+        int4 s[ROWS];
+        unsigned long long pos[ROWS];
+        int res[ROWS];
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            int64_t i = base + (int64_t)j * blockDim.x;
+            ok[j] = false;
+            k[j] = 0;
+            if (i < n) {
+                if (INT64_NO_NULLS) { k[j] = (unsigned long long)__ldg((const long long*)key.data + i); ok[j] = true; }
+                else ok[j] = join_key(key, kind, i, &k[j]);
+            }
+            pos[j] = tg::murmur3_mix(k[j]) & mask;
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            if (ok[j] && k[j] != EMPTY_KEY) s[j] = __ldg((const int4*)&table[pos[j]]);
+            else s[j] = make_int4(0, (int)0x80000000, -1, 0);
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            int r = -1;
+            if (ok[j]) {
+                if (k[j] == EMPTY_KEY) r = special_head;
+                else {
+                    unsigned long long p = pos[j];
+                    int4 cur = s[j];
+                    while (true) {
+                        unsigned long long sk = (unsigned long long)(unsigned int)cur.x | ((unsigned long long)(unsigned int)cur.y << 32);
+                        if (sk == k[j]) { r = cur.z; break; }
+                        if (sk == EMPTY_KEY) break;
+                        p = (p + 1) & mask;
+                        cur = __ldg((const int4*)&table[p]);
+                    }
+                }
+            }
+            res[j] = r;
+        }
+        // build payload: ROWS x columns independent random loads, then coalesced stores
+        for (int c = 0; c < g.count; c++) {
+            long long v[ROWS];
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) {
+                v[j] = 0;
+                if (res[j] >= 0) {
+                    switch (g.elem[c]) {
+                        case 8: v[j] = __ldg((const long long*)g.src[c] + res[j]); break;
+                        case 4: v[j] = __ldg((const int*)g.src[c] + res[j]); break;
+                        case 2: v[j] = __ldg((const short*)g.src[c] + res[j]); break;
+                        default: v[j] = __ldg((const signed char*)g.src[c] + res[j]); break;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) {
+                int64_t i = base + (int64_t)j * blockDim.x;
+                if (i >= n) continue;
+                switch (g.elem[c]) {
+                    case 8: ((long long*)g.dst[c])[i] = v[j]; break;
+                    case 4: ((int*)g.dst[c])[i] = (int)v[j]; break;
+                    case 2: ((short*)g.dst[c])[i] = (short)v[j]; break;
+                    default: ((signed char*)g.dst[c])[i] = (signed char)v[j]; break;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < ROWS; j++) {
+            int64_t i = base + (int64_t)j * blockDim.x;
+            if (i >= n) continue;
+            out[i] = res[j];
+            matched += res[j] >= 0;
+        }
+    }
+    // one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) matched += __shfl_xor_sync(0xffffffffu, matched, off);
+    if ((threadIdx.x & 31) == 0 && matched) atomicAdd(match_count, (unsigned long long)matched);
+}
+
+// validity bitmap of the build side of a PROBE_OUTER join: bit i = (jp[i] >= 0)
+__global__ void join_match_validity_kernel(const int* __restrict__ jp, int64_t n, uint8_t* __restrict__ bitmap)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nbytes = (n + 7) >> 3;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; b < nbytes; b += stride) {
+        unsigned int v = 0;
+        int64_t base = b << 3;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int64_t i = base + k;
+            if (i < n && jp[i] >= 0) v |= 1u << k;
+        }
+        bitmap[b] = (uint8_t)v;
+    }
+}
+
+__global__ void join_match_flags_kernel(const int* __restrict__ jp, int64_t n, uint8_t* __restrict__ flags)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) flags[i] = jp[i] >= 0 ? 1 : 0;
+}
+
 // --- duplicate chains -------------------------------------------------------------------------------
 // sort key = (slot << 32 | row) for rows that are in the table; rows with NULL keys sort last
 __global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
@@ -451,6 +578,96 @@ struct JoinProbeOp : tgpu_op {
 
     bool needs_input() override { return !finishing && next_out >= pending.size(); }
 
+
+    // fused probe + gather (see join_probe_gather_kernel); returns handled=false when the shape needs the general path
+    int fast_path(DevPage& in, const DevColumn& key, int64_t n, bool* handled)
+    {
+        *handled = false;
+        bool outer = join_type == TGPU_JOIN_PROBE_OUTER;
+        if (lookup->has_dups && !single_match) return TGPU_OK;
+        if (lookup->num_output > 4 || key.type == TGPU_UTF8) return TGPU_OK;
+        if (key_kind_of(key.type) != key_kind_of(lookup->key_type)) return TGPU_OK;   // reported by the general path
+        for (int32_t b = 0; b < lookup->num_output; b++) {
+            const DevColumn& c = lookup->store.cols[1 + b];
+            if (c.elem_size() == 0 || c.validity) return TGPU_OK;
+        }
+        auto jp = std::make_shared<DevBuf>();
+        TG_TRY(jp->alloc(ctx, (size_t)n * 4));
+        GatherCols g;
+        memset(&g, 0, sizeof(g));
+        g.count = lookup->num_output;
+        std::vector<DevColumn> built(lookup->num_output);
+        for (int32_t b = 0; b < lookup->num_output; b++) {
+            const DevColumn& c = lookup->store.cols[1 + b];
+            built[b].type = c.type;
+            built[b].length = n;
+            built[b].own_data = std::make_shared<DevBuf>();
+            TG_TRY(built[b].own_data->alloc(ctx, (size_t)n * c.elem_size()));
+            built[b].data = built[b].own_data->p;
+            g.elem[b] = c.elem_size();
+            g.src[b] = c.data;
+            g.dst[b] = built[b].own_data->p;
+        }
+        unsigned long long* d_matches = (unsigned long long*)(ctx->d_scratch + 12);
+        TG_CUDA(ctx, cudaMemsetAsync(d_matches, 0, 8, ctx->stream));
+        constexpr int ROWS = 4;
+        int grid = tg_grid(ctx, n, 256 * ROWS, 8);
+        auto k_fast = join_probe_gather_kernel<ROWS, true>;
+        auto k_any = join_probe_gather_kernel<ROWS, false>;
+        const JoinSlot* table = lookup->table.as<JoinSlot>();
+        if (key.type == TGPU_INT64 && !key.validity)
+            TG_LAUNCH(ctx, k_fast, grid, 256, 0, tg_colref(key), KEY_INT, n, table, lookup->mask, lookup->special_head, jp->as<int>(), g, d_matches);
+        else
+            TG_LAUNCH(ctx, k_any, grid, 256, 0, tg_colref(key), key_kind_of(key.type), n, table, lookup->mask, lookup->special_head, jp->as<int>(), g, d_matches);
+        int64_t matches = 0;
+        TG_TRY(tg_read_i64(ctx, d_matches, &matches));
+        *handled = true;
+        DevPage outp;
+        if (matches == n || outer) {
+            // every probe row yields exactly one output row: probe blocks pass through
+            // (LookupJoinPageBuilder.build :144-150 "outputProbeBlocksDirectly")
+            outp.rows = n;
+            for (int32_t ch : output_channels) outp.cols.push_back(in.cols[ch]);
+            std::shared_ptr<DevBuf> validity;
+            if (matches < n) {
+                validity = std::make_shared<DevBuf>();
+                TG_TRY(validity->alloc(ctx, (size_t)((n + 7) / 8)));
+                TG_LAUNCH(ctx, join_match_validity_kernel, tg_grid(ctx, (n + 7) / 8, 256, 8), 256, 0, jp->as<int>(), n, validity->as<uint8_t>());
+            }
+            for (auto& c : built) {
+                if (validity) { c.own_validity = validity; c.validity = validity->as<uint8_t>(); }
+                outp.cols.push_back(std::move(c));
+            }
+        }
+        else {
+            if (matches == 0) return TGPU_OK;
+            // compact the matched rows (stable): selection list, then sequential-read gathers
+            DevBuf flags, sel, tmp;
+            TG_TRY(flags.alloc(ctx, (size_t)n));
+            TG_TRY(sel.alloc(ctx, (size_t)n * 4));
+            TG_LAUNCH(ctx, join_match_flags_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, jp->as<int>(), n, flags.as<uint8_t>());
+            long long* d_count = (long long*)(ctx->d_scratch + 14);
+            size_t tmp_bytes = 0;
+            cub::CountingInputIterator<int32_t> iota(0);
+            cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream);
+            TG_TRY(tmp.alloc(ctx, tmp_bytes));
+            TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream));
+            outp.rows = matches;
+            for (int32_t ch : output_channels) {
+                DevColumn c;
+                TG_TRY(tg_gather_column(ctx, in.cols[ch], sel.as<int32_t>(), matches, false, &c));
+                outp.cols.push_back(std::move(c));
+            }
+            for (auto& b : built) {
+                DevColumn c;
+                TG_TRY(tg_gather_column(ctx, b, sel.as<int32_t>(), matches, false, &c));
+                outp.cols.push_back(std::move(c));
+            }
+        }
+        pending.push_back(tg_make_owned_page(std::move(outp)));
+        return TGPU_OK;
+    }
+
     int add_input(const tgpu_page* page) override
     {
         pending.clear();
@@ -461,7 +678,14 @@ struct JoinProbeOp : tgpu_op {
         DevPage in;
         TG_TRY(tg_ingest_page(ctx, page, &in));
         if (key_channels[0] < 0 || key_channels[0] >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key channel out of range");
+        for (int32_t ch : output_channels)
+            if (ch < 0 || ch >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe output channel out of range");
         const DevColumn& key = in.cols[key_channels[0]];
+        if (!getenv("TGPU_JOIN_GENERAL_PATH")) {
+            bool handled = false;
+            TG_TRY(fast_path(in, key, n, &handled));
+            if (handled) return TGPU_OK;
+        }
         // joinPositionCache (JoinProbe.java:112-180)
         auto jp = std::make_shared<DevBuf>();
         TG_TRY(jp->alloc(ctx, (size_t)(n + 1) * 4));
