@@ -325,6 +325,7 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
     const int64_t stride = (int64_t)gridDim.x * T;
     bool stop = false;
     for (int64_t base = (int64_t)blockIdx.x * T + tid; base < n && !stop; base += stride * R) {
+        if (*((volatile int*)&s_overflow)) break;   // some thread of this CTA ran out of key slots: the pass is void
         typename P::Regs regs[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {

@@ -877,10 +877,10 @@ struct AggOp : tgpu_op {
     int64_t group_count = 0;
     // path S scratch
     struct JitVariant { void* fn = nullptr; AccMap map; };
-    std::map<uint32_t, JitVariant> jit_variants;   // keyed by which channels carry a validity bitmap
+    std::map<uint64_t, JitVariant> jit_variants;   // keyed by (L, which channels carry a validity bitmap)
     std::vector<int> jit_elems;
     int s_L = 0, s_grid = 0;
-    size_t s_smem = 0;
+    size_t s_smem = 0, s_per_slot = 0, s_fixed = 0;
     DevBuf blk_keys, blk_first, blk_acc, blk_ps;
     // path G
     DevBuf g_table, g_special;
@@ -1091,37 +1091,45 @@ struct AggOp : tgpu_op {
         st_cap = 0;
         TG_TRY(alloc_state(S_GMAX + 2));
         use_general = gids_only;
-        // path S configuration: the largest power-of-two L whose private accumulators fit with 2 CTAs/SM,
-        // else 1 CTA/SM; L < 4 -> go straight to path G
+        // path S configuration.  Per-thread private accumulators cost (L+2) x A x 8 bytes of shared memory per
+        // thread, so the number of key slots per CTA (L) trades directly against resident warps: start with L = 4
+        // (most warps in flight) and escalate 4 -> 8 -> 16 -> 32 when a CTA meets more distinct keys than fit;
+        // beyond that the general path takes over.
         int A = plan.num_accs > 0 ? plan.num_accs : 1;
         bool jit = jit_available();
         if (jit) {
             // the specialised kernel drops non-null counters of inputs that cannot be NULL: size for the common case
-            // (a page with more NULL-able inputs than fit falls back to the general path)
             int opt = 0;
             for (int a = 0; a < plan.num_accs; a++) opt += plan.accs[a].kind != ACC_NONNULL;
             A = opt > 0 ? opt : 1;
         }
-        size_t per_slot = (size_t)A * S_THREADS * 8;
-        size_t fixed = (size_t)(has_pre && !jit ? TGPU_MAX_TEMPS * S_THREADS * 8 : 0) + 1024;
-        size_t budget2 = (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) / 2 - 2048;
-        size_t budget1 = (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) - 2048;
+        s_per_slot = (size_t)A * S_THREADS * 8;
+        s_fixed = (size_t)(has_pre && !jit ? TGPU_MAX_TEMPS * S_THREADS * 8 : 0) + 1024;
         s_L = 0;
-        for (int L = 32; L >= 4; L >>= 1) {
-            size_t need = fixed + (size_t)(L + 2) * per_slot + (size_t)L * 8 + (size_t)(L + 2) * 8;
-            if (need <= budget2 || (L <= 8 && need <= budget1)) { s_L = L; s_smem = need; break; }
-        }
-        if (s_L == 0) use_general = true;
+        s_grid = 0;
+        if (!set_small_L(4)) use_general = true;
         if (expected_groups > S_GMAX * 4) use_general = true;   // planner expects many groups: skip the S attempt
         return TGPU_OK;
     }
 
     // ---- path S -----------------------------------------------------------------------------------
+    size_t smem_limit() const { return (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) - 2048; }
+
+    bool set_small_L(int L)
+    {
+        size_t need = s_fixed + (size_t)(L + 2) * s_per_slot + (size_t)L * 8 + (size_t)(L + 2) * 8;
+        if (L > 32 || need > smem_limit()) return false;
+        s_L = L;
+        s_smem = need;
+        s_grid = 0;   // CTA partial buffers are re-sized for the new L
+        return true;
+    }
+
     int run_small(const DevPage& in, const DColumns& cols, bool* overflowed)
     {
         int64_t n = in.rows;
         int L = s_L, A = plan.num_accs;
-        int ctas_per_sm = s_smem <= ((ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024) / 2 - 2048) ? 2 : 1;
+        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (smem_limit() + 2048) / (s_smem + 1024)));
         int grid = tg_grid(ctx, n, S_THREADS * 4, ctas_per_sm);
         if (grid != s_grid) {
             TG_TRY(blk_keys.alloc(ctx, (size_t)grid * L * 8));
@@ -1152,13 +1160,14 @@ struct AggOp : tgpu_op {
             if (jit_elems.empty()) jit_elems.assign(elems, elems + TGPU_MAX_CHANNELS);
             for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++)
                 if (jit_elems[c] != elems[c]) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "channel %zu changed its type between pages", c);
-            auto it = jit_variants.find(nullable);
+            uint64_t vkey = ((uint64_t)L << 32) | nullable;
+            auto it = jit_variants.find(vkey);
             if (it == jit_variants.end()) {
                 JitVariant v;
                 std::string src = gen_agg_small_source(plan, has_pre ? &host_prog : nullptr, elems, (int)in.cols.size(), L, ctas_per_sm, nullable, &v.map);
                 // a generated program that does not compile is a bug, not a fallback case
                 TG_TRY(jit_get_function(ctx, src, "tg_agg_small_jit", &v.fn));
-                it = jit_variants.emplace(nullable, v).first;
+                it = jit_variants.emplace(vkey, v).first;
             }
             jit_fn = it->second.fn;
             map = it->second.map;
@@ -1342,9 +1351,14 @@ struct AggOp : tgpu_op {
         DColumns cols;
         TG_TRY(fill_cols(in, &cols));
         if (!use_general) {
-            bool overflowed = false;
-            TG_TRY(run_small(in, cols, &overflowed));
-            if (!overflowed) return after_page();
+            while (true) {
+                bool overflowed = false;
+                TG_TRY(run_small(in, cols, &overflowed));
+                if (!overflowed) return after_page();
+                // the state is untouched by an overflowed pass: retry the page with more key slots per CTA
+                if (group_count + 2 <= S_GMAX && set_small_L(s_L * 2)) continue;
+                break;
+            }
             TG_TRY(switch_to_general());
             if (inner_fp) return add_via_filter_project(page);
         }

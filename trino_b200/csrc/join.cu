@@ -34,6 +34,21 @@ struct __align__(16) JoinSlot {
 
 enum KeyKind { KEY_INT = 0, KEY_DOUBLE = 1 };
 
+// Slot of a key and the probe sequence: mix(key) & mask with linear probing, like the reference
+// (M/operator/join/PagesHash.java:35-51, BigintPagesHash.java:116,165).  Measured alternative (round 1): keeping the 8 keys
+// of one key >> 3 group inside one 128-byte line turned TPC-H's clustered probes sequential but doubled the probe time,
+// because TPC-H order keys (8 used, 24 skipped) load the lines very unevenly; see DESIGN.md.
+__host__ __device__ __forceinline__ unsigned long long join_slot_of(unsigned long long k, unsigned long long mask)
+{
+    return tg::murmur3_mix(k) & mask;
+}
+
+__host__ __device__ __forceinline__ unsigned long long join_next_slot(unsigned long long pos, unsigned long long k, unsigned long long mask)
+{
+    (void)k;
+    return (pos + 1) & mask;
+}
+
 // canonical 64-bit join key; returns false when the row can never match (NULL, or NaN under EQUAL)
 __device__ __forceinline__ bool join_key(const ColRef& c, int kind, int64_t i, unsigned long long* out)
 {
@@ -71,7 +86,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
             if (old >= 0) *dup_flag = 1;
             continue;
         }
-        unsigned long long pos = tg::murmur3_mix(k) & mask;
+        unsigned long long pos = join_slot_of(k, mask);
         while (true) {
             unsigned long long cur = *((volatile unsigned long long*)&table[pos].key);
             if (cur == EMPTY_KEY) cur = atomicCAS(&table[pos].key, EMPTY_KEY, k);
@@ -80,7 +95,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
                 if (old >= 0) *dup_flag = 1;
                 break;
             }
-            pos = (pos + 1) & mask;
+            pos = join_next_slot(pos, k, mask);
         }
     }
 }
@@ -88,13 +103,13 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
 __device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, unsigned long long mask, unsigned long long k, int special_head)
 {
     if (k == EMPTY_KEY) return special_head;
-    unsigned long long pos = tg::murmur3_mix(k) & mask;
+    unsigned long long pos = join_slot_of(k, mask);
     while (true) {
         int4 s = __ldg((const int4*)&table[pos]);
         unsigned long long sk = (unsigned long long)(unsigned int)s.x | ((unsigned long long)(unsigned int)s.y << 32);
         if (sk == k) return s.z;
         if (sk == EMPTY_KEY) return -1;
-        pos = (pos + 1) & mask;
+        pos = join_next_slot(pos, k, mask);
     }
 }
 
@@ -123,7 +138,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
                 if (INT64_NO_NULLS) { k[j] = (unsigned long long)__ldg((const long long*)key.data + i); ok[j] = true; }
                 else ok[j] = join_key(key, kind, i, &k[j]);
             }
-            pos[j] = tg::murmur3_mix(k[j]) & mask;
+            pos[j] = join_slot_of(k[j], mask);
         }
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
@@ -144,7 +159,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
                         unsigned long long sk = (unsigned long long)(unsigned int)cur.x | ((unsigned long long)(unsigned int)cur.y << 32);
                         if (sk == k[j]) { res = cur.z; break; }
                         if (sk == EMPTY_KEY) break;
-                        p = (p + 1) & mask;
+                        p = join_next_slot(p, k[j], mask);
                         cur = __ldg((const int4*)&table[p]);
                     }
                 }
@@ -162,6 +177,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
 // compacts only when there are any.
 struct GatherCols {
     int count;
+    int by_slot;
     int elem[4];
     const void* src[4];
     void* dst[4];
@@ -171,6 +187,7 @@ template <int ROWS, bool INT64_NO_NULLS>
 __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
                                                                 int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
 {
+    // g.by_slot: payload arrays are indexed by table slot (special key at index mask + 1), else by build row id
     int64_t tile = (int64_t)blockDim.x * ROWS;
     int64_t tiles = (n + tile - 1) / tile;
     unsigned int matched = 0;
@@ -181,6 +198,7 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
         int4 s[ROWS];
         unsigned long long pos[ROWS];
         int res[ROWS];
+        long long at[ROWS];      // index into the payload arrays
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
             int64_t i = base + (int64_t)j * blockDim.x;
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
                 if (INT64_NO_NULLS) { k[j] = (unsigned long long)__ldg((const long long*)key.data + i); ok[j] = true; }
                 else ok[j] = join_key(key, kind, i, &k[j]);
             }
-            pos[j] = tg::murmur3_mix(k[j]) & mask;
+            pos[j] = join_slot_of(k[j], mask);
         }
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
@@ -200,21 +218,23 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
             int r = -1;
+            long long where = 0;
             if (ok[j]) {
-                if (k[j] == EMPTY_KEY) r = special_head;
+                if (k[j] == EMPTY_KEY) { r = special_head; where = (long long)mask + 1; }
                 else {
                     unsigned long long p = pos[j];
                     int4 cur = s[j];
                     while (true) {
                         unsigned long long sk = (unsigned long long)(unsigned int)cur.x | ((unsigned long long)(unsigned int)cur.y << 32);
-                        if (sk == k[j]) { r = cur.z; break; }
+                        if (sk == k[j]) { r = cur.z; where = (long long)p; break; }
                         if (sk == EMPTY_KEY) break;
-                        p = (p + 1) & mask;
+                        p = join_next_slot(p, k[j], mask);
                         cur = __ldg((const int4*)&table[p]);
                     }
                 }
             }
             res[j] = r;
+            at[j] = g.by_slot ? where : (long long)r;
         }
         // build payload: ROWS x columns independent random loads, then coalesced stores
         for (int c = 0; c < g.count; c++) {
@@ -224,10 +244,10 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
                 v[j] = 0;
                 if (res[j] >= 0) {
                     switch (g.elem[c]) {
-                        case 8: v[j] = __ldg((const long long*)g.src[c] + res[j]); break;
-                        case 4: v[j] = __ldg((const int*)g.src[c] + res[j]); break;
-                        case 2: v[j] = __ldg((const short*)g.src[c] + res[j]); break;
-                        default: v[j] = __ldg((const signed char*)g.src[c] + res[j]); break;
+                        case 8: v[j] = __ldg((const long long*)g.src[c] + at[j]); break;
+                        case 4: v[j] = __ldg((const int*)g.src[c] + at[j]); break;
+                        case 2: v[j] = __ldg((const short*)g.src[c] + at[j]); break;
+                        default: v[j] = __ldg((const signed char*)g.src[c] + at[j]); break;
                     }
                 }
             }
@@ -281,6 +301,25 @@ __global__ void join_match_flags_kernel(const int* __restrict__ jp, int64_t n, u
     for (; i < n; i += stride) flags[i] = jp[i] >= 0 ? 1 : 0;
 }
 
+// build payload re-laid out in SLOT order (one pass at build time): the fused probe then reads the payload right next
+// to where it found the key instead of chasing the row id into the (arbitrarily ordered) build pages
+__global__ void join_payload_by_slot_kernel(const JoinSlot* __restrict__ table, int64_t slots, int special_head, const void* __restrict__ src, int elem,
+                                            void* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= slots; i += stride) {
+        int head = i < slots ? table[i].head : special_head;
+        if (head < 0) continue;
+        switch (elem) {
+            case 8: ((long long*)dst)[i] = ((const long long*)src)[head]; break;
+            case 4: ((int*)dst)[i] = ((const int*)src)[head]; break;
+            case 2: ((short*)dst)[i] = ((const short*)src)[head]; break;
+            default: ((signed char*)dst)[i] = ((const signed char*)src)[head]; break;
+        }
+    }
+}
+
 // --- duplicate chains -------------------------------------------------------------------------------
 // sort key = (slot << 32 | row) for rows that are in the table; rows with NULL keys sort last
 __global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
@@ -294,8 +333,8 @@ __global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const J
         if (join_key(key, kind, i, &k)) {
             if (k == EMPTY_KEY) slot = special_slot;
             else {
-                unsigned long long pos = tg::murmur3_mix(k) & mask;
-                while (table[pos].key != k) pos = (pos + 1) & mask;
+                unsigned long long pos = join_slot_of(k, mask);
+                while (table[pos].key != k) pos = join_next_slot(pos, k, mask);
                 slot = pos;
             }
         }
@@ -385,6 +424,7 @@ struct tgpu_lookup {
     DevBuf links;                       // int32[positions], only when has_dups
     DevPage store;                      // key column first, then build output columns
     int32_t num_output = 0;
+    std::vector<DevBuf> by_slot;        // build output columns in table-slot order (fused probe fast path)
 };
 
 namespace {
@@ -509,7 +549,7 @@ struct JoinBuildOp : tgpu_op {
         // sizing: IncrementalLoadFactorHashArraySizeSupplier.getHashArraySize :40-47 (capacity is not observable)
         double lf = rows <= (1 << 16) ? 0.25 : rows <= (1 << 20) ? 0.5 : 0.75;
         int64_t need = (int64_t)((double)rows / lf) + 1;
-        int64_t cap = 2;
+        int64_t cap = 8;   // at least one 8-slot line
         while (cap < need) cap <<= 1;
         if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
         lk->mask = (unsigned long long)cap - 1;
@@ -543,6 +583,20 @@ struct JoinBuildOp : tgpu_op {
             TG_LAUNCH(ctx, join_links_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, keys_out.as<unsigned long long>(), rows, lk->links.as<int>());
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
+        // slot-ordered copy of the build output columns for the fused probe
+        bool slot_payload = getenv("TGPU_JOIN_PAYLOAD_BY_SLOT") && rows > 0 && lk->num_output > 0 && lk->num_output <= 4;
+        for (int32_t b = 0; b < lk->num_output && slot_payload; b++)
+            slot_payload = lk->store.cols[1 + b].elem_size() > 0 && !lk->store.cols[1 + b].validity;
+        if (slot_payload) {
+            lk->by_slot.resize(lk->num_output);
+            for (int32_t b = 0; b < lk->num_output; b++) {
+                const DevColumn& c = lk->store.cols[1 + b];
+                TG_TRY(lk->by_slot[b].alloc(ctx, (size_t)(cap + 1) * c.elem_size()));
+                TG_LAUNCH(ctx, join_payload_by_slot_kernel, tg_grid(ctx, cap + 1, 1024, 8), 256, 0, lk->table.as<JoinSlot>(), cap, lk->special_head, c.data,
+                          c.elem_size(), lk->by_slot[b].p);
+            }
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         lookup = lk.release();
         finishing = true;
         return TGPU_OK;
@@ -605,9 +659,10 @@ struct JoinProbeOp : tgpu_op {
             TG_TRY(built[b].own_data->alloc(ctx, (size_t)n * c.elem_size()));
             built[b].data = built[b].own_data->p;
             g.elem[b] = c.elem_size();
-            g.src[b] = c.data;
+            g.src[b] = lookup->by_slot.empty() ? c.data : lookup->by_slot[b].p;
             g.dst[b] = built[b].own_data->p;
         }
+        g.by_slot = lookup->by_slot.empty() ? 0 : 1;
         unsigned long long* d_matches = (unsigned long long*)(ctx->d_scratch + 12);
         TG_CUDA(ctx, cudaMemsetAsync(d_matches, 0, 8, ctx->stream));
         constexpr int ROWS = 4;
@@ -791,7 +846,9 @@ extern "C" int64_t tgpu_lookup_position_count(const tgpu_lookup* lookup) { retur
 extern "C" int64_t tgpu_lookup_memory_bytes(const tgpu_lookup* lookup)
 {
     if (!lookup) return 0;
-    return (int64_t)lookup->table.bytes + (int64_t)lookup->links.bytes + lookup->store.memory_bytes();
+    int64_t b = (int64_t)lookup->table.bytes + (int64_t)lookup->links.bytes + lookup->store.memory_bytes();
+    for (auto& s : lookup->by_slot) b += (int64_t)s.bytes;
+    return b;
 }
 
 extern "C" int tgpu_lookup_has_duplicates(const tgpu_lookup* lookup) { return lookup && lookup->has_dups ? 1 : 0; }
