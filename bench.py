@@ -186,9 +186,9 @@ def main():
     total_orders = n_orders * world
     total_rows = lib.tgpu_synth_lineitem_rows(total_orders)
     # every rank owns a contiguous range shard of the global tables
-    o_first = n_orders * rank
-    l_first = (total_rows // world) * rank
-    l_count = (total_rows // world) if rank < world - 1 else total_rows - l_first
+    from trino_b200.sharding import shard_range
+    o_first, _ = shard_range(total_orders, world, rank)
+    l_first, l_count = shard_range(total_rows, world, rank)
     d_okeys = ctx.malloc(n_orders * 8)
     ctx.check(lib.tgpu_synth_orders_keys(ctx.h, total_orders, o_first, n_orders, SEED_ORDERS, 1, C.c_void_p(d_okeys)))
     d_lkeys = ctx.malloc(l_count * 8)

@@ -1,0 +1,93 @@
+"""Multi-GPU parity check (launched with torchrun, one rank per GPU, NOT collected by pytest):
+hash-partition + NCCL all-to-all of a device page through tgpu_exchange_partitioned, checked against the oracle's
+partition function, then the partitioned join against a single-process oracle join.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_exchange_check.py
+"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import oracle_lib as o  # noqa: E402
+from trino_b200 import abi  # noqa: E402
+from trino_b200 import operators as ops  # noqa: E402
+from trino_b200.page import Block, Page  # noqa: E402
+from trino_b200.sharding import shard_range  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = ops.Context(local)
+    lib = ctx.lib
+    idb = (C.c_uint8 * abi.COMM_ID_BYTES)()
+    if rank == 0:
+        ctx.check(lib.tgpu_comm_get_unique_id(C.cast(idb, C.c_void_p)))
+    t = torch.tensor(list(idb), dtype=torch.uint8, device=f"cuda:{local}")
+    dist.broadcast(t, 0)
+    idb = (C.c_uint8 * abi.COMM_ID_BYTES)(*t.cpu().tolist())
+    ctx.check(lib.tgpu_comm_init(ctx.h, C.cast(idb, C.c_void_p), rank, world))
+
+    n_orders = 200_003
+    total_rows = o.synth_lineitem_rows(n_orders)
+    o_first, o_count = shard_range(n_orders, world, rank)
+    l_first, l_count = shard_range(total_rows, world, rank)
+    okeys = o.synth_orders_keys(n_orders, o_first, o_count, 0x7C02, True)
+    lkeys = o.synth_lineitem_keys(n_orders, l_first, l_count, 0x7C01, False)
+    rng = np.random.default_rng(rank)
+    lnull = rng.random(l_count) < 0.01
+    lpage = Page(Block.bigint(lkeys), Block.double(lkeys * 0.25, lnull), Block.integer((lkeys % 1000).astype(np.int32)))
+    opage = Page(Block.bigint(okeys), Block.bigint(okeys % 2557))
+
+    part = ops.PartitionedOutputOperatorFactory(ctx, [0], world).create_operator()
+
+    def exchange(page):
+        from trino_b200.page import AbiPage
+        ap = AbiPage(page)
+        pp = abi.PP()
+        ctx.check(lib.tgpu_exchange_partitioned(ctx.h, part.h, ap.ref(), C.byref(pp)))
+        return ctx.page_to_host(pp)
+
+    got_l = exchange(lpage)
+    got_o = exchange(opage)
+    # every received row belongs here (oracle partition function), and globally nothing is lost or duplicated
+    assert (o.partition_ids(got_l, [0], world) == rank).all()
+    assert (o.partition_ids(got_o, [0], world) == rank).all()
+    stats = torch.tensor([got_l.position_count, got_o.position_count, int(np.asarray(got_l.get_block(0).values).sum() % (1 << 50)),
+                          int(sum(1 for v in got_l.get_block(1).to_pylist() if v is None))], dtype=torch.int64, device=f"cuda:{local}")
+    mine = torch.tensor([l_count, o_count, int(lkeys.sum() % (1 << 50)), int(lnull.sum())], dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(stats)
+    dist.all_reduce(mine)
+    assert stats[0] == mine[0] == total_rows and stats[1] == mine[1] == n_orders
+    assert stats[2] % (1 << 50) == mine[2] % (1 << 50)
+    assert stats[3] == mine[3]
+    # rows arrive grouped by source rank, each group in the sender's row order: payload follows its key
+    vals = got_l.get_block(1).to_pylist()
+    keys = got_l.get_block(0).to_pylist()
+    assert all(v is None or v == k * 0.25 for k, v in zip(keys, vals))
+    assert (np.asarray(got_l.get_block(2).values) == (np.asarray(keys) % 1000)).all()
+    # partitioned join == the oracle join restricted to this rank's keys
+    from helpers import gpu_join_rows, oracle_join_rows
+    rows = gpu_join_rows(ctx, [got_o], [got_l], 0, 0, [0, 2], [1], abi.JOIN_INNER, False)
+    want = oracle_join_rows(got_o, got_l, 0, 0, [0, 2], [1], abi.JOIN_INNER, False)
+    assert rows == want and len(rows) == got_l.position_count
+    part.close()
+    ctx.check(lib.tgpu_comm_destroy(ctx.h))
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_exchange_check ok: world={world} rows={total_rows}")
+    dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
