@@ -110,6 +110,8 @@ int tgpu_flush_l2(tgpu_ctx* ctx);
 /* device timing on the ctx stream (cudaEvent pair) */
 int tgpu_timer_start(tgpu_ctx* ctx);
 int tgpu_timer_stop_ms(tgpu_ctx* ctx, float* ms);
+/* device time (CUDA events on the ctx stream) of the dominant kernel launched by the last operator call */
+int tgpu_ctx_last_kernel_ms(tgpu_ctx* ctx, float* ms);
 
 /* ------------------------------------------------------------------ expressions (PageProcessor)
  * Stands in for the compiled PageFilter/PageProjection pair produced by

@@ -163,6 +163,7 @@ SIGNATURES = {
     "tgpu_flush_l2": (C.c_int, [VP]),
     "tgpu_timer_start": (C.c_int, [VP]),
     "tgpu_timer_stop_ms": (C.c_int, [VP, C.POINTER(C.c_float)]),
+    "tgpu_ctx_last_kernel_ms": (C.c_int, [VP, C.POINTER(C.c_float)]),
     "tgpu_filter_project_create": (C.c_int, [VP, C.POINTER(ExprProgram), C.POINTER(VP)]),
     "tgpu_agg_create": (C.c_int, [VP, C.POINTER(AggSpec), C.POINTER(VP)]),
     "tgpu_agg_group_count": (C.c_int, [VP, C.POINTER(C.c_int64)]),

@@ -27,6 +27,8 @@ struct tgpu_ctx {
     std::string err;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t kev0 = nullptr, kev1 = nullptr;   // bracket the dominant kernel of the last operator call (tgpu_ctx_last_kernel_ms)
+    bool kev_valid = false;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     int sm_count = 148;
@@ -71,6 +73,10 @@ int tg_fail(tgpu_ctx* ctx, int status, const char* fmt, ...);
         if (_e != cudaSuccess)                                                                       \
             return tg_fail((ctx), TGPU_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+// bracket one kernel launch with events on the ctx stream so benchmarks can read its device time
+#define TG_TIMED_BEGIN(ctx) do { cudaEventRecord((ctx)->kev0, (ctx)->stream); } while (0)
+#define TG_TIMED_END(ctx) do { cudaEventRecord((ctx)->kev1, (ctx)->stream); (ctx)->kev_valid = true; } while (0)
 
 static inline int64_t tg_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -70,6 +70,8 @@ extern "C" int tgpu_ctx_create(int device, tgpu_ctx** out)
     TG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     TG_CUDA(ctx, cudaEventCreate(&ctx->ev0));
     TG_CUDA(ctx, cudaEventCreate(&ctx->ev1));
+    TG_CUDA(ctx, cudaEventCreate(&ctx->kev0));
+    TG_CUDA(ctx, cudaEventCreate(&ctx->kev1));
     cudaDeviceProp prop;
     TG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
@@ -100,6 +102,8 @@ extern "C" void tgpu_ctx_destroy(tgpu_ctx* ctx)
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->kev0);
+    cudaEventDestroy(ctx->kev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -202,6 +206,17 @@ extern "C" int tgpu_timer_stop_ms(tgpu_ctx* ctx, float* ms)
     TG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     TG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     TG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_ctx_last_kernel_ms(tgpu_ctx* ctx, float* ms)
+{
+    // device time of the dominant kernel of the last operator call that has one (fused probe, index probe,
+    // small-group aggregation): CUDA events recorded right around that launch on the ctx stream
+    if (!ctx || !ms) return TGPU_ERR_INVALID_ARGUMENT;
+    if (!ctx->kev_valid) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "no timed kernel has run on this context yet");
+    TG_CUDA(ctx, cudaEventSynchronize(ctx->kev1));
+    TG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->kev0, ctx->kev1));
     return TGPU_OK;
 }
 

@@ -1176,6 +1176,7 @@ struct AggOp : tgpu_op {
             map.compact_count = A;
             for (int a = 0; a < MAX_ACCS; a++) map.of_plan[a] = a;
         }
+        TG_TIMED_BEGIN(ctx);
         if (jit_fn) {
             long long n_arg = n;
             DColumns cols_arg = cols;
@@ -1188,6 +1189,7 @@ struct AggOp : tgpu_op {
             TG_CUDA(ctx, cudaFuncSetAttribute(agg_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
             TG_LAUNCH(ctx, agg_small_kernel, grid, S_THREADS, s_smem, plan, cols, has_pre ? d_prog.as<DProgram>() : nullptr, n, L, so);
         }
+        TG_TIMED_END(ctx);
         TG_LAUNCH(ctx, agg_small_merge_kernel, 1, 256, 0, plan, cols, grid, L, so, state(), blk_ps.as<int>(), map);
         // one small readback per page: overflow flag + error bits, then the group count
         int64_t word = 0;

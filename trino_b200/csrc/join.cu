@@ -34,18 +34,28 @@ struct __align__(16) JoinSlot {
 
 enum KeyKind { KEY_INT = 0, KEY_DOUBLE = 1 };
 
-// Slot of a key and the probe sequence: mix(key) & mask with linear probing, like the reference
-// (M/operator/join/PagesHash.java:35-51, BigintPagesHash.java:116,165).  Measured alternative (round 1): keeping the 8 keys
-// of one key >> 3 group inside one 128-byte line turned TPC-H's clustered probes sequential but doubled the probe time,
-// because TPC-H order keys (8 used, 24 skipped) load the lines very unevenly; see DESIGN.md.
+// Slot of a key and the probe sequence.  Slot placement is not observable (only key -> head is).
+//   mode 0: mix(key) & mask with linear probing, like the reference (M/operator/join/PagesHash.java:35-51).
+//   mode 1: line-local: the 8 keys that share key >> 3 prefer the 8 slots of one 128-byte line (slot = key & 7), the
+//           LINES are scattered with the murmur3 finaliser; the probe sequence walks the 8 slots of the line (wrapping
+//           inside it) and then does the same in the following line.  Dense / clustered key domains probed in key
+//           order turn random sector reads into sequential line reads; random keys behave like mode 0.
+// The mode is folded into the top bit of `mask` arguments (capacity <= 2^31 slots, so the bit is free).
+constexpr unsigned long long MODE_BIT = 1ULL << 63;
+
 __host__ __device__ __forceinline__ unsigned long long join_slot_of(unsigned long long k, unsigned long long mask)
 {
+    if (mask & MODE_BIT) return ((tg::murmur3_mix(k >> 3) << 3) | (k & 7)) & (mask & ~MODE_BIT);
     return tg::murmur3_mix(k) & mask;
 }
 
 __host__ __device__ __forceinline__ unsigned long long join_next_slot(unsigned long long pos, unsigned long long k, unsigned long long mask)
 {
-    (void)k;
+    if (mask & MODE_BIT) {
+        unsigned long long in = (pos + 1) & 7;
+        if (in != (k & 7)) return (pos & ~7ULL) | in;
+        return ((((pos >> 3) + 1) << 3) | (k & 7)) & (mask & ~MODE_BIT);
+    }
     return (pos + 1) & mask;
 }
 
@@ -145,6 +155,8 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
             if (ok[j] && k[j] != EMPTY_KEY) s[j] = __ldg((const int4*)&table[pos[j]]);
             else s[j] = make_int4(0, (int)0x80000000, -1, 0);
         }
+        // each row walks its probe sequence on its own (measured alternative: lock-step rounds over the ROWS rows of a
+        // thread were ~15 % slower on B200)
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
             int64_t i = base + (int64_t)j * blockDim.x;
@@ -170,11 +182,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
 }
 
 
-// Fused probe + build-side gather for the common join shape (no duplicate chains, fixed-width non-null build
-// columns): the chain head is looked up and the build payload of the matching row is fetched while the slot is
-// still in flight in the same thread, so the positions never make a round trip through HBM before the gather and
-// no count/scan pass is needed when every probe row matches (FK -> PK joins).  Misses are counted; the host
-// compacts only when there are any.
+
 struct GatherCols {
     int count;
     int by_slot;
@@ -183,6 +191,11 @@ struct GatherCols {
     void* dst[4];
 };
 
+// Fused probe + build-side gather for the common join shape (no duplicate chains, fixed-width non-null build
+// columns): the chain head is looked up and the build payload of the matching row is fetched while the slot is
+// still in flight in the same thread, so the positions never make a round trip through HBM before the gather and
+// no count/scan pass is needed when every probe row matches (FK -> PK joins).  Misses are counted; the host
+// compacts only when there are any.
 template <int ROWS, bool INT64_NO_NULLS>
 __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
                                                                 int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
@@ -220,7 +233,7 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
             int r = -1;
             long long where = 0;
             if (ok[j]) {
-                if (k[j] == EMPTY_KEY) { r = special_head; where = (long long)mask + 1; }
+                if (k[j] == EMPTY_KEY) { r = special_head; where = (long long)(mask & ~MODE_BIT) + 1; }
                 else {
                     unsigned long long p = pos[j];
                     int4 cur = s[j];
@@ -436,15 +449,16 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
     if (key.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width join keys are not supported on the GPU path");
     if (key_kind_of(key.type) != key_kind_of(lk->key_type) || key.elem_size() == 0)
         return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key type %d does not match build key type %d", key.type, lk->key_type);
-    constexpr int ROWS = 4;
-    int grid = tg_grid(ctx, n, 256 * ROWS, 8);
     const JoinSlot* table = lk->table.as<JoinSlot>();
-    auto probe_fast = join_probe_kernel<ROWS, true>;
-    auto probe_any = join_probe_kernel<ROWS, false>;
-    if (key.type == TGPU_INT64 && !key.validity)
-        TG_LAUNCH(ctx, probe_fast, grid, 256, 0, tg_colref(key), KEY_INT, n, table, lk->mask, lk->special_head, d_out);
-    else
-        TG_LAUNCH(ctx, probe_any, grid, 256, 0, tg_colref(key), key_kind_of(key.type), n, table, lk->mask, lk->special_head, d_out);
+    bool fast = key.type == TGPU_INT64 && !key.validity;
+    int kind = fast ? KEY_INT : key_kind_of(key.type);
+    int grid = tg_grid(ctx, n, 256 * 4, 8);
+    auto k4f = join_probe_kernel<4, true>;
+    auto k4a = join_probe_kernel<4, false>;
+    TG_TIMED_BEGIN(ctx);
+    if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, tg_colref(key), kind, n, table, lk->mask, lk->special_head, d_out);
+    else TG_LAUNCH(ctx, k4a, grid, 256, 0, tg_colref(key), kind, n, table, lk->mask, lk->special_head, d_out);
+    TG_TIMED_END(ctx);
     return TGPU_OK;
 }
 
@@ -551,8 +565,15 @@ struct JoinBuildOp : tgpu_op {
         int64_t need = (int64_t)((double)rows / lf) + 1;
         int64_t cap = 8;   // at least one 8-slot line
         while (cap < need) cap <<= 1;
+        // line-local layout by default; it wants lines at most about half full (measured: exp_join_summary in profiles/)
+        const char* env_mode = getenv("TGPU_JOIN_HASH");
+        int hash_mode = env_mode ? atoi(env_mode) : 1;
+        const char* env_shift = getenv("TGPU_JOIN_CAP_SHIFT");
+        int cap_shift = env_shift ? atoi(env_shift) : (hash_mode ? 1 : 0);
+        cap <<= cap_shift;
         if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
-        lk->mask = (unsigned long long)cap - 1;
+
+        lk->mask = ((unsigned long long)cap - 1) | (hash_mode ? MODE_BIT : 0);
         TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
         TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
         int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag
@@ -584,7 +605,7 @@ struct JoinBuildOp : tgpu_op {
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
         // slot-ordered copy of the build output columns for the fused probe
-        bool slot_payload = getenv("TGPU_JOIN_PAYLOAD_BY_SLOT") && rows > 0 && lk->num_output > 0 && lk->num_output <= 4;
+        bool slot_payload = !getenv("TGPU_JOIN_PAYLOAD_BY_ROW") && rows > 0 && lk->num_output > 0 && lk->num_output <= 4;
         for (int32_t b = 0; b < lk->num_output && slot_payload; b++)
             slot_payload = lk->store.cols[1 + b].elem_size() > 0 && !lk->store.cols[1 + b].validity;
         if (slot_payload) {
@@ -670,10 +691,12 @@ struct JoinProbeOp : tgpu_op {
         auto k_fast = join_probe_gather_kernel<ROWS, true>;
         auto k_any = join_probe_gather_kernel<ROWS, false>;
         const JoinSlot* table = lookup->table.as<JoinSlot>();
+        TG_TIMED_BEGIN(ctx);
         if (key.type == TGPU_INT64 && !key.validity)
             TG_LAUNCH(ctx, k_fast, grid, 256, 0, tg_colref(key), KEY_INT, n, table, lookup->mask, lookup->special_head, jp->as<int>(), g, d_matches);
         else
             TG_LAUNCH(ctx, k_any, grid, 256, 0, tg_colref(key), key_kind_of(key.type), n, table, lookup->mask, lookup->special_head, jp->as<int>(), g, d_matches);
+        TG_TIMED_END(ctx);
         int64_t matches = 0;
         TG_TRY(tg_read_i64(ctx, d_matches, &matches));
         *handled = true;

@@ -102,6 +102,11 @@ class Context:
         self.check(self.lib.tgpu_timer_stop_ms(self.h, C.byref(ms)))
         return ms.value
 
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self.check(self.lib.tgpu_ctx_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
     # ---- output pages
     def page_to_host(self, pp, release=True):
         """device tgpu_page* -> host Page (numpy)."""
