@@ -341,6 +341,11 @@ void tgpu_page_release(tgpu_ctx* ctx, tgpu_page* page);
  * buffers large enough (UTF8: data capacity from tgpu_page_utf8_bytes)                          */
 int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* device_page, tgpu_page* host);
 int64_t tgpu_page_utf8_bytes(tgpu_ctx* ctx, const tgpu_page* device_page, int32_t channel);
+/* LookupJoinPageBuilder.build :144-150 returns probe blocks directly when the output covers the probe page 1:1, and
+ * InputPageProjection returns its input block: *input_channel = the input channel this output column is an unchanged view
+ * of (the host already holds that block and need not copy it back), or -1.  Columns of tgpu_page_copy_to_host whose host
+ * `data` pointer is NULL are skipped. */
+int tgpu_page_passthrough_channel(const tgpu_page* device_page, int32_t channel, int32_t* input_channel);
 
 /* ------------------------------------------------------------------ synthetic data (bench/tests)
  * Counter-based generators (x_i = splitmix64(seed ^ i)) so the CPU oracle and the GPU produce

@@ -39,12 +39,21 @@ struct tgpu_ctx {
     // 64-byte pinned + device scratch for small readbacks (counters, flags)
     int64_t* h_scratch = nullptr;
     int64_t* d_scratch = nullptr;
+    // cache of large device buffers released by operators (all work of a ctx is ordered on its one stream, so a block
+    // can be handed to the next request without waiting): multi-GB cudaMallocAsync calls cost milliseconds even from a
+    // warm pool, and operators allocate the same sizes page after page
+    struct BigBlock { void* p; size_t bytes; };
+    std::vector<BigBlock> big_cache;
+    size_t big_cache_bytes = 0;
     // NCCL
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
 };
 
 int tg_fail(tgpu_ctx* ctx, int status, const char* fmt, ...);
+
+constexpr size_t TG_BIG_BLOCK = (size_t)32 << 20;            // blocks at least this large go through the ctx cache
+constexpr size_t TG_BIG_CACHE_LIMIT = (size_t)64 << 30;      // bytes the cache may hold before blocks go back to the pool
 
 #define TG_CUDA(ctx, call)                                                                           \
     do {                                                                                             \
@@ -118,6 +127,20 @@ struct DevBuf {
         ctx = c;
         if (n == 0) n = 16;
         n = (n + 255) & ~(size_t)255;
+        if (n >= TG_BIG_BLOCK) {
+            size_t best = (size_t)-1;
+            for (size_t i = 0; i < c->big_cache.size(); i++) {
+                size_t b = c->big_cache[i].bytes;
+                if (b >= n && b <= n + n / 4 && (best == (size_t)-1 || b < c->big_cache[best].bytes)) best = i;
+            }
+            if (best != (size_t)-1) {
+                p = c->big_cache[best].p;
+                bytes = c->big_cache[best].bytes;
+                c->big_cache_bytes -= bytes;
+                c->big_cache.erase(c->big_cache.begin() + best);
+                return TGPU_OK;
+            }
+        }
         cudaError_t e = cudaMallocAsync(&p, n, c->stream);
         if (e != cudaSuccess) {
             p = nullptr;
@@ -128,7 +151,13 @@ struct DevBuf {
     }
     void release()
     {
-        if (p && ctx) cudaFreeAsync(p, ctx->stream);
+        if (p && ctx) {
+            if (bytes >= TG_BIG_BLOCK && ctx->big_cache.size() < 32 && ctx->big_cache_bytes + bytes <= TG_BIG_CACHE_LIMIT) {
+                ctx->big_cache.push_back(tgpu_ctx::BigBlock{p, bytes});
+                ctx->big_cache_bytes += bytes;
+            }
+            else cudaFreeAsync(p, ctx->stream);
+        }
         p = nullptr;
         bytes = 0;
     }
@@ -182,6 +211,7 @@ struct OwnedPage {
     std::vector<tgpu_column> cols;
     DevPage page;
     int32_t partition = -1;
+    std::vector<int32_t> passthrough;   // per column: input channel whose block this column IS (unchanged, same rows), else -1
 };
 
 static inline ColRef tg_colref(const DevColumn& c) { return ColRef{c.data, c.validity, c.type, c.elem_size()}; }

@@ -96,6 +96,9 @@ extern "C" void tgpu_ctx_destroy(tgpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     tg_comm_destroy_internal(ctx);
+    for (auto& b : ctx->big_cache) cudaFreeAsync(b.p, ctx->stream);
+    ctx->big_cache.clear();
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
@@ -580,6 +583,15 @@ extern "C" void tgpu_page_release(tgpu_ctx* ctx, tgpu_page* page)
     delete reinterpret_cast<OwnedPage*>(page);
 }
 
+extern "C" int tgpu_page_passthrough_channel(const tgpu_page* device_page, int32_t channel, int32_t* input_channel)
+{
+    if (!device_page || !input_channel) return TGPU_ERR_INVALID_ARGUMENT;
+    const OwnedPage* o = reinterpret_cast<const OwnedPage*>(device_page);
+    if (channel < 0 || channel >= (int32_t)o->cols.size()) return TGPU_ERR_INVALID_ARGUMENT;
+    *input_channel = channel < (int32_t)o->passthrough.size() ? o->passthrough[channel] : -1;
+    return TGPU_OK;
+}
+
 extern "C" int64_t tgpu_page_utf8_bytes(tgpu_ctx* ctx, const tgpu_page* device_page, int32_t channel)
 {
     (void)ctx;
@@ -598,6 +610,7 @@ extern "C" int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* dp, tgpu_p
         tgpu_column& h = const_cast<tgpu_column&>(host->columns[c]);
         h.type = d.type;
         h.length = n;
+        if (!h.data) continue;   // the caller does not want this column (e.g. a pass-through block it already holds)
         if (d.type == TGPU_UTF8) {
             TG_CUDA(ctx, cudaMemcpyAsync((void*)h.offsets, d.offsets, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -129,12 +129,25 @@ __device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, u
 // Algorithmic bytes per probe row: 8 (key) + 12 (slot) + 4 (position) = 24.
 template <int ROWS, bool INT64_NO_NULLS>
 __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
-                                                         int special_head, int* __restrict__ out)
+                                                         int special_head, int* __restrict__ out, int prefetch)
 {
     int64_t tile = (int64_t)blockDim.x * ROWS;
     int64_t tiles = (n + tile - 1) / tile;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         int64_t base = t * tile + threadIdx.x;
+        if (INT64_NO_NULLS && prefetch) {
+            // pull the slots of the NEXT tile of this CTA towards L2 while this tile is being resolved
+            int64_t nbase = (t + gridDim.x) * tile + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) {
+                int64_t i = nbase + (int64_t)j * blockDim.x;
+                if (i < n) {
+                    unsigned long long nk = (unsigned long long)__ldg((const long long*)key.data + i);
+                    const void* a = &table[join_slot_of(nk, mask)];
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+                }
+            }
+        }
         unsigned long long k[ROWS];
         bool ok[ROWS];
         int4 s[ROWS];
@@ -314,6 +327,100 @@ __global__ void join_match_flags_kernel(const int* __restrict__ jp, int64_t n, u
     for (; i < n; i += stride) flags[i] = jp[i] >= 0 ? 1 : 0;
 }
 
+
+// ---- lean probe kernels for the headline shape (BIGINT key without NULLs, whole 1024-row tiles) -------------------
+// Same algorithm as join_probe_kernel / join_probe_gather_kernel with the per-row bookkeeping stripped: the layout
+// mode is a template parameter, slot indices are 32-bit, there are no bounds or validity checks (the ragged tail and
+// every other key shape go through the generic kernels).  ncu showed the generic kernels spending ~215 thread
+// instructions per probe row at 44-48 % issue utilisation, i.e. instruction-bound as much as latency-bound.
+template <int MODE>
+__device__ __forceinline__ unsigned int lean_slot(unsigned long long k, unsigned int mask)
+{
+    if (MODE == 1) return (((unsigned int)tg::murmur3_mix(k >> 3) << 3) | ((unsigned int)k & 7u)) & mask;
+    return (unsigned int)tg::murmur3_mix(k) & mask;
+}
+
+template <int MODE>
+__device__ __forceinline__ unsigned int lean_next(unsigned int pos, unsigned int k_low3, unsigned int mask)
+{
+    if (MODE == 1) {
+        unsigned int in = (pos + 1) & 7u;
+        return in != k_low3 ? ((pos & ~7u) | in) : (((pos & ~7u) + 8u + k_low3) & mask);
+    }
+    return (pos + 1) & mask;
+}
+
+template <int MODE, bool GATHER>
+__global__ void __launch_bounds__(256) join_probe_lean_kernel(const long long* __restrict__ keys, int64_t tiles, const int4* __restrict__ table, unsigned int mask,
+                                                              int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
+{
+    unsigned int matched = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t base = t * 1024 + threadIdx.x;
+        unsigned long long k[4];
+        unsigned int pos[4];
+        int4 s[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = (unsigned long long)__ldg(keys + base + j * 256);
+#pragma unroll
+        for (int j = 0; j < 4; j++) pos[j] = lean_slot<MODE>(k[j], mask);
+#pragma unroll
+        for (int j = 0; j < 4; j++) s[j] = __ldg(table + pos[j]);
+        int res[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned int klo = (unsigned int)k[j], khi = (unsigned int)(k[j] >> 32);
+            int r = -1;
+            int4 cur = s[j];
+            unsigned int p = pos[j];
+            while (true) {
+                if ((unsigned int)cur.x == klo && (unsigned int)cur.y == khi) { r = cur.z; break; }
+                if (cur.x == 0 && cur.y == (int)0x80000000) break;                 // EMPTY_KEY
+                p = lean_next<MODE>(p, klo & 7u, mask);
+                cur = __ldg(table + p);
+            }
+            if (k[j] == EMPTY_KEY) { r = special_head; p = mask + 1u; }
+            res[j] = r;
+            pos[j] = p;
+        }
+        if (GATHER) {
+            for (int c = 0; c < g.count; c++) {
+                if (g.elem[c] == 8) {
+                    long long v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = res[j] >= 0 ? __ldg((const long long*)g.src[c] + (g.by_slot ? (long long)pos[j] : (long long)res[j])) : 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ((long long*)g.dst[c])[base + j * 256] = v[j];
+                }
+                else if (g.elem[c] == 4) {
+                    int v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[j] = res[j] >= 0 ? __ldg((const int*)g.src[c] + (g.by_slot ? (long long)pos[j] : (long long)res[j])) : 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ((int*)g.dst[c])[base + j * 256] = v[j];
+                }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        long long at = g.by_slot ? (long long)pos[j] : (long long)res[j];
+                        if (g.elem[c] == 2) ((short*)g.dst[c])[base + j * 256] = res[j] >= 0 ? ((const short*)g.src[c])[at] : (short)0;
+                        else ((signed char*)g.dst[c])[base + j * 256] = res[j] >= 0 ? ((const signed char*)g.src[c])[at] : (signed char)0;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            out[base + j * 256] = res[j];
+            if (GATHER) matched += res[j] >= 0;
+        }
+    }
+    if (GATHER) {
+        for (int off = 16; off > 0; off >>= 1) matched += __shfl_xor_sync(0xffffffffu, matched, off);
+        if ((threadIdx.x & 31) == 0 && matched) atomicAdd(match_count, (unsigned long long)matched);
+    }
+}
+
 // build payload re-laid out in SLOT order (one pass at build time): the fused probe then reads the payload right next
 // to where it found the key instead of chasing the row id into the (arbitrarily ordered) build pages
 __global__ void join_payload_by_slot_kernel(const JoinSlot* __restrict__ table, int64_t slots, int special_head, const void* __restrict__ src, int elem,
@@ -452,12 +559,33 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
     const JoinSlot* table = lk->table.as<JoinSlot>();
     bool fast = key.type == TGPU_INT64 && !key.validity;
     int kind = fast ? KEY_INT : key_kind_of(key.type);
-    int grid = tg_grid(ctx, n, 256 * 4, 8);
+    int prefetch = getenv("TGPU_JOIN_PREFETCH") ? 1 : 0;
     auto k4f = join_probe_kernel<4, true>;
     auto k4a = join_probe_kernel<4, false>;
+    int64_t done = 0;
     TG_TIMED_BEGIN(ctx);
-    if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, tg_colref(key), kind, n, table, lk->mask, lk->special_head, d_out);
-    else TG_LAUNCH(ctx, k4a, grid, 256, 0, tg_colref(key), kind, n, table, lk->mask, lk->special_head, d_out);
+    if (fast && !getenv("TGPU_JOIN_GENERIC_KERNELS")) {
+        // whole 1024-row tiles through the lean kernel, the ragged tail through the generic one
+        int64_t tiles = n / 1024;
+        if (tiles > 0) {
+            GatherCols none;
+            memset(&none, 0, sizeof(none));
+            int lgrid = (int)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8);
+            unsigned int mask32 = (unsigned int)(lk->mask & ~MODE_BIT);
+            auto l0 = join_probe_lean_kernel<0, false>;
+            auto l1 = join_probe_lean_kernel<1, false>;
+            if (lk->mask & MODE_BIT) TG_LAUNCH(ctx, l1, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lk->special_head, d_out, none, (unsigned long long*)nullptr);
+            else TG_LAUNCH(ctx, l0, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lk->special_head, d_out, none, (unsigned long long*)nullptr);
+            done = tiles * 1024;
+        }
+    }
+    if (done < n) {
+        ColRef kr = tg_colref(key);
+        if (done > 0) kr.data = (const char*)kr.data + done * 8;   // only the fast (INT64, no validity) shape gets here with done > 0
+        int grid = tg_grid(ctx, n - done, 256 * 4, 8);
+        if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done, prefetch);
+        else TG_LAUNCH(ctx, k4a, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done, prefetch);
+    }
     TG_TIMED_END(ctx);
     return TGPU_OK;
 }
@@ -692,10 +820,31 @@ struct JoinProbeOp : tgpu_op {
         auto k_any = join_probe_gather_kernel<ROWS, false>;
         const JoinSlot* table = lookup->table.as<JoinSlot>();
         TG_TIMED_BEGIN(ctx);
-        if (key.type == TGPU_INT64 && !key.validity)
-            TG_LAUNCH(ctx, k_fast, grid, 256, 0, tg_colref(key), KEY_INT, n, table, lookup->mask, lookup->special_head, jp->as<int>(), g, d_matches);
-        else
-            TG_LAUNCH(ctx, k_any, grid, 256, 0, tg_colref(key), key_kind_of(key.type), n, table, lookup->mask, lookup->special_head, jp->as<int>(), g, d_matches);
+        int64_t done = 0;
+        bool fast = key.type == TGPU_INT64 && !key.validity;
+        if (fast && !getenv("TGPU_JOIN_GENERIC_KERNELS")) {
+            int64_t tiles = n / 1024;
+            if (tiles > 0) {
+                int lgrid = (int)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8);
+                unsigned int mask32 = (unsigned int)(lookup->mask & ~MODE_BIT);
+                auto l0 = join_probe_lean_kernel<0, true>;
+                auto l1 = join_probe_lean_kernel<1, true>;
+                if (lookup->mask & MODE_BIT) TG_LAUNCH(ctx, l1, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lookup->special_head, jp->as<int>(), g, d_matches);
+                else TG_LAUNCH(ctx, l0, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lookup->special_head, jp->as<int>(), g, d_matches);
+                done = tiles * 1024;
+            }
+        }
+        if (done < n) {
+            ColRef kr = tg_colref(key);
+            GatherCols gt = g;
+            if (done > 0) {
+                kr.data = (const char*)kr.data + done * 8;
+                for (int c = 0; c < gt.count; c++) gt.dst[c] = (char*)gt.dst[c] + done * gt.elem[c];
+            }
+            int tgrid = tg_grid(ctx, n - done, 256 * ROWS, 8);
+            if (fast) TG_LAUNCH(ctx, k_fast, tgrid, 256, 0, kr, KEY_INT, n - done, table, lookup->mask, lookup->special_head, jp->as<int>() + done, gt, d_matches);
+            else TG_LAUNCH(ctx, k_any, tgrid, 256, 0, kr, key_kind_of(key.type), n - done, table, lookup->mask, lookup->special_head, jp->as<int>() + done, gt, d_matches);
+        }
         TG_TIMED_END(ctx);
         int64_t matches = 0;
         TG_TRY(tg_read_i64(ctx, d_matches, &matches));
@@ -742,7 +891,9 @@ struct JoinProbeOp : tgpu_op {
                 outp.cols.push_back(std::move(c));
             }
         }
-        pending.push_back(tg_make_owned_page(std::move(outp)));
+        OwnedPage* o = tg_make_owned_page(std::move(outp));
+        if (matches == n || outer) o->passthrough.assign(output_channels.begin(), output_channels.end());   // probe blocks passed through 1:1
+        pending.push_back(o);
         return TGPU_OK;
     }
 

@@ -18,6 +18,8 @@
 #include <cub/cub.cuh>
 #include <dlfcn.h>
 
+#include <chrono>
+
 #include "common.cuh"
 
 namespace {
@@ -122,6 +124,105 @@ __global__ void shift_rows_kernel(const int32_t* __restrict__ in, int64_t n, int
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = in[i] + delta;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// exchange: stable multi-split (histogram -> offsets -> scatter), all columns in one pass
+// ------------------------------------------------------------------------------------------------
+constexpr int XT = 256;          // threads per CTA
+constexpr int XMAXP = 64;        // partitions the fused exchange path handles (one per GPU)
+constexpr int XMAXC = 16;        // value columns + null-byte columns
+
+// pass A: partition id per row (uint8) and a histogram per CTA chunk
+__global__ void __launch_bounds__(XT) xchg_hist_kernel(KeyCols keys, int64_t n, int64_t chunk, int32_t bucket_count, const int32_t* __restrict__ bucket_to_partition,
+                                                       int32_t P, uint8_t* __restrict__ pid_out, unsigned int* __restrict__ hist /* [grid][P] */)
+{
+    __shared__ unsigned int sh[XMAXP];
+    for (int i = threadIdx.x; i < P; i += XT) sh[i] = 0;
+    __syncthreads();
+    int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
+    for (int64_t row = begin + threadIdx.x; row < end; row += XT) {
+        uint64_t h = 0;
+        for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
+        int32_t bucket = process_raw_hash(h, bucket_count);
+        int32_t pid = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
+        pid_out[row] = (uint8_t)pid;
+        // warp-aggregated histogram update
+        unsigned int peers = __match_any_sync(__activemask(), pid);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[pid], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += XT) hist[(size_t)blockIdx.x * P + i] = sh[i];
+}
+
+// pass B: where every CTA chunk starts inside every partition, and the partition totals
+__global__ void xchg_offsets_kernel(const unsigned int* __restrict__ hist, int grid, int32_t P, long long* __restrict__ block_off /* [grid][P] */,
+                                    long long* __restrict__ totals /* [P] */)
+{
+    int p = threadIdx.x;
+    if (p >= P) return;
+    long long run = 0;
+    for (int b = 0; b < grid; b++) {
+        block_off[(size_t)b * P + p] = run;
+        run += hist[(size_t)b * P + p];
+    }
+    totals[p] = run;
+}
+
+struct XchgCols {
+    int32_t count;
+    int32_t elem[XMAXC];          // element bytes; 0 = "null byte" pseudo column (reads the validity bitmap, writes 1 = NULL)
+    const void* src[XMAXC];       // column data, or the validity bitmap for pseudo columns
+    char* const* dst;             // device array [count][P] of destination base pointers (local send buffer or peer memory)
+};
+
+// pass C: stable scatter.  Rows keep their order inside a partition: rank = CTA offset + running offset of earlier tiles
+// + rows of earlier warps in the tile + rank inside the warp (__match_any_sync).
+__global__ void __launch_bounds__(XT) xchg_scatter_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t chunk, int32_t P,
+                                                          const long long* __restrict__ block_off, XchgCols cols)
+{
+    __shared__ long long running[XMAXP];
+    __shared__ unsigned short wcount[XT / 32][XMAXP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < P; i += XT) running[i] = block_off[(size_t)blockIdx.x * P + i];
+    int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
+    for (int64_t tile = begin; tile < end; tile += XT) {
+        for (int i = threadIdx.x; i < (XT / 32) * XMAXP; i += XT) (&wcount[0][0])[i] = 0;
+        __syncthreads();
+        int64_t row = tile + threadIdx.x;
+        bool live = row < end;
+        int pid = live ? pids[row] : 0;
+        unsigned int peers = __match_any_sync(0xffffffffu, live ? pid : -1 - lane);
+        int rank = __popc(peers & ((1u << lane) - 1));
+        if (live && rank == 0) wcount[warp][pid] = (unsigned short)__popc(peers);
+        __syncthreads();
+        long long dst = 0;
+        if (live) {
+            int before = 0;
+            for (int w = 0; w < warp; w++) before += wcount[w][pid];
+            dst = running[pid] + before + rank;
+        }
+        __syncthreads();
+        if (threadIdx.x < P) {
+            int tot = 0;
+            for (int w = 0; w < XT / 32; w++) tot += wcount[w][threadIdx.x];
+            running[threadIdx.x] += tot;
+        }
+        if (live) {
+            for (int c = 0; c < cols.count; c++) {
+                char* base = cols.dst[(size_t)c * P + pid];
+                switch (cols.elem[c]) {
+                    case 8: ((long long*)base)[dst] = ((const long long*)cols.src[c])[row]; break;
+                    case 4: ((int*)base)[dst] = ((const int*)cols.src[c])[row]; break;
+                    case 2: ((short*)base)[dst] = ((const short*)cols.src[c])[row]; break;
+                    case 1: base[dst] = ((const char*)cols.src[c])[row]; break;
+                    default: base[dst] = tg_valid((const uint8_t*)cols.src[c], row) ? 0 : 1; break;
+                }
+            }
+        }
+        __syncthreads();
+    }
 }
 
 struct PartitionOp : tgpu_op {
@@ -362,13 +463,6 @@ int load_nccl(tgpu_ctx* ctx)
 constexpr int NCCL_INT8 = 0;    // ncclInt8 / ncclChar
 constexpr int NCCL_INT64 = 4;   // ncclInt64
 
-__global__ void validity_to_bytes_kernel(const uint8_t* __restrict__ validity, const int32_t* __restrict__ idx, int64_t n, uint8_t* __restrict__ out)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = tg_valid(validity, idx[i]) ? 0 : 1;   // 1 = NULL (byte map)
-}
-
 }  // namespace
 
 int tg_comm_destroy_internal(tgpu_ctx* ctx)
@@ -480,81 +574,133 @@ extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, co
     TG_TRY(tg_ingest_page(ctx, page, &in));
     for (auto& c : in.cols)
         if (c.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
-    // 1. rows sorted by destination rank
-    DevBuf ids, sorted_rows, bounds;
-    std::vector<long long> h_bounds(W + 2, 0);
+    if (W > XMAXP) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange across more than %d ranks", XMAXP);
+    // TGPU_TRACE=1: synchronise and print the wall time of every phase (diagnostics only)
+    const bool trace = getenv("TGPU_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[tgpu exchange rank %d] %-22s %8.3f ms\n", ctx->rank, what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    const int C = (int)in.cols.size();
+    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);
+    // 1. partition ids + per-CTA histograms + offsets (stable multi-split, no sort)
+    int grid = tg_grid(ctx, n, XT * 16, 8);
+    int64_t chunk = tg_div_up(tg_div_up(std::max<int64_t>(n, 1), grid), XT) * XT;
+    grid = (int)std::max<int64_t>(1, tg_div_up(std::max<int64_t>(n, 1), chunk));
+    DevBuf pids, hist, block_off, d_totals;
+    TG_TRY(pids.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
+    TG_TRY(hist.alloc(ctx, (size_t)grid * W * 4));
+    TG_TRY(block_off.alloc(ctx, (size_t)grid * W * 8));
+    TG_TRY(d_totals.alloc(ctx, (size_t)(W + C) * 8));
+    std::vector<long long> send_vec(W + C, 0);     // W send counts, then one "has NULLs" flag per column
     if (n > 0) {
-        TG_TRY(ids.alloc(ctx, (size_t)n * 4));
-        TG_TRY(p->compute_ids(in, ids.as<int32_t>(), false));
-        TG_TRY(p->sort_rows(ids.as<int32_t>(), n, &sorted_rows, &bounds));
-        TG_CUDA(ctx, cudaMemcpyAsync(h_bounds.data(), bounds.p, (size_t)(W + 2) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        KeyCols k;
+        TG_TRY(p->key_cols(in, &k));
+        TG_LAUNCH(ctx, xchg_hist_kernel, grid, XT, 0, k, n, chunk, p->bucket_count, p->bucket_to_partition.empty() ? nullptr : p->d_b2p.as<int32_t>(), W,
+                  pids.as<uint8_t>(), hist.as<unsigned int>());
+        TG_LAUNCH(ctx, xchg_offsets_kernel, 1, 64, 0, hist.as<unsigned int>(), grid, W, block_off.as<long long>(), d_totals.as<long long>());
+        TG_CUDA(ctx, cudaMemcpyAsync(send_vec.data(), d_totals.p, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
         TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    // 2. count matrix: every rank learns what every rank sends to whom
-    std::vector<long long> send_counts(W), matrix((size_t)W * W);
-    for (int r = 0; r < W; r++) send_counts[r] = h_bounds[r + 1] - h_bounds[r];
+    mark("hist+offsets");
+    for (int c = 0; c < C; c++) send_vec[W + c] = in.cols[c].validity ? 1 : 0;
+    // 2. count matrix: every rank learns what every rank sends to whom (and which columns carry NULLs anywhere)
+    const int V = W + C;
+    std::vector<long long> matrix((size_t)W * V);
     DevBuf d_send, d_matrix;
-    TG_TRY(d_send.alloc(ctx, (size_t)W * 8));
-    TG_TRY(d_matrix.alloc(ctx, (size_t)W * W * 8));
-    TG_CUDA(ctx, cudaMemcpyAsync(d_send.p, send_counts.data(), (size_t)W * 8, cudaMemcpyHostToDevice, ctx->stream));
-    TG_NCCL(ctx, g_nccl.all_gather(d_send.p, d_matrix.p, (size_t)W, NCCL_INT64, ctx->comm, ctx->stream));
-    TG_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)W * W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_TRY(d_send.alloc(ctx, (size_t)V * 8));
+    TG_TRY(d_matrix.alloc(ctx, (size_t)W * V * 8));
+    TG_CUDA(ctx, cudaMemcpyAsync(d_send.p, send_vec.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, g_nccl.all_gather(d_send.p, d_matrix.p, (size_t)V, NCCL_INT64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)W * V * 8, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<long long> recv_counts(W), recv_off(W + 1, 0);
-    for (int r = 0; r < W; r++) { recv_counts[r] = matrix[(size_t)r * W + ctx->rank]; recv_off[r + 1] = recv_off[r] + recv_counts[r]; }
+    mark("count all-gather");
+    std::vector<long long> send_counts(send_vec.begin(), send_vec.begin() + W), send_off(W + 1, 0), recv_counts(W), recv_off(W + 1, 0);
+    for (int r = 0; r < W; r++) {
+        send_off[r + 1] = send_off[r] + send_counts[r];
+        recv_counts[r] = matrix[(size_t)r * V + ctx->rank];
+        recv_off[r + 1] = recv_off[r] + recv_counts[r];
+    }
     long long total_recv = recv_off[W];
     if (total_recv > (long long)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "exchange output exceeds 2^31-1 rows on rank %d", ctx->rank);
-    // 3. per column: gather into destination order, then all-to-all with explicit counts
+    std::vector<bool> any_nulls(C, false);
+    for (int c = 0; c < C; c++)
+        for (int r = 0; r < W; r++) any_nulls[c] = any_nulls[c] || matrix[(size_t)r * V + W + c] != 0;
+    // 3. one scatter pass writes every column (and the NULL bytes of nullable columns) partition-contiguously
+    struct Lane { int elem; const void* src; DevBuf send; std::shared_ptr<DevBuf> recv; int col; bool nulls; };
+    std::vector<Lane> lanes;
+    for (int c = 0; c < C; c++) {
+        lanes.push_back(Lane{in.cols[c].elem_size(), in.cols[c].data, DevBuf(), nullptr, c, false});
+        if (any_nulls[c]) lanes.push_back(Lane{0, in.cols[c].validity, DevBuf(), nullptr, c, true});
+    }
+    std::vector<char*> h_dst(lanes.size() * W);
+    for (size_t l = 0; l < lanes.size(); l++) {
+        int es = lanes[l].elem ? lanes[l].elem : 1;
+        TG_TRY(lanes[l].send.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * es));
+        lanes[l].recv = std::make_shared<DevBuf>();
+        TG_TRY(lanes[l].recv->alloc(ctx, (size_t)std::max<long long>(total_recv, 1) * es));
+        for (int r = 0; r < W; r++) h_dst[l * W + r] = (char*)lanes[l].send.p + send_off[r] * es;
+        // rows that stay on this GPU are scattered straight into their final place in the receive buffer
+        h_dst[l * W + ctx->rank] = (char*)lanes[l].recv->p + recv_off[ctx->rank] * es;
+    }
+    mark("buffer allocation");
+    DevBuf d_dst;
+    TG_TRY(d_dst.alloc(ctx, h_dst.size() * sizeof(char*)));
+    TG_CUDA(ctx, cudaMemcpyAsync(d_dst.p, h_dst.data(), h_dst.size() * sizeof(char*), cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        XchgCols xc;
+        memset(&xc, 0, sizeof(xc));
+        xc.count = (int32_t)lanes.size();
+        for (size_t l = 0; l < lanes.size(); l++) { xc.elem[l] = lanes[l].elem; xc.src[l] = lanes[l].src; }
+        xc.dst = d_dst.as<char*>();
+        TG_LAUNCH(ctx, xchg_scatter_kernel, grid, XT, 0, pids.as<uint8_t>(), n, chunk, W, block_off.as<long long>(), xc);
+    }
+    mark("scatter");
+    // 4. all-to-all with explicit counts: one NCCL group for every column
+    TG_NCCL(ctx, g_nccl.group_start());
+    for (size_t l = 0; l < lanes.size(); l++) {
+        int es = lanes[l].elem ? lanes[l].elem : 1;
+        for (int r = 0; r < W; r++) {
+            if (r == ctx->rank) continue;
+            if (send_counts[r] > 0)
+                TG_NCCL(ctx, g_nccl.send((const char*)lanes[l].send.p + send_off[r] * es, (size_t)send_counts[r] * es, NCCL_INT8, r, ctx->comm, ctx->stream));
+            if (recv_counts[r] > 0)
+                TG_NCCL(ctx, g_nccl.recv((char*)lanes[l].recv->p + recv_off[r] * es, (size_t)recv_counts[r] * es, NCCL_INT8, r, ctx->comm, ctx->stream));
+        }
+    }
+    TG_NCCL(ctx, g_nccl.group_end());
+    mark("nccl send/recv");
     DevPage outp;
     outp.rows = total_recv;
-    outp.cols.resize(in.cols.size());
-    for (size_t c = 0; c < in.cols.size(); c++) {
-        const DevColumn& src = in.cols[c];
-        int es = src.elem_size();
-        DevColumn sendcol;
-        if (n > 0) TG_TRY(tg_gather_column(ctx, src, sorted_rows.as<int32_t>(), n, false, &sendcol));
-        DevColumn& dst = outp.cols[c];
-        dst.type = src.type;
-        dst.length = total_recv;
-        dst.own_data = std::make_shared<DevBuf>();
-        TG_TRY(dst.own_data->alloc(ctx, (size_t)total_recv * es));
-        dst.data = dst.own_data->p;
-        TG_NCCL(ctx, g_nccl.group_start());
-        for (int r = 0; r < W; r++) {
-            if (send_counts[r] > 0)
-                TG_NCCL(ctx, g_nccl.send((const char*)sendcol.data + h_bounds[r] * es, (size_t)send_counts[r] * es, NCCL_INT8, r, ctx->comm, ctx->stream));
-            if (recv_counts[r] > 0)
-                TG_NCCL(ctx, g_nccl.recv((char*)dst.own_data->p + recv_off[r] * es, (size_t)recv_counts[r] * es, NCCL_INT8, r, ctx->comm, ctx->stream));
+    outp.cols.resize(C);
+    for (auto& lane : lanes) {
+        DevColumn& dst = outp.cols[lane.col];
+        if (!lane.nulls) {
+            dst.type = in.cols[lane.col].type;
+            dst.length = total_recv;
+            dst.own_data = lane.recv;
+            dst.data = lane.recv->p;
         }
-        TG_NCCL(ctx, g_nccl.group_end());
-        // nulls travel as one byte per row (every rank takes part, a column without nulls sends "valid")
-        DevBuf send_nulls, recv_nulls;
-        TG_TRY(send_nulls.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
-        TG_TRY(recv_nulls.alloc(ctx, (size_t)std::max<long long>(total_recv, 1)));
-        if (n > 0)
-            TG_LAUNCH(ctx, validity_to_bytes_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, src.validity, sorted_rows.as<int32_t>(), n, send_nulls.as<uint8_t>());
-        TG_NCCL(ctx, g_nccl.group_start());
-        for (int r = 0; r < W; r++) {
-            if (send_counts[r] > 0) TG_NCCL(ctx, g_nccl.send(send_nulls.as<uint8_t>() + h_bounds[r], (size_t)send_counts[r], NCCL_INT8, r, ctx->comm, ctx->stream));
-            if (recv_counts[r] > 0) TG_NCCL(ctx, g_nccl.recv(recv_nulls.as<uint8_t>() + recv_off[r], (size_t)recv_counts[r], NCCL_INT8, r, ctx->comm, ctx->stream));
-        }
-        TG_NCCL(ctx, g_nccl.group_end());
-        if (total_recv > 0) {
+        else if (total_recv > 0) {
+            // pack the received byte map into an Arrow bitmap
             tgpu_column bytemap_col;
             memset(&bytemap_col, 0, sizeof(bytemap_col));
-            // pack the byte map into an Arrow bitmap through the ingest path of a device column
             bytemap_col.type = TGPU_INT8;
             bytemap_col.flags = TGPU_COL_NULLS_BYTEMAP;
             bytemap_col.length = total_recv;
-            bytemap_col.data = recv_nulls.p;
-            bytemap_col.validity = recv_nulls.as<uint8_t>();
+            bytemap_col.data = lane.recv->p;
+            bytemap_col.validity = lane.recv->as<uint8_t>();
             DevColumn packed;
             TG_TRY(tg_ingest_column(ctx, &bytemap_col, true, &packed));
             dst.own_validity = packed.own_validity;
             dst.validity = packed.validity;
         }
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // send buffers are released after the transfers have left them
     OwnedPage* o = tg_make_owned_page(std::move(outp));
     *out = &o->hdr;
     return TGPU_OK;
