@@ -18,8 +18,10 @@ def reference_cases():
 def oracle_join_rows(build_page, probe_page, build_key, probe_key, probe_out, build_out, join_type, single_match, force_default=False):
     """Rows the reference's LookupJoinOperator emits (probe output channels then build output channels)."""
     import oracle_lib as o
-    j = o.Join(build_page, [build_key], force_default=force_default)
-    pos = j.positions(probe_page, [probe_key])
+    bk = list(build_key) if isinstance(build_key, (list, tuple)) else [build_key]
+    pk = list(probe_key) if isinstance(probe_key, (list, tuple)) else [probe_key]
+    j = o.Join(build_page, bk, force_default=force_default)
+    pos = j.positions(probe_page, pk)
     pi, bi = j.expand(pos, join_type, single_match)
     pcols = [probe_page.get_block(c).flatten().to_pylist() for c in probe_out]
     bcols = [build_page.get_block(c).flatten().to_pylist() for c in build_out]
@@ -33,14 +35,16 @@ def oracle_join_rows(build_page, probe_page, build_key, probe_key, probe_out, bu
 def gpu_join_rows(ctx, build_pages, probe_pages, build_key, probe_key, probe_out, build_out, join_type, single_match):
     from trino_b200 import operators as ops
     bridge = ops.JoinBridge()
-    bf = ops.HashBuilderOperatorFactory(ctx, bridge, [build_key], build_out)
+    bk = list(build_key) if isinstance(build_key, (list, tuple)) else [build_key]
+    pk = list(probe_key) if isinstance(probe_key, (list, tuple)) else [probe_key]
+    bf = ops.HashBuilderOperatorFactory(ctx, bridge, bk, build_out)
     b = bf.create_operator()
     for p in build_pages:
         assert b.needs_input()
         b.add_input(p)
     b.finish()
     assert b.is_finished()
-    pf = ops.LookupJoinOperatorFactory(ctx, bridge, join_type, single_match, [probe_key], probe_out)
+    pf = ops.LookupJoinOperatorFactory(ctx, bridge, join_type, single_match, pk, probe_out)
     j = pf.create_operator()
     out = ops.drive(j, probe_pages)
     rows = []

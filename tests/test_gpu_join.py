@@ -144,7 +144,64 @@ def test_operator_protocol(ctx):
     assert j.needs_input()
     j.finish()
     assert j.is_finished()
-    with pytest.raises(abi.TrinoGpuError) as e:
-        ops.HashBuilderOperatorFactory(ctx, ops.JoinBridge(), [0, 1], []).create_operator()
-    assert e.value.code == abi.ERR_NOT_SUPPORTED
     j.close(); b.close(); bridge.lookup_source.close()
+
+
+# ---------------------------------------------------------------- generic join keys (DefaultPagesHash shape)
+def test_probe_outer_join_with_varchar_key_reference_case(ctx):
+    # TestHashJoinOperator.testProbeOuterJoin :481-530 exactly as written there: VARCHAR join channel
+    c = reference_cases()["probe_outer_sequence"]
+    b0, b1, b2 = c["build_initial"]
+    p0, p1, p2 = c["probe_initial"]
+    nb, npr = c["build_rows"], c["probe_rows"]
+    build = Page(Block.varchar([str(b0 + i) for i in range(nb)]), Block.bigint([b1 + i for i in range(nb)]), Block.bigint([b2 + i for i in range(nb)]))
+    probe = Page(Block.varchar([str(p0 + i) for i in range(npr)]), Block.bigint([p1 + i for i in range(npr)]), Block.bigint([p2 + i for i in range(npr)]))
+    rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1, 2], [0, 1, 2], abi.JOIN_PROBE_OUTER, False)
+    assert rows == oracle_join_rows(build, probe, 0, 0, [0, 1, 2], [0, 1, 2], abi.JOIN_PROBE_OUTER, False)
+    assert rows[0] == (b"20", 1020, 2020, b"20", 30, 40) and rows[-1] == (b"34", 1034, 2034, None, None, None)
+
+
+@pytest.mark.parametrize("join_type,single", [(abi.JOIN_INNER, False), (abi.JOIN_PROBE_OUTER, False), (abi.JOIN_INNER, True)])
+def test_multi_channel_keys_with_nulls_nan_and_duplicates(ctx, join_type, single):
+    rng = np.random.default_rng(77)
+    nb, npr = 4000, 15000
+
+    def side(n, hi):
+        d = rng.integers(0, 4, n).astype(np.float64)
+        d[rng.random(n) < 0.05] = np.nan
+        d[rng.random(n) < 0.05] = -0.0
+        return Page(Block.bigint(rng.integers(0, hi, n), rng.random(n) < 0.03), Block.varchar([None if x < 0.03 else "k%d" % int(x * 5) for x in rng.random(n)]),
+                    Block.double(d, rng.random(n) < 0.03), Block.integer(rng.integers(0, 1000, n)))
+    build, probe = side(nb, 40), side(npr, 50)
+    got = gpu_join_rows(ctx, [build], [probe], [0, 1, 2], [0, 1, 2], [3, 0], [3, 1], join_type, single)
+    want = oracle_join_rows(build, probe, [0, 1, 2], [0, 1, 2], [3, 0], [3, 1], join_type, single)
+    assert rows_equal(got, want)
+    assert len(got) > npr // 10
+
+
+def test_multi_page_build_with_nullable_and_varchar_columns(ctx):
+    rng = np.random.default_rng(5)
+    pages, all_keys, all_pay, all_str = [], [], [], []
+    for n in (700, 1, 64, 5000, 9):
+        k = rng.integers(0, 3000, n)
+        pay = [None if x < 0.1 else float(v) for x, v in zip(rng.random(n), k)]
+        st = [None if x < 0.1 else "s%d" % v for x, v in zip(rng.random(n), k)]
+        pages.append(Page(Block.bigint(k), Block.double(pay), Block.varchar(st)))
+        all_keys += list(k); all_pay += pay; all_str += st
+    whole = Page(Block.bigint(all_keys), Block.double(all_pay), Block.varchar(all_str))
+    probe = Page(Block.bigint(rng.integers(0, 3500, 20000)))
+    got = gpu_join_rows(ctx, pages, [probe], 0, 0, [0], [1, 2], abi.JOIN_INNER, False)
+    assert rows_equal(got, oracle_join_rows(whole, probe, 0, 0, [0], [1, 2], abi.JOIN_INNER, False))
+
+
+def test_generic_lookup_positions_api(ctx):
+    build = Page(Block.bigint([1, 2, 1, 3]), Block.bigint([10, 20, 10, 30]))
+    bridge = ops.JoinBridge()
+    b = ops.HashBuilderOperatorFactory(ctx, bridge, [0, 1], []).create_operator()
+    b.add_input(build)
+    b.finish()
+    lk = bridge.lookup_source
+    pos = lk.get_join_positions(Page(Block.bigint([1, 1, 3, 2, None]), Block.bigint([10, 11, 30, 20, 5])))
+    assert list(pos) == [2, -1, 3, 1, -1]
+    assert lk.has_position_links() and list(lk.position_links()) == [-1, -1, 0, -1]
+    b.close(); lk.close()

@@ -223,6 +223,8 @@ int tg_ingest_column(tgpu_ctx* ctx, const tgpu_column* col, bool device, DevColu
 OwnedPage* tg_make_owned_page(DevPage&& page);
 // gather rows of a column by int32 indices (idx < 0 -> NULL output row)
 int tg_gather_column(tgpu_ctx* ctx, const DevColumn& src, const int32_t* d_idx, int64_t n, bool idx_may_be_negative, DevColumn* out);
+// concatenation of column chunks of one type (PagesIndex keeps block references; the device keeps one flat column)
+int tg_concat_columns(tgpu_ctx* ctx, const std::vector<const DevColumn*>& parts, DevColumn* out);
 // contiguous slice copy of a column
 int tg_slice_column(tgpu_ctx* ctx, const DevColumn& src, int64_t first, int64_t count, DevColumn* out);
 // append `src` to a growing owned column (used by the build-side store)

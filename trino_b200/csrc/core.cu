@@ -396,6 +396,127 @@ int tg_slice_column(tgpu_ctx* ctx, const DevColumn& src, int64_t first, int64_t 
     return tg_gather_column(ctx, src, idx.as<int32_t>(), count, false, out);
 }
 
+struct ConcatParts {
+    const uint8_t* validity[64];
+    long long start[65];
+    int count;
+};
+
+// validity of a concatenation: one thread per output byte, chunk found by a linear scan over <= 64 chunk starts
+__global__ void tg_concat_validity_kernel(ConcatParts parts, int64_t n, uint8_t* __restrict__ out)
+{
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t nbytes = (n + 7) >> 3;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; b < nbytes; b += stride) {
+        unsigned int v = 0;
+        for (int k = 0; k < 8; k++) {
+            int64_t i = (b << 3) + k;
+            if (i >= n) break;
+            int c = 0;
+            while (c + 1 < parts.count && i >= parts.start[c + 1]) c++;
+            if (tg_valid(parts.validity[c], i - parts.start[c])) v |= 1u << k;
+        }
+        out[b] = (uint8_t)v;
+    }
+}
+
+__global__ void tg_rebase_offsets_kernel(const int32_t* __restrict__ src, int64_t count, int32_t delta, int32_t* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) dst[i] = src[i] + delta;
+}
+
+int tg_concat_columns(tgpu_ctx* ctx, const std::vector<const DevColumn*>& parts, DevColumn* out)
+{
+    DevColumn r;
+    if (parts.empty()) { *out = std::move(r); return TGPU_OK; }
+    r.type = parts[0]->type;
+    int64_t n = 0;
+    bool any_validity = false;
+    for (auto* p : parts) {
+        if (p->type != r.type) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "column type changed between pages (%d vs %d)", p->type, r.type);
+        n += p->length;
+        any_validity |= p->validity != nullptr;
+    }
+    r.length = n;
+    if (r.type == TGPU_UTF8) {
+        // value bytes back to back, offsets rebased chunk by chunk
+        std::vector<int32_t> first(parts.size()), last(parts.size());
+        for (size_t c = 0; c < parts.size(); c++) {
+            first[c] = last[c] = 0;
+            if (parts[c]->length == 0) continue;
+            TG_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, parts[c]->offsets, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaMemcpyAsync((char*)ctx->h_scratch + 8, parts[c]->offsets + parts[c]->length, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            first[c] = *(int32_t*)ctx->h_scratch;
+            last[c] = *(int32_t*)((char*)ctx->h_scratch + 8);
+        }
+        int64_t total_bytes = 0;
+        for (size_t c = 0; c < parts.size(); c++) total_bytes += last[c] - first[c];
+        if (total_bytes > INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "variable-width column exceeds 2 GB");
+        TG_TRY(alloc_shared(ctx, (size_t)(n + 1) * 4, &r.own_offsets));
+        TG_TRY(alloc_shared(ctx, (size_t)total_bytes, &r.own_data));
+        int64_t row = 0, byte = 0;
+        for (size_t c = 0; c < parts.size(); c++) {
+            int64_t len = parts[c]->length;
+            if (len == 0) continue;
+            TG_LAUNCH(ctx, tg_rebase_offsets_kernel, tg_grid(ctx, len + 1, 1024, 8), 256, 0, parts[c]->offsets, len + 1, (int32_t)(byte - first[c]),
+                      r.own_offsets->as<int32_t>() + row);
+            if (last[c] > first[c])
+                TG_CUDA(ctx, cudaMemcpyAsync(r.own_data->as<char>() + byte, (const char*)parts[c]->data + first[c], (size_t)(last[c] - first[c]), cudaMemcpyDeviceToDevice, ctx->stream));
+            row += len;
+            byte += last[c] - first[c];
+        }
+        if (n == 0) TG_CUDA(ctx, cudaMemsetAsync(r.own_offsets->p, 0, 4, ctx->stream));
+        r.offsets = r.own_offsets->as<int32_t>();
+        r.data = r.own_data->p;
+        r.data_bytes = total_bytes;
+    }
+    else {
+        int es = r.elem_size();
+        if (es == 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "concat: unsupported column type %d", r.type);
+        TG_TRY(alloc_shared(ctx, (size_t)n * es, &r.own_data));
+        int64_t row = 0;
+        for (auto* p : parts) {
+            if (p->length) TG_CUDA(ctx, cudaMemcpyAsync(r.own_data->as<char>() + row * es, p->data, (size_t)p->length * es, cudaMemcpyDeviceToDevice, ctx->stream));
+            row += p->length;
+        }
+        r.data = r.own_data->p;
+    }
+    if (any_validity && n > 0) {
+        TG_TRY(alloc_shared(ctx, (size_t)((n + 7) / 8), &r.own_validity));
+        // merge chunk runs so the kernel's table holds at most 64 entries per launch
+        size_t c = 0;
+        int64_t row = 0;
+        if (parts.size() <= 64) {
+            ConcatParts cp;
+            memset(&cp, 0, sizeof(cp));
+            cp.count = (int)parts.size();
+            for (c = 0; c < parts.size(); c++) { cp.validity[c] = parts[c]->validity; cp.start[c] = row; row += parts[c]->length; }
+            cp.start[parts.size()] = row;
+            TG_LAUNCH(ctx, tg_concat_validity_kernel, tg_grid(ctx, (n + 7) / 8, 256, 8), 256, 0, cp, n, r.own_validity->as<uint8_t>());
+        }
+        else {
+            // many small pages: fold 64 chunks at a time into an intermediate column, then concatenate those
+            std::vector<DevColumn> mids;
+            for (size_t at = 0; at < parts.size(); at += 64) {
+                std::vector<const DevColumn*> group(parts.begin() + at, parts.begin() + std::min(parts.size(), at + 64));
+                DevColumn mid;
+                TG_TRY(tg_concat_columns(ctx, group, &mid));
+                mids.push_back(std::move(mid));
+            }
+            std::vector<const DevColumn*> refs;
+            for (auto& m : mids) refs.push_back(&m);
+            return tg_concat_columns(ctx, refs, out);
+        }
+        r.validity = r.own_validity->as<uint8_t>();
+    }
+    *out = std::move(r);
+    return TGPU_OK;
+}
+
 // upload (host) or borrow (device) `bytes` of a buffer
 static int put_buffer(tgpu_ctx* ctx, const void* src, size_t bytes, bool device, std::shared_ptr<DevBuf>* own, const void** out)
 {

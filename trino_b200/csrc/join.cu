@@ -20,9 +20,11 @@
 // observable, only key -> head is.
 #include <cub/cub.cuh>
 
-#include "common.cuh"
+#include "rowkeys.cuh"
 
 namespace {
+
+using tg::KeyCols;
 
 constexpr unsigned long long EMPTY_KEY = 0x8000000000000000ULL;   // INT64_MIN is kept out of the table
 
@@ -328,6 +330,46 @@ __global__ void join_match_flags_kernel(const int* __restrict__ jp, int64_t n, u
 }
 
 
+
+// ---- generic join keys (DefaultPagesHash shape: several channels and/or variable width) ---------------------------
+// The table is keyed by the 64-bit ROW HASH of the key columns (the reference's DefaultPagesHash also addresses by
+// mix(rowHash), M/operator/join/DefaultPagesHash.java:105-122).  Exactness comes from two checks against the real key
+// columns: at build time every row must carry the same key as the head of its slot (a 64-bit collision between
+// different keys makes the build answer NOT_SUPPORTED so the caller keeps the Java operator), and at probe time a hit
+// is kept only when the probe row's key equals the build row's key.
+__global__ void join_fingerprint_kernel(KeyCols k, int64_t n, long long* __restrict__ fp, uint8_t* __restrict__ is_null)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        bool ok = tg::row_joinable(k, i);
+        fp[i] = ok ? (long long)tg::row_hash(k, i) : 0;
+        is_null[i] = ok ? 0 : 1;
+    }
+}
+
+__global__ void join_verify_build_kernel(KeyCols k, const long long* __restrict__ fp, const uint8_t* __restrict__ fp_validity, int64_t n,
+                                         const JoinSlot* __restrict__ table, unsigned long long mask, int special_head, int* __restrict__ collision)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        if (!tg_valid(fp_validity, i)) continue;
+        int head = join_lookup(table, mask, (unsigned long long)fp[i], special_head);
+        if (head != (int)i && head >= 0 && !tg::rows_equal_for_join(k, i, k, head)) *collision = 1;
+    }
+}
+
+__global__ void join_verify_probe_kernel(KeyCols probe, KeyCols build, int64_t n, int* __restrict__ jp)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int b = jp[i];
+        if (b >= 0 && !tg::rows_equal_for_join(probe, i, build, b)) jp[i] = -1;
+    }
+}
+
 // ---- lean probe kernels for the headline shape (BIGINT key without NULLs, whole 1024-row tiles) -------------------
 // Same algorithm as join_probe_kernel / join_probe_gather_kernel with the per-row bookkeeping stripped: the layout
 // mode is a template parameter, slot indices are 32-bit, there are no bounds or validity checks (the ragged tail and
@@ -545,9 +587,55 @@ struct tgpu_lookup {
     DevPage store;                      // key column first, then build output columns
     int32_t num_output = 0;
     std::vector<DevBuf> by_slot;        // build output columns in table-slot order (fused probe fast path)
+    bool generic = false;               // keyed by row hash + verification against build_keys
+    std::vector<DevColumn> build_keys;  // generic only: the real key columns of the build side
 };
 
 namespace {
+
+
+// row-hash column (+ validity: NULL / NaN keys can never match) of a set of key columns
+int make_fingerprint(tgpu_ctx* ctx, const std::vector<const DevColumn*>& keys, int64_t n, DevColumn* out)
+{
+    KeyCols k;
+    memset(&k, 0, sizeof(k));
+    if (keys.size() > (size_t)tg::MAX_KEY_COLS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than %d join channels", tg::MAX_KEY_COLS);
+    k.count = (int32_t)keys.size();
+    for (size_t c = 0; c < keys.size(); c++) tg::key_cols_set(&k, (int)c, *keys[c]);
+    DevColumn fp;
+    fp.type = TGPU_INT64;
+    fp.length = n;
+    fp.own_data = std::make_shared<DevBuf>();
+    TG_TRY(fp.own_data->alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 8));
+    fp.data = fp.own_data->p;
+    DevBuf is_null;
+    TG_TRY(is_null.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
+    if (n > 0) {
+        TG_LAUNCH(ctx, join_fingerprint_kernel, tg_grid(ctx, n, 256, 8), 256, 0, k, n, fp.own_data->as<long long>(), is_null.as<uint8_t>());
+        tgpu_column bm;
+        memset(&bm, 0, sizeof(bm));
+        bm.type = TGPU_INT8;
+        bm.flags = TGPU_COL_NULLS_BYTEMAP;
+        bm.length = n;
+        bm.data = is_null.p;
+        bm.validity = is_null.as<uint8_t>();
+        DevColumn packed;
+        TG_TRY(tg_ingest_column(ctx, &bm, true, &packed));
+        fp.own_validity = packed.own_validity;
+        fp.validity = packed.validity;
+    }
+    *out = std::move(fp);
+    return TGPU_OK;
+}
+
+KeyCols key_cols_of(const std::vector<DevColumn>& cols)
+{
+    KeyCols k;
+    memset(&k, 0, sizeof(k));
+    k.count = (int32_t)cols.size();
+    for (size_t c = 0; c < cols.size(); c++) tg::key_cols_set(&k, (int)c, cols[c]);
+    return k;
+}
 
 int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key, int* d_out)
 {
@@ -590,6 +678,26 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
     return TGPU_OK;
 }
 
+// join positions for a generic-key lookup: probe the row hashes, then keep only hits whose key columns really match
+int lookup_positions_generic(tgpu_ctx* ctx, const tgpu_lookup* lk, const std::vector<const DevColumn*>& keys, int64_t n, int* d_out)
+{
+    if (keys.size() != lk->build_keys.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe has %zu join channels, build has %zu", keys.size(), lk->build_keys.size());
+    for (size_t c = 0; c < keys.size(); c++) {
+        bool pu = keys[c]->type == TGPU_UTF8, bu = lk->build_keys[c].type == TGPU_UTF8, pd = keys[c]->type == TGPU_FLOAT64, bd = lk->build_keys[c].type == TGPU_FLOAT64;
+        if (pu != bu || pd != bd) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "join channel %zu: probe type %d does not match build type %d", c, keys[c]->type, lk->build_keys[c].type);
+    }
+    if (n == 0) return TGPU_OK;
+    DevColumn fp;
+    TG_TRY(make_fingerprint(ctx, keys, n, &fp));
+    TG_TRY(lookup_positions(ctx, lk, fp, d_out));
+    KeyCols pk;
+    memset(&pk, 0, sizeof(pk));
+    pk.count = (int32_t)keys.size();
+    for (size_t c = 0; c < keys.size(); c++) tg::key_cols_set(&pk, (int)c, *keys[c]);
+    TG_LAUNCH(ctx, join_verify_probe_kernel, tg_grid(ctx, n, 256, 8), 256, 0, pk, key_cols_of(lk->build_keys), n, d_out);
+    return TGPU_OK;
+}
+
 // HashBuilderOperator: NEEDS_INPUT -> (finish) LOOKUP_SOURCE_BUILT -> CLOSED
 struct JoinBuildOp : tgpu_op {
     std::vector<int32_t> key_channels, output_channels;
@@ -614,7 +722,7 @@ struct JoinBuildOp : tgpu_op {
                 while ((c->type == TGPU_DICT32 || c->type == TGPU_RLE) && c->dictionary) c = c->dictionary;
                 return c->type;
             };
-            col_types.push_back(type_of(key_channels[0]));
+            for (int32_t ch : key_channels) col_types.push_back(type_of(ch));
             for (int32_t ch : output_channels) col_types.push_back(type_of(ch));
         }
         if (page->num_rows == 0) return TGPU_OK;
@@ -630,7 +738,7 @@ struct JoinBuildOp : tgpu_op {
             p.cols.push_back(std::move(c));
             return TGPU_OK;
         };
-        TG_TRY(take(key_channels[0]));
+        for (int32_t ch : key_channels) TG_TRY(take(ch));
         for (int32_t ch : output_channels) TG_TRY(take(ch));
         if (!device) TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         rows += p.rows;
@@ -643,29 +751,12 @@ struct JoinBuildOp : tgpu_op {
         if (chunks.size() == 1) { *out = std::move(chunks[0]); chunks.clear(); return TGPU_OK; }
         DevPage r;
         r.rows = rows;
-        size_t ncols = 1 + output_channels.size();
+        size_t ncols = key_channels.size() + output_channels.size();
         r.cols.resize(ncols);
-        for (size_t c = 0; c < ncols; c++) {
-            DevColumn& d = r.cols[c];
-            d.length = rows;
-            if (chunks.empty()) { d.type = TGPU_INT64; continue; }
-            d.type = chunks[0].cols[c].type;
-            bool any_valid = false;
-            for (auto& ch : chunks) any_valid |= ch.cols[c].validity != nullptr;
-            if (d.type == TGPU_UTF8 || any_valid) {
-                // general path: gather-append through row indices is overkill here; variable-width and nullable
-                // build columns are concatenated on the host-side shim for now
-                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "multi-page build with nullable or variable-width columns is not supported yet");
-            }
-            int es = d.elem_size();
-            d.own_data = std::make_shared<DevBuf>();
-            TG_TRY(d.own_data->alloc(ctx, (size_t)rows * es));
-            int64_t off = 0;
-            for (auto& ch : chunks) {
-                TG_CUDA(ctx, cudaMemcpyAsync((char*)d.own_data->p + off * es, ch.cols[c].data, (size_t)ch.rows * es, cudaMemcpyDeviceToDevice, ctx->stream));
-                off += ch.rows;
-            }
-            d.data = d.own_data->p;
+        for (size_t c = 0; c < ncols && !chunks.empty(); c++) {
+            std::vector<const DevColumn*> parts;
+            for (auto& ch : chunks) parts.push_back(&ch.cols[c]);
+            TG_TRY(tg_concat_columns(ctx, parts, &r.cols[c]));
         }
         chunks.clear();
         *out = std::move(r);
@@ -680,14 +771,27 @@ struct JoinBuildOp : tgpu_op {
         lk->ctx = ctx;
         lk->positions = rows;
         lk->num_output = (int32_t)output_channels.size();
-        TG_TRY(concat(&lk->store));
+        DevPage all;
+        TG_TRY(concat(&all));
+        const size_t nk = key_channels.size();
         if (rows == 0) {
-            lk->store.cols.resize(1 + output_channels.size());
-            for (size_t c = 0; c < lk->store.cols.size(); c++) lk->store.cols[c].type = c < col_types.size() && col_types[c] ? col_types[c] : TGPU_INT64;
-            lk->key_type = lk->store.cols[0].type;
+            all.cols.resize(nk + output_channels.size());
+            for (size_t c = 0; c < all.cols.size(); c++) all.cols[c].type = c < col_types.size() && col_types[c] ? col_types[c] : TGPU_INT64;
         }
-        else lk->key_type = lk->store.cols[0].type;
-        if (lk->key_type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width join keys are not supported on the GPU path");
+        // one fixed-width channel -> the table is keyed by the value itself; anything else -> by the row hash + verification
+        lk->generic = nk != 1 || all.cols[0].type == TGPU_UTF8;
+        lk->store.rows = rows;
+        if (lk->generic) {
+            for (size_t c = 0; c < nk; c++) lk->build_keys.push_back(all.cols[c]);
+            std::vector<const DevColumn*> kp;
+            for (auto& c : lk->build_keys) kp.push_back(&c);
+            DevColumn fp;
+            TG_TRY(make_fingerprint(ctx, kp, rows, &fp));
+            lk->store.cols.push_back(std::move(fp));
+        }
+        else lk->store.cols.push_back(all.cols[0]);
+        for (size_t c = nk; c < all.cols.size(); c++) lk->store.cols.push_back(all.cols[c]);
+        lk->key_type = lk->store.cols[0].type;
         // sizing: IncrementalLoadFactorHashArraySizeSupplier.getHashArraySize :40-47 (capacity is not observable)
         double lf = rows <= (1 << 16) ? 0.25 : rows <= (1 << 20) ? 0.5 : 0.75;
         int64_t need = (int64_t)((double)rows / lf) + 1;
@@ -731,6 +835,17 @@ struct JoinBuildOp : tgpu_op {
             TG_TRY(lk->links.alloc(ctx, (size_t)rows * 4));
             TG_LAUNCH(ctx, join_links_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, keys_out.as<unsigned long long>(), rows, lk->links.as<int>());
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        if (lk->generic && rows > 0) {
+            int* d_collision = (int*)(ctx->d_scratch + 16);
+            TG_CUDA(ctx, cudaMemsetAsync(d_collision, 0, 8, ctx->stream));
+            const DevColumn& fp = lk->store.cols[0];
+            TG_LAUNCH(ctx, join_verify_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, key_cols_of(lk->build_keys), (const long long*)fp.data, fp.validity, rows,
+                      lk->table.as<JoinSlot>(), lk->mask, lk->special_head, d_collision);
+            int64_t collided = 0;
+            TG_TRY(tg_read_i64(ctx, d_collision, &collided));
+            if (collided & 0xFFFFFFFFLL)
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "two different join keys share one 64-bit row hash: keep the Java operator for this build side");
         }
         // slot-ordered copy of the build output columns for the fused probe
         bool slot_payload = !getenv("TGPU_JOIN_PAYLOAD_BY_ROW") && rows > 0 && lk->num_output > 0 && lk->num_output <= 4;
@@ -909,8 +1024,11 @@ struct JoinProbeOp : tgpu_op {
         if (key_channels[0] < 0 || key_channels[0] >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key channel out of range");
         for (int32_t ch : output_channels)
             if (ch < 0 || ch >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe output channel out of range");
+        for (int32_t ch : key_channels)
+            if (ch < 0 || ch >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key channel out of range");
         const DevColumn& key = in.cols[key_channels[0]];
-        if (!getenv("TGPU_JOIN_GENERAL_PATH")) {
+        if (!lookup->generic && key_channels.size() != 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe has %zu join channels, build has 1", key_channels.size());
+        if (!lookup->generic && !getenv("TGPU_JOIN_GENERAL_PATH")) {
             bool handled = false;
             TG_TRY(fast_path(in, key, n, &handled));
             if (handled) return TGPU_OK;
@@ -918,7 +1036,12 @@ struct JoinProbeOp : tgpu_op {
         // joinPositionCache (JoinProbe.java:112-180)
         auto jp = std::make_shared<DevBuf>();
         TG_TRY(jp->alloc(ctx, (size_t)(n + 1) * 4));
-        TG_TRY(lookup_positions(ctx, lookup, key, jp->as<int>()));
+        if (lookup->generic) {
+            std::vector<const DevColumn*> kp;
+            for (int32_t ch : key_channels) kp.push_back(&in.cols[ch]);
+            TG_TRY(lookup_positions_generic(ctx, lookup, kp, n, jp->as<int>()));
+        }
+        else TG_TRY(lookup_positions(ctx, lookup, key, jp->as<int>()));
         bool outer = join_type == TGPU_JOIN_PROBE_OUTER;
         const int* links = lookup->has_dups ? lookup->links.as<int>() : nullptr;
         // match counts -> exclusive scan -> output offsets
@@ -987,8 +1110,8 @@ struct JoinProbeOp : tgpu_op {
 extern "C" int tgpu_join_build_create(tgpu_ctx* ctx, const tgpu_join_build_spec* spec, tgpu_op** out)
 {
     if (!ctx || !spec || !out) return TGPU_ERR_INVALID_ARGUMENT;
-    if (spec->num_key_channels != 1)
-        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports exactly one fixed-width join channel (got %d)", spec->num_key_channels);
+    if (spec->num_key_channels < 1 || spec->num_key_channels > tg::MAX_KEY_COLS)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports 1..%d join channels (got %d)", tg::MAX_KEY_COLS, spec->num_key_channels);
     JoinBuildOp* op = new JoinBuildOp(ctx);
     op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
     op->output_channels.assign(spec->output_channels, spec->output_channels + spec->num_output_channels);
@@ -1030,8 +1153,8 @@ extern "C" int tgpu_lookup_has_duplicates(const tgpu_lookup* lookup) { return lo
 extern "C" int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec* spec, tgpu_lookup* lookup, tgpu_op** out)
 {
     if (!ctx || !spec || !lookup || !out) return TGPU_ERR_INVALID_ARGUMENT;
-    if (spec->num_key_channels != 1)
-        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports exactly one fixed-width join channel (got %d)", spec->num_key_channels);
+    if (spec->num_key_channels < 1 || spec->num_key_channels > tg::MAX_KEY_COLS)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports 1..%d join channels (got %d)", tg::MAX_KEY_COLS, spec->num_key_channels);
     if (spec->join_type != TGPU_JOIN_INNER && spec->join_type != TGPU_JOIN_PROBE_OUTER)
         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "join type %d needs LookupOuterOperator: keep the Java operator", spec->join_type);
     JoinProbeOp* op = new JoinProbeOp(ctx, lookup);
@@ -1047,9 +1170,22 @@ extern "C" int tgpu_lookup_get_join_positions(tgpu_ctx* ctx, const tgpu_lookup* 
 {
     if (!ctx || !lookup || !keys_page || !out_positions) return TGPU_ERR_INVALID_ARGUMENT;
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (keys_page->num_columns != 1) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exactly one key column expected");
     bool device = (keys_page->flags & TGPU_PAGE_DEVICE) != 0;
     int64_t n = keys_page->num_rows;
+    if (lookup->generic) {
+        DevPage kp;
+        TG_TRY(tg_ingest_page(ctx, keys_page, &kp));
+        std::vector<const DevColumn*> refs;
+        for (auto& c : kp.cols) refs.push_back(&c);
+        if (device) return lookup_positions_generic(ctx, lookup, refs, n, out_positions);
+        DevBuf gout;
+        TG_TRY(gout.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4));
+        TG_TRY(lookup_positions_generic(ctx, lookup, refs, n, gout.as<int>()));
+        TG_CUDA(ctx, cudaMemcpyAsync(out_positions, gout.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return TGPU_OK;
+    }
+    if (keys_page->num_columns != 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "exactly one key column expected");
     DevColumn key;
     TG_TRY(tg_ingest_column(ctx, &keys_page->columns[0], device, &key));
     if (device) return lookup_positions(ctx, lookup, key, out_positions);

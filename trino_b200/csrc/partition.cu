@@ -20,31 +20,11 @@
 
 #include <chrono>
 
-#include "common.cuh"
+#include "rowkeys.cuh"
 
 namespace {
 
 using namespace tg;
-
-struct KeyCols {
-    int32_t count;
-    ColRef cols[8];
-    const int32_t* offsets[8];   // UTF8 only
-    int32_t is_utf8[8];
-    int32_t is_double[8];
-};
-
-__device__ __forceinline__ uint64_t type_hash(const KeyCols& k, int c, int64_t row)
-{
-    const ColRef& col = k.cols[c];
-    if (!tg_valid(col.validity, row)) return 0;   // NULL_HASH_CODE (S/type/TypeUtils.java:34)
-    if (k.is_utf8[c]) {
-        int32_t a = k.offsets[c][row], b = k.offsets[c][row + 1];
-        return xxh64_bytes((const uint8_t*)col.data + a, b - a);
-    }
-    int64_t v = tg_load_i64(col, row);
-    return k.is_double[c] ? hash_double_bits(v) : hash_long(v);
-}
 
 // partition id per row; rows whose null_channel is NULL get id == partition_count (replicated later)
 __global__ void __launch_bounds__(256) partition_ids_kernel(KeyCols keys, int64_t n, int32_t bucket_count, const int32_t* __restrict__ bucket_to_partition,
@@ -250,11 +230,7 @@ struct PartitionOp : tgpu_op {
         for (int c = 0; c < k->count; c++) {
             int ch = key_channels[c];
             if (ch < 0 || ch >= (int)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition channel %d out of range", ch);
-            const DevColumn& col = in.cols[ch];
-            k->cols[c] = tg_colref(col);
-            k->offsets[c] = col.offsets;
-            k->is_utf8[c] = col.type == TGPU_UTF8;
-            k->is_double[c] = col.type == TGPU_FLOAT64;
+            key_cols_set(k, c, in.cols[ch]);
         }
         return TGPU_OK;
     }

@@ -1,0 +1,92 @@
+// rowkeys.cuh — row-level key helpers over a set of key columns: the reference's row hash
+// (M/operator/InterpretedHashGenerator.java:102-110: h = 31*h + typeHash(col), NULL -> 0) and the two notions of
+// key equality the operators need: EQUAL (joins; M/operator/SimplePagesHashStrategy.java:194-260: NaN never matches,
+// -0.0 == +0.0) and IDENTICAL (group by; S/type/DoubleType.java:218-229: NaN identical to NaN, NULL identical to NULL).
+#pragma once
+#include "common.cuh"
+
+namespace tg {
+
+constexpr int MAX_KEY_COLS = 8;
+
+struct KeyCols {
+    int32_t count;
+    ColRef cols[MAX_KEY_COLS];
+    const int32_t* offsets[MAX_KEY_COLS];   // UTF8 only
+    int32_t is_utf8[MAX_KEY_COLS];
+    int32_t is_double[MAX_KEY_COLS];
+};
+
+static inline void key_cols_set(KeyCols* k, int c, const DevColumn& col)
+{
+    k->cols[c] = tg_colref(col);
+    k->offsets[c] = col.offsets;
+    k->is_utf8[c] = col.type == TGPU_UTF8;
+    k->is_double[c] = col.type == TGPU_FLOAT64;
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t type_hash(const KeyCols& k, int c, int64_t row)
+{
+    const ColRef& col = k.cols[c];
+    if (!tg_valid(col.validity, row)) return 0;   // NULL_HASH_CODE (S/type/TypeUtils.java:34)
+    if (k.is_utf8[c]) {
+        int32_t a = k.offsets[c][row], b = k.offsets[c][row + 1];
+        return xxh64_bytes((const uint8_t*)col.data + a, b - a);
+    }
+    int64_t v = tg_load_i64(col, row);
+    return k.is_double[c] ? hash_double_bits(v) : hash_long(v);
+}
+
+__device__ __forceinline__ uint64_t row_hash(const KeyCols& k, int64_t row)
+{
+    uint64_t h = 0;
+    for (int c = 0; c < k.count; c++) h = combine_hash(h, type_hash(k, c, row));
+    return h;
+}
+
+// true when the row can take part in an equi-join: no NULL key and no NaN key
+__device__ __forceinline__ bool row_joinable(const KeyCols& k, int64_t row)
+{
+    for (int c = 0; c < k.count; c++) {
+        const ColRef& col = k.cols[c];
+        if (!tg_valid(col.validity, row)) return false;
+        if (k.is_double[c]) {
+            unsigned long long u = (unsigned long long)tg_load_i64(col, row);
+            if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) return false;
+        }
+    }
+    return true;
+}
+
+// value equality of non-NULL keys column by column (EQUAL for joinable rows; with nan_equal also IDENTICAL on values)
+__device__ __forceinline__ bool col_value_equal(const KeyCols& a, int c, int64_t ra, const KeyCols& b, int64_t rb, bool nan_equal)
+{
+    if (a.is_utf8[c]) {
+        int32_t a0 = a.offsets[c][ra], la = a.offsets[c][ra + 1] - a0;
+        int32_t b0 = b.offsets[c][rb], lb = b.offsets[c][rb + 1] - b0;
+        if (la != lb) return false;
+        const uint8_t* pa = (const uint8_t*)a.cols[c].data + a0;
+        const uint8_t* pb = (const uint8_t*)b.cols[c].data + b0;
+        for (int32_t i = 0; i < la; i++)
+            if (pa[i] != pb[i]) return false;
+        return true;
+    }
+    int64_t va = tg_load_i64(a.cols[c], ra), vb = tg_load_i64(b.cols[c], rb);
+    if (a.is_double[c]) {
+        double x = __longlong_as_double(va), y = __longlong_as_double(vb);
+        if (nan_equal && x != x && y != y) return true;
+        return x == y;
+    }
+    return va == vb;
+}
+
+__device__ __forceinline__ bool rows_equal_for_join(const KeyCols& a, int64_t ra, const KeyCols& b, int64_t rb)
+{
+    for (int c = 0; c < a.count; c++)
+        if (!col_value_equal(a, c, ra, b, rb, false)) return false;
+    return true;
+}
+#endif
+
+}  // namespace tg
