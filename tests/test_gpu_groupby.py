@@ -72,8 +72,36 @@ def test_group_ids_packed_multi_column_and_other_types(ctx):
     assert list(g.get_group_ids(Page(k))) == [0, 1, 0, 2, 1]
     g.close()
     with pytest.raises(abi.TrinoGpuError) as e:
-        ops.GroupByHash(ctx, [0, 1], 10).get_group_ids(Page(Block.bigint([1]), Block.bigint([2])))
-    assert e.value.code == abi.ERR_NOT_SUPPORTED
+        ops.GroupByHash(ctx, [0], 10).get_group_ids(Page(Block.varchar(["a"])))
+    assert e.value.code == abi.ERR_NOT_SUPPORTED     # variable-width keys: pass dictionary codes
+
+
+def test_group_ids_wide_composite_keys_use_fingerprints(ctx):
+    # keys that do not pack into 63 bits (FlatHash territory): 64-bit fingerprint table + verification against stored keys
+    rng = np.random.default_rng(23)
+    g = ops.GroupByHash(ctx, [0, 1, 2], 1000)
+    og = o.GroupByHash(0, 1000)
+    for n in (30000, 1, 70000):
+        d = rng.integers(0, 5, n).astype(np.float64)
+        d[rng.random(n) < 0.05] = np.nan
+        d[rng.random(n) < 0.05] = -0.0
+        page = Page(Block.bigint(rng.integers(-2**62, 2**62, 40)[rng.integers(0, 40, n)], rng.random(n) < 0.02), Block.bigint(rng.integers(0, 30, n)),
+                    Block.double(d, rng.random(n) < 0.02))
+        assert (g.get_group_ids(page) == og.get_group_ids(page, [0, 1, 2])).all()
+        assert g.get_group_count() == og.group_count()
+    g.close(); og.close()
+
+
+def test_aggregation_with_wide_composite_keys(ctx):
+    rng = np.random.default_rng(31)
+    n = 20000
+    pages = [Page(Block.bigint(rng.integers(0, 40, n)), Block.bigint(rng.integers(10**12, 10**12 + 25, n), rng.random(n) < 0.05),
+                  Block.double(rng.normal(size=n)), Block.bigint(rng.integers(-9, 9, n))) for _ in range(2)]
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 2, -1), (abi.AGG_SUM, 3, -1), (abi.AGG_MAX, 2, -1)]
+    got = _gpu_agg(ctx, pages, [0, 1], aggs)
+    want = _oracle_agg(pages, [0, 1], aggs)
+    assert rows_equal(got, want, rel=1e-6)
+    assert [r[:3] for r in got] == [r[:3] for r in want]
 
 
 # ---------------------------------------------------------------- aggregation

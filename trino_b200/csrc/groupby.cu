@@ -70,6 +70,8 @@ struct AggPlan {
     int32_t num_accs;
     AccDesc accs[MAX_ACCS];
     int32_t has_pre;
+    int32_t key_hashed;              // keys do not pack into 63 bits: the table is keyed by a 64-bit fingerprint of the tuple,
+                                     // every row is verified against the stored key values (path G only)
 };
 
 // which accumulators the specialised kernel really maintains: a NONNULL counter over an input that cannot be
@@ -102,6 +104,17 @@ __device__ __forceinline__ Fetched fetch_src(const SrcRef& s, const DColumns& co
     return f;
 }
 
+// IDENTICAL-canonical bits of a key value: -0.0 -> +0.0, every NaN -> one NaN (S/type/DoubleType.java:218-229)
+__device__ __forceinline__ unsigned long long canonical_key_bits(long long bits, int is_double)
+{
+    unsigned long long u = (unsigned long long)bits;
+    if (is_double) {
+        if ((u << 1) == 0) u = 0;
+        if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;
+    }
+    return u;
+}
+
 // canonical packed key of a row.  Returns the special-slot index (0 NULL key, 1 sentinel-valued key) or -1.
 __device__ __forceinline__ int pack_key(const AggPlan& plan, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits,
                                         unsigned long long* out)
@@ -116,6 +129,17 @@ __device__ __forceinline__ int pack_key(const AggPlan& plan, const DColumns& col
         }
         if (u == EMPTY_KEY) return S_SPECIAL_SENTINEL;
         *out = u;
+        return -1;
+    }
+    if (plan.key_hashed) {
+        unsigned long long h = 0x9E3779B97F4A7C15ULL;
+        for (int k = 0; k < plan.num_keys; k++) {
+            Fetched f = fetch_src(plan.srcs[plan.key_src[k]], cols, row, temps, tstride, nullbits);
+            unsigned long long u = f.is_null ? 0ULL : canonical_key_bits(f.bits, plan.key_is_double[k]);
+            h = murmur3_mix(h ^ u) * 31ULL + (f.is_null ? 1ULL : 0ULL);
+        }
+        if (h == EMPTY_KEY) return S_SPECIAL_SENTINEL;
+        *out = h;
         return -1;
     }
     unsigned long long pk = 0;
@@ -481,6 +505,25 @@ __global__ void g_gid_kernel(int64_t n, const GSlot* __restrict__ table, const G
     for (; row < n; row += stride) {
         int s = slot_of_row[row];
         gids[row] = s <= -2 ? special->gid[-2 - s] : table[s].gid;
+    }
+}
+
+// hashed keys: every row must carry the key tuple stored for its group (first-seen values), else two different tuples
+// share one 64-bit fingerprint and the GPU path must not be used for this query
+__global__ void g_verify_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ gids, AggState st, int* __restrict__ mismatch)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; row < n; row += stride) {
+        int gid = gids[row];
+        for (int k = 0; k < plan.num_keys; k++) {
+            Fetched f = fetch_src(plan.srcs[plan.key_src[k]], cols, row, nullptr, 0, 0);
+            bool sn = st.keynull[(size_t)k * st.cap + gid] != 0;
+            bool same = f.is_null == sn;
+            if (same && !sn)
+                same = canonical_key_bits(f.bits, plan.key_is_double[k]) == canonical_key_bits(st.keyvals[(size_t)k * st.cap + gid], plan.key_is_double[k]);
+            if (!same) *mismatch = 1;
+        }
     }
 }
 
@@ -977,8 +1020,7 @@ struct AggOp : tgpu_op {
             key_types.push_back(type);
             total_bits += bits + 1;
         }
-        if (nk > 1 && total_bits > 63)
-            return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "group-by keys need %d bits; the GPU path packs keys into 63 bits", total_bits);
+        plan.key_hashed = (nk > 1 && total_bits > 63) ? 1 : 0;
         fnplans.clear();
         fn_input_types.clear();
         bool from_state = step == TGPU_STEP_FINAL || step == TGPU_STEP_INTERMEDIATE;
@@ -1108,6 +1150,7 @@ struct AggOp : tgpu_op {
         s_L = 0;
         s_grid = 0;
         if (!set_small_L(4)) use_general = true;
+        if (plan.key_hashed) use_general = true;   // the shared-memory path needs exactly packed keys
         if (expected_groups > S_GMAX * 4) use_general = true;   // planner expects many groups: skip the S attempt
         return TGPU_OK;
     }
@@ -1310,6 +1353,15 @@ struct AggOp : tgpu_op {
                       flags.as<unsigned char>(), rank.as<int>(), (int)group_count, state());
         TG_LAUNCH(ctx, g_gid_kernel, grid, 256, 0, n, g_table.as<GSlot>(), g_special.as<GSpecial>(), slot_of_row.as<int>(), d_gids);
         group_count += total_new;
+        if (plan.key_hashed) {
+            int* d_mismatch = (int*)(ctx->d_scratch + 18);
+            TG_CUDA(ctx, cudaMemsetAsync(d_mismatch, 0, 8, ctx->stream));
+            TG_LAUNCH(ctx, g_verify_kernel, grid, 256, 0, plan, cols, n, d_gids, state(), d_mismatch);
+            int64_t bad = 0;
+            TG_TRY(tg_read_i64(ctx, d_mismatch, &bad));
+            if (bad & 0xFFFFFFFFLL)
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "two different group-by keys share one 64-bit fingerprint: keep the Java operator for this query");
+        }
         return TGPU_OK;
     }
 
