@@ -134,7 +134,8 @@ def workload_config(args, n_orders, probe_rows, world):
     return {"workload": f"lineitem JOIN orders hash join, synthetic SF{args.sf:g}, BIGINT join key, INNER, build payload o_orderdate (days, BIGINT), "
                         f"probe payload l_extendedprice FLOAT64 (BASELINE.json configs[1])",
             "build_rows_per_gpu": n_orders, "probe_rows_per_gpu": probe_rows, "probe_order": "orderkey-clustered" if not args.shuffle_probe else "shuffled",
-            "parallelism": f"hash-partitioned x{world}" if world > 1 else "single GPU",
+            "parallelism": (f"hash-partitioned x{world}, probe side exchanged every step " +
+                            ("over NCCL send/recv" if os.environ.get("TGPU_EXCHANGE_NCCL") else "by P2P stores into peer HBM (NVLink)")) if world > 1 else "single GPU",
             "l2": "inputs (9.6 GB probe side, 4.3 GB table at SF100) are far larger than the 126 MB L2; no flush needed"}
 
 
@@ -240,6 +241,18 @@ def main():
     build_s = time.time() - t_build0
     lookup = bridge.lookup_source
     probe_op = ops.LookupJoinOperatorFactory(ctx, bridge, abi.JOIN_INNER, False, [0], [0, 1]).create_operator()
+    if world > 1 and not os.environ.get("TGPU_EXCHANGE_NCCL"):
+        # peer-memory exchange for the probe side: two receive arenas per rank, IPC handles all-gathered once.
+        # (created only now: the build-side page above went through NCCL send/recv and is owned by the lookup source)
+        import torch
+        arena_bytes = int(l_count * 1.3) * 16 + (4 << 20)
+        hb = (C.c_uint8 * (2 * abi.IPC_HANDLE_BYTES))()
+        ctx.check(lib.tgpu_comm_arena_create(ctx.h, arena_bytes, C.cast(hb, C.c_void_p)))
+        mine = torch.tensor(list(hb), dtype=torch.uint8, device=f"cuda:{local}")
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        allh = (C.c_uint8 * (world * 2 * abi.IPC_HANDLE_BYTES))(*torch.cat(gathered).cpu().tolist())
+        ctx.check(lib.tgpu_comm_arena_open(ctx.h, C.cast(allh, C.c_void_p)))
 
     out_rows_seen = [0]
     kernel_ms = []

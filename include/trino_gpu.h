@@ -320,6 +320,14 @@ int tgpu_partition_get_partitions(tgpu_op* op, const tgpu_page* page, int32_t* o
 int tgpu_comm_get_unique_id(uint8_t id[TGPU_COMM_ID_BYTES]);
 int tgpu_comm_init(tgpu_ctx* ctx, const uint8_t id[TGPU_COMM_ID_BYTES], int rank, int world);
 int tgpu_comm_destroy(tgpu_ctx* ctx);
+/* Peer-memory exchange (NVLink P2P): every rank allocates two receive arenas of `bytes` each and exports their CUDA IPC
+ * handles; the host distributes the handles (all-gather) and every rank maps all of them.  With arenas in place
+ * tgpu_exchange_partitioned scatters rows STRAIGHT INTO THE DESTINATION GPU'S HBM from the partitioning kernel (no send
+ * buffer, no separate transfer) and synchronises with one tiny NCCL all-reduce.  The returned page then aliases an arena
+ * and stays valid until the second-next exchange on this context; exchanges that do not fit fall back to NCCL send/recv. */
+#define TGPU_IPC_HANDLE_BYTES 64
+int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[2 * TGPU_IPC_HANDLE_BYTES]);
+int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles /* world x 2 x TGPU_IPC_HANDLE_BYTES, rank-major */);
 /* Hash-partition a device-resident page into `world` partitions and exchange: partition p goes to
  * rank p.  Returns the concatenation (in rank order) of what every rank sent here, as a
  * library-owned device page.  Fixed-width columns only.                                         */

@@ -80,11 +80,24 @@ def main():
     rows = gpu_join_rows(ctx, [got_o], [got_l], 0, 0, [0, 2], [1], abi.JOIN_INNER, False)
     want = oracle_join_rows(got_o, got_l, 0, 0, [0, 2], [1], abi.JOIN_INNER, False)
     assert rows == want and len(rows) == got_l.position_count
+    # ---- peer-memory path: same exchange through P2P stores into the destination's arena, twice (arenas alternate)
+    hb = (C.c_uint8 * (2 * abi.IPC_HANDLE_BYTES))()
+    ctx.check(lib.tgpu_comm_arena_create(ctx.h, 64 << 20, C.cast(hb, C.c_void_p)))
+    mine_h = torch.tensor(list(hb), dtype=torch.uint8, device=f"cuda:{local}")
+    gathered = [torch.zeros_like(mine_h) for _ in range(world)]
+    dist.all_gather(gathered, mine_h)
+    allh = (C.c_uint8 * (world * 2 * abi.IPC_HANDLE_BYTES))(*torch.cat(gathered).cpu().tolist())
+    ctx.check(lib.tgpu_comm_arena_open(ctx.h, C.cast(allh, C.c_void_p)))
+    for _ in range(3):
+        p2p_l = exchange(lpage)
+        assert p2p_l.rows() == got_l.rows()          # identical rows in identical order to the NCCL path
+        p2p_o = exchange(opage)
+        assert p2p_o.rows() == got_o.rows()
     part.close()
     ctx.check(lib.tgpu_comm_destroy(ctx.h))
     dist.barrier()
     if rank == 0:
-        print(f"dist_exchange_check ok: world={world} rows={total_rows}")
+        print(f"dist_exchange_check ok (NCCL and P2P paths): world={world} rows={total_rows}")
     dist.destroy_process_group()
     ctx.close()
 

@@ -30,6 +30,7 @@ AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX = 0, 1, 2, 3, 4, 5
 STEP_SINGLE, STEP_PARTIAL, STEP_FINAL, STEP_INTERMEDIATE = 0, 1, 2, 3
 JOIN_INNER, JOIN_PROBE_OUTER = 0, 1
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class Column(C.Structure):
@@ -185,6 +186,8 @@ SIGNATURES = {
     "tgpu_comm_get_unique_id": (C.c_int, [VP]),
     "tgpu_comm_init": (C.c_int, [VP, VP, C.c_int, C.c_int]),
     "tgpu_comm_destroy": (C.c_int, [VP]),
+    "tgpu_comm_arena_create": (C.c_int, [VP, C.c_size_t, VP]),
+    "tgpu_comm_arena_open": (C.c_int, [VP, VP]),
     "tgpu_exchange_partitioned": (C.c_int, [VP, VP, PP, C.POINTER(PP)]),
     "tgpu_op_needs_input": (C.c_int, [VP, C.POINTER(C.c_int)]),
     "tgpu_op_add_input": (C.c_int, [VP, PP]),

@@ -48,6 +48,11 @@ struct tgpu_ctx {
     // NCCL
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory exchange arenas (two per rank, alternating): arena[k][r] = rank r's k-th arena mapped into this process
+    void* arena_local[2] = {nullptr, nullptr};
+    std::vector<void*> arena_peer[2];
+    size_t arena_bytes = 0;
+    int64_t arena_epoch = 0;
 };
 
 int tg_fail(tgpu_ctx* ctx, int status, const char* fmt, ...);

@@ -122,15 +122,36 @@ __global__ void __launch_bounds__(XT) xchg_hist_kernel(KeyCols keys, int64_t n, 
     for (int i = threadIdx.x; i < P; i += XT) sh[i] = 0;
     __syncthreads();
     int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
-    for (int64_t row = begin + threadIdx.x; row < end; row += XT) {
-        uint64_t h = 0;
-        for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
-        int32_t bucket = process_raw_hash(h, bucket_count);
-        int32_t pid = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
-        pid_out[row] = (uint8_t)pid;
-        // warp-aggregated histogram update
-        unsigned int peers = __match_any_sync(__activemask(), pid);
-        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[pid], __popc(peers));
+    if (P <= 8) {
+        // few partitions (one per GPU of a box): private register counters, no per-row atomics or warp votes
+        unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int64_t row = begin + threadIdx.x; row < end; row += XT) {
+            uint64_t h = 0;
+            for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
+            int32_t bucket = process_raw_hash(h, bucket_count);
+            int32_t pid = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
+            pid_out[row] = (uint8_t)pid;
+#pragma unroll
+            for (int q = 0; q < 8; q++) cnt[q] += (pid == q);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            unsigned int v = cnt[q];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if ((threadIdx.x & 31) == 0 && v && q < P) atomicAdd(&sh[q], v);
+        }
+    }
+    else {
+        for (int64_t row = begin + threadIdx.x; row < end; row += XT) {
+            uint64_t h = 0;
+            for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
+            int32_t bucket = process_raw_hash(h, bucket_count);
+            int32_t pid = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
+            pid_out[row] = (uint8_t)pid;
+            // warp-aggregated histogram update
+            unsigned int peers = __match_any_sync(__activemask(), pid);
+            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[pid], __popc(peers));
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < P; i += XT) hist[(size_t)blockIdx.x * P + i] = sh[i];
@@ -392,6 +413,7 @@ typedef int (*nccl_send_t)(const void*, size_t, int, int, ncclComm*, cudaStream_
 typedef int (*nccl_recv_t)(void*, size_t, int, int, ncclComm*, cudaStream_t);
 typedef int (*nccl_group_t)(void);
 typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, ncclComm*, cudaStream_t);
+typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t);
 typedef const char* (*nccl_get_error_string_t)(int);
 
 struct NcclApi {
@@ -403,6 +425,7 @@ struct NcclApi {
     nccl_recv_t recv = nullptr;
     nccl_group_t group_start = nullptr, group_end = nullptr;
     nccl_all_gather_t all_gather = nullptr;
+    nccl_all_reduce_t all_reduce = nullptr;
     nccl_get_error_string_t error_string = nullptr;
 };
 
@@ -422,6 +445,7 @@ int load_nccl(tgpu_ctx* ctx)
     g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
     g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
     g_nccl.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
+    g_nccl.all_reduce = (nccl_all_reduce_t)dlsym(h, "ncclAllReduce");
     g_nccl.error_string = (nccl_get_error_string_t)dlsym(h, "ncclGetErrorString");
     if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end || !g_nccl.all_gather)
         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "libnccl is missing required symbols");
@@ -534,6 +558,39 @@ extern "C" int tgpu_comm_destroy(tgpu_ctx* ctx)
     return tg_comm_destroy_internal(ctx);
 }
 
+extern "C" int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[2 * TGPU_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !handles_out || bytes == 0) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == TGPU_IPC_HANDLE_BYTES, "IPC handle size");
+    for (int k = 0; k < 2; k++) {
+        if (ctx->arena_local[k]) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "arenas already created");
+        TG_CUDA(ctx, cudaMalloc(&ctx->arena_local[k], bytes));   // plain cudaMalloc: pool memory cannot be exported
+        cudaIpcMemHandle_t h;
+        TG_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->arena_local[k]));
+        memcpy(handles_out + k * TGPU_IPC_HANDLE_BYTES, &h, TGPU_IPC_HANDLE_BYTES);
+    }
+    ctx->arena_bytes = bytes;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles)
+{
+    if (!ctx || !all_handles) return TGPU_ERR_INVALID_ARGUMENT;
+    if (!ctx->arena_local[0]) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "tgpu_comm_arena_create has not been called");
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int k = 0; k < 2; k++) {
+        ctx->arena_peer[k].assign(ctx->world, nullptr);
+        for (int r = 0; r < ctx->world; r++) {
+            if (r == ctx->rank) { ctx->arena_peer[k][r] = ctx->arena_local[k]; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + ((size_t)r * 2 + k) * TGPU_IPC_HANDLE_BYTES, TGPU_IPC_HANDLE_BYTES);
+            TG_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->arena_peer[k][r], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    return TGPU_OK;
+}
+
 extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out)
 {
     PartitionOp* p = dynamic_cast<PartitionOp*>(partitioner);
@@ -613,9 +670,31 @@ extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, co
         lanes.push_back(Lane{in.cols[c].elem_size(), in.cols[c].data, DevBuf(), nullptr, c, false});
         if (any_nulls[c]) lanes.push_back(Lane{0, in.cols[c].validity, DevBuf(), nullptr, c, true});
     }
+    // Peer-memory path: every rank can compute every destination's arena layout from the all-gathered count matrix
+    // (lane regions of total_recv(dst) x elem bytes, 256-byte aligned, in lane order), so the scatter kernel can store each
+    // row directly at its final address in the destination GPU's arena.
+    std::vector<long long> total_recv_of(W, 0);
+    for (int d = 0; d < W; d++)
+        for (int r = 0; r < W; r++) total_recv_of[d] += matrix[(size_t)r * V + d];
+    auto region_off = [&](int d, size_t lane) {
+        size_t off = 0;
+        for (size_t l = 0; l < lane; l++) off += (((size_t)total_recv_of[d] * (lanes[l].elem ? lanes[l].elem : 1)) + 255) & ~(size_t)255;
+        return off;
+    };
+    bool p2p = !ctx->arena_peer[0].empty() && !getenv("TGPU_EXCHANGE_NCCL");
+    for (int d = 0; d < W && p2p; d++) p2p = region_off(d, lanes.size()) <= ctx->arena_bytes;
+    const int arena = (int)(ctx->arena_epoch & 1);
     std::vector<char*> h_dst(lanes.size() * W);
     for (size_t l = 0; l < lanes.size(); l++) {
         int es = lanes[l].elem ? lanes[l].elem : 1;
+        if (p2p) {
+            for (int d = 0; d < W; d++) {
+                long long before = 0;   // rows of lower-ranked senders come first in the destination
+                for (int r = 0; r < ctx->rank; r++) before += matrix[(size_t)r * V + d];
+                h_dst[l * W + d] = (char*)ctx->arena_peer[arena][d] + region_off(d, l) + (size_t)before * es;
+            }
+            continue;
+        }
         TG_TRY(lanes[l].send.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * es));
         lanes[l].recv = std::make_shared<DevBuf>();
         TG_TRY(lanes[l].recv->alloc(ctx, (size_t)std::max<long long>(total_recv, 1) * es));
@@ -636,6 +715,45 @@ extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, co
         TG_LAUNCH(ctx, xchg_scatter_kernel, grid, XT, 0, pids.as<uint8_t>(), n, chunk, W, block_off.as<long long>(), xc);
     }
     mark("scatter");
+    if (p2p) {
+        // the rows are already in the destination arenas; a 1-element all-reduce on the stream is the barrier that tells
+        // every rank that all its senders' scatter kernels have completed
+        DevBuf token;
+        TG_TRY(token.alloc(ctx, 16));
+        TG_CUDA(ctx, cudaMemsetAsync(token.p, 0, 16, ctx->stream));
+        TG_NCCL(ctx, g_nccl.all_reduce(token.p, (char*)token.p + 8, 1, NCCL_INT64, 0 /* ncclSum */, ctx->comm, ctx->stream));
+        mark("p2p scatter + barrier");
+        ctx->arena_epoch++;
+        DevPage outp;
+        outp.rows = total_recv;
+        outp.cols.resize(C);
+        for (size_t l = 0; l < lanes.size(); l++) {
+            DevColumn& dst = outp.cols[lanes[l].col];
+            char* region = (char*)ctx->arena_local[arena] + region_off(ctx->rank, l);
+            if (!lanes[l].nulls) {
+                dst.type = in.cols[lanes[l].col].type;
+                dst.length = total_recv;
+                dst.data = region;     // aliases the arena: valid until the second-next exchange on this context
+            }
+            else if (total_recv > 0) {
+                tgpu_column bytemap_col;
+                memset(&bytemap_col, 0, sizeof(bytemap_col));
+                bytemap_col.type = TGPU_INT8;
+                bytemap_col.flags = TGPU_COL_NULLS_BYTEMAP;
+                bytemap_col.length = total_recv;
+                bytemap_col.data = region;
+                bytemap_col.validity = (const uint8_t*)region;
+                DevColumn packed;
+                TG_TRY(tg_ingest_column(ctx, &bytemap_col, true, &packed));
+                dst.own_validity = packed.own_validity;
+                dst.validity = packed.validity;
+            }
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        OwnedPage* po = tg_make_owned_page(std::move(outp));
+        *out = &po->hdr;
+        return TGPU_OK;
+    }
     // 4. all-to-all with explicit counts: one NCCL group for every column
     TG_NCCL(ctx, g_nccl.group_start());
     for (size_t l = 0; l < lanes.size(); l++) {
