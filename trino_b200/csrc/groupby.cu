@@ -619,6 +619,250 @@ __global__ void relayout_state_kernel(const unsigned long long* __restrict__ old
     }
 }
 
+
+// =====================================================================================================
+// path G, fused form (packed integer keys): ONE pass per page.  A row finds or inserts its key slot, lowers the
+// slot's first-row stamp (global row number) and applies its accumulators with L2 atomics on state indexed BY SLOT —
+// no group-id array, no flag/scan/assign passes.  Dense first-seen ids are only needed when rows are emitted: finish()
+// compacts the used slots, sorts them by first-row stamp and gathers the state into id order.
+// Rows that cannot claim a slot because the table reached its fill limit are appended to a deferred list and replayed
+// after the table has grown (their accumulators are untouched, so nothing is counted twice).
+// =====================================================================================================
+// Slot records are AoS: {key, first-row stamp, accumulator words...} padded to a power-of-two number of 8-byte words (W),
+// so one row touches ONE 32/64/128-byte line for its key, stamp and every accumulator (measured with SoA state: 4-5
+// scattered lines per row, 37 ms per 150 M rows with 10 M groups — DRAM read-modify-write bound).
+__device__ __forceinline__ unsigned long long* gf_rec(unsigned long long* base, int64_t s, int W) { return base + (size_t)s * W; }
+
+__global__ void gf_init_kernel(unsigned long long* __restrict__ recs, int64_t cap, int W, AggPlan plan)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < cap + 2; i += stride) {
+        unsigned long long* r = gf_rec(recs, i, W);
+        r[0] = EMPTY_KEY;
+        r[1] = (unsigned long long)NO_ROW;
+        for (int a = 0; a < plan.num_accs; a++) r[2 + a] = acc_init(plan.accs[a].kind);
+    }
+}
+
+// Accumulator words inside a fused-G record differ from the canonical (path S / output) meaning in two places, both to
+// turn read-modify-write atomics into fire-and-forget reductions and to touch fewer words per row:
+//   ACC_NONNULL      holds the number of NULL inputs (usually never incremented); non-null = ROWS(same mask) - that
+//   ACC_SUM_I64_LO/HI hold L = sum of the low 32-bit halves and H = sum of (v >> 32): value = H * 2^32 + L, no carry
+//                    hand-off between the two words, so both are plain RED.ADD
+// gf_gather_kernel converts back when the state is laid out in group-id order.
+__device__ __forceinline__ void gf_accumulate(const AggPlan& plan, const DColumns& cols, int64_t row, unsigned long long* __restrict__ acc)
+{
+    int last_src = -2;
+    Fetched v;
+    v.bits = 0; v.is_null = false;
+    for (int a = 0; a < plan.num_accs; a++) {
+        const AccDesc& d = plan.accs[a];
+        if (d.kind == ACC_SUM_I64_HI) continue;
+        if (!mask_selected(plan, d.mask, cols, row, nullptr, 0, 0)) continue;
+        if (d.src >= 0 && d.src != last_src) { v = fetch_src(plan.srcs[d.src], cols, row, nullptr, 0, 0); last_src = d.src; }
+        unsigned long long* p = acc + a;
+        if (d.kind == ACC_NONNULL) {
+            if (v.is_null) atomicAdd(p, 1ULL);
+            continue;
+        }
+        if (d.kind != ACC_ROWS && v.is_null) continue;
+        switch (d.kind) {
+            case ACC_ROWS: atomicAdd(p, 1ULL); break;
+            case ACC_SUM_F64: atomicAdd((double*)p, __longlong_as_double(v.bits)); break;
+            case ACC_SUM_F64_FROM_I64: atomicAdd((double*)p, (double)v.bits); break;
+            case ACC_SUM_I64_LO:
+                atomicAdd(p, (unsigned long long)v.bits & 0xFFFFFFFFULL);
+                atomicAdd(p + 1, (unsigned long long)(v.bits >> 32));
+                break;
+            case ACC_MIN_F64: atomicMin(p, f64_order_key(v.bits)); break;
+            case ACC_MAX_F64: atomicMax(p, f64_order_key(v.bits)); break;
+            case ACC_MIN_I64: atomicMin(p, i64_order_key(v.bits)); break;
+            case ACC_MAX_I64: atomicMax(p, i64_order_key(v.bits)); break;
+            default: break;
+        }
+    }
+}
+
+// canonical accumulator words -> fused-G record words (S -> G migration)
+__device__ __forceinline__ void gf_encode(const AggPlan& plan, unsigned long long* acc)
+{
+    for (int a = 0; a < plan.num_accs; a++) {
+        const AccDesc& d = plan.accs[a];
+        if (d.kind == ACC_NONNULL) {
+            for (int r = 0; r < plan.num_accs; r++)
+                if (plan.accs[r].kind == ACC_ROWS && plan.accs[r].mask == d.mask) acc[a] = acc[r] - acc[a];
+        }
+        else if (d.kind == ACC_SUM_I64_LO) {
+            unsigned long long lo = acc[a], hi = acc[a + 1];
+            acc[a] = lo & 0xFFFFFFFFULL;
+            acc[a + 1] = (hi << 32) | (lo >> 32);
+        }
+    }
+}
+
+// fused-G record words -> canonical accumulator words
+__device__ __forceinline__ void gf_decode(const AggPlan& plan, unsigned long long* acc)
+{
+    for (int a = 0; a < plan.num_accs; a++) {
+        const AccDesc& d = plan.accs[a];
+        if (d.kind == ACC_NONNULL) {
+            for (int r = 0; r < plan.num_accs; r++)
+                if (plan.accs[r].kind == ACC_ROWS && plan.accs[r].mask == d.mask) acc[a] = acc[r] - acc[a];
+        }
+        else if (d.kind == ACC_SUM_I64_LO) {
+            unsigned long long L = acc[a];
+            long long H = (long long)acc[a + 1];
+            unsigned long long lo = L + ((unsigned long long)H << 32);
+            long long hi = (H >> 32) + (lo < L ? 1 : 0);
+            acc[a] = lo;
+            acc[a + 1] = (unsigned long long)hi;
+        }
+    }
+}
+
+// `rows` == nullptr: rows [0, n) of the page; else the deferred row list
+__global__ void __launch_bounds__(256) gf_page_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ rows, long long page_base,
+                                                     unsigned long long* __restrict__ recs, int64_t cap, int W, int* __restrict__ tickets, int budget,
+                                                     int* __restrict__ deferred)
+{
+    const unsigned long long mask = (unsigned long long)cap - 1;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int64_t row = rows ? rows[i] : i;
+        unsigned long long pk = 0;
+        int sp = pack_key(plan, cols, row, nullptr, 0, 0, &pk);
+        int64_t s = -1;
+        if (sp >= 0) s = cap + sp;
+        else {
+            unsigned long long pos = murmur3_mix(pk) & mask;
+            bool have_ticket = false;
+            while (true) {
+                unsigned long long* kp = gf_rec(recs, (int64_t)pos, W);
+                // (measured: probing with an atomic "load" instead, to keep the line at its home L2 slice for the reductions
+                //  that follow, was 13 % slower)
+                unsigned long long cur = *((volatile unsigned long long*)kp);
+                if (cur == EMPTY_KEY) {
+                    if (!have_ticket) {
+                        if (atomicAdd(tickets, 1) >= budget) { atomicSub(tickets, 1); break; }
+                        have_ticket = true;
+                    }
+                    cur = atomicCAS(kp, EMPTY_KEY, pk);
+                    if (cur == EMPTY_KEY) { s = (int64_t)pos; have_ticket = false; break; }
+                }
+                if (cur == pk) { s = (int64_t)pos; break; }
+                pos = (pos + 1) & mask;
+            }
+            if (have_ticket) atomicSub(tickets, 1);
+        }
+        if (s < 0) { deferred[atomicAdd(tickets + 1, 1)] = (int)row; continue; }
+        unsigned long long* r = gf_rec(recs, s, W);
+        long long stamp = page_base + row;
+        if (*((volatile long long*)(r + 1)) > stamp) {
+            long long old = atomicMin((long long*)(r + 1), stamp);
+            if (old == NO_ROW && s >= cap) atomicAdd(tickets + 2, 1);   // a special (NULL / sentinel key) group came to life
+        }
+        gf_accumulate(plan, cols, row, r + 2);
+    }
+}
+
+// table growth: move every used record into the bigger table
+__global__ void gf_rehash_kernel(const unsigned long long* __restrict__ orecs, int64_t ocap, unsigned long long* __restrict__ recs, int64_t cap, int W, int A)
+{
+    const unsigned long long mask = (unsigned long long)cap - 1;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < ocap + 2; i += stride) {
+        const unsigned long long* o = orecs + (size_t)i * W;
+        int64_t dst;
+        if (i >= ocap) dst = cap + (i - ocap);      // special records keep their place after the table
+        else {
+            unsigned long long k = o[0];
+            if (k == EMPTY_KEY) continue;
+            unsigned long long pos = murmur3_mix(k) & mask;
+            while (atomicCAS(gf_rec(recs, (int64_t)pos, W), EMPTY_KEY, k) != EMPTY_KEY) pos = (pos + 1) & mask;
+            dst = (int64_t)pos;
+        }
+        unsigned long long* r = gf_rec(recs, dst, W);
+        for (int w = 1; w < 2 + A; w++) r[w] = o[w];
+    }
+}
+
+// S -> fused-G migration: groups numbered so far keep their order by getting stamps below every real row
+__global__ void gf_migrate_kernel(AggState st, AggPlan plan, unsigned long long* __restrict__ recs, int64_t cap, int W)
+{
+    const unsigned long long mask = (unsigned long long)cap - 1;
+    int count = st.count[0];
+    for (int g = threadIdx.x; g < count; g += blockDim.x) {
+        int64_t dst;
+        if (g == st.count[1]) dst = cap;
+        else if (g == st.count[2]) dst = cap + 1;
+        else {
+            unsigned long long k = st.keys[g];
+            unsigned long long pos = murmur3_mix(k) & mask;
+            while (atomicCAS(gf_rec(recs, (int64_t)pos, W), EMPTY_KEY, k) != EMPTY_KEY) pos = (pos + 1) & mask;
+            dst = (int64_t)pos;
+        }
+        unsigned long long* r = gf_rec(recs, dst, W);
+        r[1] = (unsigned long long)((long long)g - (long long)count - 1);   // negative, ascending with the existing id
+        unsigned long long w[MAX_ACCS];
+        for (int a = 0; a < plan.num_accs; a++) w[a] = st.acc[(size_t)a * st.cap + g];
+        gf_encode(plan, w);
+        for (int a = 0; a < plan.num_accs; a++) r[2 + a] = w[a];
+    }
+}
+
+__global__ void gf_used_flags_kernel(const unsigned long long* __restrict__ recs, int64_t n, int W, unsigned char* __restrict__ flags)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) flags[i] = (long long)recs[(size_t)i * W + 1] != NO_ROW ? 1 : 0;
+}
+
+__global__ void gf_sort_keys_kernel(const unsigned long long* __restrict__ recs, int W, const int* __restrict__ slots, int64_t G, unsigned long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < G; i += stride) out[i] = recs[(size_t)slots[i] * W + 1] ^ 0x8000000000000000ULL;   // signed order -> unsigned order
+}
+
+// gather the slot records into group-id order (the SoA layout build_output reads)
+__global__ void gf_gather_kernel(AggPlan plan, const int* __restrict__ ordered_slots, int64_t G, const unsigned long long* __restrict__ recs, int64_t cap, int W,
+                                 AggState st)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; g < G; g += stride) {
+        int64_t s = ordered_slots[g];
+        const unsigned long long* r = recs + (size_t)s * W;
+        unsigned long long w[MAX_ACCS];
+        for (int a = 0; a < plan.num_accs; a++) w[a] = r[2 + a];
+        gf_decode(plan, w);
+        for (int a = 0; a < plan.num_accs; a++) st.acc[(size_t)a * st.cap + g] = w[a];
+        if (plan.num_keys == 1) {
+            bool isnull = s == cap;
+            unsigned long long k = s == cap + 1 ? EMPTY_KEY : (s < cap ? r[0] : 0ULL);
+            st.keyvals[g] = (long long)k;
+            st.keynull[g] = isnull ? 1 : 0;
+        }
+        else {
+            unsigned long long pk = r[0];
+            int shift = 0;
+            for (int k = 0; k < plan.num_keys; k++) {
+                int bits = plan.key_bits[k];
+                unsigned long long field = (pk >> shift) & ((2ULL << bits) - 1);
+                bool isnull = field & 1ULL;
+                long long v = (long long)(field >> 1);
+                if (bits < 64 && (v >> (bits - 1)) & 1) v |= ~((1LL << bits) - 1);   // sign-extend
+                st.keyvals[(size_t)k * st.cap + g] = isnull ? 0 : v;
+                st.keynull[(size_t)k * st.cap + g] = isnull ? 1 : 0;
+                shift += bits + 1;
+            }
+        }
+    }
+}
+
 // =====================================================================================================
 // output
 // =====================================================================================================
@@ -928,6 +1172,10 @@ struct AggOp : tgpu_op {
     // path G
     DevBuf g_table, g_special;
     int64_t g_slots = 0;
+    // path G, fused form
+    bool fused_general = false;
+    DevBuf f_recs;
+    int64_t f_cap = 0, f_used = 0, f_specials = 0, rows_seen = 0;
 
     bool finishing = false, finished = false, flushing = false;
     std::vector<OwnedPage*> pending;
@@ -1290,6 +1538,7 @@ struct AggOp : tgpu_op {
             plan.has_pre = 0;
             has_pre = false;
         }
+        if (fused_ok() && !getenv("TGPU_AGG_MULTIPASS")) return gf_start();
         TG_TRY(g_special.alloc(ctx, sizeof(GSpecial)));
         GSpecial init;
         init.gid[0] = init.gid[1] = -1;
@@ -1367,11 +1616,142 @@ struct AggOp : tgpu_op {
 
     int run_general(const DevPage& in, const DColumns& cols)
     {
+        if (fused_general) return run_fused_general(in, cols);
         DevBuf gids;
         TG_TRY(gids.alloc(ctx, (size_t)in.rows * 4));
         TG_TRY(run_general_ids(in, cols, gids.as<int>()));
         if (plan.num_accs > 0)
             TG_LAUNCH(ctx, g_accumulate_kernel, tg_grid(ctx, in.rows, 256, 8), 256, 0, plan, cols, in.rows, gids.as<int>(), state());
+        return TGPU_OK;
+    }
+
+
+    // ---- path G, fused form -------------------------------------------------------------------------
+    bool fused_ok() const
+    {
+        if (gids_only || plan.key_hashed) return false;
+        for (int k = 0; k < plan.num_keys; k++)
+            if (plan.key_is_double[k]) return false;   // first-seen raw value (-0.0 vs +0.0) needs the representative row
+        return true;
+    }
+
+    int gf_words() const
+    {
+        int need = 2 + (plan.num_accs > 0 ? plan.num_accs : 0);
+        int w = 4;
+        while (w < need) w <<= 1;
+        return w;
+    }
+
+    int gf_alloc(int64_t cap, DevBuf* recs)
+    {
+        int W = gf_words();
+        TG_TRY(recs->alloc(ctx, (size_t)(cap + 2) * W * 8));
+        TG_LAUNCH(ctx, gf_init_kernel, tg_grid(ctx, cap + 2, 1024, 8), 256, 0, recs->as<unsigned long long>(), cap, W, plan);
+        return TGPU_OK;
+    }
+
+    int gf_start()
+    {
+        int64_t want = expected_groups > 0 ? expected_groups : 1024;
+        int64_t cap = 1 << 16;
+        while (cap * 3 / 4 < want + group_count) cap <<= 1;
+        if (cap > (1LL << 30)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+        TG_TRY(gf_alloc(cap, &f_recs));
+        f_cap = cap;
+        f_used = 0;
+        if (group_count > 0) {
+            TG_LAUNCH(ctx, gf_migrate_kernel, 1, 256, 0, state(), plan, f_recs.as<unsigned long long>(), f_cap, gf_words());
+            f_used = group_count;   // migrated specials counted here too: they only ever under-use the budget
+        }
+        fused_general = true;
+        return TGPU_OK;
+    }
+
+    int gf_grow()
+    {
+        int64_t ncap = f_cap * 4;
+        if (ncap > (1LL << 30)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
+        DevBuf nr;
+        TG_TRY(gf_alloc(ncap, &nr));
+        TG_LAUNCH(ctx, gf_rehash_kernel, tg_grid(ctx, f_cap + 2, 1024, 8), 256, 0, f_recs.as<unsigned long long>(), f_cap, nr.as<unsigned long long>(), ncap, gf_words(),
+                  plan.num_accs);
+        f_recs = std::move(nr);
+        f_cap = ncap;
+        return TGPU_OK;
+    }
+
+    int run_fused_general(const DevPage& in, const DColumns& cols)
+    {
+        int64_t n = in.rows;
+        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+        DevBuf deferred;
+        TG_TRY(deferred.alloc(ctx, (size_t)n * 4));
+        int* d_tickets = (int*)(ctx->d_scratch + 20);    // [0] slots claimed by this launch, [1] deferred rows, [2] special groups born
+        const int* rows = nullptr;
+        int64_t todo = n;
+        DevBuf replay;
+        while (true) {
+            int64_t budget = f_cap * 3 / 4 - f_used;
+            TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 16, ctx->stream));
+            TG_TIMED_BEGIN(ctx);
+            TG_LAUNCH(ctx, gf_page_kernel, tg_grid(ctx, todo, 256, 8), 256, 0, plan, cols, todo, rows, (long long)rows_seen, f_recs.as<unsigned long long>(), f_cap,
+                      gf_words(), d_tickets, (int)std::min<int64_t>(std::max<int64_t>(budget, 0), INT32_MAX), deferred.as<int>());
+            TG_TIMED_END(ctx);
+            int32_t counters[4] = {0, 0, 0, 0};
+            TG_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_tickets, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            memcpy(counters, ctx->h_scratch, 16);
+            f_used += counters[0];
+            f_specials += counters[2];
+            int64_t left = counters[1];
+            if (left == 0) break;
+            // BigintGroupByHash.tryRehash :239-290 (here x4), then replay the rows that found the table full
+            TG_TRY(gf_grow());
+            replay = std::move(deferred);
+            TG_TRY(deferred.alloc(ctx, (size_t)left * 4));
+            rows = replay.as<int>();
+            todo = left;
+        }
+        rows_seen += n;
+        group_count = f_used + f_specials;
+        return TGPU_OK;
+    }
+
+    // compact used slots, order them by first-row stamp, gather the state into group-id order
+    int gf_finalize()
+    {
+        int64_t total = f_cap + 2;
+        DevBuf flags, slots, tmp;
+        TG_TRY(flags.alloc(ctx, (size_t)total));
+        TG_TRY(slots.alloc(ctx, (size_t)total * 4));
+        TG_LAUNCH(ctx, gf_used_flags_kernel, tg_grid(ctx, total, 1024, 8), 256, 0, f_recs.as<unsigned long long>(), total, gf_words(), flags.as<unsigned char>());
+        long long* d_count = (long long*)(ctx->d_scratch + 22);
+        size_t tmp_bytes = 0;
+        cub::CountingInputIterator<int> iota(0);
+        cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<unsigned char>(), slots.as<int>(), d_count, (int)total, ctx->stream);
+        TG_TRY(tmp.alloc(ctx, tmp_bytes));
+        TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<unsigned char>(), slots.as<int>(), d_count, (int)total, ctx->stream));
+        int64_t G = 0;
+        TG_TRY(tg_read_i64(ctx, d_count, &G));
+        group_count = G;
+        if (G == 0) return TGPU_OK;
+        DevBuf k_in, k_out, s_out, tmp2;
+        TG_TRY(k_in.alloc(ctx, (size_t)G * 8));
+        TG_TRY(k_out.alloc(ctx, (size_t)G * 8));
+        TG_TRY(s_out.alloc(ctx, (size_t)G * 4));
+        TG_LAUNCH(ctx, gf_sort_keys_kernel, tg_grid(ctx, G, 1024, 8), 256, 0, f_recs.as<unsigned long long>(), gf_words(), slots.as<int>(), G, k_in.as<unsigned long long>());
+        tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.as<unsigned long long>(), k_out.as<unsigned long long>(), slots.as<int>(), s_out.as<int>(), (int)G, 0, 64, ctx->stream);
+        TG_TRY(tmp2.alloc(ctx, tmp_bytes));
+        TG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp2.p, tmp_bytes, k_in.as<unsigned long long>(), k_out.as<unsigned long long>(), slots.as<int>(), s_out.as<int>(), (int)G, 0, 64, ctx->stream));
+        if (G > st_cap) {
+            int64_t keep = group_count;
+            group_count = 0;            // nothing to carry over: the dense arrays are rebuilt from the slots
+            TG_TRY(alloc_state(G));
+            group_count = keep;
+        }
+        TG_LAUNCH(ctx, gf_gather_kernel, tg_grid(ctx, G, 256, 8), 256, 0, plan, s_out.as<int>(), G, f_recs.as<unsigned long long>(), f_cap, gf_words(), state());
         return TGPU_OK;
     }
 
@@ -1446,13 +1826,14 @@ struct AggOp : tgpu_op {
     {
         int64_t A = plan.num_accs > 0 ? plan.num_accs : 1;
         int64_t b = group_count * (8 + 8 * A + 9 * (int64_t)plan.num_keys);
-        if (use_general) b += (int64_t)g_table.bytes;
+        if (use_general) b += (int64_t)g_table.bytes + (int64_t)f_recs.bytes;
         return planned ? b : 0;
     }
 
     int build_output(OwnedPage** out)
     {
         *out = nullptr;
+        if (planned && fused_general) TG_TRY(gf_finalize());
         if (!planned || group_count == 0) return TGPU_OK;
         int64_t G = group_count;
         DevPage outp;
@@ -1558,6 +1939,9 @@ struct AggOp : tgpu_op {
         planned = true;
         g_slots = 0;
         g_table.release();
+        fused_general = false;
+        f_recs.release();
+        f_cap = f_used = f_specials = rows_seen = 0;
         TG_TRY(init_state());
         if (use_general) TG_TRY(switch_to_general());
         return TGPU_OK;
