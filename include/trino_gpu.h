@@ -234,6 +234,9 @@ int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op** out);
  * the generated source (or the compiler log on failure) */
 int tgpu_jit_selftest_agg(const tgpu_agg_spec* spec, const int32_t* channel_types, int32_t num_channels, uint32_t nullable_mask,
                           int64_t* cubin_bytes, char* source_out, int64_t source_cap);
+/* Same for the FilterAndProject kernels generated from `program` (tg_fp_filter_jit / tg_fp_project_jit). */
+int tgpu_jit_selftest_filter_project(const tgpu_expr_program* program, const int32_t* channel_types, int32_t num_channels, uint32_t nullable_mask,
+                                     int64_t* cubin_bytes, char* source_out, int64_t source_cap);
 /* GroupByHash.getGroupCount() */
 int tgpu_agg_group_count(tgpu_op* op, int64_t* out);
 

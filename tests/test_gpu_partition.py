@@ -67,3 +67,19 @@ def test_single_partition_and_dictionary_keys(ctx):
     want, _ = oracle_partition(d, [0], 4, None, 4, -1, False, False)
     assert gpu_partition(ctx, op, d) == want
     op.close()
+
+
+@pytest.mark.parametrize("P", [2, 8, 37, 64, 100])
+def test_fixed_width_pages_take_the_multisplit_path(ctx, P):
+    """Fixed-width pages without replicated rows are split by one stable histogram/scatter pass (<= 64 partitions) or by the
+    sort path (100): identical per-partition rows and order either way, NULLs of value columns preserved."""
+    rng = np.random.default_rng(P)
+    n = 300_000
+    page = Page(Block.bigint(rng.integers(0, 10**7, n), rng.random(n) < 0.1), Block.double(rng.normal(size=n), rng.random(n) < 0.3),
+                Block.integer(rng.integers(-5, 5, n)), Block.tinyint(rng.integers(0, 3, n), rng.random(n) < 0.5), Block.smallint(rng.integers(0, 999, n)))
+    b2p = [int(x) for x in rng.integers(0, P, 4 * P)]
+    for keys, buckets, mapping in (([0], P, None), ([0, 2], 4 * P, b2p)):
+        op = ops.PartitionedOutputOperatorFactory(ctx, keys, buckets, mapping, -1, False).create_operator()
+        want, _ = oracle_partition(page, keys, buckets, mapping, P, -1, False, False)
+        assert gpu_partition(ctx, op, page) == want
+        op.close()

@@ -50,3 +50,18 @@ def test_unfused_plan_compiles_too():
     if st == abi.ERR_NOT_SUPPORTED:
         pytest.skip("NVRTC not installed")
     assert st == 0, src
+
+
+def test_filter_project_kernels_compile():
+    lib = abi.load_library()
+    prog = q1_program()
+    types = (C.c_int32 * 7)(abi.INT32, abi.INT8, abi.INT8, abi.FLOAT64, abi.FLOAT64, abi.FLOAT64, abi.FLOAT64)
+    n = C.c_int64()
+    buf = C.create_string_buffer(1 << 16)
+    st = lib.tgpu_jit_selftest_filter_project(C.byref(prog.struct), types, 7, 0b0010000, C.byref(n), buf, len(buf))
+    src = buf.value.decode()
+    if st == abi.ERR_NOT_SUPPORTED:
+        pytest.skip("NVRTC not installed: " + src)
+    assert st == 0, src
+    assert "tg_fp_filter_jit" in src and "tg_fp_project_jit" in src
+    assert "tg_valid(cols.cols[4].validity" in src and "tg_valid(cols.cols[5].validity" not in src

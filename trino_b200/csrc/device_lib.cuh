@@ -62,6 +62,15 @@ struct SmallOut {
     unsigned int* err;
 };
 
+// computed projection outputs of the filter/project kernels
+struct OutCols {
+    int32_t count;
+    int32_t temp[TGD_MAX_CHANNELS];
+    int32_t vtype[TGD_MAX_CHANNELS];
+    void* data[TGD_MAX_CHANNELS];
+    uint8_t* nullmap[TGD_MAX_CHANNELS];   // 1 byte per row, 1 = NULL
+};
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ bool tg_valid(const uint8_t* validity, int64_t i)

@@ -5,8 +5,10 @@
 // (ProjectSelectedPositions.processBatch :302-336); FilterAndProjectOperator
 // (M/operator/FilterAndProjectOperator.java:60-95) wraps it.  Output rows keep input order.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "expr.cuh"
+#include "jit.cuh"
 
 namespace tg {
 
@@ -98,14 +100,6 @@ __global__ void __launch_bounds__(FP_THREADS) fp_filter_kernel(const DProgram* _
     if (err) atomicOr(err_out, err);
 }
 
-struct OutCols {
-    int32_t count;
-    int32_t temp[TGPU_MAX_CHANNELS];
-    int32_t vtype[TGPU_MAX_CHANNELS];
-    void* data[TGPU_MAX_CHANNELS];
-    uint8_t* nullmap[TGPU_MAX_CHANNELS];   // 1 byte per row, 1 = NULL
-};
-
 // projection pass: output row j <- input row sel[j] (sel == nullptr: identity)
 __global__ void __launch_bounds__(FP_THREADS) fp_project_kernel(const DProgram* __restrict__ prog, DColumns cols, const int32_t* __restrict__ sel, int64_t m,
                                                                OutCols out, unsigned int* __restrict__ err_out, unsigned int* __restrict__ any_null)
@@ -133,9 +127,94 @@ __global__ void __launch_bounds__(FP_THREADS) fp_project_kernel(const DProgram* 
     if (nulls_seen) atomicOr(any_null, nulls_seen);
 }
 
-struct IotaIt {
-    __host__ __device__ int32_t operator[](int64_t i) const { return (int32_t)i; }
-};
+
+// ---- NVRTC specialisation of the two PageProcessor kernels ----------------------------------------------------------
+static void fp_appendf(std::string& s, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    s += buf;
+}
+
+static std::string fp_operand(const DOperand& o)
+{
+    char buf[128];
+    switch (o.kind) {
+        case TGPU_OPND_COLUMN: snprintf(buf, sizeof(buf), "Value{c%d, c%dn}", o.index, o.index); break;
+        case TGPU_OPND_TEMP: snprintf(buf, sizeof(buf), "Value{t%d, tn%d}", o.index, o.index); break;
+        case TGPU_OPND_CONST: snprintf(buf, sizeof(buf), "Value{(long long)0x%llxULL, false}", (unsigned long long)o.imm); break;
+        default: snprintf(buf, sizeof(buf), "Value{0, true}"); break;
+    }
+    return buf;
+}
+
+static void fp_emit_insns(std::string& s, const DProgram& prog, int first, int last, const char* err)
+{
+    for (int i = first; i < last; i++) {
+        const DInsn& in = prog.insns[i];
+        if (in.op == TGPU_EX_IN) {
+            int li = (int)in.b.imm;
+            fp_appendf(s, "    { Value a = %s; bool hit = false;\n", fp_operand(in.a).c_str());
+            for (int k = 0; k < prog.in_count[li]; k++) {
+                unsigned long long c = (unsigned long long)prog.in_values[prog.in_offset[li] + k];
+                if (in.vtype == TGPU_V_DOUBLE) fp_appendf(s, "      hit |= __longlong_as_double(a.bits) == __longlong_as_double((long long)0x%llxULL);\n", c);
+                else fp_appendf(s, "      hit |= a.bits == (long long)0x%llxULL;\n", c);
+            }
+            fp_appendf(s, "      t%d = hit ? 1 : 0; tn%d = a.is_null; }\n", in.dst, in.dst);
+        }
+        else {
+            fp_appendf(s, "    { Value x = vm_apply(%d, %d, %s, %s, %s, %s); t%d = x.bits; tn%d = x.is_null; }\n", in.op, in.vtype, fp_operand(in.a).c_str(),
+                       fp_operand(in.b).c_str(), fp_operand(in.c).c_str(), err, in.dst, in.dst);
+        }
+    }
+}
+
+// straight-line typed code for one program over channels of the given element sizes
+static std::string gen_fp_source(const DProgram& prog, const int* elems, int num_channels, uint32_t nullable_mask)
+{
+    std::string s;
+    bool used[TGPU_MAX_CHANNELS] = {false};
+    for (int i = 0; i < prog.num_insns; i++) {
+        const DOperand* ops[3] = {&prog.insns[i].a, &prog.insns[i].b, &prog.insns[i].c};
+        for (auto* o : ops)
+            if (o->kind == TGPU_OPND_COLUMN) used[o->index] = true;
+    }
+    std::string loads, temps;
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) {
+        if (!used[c]) continue;
+        fp_appendf(loads, "    const long long c%d = tg_load_elem<%d>(cols.cols[%d].data, row);", c, elems[c], c);
+        if ((nullable_mask >> c) & 1) fp_appendf(loads, " const bool c%dn = !tg_valid(cols.cols[%d].validity, row);\n", c, c);
+        else fp_appendf(loads, " const bool c%dn = false;\n", c);
+    }
+    for (int t = 0; t < TGPU_MAX_TEMPS; t++) fp_appendf(temps, "    long long t%d = 0; bool tn%d = true;\n", t, t);
+    // filter kernel
+    s += "extern \"C\" __global__ void __launch_bounds__(256) tg_fp_filter_jit(DColumns cols, long long n, unsigned char* flags, unsigned int* err_out) {\n";
+    s += "  unsigned int err = 0;\n  long long stride = (long long)gridDim.x * blockDim.x;\n";
+    s += "  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {\n";
+    s += loads + temps;
+    fp_emit_insns(s, prog, 0, prog.num_filter_insns, "&err");
+    if (prog.filter_temp >= 0) fp_appendf(s, "    flags[row] = (!tn%d && t%d != 0) ? 1 : 0;\n", prog.filter_temp, prog.filter_temp);
+    else s += "    flags[row] = 1;\n";
+    s += "  }\n  if (err) atomicOr(err_out, err);\n}\n";
+    // projection kernel
+    s += "extern \"C\" __global__ void __launch_bounds__(256) tg_fp_project_jit(DColumns cols, const int* sel, long long m, OutCols out, unsigned int* err_out, unsigned int* any_null) {\n";
+    s += "  unsigned int err = 0, ignored = 0, nulls_seen = 0;\n  long long stride = (long long)gridDim.x * blockDim.x;\n";
+    s += "  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += stride) {\n";
+    s += "    const long long row = sel ? sel[j] : j;\n";
+    s += loads + temps;
+    fp_emit_insns(s, prog, 0, prog.num_filter_insns, "&ignored");
+    fp_emit_insns(s, prog, prog.num_filter_insns, prog.num_insns, "&err");
+    s += "    for (int c = 0; c < out.count; c++) {\n      long long v = 0; bool isn = true;\n      switch (out.temp[c]) {\n";
+    for (int t = 0; t < TGPU_MAX_TEMPS; t++) fp_appendf(s, "        case %d: v = t%d; isn = tn%d; break;\n", t, t, t);
+    s += "      }\n      if (isn) v = 0;\n";
+    s += "      if (out.vtype[c] == TGD_V_BOOLEAN) ((signed char*)out.data[c])[j] = (signed char)v; else ((long long*)out.data[c])[j] = v;\n";
+    s += "      out.nullmap[c][j] = isn ? 1 : 0;\n      if (isn) nulls_seen |= 1u << c;\n    }\n";
+    s += "  }\n  (void)ignored;\n  if (err) atomicOr(err_out, err);\n  if (nulls_seen) atomicOr(any_null, nulls_seen);\n}\n";
+    return s;
+}
 
 struct FilterProjectOp : tgpu_op {
     DProgram host_prog;
@@ -188,10 +267,17 @@ struct FilterProjectOp : tgpu_op {
             DevBuf flags, tmp;
             TG_TRY(flags.alloc(ctx, (size_t)n));
             TG_TRY(sel.alloc(ctx, (size_t)n * 4));
-            TG_LAUNCH(ctx, fp_filter_kernel, grid, FP_THREADS, 0, dp, cols, n, flags.as<uint8_t>(), d_err);
+            TG_TRY(jit_prepare(in));
+            if (jit_filter) {
+                long long n_arg = n;
+                unsigned char* f_arg = flags.as<unsigned char>();
+                void* params[4] = {&cols, &n_arg, &f_arg, &d_err};
+                TG_TRY(jit_launch(ctx, jit_filter, grid, FP_THREADS, 0, params));
+            }
+            else TG_LAUNCH(ctx, fp_filter_kernel, grid, FP_THREADS, 0, dp, cols, n, flags.as<uint8_t>(), d_err);
             long long* d_count = (long long*)(ctx->d_scratch + 4);
             size_t tmp_bytes = 0;
-            cub::CountingInputIterator<int32_t> iota(0);
+            thrust::counting_iterator<int32_t> iota(0);
             cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream);
             TG_TRY(tmp.alloc(ctx, tmp_bytes));
             TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream));
@@ -237,7 +323,13 @@ struct FilterProjectOp : tgpu_op {
         }
         if (oc.count > 0) {
             int pgrid = tg_grid(ctx, m, FP_THREADS, 8);
-            TG_LAUNCH(ctx, fp_project_kernel, pgrid, FP_THREADS, 0, dp, cols, d_sel, m, oc, d_err, d_anynull);
+            TG_TRY(jit_prepare(in));
+            if (jit_project) {
+                long long m_arg = m;
+                void* params[6] = {&cols, &d_sel, &m_arg, &oc, &d_err, &d_anynull};
+                TG_TRY(jit_launch(ctx, jit_project, pgrid, FP_THREADS, 0, params));
+            }
+            else TG_LAUNCH(ctx, fp_project_kernel, pgrid, FP_THREADS, 0, dp, cols, d_sel, m, oc, d_err, d_anynull);
             int64_t word = 0;
             TG_TRY(tg_read_i64(ctx, d_err, &word));
             TG_TRY(raise(word & 0xFFFFFFFFLL));
@@ -256,6 +348,30 @@ struct FilterProjectOp : tgpu_op {
     }
 
     int pack_nullmap(const uint8_t* nullmap, int64_t m, uint8_t* bitmap);
+
+    // kernels specialised for this program and this page's channel types / nullability (NVRTC, cached)
+    void* jit_filter = nullptr;
+    void* jit_project = nullptr;
+    std::string jit_key;
+    int jit_prepare(const DevPage& in)
+    {
+        if (!jit_available()) { jit_filter = jit_project = nullptr; return TGPU_OK; }
+        int elems[TGPU_MAX_CHANNELS] = {0};
+        uint32_t nullable = 0;
+        std::string key;
+        for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++) {
+            elems[c] = in.cols[c].elem_size();
+            if (in.cols[c].validity) nullable |= 1u << c;
+            key += (char)('0' + elems[c]);
+        }
+        key += ":" + std::to_string(nullable);
+        if (key == jit_key && jit_filter) return TGPU_OK;
+        std::string src = gen_fp_source(host_prog, elems, (int)in.cols.size(), nullable);
+        TG_TRY(jit_get_function(ctx, src, "tg_fp_filter_jit", &jit_filter));
+        TG_TRY(jit_get_function(ctx, src, "tg_fp_project_jit", &jit_project));
+        jit_key = key;
+        return TGPU_OK;
+    }
 
     int raise(int64_t errbits)
     {
@@ -315,5 +431,29 @@ extern "C" int tgpu_filter_project_create(tgpu_ctx* ctx, const tgpu_expr_program
     TG_CUDA(ctx, cudaMemcpyAsync(op->d_prog.p, &op->host_prog, sizeof(tg::DProgram), cudaMemcpyHostToDevice, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = op.release();
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_jit_selftest_filter_project(const tgpu_expr_program* program, const int32_t* channel_types, int32_t num_channels, uint32_t nullable_mask,
+                                                int64_t* cubin_bytes, char* source_out, int64_t source_cap)
+{
+    if (!program || !channel_types || !cubin_bytes) return TGPU_ERR_INVALID_ARGUMENT;
+    tgpu_ctx fake;
+    tg::DProgram prog;
+    int32_t max_channel = -1;
+    int st = tg::expr_compile(&fake, program, &prog, &max_channel);
+    if (st != TGPU_OK) return st;
+    int elems[TGPU_MAX_CHANNELS] = {0};
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) {
+        DevColumn col;
+        col.type = channel_types[c];
+        elems[c] = col.elem_size();
+    }
+    std::string src = gen_fp_source(prog, elems, num_channels, nullable_mask);
+    if (source_out && source_cap > 0) { strncpy(source_out, src.c_str(), (size_t)source_cap - 1); source_out[source_cap - 1] = 0; }
+    std::string cubin;
+    st = tg::jit_compile_cubin(&fake, src, &cubin);
+    if (st != TGPU_OK) { if (source_out && source_cap > 0) { strncpy(source_out, fake.err.c_str(), (size_t)source_cap - 1); source_out[source_cap - 1] = 0; } return st; }
+    *cubin_bytes = (int64_t)cubin.size();
     return TGPU_OK;
 }

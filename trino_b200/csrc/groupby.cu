@@ -25,6 +25,7 @@
 // Keys are packed exactly into one 64-bit word (single key of any fixed width, or several narrow keys with
 // one null bit each, <= 63 bits); other key shapes return NOT_SUPPORTED so the caller keeps the Java operator.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <map>
 
@@ -1728,7 +1729,7 @@ struct AggOp : tgpu_op {
         TG_LAUNCH(ctx, gf_used_flags_kernel, tg_grid(ctx, total, 1024, 8), 256, 0, f_recs.as<unsigned long long>(), total, gf_words(), flags.as<unsigned char>());
         long long* d_count = (long long*)(ctx->d_scratch + 22);
         size_t tmp_bytes = 0;
-        cub::CountingInputIterator<int> iota(0);
+        thrust::counting_iterator<int> iota(0);
         cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<unsigned char>(), slots.as<int>(), d_count, (int)total, ctx->stream);
         TG_TRY(tmp.alloc(ctx, tmp_bytes));
         TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<unsigned char>(), slots.as<int>(), d_count, (int)total, ctx->stream));

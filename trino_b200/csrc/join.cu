@@ -19,6 +19,7 @@
 // of (slot,row) pairs only when duplicates exist.  Slot placement (mix(key) & mask, linear probing) is not
 // observable, only key -> head is.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "rowkeys.cuh"
 
@@ -990,7 +991,7 @@ struct JoinProbeOp : tgpu_op {
             TG_LAUNCH(ctx, join_match_flags_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, jp->as<int>(), n, flags.as<uint8_t>());
             long long* d_count = (long long*)(ctx->d_scratch + 14);
             size_t tmp_bytes = 0;
-            cub::CountingInputIterator<int32_t> iota(0);
+            thrust::counting_iterator<int32_t> iota(0);
             cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream);
             TG_TRY(tmp.alloc(ctx, tmp_bytes));
             TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream));

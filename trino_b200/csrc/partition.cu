@@ -178,51 +178,107 @@ struct XchgCols {
     char* const* dst;             // device array [count][P] of destination base pointers (local send buffer or peer memory)
 };
 
-// pass C: stable scatter.  Rows keep their order inside a partition: rank = CTA offset + running offset of earlier tiles
-// + rows of earlier warps in the tile + rank inside the warp (__match_any_sync).
+// pass C: stable scatter, staged through shared memory.  A CTA walks its chunk in tiles of XTILE rows.  Per tile it ranks
+// every row inside its partition (warp __match_any_sync rank + scan over the tile's (iteration, warp) cells), lays the tile
+// out partition-contiguously in shared memory one column at a time, and copies each partition's run to its destination with
+// consecutive threads writing consecutive addresses: the stores that cross NVLink (peer arenas) are >= 128-byte contiguous
+// segments instead of one 8-byte store per row.  Rows keep their order inside a partition.
+constexpr int XR = 8;                 // rows per thread per tile
+constexpr int XTILE = XT * XR;        // 2048 rows
+constexpr int XCELLS = XR * (XT / 32);
+static_assert(XCELLS == 64, "the cell scan assumes two cells per lane");
+
 __global__ void __launch_bounds__(XT) xchg_scatter_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t chunk, int32_t P,
                                                           const long long* __restrict__ block_off, XchgCols cols)
 {
+    __shared__ long long stage[XTILE];
+    __shared__ uint8_t spid[XTILE];
+    __shared__ __align__(16) unsigned short wcount[XCELLS][XMAXP];
     __shared__ long long running[XMAXP];
-    __shared__ unsigned short wcount[XT / 32][XMAXP];
+    __shared__ int tile_cnt[XMAXP];
+    __shared__ int tile_off[XMAXP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = XT / 32;
     for (int i = threadIdx.x; i < P; i += XT) running[i] = block_off[(size_t)blockIdx.x * P + i];
-    int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
-    for (int64_t tile = begin; tile < end; tile += XT) {
-        for (int i = threadIdx.x; i < (XT / 32) * XMAXP; i += XT) (&wcount[0][0])[i] = 0;
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
+    for (int64_t tile = begin; tile < end; tile += XTILE) {
+        const int tile_rows = (int)min((int64_t)XTILE, end - tile);
+        for (int i = threadIdx.x; i < XCELLS * XMAXP * 2 / 16; i += XT) ((uint4*)&wcount[0][0])[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
-        int64_t row = tile + threadIdx.x;
-        bool live = row < end;
-        int pid = live ? pids[row] : 0;
-        unsigned int peers = __match_any_sync(0xffffffffu, live ? pid : -1 - lane);
-        int rank = __popc(peers & ((1u << lane) - 1));
-        if (live && rank == 0) wcount[warp][pid] = (unsigned short)__popc(peers);
-        __syncthreads();
-        long long dst = 0;
-        if (live) {
-            int before = 0;
-            for (int w = 0; w < warp; w++) before += wcount[w][pid];
-            dst = running[pid] + before + rank;
+        int pid[XR];
+        int pos[XR];
+#pragma unroll
+        for (int i = 0; i < XR; i++) {
+            int64_t row = tile + (int64_t)i * XT + threadIdx.x;
+            bool live = row < end;
+            pid[i] = live ? (int)pids[row] : -1;
+            unsigned int peers = __match_any_sync(0xffffffffu, live ? pid[i] : -1 - lane);
+            pos[i] = __popc(peers & ((1u << lane) - 1));
+            if (live && pos[i] == 0) wcount[i * NW + warp][pid[i]] = (unsigned short)__popc(peers);
         }
         __syncthreads();
-        if (threadIdx.x < P) {
-            int tot = 0;
-            for (int w = 0; w < XT / 32; w++) tot += wcount[w][threadIdx.x];
-            running[threadIdx.x] += tot;
+        // exclusive scan over the 64 cells of every partition (cells are in row order: iteration-major, then warp)
+        for (int p = warp; p < P; p += NW) {
+            unsigned int a = wcount[2 * lane][p], b = wcount[2 * lane + 1][p];
+            unsigned int incl = a + b;
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            unsigned int excl = incl - (a + b);
+            wcount[2 * lane][p] = (unsigned short)excl;
+            wcount[2 * lane + 1][p] = (unsigned short)(excl + a);
+            if (lane == 31) tile_cnt[p] = (int)incl;
         }
-        if (live) {
-            for (int c = 0; c < cols.count; c++) {
-                char* base = cols.dst[(size_t)c * P + pid];
-                switch (cols.elem[c]) {
-                    case 8: ((long long*)base)[dst] = ((const long long*)cols.src[c])[row]; break;
-                    case 4: ((int*)base)[dst] = ((const int*)cols.src[c])[row]; break;
-                    case 2: ((short*)base)[dst] = ((const short*)cols.src[c])[row]; break;
-                    case 1: base[dst] = ((const char*)cols.src[c])[row]; break;
-                    default: base[dst] = tg_valid((const uint8_t*)cols.src[c], row) ? 0 : 1; break;
+        __syncthreads();
+        if (warp == 0) {
+            int c0 = 2 * lane < P ? tile_cnt[2 * lane] : 0, c1 = 2 * lane + 1 < P ? tile_cnt[2 * lane + 1] : 0;
+            int incl = c0 + c1;
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            int excl = incl - (c0 + c1);
+            if (2 * lane < P) tile_off[2 * lane] = excl;
+            if (2 * lane + 1 < P) tile_off[2 * lane + 1] = excl + c0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < XR; i++) {
+            if (pid[i] < 0) continue;
+            pos[i] += tile_off[pid[i]] + wcount[i * NW + warp][pid[i]];
+            spid[pos[i]] = (uint8_t)pid[i];
+        }
+        for (int c = 0; c < cols.count; c++) {
+            const int elem = cols.elem[c];
+            const void* src = cols.src[c];
+#pragma unroll
+            for (int i = 0; i < XR; i++) {
+                if (pid[i] < 0) continue;
+                int64_t row = tile + (int64_t)i * XT + threadIdx.x;
+                switch (elem) {
+                    case 8: stage[pos[i]] = ((const long long*)src)[row]; break;
+                    case 4: ((int*)stage)[pos[i]] = ((const int*)src)[row]; break;
+                    case 2: ((short*)stage)[pos[i]] = ((const short*)src)[row]; break;
+                    case 1: ((char*)stage)[pos[i]] = ((const char*)src)[row]; break;
+                    default: ((char*)stage)[pos[i]] = tg_valid((const uint8_t*)src, row) ? 0 : 1; break;
                 }
             }
+            __syncthreads();
+            for (int j = threadIdx.x; j < tile_rows; j += XT) {
+                int q = spid[j];
+                long long d = running[q] + (j - tile_off[q]);
+                char* base = cols.dst[(size_t)c * P + q];
+                switch (elem) {
+                    case 8: ((long long*)base)[d] = stage[j]; break;
+                    case 4: ((int*)base)[d] = ((const int*)stage)[j]; break;
+                    case 2: ((short*)base)[d] = ((const short*)stage)[j]; break;
+                    default: base[d] = ((const char*)stage)[j]; break;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
+        if (threadIdx.x < P) running[threadIdx.x] += tile_cnt[threadIdx.x];
     }
 }
 
@@ -313,13 +369,14 @@ struct PartitionOp : tgpu_op {
         }
         int prepend = 0, start_row = 0;
         if (replicates_any_row && !any_row_replicated) { prepend = 1; start_row = 1; any_row_replicated = true; }
+        bool row_wise = n < (int64_t)P * 2;   // COLUMNAR_STRATEGY_COEFFICIENT (:57,149)
+        if (!row_wise && prepend == 0 && multisplit_applies(in)) return add_input_multisplit(in);
         DevBuf ids;
         TG_TRY(ids.alloc(ctx, (size_t)n * 4));
         TG_TRY(compute_ids(in, ids.as<int32_t>(), true));
         std::vector<long long> h_off(P + 1, 0);
         DevBuf gather_idx;
         int64_t idx_stride = 0;
-        bool row_wise = n < (int64_t)P * 2;   // COLUMNAR_STRATEGY_COEFFICIENT (:57,149)
         if (row_wise) {
             DevBuf counts;
             TG_TRY(counts.alloc(ctx, (size_t)P * 8));
@@ -374,6 +431,98 @@ struct PartitionOp : tgpu_op {
             if (cnt == 0) continue;
             TG_TRY(emit(in, gather_idx.as<int32_t>() + h_off[p], cnt, p));
         }
+        return TGPU_OK;
+    }
+
+    // Common case (no replicated rows, fixed-width columns, <= 64 partitions): one stable multi-split pass moves every
+    // column straight to its partition-contiguous place; no sort, no gather index.  Same row order as the column-wise
+    // strategy of the reference (ascending position inside a partition, PagePartitioner.java:242-276).
+    bool multisplit_applies(const DevPage& in) const
+    {
+        if (partition_count > XMAXP || 2 * (int)in.cols.size() > XMAXC || getenv("TGPU_PARTITION_SORT")) return false;
+        if (null_channel >= 0 && null_channel < (int)in.cols.size() && in.cols[null_channel].validity) return false;
+        for (auto& c : in.cols)
+            if (c.type == TGPU_UTF8) return false;
+        return true;
+    }
+
+    int add_input_multisplit(const DevPage& in)
+    {
+        const int P = partition_count, C = (int)in.cols.size();
+        const int64_t n = in.rows;
+        int grid = tg_grid(ctx, n, XT * 16, 8);
+        int64_t chunk = tg_div_up(tg_div_up(n, grid), XT) * XT;
+        grid = (int)std::max<int64_t>(1, tg_div_up(n, chunk));
+        DevBuf pids, hist, block_off, d_totals;
+        TG_TRY(pids.alloc(ctx, (size_t)n));
+        TG_TRY(hist.alloc(ctx, (size_t)grid * P * 4));
+        TG_TRY(block_off.alloc(ctx, (size_t)grid * P * 8));
+        TG_TRY(d_totals.alloc(ctx, (size_t)P * 8));
+        KeyCols k;
+        TG_TRY(key_cols(in, &k));
+        TG_LAUNCH(ctx, xchg_hist_kernel, grid, XT, 0, k, n, chunk, bucket_count, bucket_to_partition.empty() ? nullptr : d_b2p.as<int32_t>(), P,
+                  pids.as<uint8_t>(), hist.as<unsigned int>());
+        TG_LAUNCH(ctx, xchg_offsets_kernel, 1, 64, 0, hist.as<unsigned int>(), grid, P, block_off.as<long long>(), d_totals.as<long long>());
+        std::vector<long long> counts(P), off(P + 1, 0);
+        TG_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_totals.p, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < P; q++) off[q + 1] = off[q] + counts[q];
+        struct Lane { int elem; const void* src; std::shared_ptr<DevBuf> out; int col; bool nulls; };
+        std::vector<Lane> lanes;
+        for (int c = 0; c < C; c++) {
+            lanes.push_back(Lane{in.cols[c].elem_size(), in.cols[c].data, nullptr, c, false});
+            if (in.cols[c].validity) lanes.push_back(Lane{0, in.cols[c].validity, nullptr, c, true});
+        }
+        std::vector<char*> h_dst(lanes.size() * P);
+        for (size_t l = 0; l < lanes.size(); l++) {
+            int es = lanes[l].elem ? lanes[l].elem : 1;
+            lanes[l].out = std::make_shared<DevBuf>();
+            TG_TRY(lanes[l].out->alloc(ctx, (size_t)n * es));
+            for (int q = 0; q < P; q++) h_dst[l * P + q] = (char*)lanes[l].out->p + off[q] * es;
+        }
+        DevBuf d_dst;
+        TG_TRY(d_dst.alloc(ctx, h_dst.size() * sizeof(char*)));
+        TG_CUDA(ctx, cudaMemcpyAsync(d_dst.p, h_dst.data(), h_dst.size() * sizeof(char*), cudaMemcpyHostToDevice, ctx->stream));
+        XchgCols xc;
+        memset(&xc, 0, sizeof(xc));
+        xc.count = (int32_t)lanes.size();
+        for (size_t l = 0; l < lanes.size(); l++) { xc.elem[l] = lanes[l].elem; xc.src[l] = lanes[l].src; }
+        xc.dst = d_dst.as<char*>();
+        TG_LAUNCH(ctx, xchg_scatter_kernel, grid, XT, 0, pids.as<uint8_t>(), n, chunk, P, block_off.as<long long>(), xc);
+        for (int q = 0; q < P; q++) {
+            if (counts[q] == 0) continue;
+            DevPage outp;
+            outp.rows = counts[q];
+            outp.cols.resize(C);
+            for (auto& lane : lanes) {
+                DevColumn& dst = outp.cols[lane.col];
+                int es = lane.elem ? lane.elem : 1;
+                char* base = (char*)lane.out->p + off[q] * es;
+                if (!lane.nulls) {
+                    dst.type = in.cols[lane.col].type;
+                    dst.length = counts[q];
+                    dst.own_data = lane.out;     // all partitions alias slices of one buffer per column
+                    dst.data = base;
+                }
+                else {
+                    tgpu_column bytemap_col;
+                    memset(&bytemap_col, 0, sizeof(bytemap_col));
+                    bytemap_col.type = TGPU_INT8;
+                    bytemap_col.flags = TGPU_COL_NULLS_BYTEMAP;
+                    bytemap_col.length = counts[q];
+                    bytemap_col.data = base;
+                    bytemap_col.validity = (const uint8_t*)base;
+                    DevColumn packed;
+                    TG_TRY(tg_ingest_column(ctx, &bytemap_col, true, &packed));
+                    dst.own_validity = packed.own_validity;
+                    dst.validity = packed.validity;
+                }
+            }
+            OwnedPage* o = tg_make_owned_page(std::move(outp));
+            o->partition = q;
+            pending.push_back(o);
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // h_dst staging must outlive its copy; NULL byte lanes are released here
         return TGPU_OK;
     }
 
