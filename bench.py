@@ -135,7 +135,9 @@ def workload_config(args, n_orders, probe_rows, world):
                         f"probe payload l_extendedprice FLOAT64 (BASELINE.json configs[1])",
             "build_rows_per_gpu": n_orders, "probe_rows_per_gpu": probe_rows, "probe_order": "orderkey-clustered" if not args.shuffle_probe else "shuffled",
             "parallelism": (f"hash-partitioned x{world}, probe side exchanged every step " +
-                            ("over NCCL send/recv" if os.environ.get("TGPU_EXCHANGE_NCCL") else "by P2P stores into peer HBM (NVLink)")) if world > 1 else "single GPU",
+                            ("over NCCL send/recv" if os.environ.get("TGPU_EXCHANGE_NCCL") else "by P2P stores into peer HBM (NVLink)") +
+                            ("" if os.environ.get("TGPU_BENCH_SERIAL") or os.environ.get("TGPU_EXCHANGE_NCCL") else
+                             ", two half-pages per step, split-phase: SMs partition page k+1 and probe page k while copy engines move page k+1")) if world > 1 else "single GPU",
             "l2": "inputs (9.6 GB probe side, 4.3 GB table at SF100) are far larger than the 126 MB L2; no flush needed"}
 
 
@@ -232,33 +234,76 @@ def main():
     else:
         build_page_local = build_page
 
+    # N > 1, pipelined form (default): split-phase exchange - the SMs partition page k+1 and probe page k while the copy
+    # engines move page k+1 over NVLink.  TGPU_BENCH_SERIAL=1: exchange then probe, one page per step, no overlap.
+    overlap = world > 1 and not os.environ.get("TGPU_BENCH_SERIAL") and not os.environ.get("TGPU_EXCHANGE_NCCL")
+    pctx = ctx
     bridge = ops.JoinBridge()
-    builder = ops.HashBuilderOperatorFactory(ctx, bridge, [0], [1], n_orders).create_operator()
+    builder = ops.HashBuilderOperatorFactory(pctx, bridge, [0], [1], n_orders).create_operator()
     t_build0 = time.time()
     builder.add_input(build_page_local)
     builder.finish()
-    ctx.synchronize()
+    pctx.synchronize()
     build_s = time.time() - t_build0
     lookup = bridge.lookup_source
-    probe_op = ops.LookupJoinOperatorFactory(ctx, bridge, abi.JOIN_INNER, False, [0], [0, 1]).create_operator()
+    probe_op = ops.LookupJoinOperatorFactory(pctx, bridge, abi.JOIN_INNER, False, [0], [0, 1]).create_operator()
     if world > 1 and not os.environ.get("TGPU_EXCHANGE_NCCL"):
         # peer-memory exchange for the probe side: two receive arenas per rank, IPC handles all-gathered once.
         # (created only now: the build-side page above went through NCCL send/recv and is owned by the lookup source)
         import torch
         arena_bytes = int(l_count * 1.3) * 16 + (4 << 20)
-        hb = (C.c_uint8 * (2 * abi.IPC_HANDLE_BYTES))()
+        hb = (C.c_uint8 * (abi.NUM_ARENAS * abi.IPC_HANDLE_BYTES))()
         ctx.check(lib.tgpu_comm_arena_create(ctx.h, arena_bytes, C.cast(hb, C.c_void_p)))
         mine = torch.tensor(list(hb), dtype=torch.uint8, device=f"cuda:{local}")
         gathered = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
-        allh = (C.c_uint8 * (world * 2 * abi.IPC_HANDLE_BYTES))(*torch.cat(gathered).cpu().tolist())
+        allh = (C.c_uint8 * (world * abi.NUM_ARENAS * abi.IPC_HANDLE_BYTES))(*torch.cat(gathered).cpu().tolist())
         ctx.check(lib.tgpu_comm_arena_open(ctx.h, C.cast(allh, C.c_void_p)))
 
     out_rows_seen = [0]
     kernel_ms = []
+    # pipelined form: the step's page is exchanged in two halves through tgpu_exchange_begin/_end; probe(half k) is only
+    # enqueued, its output is taken when the next page is handed to the probe
+    halves = []
+    if overlap:
+        h0 = (l_count // 2) // 1024 * 1024
+        for first, cnt in ((0, h0), (h0, l_count - h0)):
+            halves.append(ops.DevicePage([ops.DeviceColumn(abi.INT64, d_lkeys + first * 8, cnt), ops.DeviceColumn(abi.FLOAT64, d_lprice_col.ptr + first * 8, cnt)], cnt))
+    inflight = []
+    step_rows = [0]
+
+    def drain():
+        if not inflight:
+            return
+        out = probe_op.get_output_device()
+        step_rows[0] += out.rows if out else 0
+        if out:
+            out.release()
+        inflight.pop().release()
+
+    handles = []
+
+    def step_overlapped():
+        # per half page k: begin(k) [partition on the SMs, transfer on the copy engines], then end(k-1) + probe(k-1)
+        for half in halves:
+            h = C.c_void_p()
+            ctx.check(lib.tgpu_exchange_begin(ctx.h, partitioner.h, half.ref(), C.byref(h)))
+            handles.append(h)
+            if len(handles) > 1:
+                finish_one()
+
+    def finish_one():
+        drain()                      # output of the probe before (needsInput protocol)
+        pp = abi.PP()
+        ctx.check(lib.tgpu_exchange_end(ctx.h, handles.pop(0), C.byref(pp)))
+        inp = ops.DeviceOutputPage(ctx, pp)
+        probe_op.add_input(inp.as_device_page())
+        inflight.append(inp)
 
     def step():
-        if partitioner is not None:
+        if overlap:
+            step_overlapped()
+        elif partitioner is not None:
             pp = abi.PP()
             ctx.check(lib.tgpu_exchange_partitioned(ctx.h, partitioner.h, probe_page.ref(), C.byref(pp)))
             inp = ops.DeviceOutputPage(ctx, pp)
@@ -278,17 +323,28 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    while handles:
+        finish_one()
+    drain()
     ctx.synchronize()
+    pctx.synchronize()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     del kernel_ms[:]
-    launches0 = ctx.kernel_launches
+    step_rows[0] = 0
+    launches0 = ctx.kernel_launches + 0
     ctx.timer_start()
     for _ in range(args.steps):
         step()
+    if overlap:
+        # pipeline drain: the last exchange is ended and probed, its output taken (host-synchronised) before the stop event
+        while handles:
+            finish_one()
+        drain()
+        out_rows_seen[0] = step_rows[0] // args.steps     # every half of every timed step was drained inside the timed region
     ms = ctx.timer_stop_ms()
-    launches = ctx.kernel_launches - launches0
+    launches = ctx.kernel_launches + 0 - launches0
     clocks = sampler.stop()
     barrier()
     if dist is not None:
@@ -314,7 +370,7 @@ def main():
         peak, peak_src = measured_peak()
         kms = float(np.mean(kernel_ms))
         achieved = ALG_BYTES_PROBE_FUSED * l_count / (kms * 1e-3) / 1e9
-        roofline = {"kernel": "join_probe_gather_kernel<4,true>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roofline = {"kernel": "join_probe_lean_kernel<1,true> (fused probe + payload gather)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "rows_per_launch": l_count,
                     "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step, "launches_timed": len(kernel_ms)}
         d_pos = ctx.malloc(l_count * 4)
@@ -327,7 +383,7 @@ def main():
             acc += ctx.last_kernel_ms()
         ims = acc / reps
         ia = ALG_BYTES_PROBE_INDEX * l_count / (ims * 1e-3) / 1e9
-        index_probe = {"kernel": "join_probe_kernel<4,true>", "bound": "hbm", "achieved": ia, "peak": peak, "unit": "GB/s", "frac": ia / peak,
+        index_probe = {"kernel": "join_probe_lean_kernel<1,false> (index-only probe)", "bound": "hbm", "achieved": ia, "peak": peak, "unit": "GB/s", "frac": ia / peak,
                        "algorithmic_bytes_per_row": ALG_BYTES_PROBE_INDEX, "kernel_ms": ims, "kernel_rows_per_sec": l_count / (ims * 1e-3)}
         ctx.free(d_pos)
 

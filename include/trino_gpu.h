@@ -329,12 +329,30 @@ int tgpu_comm_destroy(tgpu_ctx* ctx);
  * buffer, no separate transfer) and synchronises with one tiny NCCL all-reduce.  The returned page then aliases an arena
  * and stays valid until the second-next exchange on this context; exchanges that do not fit fall back to NCCL send/recv. */
 #define TGPU_IPC_HANDLE_BYTES 64
-int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[2 * TGPU_IPC_HANDLE_BYTES]);
+#define TGPU_NUM_ARENAS 3   /* receive arenas per context: an exchanged page stays valid until the third-next exchange */
+int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[TGPU_NUM_ARENAS * TGPU_IPC_HANDLE_BYTES]);
 int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles /* world x 2 x TGPU_IPC_HANDLE_BYTES, rank-major */);
 /* Hash-partition a device-resident page into `world` partitions and exchange: partition p goes to
  * rank p.  Returns the concatenation (in rank order) of what every rank sent here, as a
  * library-owned device page.  Fixed-width columns only.                                         */
 int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out);
+/* Same, for a pipeline in which another context of this process (`consumer`, e.g. the one running the LookupJoinOperator)
+ * reads the exchanged pages: the exchange does not enter its closing barrier - after which peers may overwrite the arena of the
+ * exchange before last - until everything enqueued on `consumer` so far has completed.  The wait happens on the device, so this
+ * exchange's partition/scatter passes overlap the consumer's kernels.  consumer == NULL: identical to tgpu_exchange_partitioned. */
+int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_ctx* consumer, tgpu_page** out);
+
+/* Split-phase exchange for pipelines (one context): _begin partitions the page (multi-split into per-destination send
+ * buffers; rows that stay are written to their final place), then hands the transfer to the copy engines - one peer copy per
+ * (destination, column) over NVLink on a side stream, closed by a barrier on a second communicator - and returns while it
+ * runs; the SMs are free for the caller's next kernels on this context (e.g. the probe of the previous page).  _end makes the
+ * context's stream wait for the transfer and returns the received page (same rows, order and lifetime rules as
+ * tgpu_exchange_partitioned).  At most two exchanges may be in flight (begun, not ended) per context, and work that reads a
+ * received page must be enqueued on this context before the second-next _begin: with TGPU_NUM_ARENAS = 3 that is what keeps a
+ * peer from overwriting an arena that is still being read.  Requires arenas (tgpu_comm_arena_create/open). */
+typedef struct tgpu_exchange tgpu_exchange;
+int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_exchange** out);
+int tgpu_exchange_end(tgpu_ctx* ctx, tgpu_exchange* exchange, tgpu_page** out);
 
 /* ------------------------------------------------------------------ Operator protocol
  * One-to-one with M/operator/Operator.java:21-102.                                              */

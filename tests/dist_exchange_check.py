@@ -81,23 +81,86 @@ def main():
     want = oracle_join_rows(got_o, got_l, 0, 0, [0, 2], [1], abi.JOIN_INNER, False)
     assert rows == want and len(rows) == got_l.position_count
     # ---- peer-memory path: same exchange through P2P stores into the destination's arena, twice (arenas alternate)
-    hb = (C.c_uint8 * (2 * abi.IPC_HANDLE_BYTES))()
+    hb = (C.c_uint8 * (abi.NUM_ARENAS * abi.IPC_HANDLE_BYTES))()
     ctx.check(lib.tgpu_comm_arena_create(ctx.h, 64 << 20, C.cast(hb, C.c_void_p)))
     mine_h = torch.tensor(list(hb), dtype=torch.uint8, device=f"cuda:{local}")
     gathered = [torch.zeros_like(mine_h) for _ in range(world)]
     dist.all_gather(gathered, mine_h)
-    allh = (C.c_uint8 * (world * 2 * abi.IPC_HANDLE_BYTES))(*torch.cat(gathered).cpu().tolist())
+    allh = (C.c_uint8 * (world * abi.NUM_ARENAS * abi.IPC_HANDLE_BYTES))(*torch.cat(gathered).cpu().tolist())
     ctx.check(lib.tgpu_comm_arena_open(ctx.h, C.cast(allh, C.c_void_p)))
     for _ in range(3):
         p2p_l = exchange(lpage)
         assert p2p_l.rows() == got_l.rows()          # identical rows in identical order to the NCCL path
         p2p_o = exchange(opage)
         assert p2p_o.rows() == got_o.rows()
+    # ---- pipelined form: the exchange runs on `ctx`, build + probe on a second context of the same GPU; the probe of page k is
+    # only enqueued, its output is taken after exchange k+1 was issued (tgpu_exchange_partitioned_fenced guards the arena reuse)
+    from trino_b200.page import AbiPage
+    pctx = ops.Context(local)
+    bridge = ops.JoinBridge()
+    b = ops.HashBuilderOperatorFactory(pctx, bridge, [0], [1]).create_operator()
+    b.add_input(got_o)
+    b.finish()
+    probe = ops.LookupJoinOperatorFactory(pctx, bridge, abi.JOIN_INNER, False, [0], [0, 2]).create_operator()
+    half = l_count // 2
+    pieces = [Page(Block.bigint(lkeys[sl]), Block.double(lkeys[sl] * 0.25, lnull[sl]), Block.integer((lkeys[sl] % 1000).astype(np.int32)))
+              for sl in (slice(0, half), slice(half, l_count))]
+    want_rows = []
+    for piece in pieces:
+        ap = AbiPage(piece)
+        pp = abi.PP()
+        ctx.check(lib.tgpu_exchange_partitioned(ctx.h, part.h, ap.ref(), C.byref(pp)))
+        recv = ctx.page_to_host(pp)
+        want_rows.append(oracle_join_rows(got_o, recv, 0, 0, [0, 2], [1], abi.JOIN_INNER, False))
+    got_rows = [[], []]
+    inflight = None
+    for it in range(6):
+        piece = pieces[it % 2]
+        ap = AbiPage(piece)
+        pp = abi.PP()
+        ctx.check(lib.tgpu_exchange_partitioned_fenced(ctx.h, part.h, ap.ref(), pctx.h, C.byref(pp)))
+        inp = ops.DeviceOutputPage(ctx, pp)
+        if inflight is not None:
+            out = probe.get_output()
+            got_rows[(it - 1) % 2] = out.rows() if out is not None else []
+            assert got_rows[(it - 1) % 2] == want_rows[(it - 1) % 2], f"pipelined join differs at iteration {it - 1}"
+            inflight.release()
+        probe.add_input(inp.as_device_page())
+        inflight = inp
+    out = probe.get_output()
+    assert (out.rows() if out is not None else []) == want_rows[1]
+    inflight.release()
+    probe.close()
+    b.close()
+    # ---- split-phase form: two exchanges in flight, transfers on the copy engines; rows and order identical to the blocking call
+    handles = []
+    seq = [lpage, opage, lpage, lpage, opage]
+    want_seq = [got_l.rows(), got_o.rows(), got_l.rows(), got_l.rows(), got_o.rows()]
+    aps = []
+    done = 0
+    for page in seq:
+        ap = AbiPage(page)
+        aps.append(ap)
+        h = C.c_void_p()
+        ctx.check(lib.tgpu_exchange_begin(ctx.h, part.h, ap.ref(), C.byref(h)))
+        handles.append(h)
+        if len(handles) == 2:
+            pp = abi.PP()
+            ctx.check(lib.tgpu_exchange_end(ctx.h, handles.pop(0), C.byref(pp)))
+            assert ctx.page_to_host(pp).rows() == want_seq[done], f"split-phase exchange {done} differs"
+            done += 1
+    while handles:
+        pp = abi.PP()
+        ctx.check(lib.tgpu_exchange_end(ctx.h, handles.pop(0), C.byref(pp)))
+        assert ctx.page_to_host(pp).rows() == want_seq[done], f"split-phase exchange {done} differs"
+        done += 1
+    assert done == len(seq)
     part.close()
+    pctx.close()
     ctx.check(lib.tgpu_comm_destroy(ctx.h))
     dist.barrier()
     if rank == 0:
-        print(f"dist_exchange_check ok (NCCL and P2P paths): world={world} rows={total_rows}")
+        print(f"dist_exchange_check ok (NCCL, P2P, fenced and split-phase paths): world={world} rows={total_rows}")
     dist.destroy_process_group()
     ctx.close()
 

@@ -31,6 +31,7 @@ STEP_SINGLE, STEP_PARTIAL, STEP_FINAL, STEP_INTERMEDIATE = 0, 1, 2, 3
 JOIN_INNER, JOIN_PROBE_OUTER = 0, 1
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
+NUM_ARENAS = 3
 
 
 class Column(C.Structure):
@@ -190,6 +191,9 @@ SIGNATURES = {
     "tgpu_comm_arena_create": (C.c_int, [VP, C.c_size_t, VP]),
     "tgpu_comm_arena_open": (C.c_int, [VP, VP]),
     "tgpu_exchange_partitioned": (C.c_int, [VP, VP, PP, C.POINTER(PP)]),
+    "tgpu_exchange_partitioned_fenced": (C.c_int, [VP, VP, PP, VP, C.POINTER(PP)]),
+    "tgpu_exchange_begin": (C.c_int, [VP, VP, PP, C.POINTER(VP)]),
+    "tgpu_exchange_end": (C.c_int, [VP, VP, C.POINTER(PP)]),
     "tgpu_op_needs_input": (C.c_int, [VP, C.POINTER(C.c_int)]),
     "tgpu_op_add_input": (C.c_int, [VP, PP]),
     "tgpu_op_get_output": (C.c_int, [VP, C.POINTER(PP)]),

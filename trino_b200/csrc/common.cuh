@@ -39,6 +39,7 @@ struct tgpu_ctx {
     // 64-byte pinned + device scratch for small readbacks (counters, flags)
     int64_t* h_scratch = nullptr;
     int64_t* d_scratch = nullptr;
+    cudaEvent_t fence_ev = nullptr;     // recorded on this context's stream by an exchange that must not outrun this consumer
     // cache of large device buffers released by operators (all work of a ctx is ordered on its one stream, so a block
     // can be handed to the next request without waiting): multi-GB cudaMallocAsync calls cost milliseconds even from a
     // warm pool, and operators allocate the same sizes page after page
@@ -49,8 +50,11 @@ struct tgpu_ctx {
     ncclComm* comm = nullptr;
     int rank = 0, world = 1;
     // peer-memory exchange arenas (two per rank, alternating): arena[k][r] = rank r's k-th arena mapped into this process
-    void* arena_local[2] = {nullptr, nullptr};
-    std::vector<void*> arena_peer[2];
+    void* arena_local[TGPU_NUM_ARENAS] = {nullptr, nullptr, nullptr};
+    std::vector<void*> arena_peer[TGPU_NUM_ARENAS];
+    ncclComm* comm2 = nullptr;               // second communicator: barriers of the split-phase exchange (copy stream)
+    cudaStream_t copy_stream = nullptr;      // peer copies of the split-phase exchange (copy engines)
+    int exchanges_in_flight = 0;
     size_t arena_bytes = 0;
     int64_t arena_epoch = 0;
 };

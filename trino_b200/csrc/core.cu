@@ -81,9 +81,9 @@ extern "C" int tgpu_ctx_create(int device, tgpu_ctx** out)
     TG_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
     TG_CUDA(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    TG_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scratch, 256));
-    TG_CUDA(ctx, cudaMalloc((void**)&ctx->d_scratch, 256));
-    TG_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 256, ctx->stream));
+    TG_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scratch, 1024));
+    TG_CUDA(ctx, cudaMalloc((void**)&ctx->d_scratch, 1024));
+    TG_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch, 0, 1024, ctx->stream));
     *out = ctx;
     return TGPU_OK;
 }
@@ -103,6 +103,7 @@ extern "C" void tgpu_ctx_destroy(tgpu_ctx* ctx)
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->fence_ev) cudaEventDestroy(ctx->fence_ev);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->kev0);

@@ -272,7 +272,7 @@ struct FilterProjectOp : tgpu_op {
                 long long n_arg = n;
                 unsigned char* f_arg = flags.as<unsigned char>();
                 void* params[4] = {&cols, &n_arg, &f_arg, &d_err};
-                TG_TRY(jit_launch(ctx, jit_filter, grid, FP_THREADS, 0, params));
+                TG_TRY(jit_launch(ctx, jit_filter, tg_grid(ctx, n, FP_THREADS, jit_blocks_per_sm(jit_filter, FP_THREADS, 0)), FP_THREADS, 0, params));
             }
             else TG_LAUNCH(ctx, fp_filter_kernel, grid, FP_THREADS, 0, dp, cols, n, flags.as<uint8_t>(), d_err);
             long long* d_count = (long long*)(ctx->d_scratch + 4);
@@ -327,7 +327,7 @@ struct FilterProjectOp : tgpu_op {
             if (jit_project) {
                 long long m_arg = m;
                 void* params[6] = {&cols, &d_sel, &m_arg, &oc, &d_err, &d_anynull};
-                TG_TRY(jit_launch(ctx, jit_project, pgrid, FP_THREADS, 0, params));
+                TG_TRY(jit_launch(ctx, jit_project, tg_grid(ctx, m, FP_THREADS, jit_blocks_per_sm(jit_project, FP_THREADS, 0)), FP_THREADS, 0, params));
             }
             else TG_LAUNCH(ctx, fp_project_kernel, pgrid, FP_THREADS, 0, dp, cols, d_sel, m, oc, d_err, d_anynull);
             int64_t word = 0;

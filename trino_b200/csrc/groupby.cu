@@ -768,6 +768,37 @@ __global__ void __launch_bounds__(256) gf_page_kernel(AggPlan plan, DColumns col
     }
 }
 
+// Locality pass for tables that do not fit the L2: the slot index's top bits name a contiguous slice of the table, rows are
+// grouped by slice (stable, so first-row stamps keep their meaning) and gf_page_kernel then runs slice by slice with its
+// read-modify-write traffic staying in the L2 instead of costing a random DRAM sector pair per row and accumulator.
+__global__ void __launch_bounds__(256) gf_slice_ids_kernel(AggPlan plan, DColumns cols, int64_t n, int64_t cap, int shift, uint8_t* __restrict__ ids,
+                                                          unsigned int* __restrict__ counts /* [64] */)
+{
+    __shared__ unsigned int sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long mask = (unsigned long long)cap - 1;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        unsigned long long pk = 0;
+        int sp = pack_key(plan, cols, i, nullptr, 0, 0, &pk);
+        int id = sp >= 0 ? 0 : (int)((murmur3_mix(pk) & mask) >> shift);
+        ids[i] = (uint8_t)id;
+        unsigned int peers = __match_any_sync(__activemask(), id);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[id], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void gf_iota_kernel(int* __restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (int)i;
+}
+
 // table growth: move every used record into the bigger table
 __global__ void gf_rehash_kernel(const unsigned long long* __restrict__ orecs, int64_t ocap, unsigned long long* __restrict__ recs, int64_t cap, int W, int A)
 {
@@ -1682,16 +1713,12 @@ struct AggOp : tgpu_op {
         return TGPU_OK;
     }
 
-    int run_fused_general(const DevPage& in, const DColumns& cols)
+    // one gf_page_kernel pass over `todo` rows (`rows` == nullptr: rows [0, todo) of the page), replaying deferred rows after growth
+    int run_fused_rows(const DColumns& cols, const int* rows, int64_t todo)
     {
-        int64_t n = in.rows;
-        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
-        DevBuf deferred;
-        TG_TRY(deferred.alloc(ctx, (size_t)n * 4));
+        DevBuf deferred, replay;
+        TG_TRY(deferred.alloc(ctx, (size_t)std::max<int64_t>(todo, 1) * 4));
         int* d_tickets = (int*)(ctx->d_scratch + 20);    // [0] slots claimed by this launch, [1] deferred rows, [2] special groups born
-        const int* rows = nullptr;
-        int64_t todo = n;
-        DevBuf replay;
         while (true) {
             int64_t budget = f_cap * 3 / 4 - f_used;
             TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 16, ctx->stream));
@@ -1714,6 +1741,52 @@ struct AggOp : tgpu_op {
             rows = replay.as<int>();
             todo = left;
         }
+        return TGPU_OK;
+    }
+
+    int run_fused_general(const DevPage& in, const DColumns& cols)
+    {
+        int64_t n = in.rows;
+        if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+        // table much larger than the L2 and a page worth reordering: visit the table slice by slice
+        const size_t table_bytes = (size_t)f_cap * gf_words() * 8;
+        // (thresholds can be lowered from the environment so that the parity tests reach this path with small inputs)
+        const char* e_bytes = getenv("TGPU_AGG_SLICE_MIN_BYTES");
+        const char* e_target = getenv("TGPU_AGG_SLICE_BYTES");
+        const size_t min_bytes = e_bytes ? (size_t)atoll(e_bytes) : ((size_t)96 << 20);
+        const size_t slice_bytes = e_target ? (size_t)atoll(e_target) : ((size_t)16 << 20);
+        if (!getenv("TGPU_AGG_NO_SLICES") && table_bytes >= min_bytes && n >= (e_bytes ? 1 : (1 << 20))) {
+            int log_slices = 1;
+            while (log_slices < 6 && (table_bytes >> log_slices) > slice_bytes) log_slices++;
+            const int S = 1 << log_slices;
+            int log_cap = 0;
+            while ((1LL << log_cap) < f_cap) log_cap++;
+            DevBuf ids, ids_sorted, rows_in, rows_sorted, tmp;
+            TG_TRY(ids.alloc(ctx, (size_t)n));
+            TG_TRY(ids_sorted.alloc(ctx, (size_t)n));
+            TG_TRY(rows_in.alloc(ctx, (size_t)n * 4));
+            TG_TRY(rows_sorted.alloc(ctx, (size_t)n * 4));
+            unsigned int* d_counts = (unsigned int*)(ctx->d_scratch + 32);   // 64 counters
+            TG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 64 * 4, ctx->stream));
+            TG_LAUNCH(ctx, gf_slice_ids_kernel, tg_grid(ctx, n, 256, 8), 256, 0, plan, cols, n, f_cap, log_cap - log_slices, ids.as<uint8_t>(), d_counts);
+            TG_LAUNCH(ctx, gf_iota_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, rows_in.as<int>(), n);
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ids.as<uint8_t>(), ids_sorted.as<uint8_t>(), rows_in.as<int>(), rows_sorted.as<int>(), (int)n, 0, log_slices, ctx->stream);
+            TG_TRY(tmp.alloc(ctx, tmp_bytes));
+            TG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ids.as<uint8_t>(), ids_sorted.as<uint8_t>(), rows_in.as<int>(), rows_sorted.as<int>(), (int)n, 0,
+                                                         log_slices, ctx->stream));
+            unsigned int counts[64];
+            TG_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_counts, 64 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            memcpy(counts, ctx->h_scratch, sizeof(counts));
+            int64_t off = 0;
+            for (int q = 0; q < S; q++) {
+                if (counts[q]) TG_TRY(run_fused_rows(cols, rows_sorted.as<int>() + off, counts[q]));
+                off += counts[q];
+            }
+            if (off != n) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "slice counts %lld != rows %lld", (long long)off, (long long)n);
+        }
+        else TG_TRY(run_fused_rows(cols, nullptr, n));
         rows_seen += n;
         group_count = f_used + f_specials;
         return TGPU_OK;

@@ -37,6 +37,7 @@ struct Api {
     int (*cuModuleLoadData)(CUmodule*, const void*) = nullptr;
     int (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
     int (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, cudaStream_t, void**, void**) = nullptr;
+    int (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
     int (*cuFuncSetAttribute)(CUfunction, int, int) = nullptr;
     int (*cuGetErrorString)(int, const char**) = nullptr;
 };
@@ -71,7 +72,7 @@ void load_api()
     LOAD(rtc, nvrtcGetCUBINSize) LOAD(rtc, nvrtcGetCUBIN) LOAD(rtc, nvrtcDestroyProgram)
     g_api.rtc_ok = true;
     if (!cu) { g_api.why = "libcuda.so.1 not found"; return; }
-    LOAD(cu, cuModuleLoadData) LOAD(cu, cuModuleGetFunction) LOAD(cu, cuLaunchKernel) LOAD(cu, cuFuncSetAttribute) LOAD(cu, cuGetErrorString)
+    LOAD(cu, cuModuleLoadData) LOAD(cu, cuModuleGetFunction) LOAD(cu, cuLaunchKernel) LOAD(cu, cuFuncSetAttribute) LOAD(cu, cuGetErrorString) LOAD(cu, cuOccupancyMaxActiveBlocksPerMultiprocessor)
 #undef LOAD
     g_api.ok = true;
 }
@@ -148,6 +149,13 @@ int jit_get_function(tgpu_ctx* ctx, const std::string& body, const char* kernel_
     }
     *fn_out = (void*)fn;
     return TGPU_OK;
+}
+
+int jit_blocks_per_sm(void* fn, int block, size_t smem)
+{
+    int n = 0;
+    if (!g_api.cuOccupancyMaxActiveBlocksPerMultiprocessor || g_api.cuOccupancyMaxActiveBlocksPerMultiprocessor(&n, (CUfunction)fn, block, smem) != 0 || n < 1) return 4;
+    return n;
 }
 
 int jit_launch(tgpu_ctx* ctx, void* fn, int grid, int block, size_t smem, void** params)

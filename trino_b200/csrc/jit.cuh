@@ -12,6 +12,8 @@ const char* jit_unavailable_reason();
 int jit_compile_cubin(tgpu_ctx* ctx, const std::string& body, std::string* cubin);
 // compiled + loaded + cached kernel handle (CUfunction) for the current device
 int jit_get_function(tgpu_ctx* ctx, const std::string& body, const char* kernel_name, void** fn_out);
+// CTAs of this kernel that fit one SM (grid-stride kernels are launched as exactly one resident wave)
+int jit_blocks_per_sm(void* fn, int block, size_t smem);
 int jit_launch(tgpu_ctx* ctx, void* fn, int grid, int block, size_t smem, void** params);
 
 }  // namespace tg

@@ -925,6 +925,7 @@ typedef int (*nccl_group_t)(void);
 typedef int (*nccl_all_gather_t)(const void*, void*, size_t, int, ncclComm*, cudaStream_t);
 typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, ncclComm*, cudaStream_t);
 typedef const char* (*nccl_get_error_string_t)(int);
+typedef int (*nccl_comm_split_t)(ncclComm*, int, int, ncclComm**, void*);
 
 struct NcclApi {
     void* handle = nullptr;
@@ -937,6 +938,7 @@ struct NcclApi {
     nccl_all_gather_t all_gather = nullptr;
     nccl_all_reduce_t all_reduce = nullptr;
     nccl_get_error_string_t error_string = nullptr;
+    nccl_comm_split_t comm_split = nullptr;
 };
 
 NcclApi g_nccl;
@@ -957,6 +959,7 @@ int load_nccl(tgpu_ctx* ctx)
     g_nccl.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
     g_nccl.all_reduce = (nccl_all_reduce_t)dlsym(h, "ncclAllReduce");
     g_nccl.error_string = (nccl_get_error_string_t)dlsym(h, "ncclGetErrorString");
+    g_nccl.comm_split = (nccl_comm_split_t)dlsym(h, "ncclCommSplit");   // optional (NCCL >= 2.18): split-phase exchange only
     if (!g_nccl.get_unique_id || !g_nccl.comm_init_rank || !g_nccl.send || !g_nccl.recv || !g_nccl.group_start || !g_nccl.group_end || !g_nccl.all_gather)
         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "libnccl is missing required symbols");
     g_nccl.handle = h;
@@ -977,8 +980,10 @@ constexpr int NCCL_INT64 = 4;   // ncclInt64
 
 int tg_comm_destroy_internal(tgpu_ctx* ctx)
 {
+    if (ctx->comm2 && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm2);
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
-    ctx->comm = nullptr;
+    ctx->comm = ctx->comm2 = nullptr;
+    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
     return TGPU_OK;
 }
 
@@ -1059,6 +1064,10 @@ extern "C" int tgpu_comm_init(tgpu_ctx* ctx, const uint8_t id[TGPU_COMM_ID_BYTES
     TG_NCCL(ctx, g_nccl.comm_init_rank(&ctx->comm, world, uid, rank));
     ctx->rank = rank;
     ctx->world = world;
+    // a second communicator and a side stream for the split-phase exchange: its barrier must not be ordered behind (or ahead
+    // of) the count all-gather of the next exchange, which NCCL would do for two operations on one communicator
+    if (g_nccl.comm_split && !getenv("TGPU_NO_COMM_SPLIT")) TG_NCCL(ctx, g_nccl.comm_split(ctx->comm, 0, rank, &ctx->comm2, nullptr));
+    TG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     return TGPU_OK;
 }
 
@@ -1068,12 +1077,12 @@ extern "C" int tgpu_comm_destroy(tgpu_ctx* ctx)
     return tg_comm_destroy_internal(ctx);
 }
 
-extern "C" int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[2 * TGPU_IPC_HANDLE_BYTES])
+extern "C" int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[TGPU_NUM_ARENAS * TGPU_IPC_HANDLE_BYTES])
 {
     if (!ctx || !handles_out || bytes == 0) return TGPU_ERR_INVALID_ARGUMENT;
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
     static_assert(sizeof(cudaIpcMemHandle_t) == TGPU_IPC_HANDLE_BYTES, "IPC handle size");
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < TGPU_NUM_ARENAS; k++) {
         if (ctx->arena_local[k]) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "arenas already created");
         TG_CUDA(ctx, cudaMalloc(&ctx->arena_local[k], bytes));   // plain cudaMalloc: pool memory cannot be exported
         cudaIpcMemHandle_t h;
@@ -1089,12 +1098,12 @@ extern "C" int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles)
     if (!ctx || !all_handles) return TGPU_ERR_INVALID_ARGUMENT;
     if (!ctx->arena_local[0]) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "tgpu_comm_arena_create has not been called");
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < TGPU_NUM_ARENAS; k++) {
         ctx->arena_peer[k].assign(ctx->world, nullptr);
         for (int r = 0; r < ctx->world; r++) {
             if (r == ctx->rank) { ctx->arena_peer[k][r] = ctx->arena_local[k]; continue; }
             cudaIpcMemHandle_t h;
-            memcpy(&h, all_handles + ((size_t)r * 2 + k) * TGPU_IPC_HANDLE_BYTES, TGPU_IPC_HANDLE_BYTES);
+            memcpy(&h, all_handles + ((size_t)r * TGPU_NUM_ARENAS + k) * TGPU_IPC_HANDLE_BYTES, TGPU_IPC_HANDLE_BYTES);
             TG_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->arena_peer[k][r], h, cudaIpcMemLazyEnablePeerAccess));
         }
     }
@@ -1102,6 +1111,11 @@ extern "C" int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles)
 }
 
 extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out)
+{
+    return tgpu_exchange_partitioned_fenced(ctx, partitioner, page, nullptr, out);
+}
+
+extern "C" int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_ctx* consumer, tgpu_page** out)
 {
     PartitionOp* p = dynamic_cast<PartitionOp*>(partitioner);
     if (!ctx || !p || !page || !out) return TGPU_ERR_INVALID_ARGUMENT;
@@ -1192,7 +1206,7 @@ extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, co
     };
     bool p2p = !ctx->arena_peer[0].empty() && !getenv("TGPU_EXCHANGE_NCCL");
     for (int d = 0; d < W && p2p; d++) p2p = region_off(d, lanes.size()) <= ctx->arena_bytes;
-    const int arena = (int)(ctx->arena_epoch & 1);
+    const int arena = (int)(ctx->arena_epoch % TGPU_NUM_ARENAS);
     std::vector<char*> h_dst(lanes.size() * W);
     for (size_t l = 0; l < lanes.size(); l++) {
         int es = lanes[l].elem ? lanes[l].elem : 1;
@@ -1227,6 +1241,14 @@ extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, co
     if (p2p) {
         // the rows are already in the destination arenas; a 1-element all-reduce on the stream is the barrier that tells
         // every rank that all its senders' scatter kernels have completed
+        if (consumer && consumer != ctx) {
+            // The barrier below tells every peer that it may overwrite the arena this rank's consumer read the exchange before
+            // last from: do not enter it before everything the consumer context has enqueued so far (its probe of that page)
+            // is done.  The wait is on the device - this exchange's scatter and the consumer's probe overlap.
+            if (!consumer->fence_ev) TG_CUDA(ctx, cudaEventCreateWithFlags(&consumer->fence_ev, cudaEventDisableTiming));
+            TG_CUDA(ctx, cudaEventRecord(consumer->fence_ev, consumer->stream));
+            TG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, consumer->fence_ev, 0));
+        }
         DevBuf token;
         TG_TRY(token.alloc(ctx, 16));
         TG_CUDA(ctx, cudaMemsetAsync(token.p, 0, 16, ctx->stream));
@@ -1306,5 +1328,212 @@ extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, co
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // send buffers are released after the transfers have left them
     OwnedPage* o = tg_make_owned_page(std::move(outp));
     *out = &o->hdr;
+    return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// split-phase exchange: SMs partition, copy engines move, the caller's next kernels overlap the transfer
+// ------------------------------------------------------------------------------------------------
+struct tgpu_exchange {
+    struct Lane {
+        int elem;          // element bytes (0: NULL-byte lane of a nullable column)
+        int col;
+        bool nulls;
+        DevBuf send;       // rows for peer destinations, destination-major
+    };
+    std::vector<Lane> lanes;
+    std::vector<int32_t> col_types;
+    std::vector<size_t> region_off;   // of every lane inside this rank's arena
+    int arena = 0;
+    long long total_recv = 0;
+    cudaEvent_t done = nullptr;
+    ~tgpu_exchange() { if (done) cudaEventDestroy(done); }
+};
+
+extern "C" int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_exchange** out)
+{
+    PartitionOp* p = dynamic_cast<PartitionOp*>(partitioner);
+    if (!ctx || !p || !page || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->comm) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "tgpu_comm_init has not been called");
+    if (!ctx->comm2) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "split-phase exchange needs ncclCommSplit (NCCL >= 2.18)");
+    if (ctx->arena_peer[0].empty()) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "split-phase exchange needs arenas (tgpu_comm_arena_create/open)");
+    if (ctx->exchanges_in_flight >= 2) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "more than two exchanges in flight on one context");
+    const int W = ctx->world;
+    if (p->partition_count != W) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition count %d != world size %d", p->partition_count, W);
+    if (p->null_channel >= 0 || p->replicates_any_row) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "replicating partitioners are not supported by the exchange");
+    if (W > XMAXP) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange across more than %d ranks", XMAXP);
+    const int64_t n = page->num_rows;
+    if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+    DevPage in;
+    TG_TRY(tg_ingest_page(ctx, page, &in));
+    for (auto& c : in.cols)
+        if (c.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
+    const int C = (int)in.cols.size();
+    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);
+    // 1. partition ids, histograms, offsets.  Every destination of the scatter is LOCAL memory here (send buffers and this
+    //    rank's own arena), so the warp-granular kernels apply.
+    const XchgGeom geom = xchg_geom(ctx, n, W, false);
+    const int grid = geom.nchunks;
+    DevBuf pids, hist, block_off, d_totals;
+    TG_TRY(pids.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
+    TG_TRY(hist.alloc(ctx, (size_t)grid * W * 4));
+    TG_TRY(block_off.alloc(ctx, (size_t)grid * W * 8));
+    TG_TRY(d_totals.alloc(ctx, (size_t)(W + C) * 8));
+    std::vector<long long> send_vec(W + C, 0);
+    if (n > 0) {
+        KeyCols k;
+        TG_TRY(p->key_cols(in, &k));
+        TG_TRY(xchg_launch_hist(ctx, geom, k, n, p->bucket_count, p->bucket_to_partition.empty() ? nullptr : p->d_b2p.as<int32_t>(), W, pids.as<uint8_t>(),
+                                hist.as<unsigned int>()));
+        TG_LAUNCH(ctx, xchg_offsets_kernel, W, 256, 0, hist.as<unsigned int>(), grid, W, block_off.as<long long>(), d_totals.as<long long>());
+        TG_CUDA(ctx, cudaMemcpyAsync(send_vec.data(), d_totals.p, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int c = 0; c < C; c++) send_vec[W + c] = in.cols[c].validity ? 1 : 0;
+    // 2. count matrix
+    const int V = W + C;
+    std::vector<long long> matrix((size_t)W * V);
+    DevBuf d_send, d_matrix;
+    TG_TRY(d_send.alloc(ctx, (size_t)V * 8));
+    TG_TRY(d_matrix.alloc(ctx, (size_t)W * V * 8));
+    TG_CUDA(ctx, cudaMemcpyAsync(d_send.p, send_vec.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TG_NCCL(ctx, g_nccl.all_gather(d_send.p, d_matrix.p, (size_t)V, NCCL_INT64, ctx->comm, ctx->stream));
+    TG_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)W * V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<long long> send_off(W + 1, 0), total_recv_of(W, 0);
+    for (int r = 0; r < W; r++) send_off[r + 1] = send_off[r] + send_vec[r];
+    for (int d = 0; d < W; d++)
+        for (int r = 0; r < W; r++) total_recv_of[d] += matrix[(size_t)r * V + d];
+    if (total_recv_of[ctx->rank] > (long long)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "exchange output exceeds 2^31-1 rows on rank %d", ctx->rank);
+    std::unique_ptr<tgpu_exchange> x(new tgpu_exchange());
+    x->total_recv = total_recv_of[ctx->rank];
+    x->arena = (int)(ctx->arena_epoch % TGPU_NUM_ARENAS);
+    for (int c = 0; c < C; c++) {
+        x->col_types.push_back(in.cols[c].type);
+        bool any_nulls = false;
+        for (int r = 0; r < W; r++) any_nulls = any_nulls || matrix[(size_t)r * V + W + c] != 0;
+        x->lanes.emplace_back();
+        x->lanes.back().elem = in.cols[c].elem_size();
+        x->lanes.back().col = c;
+        x->lanes.back().nulls = false;
+        if (any_nulls) {
+            x->lanes.emplace_back();
+            x->lanes.back().elem = 0;
+            x->lanes.back().col = c;
+            x->lanes.back().nulls = true;
+        }
+    }
+    const size_t L = x->lanes.size();
+    auto es_of = [&](size_t l) { return (size_t)(x->lanes[l].elem ? x->lanes[l].elem : 1); };
+    auto region_off = [&](int d, size_t lane) {
+        size_t off = 0;
+        for (size_t l = 0; l < lane; l++) off += (((size_t)total_recv_of[d] * es_of(l)) + 255) & ~(size_t)255;
+        return off;
+    };
+    for (int d = 0; d < W; d++)
+        if (region_off(d, L) > ctx->arena_bytes) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "rank %d would receive more than its arena holds", d);
+    for (size_t l = 0; l < L; l++) x->region_off.push_back(region_off(ctx->rank, l));
+    auto before_of = [&](int d) {     // rows of lower-ranked senders come first in destination d
+        long long b = 0;
+        for (int r = 0; r < ctx->rank; r++) b += matrix[(size_t)r * V + d];
+        return b;
+    };
+    // 3. scatter: peer-bound rows into send buffers (destination-major), rows that stay into their final place
+    std::vector<char*> h_dst(L * W);
+    std::vector<const void*> srcs(L);
+    for (size_t l = 0; l < L; l++) {
+        const size_t es = es_of(l);
+        TG_TRY(x->lanes[l].send.alloc(ctx, (size_t)std::max<int64_t>(n, 1) * es));
+        const DevColumn& col = in.cols[x->lanes[l].col];
+        srcs[l] = x->lanes[l].nulls ? (const void*)col.validity : col.data;
+        for (int d = 0; d < W; d++) h_dst[l * W + d] = (char*)x->lanes[l].send.p + (size_t)send_off[d] * es;
+        h_dst[l * W + ctx->rank] = (char*)ctx->arena_local[x->arena] + x->region_off[l] + (size_t)before_of(ctx->rank) * es;
+    }
+    DevBuf d_dst;
+    TG_TRY(d_dst.alloc(ctx, h_dst.size() * sizeof(char*)));
+    TG_CUDA(ctx, cudaMemcpyAsync(d_dst.p, h_dst.data(), h_dst.size() * sizeof(char*), cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        XchgCols xc;
+        memset(&xc, 0, sizeof(xc));
+        xc.count = (int32_t)L;
+        for (size_t l = 0; l < L; l++) { xc.elem[l] = x->lanes[l].elem; xc.src[l] = srcs[l]; }
+        xc.dst = d_dst.as<char*>();
+        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc, false));
+    }
+    // 4. hand over to the copy engines.  The event also orders the transfer behind everything enqueued on this context so far:
+    //    the readers of the arena this exchange's peers will overwrite NEXT (see the header).
+    TG_CUDA(ctx, cudaEventCreateWithFlags(&x->done, cudaEventDisableTiming));
+    TG_CUDA(ctx, cudaEventRecord(x->done, ctx->stream));
+    TG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, x->done, 0));
+    for (int step = 1; step < W; step++) {
+        const int d = (ctx->rank + step) % W;          // staggered: at any moment every receiver has one sender per step
+        if (send_vec[d] == 0) continue;
+        for (size_t l = 0; l < L; l++) {
+            const size_t es = es_of(l);
+            char* dst = (char*)ctx->arena_peer[x->arena][d] + region_off(d, l) + (size_t)before_of(d) * es;
+            const char* src = (const char*)x->lanes[l].send.p + (size_t)send_off[d] * es;
+            TG_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)send_vec[d] * es, cudaMemcpyDefault, ctx->copy_stream));
+        }
+    }
+    // 5. barrier: when it completes here, every peer's copies into this rank's arena have completed
+    DevBuf token;
+    TG_TRY(token.alloc(ctx, 16));
+    TG_CUDA(ctx, cudaMemsetAsync(token.p, 0, 16, ctx->copy_stream));
+    TG_NCCL(ctx, g_nccl.all_reduce(token.p, (char*)token.p + 8, 1, NCCL_INT64, 0 /* ncclSum */, ctx->comm2, ctx->copy_stream));
+    TG_CUDA(ctx, cudaEventRecord(x->done, ctx->copy_stream));
+    // temporaries of this function (pids, histograms, pointer table) are released in stream order on ctx->stream, behind the
+    // scatter; the send buffers and the barrier token are used by the copy stream and live in the handle until _end
+    x->lanes.emplace_back();                               // park the token in a pseudo lane
+    x->lanes.back().elem = -1;
+    x->lanes.back().col = -1;
+    x->lanes.back().nulls = false;
+    x->lanes.back().send = std::move(token);
+    ctx->arena_epoch++;
+    ctx->exchanges_in_flight++;
+    *out = x.release();
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_exchange_end(tgpu_ctx* ctx, tgpu_exchange* exchange, tgpu_page** out)
+{
+    if (!ctx || !exchange || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    std::unique_ptr<tgpu_exchange> x(exchange);
+    ctx->exchanges_in_flight--;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the received rows are complete once this rank's barrier has run; everything below is ordered behind it on ctx->stream
+    TG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, x->done, 0));
+    DevPage outp;
+    outp.rows = x->total_recv;
+    outp.cols.resize(x->col_types.size());
+    size_t li = 0;
+    for (auto& lane : x->lanes) {
+        if (lane.col < 0) continue;
+        DevColumn& dst = outp.cols[lane.col];
+        char* region = (char*)ctx->arena_local[x->arena] + x->region_off[li++];
+        if (!lane.nulls) {
+            dst.type = x->col_types[lane.col];
+            dst.length = x->total_recv;
+            dst.data = region;     // aliases the arena: valid until the third-next exchange on this context
+        }
+        else if (x->total_recv > 0) {
+            tgpu_column bytemap_col;
+            memset(&bytemap_col, 0, sizeof(bytemap_col));
+            bytemap_col.type = TGPU_INT8;
+            bytemap_col.flags = TGPU_COL_NULLS_BYTEMAP;
+            bytemap_col.length = x->total_recv;
+            bytemap_col.data = region;
+            bytemap_col.validity = (const uint8_t*)region;
+            DevColumn packed;
+            TG_TRY(tg_ingest_column(ctx, &bytemap_col, true, &packed));
+            dst.own_validity = packed.own_validity;
+            dst.validity = packed.validity;
+        }
+    }
+    OwnedPage* po = tg_make_owned_page(std::move(outp));
+    *out = &po->hdr;
+    // the send buffers are returned to this context's allocator here: their next use is ordered behind the wait above
     return TGPU_OK;
 }
