@@ -29,6 +29,10 @@ SEED_LINEITEM, SEED_ORDERS = 0x7C01, 0x7C02
 ALG_BYTES_PROBE_INDEX = 24          # 8 key + 12 table entry + 4 position
 ALG_BYTES_PROBE_FUSED = 40          # fused probe + gather, this workload: 24 + 8 build payload read + 8 written (probe columns pass through by reference)
 ALG_BYTES_Q1_CODES = 38             # shipdate 4 + 4 x FLOAT64 32 + 2 INT8 key codes
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r01_kernels.md),
+# quoted only for the configuration they were captured on
+NCU_TRAFFIC_PROBE_FUSED_SF100 = 18.515783e9 + 7.239862e9     # 600 000 003 rows: 42.9 B/row
+NCU_TRAFFIC_Q1_SF300 = 68.633669e9 + 4.425216e6               # 1.8 G rows: 38.1 B/row
 
 
 def measured_peak():
@@ -371,7 +375,9 @@ def main():
         kms = float(np.mean(kernel_ms))
         achieved = ALG_BYTES_PROBE_FUSED * l_count / (kms * 1e-3) / 1e9
         roofline = {"kernel": "join_probe_lean_kernel<1,true> (fused probe + payload gather)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "rows_per_launch": l_count,
+                    "traffic": NCU_TRAFFIC_PROBE_FUSED_SF100 if (args.sf == 100.0 and not args.shuffle_probe) else None,
+                    "traffic_source": "ncu --set full capture of this kernel on this configuration, profiles/r01_kernels.md (bytes per launch)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "rows_per_launch": l_count,
                     "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step, "launches_timed": len(kernel_ms)}
         d_pos = ctx.malloc(l_count * 4)
         keys_page = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_lkeys, l_count)], l_count)
@@ -451,6 +457,9 @@ def bench_e2e(ctx, args, bridge, d_keys, d_price, n, drivers=4):
     ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(h_keys.ctypes.data), C.c_void_p(d_keys), total * 8))
     ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(h_price.ctypes.data), C.c_void_p(d_price), total * 8))
     chunks = [(lo, min(total, lo + chunk)) for lo in range(0, total, chunk)]
+    # probe blocks the join passes through (here: both probe channels; the join is 1:1) are views of the caller's blocks, as in
+    # LookupJoinPageBuilder.build: only the join key crosses PCIe on the way in, only the build payload on the way out
+    by_reference = not os.environ.get("TGPU_E2E_MATERIALIZE")
     d2h_bytes = [0]
     rows_out = [0]
     lock = threading.Lock()
@@ -459,6 +468,8 @@ def bench_e2e(ctx, args, bridge, d_keys, d_price, n, drivers=4):
         def __init__(self, index):
             self.ctx = ops.Context(ctx.device)
             self.op = ops.LookupJoinOperatorFactory(self.ctx, bridge, abi.JOIN_INNER, False, [0], [0, 1]).create_operator()
+            if by_reference:
+                self.op.set_passthrough_by_reference(True)
             # result landing zone (pinned): probe key, probe price, build payload
             self.bufs = [self.ctx.pinned_empty(chunk, np.int64), self.ctx.pinned_empty(chunk, np.float64), self.ctx.pinned_empty(chunk, np.int64)]
             self.valid = [np.empty(chunk // 8 + 8, np.uint8) for _ in range(3)]
@@ -516,10 +527,11 @@ def bench_e2e(ctx, args, bridge, d_keys, d_price, n, drivers=4):
     d0 = ds[0]
     lo, hi = d0.mine[-1]
     assert (d0.bufs[2][:8] == (h_keys[lo:lo + 8] % 2557)).all()
-    out = {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": int(total * 16), "d2h_bytes_per_step": int(d2h_bytes[0]),
+    out = {"value": total / dt, "unit": "rows/s", "h2d_bytes_per_step": int(total * (8 if by_reference else 16)), "d2h_bytes_per_step": int(d2h_bytes[0]),
            "rows_per_step": int(total), "host_page_rows": chunk, "drivers": drivers,
            "timing": "wall clock around add_input(host page) + get_output + page_copy_to_host on every driver thread, pinned memory; "
-                     "pass-through probe blocks are not copied back"}
+                     "pass-through probe blocks are not copied back" + (" and, being views of the caller's blocks, not uploaded either "
+                     "(tgpu_join_probe_set_passthrough_by_reference): H2D = join key, D2H = build payload" if by_reference else "")}
     for d in ds:
         d.op.close()
         d.ctx.close()
@@ -565,7 +577,8 @@ def bench_q1(ctx, args):
     return {"metric": "groupby_input_rows_per_sec", "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "rows": n, "groups": len(rows),
             "config": f"TPC-H Q1 GROUP-BY, synthetic SF{args.q1_sf:g} lineitem, INT8 key codes, fused filter+project+aggregate (BASELINE.json configs[2])",
             "roofline": {"kernel": "tg_agg_small_jit", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_Q1_CODES, "traffic": None, "kernel_ms": kms,
+                         "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_Q1_CODES,
+                         "traffic": NCU_TRAFFIC_Q1_SF300 if args.q1_sf == 300.0 else None, "kernel_ms": kms,
                          "kernel_share_of_step": kms / ms},
             "result_count_order": [int(r[-1]) for r in rows]}
 

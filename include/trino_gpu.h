@@ -285,6 +285,13 @@ int64_t tgpu_lookup_position_count(const tgpu_lookup* lookup);   /* LookupSource
 int64_t tgpu_lookup_memory_bytes(const tgpu_lookup* lookup);     /* getInMemorySizeInBytes */
 int tgpu_lookup_has_duplicates(const tgpu_lookup* lookup);       /* !positionLinks.isEmpty() */
 int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec* spec, tgpu_lookup* lookup, tgpu_op** out);
+/* LookupJoinPageBuilder.build (M/operator/join/LookupJoinPageBuilder.java:144-150) returns the probe blocks themselves when
+ * every probe row produced exactly one output row.  With this switch on, a HOST probe page only has its join-key channel
+ * uploaded; when the output is such a 1:1 page its pass-through columns carry no device data (data == NULL): the caller
+ * substitutes its own input blocks (tgpu_page_passthrough_channel) and passes data == NULL for them to
+ * tgpu_page_copy_to_host.  When rows were dropped or repeated the remaining channels are uploaded after all and the output is
+ * complete.  Off by default (every output column is materialised on the device); single-channel BIGINT-family keys only. */
+int tgpu_join_probe_set_passthrough_by_reference(tgpu_op* probe, int32_t enable);
 
 /* LookupSource.getJoinPosition(int[] positions, Page hashChannelsPage, Page allChannelsPage, long[] result)
  * (M/operator/join/JoinHash.java:100-143): for every row of `keys_page` (only the key columns, in

@@ -32,7 +32,7 @@ def oracle_join_rows(build_page, probe_page, build_key, probe_key, probe_out, bu
     return rows
 
 
-def gpu_join_rows(ctx, build_pages, probe_pages, build_key, probe_key, probe_out, build_out, join_type, single_match):
+def gpu_join_rows(ctx, build_pages, probe_pages, build_key, probe_key, probe_out, build_out, join_type, single_match, by_reference=False):
     from trino_b200 import operators as ops
     bridge = ops.JoinBridge()
     bk = list(build_key) if isinstance(build_key, (list, tuple)) else [build_key]
@@ -46,6 +46,8 @@ def gpu_join_rows(ctx, build_pages, probe_pages, build_key, probe_key, probe_out
     assert b.is_finished()
     pf = ops.LookupJoinOperatorFactory(ctx, bridge, join_type, single_match, pk, probe_out)
     j = pf.create_operator()
+    if by_reference:
+        j.set_passthrough_by_reference(True)
     out = ops.drive(j, probe_pages)
     rows = []
     for page in out:

@@ -205,3 +205,28 @@ def test_generic_lookup_positions_api(ctx):
     assert list(pos) == [2, -1, 3, 1, -1]
     assert lk.has_position_links() and list(lk.position_links()) == [-1, -1, 0, -1]
     b.close(); lk.close()
+
+
+@pytest.mark.parametrize("join_type", [abi.JOIN_INNER, abi.JOIN_PROBE_OUTER])
+@pytest.mark.parametrize("shape", ["all_match", "misses", "null_keys", "duplicates"])
+def test_probe_blocks_by_reference(ctx, join_type, shape):
+    """LookupJoinPageBuilder.java:144-150: a 1:1 output returns the probe blocks themselves.  With by-reference on, only the join
+    key of a host probe page is uploaded; outputs must be identical to the materialising default in every shape (rows dropped,
+    NULL keys, duplicate build keys force the remaining channels to be uploaded after all)."""
+    rng = np.random.default_rng(len(shape) + join_type)
+    nb, npr = 5000, 20000
+    bkeys = rng.permutation(nb * 2)[:nb].astype(np.int64)
+    if shape == "duplicates":
+        bkeys[: nb // 10] = bkeys[nb // 10: 2 * (nb // 10)]
+    build = Page(Block.bigint(bkeys), Block.bigint(bkeys * 7), Block.double(bkeys * 0.5))
+    pkeys = rng.choice(bkeys, npr) if shape in ("all_match", "duplicates") else rng.integers(0, nb * 2, npr)
+    knull = rng.random(npr) < 0.05 if shape == "null_keys" else None
+    probes = [Page(Block.double(rng.normal(size=m), rng.random(m) < 0.1), Block.bigint(pkeys[a:a + m], None if knull is None else knull[a:a + m]),
+                   Block.varchar(["s%d" % i if i % 7 else None for i in range(m)]))
+              for a, m in ((0, 12000), (12000, 8000))]
+    want = []
+    for p in probes:
+        want.extend(oracle_join_rows(build, p, 0, 1, [2, 0, 1], [1, 2], join_type, False))
+    got = gpu_join_rows(ctx, [build], probes, 0, 1, [2, 0, 1], [1, 2], join_type, False, by_reference=True)
+    assert got == want
+    assert got == gpu_join_rows(ctx, [build], probes, 0, 1, [2, 0, 1], [1, 2], join_type, False)

@@ -204,6 +204,7 @@ SIGNATURES = {
     "tgpu_page_release": (None, [VP, PP]),
     "tgpu_page_copy_to_host": (C.c_int, [VP, PP, PP]),
     "tgpu_page_utf8_bytes": (C.c_int64, [VP, PP, C.c_int32]),
+    "tgpu_join_probe_set_passthrough_by_reference": (C.c_int, [VP, C.c_int32]),
     "tgpu_page_passthrough_channel": (C.c_int, [PP, C.c_int32, C.POINTER(C.c_int32)]),
     "tgpu_synth_orders_keys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, VP]),
     "tgpu_synth_lineitem_rows": (C.c_int64, [C.c_int64]),

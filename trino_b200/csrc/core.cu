@@ -733,6 +733,8 @@ extern "C" int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* dp, tgpu_p
         h.type = d.type;
         h.length = n;
         if (!h.data) continue;   // the caller does not want this column (e.g. a pass-through block it already holds)
+        if (!d.data && n > 0 && d.type != TGPU_UTF8)
+            return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "column %d is a by-reference view of an input block (tgpu_page_passthrough_channel): it has no device data", c);
         if (d.type == TGPU_UTF8) {
             TG_CUDA(ctx, cudaMemcpyAsync((void*)h.offsets, d.offsets, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

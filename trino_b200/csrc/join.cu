@@ -909,6 +909,10 @@ struct JoinProbeOp : tgpu_op {
         int64_t n = 0;
     } deferred;
     DevBuf match_counter;     // per operator: the count must survive until get_output
+    // LookupJoinPageBuilder.build :144-150 hands probe blocks through as views.  With by_reference set, a HOST probe page
+    // only has its join-key channel uploaded; pass-through output columns of the result then carry no device data
+    // (data == NULL, tgpu_page_passthrough_channel names the input block) unless rows had to be dropped or repeated
+    bool by_reference = false;
 
     JoinProbeOp(tgpu_ctx* c, tgpu_lookup* lk) : tgpu_op(c), lookup(lk) { lookup->refs++; }
     ~JoinProbeOp() override
@@ -994,7 +998,40 @@ struct JoinProbeOp : tgpu_op {
     }
 
     // second half of the fast path: read the match count and shape the output page
-    int complete_fast()
+    // partial ingest of a host page: the join-key channel goes to the device, the others stay placeholders
+    int ingest_keys_only(const tgpu_page* page, DevPage* out)
+    {
+        DevPage p;
+        p.rows = page->num_rows;
+        p.cols.resize(page->num_columns);
+        for (int32_t c = 0; c < page->num_columns; c++) {
+            if (page->columns[c].length != page->num_rows) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "column %d has %lld positions, page has %lld", c,
+                                                                          (long long)page->columns[c].length, (long long)page->num_rows);
+            bool is_key = c == key_channels[0];
+            if (is_key) TG_TRY(tg_ingest_column(ctx, &page->columns[c], false, &p.cols[c]));
+            else { p.cols[c].type = page->columns[c].type; p.cols[c].length = page->num_rows; }
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *out = std::move(p);
+        return TGPU_OK;
+    }
+
+    static bool absent(const DevColumn& c) { return c.data == nullptr && c.length > 0; }
+
+    int upload_absent(const tgpu_page* page, DevPage* in)
+    {
+        bool any = false;
+        for (int32_t c = 0; c < page->num_columns; c++) {
+            if (!absent(in->cols[c])) continue;
+            TG_TRY(tg_ingest_column(ctx, &page->columns[c], false, &in->cols[c]));
+            any = true;
+        }
+        if (any) TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return TGPU_OK;
+    }
+
+    // `host_page`: the input of a by-reference probe (its pass-through channels were not uploaded), else nullptr
+    int complete_fast(const tgpu_page* host_page = nullptr)
     {
         deferred.active = false;
         DevPage in = std::move(deferred.in);
@@ -1005,6 +1042,7 @@ struct JoinProbeOp : tgpu_op {
         int64_t matches = 0;
         TG_TRY(tg_read_i64(ctx, match_counter.as<int64_t>(), &matches));
         DevPage outp;
+        if (host_page && !(matches == n || outer) && matches > 0) TG_TRY(upload_absent(host_page, &in));   // rows are dropped: the gather needs them
         if (matches == n || outer) {
             // every probe row yields exactly one output row: probe blocks pass through
             // (LookupJoinPageBuilder.build :144-150 "outputProbeBlocksDirectly")
@@ -1062,7 +1100,9 @@ struct JoinProbeOp : tgpu_op {
         if (n == 0) return TGPU_OK;
         if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
         DevPage in;
-        TG_TRY(tg_ingest_page(ctx, page, &in));
+        const bool lazy = by_reference && !(page->flags & TGPU_PAGE_DEVICE) && !lookup->generic && key_channels.size() == 1;
+        if (lazy) TG_TRY(ingest_keys_only(page, &in));
+        else TG_TRY(tg_ingest_page(ctx, page, &in));
         if (key_channels[0] < 0 || key_channels[0] >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key channel out of range");
         for (int32_t ch : output_channels)
             if (ch < 0 || ch >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe output channel out of range");
@@ -1073,8 +1113,9 @@ struct JoinProbeOp : tgpu_op {
         if (!lookup->generic && !getenv("TGPU_JOIN_GENERAL_PATH")) {
             bool handled = false;
             TG_TRY(fast_path(in, key, n, &handled));
-            if (handled) return TGPU_OK;
+            if (handled) return lazy ? complete_fast(page) : TGPU_OK;   // host buffers are the caller's again after this call
         }
+        if (lazy) TG_TRY(upload_absent(page, &in));
         // joinPositionCache (JoinProbe.java:112-180)
         auto jp = std::make_shared<DevBuf>();
         TG_TRY(jp->alloc(ctx, (size_t)(n + 1) * 4));
@@ -1206,6 +1247,14 @@ extern "C" int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec*
     op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
     op->output_channels.assign(spec->output_channels, spec->output_channels + spec->num_output_channels);
     *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_join_probe_set_passthrough_by_reference(tgpu_op* op, int32_t enable)
+{
+    JoinProbeOp* p = dynamic_cast<JoinProbeOp*>(op);
+    if (!p) return TGPU_ERR_INVALID_ARGUMENT;
+    p->by_reference = enable != 0;
     return TGPU_OK;
 }
 

@@ -108,8 +108,9 @@ class Context:
         return ms.value
 
     # ---- output pages
-    def page_to_host(self, pp, release=True):
-        """device tgpu_page* -> host Page (numpy)."""
+    def page_to_host(self, pp, release=True, views_of=None):
+        """device tgpu_page* -> host Page (numpy).  `views_of`: the host input Page of a by-reference probe; output columns
+        without device data are views of its blocks (tgpu_page_passthrough_channel)."""
         dp = pp.contents
         n = dp.num_rows
         host_cols = (abi.Column * max(1, dp.num_columns))()
@@ -119,6 +120,14 @@ class Context:
             h = host_cols[c]
             h.type = d.type
             h.length = n
+            if views_of is not None and n > 0 and not d.data:
+                src = C.c_int32(-1)
+                self.check(self.lib.tgpu_page_passthrough_channel(pp, c, C.byref(src)))
+                if src.value < 0:
+                    raise RuntimeError(f"output column {c} has no device data and is not a pass-through view")
+                h.data = None
+                keep.append(("view", views_of.get_block(src.value), None, None))
+                continue
             valid = np.empty((n + 7) // 8 + 1, dtype=np.uint8)
             h.validity = valid.ctypes.data
             if d.type == abi.UTF8:
@@ -140,6 +149,9 @@ class Context:
         self.check(self.lib.tgpu_page_copy_to_host(self.h, pp, C.byref(hp)))
         blocks = []
         for type_, data, valid, offs in keep:
+            if type_ == "view":
+                blocks.append(data)
+                continue
             bits = np.unpackbits(valid, bitorder="little")[:n].astype(np.bool_)
             nulls = ~bits
             blocks.append(Block(type_, data, nulls if nulls.any() else None, offs))
@@ -219,7 +231,13 @@ class Operator:
 
     def add_input(self, page):
         ap = _as_abi_page(page)
+        self._last_input = page
         self.ctx.check(self.ctx.lib.tgpu_op_add_input(self.h, ap.ref()))
+
+    def set_passthrough_by_reference(self, enable=True):
+        """LookupJoinOperator only: host probe pages upload their join key alone; 1:1 outputs return the input blocks as views"""
+        self.ctx.check(self.ctx.lib.tgpu_join_probe_set_passthrough_by_reference(self.h, int(enable)))
+        self._by_reference = bool(enable)
 
     def get_output_device(self):
         pp = abi.PP()
@@ -229,7 +247,10 @@ class Operator:
     def get_output(self):
         pp = abi.PP()
         self.ctx.check(self.ctx.lib.tgpu_op_get_output(self.h, C.byref(pp)))
-        return self.ctx.page_to_host(pp) if pp else None
+        views = getattr(self, "_last_input", None) if getattr(self, "_by_reference", False) else None
+        if views is not None and not hasattr(views, "get_block"):
+            views = None      # device-resident input pages are never by-reference
+        return self.ctx.page_to_host(pp, views_of=views) if pp else None
 
     def finish(self):
         self.ctx.check(self.ctx.lib.tgpu_op_finish(self.h))
