@@ -433,7 +433,7 @@ def main():
     return 0
 
 
-def bench_e2e(ctx, args, bridge, d_keys, d_price, n, drivers=4):
+def bench_e2e(ctx, args, bridge, d_keys, d_price, n, drivers=int(os.environ.get("TGPU_E2E_DRIVERS", "4"))):
     """host -> device -> host through add_input / get_output / page_copy_to_host with pinned host memory.
     `drivers` probe operators run concurrently, each on its own context/stream, sharing the lookup source — the shape of a
     Trino task (task.concurrency drivers over one PartitionedLookupSourceFactory).  Probe blocks that the operator passes

@@ -256,7 +256,9 @@ int tgpu_groupby_hash_get_group_ids(tgpu_op* op, const tgpu_page* page, int32_t*
  * LookupJoinPageBuilder (LookupJoinPageBuilder.java:89-160).                                     */
 typedef enum tgpu_join_type {  /* M/operator/join/LookupJoinOperatorFactory.JoinType */
     TGPU_JOIN_INNER = 0,
-    TGPU_JOIN_PROBE_OUTER = 1
+    TGPU_JOIN_PROBE_OUTER = 1,
+    TGPU_JOIN_LOOKUP_OUTER = 2,   /* JoinOperatorType.lookupOuterJoin: INNER on the probe side + visited build positions */
+    TGPU_JOIN_FULL_OUTER = 3      /* JoinOperatorType.fullOuterJoin: PROBE_OUTER on the probe side + visited build positions */
 } tgpu_join_type;
 
 typedef struct tgpu_join_build_spec {
@@ -292,6 +294,25 @@ int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec* spec, tgpu
  * tgpu_page_copy_to_host.  When rows were dropped or repeated the remaining channels are uploaded after all and the output is
  * complete.  Off by default (every output column is materialised on the device); single-channel BIGINT-family keys only. */
 int tgpu_join_probe_set_passthrough_by_reference(tgpu_op* probe, int32_t enable);
+
+/* LookupOuterOperator (M/operator/join/LookupOuterOperator.java:170-206, OuterLookupSource.java:109-196): a source operator
+ * that, once every LOOKUP_OUTER / FULL_OUTER probe of `lookup` has finished (the caller's outerPositionsFuture), returns the build
+ * rows no probe emitted, in build position order: `num_probe_outputs` all-NULL columns of the given tgpu_type, then the build
+ * output channels.  One page; getOutput then returns NULL and isFinished is true. */
+int tgpu_join_outer_create(tgpu_ctx* ctx, tgpu_lookup* lookup, const int32_t* probe_output_types, int32_t num_probe_outputs, tgpu_op** out);
+
+/* HashSemiJoinOperator (M/operator/HashSemiJoinOperator.java:155-201): `lookup` is built by a hash builder over the filtering
+ * source's join channel (SetBuilderOperator's ChannelSet; no output channels needed).  Output = the input page's columns + one
+ * BOOLEAN (TGPU_INT8) column: NULL probe key -> false if the set is empty else NULL; otherwise contained -> true, not contained ->
+ * NULL if the set holds a NULL else false.  DOUBLE keys: TGPU_ERR_NOT_SUPPORTED. */
+int tgpu_semi_join_create(tgpu_ctx* ctx, tgpu_lookup* lookup, int32_t probe_join_channel, tgpu_op** out);
+
+/* DynamicFilterSourceOperator / JoinDomainBuilder (M/operator/DynamicFilterSourceOperator.java, M/operator/JoinDomainBuilder.java):
+ * the domain of the build-side join key read off the finished table: min, max and number of distinct non-NULL keys, and the keys
+ * themselves (ascending) when there are at most `max_values` of them (distinct_out > max_values: only min/max are meaningful, the
+ * reference's fallback to a range).  Single BIGINT-family key only. */
+int tgpu_lookup_key_domain(tgpu_ctx* ctx, tgpu_lookup* lookup, int64_t max_values, int64_t* min_out, int64_t* max_out, int64_t* distinct_out,
+                           int64_t* values_out, int32_t* has_null_out);
 
 /* LookupSource.getJoinPosition(int[] positions, Page hashChannelsPage, Page allChannelsPage, long[] result)
  * (M/operator/join/JoinHash.java:100-143): for every row of `keys_page` (only the key columns, in

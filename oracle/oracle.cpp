@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_set>
 #include <thread>
 #include <vector>
 
@@ -692,7 +693,9 @@ int64_t orc_join_expand(const orc_join* j, const int32_t* jp, int64_t n, int32_t
 {
     // PageJoiner.processProbe :138-163, joinCurrentPosition :203-227, outerJoinCurrentPosition :234-242
     int64_t count = 0;
-    bool outer = join_type == TGPU_JOIN_PROBE_OUTER;
+    // lookupOuterJoin probes like INNER, fullOuterJoin like PROBE_OUTER (M/operator/JoinOperatorType.java); the build rows they
+    // emit are the "visited" positions of OuterLookupSource.java:168-196
+    bool outer = join_type == TGPU_JOIN_PROBE_OUTER || join_type == TGPU_JOIN_FULL_OUTER;
     for (int64_t i = 0; i < n; i++) {
         int32_t pos = jp[i];
         bool produced = false;
@@ -1046,3 +1049,30 @@ int32_t orc_hardware_threads(void)
 }
 
 }  // extern "C"
+
+
+// ---- HashSemiJoinOperator -------------------------------------------------------------------------------------------------
+// M/operator/HashSemiJoinOperator.java:181-199; the set is SetBuilderOperator's ChannelSet (FlatSet.java:120-153)
+extern "C" void orc_semi_join_bigint(const int64_t* set_values, const uint8_t* set_validity, int64_t set_rows, const int64_t* probe, const uint8_t* probe_validity,
+                                     int64_t probe_rows, int8_t* out_value, uint8_t* out_null)
+{
+    std::unordered_set<int64_t> set;
+    bool has_null = false;
+    for (int64_t i = 0; i < set_rows; i++) {
+        bool valid = !set_validity || ((set_validity[i >> 3] >> (i & 7)) & 1);
+        if (!valid) has_null = true;          // FlatSet.add :146-153
+        else set.insert(set_values[i]);
+    }
+    const bool empty = set.empty() && !has_null;   // FlatSet.size :120-123 counts the NULL
+    for (int64_t i = 0; i < probe_rows; i++) {
+        bool valid = !probe_validity || ((probe_validity[i >> 3] >> (i & 7)) & 1);
+        if (!valid) {
+            out_value[i] = 0;
+            out_null[i] = empty ? 0 : 1;      // :184-190
+            continue;
+        }
+        bool contains = set.count(probe[i]) != 0;
+        if (!contains && has_null) { out_value[i] = 0; out_null[i] = 1; }   // :193-195
+        else { out_value[i] = contains ? 1 : 0; out_null[i] = 0; }
+    }
+}

@@ -83,6 +83,12 @@ void orc_join_positions(const orc_join* j, const tgpu_page* probe, const int32_t
  * Returns the number of pairs (call with capacity 0 to count). */
 int64_t orc_join_expand(const orc_join* j, const int32_t* join_positions, int64_t num_probe_rows, int32_t join_type, int32_t single_match,
                         int32_t* out_probe, int32_t* out_build, int64_t capacity);
+
+/* HashSemiJoinOperator.process (M/operator/HashSemiJoinOperator.java:181-199) over a ChannelSet of BIGINT values
+ * (M/operator/ChannelSet.java:43-61, FlatSet.java:120-153: size counts the NULL once).  validity: Arrow bitmaps or NULL.
+ * out_value[i] = the BOOLEAN, out_null[i] = 1 when the result is NULL. */
+void orc_semi_join_bigint(const int64_t* set_values, const uint8_t* set_validity, int64_t set_rows, const int64_t* probe, const uint8_t* probe_validity,
+                          int64_t probe_rows, int8_t* out_value, uint8_t* out_null);
 /* multi-threaded probe timing leg for the CPU baseline: `threads` workers each take 8192-row pages
  * (BigintPagesHash.getAddressIndex(int[],Page) 3-phase batching); returns seconds */
 double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_t n, int32_t threads, int32_t* out,

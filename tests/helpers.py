@@ -32,6 +32,27 @@ def oracle_join_rows(build_page, probe_page, build_key, probe_key, probe_out, bu
     return rows
 
 
+def join_type_of(case):
+    from trino_b200 import abi
+    return {"inner": abi.JOIN_INNER, "lookup_outer": abi.JOIN_LOOKUP_OUTER, "full_outer": abi.JOIN_FULL_OUTER}.get(case["join_type"], abi.JOIN_PROBE_OUTER)
+
+
+def oracle_outer_rows(build_page, probe_pages, build_key, probe_key, num_probe_out, build_out, join_type, single_match):
+    """Rows of the LookupOuterOperator after all probe pages: unvisited build positions in order (OuterLookupSource.java:109-139)"""
+    import oracle_lib as o
+    bk = list(build_key) if isinstance(build_key, (list, tuple)) else [build_key]
+    pk = list(probe_key) if isinstance(probe_key, (list, tuple)) else [probe_key]
+    j = o.Join(build_page, bk)
+    visited = set()
+    for p in probe_pages:
+        pos = j.positions(p, pk)
+        _, bi = j.expand(pos, join_type, single_match)
+        visited.update(int(b) for b in bi if b >= 0)
+    j.close()
+    bcols = [build_page.get_block(c).flatten().to_pylist() for c in build_out]
+    return [tuple([None] * num_probe_out) + tuple(c[b] for c in bcols) for b in range(build_page.position_count) if b not in visited]
+
+
 def gpu_join_rows(ctx, build_pages, probe_pages, build_key, probe_key, probe_out, build_out, join_type, single_match, by_reference=False):
     from trino_b200 import operators as ops
     bridge = ops.JoinBridge()

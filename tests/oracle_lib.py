@@ -65,6 +65,7 @@ def load():
         "orc_join_copy_links": (None, [VP, VP]),
         "orc_join_positions": (None, [VP, PP, VP, VP]),
         "orc_join_expand": (C.c_int64, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP, C.c_int64]),
+        "orc_semi_join_bigint": (None, [VP, VP, C.c_int64, VP, VP, C.c_int64, VP, VP]),
         "orc_join_probe_timed": (C.c_double, [VP, VP, C.c_int64, C.c_int32, VP, VP, VP]),
         "orc_partition_ids": (None, [PP, VP, C.c_int32, C.c_int32, VP, VP]),
         "orc_partition_positions": (None, [PP, VP, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
@@ -236,3 +237,16 @@ def q1_run(cols, cutoff, threads):
 
 def hardware_threads():
     return load().orc_hardware_threads()
+
+
+def semi_join_bigint(set_block, probe_block):
+    """rows of the BOOLEAN column HashSemiJoinOperator appends: True / False / None"""
+    lib = load()
+    sv = np.ascontiguousarray(set_block.values, dtype=np.int64)
+    pv = np.ascontiguousarray(probe_block.values, dtype=np.int64)
+    svalid = None if set_block.nulls is None else np.packbits(~set_block.nulls, bitorder="little")
+    pvalid = None if probe_block.nulls is None else np.packbits(~probe_block.nulls, bitorder="little")
+    val = np.zeros(max(len(pv), 1), dtype=np.int8)
+    isnull = np.zeros(max(len(pv), 1), dtype=np.uint8)
+    lib.orc_semi_join_bigint(_p(sv), _p(svalid), len(sv), _p(pv), _p(pvalid), len(pv), _p(val), _p(isnull))
+    return [None if isnull[i] else bool(val[i]) for i in range(len(pv))]

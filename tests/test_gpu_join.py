@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as o
-from helpers import gpu_join_rows, oracle_join_rows, reference_cases, rows_equal
+from helpers import join_type_of, oracle_outer_rows, gpu_join_rows, oracle_join_rows, reference_cases, rows_equal
 from trino_b200 import abi
 from trino_b200 import operators as ops
 from trino_b200.page import Block, DictionaryBlock, Page, RunLengthEncodedBlock
@@ -24,7 +24,7 @@ def test_reference_join_cases(ctx):
     for case in reference_cases()["join"]:
         build = Page(Block.bigint(case["build"])) if case["build"] else Page(Block.bigint([]), position_count=0)
         probe = Page(Block.bigint(case["probe"]))
-        jt = abi.JOIN_INNER if case["join_type"] == "inner" else abi.JOIN_PROBE_OUTER
+        jt = join_type_of(case)
         rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0], [0], jt, case["single_match"])
         assert rows == [tuple(r) for r in case["expected"]], case["source"]
 
@@ -230,3 +230,117 @@ def test_probe_blocks_by_reference(ctx, join_type, shape):
     got = gpu_join_rows(ctx, [build], probes, 0, 1, [2, 0, 1], [1, 2], join_type, False, by_reference=True)
     assert got == want
     assert got == gpu_join_rows(ctx, [build], probes, 0, 1, [2, 0, 1], [1, 2], join_type, False)
+
+
+def _types_of(page, channels):
+    return [page.get_block(c).flatten().type for c in channels]
+
+
+@pytest.mark.parametrize("join_type", [abi.JOIN_LOOKUP_OUTER, abi.JOIN_FULL_OUTER])
+@pytest.mark.parametrize("single", [False, True])
+def test_lookup_outer_and_full_outer(ctx, join_type, single):
+    """JoinOperatorType.lookupOuterJoin / fullOuterJoin: the probe side behaves like INNER / PROBE_OUTER and marks the build
+    positions it emits (OuterLookupSource.java:95-100); the LookupOuterOperator then returns the unvisited build rows in position
+    order with NULL probe channels (LookupOuterOperator.java:170-206).  Several probe pages and two probe operators share the marks."""
+    rng = np.random.default_rng(11 + join_type + int(single))
+    nb = 6000
+    bkeys = rng.integers(0, 4000, nb)
+    build = Page(Block.bigint(bkeys, rng.random(nb) < 0.03), Block.double(rng.normal(size=nb)), Block.varchar(["b%d" % i if i % 11 else None for i in range(nb)]))
+    probes = []
+    for m in (7000, 1, 5000):
+        probes.append(Page(Block.varchar(["p%d" % i for i in range(m)]), Block.bigint(rng.integers(1000, 6000, m), rng.random(m) < 0.05)))
+    probe_out, build_out = [1, 0], [0, 2, 1]
+    bridge = ops.JoinBridge()
+    b = ops.HashBuilderOperatorFactory(ctx, bridge, [0], build_out).create_operator()
+    b.add_input(build)
+    b.finish()
+    pf = ops.LookupJoinOperatorFactory(ctx, bridge, join_type, single, [1], probe_out)
+    j1, j2 = pf.create_operator(), pf.create_operator()
+    got = []
+    want = []
+    for i, p in enumerate(probes):
+        op = j1 if i % 2 == 0 else j2
+        op.add_input(p)
+        out = op.get_output()
+        got.extend(out.rows() if out is not None else [])
+        want.extend(oracle_join_rows(build, p, 0, 1, probe_out, build_out, join_type, single))
+    assert got == want
+    j1.finish()
+    j2.finish()
+    outer = ops.LookupOuterOperatorFactory(ctx, bridge, _types_of(probes[0], probe_out)).create_operator()
+    assert not outer.needs_input()
+    page = outer.get_output()
+    rows = page.rows() if page is not None else []
+    assert rows == oracle_outer_rows(build, probes, 0, 1, len(probe_out), build_out, join_type, single)
+    assert outer.get_output() is None and outer.is_finished()
+    for op in (outer, j1, j2, b):
+        op.close()
+    bridge.lookup_source.close()
+
+
+def test_outer_reference_cases_and_untouched_lookup(ctx):
+    # empty lookup sources (TestHashJoinOperator :961-1000, :1052-1103) are in the golden file; a lookup no probe touched
+    # returns every build row from the outer operator
+    build = Page(Block.bigint([5, 6, None, 5]), Block.bigint([50, 60, 70, 80]))
+    bridge = ops.JoinBridge()
+    b = ops.HashBuilderOperatorFactory(ctx, bridge, [0], [1, 0]).create_operator()
+    b.add_input(build)
+    b.finish()
+    ops.LookupJoinOperatorFactory(ctx, bridge, abi.JOIN_FULL_OUTER, False, [0], [0]).create_operator().close()
+    outer = ops.LookupOuterOperatorFactory(ctx, bridge, [abi.INT64]).create_operator()
+    assert outer.get_output().rows() == [(None, 50, 5), (None, 60, 6), (None, 70, None), (None, 80, 5)]
+    outer.close()
+    b.close()
+    bridge.lookup_source.close()
+
+
+def test_semi_join_reference_cases_and_random(ctx):
+    def run(set_block, probe_page, channel):
+        bridge = ops.JoinBridge()
+        sb = ops.SetBuilderOperatorFactory(ctx, bridge, 0).create_operator()
+        sb.add_input(Page(set_block))
+        sb.finish()
+        sj = ops.HashSemiJoinOperatorFactory(ctx, bridge, channel).create_operator()
+        sj.add_input(probe_page)
+        out = sj.get_output()
+        sj.close()
+        sb.close()
+        bridge.lookup_source.close()
+        return out
+    for case in reference_cases()["semi_join"]:
+        probe = Page(Block.bigint(case["probe"]))
+        out = run(Block.bigint(case["set"]), probe, 0)
+        assert out.rows() == [(p, e) for p, e in zip(case["probe"], case["expected"])], case["source"]
+    rng = np.random.default_rng(3)
+    for set_nulls, probe_nulls in ((False, False), (True, False), (False, True), (True, True)):
+        sv = Block.bigint(rng.integers(0, 5000, 3000), rng.random(3000) < 0.01 if set_nulls else None)
+        pk = Block.bigint(rng.integers(0, 8000, 20000), rng.random(20000) < 0.05 if probe_nulls else None)
+        probe = Page(Block.double(rng.normal(size=20000)), pk, Block.varchar(["x%d" % (i % 13) for i in range(20000)]))
+        out = run(sv, probe, 1)
+        assert [r[3] for r in out.rows()] == o.semi_join_bigint(sv, pk)
+        assert [r[:3] for r in out.rows()] == probe.rows()
+    # empty set: NULL probe keys answer false
+    out = run(Block.bigint([]), Page(Block.bigint([1, None])), 0)
+    assert out.rows() == [(1, False), (None, False)]
+
+
+def test_build_side_key_domain(ctx):
+    """DynamicFilterSourceOperator / JoinDomainBuilder collect the build-side key domain: the distinct values while they are few,
+    else min/max.  Here it is read off the finished table."""
+    rng = np.random.default_rng(17)
+    keys = rng.integers(-50, 50, 5000)
+    nulls = rng.random(5000) < 0.02
+    b, lookup = _build_lookup(ctx, [Page(Block.bigint(keys[:3000], nulls[:3000])), Page(Block.bigint(keys[3000:], nulls[3000:]))])
+    want = np.unique(keys[~nulls])
+    lo, hi, cnt, values, has_null = lookup.key_domain(1000)
+    assert (lo, hi, cnt, has_null) == (int(want.min()), int(want.max()), len(want), True)
+    assert (values == want).all()
+    lo, hi, cnt, values, _ = lookup.key_domain(10)           # too many distinct values: the range is the filter
+    assert (lo, hi, cnt) == (int(want.min()), int(want.max()), len(want)) and values is None
+    lookup.close()
+    b.close()
+    b, lookup = _build_lookup(ctx, [Page(Block.bigint([7, -2**63, 7, 3]))])    # INT64_MIN lives beside the table
+    lo, hi, cnt, values, has_null = lookup.key_domain(8)
+    assert (lo, hi, cnt, has_null) == (-2**63, 7, 3, False) and list(values) == [-2**63, 3, 7]
+    lookup.close()
+    b.close()

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as o
-from helpers import oracle_join_rows, reference_cases, rows_equal
+from helpers import join_type_of, oracle_outer_rows, oracle_join_rows, reference_cases, rows_equal
 from trino_b200 import abi
 from trino_b200.page import Block, DictionaryBlock, Page, RunLengthEncodedBlock
 
@@ -94,7 +94,7 @@ def test_flat_multi_column_keys_with_varchar_and_double():
 def _case_pages(case):
     build = Page(Block.bigint(case["build"])) if case["build"] else Page(Block.bigint([]), position_count=0)
     probe = Page(Block.bigint(case["probe"]))
-    jt = abi.JOIN_INNER if case["join_type"] == "inner" else abi.JOIN_PROBE_OUTER
+    jt = join_type_of(case)
     return build, probe, jt
 
 
@@ -211,3 +211,12 @@ def test_synth_shapes():
     assert counts.min() >= 1 and counts.max() <= 7 and abs(counts.mean() - 4) < 0.05
     # slices agree with the whole
     assert (o.synth_lineitem_keys(1000, 100, 50, 0x7C01, True) == o.synth_lineitem_keys(1000, 0, rows, 0x7C01, True)[100:150]).all()
+
+
+def test_semi_join_reference_cases():
+    # TestHashSemiJoinOperator: testSemiJoin, testBuildSideNulls, testProbeSideNulls, testProbeAndBuildNulls
+    for case in reference_cases()["semi_join"]:
+        got = o.semi_join_bigint(Block.bigint(case["set"]), Block.bigint(case["probe"]))
+        assert got == case["expected"], case["source"]
+    # an empty set answers false even for a NULL probe (HashSemiJoinOperator.java:184-187)
+    assert o.semi_join_bigint(Block.bigint([]), Block.bigint([1, None])) == [False, False]

@@ -28,7 +28,7 @@ OPND_NONE, OPND_COLUMN, OPND_TEMP, OPND_CONST, OPND_NULL = 0, 1, 2, 3, 4
 
 AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX = 0, 1, 2, 3, 4, 5
 STEP_SINGLE, STEP_PARTIAL, STEP_FINAL, STEP_INTERMEDIATE = 0, 1, 2, 3
-JOIN_INNER, JOIN_PROBE_OUTER = 0, 1
+JOIN_INNER, JOIN_PROBE_OUTER, JOIN_LOOKUP_OUTER, JOIN_FULL_OUTER = 0, 1, 2, 3
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 NUM_ARENAS = 3
@@ -205,6 +205,9 @@ SIGNATURES = {
     "tgpu_page_copy_to_host": (C.c_int, [VP, PP, PP]),
     "tgpu_page_utf8_bytes": (C.c_int64, [VP, PP, C.c_int32]),
     "tgpu_join_probe_set_passthrough_by_reference": (C.c_int, [VP, C.c_int32]),
+    "tgpu_join_outer_create": (C.c_int, [VP, VP, C.POINTER(C.c_int32), C.c_int32, C.POINTER(VP)]),
+    "tgpu_semi_join_create": (C.c_int, [VP, VP, C.c_int32, C.POINTER(VP)]),
+    "tgpu_lookup_key_domain": (C.c_int, [VP, VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "tgpu_page_passthrough_channel": (C.c_int, [PP, C.c_int32, C.POINTER(C.c_int32)]),
     "tgpu_synth_orders_keys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, VP]),
     "tgpu_synth_lineitem_rows": (C.c_int64, [C.c_int64]),

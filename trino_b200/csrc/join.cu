@@ -18,6 +18,9 @@
 // reference insert order is obtained with atomicMax, and duplicate chains are materialised by a radix sort
 // of (slot,row) pairs only when duplicates exist.  Slot placement (mix(key) & mask, linear probing) is not
 // observable, only key -> head is.
+#include <algorithm>
+#include <mutex>
+
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -601,6 +604,11 @@ struct tgpu_lookup {
     std::vector<DevBuf> by_slot;        // build output columns in table-slot order (fused probe fast path)
     bool generic = false;               // keyed by row hash + verification against build_keys
     std::vector<DevColumn> build_keys;  // generic only: the real key columns of the build side
+    // OuterPositionTracker (M/operator/join/OuterLookupSource.java:168-196): one byte per build position, set by the
+    // LOOKUP_OUTER / FULL_OUTER probes for every build row they emit, read by the LookupOuterOperator
+    DevBuf visited;
+    std::mutex visited_lock;
+    int64_t null_key_rows = -1;         // build rows whose (first) key channel is NULL; -1 = not counted yet
 };
 
 namespace {
@@ -709,6 +717,69 @@ int lookup_positions_generic(tgpu_ctx* ctx, const tgpu_lookup* lk, const std::ve
     for (size_t c = 0; c < keys.size(); c++) tg::key_cols_set(&pk, (int)c, *keys[c]);
     TG_LAUNCH(ctx, join_verify_probe_kernel, tg_grid(ctx, n, 256, 8), 256, 0, pk, key_cols_of(lk->build_keys), n, d_out);
     return TGPU_OK;
+}
+
+// LookupSource.appendTo -> positionVisited for every build row an outer-tracking probe emitted
+__global__ void join_mark_visited_kernel(const int* __restrict__ build_idx, int64_t n, uint8_t* __restrict__ visited)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int b = build_idx[i];
+        if (b >= 0) visited[b] = 1;
+    }
+}
+
+__global__ void join_unvisited_flags_kernel(const uint8_t* __restrict__ visited, int64_t n, uint8_t* __restrict__ flags)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) flags[i] = visited[i] ? 0 : 1;
+}
+
+// HashSemiJoinOperator.process :181-199: value and NULL byte of the appended BOOLEAN column
+__global__ void semi_join_kernel(const int* __restrict__ positions, const uint8_t* __restrict__ key_validity, int64_t n, int set_empty, int set_has_null,
+                                 signed char* __restrict__ value, uint8_t* __restrict__ is_null)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        bool probe_null = !tg_valid(key_validity, i);
+        bool contains = positions[i] >= 0;
+        bool out_null, v;
+        if (probe_null) { out_null = !set_empty; v = false; }
+        else if (!contains && set_has_null) { out_null = true; v = false; }
+        else { out_null = false; v = contains; }
+        value[i] = v ? 1 : 0;
+        is_null[i] = out_null ? 1 : 0;
+    }
+}
+
+__global__ void count_nulls_kernel(const uint8_t* __restrict__ validity, int64_t n, unsigned long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int c = 0;
+    for (; i < n; i += stride) c += tg_valid(validity, i) ? 0 : 1;
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+// DynamicFilterSourceOperator / JoinDomainBuilder: min, max, number of distinct keys and (while they fit) the keys themselves,
+// read off the table (one occupied slot per distinct non-NULL key)
+__global__ void join_key_domain_kernel(const JoinSlot* __restrict__ table, int64_t slots, int64_t max_values, long long* __restrict__ minmax /* [2] */,
+                                       unsigned long long* __restrict__ count, long long* __restrict__ values)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < slots; i += stride) {
+        long long k = table[i].key;
+        if ((unsigned long long)k == EMPTY_KEY) continue;
+        atomicMin(minmax, k);
+        atomicMax(minmax + 1, k);
+        unsigned long long at = atomicAdd(count, 1ULL);
+        if ((long long)at < max_values) values[at] = k;
+    }
 }
 
 // HashBuilderOperator: NEEDS_INPUT -> (finish) LOOKUP_SOURCE_BUILT -> CLOSED
@@ -1038,7 +1109,7 @@ struct JoinProbeOp : tgpu_op {
         std::shared_ptr<DevBuf> jp = std::move(deferred.jp);
         std::vector<DevColumn> built = std::move(deferred.built);
         const int64_t n = deferred.n;
-        const bool outer = join_type == TGPU_JOIN_PROBE_OUTER;
+        const bool outer = join_type == TGPU_JOIN_PROBE_OUTER;     // (tracking join types never take the fast path)
         int64_t matches = 0;
         TG_TRY(tg_read_i64(ctx, match_counter.as<int64_t>(), &matches));
         DevPage outp;
@@ -1110,7 +1181,8 @@ struct JoinProbeOp : tgpu_op {
             if (ch < 0 || ch >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe key channel out of range");
         const DevColumn& key = in.cols[key_channels[0]];
         if (!lookup->generic && key_channels.size() != 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe has %zu join channels, build has 1", key_channels.size());
-        if (!lookup->generic && !getenv("TGPU_JOIN_GENERAL_PATH")) {
+        const bool tracking = join_type == TGPU_JOIN_LOOKUP_OUTER || join_type == TGPU_JOIN_FULL_OUTER;
+        if (!lookup->generic && !tracking && !getenv("TGPU_JOIN_GENERAL_PATH")) {
             bool handled = false;
             TG_TRY(fast_path(in, key, n, &handled));
             if (handled) return lazy ? complete_fast(page) : TGPU_OK;   // host buffers are the caller's again after this call
@@ -1125,7 +1197,7 @@ struct JoinProbeOp : tgpu_op {
             TG_TRY(lookup_positions_generic(ctx, lookup, kp, n, jp->as<int>()));
         }
         else TG_TRY(lookup_positions(ctx, lookup, key, jp->as<int>()));
-        bool outer = join_type == TGPU_JOIN_PROBE_OUTER;
+        bool outer = join_type == TGPU_JOIN_PROBE_OUTER || join_type == TGPU_JOIN_FULL_OUTER;
         const int* links = lookup->has_dups ? lookup->links.as<int>() : nullptr;
         // match counts -> exclusive scan -> output offsets
         DevBuf counts, offsets, tmp;
@@ -1171,7 +1243,10 @@ struct JoinProbeOp : tgpu_op {
             TG_TRY(tg_gather_column(ctx, lookup->store.cols[1 + b], build_idx, total, build_may_be_null, &c));
             outp.cols.push_back(std::move(c));
         }
+        if (tracking && lookup->visited.p)
+            TG_LAUNCH(ctx, join_mark_visited_kernel, tg_grid(ctx, total, 1024, 8), 256, 0, build_idx, total, lookup->visited.as<uint8_t>());
         pending.push_back(tg_make_owned_page(std::move(outp)));
+        if (tracking) TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the marks must be visible to the outer operator's context
         return TGPU_OK;
     }
 
@@ -1185,6 +1260,176 @@ struct JoinProbeOp : tgpu_op {
     int finish() override { finishing = true; return TGPU_OK; }
     bool is_finished() override { return finishing && !deferred.active && next_out >= pending.size(); }
 };
+
+// LookupOuterOperator (M/operator/join/LookupOuterOperator.java:170-206): after every probe has finished, the build rows no
+// probe emitted, in position order, with NULLs in the probe output channels.  A source operator.
+struct JoinOuterOp : tgpu_op {
+    tgpu_lookup* lookup;
+    std::vector<int32_t> probe_types;
+    bool done = false;
+    OwnedPage* pending = nullptr;
+
+    JoinOuterOp(tgpu_ctx* c, tgpu_lookup* lk) : tgpu_op(c), lookup(lk) { lookup->refs++; }
+    ~JoinOuterOp() override { delete pending; tgpu_lookup_release(lookup); }
+
+    bool needs_input() override { return false; }
+    int add_input(const tgpu_page*) override { return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "LookupOuterOperator does not take input"); }
+
+    int produce()
+    {
+        done = true;
+        const int64_t n = lookup->positions;
+        if (n == 0) return TGPU_OK;
+        DevBuf flags, sel, tmp;
+        TG_TRY(flags.alloc(ctx, (size_t)n));
+        TG_TRY(sel.alloc(ctx, (size_t)n * 4));
+        if (lookup->visited.p) TG_LAUNCH(ctx, join_unvisited_flags_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, lookup->visited.as<uint8_t>(), n, flags.as<uint8_t>());
+        else TG_CUDA(ctx, cudaMemsetAsync(flags.p, 1, (size_t)n, ctx->stream));     // no tracking probe ever ran: every row is unvisited
+        long long* d_count = (long long*)(ctx->d_scratch + 14);
+        size_t tmp_bytes = 0;
+        thrust::counting_iterator<int32_t> iota(0);
+        cub::DeviceSelect::Flagged(nullptr, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream);
+        TG_TRY(tmp.alloc(ctx, tmp_bytes));
+        TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, iota, flags.as<uint8_t>(), sel.as<int32_t>(), d_count, (int)n, ctx->stream));
+        int64_t m = 0;
+        TG_TRY(tg_read_i64(ctx, d_count, &m));
+        if (m == 0) return TGPU_OK;
+        DevPage outp;
+        outp.rows = m;
+        // probe channels: all NULL
+        auto all_null = std::make_shared<DevBuf>();
+        TG_TRY(all_null->alloc(ctx, (size_t)((m + 7) / 8)));
+        TG_CUDA(ctx, cudaMemsetAsync(all_null->p, 0, (size_t)((m + 7) / 8), ctx->stream));
+        for (int32_t t : probe_types) {
+            DevColumn c;
+            c.type = t;
+            c.length = m;
+            c.own_validity = all_null;
+            c.validity = all_null->as<uint8_t>();
+            size_t es = (size_t)(t == TGPU_UTF8 ? 1 : c.elem_size());
+            c.own_data = std::make_shared<DevBuf>();
+            TG_TRY(c.own_data->alloc(ctx, std::max<size_t>((size_t)m * es, 8)));
+            TG_CUDA(ctx, cudaMemsetAsync(c.own_data->p, 0, std::max<size_t>((size_t)m * es, 8), ctx->stream));
+            c.data = c.own_data->p;
+            if (t == TGPU_UTF8) {
+                c.own_offsets = std::make_shared<DevBuf>();
+                TG_TRY(c.own_offsets->alloc(ctx, (size_t)(m + 1) * 4));
+                TG_CUDA(ctx, cudaMemsetAsync(c.own_offsets->p, 0, (size_t)(m + 1) * 4, ctx->stream));
+                c.offsets = c.own_offsets->as<int32_t>();
+            }
+            outp.cols.push_back(std::move(c));
+        }
+        for (int32_t b = 0; b < lookup->num_output; b++) {
+            DevColumn c;
+            TG_TRY(tg_gather_column(ctx, lookup->store.cols[1 + b], sel.as<int32_t>(), m, false, &c));
+            outp.cols.push_back(std::move(c));
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pending = tg_make_owned_page(std::move(outp));
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override
+    {
+        *out = nullptr;
+        if (!done) TG_TRY(produce());
+        *out = pending;
+        pending = nullptr;
+        return TGPU_OK;
+    }
+    int finish() override { return TGPU_OK; }
+    bool is_finished() override { return done && !pending; }
+};
+
+// HashSemiJoinOperator (M/operator/HashSemiJoinOperator.java:155-201) over a lookup built by a HashBuilder on the filtering
+// source's join channel (the ChannelSet of SetBuilderOperator): input page + one BOOLEAN column.
+struct SemiJoinOp : tgpu_op {
+    tgpu_lookup* lookup;
+    int32_t probe_channel = 0;
+    OwnedPage* pending = nullptr;
+    bool finishing = false;
+
+    SemiJoinOp(tgpu_ctx* c, tgpu_lookup* lk) : tgpu_op(c), lookup(lk) { lookup->refs++; }
+    ~SemiJoinOp() override { delete pending; tgpu_lookup_release(lookup); }
+
+    bool needs_input() override { return !finishing && !pending; }
+
+    int add_input(const tgpu_page* page) override
+    {
+        if (pending) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "addInput while the previous page's output has not been taken");
+        int64_t n = page->num_rows;
+        if (n == 0) return TGPU_OK;
+        DevPage in;
+        TG_TRY(tg_ingest_page(ctx, page, &in));
+        if (probe_channel < 0 || probe_channel >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe join channel out of range");
+        const DevColumn& key = in.cols[probe_channel];
+        if (key.type == TGPU_FLOAT64 || lookup->key_type == TGPU_FLOAT64)
+            return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "DOUBLE semi-join keys (NaN is IDENTICAL to NaN in a ChannelSet): keep the Java operator");
+        DevBuf pos;
+        TG_TRY(pos.alloc(ctx, (size_t)n * 4));
+        if (lookup->generic) {
+            std::vector<const DevColumn*> kp{&key};
+            TG_TRY(lookup_positions_generic(ctx, lookup, kp, n, pos.as<int>()));
+        }
+        else TG_TRY(lookup_positions(ctx, lookup, key, pos.as<int>()));
+        DevColumn out;
+        out.type = TGPU_INT8;
+        out.length = n;
+        out.own_data = std::make_shared<DevBuf>();
+        TG_TRY(out.own_data->alloc(ctx, (size_t)n));
+        out.data = out.own_data->p;
+        DevBuf is_null;
+        TG_TRY(is_null.alloc(ctx, (size_t)n));
+        TG_LAUNCH(ctx, semi_join_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, pos.as<int>(), key.validity, n, lookup->positions == 0 ? 1 : 0,
+                  lookup->null_key_rows > 0 ? 1 : 0, out.own_data->as<signed char>(), is_null.as<uint8_t>());
+        tgpu_column bm;
+        memset(&bm, 0, sizeof(bm));
+        bm.type = TGPU_INT8;
+        bm.flags = TGPU_COL_NULLS_BYTEMAP;
+        bm.length = n;
+        bm.data = is_null.p;
+        bm.validity = is_null.as<uint8_t>();
+        DevColumn packed;
+        TG_TRY(tg_ingest_column(ctx, &bm, true, &packed));
+        out.own_validity = packed.own_validity;
+        out.validity = packed.validity;
+        DevPage outp;
+        outp.rows = n;
+        outp.cols = in.cols;            // inputPage.appendColumn(...): the input blocks pass through
+        outp.cols.push_back(std::move(out));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pending = tg_make_owned_page(std::move(outp));
+        for (int32_t c = 0; c + 1 < (int32_t)pending->page.cols.size(); c++) pending->passthrough.push_back(c);
+        return TGPU_OK;
+    }
+
+    int get_output(OwnedPage** out) override
+    {
+        *out = pending;
+        pending = nullptr;
+        return TGPU_OK;
+    }
+    int finish() override { finishing = true; return TGPU_OK; }
+    bool is_finished() override { return finishing && !pending; }
+};
+
+// rows of the build side whose join key is NULL (HashSemiJoin's containsNull; never matched, so always outer rows)
+static int lookup_count_null_keys(tgpu_ctx* ctx, tgpu_lookup* lk)
+{
+    if (lk->null_key_rows >= 0) return TGPU_OK;
+    lk->null_key_rows = 0;
+    if (lk->positions == 0) return TGPU_OK;
+    const DevColumn* key = lk->generic ? (lk->build_keys.empty() ? nullptr : &lk->build_keys[0]) : (lk->store.cols.empty() ? nullptr : &lk->store.cols[0]);
+    if (!key || !key->validity) return TGPU_OK;
+    DevBuf cnt;
+    TG_TRY(cnt.alloc(ctx, 8));
+    TG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, 8, ctx->stream));
+    TG_LAUNCH(ctx, count_nulls_kernel, tg_grid(ctx, lk->positions, 1024, 8), 256, 0, key->validity, lk->positions, cnt.as<unsigned long long>());
+    int64_t v = 0;
+    TG_TRY(tg_read_i64(ctx, cnt.p, &v));
+    lk->null_key_rows = v;
+    return TGPU_OK;
+}
 
 }  // namespace
 
@@ -1239,14 +1484,84 @@ extern "C" int tgpu_join_probe_create(tgpu_ctx* ctx, const tgpu_join_probe_spec*
     if (!ctx || !spec || !lookup || !out) return TGPU_ERR_INVALID_ARGUMENT;
     if (spec->num_key_channels < 1 || spec->num_key_channels > tg::MAX_KEY_COLS)
         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "GPU hash join supports 1..%d join channels (got %d)", tg::MAX_KEY_COLS, spec->num_key_channels);
-    if (spec->join_type != TGPU_JOIN_INNER && spec->join_type != TGPU_JOIN_PROBE_OUTER)
-        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "join type %d needs LookupOuterOperator: keep the Java operator", spec->join_type);
+    if (spec->join_type < TGPU_JOIN_INNER || spec->join_type > TGPU_JOIN_FULL_OUTER) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "bad join type %d", spec->join_type);
+    if (spec->join_type == TGPU_JOIN_LOOKUP_OUTER || spec->join_type == TGPU_JOIN_FULL_OUTER) {
+        // OuterLookupSourceSupplier: the visited-positions array is shared by every probe of this lookup source
+        TG_CUDA(ctx, cudaSetDevice(ctx->device));
+        std::lock_guard<std::mutex> guard(lookup->visited_lock);
+        if (!lookup->visited.p && lookup->positions > 0) {
+            TG_TRY(lookup->visited.alloc(ctx, (size_t)lookup->positions));
+            TG_CUDA(ctx, cudaMemsetAsync(lookup->visited.p, 0, (size_t)lookup->positions, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
     JoinProbeOp* op = new JoinProbeOp(ctx, lookup);
     op->join_type = spec->join_type;
     op->single_match = spec->output_single_match;
     op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
     op->output_channels.assign(spec->output_channels, spec->output_channels + spec->num_output_channels);
     *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_join_outer_create(tgpu_ctx* ctx, tgpu_lookup* lookup, const int32_t* probe_output_types, int32_t num_probe_outputs, tgpu_op** out)
+{
+    if (!ctx || !lookup || !out || num_probe_outputs < 0 || (num_probe_outputs > 0 && !probe_output_types)) return TGPU_ERR_INVALID_ARGUMENT;
+    JoinOuterOp* op = new JoinOuterOp(ctx, lookup);
+    op->probe_types.assign(probe_output_types, probe_output_types + num_probe_outputs);
+    *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_semi_join_create(tgpu_ctx* ctx, tgpu_lookup* lookup, int32_t probe_join_channel, tgpu_op** out)
+{
+    if (!ctx || !lookup || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (lookup->generic && lookup->build_keys.size() != 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a semi-join set has one channel");
+    TG_TRY(lookup_count_null_keys(ctx, lookup));
+    SemiJoinOp* op = new SemiJoinOp(ctx, lookup);
+    op->probe_channel = probe_join_channel;
+    *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_lookup_key_domain(tgpu_ctx* ctx, tgpu_lookup* lookup, int64_t max_values, int64_t* min_out, int64_t* max_out, int64_t* distinct_out,
+                                      int64_t* values_out, int32_t* has_null_out)
+{
+    if (!ctx || !lookup || !min_out || !max_out || !distinct_out || max_values < 0 || (max_values > 0 && !values_out)) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (lookup->generic || lookup->key_type == TGPU_FLOAT64 || lookup->key_type == TGPU_UTF8)
+        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "key domains are collected for single BIGINT-family join keys only");
+    TG_TRY(lookup_count_null_keys(ctx, lookup));
+    if (has_null_out) *has_null_out = lookup->null_key_rows > 0;
+    const int64_t slots = (int64_t)(lookup->mask & ~MODE_BIT) + 1;
+    DevBuf state, vals;
+    TG_TRY(state.alloc(ctx, 24));
+    TG_TRY(vals.alloc(ctx, (size_t)std::max<int64_t>(max_values, 1) * 8));
+    long long init[3] = {INT64_MAX, INT64_MIN, 0};
+    TG_CUDA(ctx, cudaMemcpyAsync(state.p, init, 24, cudaMemcpyHostToDevice, ctx->stream));
+    if (lookup->table.p && lookup->positions > 0)
+        TG_LAUNCH(ctx, join_key_domain_kernel, tg_grid(ctx, slots, 1024, 8), 256, 0, lookup->table.as<JoinSlot>(), slots, max_values, state.as<long long>(),
+                  (unsigned long long*)(state.as<long long>() + 2), vals.as<long long>());
+    long long res[3];
+    TG_CUDA(ctx, cudaMemcpyAsync(res, state.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t distinct = res[2];
+    int64_t got = std::min<int64_t>(distinct, max_values);
+    if (got > 0) {
+        TG_CUDA(ctx, cudaMemcpyAsync(values_out, vals.p, (size_t)got * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (lookup->special_head >= 0) {       // the key INT64_MIN lives beside the table
+        if (distinct < max_values) values_out[distinct] = INT64_MIN;
+        distinct++;
+        res[0] = INT64_MIN;
+        if (res[1] < res[0]) res[1] = INT64_MIN;
+    }
+    if (distinct <= max_values && distinct > 0) std::sort(values_out, values_out + distinct);
+    *min_out = res[0];
+    *max_out = res[1];
+    *distinct_out = distinct;
     return TGPU_OK;
 }
 

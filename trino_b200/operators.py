@@ -530,6 +530,16 @@ class LookupSource:
     def get_join_positions_device(self, device_page, out_ptr):
         self.ctx.check(self.ctx.lib.tgpu_lookup_get_join_positions(self.ctx.h, self.h, device_page.ref(), C.c_void_p(out_ptr)))
 
+    def key_domain(self, max_values):
+        """DynamicFilterSourceOperator / JoinDomainBuilder: (min, max, distinct count, sorted values or None, has_null) of the
+        build-side join key; values are None when there are more than max_values distinct keys (range fallback)."""
+        lo, hi, cnt, has_null = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        vals = np.empty(max(max_values, 1), dtype=np.int64)
+        self.ctx.check(self.ctx.lib.tgpu_lookup_key_domain(self.ctx.h, self.h, max_values, C.byref(lo), C.byref(hi), C.byref(cnt),
+                                                            vals.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(has_null)))
+        values = vals[:cnt.value].copy() if cnt.value <= max_values else None
+        return lo.value, hi.value, cnt.value, values, bool(has_null.value)
+
     def position_links(self):
         out = np.empty(self.get_join_position_count(), dtype=np.int32)
         self.ctx.check(self.ctx.lib.tgpu_lookup_copy_position_links(self.ctx.h, self.h, C.c_void_p(out.ctypes.data)))
@@ -606,6 +616,49 @@ class LookupJoinOperatorFactory(OperatorFactory):
     def duplicate(self):
         return LookupJoinOperatorFactory(self.ctx, self.bridge, self.join_type, self.output_single_match, self.probe_join_channels,
                                          self.probe_output_channels)
+
+
+class LookupOuterOperatorFactory(OperatorFactory):
+    """M/operator/join/LookupOuterOperator.java:38-95.  `probe_output_types`: tgpu types of the probe output channels."""
+
+    def __init__(self, ctx, bridge, probe_output_types):
+        super().__init__()
+        self.ctx, self.bridge, self.probe_output_types = ctx, bridge, list(probe_output_types)
+
+    def _create(self):
+        if not self.bridge.is_built():
+            raise RuntimeError("lookup source is not built yet")
+        t = _i32(self.probe_output_types)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_join_outer_create(self.ctx.h, self.bridge.lookup_source.h, C.cast(t, C.POINTER(C.c_int32)), len(self.probe_output_types),
+                                                            C.byref(h)))
+        return Operator(self.ctx, h)
+
+
+class SetBuilderOperatorFactory(OperatorFactory):
+    """M/operator/SetBuilderOperator.java: the ChannelSet of a semi-join is a lookup source over one channel without outputs."""
+
+    def __init__(self, ctx, bridge, set_channel, expected_positions=0):
+        super().__init__()
+        self.inner = HashBuilderOperatorFactory(ctx, bridge, [set_channel], [], expected_positions)
+
+    def _create(self):
+        return self.inner.create_operator()
+
+
+class HashSemiJoinOperatorFactory(OperatorFactory):
+    """M/operator/HashSemiJoinOperator.java:43-100"""
+
+    def __init__(self, ctx, bridge, probe_join_channel):
+        super().__init__()
+        self.ctx, self.bridge, self.probe_join_channel = ctx, bridge, probe_join_channel
+
+    def _create(self):
+        if not self.bridge.is_built():
+            raise RuntimeError("channel set is not built yet")
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_semi_join_create(self.ctx.h, self.bridge.lookup_source.h, self.probe_join_channel, C.byref(h)))
+        return Operator(self.ctx, h)
 
 
 # ---- partitioned output -----------------------------------------------------------------------------
