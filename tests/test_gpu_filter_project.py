@@ -125,3 +125,33 @@ def test_empty_and_all_filtered_pages(ctx):
     prog = ops.PageProcessorProgram(ops.Call(abi.EX_GT, ops.Col(0, B), ops.Const(100, B)), [0])
     assert run(ctx, prog, [Page(Block.bigint([1, 2, 3])), Page(Block.bigint([]), position_count=0)]) == []
     assert run(ctx, prog, [Page(Block.bigint([1, 200, 3]))]) == [(200,)]
+
+
+@pytest.mark.parametrize("selectivity", [0.001, 0.3, 0.97])
+def test_chunked_two_pass_form_matches_selection_vector_form(ctx, selectivity, monkeypatch):
+    """Fixed-width pass-through channels + a filter run without a selection vector (flags + chunk ranks); the rows, their order
+    and NULLs must be those of the select/gather form and of numpy, across several chunks and pages."""
+    rng = np.random.default_rng(int(selectivity * 1000))
+    pages = []
+    for n in (700_000, 1, 1023, 300_001):
+        pages.append(Page(Block.double(rng.random(n), rng.random(n) < 0.02), Block.bigint(rng.integers(-10**9, 10**9, n), rng.random(n) < 0.1),
+                          Block.integer(rng.integers(0, 100, n)), Block.tinyint(rng.integers(-5, 5, n), rng.random(n) < 0.3),
+                          Block.smallint(rng.integers(0, 30000, n))))
+    flt = ops.Call(abi.EX_LT, ops.Col(0, D), ops.Const(selectivity, D))
+    prog = ops.PageProcessorProgram(flt, [1, ops.Call(abi.EX_ADD, ops.Col(1, B), ops.Col(2, B)), 3, 4, ops.Call(abi.EX_MUL, ops.Col(0, D), ops.Const(2.0, D)), 2])
+    got = run(ctx, prog, pages)
+    want = []
+    def nulls_of(blk):
+        return blk.nulls if blk.nulls is not None else np.zeros(len(blk.values), dtype=bool)
+
+    for p in pages:
+        x, k, i, t, s = (p.get_block(c) for c in range(5))
+        xn, kn_, tn = nulls_of(x), nulls_of(k), nulls_of(t)
+        sel = (x.values < selectivity) & ~xn
+        for r in np.nonzero(sel)[0]:
+            kn = bool(kn_[r])
+            want.append((None if kn else int(k.values[r]), None if kn else int(k.values[r]) + int(i.values[r]), None if tn[r] else int(t.values[r]),
+                         int(s.values[r]), float(x.values[r]) * 2.0, int(i.values[r])))
+    assert got == want
+    monkeypatch.setenv("TGPU_FP_SELECTION_VECTOR", "1")
+    assert run(ctx, prog, pages) == want

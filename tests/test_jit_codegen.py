@@ -64,4 +64,6 @@ def test_filter_project_kernels_compile():
         pytest.skip("NVRTC not installed: " + src)
     assert st == 0, src
     assert "tg_fp_filter_jit" in src and "tg_fp_project_jit" in src
+    # fixed-width pass-through channels + a filter: the chunked two-pass form (no selection vector) is generated as well
+    assert "tg_fp_filter_chunks_jit" in src and "tg_fp_project_chunks_jit" in src and "out.pass_data[1]" in src
     assert "tg_valid(cols.cols[4].validity" in src and "tg_valid(cols.cols[5].validity" not in src

@@ -69,6 +69,10 @@ struct OutCols {
     int32_t vtype[TGD_MAX_CHANNELS];
     void* data[TGD_MAX_CHANNELS];
     uint8_t* nullmap[TGD_MAX_CHANNELS];   // 1 byte per row, 1 = NULL
+    // pass-through projections copied by the fused (chunked) projection kernel; nullmap == nullptr: the input has no NULLs
+    int32_t pass_count;
+    void* pass_data[TGD_MAX_CHANNELS];
+    uint8_t* pass_nullmap[TGD_MAX_CHANNELS];
 };
 
 #if defined(__CUDACC__)
@@ -408,6 +412,86 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
         out.blk_first[b * (L + 2) + s] = lfirst[s];
         if (s < L) out.blk_keys[b * L + s] = tkeys[s];
     }
+}
+
+// ---- FilterAndProject in two passes without a selection vector -------------------------------------------------------------
+// Every CTA owns a contiguous chunk of rows.  Pass 1 evaluates the filter (flags, 1 byte per row) and counts the selected rows
+// of the chunk; a scan of the chunk counts gives every chunk its first output row.  Pass 2 ranks the selected rows of a tile
+// (ballot + a scan over the tile's (iteration, warp) cells), evaluates the projections and copies the pass-through channels
+// straight to output row chunk_off + rank: output order = input order (PageProcessor.java:302-336).
+// P supplies: static bool filter(cols, row, err*), static void row(cols, row, j, out, err*, nulls_seen*).
+constexpr int FPC_R = 4;          // tile = FPC_R x 256 rows
+constexpr int FPC_T = 256;
+
+template <class P>
+__device__ __forceinline__ void fp_filter_chunks_body(const DColumns& cols, long long n, long long chunk, unsigned char* __restrict__ flags,
+                                                      unsigned int* __restrict__ chunk_counts, unsigned int* __restrict__ err_out)
+{
+    __shared__ unsigned int warp_sel[FPC_T / 32];
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < n ? begin + chunk : n;
+    unsigned int err = 0, mine = 0;
+    for (long long row = begin + threadIdx.x; row < end; row += FPC_T) {
+        bool s = P::filter(cols, row, &err);
+        flags[row] = s ? 1 : 0;
+        mine += s ? 1u : 0u;
+    }
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+    if ((threadIdx.x & 31) == 0) warp_sel[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int total = 0;
+        for (int w = 0; w < FPC_T / 32; w++) total += warp_sel[w];
+        chunk_counts[blockIdx.x] = total;
+    }
+    if (err) atomicOr(err_out, err);
+}
+
+template <class P>
+__device__ __forceinline__ void fp_project_chunks_body(const DColumns& cols, const unsigned char* __restrict__ flags, long long n, long long chunk,
+                                                       const long long* __restrict__ chunk_off, const OutCols& out, unsigned int* __restrict__ err_out,
+                                                       unsigned int* __restrict__ any_null)
+{
+    constexpr int NW = FPC_T / 32;
+    __shared__ unsigned int cells[FPC_R * NW];     // selected rows per (iteration, warp), then their exclusive prefix
+    __shared__ unsigned int tile_total;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < n ? begin + chunk : n;
+    long long running = chunk_off[blockIdx.x];
+    unsigned int err = 0, nulls_seen = 0;
+    for (long long tile = begin; tile < end; tile += (long long)FPC_R * FPC_T) {
+        bool sel[FPC_R];
+        unsigned int rank[FPC_R];
+#pragma unroll
+        for (int i = 0; i < FPC_R; i++) {
+            long long row = tile + (long long)i * FPC_T + threadIdx.x;
+            sel[i] = row < end && flags[row] != 0;
+            unsigned int b = __ballot_sync(0xffffffffu, sel[i]);
+            rank[i] = __popc(b & ((1u << lane) - 1));
+            if (lane == 0) cells[i * NW + warp] = __popc(b);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            static_assert(FPC_R * NW == 32, "one cell per lane");
+            unsigned int v = cells[lane], incl = v;
+            for (int off = 1; off < 32; off <<= 1) {
+                unsigned int u = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += u;
+            }
+            cells[lane] = incl - v;
+            if (lane == 31) tile_total = incl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < FPC_R; i++) {
+            if (!sel[i]) continue;
+            long long row = tile + (long long)i * FPC_T + threadIdx.x;
+            P::row(cols, row, running + cells[i * NW + warp] + rank[i], out, &err, &nulls_seen);
+        }
+        running += tile_total;
+        __syncthreads();
+    }
+    if (err) atomicOr(err_out, err);
+    if (nulls_seen) atomicOr(any_null, nulls_seen);
 }
 
 #endif  // __CUDACC__

@@ -173,7 +173,7 @@ static void fp_emit_insns(std::string& s, const DProgram& prog, int first, int l
 }
 
 // straight-line typed code for one program over channels of the given element sizes
-static std::string gen_fp_source(const DProgram& prog, const int* elems, int num_channels, uint32_t nullable_mask)
+static std::string gen_fp_source(const DProgram& prog, const int* elems, int num_channels, uint32_t nullable_mask, const std::vector<int>& pass_channels)
 {
     std::string s;
     bool used[TGPU_MAX_CHANNELS] = {false};
@@ -213,7 +213,65 @@ static std::string gen_fp_source(const DProgram& prog, const int* elems, int num
     s += "      if (out.vtype[c] == TGD_V_BOOLEAN) ((signed char*)out.data[c])[j] = (signed char)v; else ((long long*)out.data[c])[j] = v;\n";
     s += "      out.nullmap[c][j] = isn ? 1 : 0;\n      if (isn) nulls_seen |= 1u << c;\n    }\n";
     s += "  }\n  (void)ignored;\n  if (err) atomicOr(err_out, err);\n  if (nulls_seen) atomicOr(any_null, nulls_seen);\n}\n";
+    // chunked two-pass form (no selection vector): per-row functors + the two kernels around the bodies of device_lib.cuh
+    bool chunkable = prog.filter_temp >= 0;
+    for (int ch : pass_channels)
+        if (ch < 0 || ch >= num_channels || elems[ch] == 0) chunkable = false;     // variable-width pass-through: not in this form
+    if (!chunkable) return s;
+    s += "struct FProg {\n";
+    s += "  static __device__ __forceinline__ bool filter(const DColumns& cols, long long row, unsigned int* errp) {\n    unsigned int err = 0;\n";
+    s += loads + temps;
+    fp_emit_insns(s, prog, 0, prog.num_filter_insns, "&err");
+    fp_appendf(s, "    *errp |= err;\n    return !tn%d && t%d != 0;\n  }\n", prog.filter_temp, prog.filter_temp);
+    s += "  static __device__ __forceinline__ void row(const DColumns& cols, long long row, long long j, const OutCols& out, unsigned int* errp, unsigned int* nullsp) {\n";
+    s += "    unsigned int err = 0, ignored = 0, nulls_seen = 0;\n";
+    s += loads + temps;
+    fp_emit_insns(s, prog, 0, prog.num_filter_insns, "&ignored");
+    fp_emit_insns(s, prog, prog.num_filter_insns, prog.num_insns, "&err");
+    s += "    for (int c = 0; c < out.count; c++) {\n      long long v = 0; bool isn = true;\n      switch (out.temp[c]) {\n";
+    for (int t = 0; t < TGPU_MAX_TEMPS; t++) fp_appendf(s, "        case %d: v = t%d; isn = tn%d; break;\n", t, t, t);
+    s += "      }\n      if (isn) v = 0;\n";
+    s += "      if (out.vtype[c] == TGD_V_BOOLEAN) ((signed char*)out.data[c])[j] = (signed char)v; else ((long long*)out.data[c])[j] = v;\n";
+    s += "      out.nullmap[c][j] = isn ? 1 : 0;\n      if (isn) nulls_seen |= 1u << c;\n    }\n";
+    for (size_t k = 0; k < pass_channels.size(); k++) {
+        int ch = pass_channels[k];
+        const char* ty = elems[ch] == 8 ? "long long" : elems[ch] == 4 ? "int" : elems[ch] == 2 ? "short" : "signed char";
+        fp_appendf(s, "    ((%s*)out.pass_data[%d])[j] = ((const %s*)cols.cols[%d].data)[row];\n", ty, (int)k, ty, ch);
+        if ((nullable_mask >> ch) & 1) fp_appendf(s, "    out.pass_nullmap[%d][j] = tg_valid(cols.cols[%d].validity, row) ? 0 : 1;\n", (int)k, ch);
+    }
+    s += "    (void)ignored;\n    *errp |= err;\n    *nullsp |= nulls_seen;\n  }\n};\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) tg_fp_filter_chunks_jit(DColumns cols, long long n, long long chunk, unsigned char* flags, "
+         "unsigned int* counts, unsigned int* err_out) { fp_filter_chunks_body<FProg>(cols, n, chunk, flags, counts, err_out); }\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) tg_fp_project_chunks_jit(DColumns cols, const unsigned char* flags, long long n, long long chunk, "
+         "const long long* chunk_off, OutCols out, unsigned int* err_out, unsigned int* any_null) "
+         "{ fp_project_chunks_body<FProg>(cols, flags, n, chunk, chunk_off, out, err_out, any_null); }\n";
     return s;
+}
+
+// exclusive scan of the chunk counts of the chunked FilterAndProject form (one CTA)
+__global__ void __launch_bounds__(256) fp_chunk_scan_kernel(const unsigned int* __restrict__ counts, int chunks, long long* __restrict__ chunk_off,
+                                                            long long* __restrict__ total)
+{
+    __shared__ long long part[256];
+    const int t = threadIdx.x;
+    const int per = (chunks + 255) / 256;
+    const int b0 = min(chunks, t * per), b1 = min(chunks, b0 + per);
+    long long sum = 0;
+    for (int b = b0; b < b1; b++) sum += counts[b];
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        long long v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - sum;
+    for (int b = b0; b < b1; b++) {
+        chunk_off[b] = run;
+        run += counts[b];
+    }
+    if (t == 255) *total = part[255];
 }
 
 struct FilterProjectOp : tgpu_op {
@@ -264,6 +322,15 @@ struct FilterProjectOp : tgpu_op {
         DevBuf sel;
         const int32_t* d_sel = nullptr;
         if (host_prog.filter_temp >= 0) {
+            TG_TRY(jit_prepare(in));
+            if (jit_project_chunks) {
+                bool handled = false;
+                TG_TRY(add_input_chunked(in, cols, n, d_err, d_anynull, &handled, &m));
+                if (handled) return TGPU_OK;
+                // every row passed the filter: fall through to the identity form (blocks pass through, no copies)
+            }
+        }
+        if (host_prog.filter_temp >= 0 && !jit_project_chunks) {
             DevBuf flags, tmp;
             TG_TRY(flags.alloc(ctx, (size_t)n));
             TG_TRY(sel.alloc(ctx, (size_t)n * 4));
@@ -349,10 +416,125 @@ struct FilterProjectOp : tgpu_op {
 
     int pack_nullmap(const uint8_t* nullmap, int64_t m, uint8_t* bitmap);
 
+    // chunked two-pass form: handled = false (and *m_out = n) when every row is selected
+    int add_input_chunked(const DevPage& in, const DColumns& cols, int64_t n, unsigned int* d_err, unsigned int* d_anynull, bool* handled, int64_t* m_out)
+    {
+        *handled = false;
+        const int64_t tile = (int64_t)FPC_R * FPC_T;
+        int per_sm = std::min(jit_blocks_per_sm(jit_filter_chunks, FPC_T, 0), jit_blocks_per_sm(jit_project_chunks, FPC_T, 0));
+        int64_t want = std::min<int64_t>(tg_div_up(n, tile), (int64_t)ctx->sm_count * per_sm);
+        long long chunk = (long long)(tg_div_up(tg_div_up(n, want), tile) * tile);
+        int chunks = (int)tg_div_up(n, chunk);
+        DevBuf flags, counts, chunk_off, d_total;
+        TG_TRY(flags.alloc(ctx, (size_t)n));
+        TG_TRY(counts.alloc(ctx, (size_t)chunks * 4));
+        TG_TRY(chunk_off.alloc(ctx, (size_t)chunks * 8));
+        TG_TRY(d_total.alloc(ctx, 8));
+        long long n_arg = n;
+        {
+            DColumns c = cols;
+            unsigned char* f_arg = flags.as<unsigned char>();
+            unsigned int* cnt_arg = counts.as<unsigned int>();
+            void* params[6] = {&c, &n_arg, &chunk, &f_arg, &cnt_arg, &d_err};
+            TG_TRY(jit_launch(ctx, jit_filter_chunks, chunks, FPC_T, 0, params));
+        }
+        TG_LAUNCH(ctx, fp_chunk_scan_kernel, 1, 256, 0, counts.as<unsigned int>(), chunks, chunk_off.as<long long>(), d_total.as<long long>());
+        int64_t m = 0, errw = 0;
+        TG_TRY(tg_read_i64(ctx, d_total.p, &m));
+        TG_TRY(tg_read_i64(ctx, d_err, &errw));
+        TG_TRY(raise(errw & 0xFFFFFFFFLL));
+        *m_out = m;
+        if (m == n) return TGPU_OK;
+        *handled = true;
+        if (m == 0) return TGPU_OK;
+        DevPage outp;
+        outp.rows = m;
+        outp.cols.resize(projections.size());
+        OutCols oc;
+        memset(&oc, 0, sizeof(oc));
+        std::vector<std::shared_ptr<DevBuf>> nullmaps, pass_nullmaps;
+        std::vector<int> computed_at, pass_at;
+        for (size_t pi = 0; pi < projections.size(); pi++) {
+            const tgpu_projection& pr = projections[pi];
+            DevColumn& c = outp.cols[pi];
+            c.length = m;
+            c.own_data = std::make_shared<DevBuf>();
+            if (pr.kind == 0) {
+                if (pr.index < 0 || pr.index >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "projection channel out of range");
+                const DevColumn& src = in.cols[pr.index];
+                c.type = src.type;
+                TG_TRY(c.own_data->alloc(ctx, (size_t)m * src.elem_size()));
+                c.data = c.own_data->p;
+                int k = oc.pass_count++;
+                oc.pass_data[k] = c.own_data->p;
+                std::shared_ptr<DevBuf> nm;
+                if (src.validity) {
+                    nm = std::make_shared<DevBuf>();
+                    TG_TRY(nm->alloc(ctx, (size_t)m));
+                    oc.pass_nullmap[k] = nm->as<uint8_t>();
+                }
+                pass_nullmaps.push_back(nm);
+                pass_at.push_back((int)pi);
+            }
+            else {
+                c.type = pr.vtype == TGPU_V_DOUBLE ? TGPU_FLOAT64 : pr.vtype == TGPU_V_BOOLEAN ? TGPU_INT8 : TGPU_INT64;
+                TG_TRY(c.own_data->alloc(ctx, (size_t)m * c.elem_size()));
+                c.data = c.own_data->p;
+                auto nm = std::make_shared<DevBuf>();
+                TG_TRY(nm->alloc(ctx, (size_t)m));
+                int k = oc.count++;
+                oc.temp[k] = pr.index;
+                oc.vtype[k] = pr.vtype;
+                oc.data[k] = c.own_data->p;
+                oc.nullmap[k] = nm->as<uint8_t>();
+                nullmaps.push_back(nm);
+                computed_at.push_back((int)pi);
+            }
+        }
+        {
+            DColumns c = cols;
+            const unsigned char* f_arg = flags.as<unsigned char>();
+            const long long* off_arg = chunk_off.as<long long>();
+            void* params[8] = {&c, &f_arg, &n_arg, &chunk, &off_arg, &oc, &d_err, &d_anynull};
+            TG_TRY(jit_launch(ctx, jit_project_chunks, chunks, FPC_T, 0, params));
+        }
+        int64_t word = 0;
+        TG_TRY(tg_read_i64(ctx, d_err, &word));
+        TG_TRY(raise(word & 0xFFFFFFFFLL));
+        uint32_t any_null = (uint32_t)((uint64_t)word >> 32);
+        for (int k = 0; k < oc.count; k++) {
+            if (!((any_null >> k) & 1)) continue;
+            DevColumn& c = outp.cols[computed_at[k]];
+            c.own_validity = std::make_shared<DevBuf>();
+            TG_TRY(c.own_validity->alloc(ctx, (size_t)((m + 7) / 8)));
+            TG_TRY(pack_nullmap(nullmaps[k]->as<uint8_t>(), m, c.own_validity->as<uint8_t>()));
+            c.validity = c.own_validity->as<uint8_t>();
+        }
+        for (int k = 0; k < oc.pass_count; k++) {
+            if (!pass_nullmaps[k]) continue;
+            DevColumn& c = outp.cols[pass_at[k]];
+            c.own_validity = std::make_shared<DevBuf>();
+            TG_TRY(c.own_validity->alloc(ctx, (size_t)((m + 7) / 8)));
+            TG_TRY(pack_nullmap(pass_nullmaps[k]->as<uint8_t>(), m, c.own_validity->as<uint8_t>()));
+            c.validity = c.own_validity->as<uint8_t>();
+        }
+        pending.push_back(tg_make_owned_page(std::move(outp)));
+        return TGPU_OK;
+    }
+
     // kernels specialised for this program and this page's channel types / nullability (NVRTC, cached)
     void* jit_filter = nullptr;
     void* jit_project = nullptr;
+    void* jit_filter_chunks = nullptr;      // chunked two-pass form (nullptr: not applicable to this program / page shape)
+    void* jit_project_chunks = nullptr;
     std::string jit_key;
+    std::vector<int> pass_channels() const
+    {
+        std::vector<int> v;
+        for (auto& pr : projections)
+            if (pr.kind == 0) v.push_back(pr.index);
+        return v;
+    }
     int jit_prepare(const DevPage& in)
     {
         if (!jit_available()) { jit_filter = jit_project = nullptr; return TGPU_OK; }
@@ -366,9 +548,15 @@ struct FilterProjectOp : tgpu_op {
         }
         key += ":" + std::to_string(nullable);
         if (key == jit_key && jit_filter) return TGPU_OK;
-        std::string src = gen_fp_source(host_prog, elems, (int)in.cols.size(), nullable);
+        std::vector<int> pass = pass_channels();
+        std::string src = gen_fp_source(host_prog, elems, (int)in.cols.size(), nullable, pass);
         TG_TRY(jit_get_function(ctx, src, "tg_fp_filter_jit", &jit_filter));
         TG_TRY(jit_get_function(ctx, src, "tg_fp_project_jit", &jit_project));
+        jit_filter_chunks = jit_project_chunks = nullptr;
+        if (src.find("tg_fp_project_chunks_jit") != std::string::npos && pass.size() <= TGPU_MAX_CHANNELS && !getenv("TGPU_FP_SELECTION_VECTOR")) {
+            TG_TRY(jit_get_function(ctx, src, "tg_fp_filter_chunks_jit", &jit_filter_chunks));
+            TG_TRY(jit_get_function(ctx, src, "tg_fp_project_chunks_jit", &jit_project_chunks));
+        }
         jit_key = key;
         return TGPU_OK;
     }
@@ -449,7 +637,10 @@ extern "C" int tgpu_jit_selftest_filter_project(const tgpu_expr_program* program
         col.type = channel_types[c];
         elems[c] = col.elem_size();
     }
-    std::string src = gen_fp_source(prog, elems, num_channels, nullable_mask);
+    std::vector<int> pass;
+    for (int32_t i = 0; i < program->num_projections; i++)
+        if (program->projections[i].kind == 0) pass.push_back(program->projections[i].index);
+    std::string src = gen_fp_source(prog, elems, num_channels, nullable_mask, pass);
     if (source_out && source_cap > 0) { strncpy(source_out, src.c_str(), (size_t)source_cap - 1); source_out[source_cap - 1] = 0; }
     std::string cubin;
     st = tg::jit_compile_cubin(&fake, src, &cubin);

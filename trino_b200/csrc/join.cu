@@ -135,25 +135,12 @@ __device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, u
 // Algorithmic bytes per probe row: 8 (key) + 12 (slot) + 4 (position) = 24.
 template <int ROWS, bool INT64_NO_NULLS>
 __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
-                                                         int special_head, int* __restrict__ out, int prefetch)
+                                                         int special_head, int* __restrict__ out)
 {
     int64_t tile = (int64_t)blockDim.x * ROWS;
     int64_t tiles = (n + tile - 1) / tile;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         int64_t base = t * tile + threadIdx.x;
-        if (INT64_NO_NULLS && prefetch) {
-            // pull the slots of the NEXT tile of this CTA towards L2 while this tile is being resolved
-            int64_t nbase = (t + gridDim.x) * tile + threadIdx.x;
-#pragma unroll
-            for (int j = 0; j < ROWS; j++) {
-                int64_t i = nbase + (int64_t)j * blockDim.x;
-                if (i < n) {
-                    unsigned long long nk = (unsigned long long)__ldg((const long long*)key.data + i);
-                    const void* a = &table[join_slot_of(nk, mask)];
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
-                }
-            }
-        }
         unsigned long long k[ROWS];
         bool ok[ROWS];
         int4 s[ROWS];
@@ -667,7 +654,6 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
     const JoinSlot* table = lk->table.as<JoinSlot>();
     bool fast = key.type == TGPU_INT64 && !key.validity;
     int kind = fast ? KEY_INT : key_kind_of(key.type);
-    int prefetch = getenv("TGPU_JOIN_PREFETCH") ? 1 : 0;
     auto k4f = join_probe_kernel<4, true>;
     auto k4a = join_probe_kernel<4, false>;
     int64_t done = 0;
@@ -692,8 +678,8 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
         ColRef kr = tg_colref(key);
         if (done > 0) kr.data = (const char*)kr.data + done * 8;   // only the fast (INT64, no validity) shape gets here with done > 0
         int grid = tg_grid(ctx, n - done, 256 * 4, 8);
-        if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done, prefetch);
-        else TG_LAUNCH(ctx, k4a, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done, prefetch);
+        if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done);
+        else TG_LAUNCH(ctx, k4a, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done);
     }
     TG_TIMED_END(ctx);
     return TGPU_OK;

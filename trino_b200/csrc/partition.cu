@@ -397,15 +397,15 @@ __device__ __forceinline__ unsigned int field16(unsigned long long lo, unsigned 
     return (unsigned int)(((q & 4) ? hi : lo) >> ((q & 3) * 16)) & 0xffffu;
 }
 
-// ALIGNED selects the copy-out: aligned windows per partition run (destinations across NVLink) or one pass in staged order
-// (local destinations: fewer, fuller store instructions)
-template <bool VEC, bool ALIGNED>
+// (An aligned-window copy-out - every warp store one aligned segment of one partition run - was worth +15 % when the stores
+// crossed NVLink and cost 50 % for local destinations; peer destinations no longer use this kernel, so it is gone.)
+template <bool VEC>
 __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t wchunk, int32_t P,
                                                                         const long long* __restrict__ block_off, XchgCols cols)
 {
     __shared__ long long stage_all[WWARPS][WTILE];
     __shared__ long long run_all[WWARPS][8];
-    __shared__ uint8_t spid_all[ALIGNED ? 1 : WWARPS][WTILE];
+    __shared__ uint8_t spid_all[WWARPS][WTILE];
     __shared__ int toff_all[WWARPS][8];
     __shared__ char* sdst[XMAXC * 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
     if (begin >= n) return;
     long long* stage = stage_all[warp];
     long long* run = run_all[warp];
-    uint8_t* spid = spid_all[ALIGNED ? 0 : warp];
+    uint8_t* spid = spid_all[warp];
     int* toff = toff_all[warp];
     if (lane < 8) run[lane] = lane < P ? block_off[(size_t)vchunk * P + lane] : 0;
     __syncwarp();
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
                 acc += field16(tlo, thi, q);
             }
         }
-        if (!ALIGNED && lane < 8) toff[lane] = (int)field16(olo, ohi, lane);
+        if (lane < 8) toff[lane] = (int)field16(olo, ohi, lane);
         unsigned long long pos8 = 0;
 #pragma unroll
         for (int i = 0; i < WR; i++) {
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
             if (q < 8) {
                 unsigned int pos = field16(olo, ohi, q) + field16(elo, ehi, q) + ((unsigned int)(before8 >> (8 * i)) & 0xffu);
                 pos8 |= (unsigned long long)pos << (8 * i);
-                if (!ALIGNED) spid[pos] = (uint8_t)q;
+                spid[pos] = (uint8_t)q;
             }
         }
         for (int c = 0; c < cols.count; c++) {
@@ -527,44 +527,18 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
                     if (((pid8 >> (8 * i)) & 0xffu) < 8) ((char*)stage)[(pos8 >> (8 * i)) & 0xffu] = ((bits >> i) & 1) ? 0 : 1;
             }
             __syncwarp();
-            // copy-out, one partition run at a time: lane l of window w stores the element whose destination address is
-            // (32 x elem)-byte aligned window w + l, so every warp store is one aligned segment (partial only at the two ends
-            // of a run) - unaligned 256-byte stores cost ~25 % of the NVLink write bandwidth (tools/p2p_write_bench.cu)
+            // copy-out in staged order: consecutive lanes write consecutive addresses inside a partition's run
             char* const* dstc = sdst + c * 8;
             const int es = elem ? elem : 1;
-            const int es_shift = es == 8 ? 3 : es == 4 ? 2 : es == 2 ? 1 : 0;
-            if (!ALIGNED) {
-                for (int j = lane; j < tile_rows; j += 32) {
-                    int q = spid[j];
-                    long long d = run[q] + (j - toff[q]);
-                    char* base = dstc[q];
-                    switch (es) {
-                        case 8: ((long long*)base)[d] = stage[j]; break;
-                        case 4: ((int*)base)[d] = ((const int*)stage)[j]; break;
-                        case 2: ((short*)base)[d] = ((const short*)stage)[j]; break;
-                        default: base[d] = ((const char*)stage)[j]; break;
-                    }
-                }
-            }
-            // destinations are visited in an order rotated per warp and tile: if every warp of every GPU walked 0..P-1 in step,
-            // all senders would hit the same receiver's link at once (incast) and stall behind it
-            const int q_first = (int)((vchunk + (tile >> 8)) % P);
-            for (int qi = 0; ALIGNED && qi < P; qi++) {
-                const int q = qi + q_first < P ? qi + q_first : qi + q_first - P;
-                const int cnt = (int)field16(tlo, thi, q);
-                if (cnt == 0) continue;
-                const int s0 = (int)field16(olo, ohi, q);
-                const long long d0 = run[q];
+            for (int j = lane; j < tile_rows; j += 32) {
+                int q = spid[j];
+                long long d = run[q] + (j - toff[q]);
                 char* base = dstc[q];
-                const int a = (int)((((unsigned long long)base >> es_shift) + (unsigned long long)d0) & 31);
-                for (int k = lane - a; k < cnt; k += 32) {
-                    if (k < 0) continue;
-                    switch (es) {
-                        case 8: ((long long*)base)[d0 + k] = stage[s0 + k]; break;
-                        case 4: ((int*)base)[d0 + k] = ((const int*)stage)[s0 + k]; break;
-                        case 2: ((short*)base)[d0 + k] = ((const short*)stage)[s0 + k]; break;
-                        default: base[d0 + k] = ((const char*)stage)[s0 + k]; break;
-                    }
+                switch (es) {
+                    case 8: ((long long*)base)[d] = stage[j]; break;
+                    case 4: ((int*)base)[d] = ((const int*)stage)[j]; break;
+                    case 2: ((short*)base)[d] = ((const short*)stage)[j]; break;
+                    default: base[d] = ((const char*)stage)[j]; break;
                 }
             }
             __syncwarp();
@@ -616,17 +590,13 @@ static int xchg_launch_hist(tgpu_ctx* ctx, const XchgGeom& g, const KeyCols& k, 
     return TGPU_OK;
 }
 
-static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* pids, int64_t n, int32_t P, const long long* block_off, const XchgCols& xc,
-                               bool remote)
+static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* pids, int64_t n, int32_t P, const long long* block_off, const XchgCols& xc)
 {
     if (g.warp_mode) {
         bool vec = ((uintptr_t)pids & 7) == 0;
         for (int c = 0; c < xc.count; c++) vec = vec && ((uintptr_t)xc.src[c] & 15) == 0;
-        remote = remote && getenv("TGPU_XCHG_ALIGNED");   // aligned-window copy-out: kept for experiments, not used by default
-        if (vec && remote) TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<true, true>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
-        else if (vec) TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<true, false>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
-        else if (remote) TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<false, true>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
-        else TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<false, false>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
+        if (vec) TG_LAUNCH(ctx, xchg_scatter_warp_kernel<true>, g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
+        else TG_LAUNCH(ctx, xchg_scatter_warp_kernel<false>, g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
         return TGPU_OK;
     }
     TG_LAUNCH(ctx, xchg_scatter_kernel<4>, g.grid, XT, 0, pids, n, g.chunk, P, block_off, xc);
@@ -848,7 +818,7 @@ struct PartitionOp : tgpu_op {
         xc.count = (int32_t)lanes.size();
         for (size_t l = 0; l < lanes.size(); l++) { xc.elem[l] = lanes[l].elem; xc.src[l] = lanes[l].src; }
         xc.dst = d_dst.as<char*>();
-        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, P, block_off.as<long long>(), xc, false));
+        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, P, block_off.as<long long>(), xc));
         mark("scatter");
         for (int q = 0; q < P; q++) {
             if (counts[q] == 0) continue;
@@ -1235,7 +1205,7 @@ extern "C" int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitio
         xc.count = (int32_t)lanes.size();
         for (size_t l = 0; l < lanes.size(); l++) { xc.elem[l] = lanes[l].elem; xc.src[l] = lanes[l].src; }
         xc.dst = d_dst.as<char*>();
-        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc, p2p));
+        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc));
     }
     mark("scatter");
     if (p2p) {
@@ -1460,7 +1430,7 @@ extern "C" int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tg
         xc.count = (int32_t)L;
         for (size_t l = 0; l < L; l++) { xc.elem[l] = x->lanes[l].elem; xc.src[l] = srcs[l]; }
         xc.dst = d_dst.as<char*>();
-        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc, false));
+        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc));
     }
     // 4. hand over to the copy engines.  The event also orders the transfer behind everything enqueued on this context so far:
     //    the readers of the arena this exchange's peers will overwrite NEXT (see the header).
