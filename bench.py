@@ -139,9 +139,10 @@ def workload_config(args, n_orders, probe_rows, world):
                         f"probe payload l_extendedprice FLOAT64 (BASELINE.json configs[1])",
             "build_rows_per_gpu": n_orders, "probe_rows_per_gpu": probe_rows, "probe_order": "orderkey-clustered" if not args.shuffle_probe else "shuffled",
             "parallelism": (f"hash-partitioned x{world}, probe side exchanged every step " +
-                            ("over NCCL send/recv" if os.environ.get("TGPU_EXCHANGE_NCCL") else "by P2P stores into peer HBM (NVLink)") +
-                            ("" if os.environ.get("TGPU_BENCH_SERIAL") or os.environ.get("TGPU_EXCHANGE_NCCL") else
-                             ", two half-pages per step, split-phase: SMs partition page k+1 and probe page k while copy engines move page k+1")) if world > 1 else "single GPU",
+                            ("over NCCL send/recv" if os.environ.get("TGPU_EXCHANGE_NCCL") else
+                             "by SM stores into peer HBM (NVLink)" if os.environ.get("TGPU_BENCH_SERIAL") else
+                             "into peer HBM over NVLink by the copy engines, two half-pages per step, split-phase: SMs partition page k+1 and probe page k "
+                             "while page k+1 is in flight")) if world > 1 else "single GPU",
             "l2": "inputs (9.6 GB probe side, 4.3 GB table at SF100) are far larger than the 126 MB L2; no flush needed"}
 
 
@@ -402,6 +403,8 @@ def main():
     e2e = None
     if world == 1:
         e2e = bench_e2e(ctx, args, bridge, d_lkeys, d_lprice_col.ptr, l_count)
+    elif overlap:
+        e2e = bench_e2e_dist(ctx, args, dist, local, world, partitioner, probe_op, d_lkeys, d_lprice_col.ptr, l_count)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -536,6 +539,87 @@ def bench_e2e(ctx, args, bridge, d_keys, d_price, n, drivers=int(os.environ.get(
         d.op.close()
         d.ctx.close()
     return out
+
+
+def bench_e2e_dist(ctx, args, dist, local, world, partitioner, probe_op, d_keys, d_price, n):
+    """N > 1: every rank feeds its probe rows from pinned host pages through the split-phase exchange and the probe, and reads the
+    joined rows back (probe key, probe payload, build payload: the received rows are not the host's own blocks, so all three
+    columns come back).  Same call sequence on every rank (the exchange is collective); time = max over ranks."""
+    import torch
+    from trino_b200 import abi
+    from trino_b200.page import Block, Page, AbiPage
+    lib = ctx.lib
+    chunk = 32 << 20
+    cap = torch.tensor([n if args.e2e_rows <= 0 else min(n, args.e2e_rows)], dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(cap, op=dist.ReduceOp.MIN)            # identical chunk count on every rank
+    total = int(cap.item())
+    h_keys = ctx.pinned_empty(total, np.int64)
+    h_price = ctx.pinned_empty(total, np.float64)
+    ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(h_keys.ctypes.data), C.c_void_p(d_keys), total * 8))
+    ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(h_price.ctypes.data), C.c_void_p(d_price), total * 8))
+    land = int(chunk * 1.5) + 1024                          # a rank may receive more rows than it sent
+    bufs = [ctx.pinned_empty(land, np.int64), ctx.pinned_empty(land, np.float64), ctx.pinned_empty(land, np.int64)]
+    valid = [np.empty(land // 8 + 8, np.uint8) for _ in range(3)]
+    host_cols = (abi.Column * 3)()
+    chunks = [(lo, min(total, lo + chunk)) for lo in range(0, total, chunk)]
+    state = {"rows": 0, "d2h": 0}
+
+    def take_output():
+        pp = abi.PP()
+        ctx.check(lib.tgpu_op_get_output(probe_op.h, C.byref(pp)))
+        if not pp:
+            return
+        m = pp.contents.num_rows
+        for col, (arr, t) in enumerate(zip(bufs, (abi.INT64, abi.FLOAT64, abi.INT64))):
+            host_cols[col].type = t
+            host_cols[col].validity = valid[col].ctypes.data
+            host_cols[col].data = arr.ctypes.data
+        hp = abi.Page(3, 0, m, C.cast(host_cols, C.POINTER(abi.Column)))
+        ctx.check(lib.tgpu_page_copy_to_host(ctx.h, pp, C.byref(hp)))
+        lib.tgpu_page_release(ctx.h, pp)
+        state["rows"] += m
+        state["d2h"] += m * 24
+
+    def one_pass():
+        state["rows"] = state["d2h"] = 0
+        handles, pages, inflight = [], [], []
+
+        def finish_one():
+            if inflight:
+                take_output()
+                lib.tgpu_page_release(ctx.h, inflight.pop())
+            pp = abi.PP()
+            ctx.check(lib.tgpu_exchange_end(ctx.h, handles.pop(0), C.byref(pp)))
+            pages.pop(0)
+            ctx.check(lib.tgpu_op_add_input(probe_op.h, pp))
+            inflight.append(pp)
+
+        for lo, hi in chunks:
+            ap = AbiPage(Page(Block(abi.INT64, h_keys[lo:hi]), Block(abi.FLOAT64, h_price[lo:hi])))
+            h = C.c_void_p()
+            ctx.check(lib.tgpu_exchange_begin(ctx.h, partitioner.h, ap.ref(), C.byref(h)))
+            handles.append(h)
+            pages.append(ap)
+            if len(handles) > 1:
+                finish_one()
+        while handles:
+            finish_one()
+        if inflight:
+            take_output()
+            lib.tgpu_page_release(ctx.h, inflight.pop())
+
+    one_pass()
+    dist.barrier()
+    t0 = time.time()
+    one_pass()
+    dt = torch.tensor([time.time() - t0], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    rows = torch.tensor([float(state["rows"]), float(state["d2h"])], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(rows)
+    return {"value": float(rows[0].item()) / float(dt.item()), "unit": "rows/s", "h2d_bytes_per_step": int(total * 16) * world, "d2h_bytes_per_step": int(rows[1].item()),
+            "rows_per_step": int(rows[0].item()), "host_page_rows": chunk,
+            "timing": "wall clock (max over ranks) around one pass of every rank's probe rows: pinned host pages -> tgpu_exchange_begin/_end -> "
+                      "LookupJoinOperator -> page_copy_to_host of all three output columns"}
 
 
 def bench_q1(ctx, args):
