@@ -106,3 +106,119 @@ def random_bigint_block(rng, n, lo, hi, null_frac=0.0):
     v = rng.integers(lo, hi, size=n, dtype=np.int64)
     nulls = rng.random(n) < null_frac if null_frac > 0 else None
     return Block.bigint(v, nulls)
+
+
+def oracle_agg_rows(pages, key_channels, aggs):
+    """group-id order rows: keys then aggregate values (None = NULL), sequential left fold like the reference"""
+    import numpy as np
+    import oracle_lib as o
+    from trino_b200 import abi
+    lib = o.load()
+    og = o.GroupByHash(0, 16)
+    state = []
+    keyrows = {}
+    for page in pages:
+        ids = og.get_group_ids(page, key_channels)
+        G = og.group_count()
+        for i, gid in enumerate(ids):
+            if gid not in keyrows:
+                keyrows[int(gid)] = tuple(page.get_block(c).flatten().get(i) for c in key_channels)
+        for ai, (fn, ch, mask) in enumerate(aggs):
+            if len(state) <= ai:
+                state.append({"sum": np.zeros(0), "cnt": np.zeros(0, np.int64), "isum": np.zeros(0, np.int64), "nn": np.zeros(0, np.uint8), "acc": np.zeros(0), "iacc": np.zeros(0, np.int64)})
+            st = state[ai]
+            for k in [k for k in st if k != "dbl"]:
+                if len(st[k]) < G:
+                    st[k] = np.concatenate([st[k], np.zeros(G - len(st[k]), st[k].dtype)])
+            blk = page.get_block(ch).flatten() if ch >= 0 else None
+            valid = None
+            if blk is not None and blk.nulls is not None:
+                valid = np.packbits(~blk.nulls, bitorder="little")
+            sel = None
+            if mask >= 0:
+                mb = page.get_block(mask).flatten()
+                sel = ((mb.values != 0) & (~mb.nulls if mb.nulls is not None else True)).astype(np.uint8)
+            n = page.position_count
+            P = o._p
+            ids32 = np.ascontiguousarray(ids, np.int32)
+            is_dbl = blk is not None and blk.type == abi.FLOAT64
+            vals = None if blk is None else np.ascontiguousarray(blk.values.astype(np.float64 if is_dbl else np.int64))
+            if fn == abi.AGG_COUNT_STAR:
+                lib.orc_agg_count(P(ids32), n, None, P(sel), P(st["cnt"]))
+            elif fn == abi.AGG_COUNT:
+                lib.orc_agg_count(P(ids32), n, P(valid), P(sel), P(st["cnt"]))
+            elif fn == abi.AGG_SUM and is_dbl:
+                lib.orc_agg_sum_double(P(ids32), n, P(vals), P(valid), P(sel), P(st["sum"]), P(st["nn"]))
+            elif fn == abi.AGG_SUM:
+                assert lib.orc_agg_sum_bigint(P(ids32), n, P(vals), P(valid), P(sel), P(st["isum"]), P(st["nn"])) == 0
+            elif fn == abi.AGG_AVG:
+                fvals = np.ascontiguousarray(vals.astype(np.float64))   # keep alive across the call
+                lib.orc_agg_avg_double(P(ids32), n, P(fvals), P(valid), P(sel), P(st["sum"]), P(st["cnt"]))
+            elif is_dbl:
+                lib.orc_agg_minmax_double(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["acc"]), P(st["nn"]))
+            else:
+                lib.orc_agg_minmax_bigint(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["iacc"]), P(st["nn"]))
+            st["dbl"] = is_dbl
+    G = og.group_count()
+    rows = []
+    for g in range(G):
+        r = list(keyrows[g])
+        for ai, (fn, ch, mask) in enumerate(aggs):
+            st = state[ai]
+            if fn in (abi.AGG_COUNT_STAR, abi.AGG_COUNT):
+                r.append(int(st["cnt"][g]))
+            elif fn == abi.AGG_SUM:
+                r.append(None if not st["nn"][g] else (float(st["sum"][g]) if st["dbl"] else int(st["isum"][g])))
+            elif fn == abi.AGG_AVG:
+                r.append(None if st["cnt"][g] == 0 else float(st["sum"][g]) / float(st["cnt"][g]))
+            else:
+                r.append(None if not st["nn"][g] else (float(st["acc"][g]) if st["dbl"] else int(st["iacc"][g])))
+        rows.append(tuple(r))
+    og.close()
+    return rows
+
+
+
+
+def aggregation_known_answer_cases():
+    """The sequences of the reference's AbstractTestAggregationFunction (:70-127: testNoPositions is omitted - a grouped aggregation
+    without rows has no group -, testSinglePosition, testMultiplePositions, testAllPositionsNull, testMixedNullAndNonNullPositions,
+    testNegativeOnlyValues, testPositiveOnlyValues) with the expected values of TestDoubleSumAggregation.java:38-50,
+    TestDoubleAverageAggregation.java:38-50, TestCountAggregation / TestLongSumAggregation (same formulas over BIGINT)."""
+    import numpy as np
+    cases = []
+    for name, start, length, total, pattern in (("single", 0, 1, 1, "none"), ("multiple", 0, 5, 5, "none"), ("all_null", 0, 0, 10, "all"),
+                                                ("alternating", 0, 10, 20, "alternate"), ("negative", -10, 5, 5, "none"), ("positive", 2, 4, 4, "none")):
+        if pattern == "none":
+            values = np.arange(start, start + length)
+            nulls = None
+        elif pattern == "all":
+            values = np.zeros(total, dtype=np.int64)
+            nulls = np.ones(total, dtype=bool)
+        else:       # AbstractTestAggregationFunction.createAlternatingNullsBlock: null, v0, null, v1, ...
+            values = np.repeat(np.arange(start, start + length), 2)
+            nulls = np.tile(np.array([True, False]), length)
+        seq = [float(i) for i in range(start, start + length)]
+        s = 0.0
+        for v in seq:
+            s += v
+        cases.append({"name": name, "values": values, "nulls": nulls, "count_star": total, "count": length, "sum_double": s if length else None,
+                      "avg_double": (s / length) if length else None, "sum_bigint": int(sum(range(start, start + length))) if length else None,
+                      "min": float(start) if length else None, "max": float(start + length - 1) if length else None})
+    return cases
+
+
+def hash_aggregation_operator_case(number_of_rows=40_000):
+    """TestHashAggregationOperator.testHashAggregation (:138-188) restated over BIGINT channels (the GPU path takes dictionary codes
+    where the reference test uses VARCHAR; max(varchar) is left out): three sequence pages, group key = channel 1 starting at 0,
+    aggregates count(*), sum(ch3), avg(ch3), count(ch0), count(ch4 boolean).  Expected row i: (i, 3, 3*i, float(i), 3, 3)."""
+    import numpy as np
+    from trino_b200 import abi
+    from trino_b200.page import Block, Page
+    pages = []
+    for start2 in (100_000, 200_000, 300_000):
+        seq = np.arange(number_of_rows, dtype=np.int64)
+        pages.append(Page(Block.bigint(100 + seq), Block.bigint(seq), Block.bigint(start2 + seq), Block.bigint(seq), Block.boolean((500 + seq) % 2 == 0)))
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 3, -1), (abi.AGG_AVG, 3, -1), (abi.AGG_COUNT, 0, -1), (abi.AGG_COUNT, 4, -1)]
+    expected = [(i, 3, 3 * i, float(i), 3, 3) for i in range(number_of_rows)]
+    return pages, [1], aggs, expected

@@ -155,3 +155,17 @@ def test_chunked_two_pass_form_matches_selection_vector_form(ctx, selectivity, m
     assert got == want
     monkeypatch.setenv("TGPU_FP_SELECTION_VECTOR", "1")
     assert run(ctx, prog, pages) == want
+
+
+def test_page_processor_reference_cases(ctx):
+    """TestPageProcessor.java :126-175 restated with expression filters: testPartialFilter (positionsRange(25, 50) of a 0..99 sequence
+    -> rows 25..74 through InputPageProjection(0)), testSelectAllFilter (the page itself), testSelectNoneFilter (no output page)."""
+    seq = Page(Block.bigint(np.arange(100)))
+    c = ops.Col(0, B)
+    partial = ops.Call(abi.EX_AND, ops.Call(abi.EX_GE, c, ops.Const(25, B)), ops.Call(abi.EX_LT, c, ops.Const(75, B)))
+    assert run(ctx, ops.PageProcessorProgram(partial, [0]), [seq]) == [(i,) for i in range(25, 75)]
+    assert run(ctx, ops.PageProcessorProgram(ops.Call(abi.EX_GE, c, ops.Const(0, B)), [0]), [seq]) == [(i,) for i in range(100)]
+    op = ops.FilterAndProjectOperatorFactory(ctx, ops.PageProcessorProgram(ops.Call(abi.EX_LT, c, ops.Const(0, B)), [0])).create_operator()
+    op.add_input(seq)
+    assert op.get_output() is None
+    op.close()

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as o
-from helpers import rows_equal
+from helpers import aggregation_known_answer_cases, hash_aggregation_operator_case, rows_equal
 from q1 import CUTOFF, q1_gpu_rows
 from trino_b200 import abi
 from trino_b200 import operators as ops
@@ -105,71 +105,7 @@ def test_aggregation_with_wide_composite_keys(ctx):
 
 
 # ---------------------------------------------------------------- aggregation
-def _oracle_agg(pages, key_channels, aggs):
-    """group-id order rows: keys then aggregate values (None = NULL), sequential left fold like the reference"""
-    lib = o.load()
-    og = o.GroupByHash(0, 16)
-    state = []
-    keyrows = {}
-    for page in pages:
-        ids = og.get_group_ids(page, key_channels)
-        G = og.group_count()
-        for i, gid in enumerate(ids):
-            if gid not in keyrows:
-                keyrows[int(gid)] = tuple(page.get_block(c).flatten().get(i) for c in key_channels)
-        for ai, (fn, ch, mask) in enumerate(aggs):
-            if len(state) <= ai:
-                state.append({"sum": np.zeros(0), "cnt": np.zeros(0, np.int64), "isum": np.zeros(0, np.int64), "nn": np.zeros(0, np.uint8), "acc": np.zeros(0), "iacc": np.zeros(0, np.int64)})
-            st = state[ai]
-            for k in [k for k in st if k != "dbl"]:
-                if len(st[k]) < G:
-                    st[k] = np.concatenate([st[k], np.zeros(G - len(st[k]), st[k].dtype)])
-            blk = page.get_block(ch).flatten() if ch >= 0 else None
-            valid = None
-            if blk is not None and blk.nulls is not None:
-                valid = np.packbits(~blk.nulls, bitorder="little")
-            sel = None
-            if mask >= 0:
-                mb = page.get_block(mask).flatten()
-                sel = ((mb.values != 0) & (~mb.nulls if mb.nulls is not None else True)).astype(np.uint8)
-            n = page.position_count
-            P = o._p
-            ids32 = np.ascontiguousarray(ids, np.int32)
-            is_dbl = blk is not None and blk.type == abi.FLOAT64
-            vals = None if blk is None else np.ascontiguousarray(blk.values.astype(np.float64 if is_dbl else np.int64))
-            if fn == abi.AGG_COUNT_STAR:
-                lib.orc_agg_count(P(ids32), n, None, P(sel), P(st["cnt"]))
-            elif fn == abi.AGG_COUNT:
-                lib.orc_agg_count(P(ids32), n, P(valid), P(sel), P(st["cnt"]))
-            elif fn == abi.AGG_SUM and is_dbl:
-                lib.orc_agg_sum_double(P(ids32), n, P(vals), P(valid), P(sel), P(st["sum"]), P(st["nn"]))
-            elif fn == abi.AGG_SUM:
-                assert lib.orc_agg_sum_bigint(P(ids32), n, P(vals), P(valid), P(sel), P(st["isum"]), P(st["nn"])) == 0
-            elif fn == abi.AGG_AVG:
-                fvals = np.ascontiguousarray(vals.astype(np.float64))   # keep alive across the call
-                lib.orc_agg_avg_double(P(ids32), n, P(fvals), P(valid), P(sel), P(st["sum"]), P(st["cnt"]))
-            elif is_dbl:
-                lib.orc_agg_minmax_double(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["acc"]), P(st["nn"]))
-            else:
-                lib.orc_agg_minmax_bigint(P(ids32), n, P(vals), P(valid), int(fn == abi.AGG_MAX), P(st["iacc"]), P(st["nn"]))
-            st["dbl"] = is_dbl
-    G = og.group_count()
-    rows = []
-    for g in range(G):
-        r = list(keyrows[g])
-        for ai, (fn, ch, mask) in enumerate(aggs):
-            st = state[ai]
-            if fn in (abi.AGG_COUNT_STAR, abi.AGG_COUNT):
-                r.append(int(st["cnt"][g]))
-            elif fn == abi.AGG_SUM:
-                r.append(None if not st["nn"][g] else (float(st["sum"][g]) if st["dbl"] else int(st["isum"][g])))
-            elif fn == abi.AGG_AVG:
-                r.append(None if st["cnt"][g] == 0 else float(st["sum"][g]) / float(st["cnt"][g]))
-            else:
-                r.append(None if not st["nn"][g] else (float(st["acc"][g]) if st["dbl"] else int(st["iacc"][g])))
-        rows.append(tuple(r))
-    og.close()
-    return rows
+from helpers import oracle_agg_rows as _oracle_agg  # noqa: E402
 
 
 def _gpu_agg(ctx, pages, key_channels, aggs, step=abi.STEP_SINGLE, expected=100, max_partial=0):
@@ -222,6 +158,24 @@ def test_general_path_slice_by_slice_matches_oracle(ctx, monkeypatch):
     assert rows_equal(got, want, rel=1e-6)
     assert [r[0] for r in got] == [r[0] for r in want]
     assert [(r[1], r[4], r[7], r[12]) for r in got] == [(r[1], r[4], r[7], r[12]) for r in want]
+
+
+def test_accumulator_known_answers(ctx):
+    # the reference's AbstractTestAggregationFunction sequences (see helpers.aggregation_known_answer_cases): exact here, the sums are
+    # of small integers
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_COUNT, 1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_MAX, 1, -1),
+            (abi.AGG_SUM, 2, -1), (abi.AGG_COUNT, 2, -1)]
+    for case in aggregation_known_answer_cases():
+        n = len(case["values"])
+        page = Page(Block.bigint(np.zeros(n, dtype=np.int64)), Block.double(case["values"].astype(np.float64), case["nulls"]), Block.bigint(case["values"], case["nulls"]))
+        got = _gpu_agg(ctx, [page], [0], aggs)
+        assert got == [(0, case["count_star"], case["count"], case["sum_double"], case["avg_double"], case["min"], case["max"], case["sum_bigint"], case["count"])], case["name"]
+
+
+def test_hash_aggregation_operator_reference_case(ctx):
+    # TestHashAggregationOperator.testHashAggregation :138-188 (restated over BIGINT channels), full size: 40 000 groups in 3 pages
+    pages, keys, aggs, expected = hash_aggregation_operator_case()
+    assert _gpu_agg(ctx, pages, keys, aggs, expected=100_000) == expected
 
 
 def test_small_path_spills_into_general_path(ctx):

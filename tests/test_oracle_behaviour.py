@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as o
-from helpers import join_type_of, oracle_outer_rows, oracle_join_rows, reference_cases, rows_equal
+from helpers import aggregation_known_answer_cases, hash_aggregation_operator_case, join_type_of, oracle_agg_rows, oracle_outer_rows, oracle_join_rows, reference_cases, rows_equal
 from trino_b200 import abi
 from trino_b200.page import Block, DictionaryBlock, Page, RunLengthEncodedBlock
 
@@ -220,3 +220,19 @@ def test_semi_join_reference_cases():
         assert got == case["expected"], case["source"]
     # an empty set answers false even for a NULL probe (HashSemiJoinOperator.java:184-187)
     assert o.semi_join_bigint(Block.bigint([]), Block.bigint([1, None])) == [False, False]
+
+
+def test_accumulator_known_answers():
+    # AbstractTestAggregationFunction sequences with the expected values of TestDoubleSum/TestDoubleAverage/TestCount/TestLongSum
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_COUNT, 1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_MAX, 1, -1),
+            (abi.AGG_SUM, 2, -1), (abi.AGG_COUNT, 2, -1)]
+    for case in aggregation_known_answer_cases():
+        n = len(case["values"])
+        page = Page(Block.bigint(np.zeros(n, dtype=np.int64)), Block.double(case["values"].astype(np.float64), case["nulls"]), Block.bigint(case["values"], case["nulls"]))
+        rows = oracle_agg_rows([page], [0], aggs)
+        assert rows == [(0, case["count_star"], case["count"], case["sum_double"], case["avg_double"], case["min"], case["max"], case["sum_bigint"], case["count"])], case["name"]
+
+
+def test_hash_aggregation_operator_reference_case():
+    pages, keys, aggs, expected = hash_aggregation_operator_case(4000)
+    assert oracle_agg_rows(pages, keys, aggs) == expected
