@@ -290,6 +290,7 @@ struct FilterProjectOp : tgpu_op {
 
     int add_input(const tgpu_page* page) override
     {
+        for (size_t i = next_out; i < pending.size(); i++) delete pending[i];   // pages the caller never took
         pending.clear();
         next_out = 0;
         int64_t n = page->num_rows;
