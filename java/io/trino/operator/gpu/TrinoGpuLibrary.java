@@ -38,6 +38,17 @@ public final class TrinoGpuLibrary
     static final MethodHandle JOIN_BUILD_GET_LOOKUP = handle("tgpu_join_build_get_lookup", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle JOIN_PROBE_CREATE = handle("tgpu_join_probe_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle LOOKUP_RELEASE = handle("tgpu_lookup_release", FunctionDescriptor.ofVoid(ADDRESS));
+    // LookupJoinPageBuilder.build :144-150: probe blocks of a 1:1 page stay on the heap, only the join key is uploaded
+    static final MethodHandle JOIN_PROBE_BY_REFERENCE = handle("tgpu_join_probe_set_passthrough_by_reference", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    static final MethodHandle PAGE_PASSTHROUGH_CHANNEL = handle("tgpu_page_passthrough_channel", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    // LookupOuterOperator / HashSemiJoinOperator / DynamicFilterSourceOperator counterparts
+    static final MethodHandle JOIN_OUTER_CREATE = handle("tgpu_join_outer_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle SEMI_JOIN_CREATE = handle("tgpu_semi_join_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle LOOKUP_KEY_DOMAIN = handle("tgpu_lookup_key_domain",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    // exchange between two GPU stages inside one box (replaces PartitionedOutputOperator -> OutputBuffer -> HTTP -> ExchangeOperator)
+    static final MethodHandle EXCHANGE_BEGIN = handle("tgpu_exchange_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle EXCHANGE_END = handle("tgpu_exchange_end", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle PARTITION_CREATE = handle("tgpu_partition_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle PARTITION_LAST_OUTPUT = handle("tgpu_partition_last_output_partition", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     // Operator protocol (M/operator/Operator.java:21-102)
