@@ -550,7 +550,15 @@ def bench_e2e_dist(ctx, args, dist, local, world, partitioner, probe_op, d_keys,
     from trino_b200.page import Block, Page, AbiPage
     lib = ctx.lib
     chunk = 32 << 20
-    cap = torch.tensor([n if args.e2e_rows <= 0 else min(n, args.e2e_rows)], dtype=torch.int64, device=f"cuda:{local}")
+    want = n if args.e2e_rows <= 0 else min(n, args.e2e_rows)
+    try:
+        avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+    except Exception:
+        avail = 32 << 30
+    budget = int(avail * 0.5 / world)                       # pinned host memory this rank may take
+    if want * 16 + 4 * chunk * 24 > budget:
+        want = max(chunk, (budget - 4 * chunk * 24) // 16)
+    cap = torch.tensor([want], dtype=torch.int64, device=f"cuda:{local}")
     dist.all_reduce(cap, op=dist.ReduceOp.MIN)            # identical chunk count on every rank
     total = int(cap.item())
     h_keys = ctx.pinned_empty(total, np.int64)
