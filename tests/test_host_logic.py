@@ -80,3 +80,24 @@ def test_factory_protocol():
         ops.HashBuilderOperatorFactory(None, ops.JoinBridge(), [0], []).duplicate()
     with pytest.raises(RuntimeError):
         ops.LookupJoinOperatorFactory(None, ops.JoinBridge(), abi.JOIN_INNER, False, [0], [0]).create_operator()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) on a tiny scale factor: one JSON line with the
+    contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--sf", "0.02", "--steps", "1", "--warmup", "1", "--cpu-sample-rows", "50000"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env={**os.environ, "RANK": "0", "WORLD_SIZE": "1"})
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "hash_join_probe_rows_per_sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
