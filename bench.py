@@ -557,7 +557,7 @@ def bench_e2e_dist(ctx, args, dist, local, world, partitioner, probe_op, d_keys,
         avail = 32 << 30
     budget = int(avail * 0.5 / world)                       # pinned host memory this rank may take
     if want * 16 + 4 * chunk * 24 > budget:
-        want = max(chunk, (budget - 4 * chunk * 24) // 16)
+        want = min(want, max(chunk, (budget - 4 * chunk * 24) // 16))
     cap = torch.tensor([want], dtype=torch.int64, device=f"cuda:{local}")
     dist.all_reduce(cap, op=dist.ReduceOp.MIN)            # identical chunk count on every rank
     total = int(cap.item())
