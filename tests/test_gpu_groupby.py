@@ -178,6 +178,21 @@ def test_hash_aggregation_operator_reference_case(ctx):
     assert _gpu_agg(ctx, pages, keys, aggs, expected=100_000) == expected
 
 
+def test_general_path_physical_slices_match_oracle(ctx, monkeypatch):
+    # EXPERIMENTAL (branch wip/path-g-physical): the sliced pass over a slice-ordered COPY of the page (multi-split scatter of the
+    # channels the plan reads + page row numbers for the stamps) instead of a row list
+    monkeypatch.setenv("TGPU_AGG_PHYSICAL_SLICES", "1")
+    monkeypatch.setenv("TGPU_AGG_SLICE_MIN_BYTES", "0")
+    monkeypatch.setenv("TGPU_AGG_SLICE_BYTES", str(256 << 10))
+    rng = np.random.default_rng(78)
+    pages = _agg_pages(rng, 20000, (60000, 7, 90000)) + _agg_pages(rng, 400000, (150000,))
+    got = _gpu_agg(ctx, pages, [0], AGGS, expected=30000)
+    want = _oracle_agg(pages, [0], AGGS)
+    assert rows_equal(got, want, rel=1e-6)
+    assert [r[0] for r in got] == [r[0] for r in want]
+    assert [(r[1], r[4], r[7], r[12]) for r in got] == [(r[1], r[4], r[7], r[12]) for r in want]
+
+
 def test_small_path_spills_into_general_path(ctx):
     # first page has few groups (path S), the next one thousands: state must migrate without losing ids or sums
     rng = np.random.default_rng(99)

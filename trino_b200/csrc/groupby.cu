@@ -31,6 +31,7 @@
 
 #include "expr.cuh"
 #include "jit.cuh"
+#include "multisplit.cuh"
 
 namespace {
 
@@ -722,8 +723,10 @@ __device__ __forceinline__ void gf_decode(const AggPlan& plan, unsigned long lon
     }
 }
 
-// `rows` == nullptr: rows [0, n) of the page; else the deferred row list
-__global__ void __launch_bounds__(256) gf_page_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ rows, long long page_base,
+// `rows` == nullptr: rows [first, first + n) of `cols`; else the deferred row list.  `stamp_rows`: cols is a slice-ordered copy of the
+// page, stamp_rows[row] is the row's position in the page (first-row stamps must follow page order)
+__global__ void __launch_bounds__(256) gf_page_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ rows, int64_t first,
+                                                     const int* __restrict__ stamp_rows, long long page_base,
                                                      unsigned long long* __restrict__ recs, int64_t cap, int W, int* __restrict__ tickets, int budget,
                                                      int* __restrict__ deferred)
 {
@@ -731,7 +734,7 @@ __global__ void __launch_bounds__(256) gf_page_kernel(AggPlan plan, DColumns col
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        int64_t row = rows ? rows[i] : i;
+        int64_t row = rows ? rows[i] : first + i;
         unsigned long long pk = 0;
         int sp = pack_key(plan, cols, row, nullptr, 0, 0, &pk);
         int64_t s = -1;
@@ -759,7 +762,7 @@ __global__ void __launch_bounds__(256) gf_page_kernel(AggPlan plan, DColumns col
         }
         if (s < 0) { deferred[atomicAdd(tickets + 1, 1)] = (int)row; continue; }
         unsigned long long* r = gf_rec(recs, s, W);
-        long long stamp = page_base + row;
+        long long stamp = page_base + (stamp_rows ? (long long)stamp_rows[row] : row);
         if (*((volatile long long*)(r + 1)) > stamp) {
             long long old = atomicMin((long long*)(r + 1), stamp);
             if (old == NO_ROW && s >= cap) atomicAdd(tickets + 2, 1);   // a special (NULL / sentinel key) group came to life
@@ -797,6 +800,27 @@ __global__ void gf_iota_kernel(int* __restrict__ out, int64_t n)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) out[i] = (int)i;
+}
+
+// per-chunk histogram form of gf_slice_ids_kernel for the multi-split scatter (chunks as in multisplit.cuh, CTA granularity)
+__global__ void __launch_bounds__(XT) gf_slice_hist_kernel(AggPlan plan, DColumns cols, int64_t n, int64_t chunk, int64_t cap, int shift, int S,
+                                                          uint8_t* __restrict__ ids, unsigned int* __restrict__ hist /* [chunks][S] */)
+{
+    __shared__ unsigned int sh[XMAXP];
+    for (int i = threadIdx.x; i < S; i += XT) sh[i] = 0;
+    __syncthreads();
+    const unsigned long long mask = (unsigned long long)cap - 1;
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
+    for (int64_t row = begin + threadIdx.x; row < end; row += XT) {
+        unsigned long long pk = 0;
+        int sp = pack_key(plan, cols, row, nullptr, 0, 0, &pk);
+        int id = sp >= 0 ? 0 : (int)((murmur3_mix(pk) & mask) >> shift);
+        ids[row] = (uint8_t)id;
+        unsigned int peers = __match_any_sync(__activemask(), id);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[id], __popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += XT) hist[(size_t)blockIdx.x * S + i] = sh[i];
 }
 
 // table growth: move every used record into the bigger table
@@ -1714,7 +1738,7 @@ struct AggOp : tgpu_op {
     }
 
     // one gf_page_kernel pass over `todo` rows (`rows` == nullptr: rows [0, todo) of the page), replaying deferred rows after growth
-    int run_fused_rows(const DColumns& cols, const int* rows, int64_t todo)
+    int run_fused_rows(const DColumns& cols, const int* rows, int64_t todo, int64_t first = 0, const int* stamp_rows = nullptr)
     {
         DevBuf deferred, replay;
         TG_TRY(deferred.alloc(ctx, (size_t)std::max<int64_t>(todo, 1) * 4));
@@ -1723,7 +1747,7 @@ struct AggOp : tgpu_op {
             int64_t budget = f_cap * 3 / 4 - f_used;
             TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 16, ctx->stream));
             TG_TIMED_BEGIN(ctx);
-            TG_LAUNCH(ctx, gf_page_kernel, tg_grid(ctx, todo, 256, 8), 256, 0, plan, cols, todo, rows, (long long)rows_seen, f_recs.as<unsigned long long>(), f_cap,
+            TG_LAUNCH(ctx, gf_page_kernel, tg_grid(ctx, todo, 256, 8), 256, 0, plan, cols, todo, rows, first, stamp_rows, (long long)rows_seen, f_recs.as<unsigned long long>(), f_cap,
                       gf_words(), d_tickets, (int)std::min<int64_t>(std::max<int64_t>(budget, 0), INT32_MAX), deferred.as<int>());
             TG_TIMED_END(ctx);
             int32_t counters[4] = {0, 0, 0, 0};
@@ -1744,6 +1768,84 @@ struct AggOp : tgpu_op {
         return TGPU_OK;
     }
 
+    // Sliced pass over a slice-ORDERED COPY of the page: the channels the plan reads (and the page row numbers, for the stamps) are
+    // moved into slice order by the stable multi-split, so every slice launch streams its rows instead of gathering them through a
+    // row list (which cost a 2-sector DRAM fetch per value).  *done = false: shape not handled, use the row-list form.
+    // EXPERIMENTAL (branch wip/path-g-physical): written without GPU time left in round 1, not yet run on hardware.
+    int run_physical_slices(const DevPage& in, const DColumns& cols, int64_t n, int log_slices, int log_cap, bool* done)
+    {
+        *done = false;
+        const int S = 1 << log_slices;
+        bool used[TGPU_MAX_CHANNELS] = {false};
+        for (int i = 0; i < plan.num_srcs; i++) {
+            if (plan.srcs[i].is_temp) return TGPU_OK;
+            if (plan.srcs[i].index < 0 || plan.srcs[i].index >= (int)in.cols.size()) return TGPU_OK;
+            used[plan.srcs[i].index] = true;
+        }
+        struct Lane { int elem; const void* src; int col; bool nulls; DevBuf buf; };
+        std::vector<Lane> lanes;
+        for (int c = 0; c < (int)in.cols.size() && c < TGPU_MAX_CHANNELS; c++) {
+            if (!used[c]) continue;
+            if (in.cols[c].elem_size() == 0) return TGPU_OK;
+            lanes.push_back(Lane{in.cols[c].elem_size(), in.cols[c].data, c, false, DevBuf()});
+            if (in.cols[c].validity) lanes.push_back(Lane{0, in.cols[c].validity, c, true, DevBuf()});
+        }
+        lanes.push_back(Lane{XCHG_ROW_NUMBER, nullptr, -1, false, DevBuf()});
+        if ((int)lanes.size() > XMAXC || S > XMAXP) return TGPU_OK;
+        const XchgGeom geom = xchg_geom(ctx, n, S, true);     // CTA tiles: any number of slices up to 64, row-number lane supported
+        DevBuf ids, hist, block_off, d_totals;
+        TG_TRY(ids.alloc(ctx, (size_t)n));
+        TG_TRY(hist.alloc(ctx, (size_t)geom.nchunks * S * 4));
+        TG_TRY(block_off.alloc(ctx, (size_t)geom.nchunks * S * 8));
+        TG_TRY(d_totals.alloc(ctx, (size_t)S * 8));
+        TG_LAUNCH(ctx, gf_slice_hist_kernel, geom.grid, XT, 0, plan, cols, n, geom.chunk, f_cap, log_cap - log_slices, S, ids.as<uint8_t>(), hist.as<unsigned int>());
+        TG_LAUNCH(ctx, xchg_offsets_kernel, S, 256, 0, hist.as<unsigned int>(), geom.nchunks, S, block_off.as<long long>(), d_totals.as<long long>());
+        std::vector<long long> counts(S), off(S + 1, 0);
+        TG_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_totals.p, (size_t)S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int q = 0; q < S; q++) off[q + 1] = off[q] + counts[q];
+        if (off[S] != n) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "slice counts %lld != rows %lld", off[S], (long long)n);
+        std::vector<char*> h_dst(lanes.size() * S);
+        for (size_t l = 0; l < lanes.size(); l++) {
+            size_t es = lanes[l].elem == XCHG_ROW_NUMBER ? 4 : lanes[l].elem ? (size_t)lanes[l].elem : 1;
+            TG_TRY(lanes[l].buf.alloc(ctx, (size_t)n * es));
+            for (int q = 0; q < S; q++) h_dst[l * S + q] = (char*)lanes[l].buf.p + (size_t)off[q] * es;
+        }
+        DevBuf d_dst;
+        TG_TRY(d_dst.alloc(ctx, h_dst.size() * sizeof(char*)));
+        TG_CUDA(ctx, cudaMemcpyAsync(d_dst.p, h_dst.data(), h_dst.size() * sizeof(char*), cudaMemcpyHostToDevice, ctx->stream));
+        XchgCols xc;
+        memset(&xc, 0, sizeof(xc));
+        xc.count = (int32_t)lanes.size();
+        for (size_t l = 0; l < lanes.size(); l++) { xc.elem[l] = lanes[l].elem; xc.src[l] = lanes[l].src; }
+        xc.dst = d_dst.as<char*>();
+        TG_TRY(xchg_launch_scatter(ctx, geom, ids.as<uint8_t>(), n, S, block_off.as<long long>(), xc));
+        // the slice-ordered page: same channel numbers, data and validity of the channels the plan reads replaced by the copies
+        DColumns pcols = cols;
+        std::vector<DevColumn> packed_keep;
+        const int* stamp_rows = nullptr;
+        for (auto& lane : lanes) {
+            if (lane.elem == XCHG_ROW_NUMBER) { stamp_rows = lane.buf.as<int>(); continue; }
+            if (!lane.nulls) { pcols.cols[lane.col].data = lane.buf.p; continue; }
+            tgpu_column bm;
+            memset(&bm, 0, sizeof(bm));
+            bm.type = TGPU_INT8;
+            bm.flags = TGPU_COL_NULLS_BYTEMAP;
+            bm.length = n;
+            bm.data = lane.buf.p;
+            bm.validity = lane.buf.as<uint8_t>();
+            DevColumn packed;
+            TG_TRY(tg_ingest_column(ctx, &bm, true, &packed));
+            pcols.cols[lane.col].validity = packed.validity;
+            packed_keep.push_back(std::move(packed));
+        }
+        for (int q = 0; q < S; q++)
+            if (counts[q]) TG_TRY(run_fused_rows(pcols, nullptr, counts[q], off[q], stamp_rows));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the copies are released below: the last slice launch must be done with them
+        *done = true;
+        return TGPU_OK;
+    }
+
     int run_fused_general(const DevPage& in, const DColumns& cols)
     {
         int64_t n = in.rows;
@@ -1761,6 +1863,15 @@ struct AggOp : tgpu_op {
             const int S = 1 << log_slices;
             int log_cap = 0;
             while ((1LL << log_cap) < f_cap) log_cap++;
+            if (getenv("TGPU_AGG_PHYSICAL_SLICES")) {
+                bool done = false;
+                TG_TRY(run_physical_slices(in, cols, n, log_slices, log_cap, &done));
+                if (done) {
+                    rows_seen += n;
+                    group_count = f_used + f_specials;
+                    return TGPU_OK;
+                }
+            }
             DevBuf ids, ids_sorted, rows_in, rows_sorted, tmp;
             TG_TRY(ids.alloc(ctx, (size_t)n));
             TG_TRY(ids_sorted.alloc(ctx, (size_t)n));

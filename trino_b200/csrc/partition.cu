@@ -20,7 +20,7 @@
 
 #include <chrono>
 
-#include "rowkeys.cuh"
+#include "multisplit.cuh"
 
 namespace {
 
@@ -106,502 +106,6 @@ __global__ void shift_rows_kernel(const int32_t* __restrict__ in, int64_t n, int
     for (; i < n; i += stride) out[i] = in[i] + delta;
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// exchange: stable multi-split (histogram -> offsets -> scatter), all columns in one pass
-// ------------------------------------------------------------------------------------------------
-constexpr int XT = 256;          // threads per CTA
-constexpr int XMAXP = 64;        // partitions the fused exchange path handles (one per GPU)
-constexpr int XMAXC = 16;        // value columns + null-byte columns
-
-// pass A: partition id per row (uint8) and a histogram per CTA chunk
-__global__ void __launch_bounds__(XT) xchg_hist_kernel(KeyCols keys, int64_t n, int64_t chunk, int32_t bucket_count, const int32_t* __restrict__ bucket_to_partition,
-                                                       int32_t P, uint8_t* __restrict__ pid_out, unsigned int* __restrict__ hist /* [grid][P] */)
-{
-    __shared__ unsigned int sh[XMAXP];
-    for (int i = threadIdx.x; i < P; i += XT) sh[i] = 0;
-    __syncthreads();
-    int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
-    if (P <= 8) {
-        // few partitions (one per GPU of a box): private register counters, no per-row atomics or warp votes;
-        // U independent rows in flight per thread, loads issued together on the single-BIGINT-key fast path
-        constexpr int U = 8;
-        const bool fast = keys.count == 1 && !keys.is_utf8[0] && !keys.is_double[0] && keys.cols[0].elem == 8 && !keys.cols[0].validity;
-        const long long* __restrict__ key0 = (const long long*)keys.cols[0].data;
-        unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int64_t base = begin; base < end; base += U * XT) {
-            int pidv[U];
-            if (fast && base + U * XT <= end) {
-                long long v[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) v[u] = key0[base + u * XT + threadIdx.x];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    int32_t bucket = process_raw_hash(hash_long(v[u]), bucket_count);
-                    pidv[u] = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
-                }
-            }
-            else {
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    int64_t row = base + u * XT + threadIdx.x;
-                    pidv[u] = -1;
-                    if (row < end) {
-                        uint64_t h = 0;
-                        for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
-                        int32_t bucket = process_raw_hash(h, bucket_count);
-                        pidv[u] = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                int64_t row = base + u * XT + threadIdx.x;
-                if (row < end) pid_out[row] = (uint8_t)pidv[u];
-#pragma unroll
-                for (int q = 0; q < 8; q++) cnt[q] += (pidv[u] == q);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            unsigned int v = cnt[q];
-            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if ((threadIdx.x & 31) == 0 && v && q < P) atomicAdd(&sh[q], v);
-        }
-    }
-    else {
-        for (int64_t row = begin + threadIdx.x; row < end; row += XT) {
-            uint64_t h = 0;
-            for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
-            int32_t bucket = process_raw_hash(h, bucket_count);
-            int32_t pid = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
-            pid_out[row] = (uint8_t)pid;
-            // warp-aggregated histogram update
-            unsigned int peers = __match_any_sync(__activemask(), pid);
-            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[pid], __popc(peers));
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < P; i += XT) hist[(size_t)blockIdx.x * P + i] = sh[i];
-}
-
-// pass B: where every CTA chunk starts inside every partition, and the partition totals.  One CTA per partition.
-__global__ void __launch_bounds__(256) xchg_offsets_kernel(const unsigned int* __restrict__ hist, int grid, int32_t P, long long* __restrict__ block_off /* [grid][P] */,
-                                                           long long* __restrict__ totals /* [P] */)
-{
-    __shared__ long long part[256];
-    const int p = blockIdx.x, t = threadIdx.x;
-    const int per = (grid + 255) / 256;
-    const int b0 = min(grid, t * per), b1 = min(grid, b0 + per);
-    long long sum = 0;
-    for (int b = b0; b < b1; b++) sum += hist[(size_t)b * P + p];
-    part[t] = sum;
-    __syncthreads();
-    for (int off = 1; off < 256; off <<= 1) {
-        long long v = t >= off ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    long long run = part[t] - sum;
-    for (int b = b0; b < b1; b++) {
-        block_off[(size_t)b * P + p] = run;
-        run += hist[(size_t)b * P + p];
-    }
-    if (t == 255) totals[p] = part[255];
-}
-
-struct XchgCols {
-    int32_t count;
-    int32_t elem[XMAXC];          // element bytes; 0 = "null byte" pseudo column (reads the validity bitmap, writes 1 = NULL)
-    const void* src[XMAXC];       // column data, or the validity bitmap for pseudo columns
-    char* const* dst;             // device array [count][P] of destination base pointers (local send buffer or peer memory)
-};
-
-// pass C: stable scatter, staged through shared memory.  A CTA walks its chunk in tiles of XTILE rows.  Per tile it ranks
-// every row inside its partition (warp __match_any_sync rank + scan over the tile's (iteration, warp) cells), lays the tile
-// out partition-contiguously in shared memory one column at a time, and copies each partition's run to its destination with
-// consecutive threads writing consecutive addresses: the stores that cross NVLink (peer arenas) are >= 128-byte contiguous
-// segments instead of one 8-byte store per row.  Rows keep their order inside a partition.
-constexpr int XR = 8;                 // rows per thread per tile
-constexpr int XTILE = XT * XR;        // 2048 rows
-constexpr int XCELLS = XR * (XT / 32);
-static_assert(XCELLS == 64, "the cell scan assumes two cells per lane");
-
-template <int OCC>
-__global__ void __launch_bounds__(XT, OCC) xchg_scatter_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t chunk, int32_t P,
-                                                               const long long* __restrict__ block_off, XchgCols cols)
-{
-    __shared__ long long stage[XTILE];
-    __shared__ uint8_t spid[XTILE];
-    __shared__ __align__(16) unsigned short wcount[XCELLS][XMAXP];
-    __shared__ long long running[XMAXP];
-    __shared__ int tile_cnt[XMAXP];
-    __shared__ int tile_off[XMAXP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int NW = XT / 32;
-    for (int i = threadIdx.x; i < P; i += XT) running[i] = block_off[(size_t)blockIdx.x * P + i];
-    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
-    for (int64_t tile = begin; tile < end; tile += XTILE) {
-        const int tile_rows = (int)min((int64_t)XTILE, end - tile);
-        for (int i = threadIdx.x; i < XCELLS * XMAXP * 2 / 16; i += XT) ((uint4*)&wcount[0][0])[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        int pid[XR];
-        int pos[XR];
-#pragma unroll
-        for (int i = 0; i < XR; i++) {
-            int64_t row = tile + (int64_t)i * XT + threadIdx.x;
-            bool live = row < end;
-            pid[i] = live ? (int)pids[row] : -1;
-            unsigned int peers = __match_any_sync(0xffffffffu, live ? pid[i] : -1 - lane);
-            pos[i] = __popc(peers & ((1u << lane) - 1));
-            if (live && pos[i] == 0) wcount[i * NW + warp][pid[i]] = (unsigned short)__popc(peers);
-        }
-        __syncthreads();
-        // exclusive scan over the 64 cells of every partition (cells are in row order: iteration-major, then warp)
-        for (int p = warp; p < P; p += NW) {
-            unsigned int a = wcount[2 * lane][p], b = wcount[2 * lane + 1][p];
-            unsigned int incl = a + b;
-            for (int off = 1; off < 32; off <<= 1) {
-                unsigned int v = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += v;
-            }
-            unsigned int excl = incl - (a + b);
-            wcount[2 * lane][p] = (unsigned short)excl;
-            wcount[2 * lane + 1][p] = (unsigned short)(excl + a);
-            if (lane == 31) tile_cnt[p] = (int)incl;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            int c0 = 2 * lane < P ? tile_cnt[2 * lane] : 0, c1 = 2 * lane + 1 < P ? tile_cnt[2 * lane + 1] : 0;
-            int incl = c0 + c1;
-            for (int off = 1; off < 32; off <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += v;
-            }
-            int excl = incl - (c0 + c1);
-            if (2 * lane < P) tile_off[2 * lane] = excl;
-            if (2 * lane + 1 < P) tile_off[2 * lane + 1] = excl + c0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < XR; i++) {
-            if (pid[i] < 0) continue;
-            pos[i] += tile_off[pid[i]] + wcount[i * NW + warp][pid[i]];
-            spid[pos[i]] = (uint8_t)pid[i];
-        }
-        for (int c = 0; c < cols.count; c++) {
-            const int elem = cols.elem[c];
-            const void* src = cols.src[c];
-#pragma unroll
-            for (int i = 0; i < XR; i++) {
-                if (pid[i] < 0) continue;
-                int64_t row = tile + (int64_t)i * XT + threadIdx.x;
-                switch (elem) {
-                    case 8: stage[pos[i]] = ((const long long*)src)[row]; break;
-                    case 4: ((int*)stage)[pos[i]] = ((const int*)src)[row]; break;
-                    case 2: ((short*)stage)[pos[i]] = ((const short*)src)[row]; break;
-                    case 1: ((char*)stage)[pos[i]] = ((const char*)src)[row]; break;
-                    default: ((char*)stage)[pos[i]] = tg_valid((const uint8_t*)src, row) ? 0 : 1; break;
-                }
-            }
-            __syncthreads();
-            for (int j = threadIdx.x; j < tile_rows; j += XT) {
-                int q = spid[j];
-                long long d = running[q] + (j - tile_off[q]);
-                char* base = cols.dst[(size_t)c * P + q];
-                switch (elem) {
-                    case 8: ((long long*)base)[d] = stage[j]; break;
-                    case 4: ((int*)base)[d] = ((const int*)stage)[j]; break;
-                    case 2: ((short*)base)[d] = ((const short*)stage)[j]; break;
-                    default: base[d] = ((const char*)stage)[j]; break;
-                }
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x < P) running[threadIdx.x] += tile_cnt[threadIdx.x];
-    }
-}
-
-// ---- warp-granular variant for <= 8 partitions (one per GPU of a box) ------------------------------------------------------
-// Every warp owns a contiguous chunk of rows and walks it in tiles of 256 rows (8 consecutive rows per lane), with no CTA
-// barrier anywhere: warps drift apart, so the load latency of one warp hides behind the staging / copy-out of the others.
-// Ranks come from packed per-lane counters and one warp scan (no __match_any_sync, no shared-memory counters).
-constexpr int WR = 8;                  // consecutive rows per lane
-constexpr int WTILE = 32 * WR;         // rows per warp tile
-constexpr int WWARPS = 8;              // warps per CTA
-
-// FAST: one BIGINT key channel without NULLs (the join-key shape) - the loads of a group of rows are issued together
-template <bool FAST>
-__global__ void __launch_bounds__(32 * WWARPS) xchg_hist_warp_kernel(KeyCols keys, int64_t n, int64_t wchunk, int32_t bucket_count,
-                                                                     const int32_t* __restrict__ bucket_to_partition, int32_t P, uint8_t* __restrict__ pid_out,
-                                                                     unsigned int* __restrict__ hist /* [chunks][P] */)
-{
-    constexpr int U = 8;
-    const int lane = threadIdx.x & 31;
-    const int64_t vchunk = (int64_t)blockIdx.x * WWARPS + (threadIdx.x >> 5);
-    const int64_t begin = vchunk * wchunk, end = min(n, begin + wchunk);
-    if (begin >= n) return;
-    unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long* __restrict__ key0 = (const long long*)keys.cols[0].data;
-    for (int64_t base = begin; base < end; base += U * 32) {
-        int pidv[U];
-        const bool full = base + U * 32 <= end;
-        if (FAST && full) {
-            long long v[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) v[u] = key0[base + u * 32 + lane];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                int32_t bucket = process_raw_hash(hash_long(v[u]), bucket_count);
-                pidv[u] = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
-            }
-        }
-        else {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                int64_t row = base + u * 32 + lane;
-                pidv[u] = -1;
-                if (row < end) {
-                    uint64_t h = 0;
-                    for (int c = 0; c < keys.count; c++) h = combine_hash(h, type_hash(keys, c, row));
-                    int32_t bucket = process_raw_hash(h, bucket_count);
-                    pidv[u] = bucket_to_partition ? bucket_to_partition[bucket] : bucket;
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            int64_t row = base + u * 32 + lane;
-            if (row < end) pid_out[row] = (uint8_t)pidv[u];
-#pragma unroll
-            for (int q = 0; q < 8; q++) cnt[q] += (pidv[u] == q);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        unsigned int v = cnt[q];
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == 0 && q < P) hist[(size_t)vchunk * P + q] = v;
-    }
-}
-
-// four packed bytes -> four 16-bit fields
-__device__ __forceinline__ unsigned long long spread4(unsigned int x)
-{
-    return (unsigned long long)(x & 0xffu) | ((unsigned long long)(x & 0xff00u) << 8) | ((unsigned long long)(x & 0xff0000u) << 16) |
-           ((unsigned long long)(x & 0xff000000u) << 24);
-}
-__device__ __forceinline__ unsigned int field16(unsigned long long lo, unsigned long long hi, int q)
-{
-    return (unsigned int)(((q & 4) ? hi : lo) >> ((q & 3) * 16)) & 0xffffu;
-}
-
-// (An aligned-window copy-out - every warp store one aligned segment of one partition run - was worth +15 % when the stores
-// crossed NVLink and cost 50 % for local destinations; peer destinations no longer use this kernel, so it is gone.)
-template <bool VEC>
-__global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t wchunk, int32_t P,
-                                                                        const long long* __restrict__ block_off, XchgCols cols)
-{
-    __shared__ long long stage_all[WWARPS][WTILE];
-    __shared__ long long run_all[WWARPS][8];
-    __shared__ uint8_t spid_all[WWARPS][WTILE];
-    __shared__ int toff_all[WWARPS][8];
-    __shared__ char* sdst[XMAXC * 8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < cols.count * P; i += blockDim.x) sdst[(i / P) * 8 + (i % P)] = cols.dst[i];
-    __syncthreads();
-    const int64_t vchunk = (int64_t)blockIdx.x * WWARPS + warp;
-    const int64_t begin = vchunk * wchunk, end = min(n, begin + wchunk);
-    if (begin >= n) return;
-    long long* stage = stage_all[warp];
-    long long* run = run_all[warp];
-    uint8_t* spid = spid_all[warp];
-    int* toff = toff_all[warp];
-    if (lane < 8) run[lane] = lane < P ? block_off[(size_t)vchunk * P + lane] : 0;
-    __syncwarp();
-    auto load_pids = [&](int64_t tile) -> unsigned long long {
-        int64_t row0 = tile + lane * WR;
-        if (row0 + WR <= end) return *(const unsigned long long*)(pids + row0);
-        unsigned long long v = ~0ull;     // 0xff = no row
-        for (int i = 0; i < WR; i++)
-            if (row0 + i < end) v = (v & ~(0xffull << (8 * i))) | ((unsigned long long)pids[row0 + i] << (8 * i));
-        return v;
-    };
-    unsigned long long next_pid8 = load_pids(begin);
-    for (int64_t tile = begin; tile < end; tile += WTILE) {
-        const unsigned long long pid8 = next_pid8;
-        if (tile + WTILE < end) next_pid8 = load_pids(tile + WTILE);
-        const int64_t row0 = tile + lane * WR;
-        const int tile_rows = (int)min((int64_t)WTILE, end - tile);
-        // per-lane counters (8-bit fields) and the rank of each of my rows among my earlier rows of the same partition
-        unsigned long long c8 = 0, before8 = 0;
-#pragma unroll
-        for (int i = 0; i < WR; i++) {
-            unsigned int q = (unsigned int)(pid8 >> (8 * i)) & 0xffu;
-            if (q < 8) {
-                before8 |= ((c8 >> (8 * q)) & 0xffull) << (8 * i);
-                c8 += 1ull << (8 * q);
-            }
-        }
-        unsigned long long lo = spread4((unsigned int)c8), hi = spread4((unsigned int)(c8 >> 32));
-        unsigned long long ilo = lo, ihi = hi;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            unsigned long long a = __shfl_up_sync(0xffffffffu, ilo, off), b = __shfl_up_sync(0xffffffffu, ihi, off);
-            if (lane >= off) { ilo += a; ihi += b; }
-        }
-        const unsigned long long tlo = __shfl_sync(0xffffffffu, ilo, 31), thi = __shfl_sync(0xffffffffu, ihi, 31);
-        const unsigned long long elo = ilo - lo, ehi = ihi - hi;    // rows of lower lanes, per partition
-        // start of every partition inside the tile
-        unsigned long long olo = 0, ohi = 0;
-        {
-            unsigned int acc = 0;
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                if (q < 4) olo |= (unsigned long long)acc << (16 * q);
-                else ohi |= (unsigned long long)acc << (16 * (q - 4));
-                acc += field16(tlo, thi, q);
-            }
-        }
-        if (lane < 8) toff[lane] = (int)field16(olo, ohi, lane);
-        unsigned long long pos8 = 0;
-#pragma unroll
-        for (int i = 0; i < WR; i++) {
-            unsigned int q = (unsigned int)(pid8 >> (8 * i)) & 0xffu;
-            if (q < 8) {
-                unsigned int pos = field16(olo, ohi, q) + field16(elo, ehi, q) + ((unsigned int)(before8 >> (8 * i)) & 0xffu);
-                pos8 |= (unsigned long long)pos << (8 * i);
-                spid[pos] = (uint8_t)q;
-            }
-        }
-        for (int c = 0; c < cols.count; c++) {
-            const int elem = cols.elem[c];
-            const char* src = (const char*)cols.src[c];
-            const bool full = row0 + WR <= end;
-            if (elem == 8) {
-                long long v[WR];
-                if (VEC && full) {
-                    const longlong2* s2 = (const longlong2*)(src + row0 * 8);
-#pragma unroll
-                    for (int k = 0; k < WR / 2; k++) { longlong2 t = s2[k]; v[2 * k] = t.x; v[2 * k + 1] = t.y; }
-                }
-                else {
-#pragma unroll
-                    for (int i = 0; i < WR; i++) v[i] = row0 + i < end ? ((const long long*)src)[row0 + i] : 0;
-                }
-#pragma unroll
-                for (int i = 0; i < WR; i++)
-                    if (((pid8 >> (8 * i)) & 0xffu) < 8) stage[(pos8 >> (8 * i)) & 0xffu] = v[i];
-            }
-            else if (elem == 4) {
-                int v[WR];
-                if (VEC && full) {
-                    const int4* s4 = (const int4*)(src + row0 * 4);
-#pragma unroll
-                    for (int k = 0; k < WR / 4; k++) { int4 t = s4[k]; v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w; }
-                }
-                else {
-#pragma unroll
-                    for (int i = 0; i < WR; i++) v[i] = row0 + i < end ? ((const int*)src)[row0 + i] : 0;
-                }
-#pragma unroll
-                for (int i = 0; i < WR; i++)
-                    if (((pid8 >> (8 * i)) & 0xffu) < 8) ((int*)stage)[(pos8 >> (8 * i)) & 0xffu] = v[i];
-            }
-            else if (elem == 2) {
-#pragma unroll
-                for (int i = 0; i < WR; i++)
-                    if (((pid8 >> (8 * i)) & 0xffu) < 8) ((short*)stage)[(pos8 >> (8 * i)) & 0xffu] = ((const short*)src)[row0 + i];
-            }
-            else if (elem == 1) {
-#pragma unroll
-                for (int i = 0; i < WR; i++)
-                    if (((pid8 >> (8 * i)) & 0xffu) < 8) ((char*)stage)[(pos8 >> (8 * i)) & 0xffu] = src[row0 + i];
-            }
-            else {
-                // NULL-byte pseudo column: rows row0..row0+7 are exactly one byte of the validity bitmap (row0 % 8 == 0)
-                unsigned int bits = row0 < end ? ((const uint8_t*)src)[row0 >> 3] : 0xffu;
-#pragma unroll
-                for (int i = 0; i < WR; i++)
-                    if (((pid8 >> (8 * i)) & 0xffu) < 8) ((char*)stage)[(pos8 >> (8 * i)) & 0xffu] = ((bits >> i) & 1) ? 0 : 1;
-            }
-            __syncwarp();
-            // copy-out in staged order: consecutive lanes write consecutive addresses inside a partition's run
-            char* const* dstc = sdst + c * 8;
-            const int es = elem ? elem : 1;
-            for (int j = lane; j < tile_rows; j += 32) {
-                int q = spid[j];
-                long long d = run[q] + (j - toff[q]);
-                char* base = dstc[q];
-                switch (es) {
-                    case 8: ((long long*)base)[d] = stage[j]; break;
-                    case 4: ((int*)base)[d] = ((const int*)stage)[j]; break;
-                    case 2: ((short*)base)[d] = ((const short*)stage)[j]; break;
-                    default: base[d] = ((const char*)stage)[j]; break;
-                }
-            }
-            __syncwarp();
-        }
-        if (lane < 8) run[lane] += field16(tlo, thi, lane);
-        __syncwarp();
-    }
-}
-
-// launch geometry shared by the histogram and scatter passes
-struct XchgGeom {
-    bool warp_mode;     // chunks are per warp (<= 8 partitions) or per CTA
-    int grid;
-    int64_t chunk;      // rows per chunk
-    int nchunks;
-};
-
-// Local destinations and <= 8 partitions: warp-granular kernels.  Peer destinations: CTA-granular kernels - a warp-granular
-// scatter keeps 8 x more destination streams open per SM, and on 8 GPUs (7 peer apertures) that fell off a cliff
-// (340 ms instead of 15 ms per 600 M rows, measured), most likely peer-aperture TLB reach.
-static XchgGeom xchg_geom(tgpu_ctx* ctx, int64_t n, int P, bool remote)
-{
-    XchgGeom g;
-    n = std::max<int64_t>(n, 1);
-    g.warp_mode = P <= 8 && !remote && !getenv("TGPU_XCHG_CTA");
-    if (g.warp_mode) {
-        int64_t warps = (int64_t)ctx->sm_count * 4 * WWARPS;
-        g.chunk = tg_div_up(tg_div_up(n, warps), WTILE) * WTILE;
-        g.nchunks = (int)tg_div_up(n, g.chunk);
-        g.grid = (int)tg_div_up(g.nchunks, WWARPS);
-    }
-    else {
-        int grid = tg_grid(ctx, n, XT * 16, 8);
-        g.chunk = tg_div_up(tg_div_up(n, grid), XT) * XT;
-        g.grid = g.nchunks = (int)std::max<int64_t>(1, tg_div_up(n, g.chunk));
-    }
-    return g;
-}
-
-static int xchg_launch_hist(tgpu_ctx* ctx, const XchgGeom& g, const KeyCols& k, int64_t n, int32_t bucket_count, const int32_t* b2p, int32_t P, uint8_t* pids,
-                            unsigned int* hist)
-{
-    if (g.warp_mode) {
-        bool fast = k.count == 1 && !k.is_utf8[0] && !k.is_double[0] && k.cols[0].elem == 8 && !k.cols[0].validity;
-        if (fast) TG_LAUNCH(ctx, xchg_hist_warp_kernel<true>, g.grid, 32 * WWARPS, 0, k, n, g.chunk, bucket_count, b2p, P, pids, hist);
-        else TG_LAUNCH(ctx, xchg_hist_warp_kernel<false>, g.grid, 32 * WWARPS, 0, k, n, g.chunk, bucket_count, b2p, P, pids, hist);
-    }
-    else TG_LAUNCH(ctx, xchg_hist_kernel, g.grid, XT, 0, k, n, g.chunk, bucket_count, b2p, P, pids, hist);
-    return TGPU_OK;
-}
-
-static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* pids, int64_t n, int32_t P, const long long* block_off, const XchgCols& xc)
-{
-    if (g.warp_mode) {
-        bool vec = ((uintptr_t)pids & 7) == 0;
-        for (int c = 0; c < xc.count; c++) vec = vec && ((uintptr_t)xc.src[c] & 15) == 0;
-        if (vec) TG_LAUNCH(ctx, xchg_scatter_warp_kernel<true>, g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
-        else TG_LAUNCH(ctx, xchg_scatter_warp_kernel<false>, g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
-        return TGPU_OK;
-    }
-    TG_LAUNCH(ctx, xchg_scatter_kernel<4>, g.grid, XT, 0, pids, n, g.chunk, P, block_off, xc);
-    return TGPU_OK;
-}
 
 struct PartitionOp : tgpu_op {
     std::vector<int32_t> key_channels;
