@@ -397,6 +397,16 @@ void tgpu_page_release(tgpu_ctx* ctx, tgpu_page* page);
 /* copy a device page into caller-provided host buffers: `host` must describe the same schema with
  * buffers large enough (UTF8: data capacity from tgpu_page_utf8_bytes)                          */
 int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* device_page, tgpu_page* host);
+
+/* The reference's page wire format, uncompressed and unencrypted (PagesSerdeUtil.writeRawPage / CompressingEncryptingPageSerializer
+ * with CompressionCodec.NONE; M/execution/buffer/PagesSerdeUtil.java:44-76, S/block/LongArrayBlockEncoding.java:61-133,
+ * S/block/EncoderUtil.java:35-70, S/block/VariableWidthBlockEncoding.java:57-146): lets a GPU stage exchange pages with Java
+ * tasks over the existing HTTP exchange.  EXPERIMENTAL - not yet run on hardware (branch wip/page-serde).
+ * serialize: `out` is host memory of `capacity` bytes (tgpu_page_serialized_size_bound gives a bound), *bytes_out the length.
+ * deserialize: `types[c]` is the tgpu_type of channel c (the wire names the block encoding, not the SQL type). */
+int64_t tgpu_page_serialized_size_bound(const tgpu_page* page);
+int tgpu_page_serialize(tgpu_ctx* ctx, const tgpu_page* page, uint8_t* out, int64_t capacity, int64_t* bytes_out);
+int tgpu_page_deserialize(tgpu_ctx* ctx, const uint8_t* data, int64_t length, const int32_t* types, int32_t num_types, tgpu_page** out);
 int64_t tgpu_page_utf8_bytes(tgpu_ctx* ctx, const tgpu_page* device_page, int32_t channel);
 /* LookupJoinPageBuilder.build :144-150 returns probe blocks directly when the output covers the probe page 1:1, and
  * InputPageProjection returns its input block: *input_channel = the input channel this output column is an unchanged view

@@ -208,6 +208,9 @@ SIGNATURES = {
     "tgpu_join_outer_create": (C.c_int, [VP, VP, C.POINTER(C.c_int32), C.c_int32, C.POINTER(VP)]),
     "tgpu_semi_join_create": (C.c_int, [VP, VP, C.c_int32, C.POINTER(VP)]),
     "tgpu_lookup_key_domain": (C.c_int, [VP, VP, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "tgpu_page_serialized_size_bound": (C.c_int64, [PP]),
+    "tgpu_page_serialize": (C.c_int, [VP, PP, VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "tgpu_page_deserialize": (C.c_int, [VP, VP, C.c_int64, C.POINTER(C.c_int32), C.c_int32, C.POINTER(PP)]),
     "tgpu_page_passthrough_channel": (C.c_int, [PP, C.c_int32, C.POINTER(C.c_int32)]),
     "tgpu_synth_orders_keys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, VP]),
     "tgpu_synth_lineitem_rows": (C.c_int64, [C.c_int64]),
