@@ -15,6 +15,15 @@
  *     distinct handles may be used concurrently.
  *   - pages are Arrow-layout column buffers.  Host pages are copied to the device inside
  *     add_input; pages flagged TGPU_PAGE_DEVICE already live in HBM and are consumed in place.
+ *   - lifetime of TGPU_PAGE_DEVICE inputs.  When the input IS a page this library returned (the tgpu_page* of
+ *     tgpu_op_get_output / tgpu_exchange_*, passed on unchanged: GPU -> GPU operator chaining), the consumer shares
+ *     ownership of its buffers and the caller may release the page right after add_input, as Operator.addInput
+ *     allows (M/operator/Operator.java:60-66).  Any other device page (descriptors the caller built around its own
+ *     device memory) is BORROWED: the memory must stay allocated while an operator can still read it - until the
+ *     lookup source is released for a join build side (PagesIndex keeps block references, M/operator/PagesIndex.java:224-256),
+ *     until the output page is released for operators that pass input blocks through (LookupJoinOperator 1:1 outputs,
+ *     HashSemiJoinOperator, pass-through projections, a single-partition PartitionedOutput), and until add_input
+ *     returns otherwise.  Pages returned by the exchange alias a receive arena and follow the arena rule stated there.
  *   - there is NO CPU fallback: without a CUDA device every create call fails with TGPU_ERR_CUDA.
  */
 #ifndef TRINO_GPU_H
@@ -357,7 +366,8 @@ int tgpu_comm_destroy(tgpu_ctx* ctx);
  * buffer, no separate transfer) and synchronises with one tiny NCCL all-reduce.  The returned page then aliases an arena
  * and stays valid until the second-next exchange on this context; exchanges that do not fit fall back to NCCL send/recv. */
 #define TGPU_IPC_HANDLE_BYTES 64
-#define TGPU_NUM_ARENAS 3   /* receive arenas per context: an exchanged page stays valid until the third-next exchange */
+#define TGPU_NUM_ARENAS 3   /* receive arenas per context; an exchanged page stays valid until the SECOND-next exchange on the context
+                               (with three arenas a peer may overwrite page j's arena once this rank entered the barrier of exchange j+2) */
 int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[TGPU_NUM_ARENAS * TGPU_IPC_HANDLE_BYTES]);
 int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles /* world x 2 x TGPU_IPC_HANDLE_BYTES, rank-major */);
 /* Hash-partition a device-resident page into `world` partitions and exchange: partition p goes to

@@ -542,7 +542,10 @@ int32_t orc_agg_sum_bigint(const int32_t* gids, int64_t n, const int64_t* v, con
 }
 
 void orc_agg_minmax_double(const int32_t* gids, int64_t n, const double* v, const uint8_t* validity, int32_t is_max, double* acc, uint8_t* nonnull)
-{   // MinMax aggregation on DOUBLE uses COMPARISON_UNORDERED_LAST/FIRST: NaN is largest
+{   // min(DOUBLE): COMPARISON_UNORDERED_LAST, NaN is the largest value (M/operator/aggregation/MinAggregationFunction.java:49,
+    // S/type/DoubleType.java:231-235); max(DOUBLE): COMPARISON_UNORDERED_FIRST, NaN is the smallest value
+    // (MaxAggregationFunction.java:49, DoubleType.java:237-252): the state is replaced when compare(value, state) > 0 (max)
+    // or < 0 (min)
     for (int64_t i = 0; i < n; i++) {
         if (!valid_bit(validity, i)) continue;
         int32_t g = gids[i];
@@ -550,8 +553,9 @@ void orc_agg_minmax_double(const int32_t* gids, int64_t n, const double* v, cons
         if (!nonnull[g]) { nonnull[g] = 1; acc[g] = x; continue; }
         double a = acc[g];
         bool xnan = x != x, anan = a != a;
-        bool x_greater = xnan ? !anan : (!anan && x > a);
-        bool x_less = anan ? !xnan : (!xnan && x < a);
+        bool x_greater = is_max ? (anan ? !xnan : (!xnan && x > a))      // unordered first: any number beats NaN
+                                : (xnan ? !anan : (!anan && x > a));
+        bool x_less = anan ? !xnan : (!xnan && x < a);                   // unordered last (only read for min)
         if (is_max ? x_greater : x_less) acc[g] = x;
     }
 }

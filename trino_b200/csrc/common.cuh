@@ -215,12 +215,18 @@ struct DevPage {
 
 // a page handed to the caller by get_output: the tgpu_page header is the first member so the
 // pointer can be cast back in tgpu_page_release
+struct OwnedPage;
+void tg_owned_page_unregister(OwnedPage* page);
 struct OwnedPage {
     tgpu_page hdr;
     std::vector<tgpu_column> cols;
     DevPage page;
     int32_t partition = -1;
     std::vector<int32_t> passthrough;   // per column: input channel whose block this column IS (unchanged, same rows), else -1
+    // Output pages are registered by the address of their column descriptors: when one is handed to another operator as a
+    // TGPU_PAGE_DEVICE input (GPU -> GPU chaining), ingestion finds it and SHARES the buffers' ownership, so the caller may
+    // release the upstream page right after addInput, as the Operator contract allows (ingest_value_column in core.cu).
+    ~OwnedPage() { tg_owned_page_unregister(this); }
 };
 
 static inline ColRef tg_colref(const DevColumn& c) { return ColRef{c.data, c.validity, c.type, c.elem_size()}; }

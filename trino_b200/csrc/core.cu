@@ -2,6 +2,9 @@
 // generic Operator-protocol entry points of the C ABI (include/trino_gpu.h).
 #include <cub/cub.cuh>
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -518,6 +521,34 @@ int tg_concat_columns(tgpu_ctx* ctx, const std::vector<const DevColumn*>& parts,
     return TGPU_OK;
 }
 
+// registry of live library-owned pages, keyed by the first element of their column descriptor array
+static std::mutex g_owned_lock;
+static std::map<const tgpu_column*, OwnedPage*> g_owned;
+
+void tg_owned_page_unregister(OwnedPage* page)
+{
+    if (page->cols.empty()) return;
+    std::lock_guard<std::mutex> guard(g_owned_lock);
+    auto it = g_owned.find(page->cols.data());
+    if (it != g_owned.end() && it->second == page) g_owned.erase(it);
+}
+
+// `col` is a column descriptor of a live library-owned page: copy its DevColumn (shares the buffers' ownership)
+static bool share_owned_column(const tgpu_column* col, DevColumn* out)
+{
+    std::lock_guard<std::mutex> guard(g_owned_lock);
+    auto it = g_owned.upper_bound(col);
+    if (it == g_owned.begin()) return false;
+    --it;
+    OwnedPage* o = it->second;
+    size_t idx = (size_t)(col - it->first);
+    if (idx >= o->cols.size() || &o->cols[idx] != col) return false;
+    const DevColumn& d = o->page.cols[idx];
+    if (d.data != col->data || d.length != col->length || d.type != col->type) return false;   // descriptor was edited by the caller
+    *out = d;
+    return true;
+}
+
 // upload (host) or borrow (device) `bytes` of a buffer
 static int put_buffer(tgpu_ctx* ctx, const void* src, size_t bytes, bool device, std::shared_ptr<DevBuf>* own, const void** out)
 {
@@ -530,6 +561,7 @@ static int put_buffer(tgpu_ctx* ctx, const void* src, size_t bytes, bool device,
 
 static int ingest_value_column(tgpu_ctx* ctx, const tgpu_column* col, bool device, DevColumn* out)
 {
+    if (device && share_owned_column(col, out)) return TGPU_OK;
     DevColumn r;
     r.type = col->type;
     r.length = col->length;
@@ -642,6 +674,10 @@ OwnedPage* tg_make_owned_page(DevPage&& page)
     o->hdr.flags = TGPU_PAGE_DEVICE;
     o->hdr.num_rows = o->page.rows;
     o->hdr.columns = o->cols.data();
+    if (!o->cols.empty()) {
+        std::lock_guard<std::mutex> guard(g_owned_lock);
+        g_owned[o->cols.data()] = o;
+    }
     return o;
 }
 

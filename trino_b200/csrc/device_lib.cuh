@@ -252,15 +252,25 @@ __device__ __forceinline__ Value vm_apply(int op, int vtype, Value a, Value b, V
 }
 
 // ---- accumulators -------------------------------------------------------------------------------------
-// order-preserving encodings so MIN/MAX are plain integer min/max (NaN sorts last, like the reference)
+// order-preserving encodings so MIN/MAX are plain integer min/max.  min(DOUBLE) compares with COMPARISON_UNORDERED_LAST
+// (NaN is the largest value, S/type/DoubleType.java:231-235), max(DOUBLE) with COMPARISON_UNORDERED_FIRST (NaN is the
+// smallest, :237-252; M/operator/aggregation/MaxAggregationFunction.java:49): max({1.0, NaN}) = 1.0, max({NaN}) = NaN.
 __host__ __device__ __forceinline__ unsigned long long f64_order_key(long long bits)
 {
     unsigned long long u = (unsigned long long)bits;
     if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) u = 0x7FF8000000000000ULL;
     return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
 }
+// key for MAX: NaN ranks below every other value (key 1: above the "no row yet" initial 0, below -Infinity's key)
+__host__ __device__ __forceinline__ unsigned long long f64_order_key_max(long long bits)
+{
+    unsigned long long u = (unsigned long long)bits;
+    if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) return 1ULL;
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
 __host__ __device__ __forceinline__ long long f64_from_order_key(unsigned long long k)
 {
+    if (k == 1ULL) return 0x7FF8000000000000LL;      // MAX's NaN (never produced by f64_order_key)
     return (long long)((k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k);
 }
 __host__ __device__ __forceinline__ unsigned long long i64_order_key(long long v) { return (unsigned long long)v ^ 0x8000000000000000ULL; }
@@ -295,7 +305,7 @@ __device__ __forceinline__ void acc_update_private(int kind, unsigned long long*
             break;
         }
         case ACC_MIN_F64: { unsigned long long k = f64_order_key(bits); if (k < *p) *p = k; break; }
-        case ACC_MAX_F64: { unsigned long long k = f64_order_key(bits); if (k > *p) *p = k; break; }
+        case ACC_MAX_F64: { unsigned long long k = f64_order_key_max(bits); if (k > *p) *p = k; break; }
         case ACC_MIN_I64: { unsigned long long k = i64_order_key(bits); if (k < *p) *p = k; break; }
         case ACC_MAX_I64: { unsigned long long k = i64_order_key(bits); if (k > *p) *p = k; break; }
         default: break;

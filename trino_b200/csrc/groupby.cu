@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(256) g_accumulate_kernel(AggPlan plan, DColumn
                     break;
                 }
                 case ACC_MIN_F64: atomicMin(p, f64_order_key(v.bits)); break;
-                case ACC_MAX_F64: atomicMax(p, f64_order_key(v.bits)); break;
+                case ACC_MAX_F64: atomicMax(p, f64_order_key_max(v.bits)); break;
                 case ACC_MIN_I64: atomicMin(p, i64_order_key(v.bits)); break;
                 case ACC_MAX_I64: atomicMax(p, i64_order_key(v.bits)); break;
                 default: break;
@@ -678,7 +678,7 @@ __device__ __forceinline__ void gf_accumulate(const AggPlan& plan, const DColumn
                 atomicAdd(p + 1, (unsigned long long)(v.bits >> 32));
                 break;
             case ACC_MIN_F64: atomicMin(p, f64_order_key(v.bits)); break;
-            case ACC_MAX_F64: atomicMax(p, f64_order_key(v.bits)); break;
+            case ACC_MAX_F64: atomicMax(p, f64_order_key_max(v.bits)); break;
             case ACC_MIN_I64: atomicMin(p, i64_order_key(v.bits)); break;
             case ACC_MAX_I64: atomicMax(p, i64_order_key(v.bits)); break;
             default: break;
@@ -2128,6 +2128,9 @@ struct AggOp : tgpu_op {
         f_recs.release();
         f_cap = f_used = f_specials = rows_seen = 0;
         TG_TRY(init_state());
+        // once the pre-stage was un-fused (inner_fp exists, the plan's sources point at projection OUTPUT channels) the
+        // shared-memory path must never see a raw input page again: stay on the general path across flushes
+        if (inner_fp) use_general = true;
         if (use_general) TG_TRY(switch_to_general());
         return TGPU_OK;
     }

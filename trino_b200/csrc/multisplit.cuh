@@ -425,7 +425,8 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
             }
             else {
                 // NULL-byte pseudo column: rows row0..row0+7 are exactly one byte of the validity bitmap (row0 % 8 == 0)
-                unsigned int bits = row0 < end ? ((const uint8_t*)src)[row0 >> 3] : 0xffu;
+                // (src == nullptr: this rank's page has no NULLs in the column, another rank's has - every row is valid)
+                unsigned int bits = (src && row0 < end) ? ((const uint8_t*)src)[row0 >> 3] : 0xffu;
 #pragma unroll
                 for (int i = 0; i < WR; i++)
                     if (((pid8 >> (8 * i)) & 0xffu) < 8) ((char*)stage)[(pos8 >> (8 * i)) & 0xffu] = ((bits >> i) & 1) ? 0 : 1;

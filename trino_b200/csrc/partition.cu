@@ -991,7 +991,7 @@ extern "C" int tgpu_exchange_end(tgpu_ctx* ctx, tgpu_exchange* exchange, tgpu_pa
         if (!lane.nulls) {
             dst.type = x->col_types[lane.col];
             dst.length = x->total_recv;
-            dst.data = region;     // aliases the arena: valid until the third-next exchange on this context
+            dst.data = region;     // aliases the arena: valid until the second-next exchange on this context
         }
         else if (x->total_recv > 0) {
             tgpu_column bytemap_col;
