@@ -97,37 +97,53 @@ def dist_env():
     return rank, world, local
 
 
+def cpu_probe_measure(args, n_orders, probe_rows, passes, warm):
+    """The CPU probe arm, shared by --impl reference and the cpu_baseline block: PartitionedLookupSource of P partitions built in
+    parallel (one builder per partition), persistent pool of T probe drivers on 8192-row pages, every buffer of the timed region
+    allocated and first-touched by the drivers beforehand (oracle.h: orc_pjoin_*).  Returns the median pass and the spread."""
+    import oracle_lib as o
+    threads = o.hardware_threads()
+    partitions = 2
+    while partitions < min(threads, 256):
+        partitions <<= 1
+    sample = min(probe_rows, args.cpu_sample_rows)
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, SEED_ORDERS, True)
+    payload = (okeys % 2557).astype(np.int32)
+    pj = o.PartitionedJoin(okeys, payload, partitions, threads)
+    lkeys = pj.alloc(sample, np.int64)
+    lkeys[:] = o.synth_lineitem_keys(n_orders, 0, sample, SEED_LINEITEM, int(args.shuffle_probe))
+    pos = pj.alloc(sample, np.int64)
+    pay = pj.alloc(sample, np.int32)
+    for _ in range(max(1, warm)):
+        pj.probe(lkeys, pos, pay)
+    times = sorted(pj.probe(lkeys, pos, pay) for _ in range(max(passes, 10)))
+    assert (pos >= 0).all()
+    assert (pay[:4096] == (lkeys[:4096] % 2557)).all()
+    med = float(np.median(times))
+    out = {"value": sample / med, "unit": "rows/s", "cores": threads, "kind": "port", "seconds_median": med, "passes": len(times),
+           "spread": {"min_s": times[0], "max_s": times[-1], "rel_iqr": float((np.percentile(times, 75) - np.percentile(times, 25)) / med)},
+           "sample": f"{sample} of {probe_rows} probe rows against the full {n_orders}-row build side; PartitionedLookupSource of {pj.partitions} partitions "
+                     f"(parallel build {pj.build_seconds:.1f} s, untimed), {threads} persistent probe drivers on 8192-row pages, batched 3-phase "
+                     f"getAddressIndex + build payload copy; outputs pre-allocated and first-touched by the drivers; median of {len(times)} passes; "
+                     f"{os.cpu_count()} logical CPUs"}
+    pj.close()
+    return out
+
+
 def reference_arm(args):
-    """The reference's CPU algorithm (oracle port: BigintPagesHash 3-phase batched probe + payload copy, T drivers)
-    on a bounded sample of the same workload.  Test infrastructure timed as the baseline; never on the product path."""
+    """The reference's CPU algorithm (oracle port, see cpu_probe_measure) on a bounded sample of the same workload.
+    Test infrastructure timed as the baseline; never on the product path."""
     import oracle_lib as o
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    threads = o.hardware_threads()
     sf = args.sf
     n_orders = int(1_500_000 * sf)
     rows = o.synth_lineitem_rows(n_orders)
-    sample = min(rows, args.cpu_sample_rows)
-    okeys = o.synth_orders_keys(n_orders, 0, n_orders, SEED_ORDERS, True)
-    payload = (okeys % 2557).astype(np.int32)
-    from trino_b200.page import Block, Page
-    t0 = time.time()
-    join = o.Join(Page(Block.bigint(okeys)), [0], force_default=2)
-    build_s = time.time() - t0
-    lkeys = o.synth_lineitem_keys(n_orders, 0, sample, SEED_LINEITEM, False)
-    times = []
-    for i in range(args.warmup + args.steps):
-        secs, pos, _ = join.probe_timed(lkeys, threads, payload)
-        if i >= args.warmup:
-            times.append(secs)
-    assert (pos >= 0).all()
-    t = float(np.mean(times))
-    value = sample / t
-    cpu = {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
-           "sample": f"{sample} of {rows} probe rows against the full {n_orders}-row build table (built in {build_s:.1f} s, untimed); {os.cpu_count()} logical CPUs"}
+    cpu = cpu_probe_measure(args, n_orders, rows, args.steps, args.warmup)
+    value = cpu["value"]
     line = {"impl": "reference", "metric": "hash_join_probe_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "warmup": args.warmup, "ms_per_step": cpu["seconds_median"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic", "config": workload_config(args, n_orders, rows, 1), "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -677,27 +693,16 @@ def bench_q1(ctx, args):
 
 def cpu_baseline(args, n_orders, probe_rows):
     import oracle_lib as o
-    from trino_b200.page import Block, Page
-    threads = o.hardware_threads()
-    sample = min(probe_rows, args.cpu_sample_rows)
-    okeys = o.synth_orders_keys(n_orders, 0, n_orders, SEED_ORDERS, True)
-    payload = (okeys % 2557).astype(np.int32)
-    t0 = time.time()
-    join = o.Join(Page(Block.bigint(okeys)), [0], force_default=2)
-    build_s = time.time() - t0
-    lkeys = o.synth_lineitem_keys(n_orders, 0, sample, SEED_LINEITEM, int(args.shuffle_probe))
-    join.probe_timed(lkeys[: sample // 8], threads, payload)
-    secs, pos, _ = join.probe_timed(lkeys, threads, payload)
-    join.close()
-    out = {"value": sample / secs, "unit": "rows/s", "cores": threads, "kind": "port",
-           "sample": f"{sample} of {probe_rows} probe rows against the full {n_orders}-row build table (CPU build {build_s:.1f} s, untimed), "
-                     f"BigintPagesHash 3-phase batched probe on 8192-row pages + build payload copy, {threads} threads"}
+    out = cpu_probe_measure(args, n_orders, probe_rows, 10, 2)
+    threads = out["cores"]
     if args.q1_sf > 0:
         n = 60_000_000
         cols = o.synth_lineitem_q1(n, 0, SEED_LINEITEM)
-        secs, rows = o.q1_run(cols, 10471, threads)
-        out["groupby_q1"] = {"value": n / secs, "unit": "rows/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} synthetic lineitem rows, filter -> 7 projection loops -> FlatHash group ids -> 8 accumulator passes, {threads} partial drivers + final merge"}
+        o.q1_run(cols, 10471, threads)
+        runs = sorted(o.q1_run(cols, 10471, threads)[0] for _ in range(5))
+        secs = runs[len(runs) // 2]
+        out["groupby_q1"] = {"value": n / secs, "unit": "rows/s", "cores": threads, "kind": "port", "spread": {"min_s": runs[0], "max_s": runs[-1]},
+                             "sample": f"{n} synthetic lineitem rows, filter -> 7 projection loops -> FlatHash group ids -> 8 accumulator passes, {threads} partial drivers + final merge; median of 5 passes"}
     return out
 
 

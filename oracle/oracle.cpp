@@ -5,6 +5,10 @@
 #include "oracle.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -764,6 +768,263 @@ double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_
     }
     for (auto& th : pool) th.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Partitioned lookup source + persistent probe drivers: the stable CPU timing arm.
+// Structure of a Trino task: the build side goes through a local hash exchange into P HashBuilderOperators
+// (P = task.concurrency; partition = LocalPartitionGenerator.getPartition(rawHash),
+// M/operator/exchange/LocalPartitionGenerator.java:76-80), each builds its own PagesHash over its own PagesIndex;
+// T probe drivers share the PartitionedLookupSource (M/operator/join/unspilled/PartitionedLookupSource.java:149-186).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// a fixed set of worker threads; run(fn) executes fn(worker) on every worker and returns when all are done
+struct WorkerPool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_start, cv_done;
+    std::function<void(int)> job;
+    int64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+
+    explicit WorkerPool(int n)
+    {
+        for (int t = 0; t < n; t++) threads.emplace_back([this, t]() { loop(t); });
+    }
+    ~WorkerPool()
+    {
+        { std::lock_guard<std::mutex> g(m); stop = true; generation++; }
+        cv_start.notify_all();
+        for (auto& th : threads) th.join();
+    }
+    void loop(int t)
+    {
+        int64_t seen = 0;
+        while (true) {
+            std::function<void(int)> fn;
+            {
+                std::unique_lock<std::mutex> g(m);
+                cv_start.wait(g, [&]() { return generation != seen; });
+                seen = generation;
+                if (stop) return;
+                fn = job;
+            }
+            fn(t);
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void run(const std::function<void(int)>& fn)
+    {
+        std::unique_lock<std::mutex> g(m);
+        job = fn;
+        pending = (int)threads.size();
+        generation++;
+        cv_start.notify_all();
+        cv_done.wait(g, [&]() { return pending == 0; });
+    }
+    int size() const { return (int)threads.size(); }
+};
+
+struct PJoinPart {
+    bool bigint = true;                 // JoinHashSupplier.getPagesHashType :162-168: BigintPagesHash up to 2^20 positions, else DefaultPagesHash
+    int32_t mask = 0;
+    int64_t n = 0;
+    std::vector<int32_t> keys;          // slot -> address index inside the partition, -1 empty
+    std::vector<int64_t> values;        // address index -> key (BigintPagesHash.values / the key block of the partition's PagesIndex)
+    std::vector<uint8_t> tags;          // DefaultPagesHash.positionToHashes
+    std::vector<int32_t> payload;       // the partition's build output channel
+    std::vector<int32_t> global_row;    // address index -> row of the unpartitioned build side (verification only)
+};
+
+}  // namespace
+
+struct orc_pjoin {
+    int32_t P = 1, shift = 1;
+    std::vector<PJoinPart> parts;
+    WorkerPool* pool = nullptr;
+    ~orc_pjoin() { delete pool; }
+};
+
+orc_pjoin* orc_pjoin_build(const int64_t* build_keys, const int32_t* build_payload, int64_t n, int32_t partitions, int32_t threads, double* seconds_out)
+{
+    // partitions must be a power of two (LocalPartitionGenerator.java:43-47)
+    orc_pjoin* j = new orc_pjoin();
+    int32_t P = 1;
+    while (P < partitions) P <<= 1;
+    j->P = P;
+    j->shift = __builtin_ctz((unsigned)P) + 1;            // PartitionedLookupSource.java:105-106
+    j->parts.resize(P);
+    j->pool = new WorkerPool(threads);
+    const int T = threads;
+    auto t0 = std::chrono::steady_clock::now();
+    // local exchange: rows to partitions, stable (PartitioningExchanger.accept :58-103 appends positions in page order)
+    std::vector<uint8_t> part_of((size_t)n);
+    std::vector<std::vector<int64_t>> counts(T, std::vector<int64_t>(P, 0));
+    const int64_t slice = (n + T - 1) / T;
+    j->pool->run([&](int t) {
+        int64_t lo = std::min<int64_t>(n, t * slice), hi = std::min<int64_t>(n, lo + slice);
+        for (int64_t r = lo; r < hi; r++) {
+            int32_t p = (int32_t)xxh64_long((int64_t)bitreverse64(hash_long(build_keys[r]))) & (P - 1);
+            part_of[r] = (uint8_t)p;
+            counts[t][p]++;
+        }
+    });
+    std::vector<std::vector<int64_t>> start(T, std::vector<int64_t>(P, 0));
+    for (int p = 0; p < P; p++) {
+        int64_t run = 0;
+        for (int t = 0; t < T; t++) { start[t][p] = run; run += counts[t][p]; }
+        j->parts[p].n = run;
+    }
+    // every partition is allocated, first-touched and built by its own builder thread (one HashBuilderOperator per partition)
+    std::vector<std::vector<int32_t>> rows(P);
+    j->pool->run([&](int t) {
+        for (int p = t; p < P; p += T) rows[p].assign((size_t)j->parts[p].n, 0);
+    });
+    j->pool->run([&](int t) {
+        int64_t lo = std::min<int64_t>(n, t * slice), hi = std::min<int64_t>(n, lo + slice);
+        std::vector<int64_t> at = start[t];
+        for (int64_t r = lo; r < hi; r++) rows[part_of[r]][at[part_of[r]]++] = (int32_t)r;
+    });
+    j->pool->run([&](int t) {
+        for (int p = t; p < P; p += T) {
+            PJoinPart& part = j->parts[p];
+            const int64_t m = part.n;
+            part.bigint = m <= (1 << 20);
+            int32_t hash_size = orc_join_hash_array_size(m);      // IncrementalLoadFactorHashArraySizeSupplier, multiplier 1
+            part.mask = hash_size - 1;
+            part.keys.assign((size_t)hash_size, -1);
+            part.values.resize((size_t)m);
+            part.payload.resize((size_t)m);
+            part.global_row.resize((size_t)m);
+            if (!part.bigint) part.tags.resize((size_t)m);
+            for (int64_t a = 0; a < m; a++) {
+                int64_t r = rows[p][a];
+                int64_t value = build_keys[r];
+                part.values[a] = value;
+                part.payload[a] = build_payload ? build_payload[r] : 0;
+                part.global_row[a] = (int32_t)r;
+                uint64_t raw = hash_long(value);
+                if (!part.bigint) part.tags[a] = (uint8_t)raw;
+                // BigintPagesHash.insertValue :122-141 (slot = mix(key)) / DefaultPagesHash.insertValue :126-144 (slot = mix(rawHash)).
+                // The timing workload has unique keys; a repeated key replaces the slot's address like the reference (links are
+                // kept by the single-table oracle, orc_join_build, which is the one the parity tests check chains against).
+                int32_t pos = (int32_t)(murmur3(part.bigint ? (uint64_t)value : raw) & (uint64_t)part.mask);
+                while (part.keys[pos] != -1) {
+                    if (part.values[part.keys[pos]] == value) break;
+                    pos = (pos + 1) & part.mask;
+                }
+                part.keys[pos] = (int32_t)a;
+            }
+            std::vector<int32_t>().swap(rows[p]);
+        }
+    });
+    if (seconds_out) *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return j;
+}
+
+void orc_pjoin_destroy(orc_pjoin* j) { delete j; }
+int32_t orc_pjoin_partitions(const orc_pjoin* j) { return j->P; }
+int32_t orc_pjoin_threads(const orc_pjoin* j) { return j->pool->size(); }
+
+// first touch of caller-allocated probe-side arrays by the worker that will use them: page p (8192 rows) belongs to worker
+// p % T in orc_pjoin_probe, so its memory lands on that worker's NUMA node
+void orc_pjoin_touch(orc_pjoin* j, void* base, int64_t bytes_per_row, int64_t n)
+{
+    const int64_t PAGE = 8192;
+    const int64_t pages = (n + PAGE - 1) / PAGE;
+    const int T = j->pool->size();
+    j->pool->run([&](int t) {
+        for (int64_t p = t; p < pages; p += T) {
+            int64_t lo = p * PAGE, hi = std::min(n, lo + PAGE);
+            memset((char*)base + lo * bytes_per_row, 0, (size_t)((hi - lo) * bytes_per_row));
+        }
+    });
+}
+
+double orc_pjoin_probe(orc_pjoin* j, const int64_t* probe_keys, int64_t n, int64_t* out_positions, int32_t* out_payload)
+{
+    const int64_t PAGE = 8192;
+    const int64_t pages = (n + PAGE - 1) / PAGE;
+    const int T = j->pool->size();
+    const int P = j->P;
+    const int shift = j->shift;
+    auto t0 = std::chrono::steady_clock::now();
+    j->pool->run([&](int t) {
+        std::vector<int64_t> raw(PAGE);
+        std::vector<int32_t> part(PAGE), hash_pos(PAGE), found_keys(PAGE), found(PAGE), list(PAGE), res(PAGE);
+        std::vector<int32_t> pcount(P), pstart(P + 1);
+        for (int64_t pg = t; pg < pages; pg += T) {
+            const int64_t base = pg * PAGE;
+            const int32_t cnt = (int32_t)std::min(PAGE, n - base);
+            const int64_t* in = probe_keys + base;
+            // PartitionedLookupSource.getJoinPosition(int[], Page, Page, long[]) :187-199 raw hashes, then :149-186
+            for (int32_t i = 0; i < cnt; i++) raw[i] = (int64_t)hash_long(in[i]);
+            std::fill(pcount.begin(), pcount.end(), 0);
+            for (int32_t i = 0; i < cnt; i++) {
+                int32_t p = (int32_t)xxh64_long((int64_t)bitreverse64((uint64_t)raw[i])) & (P - 1);
+                part[i] = p;
+                pcount[p]++;
+            }
+            pstart[0] = 0;
+            for (int p = 0; p < P; p++) pstart[p + 1] = pstart[p] + pcount[p];
+            std::fill(pcount.begin(), pcount.end(), 0);
+            for (int32_t i = 0; i < cnt; i++) list[pstart[part[i]] + pcount[part[i]]++] = i;
+            for (int p = 0; p < P; p++) {
+                const PJoinPart& ps = j->parts[p];
+                const int32_t* pos_list = list.data() + pstart[p];
+                const int32_t m = pstart[p + 1] - pstart[p];
+                if (m == 0) continue;
+                // the partition's 3-phase batched getAddressIndex: BigintPagesHash.java:184-268 / DefaultPagesHash.java:193-282
+                for (int32_t k = 0; k < m; k++) {
+                    int32_t i = pos_list[k];
+                    hash_pos[k] = (int32_t)(murmur3(ps.bigint ? (uint64_t)in[i] : (uint64_t)raw[i]) & (uint64_t)ps.mask);
+                }
+                for (int32_t k = 0; k < m; k++) found_keys[k] = ps.keys[hash_pos[k]];
+                int32_t fc = 0;
+                for (int32_t k = 0; k < m; k++) { res[pos_list[k]] = -1; if (found_keys[k] != -1) found[fc++] = k; }
+                int32_t rc = 0;
+                for (int32_t f = 0; f < fc; f++) {
+                    int32_t k = found[f], i = pos_list[k], a = found_keys[k];
+                    bool eq = (ps.bigint || ps.tags[a] == (uint8_t)raw[i]) && ps.values[a] == in[i];
+                    if (eq) res[i] = a;
+                    else found[rc++] = k;
+                }
+                for (int32_t f = 0; f < rc; f++) {
+                    int32_t k = found[f], i = pos_list[k];
+                    int32_t pos = (hash_pos[k] + 1) & ps.mask;
+                    while (ps.keys[pos] != -1) {
+                        int32_t a = ps.keys[pos];
+                        if ((ps.bigint || ps.tags[a] == (uint8_t)raw[i]) && ps.values[a] == in[i]) { res[i] = a; break; }
+                        pos = (pos + 1) & ps.mask;
+                    }
+                }
+            }
+            // encodePartitionedJoinPosition :259-262, then PageJoiner.joinCurrentPosition :203-227 -> PartitionedLookupSource.appendTo
+            // :226-233 -> the partition's PagesIndex: one build output value copied per match
+            int64_t* out = out_positions + base;
+            for (int32_t i = 0; i < cnt; i++) out[i] = res[i] < 0 ? -1 : (((int64_t)res[i] << shift) | part[i]);
+            if (out_payload) {
+                int32_t* po = out_payload + base;
+                for (int32_t i = 0; i < cnt; i++) po[i] = res[i] >= 0 ? j->parts[part[i]].payload[res[i]] : 0;
+            }
+        }
+    });
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// decodePartition / decodeJoinPosition :264-275, mapped back to rows of the unpartitioned build side
+void orc_pjoin_decode(const orc_pjoin* j, const int64_t* positions, int64_t n, int32_t* out_rows)
+{
+    for (int64_t i = 0; i < n; i++) {
+        if (positions[i] < 0) { out_rows[i] = -1; continue; }
+        int32_t p = (int32_t)(positions[i] & (j->P - 1));
+        out_rows[i] = j->parts[p].global_row[(size_t)(positions[i] >> j->shift)];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

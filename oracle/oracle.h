@@ -95,6 +95,25 @@ double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_
                             const int32_t* build_payload, int32_t* out_payload);
 /* force BigintPagesHash layout (keys[] + values[]) regardless of size: the timing leg probes BIGINT keys */
 
+/* ---- the stable CPU timing arm: a PartitionedLookupSource (M/operator/join/unspilled/PartitionedLookupSource.java:97-186) of
+ * `partitions` (rounded up to a power of two) lookup sources, each built by its own builder thread over its own slice of the build
+ * side (one HashBuilderOperator per partition behind the local exchange, LocalPartitionGenerator.java:76-80; BigintPagesHash up to
+ * 2^20 positions per partition, DefaultPagesHash above, JoinHashSupplier.java:162-168), probed by a persistent pool of `threads`
+ * drivers on 8192-row pages.  Single BIGINT join channel without NULLs, unique build keys, one INT32 build output channel. */
+typedef struct orc_pjoin orc_pjoin;
+orc_pjoin* orc_pjoin_build(const int64_t* build_keys, const int32_t* build_payload, int64_t n, int32_t partitions, int32_t threads, double* seconds_out);
+void orc_pjoin_destroy(orc_pjoin* j);
+int32_t orc_pjoin_partitions(const orc_pjoin* j);
+int32_t orc_pjoin_threads(const orc_pjoin* j);
+/* zero-fill a caller-allocated probe-side array with the page -> worker assignment of orc_pjoin_probe (NUMA first touch) */
+void orc_pjoin_touch(orc_pjoin* j, void* base, int64_t bytes_per_row, int64_t n);
+/* one pass of the probe drivers: out_positions[i] = encodePartitionedJoinPosition(partition, joinPosition) or -1
+ * (PartitionedLookupSource.java:259-262), out_payload[i] = the build output value of the match (0 when none).  Outputs are
+ * caller-allocated (pre-touched); nothing is allocated or spawned inside the timed region.  Returns seconds. */
+double orc_pjoin_probe(orc_pjoin* j, const int64_t* probe_keys, int64_t n, int64_t* out_positions, int32_t* out_payload);
+/* decodePartition / decodeJoinPosition (:264-275) mapped back to rows of the unpartitioned build side, for verification */
+void orc_pjoin_decode(const orc_pjoin* j, const int64_t* positions, int64_t n, int32_t* out_rows);
+
 /* ---- PagePartitioner (M/operator/output/PagePartitioner.java:133-162,229-433) */
 /* partition id per row: bucketToPartition[processRawHash(rowHash, bucketCount)] */
 void orc_partition_ids(const tgpu_page* page, const int32_t* key_channels, int32_t num_keys, int32_t bucket_count,

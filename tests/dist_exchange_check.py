@@ -1,4 +1,4 @@
-"""Multi-GPU parity check (launched with torchrun, one rank per GPU, NOT collected by pytest):
+"""Multi-GPU parity check (launched with torchrun, one rank per GPU; tests/test_gpu_dist.py runs it under pytest -m gpu):
 hash-partition + NCCL all-to-all of a device page through tgpu_exchange_partitioned, checked against the oracle's
 partition function, then the partitioned join against a single-process oracle join.
 
@@ -59,6 +59,15 @@ def main():
 
     got_l = exchange(lpage)
     got_o = exchange(opage)
+    # a column that carries NULLs on the last rank only: every other rank's page has no validity buffer at all, but must still
+    # ship a NULL-byte lane because some rank's page does (the advisor's round-1 finding on the warp-granular scatter)
+    onesided = Page(Block.bigint(lkeys), Block.double(lkeys * 0.25, lnull if rank == world - 1 else None))
+    got_1 = exchange(onesided)
+    nulls_1 = torch.tensor([sum(1 for v in got_1.get_block(1).to_pylist() if v is None), int(lnull.sum()) if rank == world - 1 else 0],
+                           dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(nulls_1)
+    assert nulls_1[0] == nulls_1[1]
+    assert all(v is None or v == k * 0.25 for k, v in zip(got_1.get_block(0).to_pylist(), got_1.get_block(1).to_pylist()))
     # every received row belongs here (oracle partition function), and globally nothing is lost or duplicated
     assert (o.partition_ids(got_l, [0], world) == rank).all()
     assert (o.partition_ids(got_o, [0], world) == rank).all()
@@ -93,6 +102,7 @@ def main():
         assert p2p_l.rows() == got_l.rows()          # identical rows in identical order to the NCCL path
         p2p_o = exchange(opage)
         assert p2p_o.rows() == got_o.rows()
+    assert exchange(onesided).rows() == got_1.rows()
     # ---- pipelined form: the exchange runs on `ctx`, build + probe on a second context of the same GPU; the probe of page k is
     # only enqueued, its output is taken after exchange k+1 was issued (tgpu_exchange_partitioned_fenced guards the arena reuse)
     from trino_b200.page import AbiPage
@@ -134,8 +144,8 @@ def main():
     b.close()
     # ---- split-phase form: two exchanges in flight, transfers on the copy engines; rows and order identical to the blocking call
     handles = []
-    seq = [lpage, opage, lpage, lpage, opage]
-    want_seq = [got_l.rows(), got_o.rows(), got_l.rows(), got_l.rows(), got_o.rows()]
+    seq = [lpage, opage, onesided, lpage, lpage, onesided, opage]
+    want_seq = [got_l.rows(), got_o.rows(), got_1.rows(), got_l.rows(), got_l.rows(), got_1.rows(), got_o.rows()]
     aps = []
     done = 0
     for page in seq:

@@ -76,6 +76,13 @@ def load():
         "orc_synth_lineitem_keys": (None, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, VP]),
         "orc_synth_lineitem_q1": (None, [C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP]),
         "orc_hardware_threads": (C.c_int32, []),
+        "orc_pjoin_build": (VP, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP]),
+        "orc_pjoin_destroy": (None, [VP]),
+        "orc_pjoin_partitions": (C.c_int32, [VP]),
+        "orc_pjoin_threads": (C.c_int32, [VP]),
+        "orc_pjoin_touch": (None, [VP, VP, C.c_int64, C.c_int64]),
+        "orc_pjoin_probe": (C.c_double, [VP, VP, C.c_int64, VP, VP]),
+        "orc_pjoin_decode": (None, [VP, VP, C.c_int64, VP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -172,6 +179,40 @@ class Join:
     def close(self):
         if self.h:
             self.lib.orc_join_destroy(self.h)
+            self.h = None
+
+
+class PartitionedJoin:
+    """The stable CPU timing arm (oracle.h: orc_pjoin_*): PartitionedLookupSource of P lookup sources built in parallel, probed by a
+    persistent pool of drivers; every buffer of the timed region is allocated and first-touched before it."""
+
+    def __init__(self, build_keys, build_payload, partitions, threads):
+        self.lib = load()
+        self.keys = np.ascontiguousarray(build_keys, dtype=np.int64)
+        self.payload = None if build_payload is None else np.ascontiguousarray(build_payload, dtype=np.int32)
+        secs = C.c_double()
+        self.h = self.lib.orc_pjoin_build(_p(self.keys), _p(self.payload), len(self.keys), partitions, threads, C.cast(C.byref(secs), VP))
+        self.build_seconds = secs.value
+        self.partitions = self.lib.orc_pjoin_partitions(self.h)
+        self.threads = self.lib.orc_pjoin_threads(self.h)
+
+    def alloc(self, n, dtype):
+        """probe-side array of n rows, first-touched by the drivers that will use its pages"""
+        a = np.empty(n, dtype=dtype)
+        self.lib.orc_pjoin_touch(self.h, _p(a), a.itemsize, n)
+        return a
+
+    def probe(self, keys, out_positions, out_payload=None):
+        return self.lib.orc_pjoin_probe(self.h, _p(keys), len(keys), _p(out_positions), _p(out_payload))
+
+    def decode(self, positions):
+        out = np.empty(len(positions), dtype=np.int32)
+        self.lib.orc_pjoin_decode(self.h, _p(positions), len(positions), _p(out))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.orc_pjoin_destroy(self.h)
             self.h = None
 
 

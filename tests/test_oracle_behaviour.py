@@ -236,3 +236,48 @@ def test_accumulator_known_answers():
 def test_hash_aggregation_operator_reference_case():
     pages, keys, aggs, expected = hash_aggregation_operator_case(4000)
     assert oracle_agg_rows(pages, keys, aggs) == expected
+
+
+def test_min_max_double_nan_ordering():
+    # max uses COMPARISON_UNORDERED_FIRST (NaN lowest), min COMPARISON_UNORDERED_LAST (NaN highest): the orderings pinned by
+    # TestMinMaxByAggregation.testMaxDoubleVarchar :270-291 (max_by over (NaN,1,2) / (1,NaN,2) / (1,2,NaN) picks the 2.0 row) and
+    # testMinRealVarchar :316-337 (min_by picks the 1.0 row); MaxAggregationFunction.java:49 / MinAggregationFunction.java:49
+    nan = float("nan")
+    aggs = [(abi.AGG_MAX, 1, -1), (abi.AGG_MIN, 1, -1)]
+    for values in ([nan, 1.0, 2.0], [1.0, nan, 2.0], [1.0, 2.0, nan]):
+        page = Page(Block.bigint(np.zeros(3, dtype=np.int64)), Block.double(values))
+        assert oracle_agg_rows([page], [0], aggs) == [(0, 2.0, 1.0)], values
+    # only NaN rows: the first value sets the state, nothing replaces it (state.isNull() branch)
+    rows = oracle_agg_rows([Page(Block.bigint([0, 0]), Block.double([nan, nan]))], [0], aggs)
+    assert rows[0][1] != rows[0][1] and rows[0][2] != rows[0][2]
+
+
+def test_partitioned_lookup_source_matches_single_table():
+    # PartitionedLookupSource over P partitions == one table: decode(partition, position) lands on the same build row
+    # (M/operator/join/unspilled/PartitionedLookupSource.java:149-186,259-275)
+    n_orders = 30_011
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, 0x7C02, True)
+    payload = (okeys % 2557).astype(np.int32)
+    rows = o.synth_lineitem_rows(n_orders)
+    lkeys = o.synth_lineitem_keys(n_orders, 0, rows, 0x7C01, True)
+    lkeys[::97] = -5                                             # misses
+    single = o.Join(Page(Block.bigint(okeys)), [0])
+    want = single.positions(Page(Block.bigint(lkeys)), [0])
+    for partitions, threads in ((1, 1), (4, 3), (16, 8)):
+        pj = o.PartitionedJoin(okeys, payload, partitions, threads)
+        assert pj.partitions == partitions and pj.threads == threads
+        pos = pj.alloc(rows, np.int64)
+        pay = pj.alloc(rows, np.int32)
+        for _ in range(2):                                       # the pool is reused across passes
+            assert pj.probe(lkeys, pos, pay) > 0
+        got = pj.decode(pos)
+        assert (got == want).all()
+        assert (pay == np.where(want >= 0, payload[np.maximum(want, 0)], 0)).all()
+        # the partition field of the encoded position is LocalPartitionGenerator.getPartition(rawHash) (:139,159)
+        lib = o.load()
+        for k, e in list(zip(lkeys[want >= 0], pos[want >= 0]))[:64]:
+            raw = lib.orc_hash_long(int(k))
+            raw = raw - (1 << 64) if raw >= (1 << 63) else raw
+            assert (int(e) & (pj.partitions - 1)) == lib.orc_local_partition(raw, pj.partitions)
+        pj.close()
+    single.close()
