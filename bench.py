@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000_000)
     ap.add_argument("--e2e-rows", type=int, default=0, help="probe rows fed from host per e2e step (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host pages) measurement: kernel experiments only")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128; 0 = leave the default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -293,12 +294,41 @@ def main():
     inflight = []
     step_rows = [0]
 
+    check = {"on": False, "rows": 0, "key": 0, "payload": 0, "key_mod": 0, "spot": 0}
+    M64 = (1 << 64) - 1
+
+    def column_sum(col, mod=0):
+        c = abi.Column()
+        c.type, c.flags, c.length, c.data, c.offsets, c.validity = col.type, 0, col.length, col.ptr, col.offsets, col.validity
+        v = C.c_int64()
+        ctx.check(lib.tgpu_column_sum(ctx.h, C.byref(c), mod, C.byref(v)))
+        return v.value & M64
+
+    def check_output(out):
+        """closed-form checks of one joined page (untimed verification pass): see `verify` in the JSON line"""
+        check["rows"] += out.rows
+        check["key"] = (check["key"] + column_sum(out.column(0))) & M64
+        check["payload"] = (check["payload"] + column_sum(out.column(2))) & M64
+        check["key_mod"] = (check["key_mod"] + column_sum(out.column(0), 2557)) & M64
+        if check["spot"] == 0 and out.rows > 0:
+            import oracle_lib as o
+            from trino_b200.page import Block, Page
+            m = min(out.rows, 1 << 20)
+            hk, hp, hb = np.empty(m, np.int64), np.empty(m, np.float64), np.empty(m, np.int64)
+            for arr, c in ((hk, 0), (hp, 1), (hb, 2)):
+                ctx.check(lib.tgpu_memcpy_d2h(ctx.h, C.c_void_p(arr.ctypes.data), C.c_void_p(out.column(c).ptr), m * 8))
+            assert (hb == hk % 2557).all() and (hp == hk * 0.5).all(), "joined row carries the wrong payload"
+            assert (o.partition_ids(Page(Block.bigint(hk)), [0], world) == rank).all(), "row received by the wrong rank (HashGenerator.java:41-46)"
+            check["spot"] = m
+
     def drain():
         if not inflight:
             return
         out = probe_op.get_output_device()
         step_rows[0] += out.rows if out else 0
         if out:
+            if check["on"]:
+                check_output(out)
             out.release()
         inflight.pop().release()
 
@@ -332,6 +362,8 @@ def main():
             out = probe_op.get_output_device()
             out_rows_seen[0] = out.rows if out else 0
             if out:
+                if check["on"]:
+                    check_output(out)
                 out.release()
             inp.release()
         else:
@@ -379,6 +411,30 @@ def main():
     else:
         total_out = out_rows_seen[0]
     assert total_out == total_rows, f"join produced {total_out} rows, expected {total_rows} (100 % match rate)"
+    verify = None
+    if world > 1:
+        # untimed verification pass of the partitioned path: row count and key sum conserved across exchange + join, every joined row
+        # carries the build payload of ITS key (sum(payload) == sum(key % 2557), the generator's closed form), and an oracle spot
+        # check that received rows belong to this rank under the reference's partition function
+        import torch
+        check["on"] = True
+        step()
+        if overlap:
+            while handles:
+                finish_one()
+            drain()
+        check["on"] = False
+        in_key = column_sum(ops.DeviceColumn(abi.INT64, d_lkeys, l_count))
+        mine = torch.tensor([check["rows"], l_count] + [x >> 32 for x in (check["key"], check["payload"], check["key_mod"], in_key)] +
+                            [x & 0xFFFFFFFF for x in (check["key"], check["payload"], check["key_mod"], in_key)], dtype=torch.int64, device=f"cuda:{local}")
+        dist.all_reduce(mine)
+        t = [int(x) for x in mine.tolist()]
+        tot = lambda i: ((t[2 + i] << 32) + t[6 + i]) & M64
+        verify = {"rows_out": t[0], "rows_in": t[1], "key_sum_conserved": tot(0) == tot(3), "payload_sum_matches_keys": tot(1) == tot(2),
+                  "oracle_spot_check_rows_per_rank": check["spot"],
+                  "how": "one untimed pass after the timed region: tgpu_column_sum over every joined page, all-reduced; spot check against oracle partition ids"}
+        assert verify["rows_out"] == verify["rows_in"] == total_rows, verify
+        assert verify["key_sum_conserved"] and verify["payload_sum_matches_keys"], verify
     ms_per_step = ms / args.steps
     value = total_rows / (ms_per_step * 1e-3)
 
@@ -417,7 +473,9 @@ def main():
 
     # ---------------- end to end: host pages in, host result out, through the same operator calls
     e2e = None
-    if world == 1:
+    if args.no_e2e:
+        pass
+    elif world == 1:
         e2e = bench_e2e(ctx, args, bridge, d_lkeys, d_lprice_col.ptr, l_count)
     elif overlap:
         e2e = bench_e2e_dist(ctx, args, dist, local, world, partitioner, probe_op, d_lkeys, d_lprice_col.ptr, l_count)
@@ -431,6 +489,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
                 "config": workload_config(args, n_orders, probe_rows, world), "gpu_launches": int(launches), "clocks": clocks,
                 "build_seconds": build_s, "output_rows_per_step": total_out, "l2_fetch_granularity": l2g.value}
+        if verify:
+            line["verify"] = verify
         if roofline:
             line["roofline"] = roofline
             line["roofline_index_probe"] = index_probe

@@ -434,6 +434,11 @@ int tgpu_synth_lineitem_q1(tgpu_ctx* ctx, int64_t n, int64_t first, uint64_t see
                            int32_t* shipdate, int8_t* returnflag, int8_t* linestatus,
                            double* quantity, double* extendedprice, double* discount, double* tax);
 
+/* bench / test hygiene: wrapping 64-bit sum of a fixed-width device column (raw bits for FLOAT64; value % mod when mod > 0; NULL rows
+ * skipped).  bench.py's N > 1 pass checks the partitioned join with it: sum(build payload) == sum(probe key % 2557), key sum and row
+ * count conserved across the exchange.  One small reduction kernel, independent of the aggregation operator it cross-checks. */
+int tgpu_column_sum(tgpu_ctx* ctx, const tgpu_column* device_column, int64_t mod, int64_t* out_sum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -344,3 +344,38 @@ def test_build_side_key_domain(ctx):
     assert (lo, hi, cnt, has_null) == (-2**63, 7, 3, False) and list(values) == [-2**63, 3, 7]
     lookup.close()
     b.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2", None])
+@pytest.mark.parametrize("shape", ["tpch", "every_8th", "clustered", "extremes", "shuffled_probe"])
+def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
+    """Slot placement is not observable: mix(key) (mode 0, M/operator/join/PagesHash.java:35-51), line-local (1) and order-preserving
+    lines (2, the default for integer keys; falls back to 1 when the keys pile up in a few lines) give the oracle's positions for dense,
+    strided (what a hash exchange leaves on one rank), clustered and extreme key sets."""
+    if mode is None:
+        monkeypatch.delenv("TGPU_JOIN_HASH", raising=False)
+    else:
+        monkeypatch.setenv("TGPU_JOIN_HASH", mode)
+    rng = np.random.default_rng(11)
+    n_orders = 100_000
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, 0x7C02, True)
+    rows = o.synth_lineitem_rows(n_orders)
+    lkeys = o.synth_lineitem_keys(n_orders, 0, rows, 0x7C01, shape == "shuffled_probe")
+    if shape == "every_8th":
+        okeys = okeys[o.partition_ids(Page(Block.bigint(okeys)), [0], 8) == 3]
+    elif shape == "clustered":      # two dense islands and a far outlier: most rows cannot stay in their home line
+        okeys = np.concatenate([np.arange(0, 100_000), np.arange(10**12, 10**12 + 100_000), [2**61]]).astype(np.int64)
+        lkeys = np.concatenate([rng.integers(-5, 100_010, 150_000), rng.integers(10**12 - 5, 10**12 + 100_010, 150_000), [2**61, 2**61 - 1]]).astype(np.int64)
+    elif shape == "extremes":       # span of almost 2^64, INT64_MIN (kept beside the table), negative keys
+        okeys = np.concatenate([[-2**63, 2**63 - 1, -1, 0, 1], rng.integers(-2**62, 2**62, 50_000)]).astype(np.int64)
+        lkeys = np.concatenate([okeys[::3], rng.integers(-2**63, 2**63 - 1, 100_000)]).astype(np.int64)
+    build = Page(Block.bigint(okeys), Block.bigint(okeys % 2557))
+    probe = Page(Block.bigint(lkeys), Block.double(lkeys * 0.5))
+    b, lk = _build_lookup(ctx, [build], out=[1])
+    oj = o.Join(build, [0])
+    want = oj.positions(Page(Block.bigint(lkeys)), [0])
+    assert (lk.get_join_positions(Page(Block.bigint(lkeys))) == want).all()
+    oj.close(); b.close(); lk.close()
+    # the operator (fused probe + payload gather, whole tiles + ragged tail) emits the oracle's rows
+    got = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
+    assert got == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False)

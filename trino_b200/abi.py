@@ -216,6 +216,7 @@ SIGNATURES = {
     "tgpu_synth_lineitem_rows": (C.c_int64, [C.c_int64]),
     "tgpu_synth_lineitem_keys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, VP]),
     "tgpu_synth_lineitem_q1": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP]),
+    "tgpu_column_sum": (C.c_int, [VP, VP, C.c_int64, VP]),
 }
 
 _lib = None

@@ -46,23 +46,34 @@ enum KeyKind { KEY_INT = 0, KEY_DOUBLE = 1 };
 //           LINES are scattered with the murmur3 finaliser; the probe sequence walks the 8 slots of the line (wrapping
 //           inside it) and then does the same in the following line.  Dense / clustered key domains probed in key
 //           order turn random sector reads into sequential line reads; random keys behave like mode 0.
-// The mode is folded into the top bit of `mask` arguments (capacity <= 2^31 slots, so the bit is free).
-constexpr unsigned long long MODE_BIT = 1ULL << 63;
+//   mode 2: order-preserving lines: line = (key - kmin) >> shift, with shift chosen at build time so that a line expects
+//           about four keys; same in-line walk as mode 1.  The table is then laid out in key order: a probe page that arrives in
+//           key order (TPC-H clustering; every sender's run after a stable hash exchange) walks the table front to back, whatever
+//           subset of the key domain this table holds - after a hash exchange over W ranks a table holds every W-th key or so
+//           of its domain, which leaves mode 1 with one useful key per line.  Chosen when the build keys spread evenly enough
+//           over [kmin, kmax] (rows that had to leave their home line are counted during the build; too many -> mode 1).
+struct JoinGeom {
+    unsigned long long mask;   // capacity - 1 (capacity is a power of two, at least one 8-slot line)
+    unsigned long long kmin;   // mode 2
+    int shift;                 // mode 2
+    int mode;
+};
 
-__host__ __device__ __forceinline__ unsigned long long join_slot_of(unsigned long long k, unsigned long long mask)
+__host__ __device__ __forceinline__ unsigned long long join_slot_of(unsigned long long k, const JoinGeom& g)
 {
-    if (mask & MODE_BIT) return ((tg::murmur3_mix(k >> 3) << 3) | (k & 7)) & (mask & ~MODE_BIT);
-    return tg::murmur3_mix(k) & mask;
+    if (g.mode == 2) return ((((k - g.kmin) >> g.shift) << 3) | (k & 7)) & g.mask;
+    if (g.mode == 1) return ((tg::murmur3_mix(k >> 3) << 3) | (k & 7)) & g.mask;
+    return tg::murmur3_mix(k) & g.mask;
 }
 
-__host__ __device__ __forceinline__ unsigned long long join_next_slot(unsigned long long pos, unsigned long long k, unsigned long long mask)
+__host__ __device__ __forceinline__ unsigned long long join_next_slot(unsigned long long pos, unsigned long long k, const JoinGeom& g)
 {
-    if (mask & MODE_BIT) {
+    if (g.mode != 0) {
         unsigned long long in = (pos + 1) & 7;
         if (in != (k & 7)) return (pos & ~7ULL) | in;
-        return ((((pos >> 3) + 1) << 3) | (k & 7)) & (mask & ~MODE_BIT);
+        return ((((pos >> 3) + 1) << 3) | (k & 7)) & g.mask;
     }
-    return (pos + 1) & mask;
+    return (pos + 1) & g.mask;
 }
 
 // canonical 64-bit join key; returns false when the row can never match (NULL, or NaN under EQUAL)
@@ -89,11 +100,13 @@ __global__ void join_table_init_kernel(int4* table, int64_t slots)
 }
 
 // one thread per build row: claim/find the key's slot, head = max(row).  *dup_flag is set when a key repeats.
-__global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, int64_t n, JoinSlot* __restrict__ table, unsigned long long mask,
-                                                         int* __restrict__ special_head, int* __restrict__ dup_flag)
+// moved[0] += rows that left their home line, moved[1] += rows that went more than 8 lines away (layout quality of modes 1 / 2)
+__global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, int64_t n, JoinSlot* __restrict__ table, JoinGeom geo,
+                                                         int* __restrict__ special_head, int* __restrict__ dup_flag, unsigned int* __restrict__ moved)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int left_home = 0, went_far = 0;
     for (; i < n; i += stride) {
         unsigned long long k;
         if (!join_key(key, kind, i, &k)) continue;
@@ -102,7 +115,8 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
             if (old >= 0) *dup_flag = 1;
             continue;
         }
-        unsigned long long pos = join_slot_of(k, mask);
+        unsigned long long pos = join_slot_of(k, geo);
+        const unsigned long long home = pos >> 3;
         while (true) {
             unsigned long long cur = *((volatile unsigned long long*)&table[pos].key);
             if (cur == EMPTY_KEY) cur = atomicCAS(&table[pos].key, EMPTY_KEY, k);
@@ -111,21 +125,53 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
                 if (old >= 0) *dup_flag = 1;
                 break;
             }
-            pos = join_next_slot(pos, k, mask);
+            pos = join_next_slot(pos, k, geo);
         }
+        if (geo.mode != 0 && (pos >> 3) != home) {
+            left_home++;
+            went_far += (((pos >> 3) - home) & (geo.mask >> 3)) > 8;
+        }
+    }
+    if (geo.mode != 0) {
+        for (int off = 16; off > 0; off >>= 1) {
+            left_home += __shfl_xor_sync(0xffffffffu, left_home, off);
+            went_far += __shfl_xor_sync(0xffffffffu, went_far, off);
+        }
+        if ((threadIdx.x & 31) == 0 && left_home) { atomicAdd(moved, left_home); atomicAdd(moved + 1, went_far); }
     }
 }
 
-__device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, unsigned long long mask, unsigned long long k, int special_head)
+// min / max of the non-NULL integer keys of the build side (mode 2 geometry)
+__global__ void join_key_range_kernel(ColRef key, int64_t n, long long* __restrict__ minmax)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    long long lo = INT64_MAX, hi = INT64_MIN;
+    for (; i < n; i += stride) {
+        if (!tg_valid(key.validity, i)) continue;
+        long long v = tg_load_i64(key, i);
+        if ((unsigned long long)v == EMPTY_KEY) continue;
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        long long a = __shfl_xor_sync(0xffffffffu, lo, off), b = __shfl_xor_sync(0xffffffffu, hi, off);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(minmax, lo); atomicMax(minmax + 1, hi); }
+}
+
+__device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, JoinGeom geo, unsigned long long k, int special_head)
 {
     if (k == EMPTY_KEY) return special_head;
-    unsigned long long pos = join_slot_of(k, mask);
+    unsigned long long pos = join_slot_of(k, geo);
     while (true) {
         int4 s = __ldg((const int4*)&table[pos]);
         unsigned long long sk = (unsigned long long)(unsigned int)s.x | ((unsigned long long)(unsigned int)s.y << 32);
         if (sk == k) return s.z;
         if (sk == EMPTY_KEY) return -1;
-        pos = join_next_slot(pos, k, mask);
+        pos = join_next_slot(pos, k, geo);
     }
 }
 
@@ -134,7 +180,7 @@ __device__ __forceinline__ int join_lookup(const JoinSlot* __restrict__ table, u
 // the same key (TPC-H clustering) collapse in the coalescer / L1.
 // Algorithmic bytes per probe row: 8 (key) + 12 (slot) + 4 (position) = 24.
 template <int ROWS, bool INT64_NO_NULLS>
-__global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
+__global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, JoinGeom geo,
                                                          int special_head, int* __restrict__ out)
 {
     int64_t tile = (int64_t)blockDim.x * ROWS;
@@ -154,7 +200,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
                 if (INT64_NO_NULLS) { k[j] = (unsigned long long)__ldg((const long long*)key.data + i); ok[j] = true; }
                 else ok[j] = join_key(key, kind, i, &k[j]);
             }
-            pos[j] = join_slot_of(k[j], mask);
+            pos[j] = join_slot_of(k[j], geo);
         }
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
@@ -177,7 +223,7 @@ __global__ void __launch_bounds__(256) join_probe_kernel(ColRef key, int kind, i
                         unsigned long long sk = (unsigned long long)(unsigned int)cur.x | ((unsigned long long)(unsigned int)cur.y << 32);
                         if (sk == k[j]) { res = cur.z; break; }
                         if (sk == EMPTY_KEY) break;
-                        p = join_next_slot(p, k[j], mask);
+                        p = join_next_slot(p, k[j], geo);
                         cur = __ldg((const int4*)&table[p]);
                     }
                 }
@@ -203,7 +249,7 @@ struct GatherCols {
 // no count/scan pass is needed when every probe row matches (FK -> PK joins).  Misses are counted; the host
 // compacts only when there are any.
 template <int ROWS, bool INT64_NO_NULLS>
-__global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
+__global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, JoinGeom geo,
                                                                 int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
 {
     // g.by_slot: payload arrays are indexed by table slot (special key at index mask + 1), else by build row id
@@ -227,7 +273,7 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
                 if (INT64_NO_NULLS) { k[j] = (unsigned long long)__ldg((const long long*)key.data + i); ok[j] = true; }
                 else ok[j] = join_key(key, kind, i, &k[j]);
             }
-            pos[j] = join_slot_of(k[j], mask);
+            pos[j] = join_slot_of(k[j], geo);
         }
 #pragma unroll
         for (int j = 0; j < ROWS; j++) {
@@ -239,7 +285,7 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
             int r = -1;
             long long where = 0;
             if (ok[j]) {
-                if (k[j] == EMPTY_KEY) { r = special_head; where = (long long)(mask & ~MODE_BIT) + 1; }
+                if (k[j] == EMPTY_KEY) { r = special_head; where = (long long)geo.mask + 1; }
                 else {
                     unsigned long long p = pos[j];
                     int4 cur = s[j];
@@ -247,7 +293,7 @@ __global__ void __launch_bounds__(256) join_probe_gather_kernel(ColRef key, int 
                         unsigned long long sk = (unsigned long long)(unsigned int)cur.x | ((unsigned long long)(unsigned int)cur.y << 32);
                         if (sk == k[j]) { r = cur.z; where = (long long)p; break; }
                         if (sk == EMPTY_KEY) break;
-                        p = join_next_slot(p, k[j], mask);
+                        p = join_next_slot(p, k[j], geo);
                         cur = __ldg((const int4*)&table[p]);
                     }
                 }
@@ -340,13 +386,13 @@ __global__ void join_fingerprint_kernel(KeyCols k, int64_t n, long long* __restr
 }
 
 __global__ void join_verify_build_kernel(KeyCols k, const long long* __restrict__ fp, const uint8_t* __restrict__ fp_validity, int64_t n,
-                                         const JoinSlot* __restrict__ table, unsigned long long mask, int special_head, int* __restrict__ collision)
+                                         const JoinSlot* __restrict__ table, JoinGeom geo, int special_head, int* __restrict__ collision)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         if (!tg_valid(fp_validity, i)) continue;
-        int head = join_lookup(table, mask, (unsigned long long)fp[i], special_head);
+        int head = join_lookup(table, geo, (unsigned long long)fp[i], special_head);
         if (head != (int)i && head >= 0 && !tg::rows_equal_for_join(k, i, k, head)) *collision = 1;
     }
 }
@@ -367,8 +413,9 @@ __global__ void join_verify_probe_kernel(KeyCols probe, KeyCols build, int64_t n
 // every other key shape go through the generic kernels).  ncu showed the generic kernels spending ~215 thread
 // instructions per probe row at 44-48 % issue utilisation, i.e. instruction-bound as much as latency-bound.
 template <int MODE>
-__device__ __forceinline__ unsigned int lean_slot(unsigned long long k, unsigned int mask)
+__device__ __forceinline__ unsigned int lean_slot(unsigned long long k, unsigned int mask, unsigned long long kmin, int shift)
 {
+    if (MODE == 2) return (((unsigned int)((k - kmin) >> shift) << 3) | ((unsigned int)k & 7u)) & mask;
     if (MODE == 1) return (((unsigned int)tg::murmur3_mix(k >> 3) << 3) | ((unsigned int)k & 7u)) & mask;
     return (unsigned int)tg::murmur3_mix(k) & mask;
 }
@@ -376,7 +423,7 @@ __device__ __forceinline__ unsigned int lean_slot(unsigned long long k, unsigned
 template <int MODE>
 __device__ __forceinline__ unsigned int lean_next(unsigned int pos, unsigned int k_low3, unsigned int mask)
 {
-    if (MODE == 1) {
+    if (MODE != 0) {
         unsigned int in = (pos + 1) & 7u;
         return in != k_low3 ? ((pos & ~7u) | in) : (((pos & ~7u) + 8u + k_low3) & mask);
     }
@@ -394,7 +441,7 @@ static int lean_grid(tgpu_ctx* ctx, K kernel, int64_t tiles)
 
 template <int MODE, bool GATHER, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB) join_probe_lean_kernel(const long long* __restrict__ keys, int64_t tiles, const int4* __restrict__ table, unsigned int mask,
-                                                              int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
+                                                              unsigned long long kmin, int shift, int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
 {
     unsigned int matched = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -405,7 +452,7 @@ __global__ void __launch_bounds__(256, MINB) join_probe_lean_kernel(const long l
 #pragma unroll
         for (int j = 0; j < 4; j++) k[j] = (unsigned long long)__ldg(keys + base + j * 256);
 #pragma unroll
-        for (int j = 0; j < 4; j++) pos[j] = lean_slot<MODE>(k[j], mask);
+        for (int j = 0; j < 4; j++) pos[j] = lean_slot<MODE>(k[j], mask, kmin, shift);
 #pragma unroll
         for (int j = 0; j < 4; j++) s[j] = __ldg(table + pos[j]);
         int res[4];
@@ -465,6 +512,28 @@ __global__ void __launch_bounds__(256, MINB) join_probe_lean_kernel(const long l
     }
 }
 
+// launch of the lean probe kernel for the table's layout mode
+template <bool GATHER>
+static int launch_lean(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys, int64_t tiles, const int4* table, int special_head, int* out, const GatherCols& g,
+                       unsigned long long* matches)
+{
+    const unsigned int mask32 = (unsigned int)geo.mask;
+    // 8 CTAs per SM (32 registers): full occupancy is worth more than the registers (measured 4.9 -> 3.4 ms at SF100)
+    if (geo.mode == 2) {
+        auto k = join_probe_lean_kernel<2, GATHER, 8>;
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, table, mask32, geo.kmin, geo.shift, special_head, out, g, matches);
+    }
+    else if (geo.mode == 1) {
+        auto k = join_probe_lean_kernel<1, GATHER, 8>;
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, table, mask32, 0ULL, 0, special_head, out, g, matches);
+    }
+    else {
+        auto k = join_probe_lean_kernel<0, GATHER, 8>;
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, table, mask32, 0ULL, 0, special_head, out, g, matches);
+    }
+    return TGPU_OK;
+}
+
 // build payload re-laid out in SLOT order (one pass at build time): the fused probe then reads the payload right next
 // to where it found the key instead of chasing the row id into the (arbitrarily ordered) build pages
 __global__ void join_payload_by_slot_kernel(const JoinSlot* __restrict__ table, int64_t slots, int special_head, const void* __restrict__ src, int elem,
@@ -486,7 +555,7 @@ __global__ void join_payload_by_slot_kernel(const JoinSlot* __restrict__ table, 
 
 // --- duplicate chains -------------------------------------------------------------------------------
 // sort key = (slot << 32 | row) for rows that are in the table; rows with NULL keys sort last
-__global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, unsigned long long mask,
+__global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const JoinSlot* __restrict__ table, JoinGeom geo,
                                         unsigned long long special_slot, unsigned long long* __restrict__ out)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,8 +566,8 @@ __global__ void join_slot_of_row_kernel(ColRef key, int kind, int64_t n, const J
         if (join_key(key, kind, i, &k)) {
             if (k == EMPTY_KEY) slot = special_slot;
             else {
-                unsigned long long pos = join_slot_of(k, mask);
-                while (table[pos].key != k) pos = join_next_slot(pos, k, mask);
+                unsigned long long pos = join_slot_of(k, geo);
+                while (table[pos].key != k) pos = join_next_slot(pos, k, geo);
                 slot = pos;
             }
         }
@@ -582,7 +651,7 @@ struct tgpu_lookup {
     int64_t positions = 0;              // build rows (incl. NULL-key rows: PagesIndex keeps them)
     int key_type = 0;
     DevBuf table;                       // JoinSlot[capacity]
-    unsigned long long mask = 0;
+    JoinGeom geo = {0, 0, 0, 0};        // capacity - 1, slot placement mode and its parameters
     int special_head = -1;
     bool has_dups = false;
     DevBuf links;                       // int32[positions], only when has_dups
@@ -664,13 +733,7 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
         if (tiles > 0) {
             GatherCols none;
             memset(&none, 0, sizeof(none));
-            unsigned int mask32 = (unsigned int)(lk->mask & ~MODE_BIT);
-            // 8 CTAs per SM (32 registers): full occupancy is worth more than the registers (measured 4.9 -> 3.4 ms at SF100)
-            auto l0 = join_probe_lean_kernel<0, false, 8>;
-            auto l1 = join_probe_lean_kernel<1, false, 8>;
-            int lgrid = lean_grid(ctx, (lk->mask & MODE_BIT) ? l1 : l0, tiles);
-            if (lk->mask & MODE_BIT) TG_LAUNCH(ctx, l1, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lk->special_head, d_out, none, (unsigned long long*)nullptr);
-            else TG_LAUNCH(ctx, l0, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lk->special_head, d_out, none, (unsigned long long*)nullptr);
+            TG_TRY(launch_lean<false>(ctx, lk->geo, (const long long*)key.data, tiles, (const int4*)table, lk->special_head, d_out, none, (unsigned long long*)nullptr));
             done = tiles * 1024;
         }
     }
@@ -678,8 +741,8 @@ int lookup_positions(tgpu_ctx* ctx, const tgpu_lookup* lk, const DevColumn& key,
         ColRef kr = tg_colref(key);
         if (done > 0) kr.data = (const char*)kr.data + done * 8;   // only the fast (INT64, no validity) shape gets here with done > 0
         int grid = tg_grid(ctx, n - done, 256 * 4, 8);
-        if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done);
-        else TG_LAUNCH(ctx, k4a, grid, 256, 0, kr, kind, n - done, table, lk->mask, lk->special_head, d_out + done);
+        if (fast) TG_LAUNCH(ctx, k4f, grid, 256, 0, kr, kind, n - done, table, lk->geo, lk->special_head, d_out + done);
+        else TG_LAUNCH(ctx, k4a, grid, 256, 0, kr, kind, n - done, table, lk->geo, lk->special_head, d_out + done);
     }
     TG_TIMED_END(ctx);
     return TGPU_OK;
@@ -867,24 +930,58 @@ struct JoinBuildOp : tgpu_op {
         int64_t need = (int64_t)((double)rows / lf) + 1;
         int64_t cap = 8;   // at least one 8-slot line
         while (cap < need) cap <<= 1;
-        // line-local layout by default; it wants lines at most about half full (measured: exp_join_summary in profiles/)
+        // line layouts (modes 1 / 2) want lines at most about half full (measured: exp_join_summary in profiles/)
         const char* env_mode = getenv("TGPU_JOIN_HASH");
-        int hash_mode = env_mode ? atoi(env_mode) : 1;
+        const DevColumn& bkey = lk->store.cols[0];
+        const bool int_key = !lk->generic && key_kind_of(bkey.type) == KEY_INT;
+        int hash_mode = env_mode ? atoi(env_mode) : (int_key && rows > 0 ? 2 : 1);
+        if (hash_mode == 2 && !(int_key && rows > 0)) hash_mode = 1;
         const char* env_shift = getenv("TGPU_JOIN_CAP_SHIFT");
         int cap_shift = env_shift ? atoi(env_shift) : (hash_mode ? 1 : 0);
         cap <<= cap_shift;
         if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
-
-        lk->mask = ((unsigned long long)cap - 1) | (hash_mode ? MODE_BIT : 0);
+        lk->geo.mask = (unsigned long long)cap - 1;
+        lk->geo.kmin = 0;
+        lk->geo.shift = 0;
+        if (hash_mode == 2) {
+            // order-preserving lines: the key range [kmin, kmax] is cut into cap / 8 lines of 2^shift key values
+            long long* d_range = (long long*)(ctx->d_scratch + 24);
+            long long init_range[2] = {INT64_MAX, INT64_MIN};
+            TG_CUDA(ctx, cudaMemcpyAsync(d_range, init_range, sizeof(init_range), cudaMemcpyHostToDevice, ctx->stream));
+            TG_LAUNCH(ctx, join_key_range_kernel, tg_grid(ctx, rows, 1024, 8), 256, 0, tg_colref(bkey), rows, d_range);
+            long long h_range[2];
+            TG_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_range[0] > h_range[1]) hash_mode = 1;      // no insertable key at all
+            else {
+                const unsigned long long span = (unsigned long long)h_range[1] - (unsigned long long)h_range[0];   // kmax - kmin, exact in 64 bits
+                const unsigned long long lines = (unsigned long long)cap >> 3;
+                int shift = 0;
+                while (shift < 63 && (span >> shift) >= lines) shift++;
+                if ((span >> shift) >= lines) hash_mode = 1;  // a span of 2^63 or more over very few lines: not worth a special case
+                lk->geo.kmin = (unsigned long long)h_range[0];
+                lk->geo.shift = shift;
+            }
+        }
         TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
-        TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
-        int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag
-        int init[2] = {-1, 0};
-        TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        if (rows > 0) {
-            const DevColumn& key = lk->store.cols[0];
-            TG_LAUNCH(ctx, join_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(key), key_kind_of(key.type), rows,
-                      lk->table.as<JoinSlot>(), lk->mask, d_flags, d_flags + 1);
+        int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag, [2] rows off their home line, [3] rows more than 8 lines off
+        while (true) {
+            lk->geo.mode = hash_mode;
+            TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
+            int init[4] = {-1, 0, 0, 0};
+            TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+            if (rows > 0) {
+                TG_LAUNCH(ctx, join_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(bkey), key_kind_of(bkey.type), rows,
+                          lk->table.as<JoinSlot>(), lk->geo, d_flags, d_flags + 1, (unsigned int*)(d_flags + 2));
+            }
+            if (hash_mode != 2) break;
+            // mode 2 relies on the keys spreading evenly over their range; clustered domains pile up in a few lines.  More than
+            // 1/8 of the rows off their home line, or any row further than 8 lines away: rebuild with scattered lines (mode 1)
+            int64_t moved = 0;
+            TG_TRY(tg_read_i64(ctx, d_flags + 2, &moved));
+            const int64_t off_home = moved & 0xFFFFFFFFLL, far = (moved >> 32) & 0xFFFFFFFFLL;
+            if (off_home * 8 <= rows && far * 1024 <= rows) break;
+            hash_mode = 1;
         }
         int64_t packed = 0;
         TG_TRY(tg_read_i64(ctx, d_flags, &packed));
@@ -897,7 +994,7 @@ struct JoinBuildOp : tgpu_op {
             TG_TRY(keys_in.alloc(ctx, (size_t)rows * 8));
             TG_TRY(keys_out.alloc(ctx, (size_t)rows * 8));
             TG_LAUNCH(ctx, join_slot_of_row_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(key), key_kind_of(key.type), rows,
-                      lk->table.as<JoinSlot>(), lk->mask, (unsigned long long)cap, keys_in.as<unsigned long long>());
+                      lk->table.as<JoinSlot>(), lk->geo, (unsigned long long)cap, keys_in.as<unsigned long long>());
             size_t tmp_bytes = 0;
             cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys_in.as<unsigned long long>(), keys_out.as<unsigned long long>(), (int)rows, 0, 64, ctx->stream);
             TG_TRY(tmp.alloc(ctx, tmp_bytes));
@@ -911,7 +1008,7 @@ struct JoinBuildOp : tgpu_op {
             TG_CUDA(ctx, cudaMemsetAsync(d_collision, 0, 8, ctx->stream));
             const DevColumn& fp = lk->store.cols[0];
             TG_LAUNCH(ctx, join_verify_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, key_cols_of(lk->build_keys), (const long long*)fp.data, fp.validity, rows,
-                      lk->table.as<JoinSlot>(), lk->mask, lk->special_head, d_collision);
+                      lk->table.as<JoinSlot>(), lk->geo, lk->special_head, d_collision);
             int64_t collided = 0;
             TG_TRY(tg_read_i64(ctx, d_collision, &collided));
             if (collided & 0xFFFFFFFFLL)
@@ -1024,12 +1121,7 @@ struct JoinProbeOp : tgpu_op {
         if (fast && !getenv("TGPU_JOIN_GENERIC_KERNELS")) {
             int64_t tiles = n / 1024;
             if (tiles > 0) {
-                unsigned int mask32 = (unsigned int)(lookup->mask & ~MODE_BIT);
-                auto l0 = join_probe_lean_kernel<0, true, 8>;
-                auto l1 = join_probe_lean_kernel<1, true, 8>;
-                int lgrid = lean_grid(ctx, (lookup->mask & MODE_BIT) ? l1 : l0, tiles);
-                if (lookup->mask & MODE_BIT) TG_LAUNCH(ctx, l1, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lookup->special_head, jp->as<int>(), g, d_matches);
-                else TG_LAUNCH(ctx, l0, lgrid, 256, 0, (const long long*)key.data, tiles, (const int4*)table, mask32, lookup->special_head, jp->as<int>(), g, d_matches);
+                TG_TRY(launch_lean<true>(ctx, lookup->geo, (const long long*)key.data, tiles, (const int4*)table, lookup->special_head, jp->as<int>(), g, d_matches));
                 done = tiles * 1024;
             }
         }
@@ -1041,8 +1133,8 @@ struct JoinProbeOp : tgpu_op {
                 for (int c = 0; c < gt.count; c++) gt.dst[c] = (char*)gt.dst[c] + done * gt.elem[c];
             }
             int tgrid = tg_grid(ctx, n - done, 256 * ROWS, 8);
-            if (fast) TG_LAUNCH(ctx, k_fast, tgrid, 256, 0, kr, KEY_INT, n - done, table, lookup->mask, lookup->special_head, jp->as<int>() + done, gt, d_matches);
-            else TG_LAUNCH(ctx, k_any, tgrid, 256, 0, kr, key_kind_of(key.type), n - done, table, lookup->mask, lookup->special_head, jp->as<int>() + done, gt, d_matches);
+            if (fast) TG_LAUNCH(ctx, k_fast, tgrid, 256, 0, kr, KEY_INT, n - done, table, lookup->geo, lookup->special_head, jp->as<int>() + done, gt, d_matches);
+            else TG_LAUNCH(ctx, k_any, tgrid, 256, 0, kr, key_kind_of(key.type), n - done, table, lookup->geo, lookup->special_head, jp->as<int>() + done, gt, d_matches);
         }
         TG_TIMED_END(ctx);
         *handled = true;
@@ -1520,7 +1612,7 @@ extern "C" int tgpu_lookup_key_domain(tgpu_ctx* ctx, tgpu_lookup* lookup, int64_
         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "key domains are collected for single BIGINT-family join keys only");
     TG_TRY(lookup_count_null_keys(ctx, lookup));
     if (has_null_out) *has_null_out = lookup->null_key_rows > 0;
-    const int64_t slots = (int64_t)(lookup->mask & ~MODE_BIT) + 1;
+    const int64_t slots = (int64_t)lookup->geo.mask + 1;
     DevBuf state, vals;
     TG_TRY(state.alloc(ctx, 24));
     TG_TRY(vals.alloc(ctx, (size_t)std::max<int64_t>(max_values, 1) * 8));

@@ -80,7 +80,36 @@ __global__ void synth_q1_kernel(int64_t n, int64_t first, uint64_t seed, int32_t
     }
 }
 
+// wrapping 64-bit sum of the values of a fixed-width column (value % mod when mod > 0); NULL rows are skipped
+__global__ void column_sum_kernel(ColRef col, int64_t n, long long mod, unsigned long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long acc = 0;
+    for (; i < n; i += stride) {
+        if (!tg_valid(col.validity, i)) continue;
+        long long v = tg_load_i64(col, i);
+        acc += (unsigned long long)(mod > 0 ? v % mod : v);
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 }  // namespace
+
+extern "C" int tgpu_column_sum(tgpu_ctx* ctx, const tgpu_column* device_column, int64_t mod, int64_t* out_sum)
+{
+    if (!ctx || !device_column || !out_sum) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevColumn c;
+    TG_TRY(tg_ingest_column(ctx, device_column, true, &c));
+    if (c.elem_size() == 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "tgpu_column_sum needs a fixed-width column");
+    DevBuf acc;
+    TG_TRY(acc.alloc(ctx, 8));
+    TG_CUDA(ctx, cudaMemsetAsync(acc.p, 0, 8, ctx->stream));
+    if (c.length > 0) TG_LAUNCH(ctx, column_sum_kernel, tg_grid(ctx, c.length, 1024, 8), 256, 0, tg_colref(c), c.length, (long long)mod, acc.as<unsigned long long>());
+    return tg_read_i64(ctx, acc.p, out_sum);
+}
 
 extern "C" int64_t tgpu_synth_lineitem_rows(int64_t n_orders)
 {
