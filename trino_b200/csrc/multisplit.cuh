@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(32 * WWARPS) xchg_hist_warp_kernel(KeyCols key
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int64_t row = base + u * 32 + lane;
-            if (row < end) pid_out[row] = (uint8_t)pidv[u];
+            if (pid_out && row < end) pid_out[row] = (uint8_t)pidv[u];     // pid_out == nullptr: the scatter recomputes the ids from the key
 #pragma unroll
             for (int q = 0; q < 8; q++) cnt[q] += (pidv[u] == q);
         }
@@ -303,9 +303,12 @@ __device__ __forceinline__ unsigned int field16(unsigned long long lo, unsigned 
 
 // (An aligned-window copy-out - every warp store one aligned segment of one partition run - was worth +15 % when the stores
 // crossed NVLink and cost 50 % for local destinations; peer destinations no longer use this kernel, so it is gone.)
-template <bool VEC>
+// KEYS: the partition ids are recomputed from the single BIGINT key column (`key0`, no NULLs) instead of being read from the 1-byte id
+// array the histogram pass would otherwise have to write: 2 bytes per row less HBM traffic for one hash (two multiplies) per row
+template <bool VEC, bool KEYS>
 __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t wchunk, int32_t P,
-                                                                        const long long* __restrict__ block_off, XchgCols cols)
+                                                                        const long long* __restrict__ block_off, XchgCols cols,
+                                                                        const long long* __restrict__ key0, int32_t bucket_count, const int32_t* __restrict__ b2p)
 {
     __shared__ long long stage_all[WWARPS][WTILE];
     __shared__ long long run_all[WWARPS][8];
@@ -326,16 +329,46 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
     __syncwarp();
     auto load_pids = [&](int64_t tile) -> unsigned long long {
         int64_t row0 = tile + lane * WR;
+        if (KEYS) {
+            unsigned long long v = ~0ull;     // 0xff = no row
+            if (row0 + WR <= end) {
+                long long k[WR];
+                if (VEC) {
+                    const longlong2* s2 = (const longlong2*)(key0 + row0);
+#pragma unroll
+                    for (int j = 0; j < WR / 2; j++) { longlong2 t = s2[j]; k[2 * j] = t.x; k[2 * j + 1] = t.y; }
+                }
+                else {
+#pragma unroll
+                    for (int i = 0; i < WR; i++) k[i] = key0[row0 + i];
+                }
+                v = 0;
+#pragma unroll
+                for (int i = 0; i < WR; i++) {
+                    int32_t bucket = process_raw_hash(hash_long(k[i]), bucket_count);
+                    v |= (unsigned long long)(unsigned int)(b2p ? b2p[bucket] : bucket) << (8 * i);
+                }
+            }
+            else {
+                for (int i = 0; i < WR; i++)
+                    if (row0 + i < end) {
+                        int32_t bucket = process_raw_hash(hash_long(key0[row0 + i]), bucket_count);
+                        v = (v & ~(0xffull << (8 * i))) | ((unsigned long long)(unsigned int)(b2p ? b2p[bucket] : bucket) << (8 * i));
+                    }
+            }
+            return v;
+        }
         if (row0 + WR <= end) return *(const unsigned long long*)(pids + row0);
         unsigned long long v = ~0ull;     // 0xff = no row
         for (int i = 0; i < WR; i++)
             if (row0 + i < end) v = (v & ~(0xffull << (8 * i))) | ((unsigned long long)pids[row0 + i] << (8 * i));
         return v;
     };
-    unsigned long long next_pid8 = load_pids(begin);
+    unsigned long long next_pid8 = KEYS ? 0ull : load_pids(begin);
     for (int64_t tile = begin; tile < end; tile += WTILE) {
-        const unsigned long long pid8 = next_pid8;
-        if (tile + WTILE < end) next_pid8 = load_pids(tile + WTILE);
+        // (the id-array form prefetches the next tile's ids; the key form would hold 16 more registers across the tile)
+        const unsigned long long pid8 = KEYS ? load_pids(tile) : next_pid8;
+        if (!KEYS && tile + WTILE < end) next_pid8 = load_pids(tile + WTILE);
         const int64_t row0 = tile + lane * WR;
         const int tile_rows = (int)min((int64_t)WTILE, end - tile);
         // per-lane counters (8-bit fields) and the rank of each of my rows among my earlier rows of the same partition
@@ -483,11 +516,18 @@ static XchgGeom xchg_geom(tgpu_ctx* ctx, int64_t n, int P, bool remote)
     return g;
 }
 
+// single BIGINT key channel without NULLs: the shape whose partition ids the scatter can recompute
+static bool xchg_key_is_plain_bigint(const KeyCols& k)
+{
+    return k.count == 1 && !k.is_utf8[0] && !k.is_double[0] && k.cols[0].elem == 8 && !k.cols[0].validity;
+}
+
+// `pids` == nullptr (warp mode, plain BIGINT key only): no id array is written; pass the key to xchg_launch_scatter instead
 static int xchg_launch_hist(tgpu_ctx* ctx, const XchgGeom& g, const KeyCols& k, int64_t n, int32_t bucket_count, const int32_t* b2p, int32_t P, uint8_t* pids,
                             unsigned int* hist)
 {
     if (g.warp_mode) {
-        bool fast = k.count == 1 && !k.is_utf8[0] && !k.is_double[0] && k.cols[0].elem == 8 && !k.cols[0].validity;
+        bool fast = xchg_key_is_plain_bigint(k);
         if (fast) TG_LAUNCH(ctx, xchg_hist_warp_kernel<true>, g.grid, 32 * WWARPS, 0, k, n, g.chunk, bucket_count, b2p, P, pids, hist);
         else TG_LAUNCH(ctx, xchg_hist_warp_kernel<false>, g.grid, 32 * WWARPS, 0, k, n, g.chunk, bucket_count, b2p, P, pids, hist);
     }
@@ -495,13 +535,27 @@ static int xchg_launch_hist(tgpu_ctx* ctx, const XchgGeom& g, const KeyCols& k, 
     return TGPU_OK;
 }
 
-static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* pids, int64_t n, int32_t P, const long long* block_off, const XchgCols& xc)
+// true when hist + scatter can run without the 1-byte id array for this geometry and key
+static bool xchg_ids_from_key(const XchgGeom& g, const KeyCols& k)
+{
+    return g.warp_mode && xchg_key_is_plain_bigint(k) && !getenv("TGPU_XCHG_PID_ARRAY");
+}
+
+static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* pids, int64_t n, int32_t P, const long long* block_off, const XchgCols& xc,
+                               const KeyCols* key = nullptr, int32_t bucket_count = 0, const int32_t* b2p = nullptr)
 {
     if (g.warp_mode) {
-        bool vec = ((uintptr_t)pids & 7) == 0;
+        const long long* key0 = pids ? nullptr : (const long long*)key->cols[0].data;
+        bool vec = pids ? ((uintptr_t)pids & 7) == 0 : ((uintptr_t)key0 & 15) == 0;
         for (int c = 0; c < xc.count; c++) vec = vec && ((uintptr_t)xc.src[c] & 15) == 0;
-        if (vec) TG_LAUNCH(ctx, xchg_scatter_warp_kernel<true>, g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
-        else TG_LAUNCH(ctx, xchg_scatter_warp_kernel<false>, g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc);
+        if (key0) {
+            if (vec) TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<true, true>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);
+            else TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<false, true>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);
+        }
+        else {
+            if (vec) TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<true, false>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);
+            else TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<false, false>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);
+        }
         return TGPU_OK;
     }
     TG_LAUNCH(ctx, xchg_scatter_kernel<4>, g.grid, XT, 0, pids, n, g.chunk, P, block_off, xc);

@@ -288,14 +288,15 @@ struct PartitionOp : tgpu_op {
         const XchgGeom geom = xchg_geom(ctx, n, P, false);
         const int grid = geom.nchunks;
         DevBuf pids, hist, block_off, d_totals;
-        TG_TRY(pids.alloc(ctx, (size_t)n));
         TG_TRY(hist.alloc(ctx, (size_t)grid * P * 4));
         TG_TRY(block_off.alloc(ctx, (size_t)grid * P * 8));
         TG_TRY(d_totals.alloc(ctx, (size_t)P * 8));
         KeyCols k;
         TG_TRY(key_cols(in, &k));
-        TG_TRY(xchg_launch_hist(ctx, geom, k, n, bucket_count, bucket_to_partition.empty() ? nullptr : d_b2p.as<int32_t>(), P, pids.as<uint8_t>(),
-                                hist.as<unsigned int>()));
+        const int32_t* b2p = bucket_to_partition.empty() ? nullptr : d_b2p.as<int32_t>();
+        const bool ids_from_key = xchg_ids_from_key(geom, k);      // plain BIGINT key: no 1-byte id array between the two passes
+        if (!ids_from_key) TG_TRY(pids.alloc(ctx, (size_t)n));
+        TG_TRY(xchg_launch_hist(ctx, geom, k, n, bucket_count, b2p, P, ids_from_key ? nullptr : pids.as<uint8_t>(), hist.as<unsigned int>()));
         TG_LAUNCH(ctx, xchg_offsets_kernel, P, 256, 0, hist.as<unsigned int>(), grid, P, block_off.as<long long>(), d_totals.as<long long>());
         std::vector<long long> counts(P), off(P + 1, 0);
         TG_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_totals.p, (size_t)P * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -323,7 +324,7 @@ struct PartitionOp : tgpu_op {
         xc.count = (int32_t)lanes.size();
         for (size_t l = 0; l < lanes.size(); l++) { xc.elem[l] = lanes[l].elem; xc.src[l] = lanes[l].src; }
         xc.dst = d_dst.as<char*>();
-        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, P, block_off.as<long long>(), xc));
+        TG_TRY(xchg_launch_scatter(ctx, geom, ids_from_key ? nullptr : pids.as<uint8_t>(), n, P, block_off.as<long long>(), xc, &k, bucket_count, b2p));
         mark("scatter");
         for (int q = 0; q < P; q++) {
             if (counts[q] == 0) continue;
@@ -852,31 +853,34 @@ extern "C" int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tg
     const XchgGeom geom = xchg_geom(ctx, n, W, false);
     const int grid = geom.nchunks;
     DevBuf pids, hist, block_off, d_totals;
-    TG_TRY(pids.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
     TG_TRY(hist.alloc(ctx, (size_t)grid * W * 4));
     TG_TRY(block_off.alloc(ctx, (size_t)grid * W * 8));
     TG_TRY(d_totals.alloc(ctx, (size_t)(W + C) * 8));
-    std::vector<long long> send_vec(W + C, 0);
-    if (n > 0) {
-        KeyCols k;
-        TG_TRY(p->key_cols(in, &k));
-        TG_TRY(xchg_launch_hist(ctx, geom, k, n, p->bucket_count, p->bucket_to_partition.empty() ? nullptr : p->d_b2p.as<int32_t>(), W, pids.as<uint8_t>(),
-                                hist.as<unsigned int>()));
-        TG_LAUNCH(ctx, xchg_offsets_kernel, W, 256, 0, hist.as<unsigned int>(), grid, W, block_off.as<long long>(), d_totals.as<long long>());
-        TG_CUDA(ctx, cudaMemcpyAsync(send_vec.data(), d_totals.p, (size_t)W * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    for (int c = 0; c < C; c++) send_vec[W + c] = in.cols[c].validity ? 1 : 0;
-    // 2. count matrix
     const int V = W + C;
+    KeyCols k;
+    memset(&k, 0, sizeof(k));
+    const int32_t* b2p = p->bucket_to_partition.empty() ? nullptr : p->d_b2p.as<int32_t>();
+    bool ids_from_key = false;
+    // the vector this rank contributes to the count matrix is assembled ON THE DEVICE (W send counts from the offsets kernel, then one
+    // "has NULLs" flag per column), so the host waits once per exchange - for the all-gathered matrix - not twice
+    std::vector<long long> flags(V, 0);
+    for (int c = 0; c < C; c++) flags[W + c] = in.cols[c].validity ? 1 : 0;
+    TG_CUDA(ctx, cudaMemcpyAsync(d_totals.p, flags.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n > 0) {
+        TG_TRY(p->key_cols(in, &k));
+        ids_from_key = xchg_ids_from_key(geom, k);
+        if (!ids_from_key) TG_TRY(pids.alloc(ctx, (size_t)n));
+        TG_TRY(xchg_launch_hist(ctx, geom, k, n, p->bucket_count, b2p, W, ids_from_key ? nullptr : pids.as<uint8_t>(), hist.as<unsigned int>()));
+        TG_LAUNCH(ctx, xchg_offsets_kernel, W, 256, 0, hist.as<unsigned int>(), grid, W, block_off.as<long long>(), d_totals.as<long long>());
+    }
+    // 2. count matrix
     std::vector<long long> matrix((size_t)W * V);
-    DevBuf d_send, d_matrix;
-    TG_TRY(d_send.alloc(ctx, (size_t)V * 8));
+    DevBuf d_matrix;
     TG_TRY(d_matrix.alloc(ctx, (size_t)W * V * 8));
-    TG_CUDA(ctx, cudaMemcpyAsync(d_send.p, send_vec.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ctx->stream));
-    TG_NCCL(ctx, g_nccl.all_gather(d_send.p, d_matrix.p, (size_t)V, NCCL_INT64, ctx->comm, ctx->stream));
+    TG_NCCL(ctx, g_nccl.all_gather(d_totals.p, d_matrix.p, (size_t)V, NCCL_INT64, ctx->comm, ctx->stream));
     TG_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)W * V * 8, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<long long> send_vec(matrix.begin() + (size_t)ctx->rank * V, matrix.begin() + (size_t)(ctx->rank + 1) * V);
     std::vector<long long> send_off(W + 1, 0), total_recv_of(W, 0);
     for (int r = 0; r < W; r++) send_off[r + 1] = send_off[r] + send_vec[r];
     for (int d = 0; d < W; d++)
@@ -935,7 +939,7 @@ extern "C" int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tg
         xc.count = (int32_t)L;
         for (size_t l = 0; l < L; l++) { xc.elem[l] = x->lanes[l].elem; xc.src[l] = srcs[l]; }
         xc.dst = d_dst.as<char*>();
-        TG_TRY(xchg_launch_scatter(ctx, geom, pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc));
+        TG_TRY(xchg_launch_scatter(ctx, geom, ids_from_key ? nullptr : pids.as<uint8_t>(), n, W, block_off.as<long long>(), xc, &k, p->bucket_count, b2p));
     }
     // 4. hand over to the copy engines.  The event also orders the transfer behind everything enqueued on this context so far:
     //    the readers of the arena this exchange's peers will overwrite NEXT (see the header).
