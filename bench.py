@@ -172,7 +172,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--sf", type=float, default=100.0, help="TPC-H scale factor of the join workload per GPU")
+    ap.add_argument("--workload", default="join", choices=["join", "q3way", "star", "q1"],
+                    help="join (default, BASELINE.json configs[1]; the line the driver reads) | q3way (configs[3]) | star (configs[4]) | q1 (configs[2] across GPUs): bench_workloads.py")
+    ap.add_argument("--sf", type=float, default=None, help="TPC-H scale factor per GPU (default 100 for the join workload, 37.5 = SF300 / 8 for q3way)")
+    ap.add_argument("--ds-sf", type=float, default=125.0, help="TPC-DS scale factor per GPU of the star workload (125 = SF1000 / 8)")
+    ap.add_argument("--star-chunks", type=int, default=4, help="pages the fact shard is fed in per step (bounds the intermediate pages)")
     ap.add_argument("--q1-sf", type=float, default=300.0, help="scale factor of the Q1 GROUP-BY side measurement (0 = skip)")
     ap.add_argument("--shuffle-probe", action="store_true", help="variant B: uniformly shuffled probe keys")
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000_000)
@@ -181,8 +185,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host pages) measurement: kernel experiments only")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128; 0 = leave the default)")
     args = ap.parse_args()
+    if args.sf is None:
+        args.sf = 37.5 if args.workload == "q3way" else 100.0
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload != "join":
+        import bench_workloads
+        return bench_workloads.main(args, ClockSampler, dist_env)
 
     rank, world, local = dist_env()
     from trino_b200 import abi

@@ -380,6 +380,12 @@ int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_pa
  * exchange's partition/scatter passes overlap the consumer's kernels.  consumer == NULL: identical to tgpu_exchange_partitioned. */
 int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_ctx* consumer, tgpu_page** out);
 
+/* Broadcast exchange: the REPLICATED join distribution (FIXED_BROADCAST_DISTRIBUTION, M/sql/planner/SystemPartitioningHandle.java:51;
+ * BroadcastOutputBuffer hands every page to every consumer): every rank receives the concatenation, in rank order, of the pages all
+ * ranks passed in - the whole (small) build side on every GPU.  Collective: every rank calls it, also with an empty page.  Fixed-width
+ * columns only.  With world == 1 it returns a copy of the page. */
+int tgpu_exchange_broadcast(tgpu_ctx* ctx, const tgpu_page* page, tgpu_page** out);
+
 /* Split-phase exchange for pipelines (one context): _begin partitions the page (multi-split into per-destination send
  * buffers; rows that stay are written to their final place), then hands the transfer to the copy engines - one peer copy per
  * (destination, column) over NVLink on a side stream, closed by a barrier on a second communicator - and returns while it
@@ -433,6 +439,17 @@ int tgpu_synth_lineitem_keys(tgpu_ctx* ctx, int64_t n_orders, int64_t first, int
 int tgpu_synth_lineitem_q1(tgpu_ctx* ctx, int64_t n, int64_t first, uint64_t seed,
                            int32_t* shipdate, int8_t* returnflag, int8_t* linestatus,
                            double* quantity, double* extendedprice, double* discount, double* tax);
+
+/* partitioned 3-way join (BASELINE.json configs[3]): o_custkey of the same orders rows tgpu_synth_orders_keys makes (uniform over the two
+ * thirds of the customers that have orders, custkey % 3 != 0); dense key sequences (c_custkey, dimension surrogate keys) */
+int tgpu_synth_orders_custkeys(tgpu_ctx* ctx, int64_t n_total, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t n_customers,
+                               uint64_t cust_seed, int64_t* out_device);
+int tgpu_synth_sequence(tgpu_ctx* ctx, int64_t first_value, int64_t count, int64_t* out_device);
+/* star join (BASELINE.json configs[4]): rows [first, first + n) of a TPC-DS store_sales-shaped fact table: ss_sold_date_sk over a
+ * 1 823-day window, ss_item_sk 1..300 000, ss_customer_sk 1..12 M and ss_store_sk 1..1 002 with 4.5 % NULLs each (Arrow validity
+ * bitmaps, (n + 7) / 8 bytes), ss_net_paid FLOAT64.  *rows_with_both_keys = rows whose two nullable keys are both present. */
+int tgpu_synth_store_sales(tgpu_ctx* ctx, int64_t n, int64_t first, uint64_t seed, int64_t* date_sk, int64_t* item_sk, int64_t* customer_sk,
+                           uint8_t* customer_valid, int64_t* store_sk, uint8_t* store_valid, double* net_paid, int64_t* rows_with_both_keys);
 
 /* bench / test hygiene: wrapping 64-bit sum of a fixed-width device column (raw bits for FLOAT64; value % mod when mod > 0; NULL rows
  * skipped).  bench.py's N > 1 pass checks the partitioned join with it: sum(build payload) == sum(probe key % 2557), key sum and row

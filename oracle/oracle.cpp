@@ -1307,6 +1307,44 @@ void orc_synth_lineitem_q1(int64_t n, int64_t first, uint64_t seed, int32_t* shi
     }
 }
 
+// o_custkey of order index i (same formula as the device generator, synth.cu)
+static inline int64_t order_custkey(int64_t i, int64_t n_customers, uint64_t seed)
+{
+    uint64_t with_orders = (uint64_t)(n_customers - n_customers / 3);
+    uint64_t j = orc_splitmix64(seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1))) % with_orders;
+    return (int64_t)((j / 2) * 3 + (j % 2) + 1);
+}
+
+void orc_synth_orders_custkeys(int64_t n_total, int64_t first, int64_t count, uint64_t seed, int32_t shuffle, int64_t n_customers, uint64_t cust_seed, int64_t* out)
+{
+    for (int64_t j = 0; j < count; j++) {
+        int64_t i = shuffle ? (int64_t)feistel_perm((uint64_t)(first + j), (uint64_t)n_total, seed) : first + j;
+        out[j] = order_custkey(i, n_customers, cust_seed);
+    }
+}
+
+int64_t orc_synth_store_sales(int64_t n, int64_t first, uint64_t seed, int64_t* date_sk, int64_t* item_sk, int64_t* customer_sk, uint8_t* customer_valid,
+                              int64_t* store_sk, uint8_t* store_valid, double* net_paid)
+{
+    int64_t both = 0;
+    memset(customer_valid, 0, (size_t)((n + 7) / 8));
+    memset(store_valid, 0, (size_t)((n + 7) / 8));
+    for (int64_t j = 0; j < n; j++) {
+        uint64_t x = orc_splitmix64(seed ^ (uint64_t)(first + j));
+        uint64_t y = orc_splitmix64(x);
+        bool cn = ((x >> 40) % 1000) < 45, sn = ((y >> 48) % 1000) < 45;
+        date_sk[j] = 2450816 + (int64_t)(x % 1823);
+        item_sk[j] = 1 + (int64_t)((x >> 16) % 300000);
+        customer_sk[j] = cn ? 0 : 1 + (int64_t)(y % 12000000);
+        store_sk[j] = sn ? 0 : 1 + (int64_t)((y >> 32) % 1002);
+        net_paid[j] = (double)((x >> 8) % 2000000) / 100.0;
+        if (!cn) customer_valid[j >> 3] |= (uint8_t)(1u << (j & 7));
+        if (!sn) store_valid[j >> 3] |= (uint8_t)(1u << (j & 7));
+        both += (!cn && !sn) ? 1 : 0;
+    }
+    return both;
+}
+
 int32_t orc_hardware_threads(void)
 {
     unsigned n = std::thread::hardware_concurrency();

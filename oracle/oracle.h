@@ -153,6 +153,11 @@ void orc_synth_lineitem_keys(int64_t n_orders, int64_t first, int64_t count, uin
 void orc_synth_lineitem_q1(int64_t n, int64_t first, uint64_t seed, int32_t* shipdate, int8_t* returnflag, int8_t* linestatus,
                            double* quantity, double* extendedprice, double* discount, double* tax);
 
+void orc_synth_orders_custkeys(int64_t n_total, int64_t first, int64_t count, uint64_t seed, int32_t shuffle, int64_t n_customers, uint64_t cust_seed, int64_t* out);
+/* returns the number of rows whose two nullable keys are both present */
+int64_t orc_synth_store_sales(int64_t n, int64_t first, uint64_t seed, int64_t* date_sk, int64_t* item_sk, int64_t* customer_sk, uint8_t* customer_valid,
+                              int64_t* store_sk, uint8_t* store_valid, double* net_paid);
+
 int32_t orc_hardware_threads(void);
 
 #ifdef __cplusplus

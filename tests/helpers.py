@@ -222,3 +222,37 @@ def hash_aggregation_operator_case(number_of_rows=40_000):
     aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 3, -1), (abi.AGG_AVG, 3, -1), (abi.AGG_COUNT, 0, -1), (abi.AGG_COUNT, 4, -1)]
     expected = [(i, 3, 3 * i, float(i), 3, 3) for i in range(number_of_rows)]
     return pages, [1], aggs, expected
+
+
+def _oracle_inner_probe(build_keys, build_payload, probe_keys, probe_valid):
+    """INNER join of probe rows (NULL keys never match, JoinProbe.java:154-171) against unique build keys through the oracle:
+    (selected probe rows, their build payload)"""
+    import oracle_lib as o
+    j = o.Join(Page(Block.bigint(build_keys)), [0])
+    pos = j.positions(Page(Block.bigint(probe_keys, None if probe_valid is None else ~probe_valid)), [0])
+    j.close()
+    sel = np.nonzero(pos >= 0)[0]
+    return sel, build_payload[pos[sel]]
+
+
+def oracle_star_rows(n, first, seed=0xD501):
+    """store_sales rows [first, first + n) through the star join of bench_workloads.py as a chain of oracle joins:
+    rows (ss_customer_sk, ss_net_paid, d_year, i_brand_id, s_val, c_birth_year) in fact order, and the generator's count of rows with
+    both nullable keys present"""
+    import oracle_lib as o
+    date0 = 2415022
+    cols, both = o.synth_store_sales(n, first, seed)
+    cv = np.unpackbits(cols["customer_valid"], bitorder="little")[:n].astype(bool)
+    sv = np.unpackbits(cols["store_valid"], bitorder="little")[:n].astype(bool)
+    date_k, item_k, store_k, cust_k = np.arange(date0, date0 + 73049), np.arange(1, 300001), np.arange(1, 1003), np.arange(1, 12_000_001)
+    idx = np.arange(n)
+    sel, d_year = _oracle_inner_probe(date_k, 1900 + (date_k - date0) // 365, cols["date_sk"], None)
+    idx = idx[sel]
+    sel, i_brand = _oracle_inner_probe(item_k, item_k % 1000 + 1, cols["item_sk"][idx], None)
+    idx, d_year = idx[sel], d_year[sel]
+    sel, s_val = _oracle_inner_probe(store_k, store_k * 7 % 100, cols["store_sk"][idx], sv[idx])
+    idx, d_year, i_brand = idx[sel], d_year[sel], i_brand[sel]
+    sel, c_birth = _oracle_inner_probe(cust_k, 1920 + cust_k % 70, cols["customer_sk"][idx], cv[idx])
+    idx, d_year, i_brand, s_val = idx[sel], d_year[sel], i_brand[sel], s_val[sel]
+    rows = list(zip(cols["customer_sk"][idx].tolist(), cols["net_paid"][idx].tolist(), d_year.tolist(), i_brand.tolist(), s_val.tolist(), c_birth.tolist()))
+    return rows, both

@@ -75,6 +75,8 @@ def load():
         "orc_synth_lineitem_rows": (C.c_int64, [C.c_int64]),
         "orc_synth_lineitem_keys": (None, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, VP]),
         "orc_synth_lineitem_q1": (None, [C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP]),
+        "orc_synth_orders_custkeys": (None, [C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int32, C.c_int64, C.c_uint64, VP]),
+        "orc_synth_store_sales": (C.c_int64, [C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP]),
         "orc_hardware_threads": (C.c_int32, []),
         "orc_pjoin_build": (VP, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP]),
         "orc_pjoin_destroy": (None, [VP]),
@@ -262,6 +264,22 @@ def synth_lineitem_q1(n, first, seed):
     load().orc_synth_lineitem_q1(n, first, seed, *[_p(cols[k]) for k in
                                                    ("shipdate", "returnflag", "linestatus", "quantity", "extendedprice", "discount", "tax")])
     return cols
+
+
+def synth_orders_custkeys(n_total, first, count, seed, shuffle, n_customers, cust_seed):
+    out = np.empty(count, dtype=np.int64)
+    load().orc_synth_orders_custkeys(n_total, first, count, seed, int(shuffle), n_customers, cust_seed, _p(out))
+    return out
+
+
+def synth_store_sales(n, first, seed):
+    """dict of columns (+ Arrow validity bitmaps of the two nullable keys) and the count of rows with both keys present"""
+    cols = dict(date_sk=np.empty(n, np.int64), item_sk=np.empty(n, np.int64), customer_sk=np.empty(n, np.int64),
+                customer_valid=np.empty((n + 7) // 8, np.uint8), store_sk=np.empty(n, np.int64), store_valid=np.empty((n + 7) // 8, np.uint8),
+                net_paid=np.empty(n, np.float64))
+    both = load().orc_synth_store_sales(n, first, seed, *[_p(cols[k]) for k in
+                                                          ("date_sk", "item_sk", "customer_sk", "customer_valid", "store_sk", "store_valid", "net_paid")])
+    return cols, both
 
 
 def q1_run(cols, cutoff, threads):

@@ -38,3 +38,12 @@ def test_two_rank_exchange_and_partitioned_join_match_oracle():
     r = _torchrun("tests/dist_exchange_check.py", 2)
     assert r.returncode == 0, r.stdout[-4000:]
     assert "dist_exchange_check ok" in r.stdout
+
+
+def test_two_rank_workloads_match_oracle():
+    # configs[3] / configs[4] / multi-GPU Q1 pipelines and the broadcast exchange on 2 ranks
+    if _gpus() < 2:
+        pytest.skip("needs two GPUs")
+    r = _torchrun("tests/dist_workloads_check.py", 2)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert "dist_workloads_check ok" in r.stdout

@@ -192,6 +192,7 @@ SIGNATURES = {
     "tgpu_comm_arena_open": (C.c_int, [VP, VP]),
     "tgpu_exchange_partitioned": (C.c_int, [VP, VP, PP, C.POINTER(PP)]),
     "tgpu_exchange_partitioned_fenced": (C.c_int, [VP, VP, PP, VP, C.POINTER(PP)]),
+    "tgpu_exchange_broadcast": (C.c_int, [VP, PP, C.POINTER(PP)]),
     "tgpu_exchange_begin": (C.c_int, [VP, VP, PP, C.POINTER(VP)]),
     "tgpu_exchange_end": (C.c_int, [VP, VP, C.POINTER(PP)]),
     "tgpu_op_needs_input": (C.c_int, [VP, C.POINTER(C.c_int)]),
@@ -217,6 +218,9 @@ SIGNATURES = {
     "tgpu_synth_lineitem_keys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, VP]),
     "tgpu_synth_lineitem_q1": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP]),
     "tgpu_column_sum": (C.c_int, [VP, VP, C.c_int64, VP]),
+    "tgpu_synth_orders_custkeys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64, C.c_uint64, VP]),
+    "tgpu_synth_sequence": (C.c_int, [VP, C.c_int64, C.c_int64, VP]),
+    "tgpu_synth_store_sales": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP, VP]),
 }
 
 _lib = None

@@ -117,6 +117,7 @@ extern "C" void tgpu_ctx_destroy(tgpu_ctx* ctx)
 
 extern "C" int tgpu_ctx_synchronize(tgpu_ctx* ctx)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TGPU_OK;
 }
@@ -150,12 +151,14 @@ extern "C" int tgpu_malloc(tgpu_ctx* ctx, size_t bytes, void** out)
 
 extern "C" int tgpu_free(tgpu_ctx* ctx, void* ptr)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     if (ptr) TG_CUDA(ctx, cudaFreeAsync(ptr, ctx->stream));
     return TGPU_OK;
 }
 
 extern "C" int tgpu_memcpy_h2d(tgpu_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     TG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TGPU_OK;
@@ -163,6 +166,7 @@ extern "C" int tgpu_memcpy_h2d(tgpu_ctx* ctx, void* dst, const void* src, size_t
 
 extern "C" int tgpu_memcpy_d2h(tgpu_ctx* ctx, void* dst, const void* src, size_t bytes)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     TG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TGPU_OK;
@@ -190,6 +194,7 @@ __global__ void tg_flush_l2_kernel(int4* buf, int64_t n, int v)
 
 extern "C" int tgpu_flush_l2(tgpu_ctx* ctx)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     // 256 MiB > 126 MB L2
     if (!ctx->flush_buf) {
         ctx->flush_bytes = (size_t)256 << 20;
@@ -204,12 +209,14 @@ extern "C" int tgpu_flush_l2(tgpu_ctx* ctx)
 
 extern "C" int tgpu_timer_start(tgpu_ctx* ctx)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     TG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     return TGPU_OK;
 }
 
 extern "C" int tgpu_timer_stop_ms(tgpu_ctx* ctx, float* ms)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     TG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     TG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     TG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
@@ -760,6 +767,7 @@ extern "C" int64_t tgpu_page_utf8_bytes(tgpu_ctx* ctx, const tgpu_page* device_p
 
 extern "C" int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* dp, tgpu_page* host)
 {
+    if (ctx) cudaSetDevice(ctx->device);     // callable from any thread: the calling thread's current device may differ
     if (!dp || !host) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "null page");
     if (host->num_columns != dp->num_columns) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "column count mismatch");
     int64_t n = dp->num_rows;

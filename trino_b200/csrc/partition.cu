@@ -460,6 +460,18 @@ int tg_comm_destroy_internal(tgpu_ctx* ctx)
     if (ctx->comm && g_nccl.comm_destroy) g_nccl.comm_destroy(ctx->comm);
     ctx->comm = ctx->comm2 = nullptr;
     if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
+    // receive arenas: unmap the peers', free this rank's (the caller synchronises the ranks before tearing a communicator down)
+    for (int k = 0; k < TGPU_NUM_ARENAS; k++) {
+        for (size_t r = 0; r < ctx->arena_peer[k].size(); r++)
+            if ((int)r != ctx->rank && ctx->arena_peer[k][r]) cudaIpcCloseMemHandle(ctx->arena_peer[k][r]);
+        ctx->arena_peer[k].clear();
+        if (ctx->arena_local[k]) { cudaFree(ctx->arena_local[k]); ctx->arena_local[k] = nullptr; }
+    }
+    ctx->arena_bytes = 0;
+    ctx->arena_epoch = 0;
+    ctx->exchanges_in_flight = 0;
+    ctx->rank = 0;
+    ctx->world = 1;
     return TGPU_OK;
 }
 
@@ -802,6 +814,114 @@ extern "C" int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitio
         }
     }
     TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // send buffers are released after the transfers have left them
+    OwnedPage* o = tg_make_owned_page(std::move(outp));
+    *out = &o->hdr;
+    return TGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// broadcast exchange: FIXED_BROADCAST_DISTRIBUTION (M/sql/planner/SystemPartitioningHandle.java:51) - the build side of a REPLICATED
+// join: BroadcastOutputBuffer hands every page to every consumer (M/execution/buffer/BroadcastOutputBuffer.java), so every rank ends up
+// with all rows.  Here: one all-gather of the row counts, then ncclSend/ncclRecv of every column (NULL bytes for nullable ones).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void validity_to_bytes_kernel(const uint8_t* __restrict__ validity, int64_t n, uint8_t* __restrict__ is_null)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) is_null[i] = tg_valid(validity, i) ? 0 : 1;
+}
+}  // namespace
+
+extern "C" int tgpu_exchange_broadcast(tgpu_ctx* ctx, const tgpu_page* page, tgpu_page** out)
+{
+    if (!ctx || !page || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = ctx->comm ? ctx->world : 1;     // no communicator: a single-GPU plan, the "broadcast" is a copy
+    DevPage in;
+    TG_TRY(tg_ingest_page(ctx, page, &in));
+    const int C = (int)in.cols.size();
+    for (auto& c : in.cols)
+        if (c.elem_size() == 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
+    const int64_t n = in.rows;
+    // count matrix: rows and one "has NULLs" flag per column from every rank
+    const int V = 1 + C;
+    std::vector<long long> mine(V, 0), matrix((size_t)W * V);
+    mine[0] = n;
+    for (int c = 0; c < C; c++) mine[1 + c] = in.cols[c].validity ? 1 : 0;
+    DevBuf d_mine, d_matrix;
+    TG_TRY(d_mine.alloc(ctx, (size_t)V * 8));
+    TG_TRY(d_matrix.alloc(ctx, (size_t)W * V * 8));
+    if (W > 1) {
+        TG_CUDA(ctx, cudaMemcpyAsync(d_mine.p, mine.data(), (size_t)V * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TG_NCCL(ctx, g_nccl.all_gather(d_mine.p, d_matrix.p, (size_t)V, NCCL_INT64, ctx->comm, ctx->stream));
+        TG_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)W * V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    else matrix = mine;
+    const int my_rank = W > 1 ? ctx->rank : 0;
+    std::vector<long long> off(W + 1, 0);
+    for (int r = 0; r < W; r++) off[r + 1] = off[r] + matrix[(size_t)r * V];
+    const long long total = off[W];
+    if (total > (long long)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "broadcast output exceeds 2^31-1 rows");
+    struct Lane { int es; const void* src; std::shared_ptr<DevBuf> recv; DevBuf staged; int col; bool nulls; };
+    std::vector<Lane> lanes;
+    for (int c = 0; c < C; c++) {
+        lanes.push_back(Lane{in.cols[c].elem_size(), in.cols[c].data, nullptr, DevBuf(), c, false});
+        bool any = false;
+        for (int r = 0; r < W; r++) any = any || matrix[(size_t)r * V + 1 + c] != 0;
+        if (any) lanes.push_back(Lane{1, nullptr, nullptr, DevBuf(), c, true});
+    }
+    for (auto& lane : lanes) {
+        lane.recv = std::make_shared<DevBuf>();
+        TG_TRY(lane.recv->alloc(ctx, (size_t)std::max<long long>(total, 1) * lane.es));
+        if (lane.nulls) {
+            // this rank's NULL bytes (all zero when its own page has no validity buffer)
+            TG_TRY(lane.staged.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
+            if (in.cols[lane.col].validity && n > 0)
+                TG_LAUNCH(ctx, validity_to_bytes_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, in.cols[lane.col].validity, n, lane.staged.as<uint8_t>());
+            else TG_CUDA(ctx, cudaMemsetAsync(lane.staged.p, 0, (size_t)std::max<int64_t>(n, 1), ctx->stream));
+            lane.src = lane.staged.p;
+        }
+        if (n > 0)
+            TG_CUDA(ctx, cudaMemcpyAsync((char*)lane.recv->p + (size_t)off[my_rank] * lane.es, lane.src, (size_t)n * lane.es, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (W > 1) TG_NCCL(ctx, g_nccl.group_start());
+    for (auto& lane : lanes)
+        for (int r = 0; r < W && W > 1; r++) {
+            if (r == my_rank) continue;
+            if (n > 0) TG_NCCL(ctx, g_nccl.send(lane.src, (size_t)n * lane.es, NCCL_INT8, r, ctx->comm, ctx->stream));
+            long long cnt = matrix[(size_t)r * V];
+            if (cnt > 0) TG_NCCL(ctx, g_nccl.recv((char*)lane.recv->p + (size_t)off[r] * lane.es, (size_t)cnt * lane.es, NCCL_INT8, r, ctx->comm, ctx->stream));
+        }
+    if (W > 1) TG_NCCL(ctx, g_nccl.group_end());
+    DevPage outp;
+    outp.rows = total;
+    outp.cols.resize(C);
+    for (auto& lane : lanes) {
+        DevColumn& dst = outp.cols[lane.col];
+        if (!lane.nulls) {
+            dst.type = in.cols[lane.col].type;
+            dst.length = total;
+            dst.own_data = lane.recv;
+            dst.data = lane.recv->p;
+        }
+        else if (total > 0) {
+            tgpu_column bm;
+            memset(&bm, 0, sizeof(bm));
+            bm.type = TGPU_INT8;
+            bm.flags = TGPU_COL_NULLS_BYTEMAP;
+            bm.length = total;
+            bm.data = lane.recv->p;
+            bm.validity = lane.recv->as<uint8_t>();
+            DevColumn packed;
+            TG_TRY(tg_ingest_column(ctx, &bm, true, &packed));
+            dst.own_validity = packed.own_validity;
+            dst.validity = packed.validity;
+        }
+    }
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // staged NULL bytes and the borrowed input are the caller's again
     OwnedPage* o = tg_make_owned_page(std::move(outp));
     *out = &o->hdr;
     return TGPU_OK;
