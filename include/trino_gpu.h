@@ -222,7 +222,10 @@ typedef struct tgpu_agg_fn {
  *   count/count(*) : INT64 count
  *   sum            : value (INT64 or FLOAT64), NULL when no input rows (NullableDoubleState / NullableLongState)
  *   avg            : INT64 count, FLOAT64 sum (LongAndDoubleState)
- *   min/max        : value, NULL when no input rows                                            */
+ *   min/max        : value, NULL when no input rows
+ * Variable-width (TGPU_UTF8) group-by keys are supported: each such key column owns a device string dictionary
+ * (csrc/strdict.cuh, the AppendOnlyVariableWidthData analogue of M/operator/FlatHash.java:309-348); identity is exact
+ * (full-byte comparison, colliding strings rehash), output key columns are UTF8 again.                                 */
 typedef struct tgpu_agg_spec {
     int32_t num_keys;
     const int32_t* key_channels;  /* groupByChannels */
@@ -235,6 +238,16 @@ typedef struct tgpu_agg_spec {
        aggregates, so projected columns never reach HBM (ScanFilterAndProject -> HashAggregation chain of Q1).
        When set, key_channels / input_channel refer to the program's projection outputs.        */
     const tgpu_expr_program* pre;
+    /* global grouping sets (GROUPING SETS / ROLLUP / CUBE with an empty set): when no row reaches a SINGLE / FINAL step the operator
+       emits one default row per listed id - the $group_id key holds the id, the other keys are NULL, count is 0 and every other
+       aggregate NULL (HashAggregationOperator.getGlobalAggregationOutput, M/operator/HashAggregationOperator.java:466-470,537-567).
+       group_id_key indexes key_channels (groupIdChannel); input_channel_types (tgpu_type per aggregation-input channel - the
+       operator's source types at LocalExecutionPlanner.java:4086-4089) shapes those rows, as no page was ever seen.  All optional. */
+    int32_t num_global_group_ids;
+    const int32_t* global_group_ids;      /* globalAggregationGroupIds */
+    int32_t group_id_key;
+    int32_t num_input_channels;
+    const int32_t* input_channel_types;
 } tgpu_agg_spec;
 
 int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op** out);

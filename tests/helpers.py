@@ -256,3 +256,56 @@ def oracle_star_rows(n, first, seed=0xD501):
     idx, d_year, i_brand, s_val = idx[sel], d_year[sel], i_brand[sel], s_val[sel]
     rows = list(zip(cols["customer_sk"][idx].tolist(), cols["net_paid"][idx].tolist(), d_year.tolist(), i_brand.tolist(), s_val.tolist(), c_birth.tolist()))
     return rows, both
+
+
+# ---- constructing 64-bit hash collisions (to drive the full-key-compare-and-rehash paths that replace the round-1 "abort on collision")
+_M = (1 << 64) - 1
+_P1, _P2 = 0x9E3779B185EBCA87, 0xC2B2AE3D27D4EB4F
+
+
+def _rotl(x, r):
+    return ((x << r) | (x >> (64 - r))) & _M
+
+
+def _rotr(x, r):
+    return ((x >> r) | (x << (64 - r))) & _M
+
+
+def _hash_long(v):
+    return (_rotl((v * _P2) & _M, 31) * _P1) & _M
+
+
+def _unhash_long(h):
+    v = (_rotr((h * pow(_P1, -1, 1 << 64)) & _M, 31) * pow(_P2, -1, 1 << 64)) & _M
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def colliding_bigint_pairs(a1, b1, a2):
+    """b2 such that the reference row hash 31 * H(a) + H(b) (InterpretedHashGenerator.java:102-110) of (a2, b2) equals that of (a1, b1)"""
+    target = (31 * _hash_long(a1 & _M) + _hash_long(b1 & _M) - 31 * _hash_long(a2 & _M)) & _M
+    return _unhash_long(target)
+
+
+def _fmix(x):
+    x ^= x >> 33; x = (x * 0xff51afd7ed558ccd) & _M; x ^= x >> 33; x = (x * 0xc4ceb9fe1a85ec53) & _M; x ^= x >> 33
+    return x
+
+
+def _unfmix(x):
+    x ^= x >> 33; x = (x * pow(0xc4ceb9fe1a85ec53, -1, 1 << 64)) & _M; x ^= x >> 33; x = (x * pow(0xff51afd7ed558ccd, -1, 1 << 64)) & _M; x ^= x >> 33
+    return x
+
+
+def colliding_groupby_pairs(a1, b1, a2):
+    """b2 such that the composite-key fingerprint of the general group-by path (csrc/groupby.cu pack_key, two non-NULL BIGINT keys,
+    attempt 0) of (a2, b2) equals that of (a1, b1)"""
+    seed = 0x9E3779B97F4A7C15
+
+    def step(h, u):
+        return (_fmix(h ^ (u & _M)) * 31) & _M
+
+    target = step(step(seed, a1), b1)
+    h1 = step(seed, a2)
+    x = (target * pow(31, -1, 1 << 64)) & _M
+    b2 = _unfmix(x) ^ h1
+    return b2 - (1 << 64) if b2 >= (1 << 63) else b2

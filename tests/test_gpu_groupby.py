@@ -71,9 +71,6 @@ def test_group_ids_packed_multi_column_and_other_types(ctx):
     g = ops.GroupByHash(ctx, [0], 10)
     assert list(g.get_group_ids(Page(k))) == [0, 1, 0, 2, 1]
     g.close()
-    with pytest.raises(abi.TrinoGpuError) as e:
-        ops.GroupByHash(ctx, [0], 10).get_group_ids(Page(Block.varchar(["a"])))
-    assert e.value.code == abi.ERR_NOT_SUPPORTED     # variable-width keys: pass dictionary codes
 
 
 def test_group_ids_wide_composite_keys_use_fingerprints(ctx):
@@ -275,3 +272,146 @@ def test_q1_fused_is_run_to_run_deterministic(ctx):
     a = q1_gpu_rows(ctx, cols, CUTOFF)
     b = q1_gpu_rows(ctx, cols, CUTOFF)
     assert a == b
+
+
+# ---------------------------------------------------------------- variable-width keys (FlatHash territory: M/operator/FlatHash.java:309-348)
+def _words(rng, n, vocab):
+    return [vocab[i] for i in rng.integers(0, len(vocab), n)]
+
+
+def test_group_ids_varchar_keys_match_oracle(ctx):
+    rng = np.random.default_rng(41)
+    short = ["", "A", "N", "R", "ab", "abc", "1234567"]                        # <= 7 bytes: keyed by their bytes
+    long_ = ["12345678", "a much longer string than seven bytes", "x" * 40, "x" * 41, "naïve café", "日本語のキー"]   # hashed + compared
+    vocab = short + long_ + [f"key-{i:06d}" for i in range(3000)]
+    g = ops.GroupByHash(ctx, [0], 100)
+    og = o.GroupByHash(0, 100)
+    for n in (1, 5000, 70000, 3):
+        vals = _words(rng, n, vocab)
+        nulls = rng.random(n) < 0.03
+        page = Page(Block.varchar([None if z else v for v, z in zip(vals, nulls)]))
+        assert (g.get_group_ids(page) == og.get_group_ids(page, [0])).all()
+        assert g.get_group_count() == og.group_count()
+    g.close(); og.close()
+    # TestGroupByHash shapes over VARCHAR: dictionary and run-length encoded inputs give the ids of the flat block (:111-160)
+    g = ops.GroupByHash(ctx, [0], 100)
+    assert list(g.get_group_ids(Page(DictionaryBlock(Block.varchar(["x", "yy"]), [0, 0, 1, 1, 0])))) == [0, 0, 1, 1, 0]
+    assert list(g.get_group_ids(Page(RunLengthEncodedBlock(Block.varchar(["yy"]), 3)))) == [1, 1, 1]
+    assert list(g.get_group_ids(Page(Block.varchar(["zzz", "x", None, "yy"])))) == [2, 0, 3, 1]
+    g.close()
+
+
+def test_group_ids_mixed_varchar_and_fixed_keys(ctx):
+    rng = np.random.default_rng(43)
+    g = ops.GroupByHash(ctx, [0, 1, 2], 1000)
+    og = o.GroupByHash(0, 1000)
+    for n in (20000, 1, 60000):
+        page = Page(Block.varchar(_words(rng, n, ["A", "N", "R"])), Block.varchar(_words(rng, n, ["F", "O", "a-long-line-status"])),
+                    Block.integer(rng.integers(0, 40, n), rng.random(n) < 0.02))
+        assert (g.get_group_ids(page) == og.get_group_ids(page, [0, 1, 2])).all()
+        assert g.get_group_count() == og.group_count()
+    g.close(); og.close()
+
+
+@pytest.mark.parametrize("step_pages", [1, 3])
+def test_aggregation_with_varchar_keys_matches_oracle(ctx, step_pages):
+    rng = np.random.default_rng(47)
+    vocab = ["", "A", "N", "R", "a much longer string than seven bytes", "12345678"] + [f"k{i}" for i in range(500)]
+    pages = []
+    for _ in range(step_pages):
+        n = 30000
+        keys = _words(rng, n, vocab)
+        nulls = rng.random(n) < 0.02
+        pages.append(Page(Block.varchar([None if z else v for v, z in zip(keys, nulls)]), Block.double(rng.normal(size=n), rng.random(n) < 0.05),
+                          Block.bigint(rng.integers(-50, 50, n))))
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_SUM, 2, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_COUNT, 0, -1)]
+    got = _gpu_agg(ctx, pages, [0], aggs)
+    want = _oracle_agg(pages, [0], aggs)
+    assert rows_equal(got, want, rel=1e-6)
+    assert [r[0] for r in got] == [r[0] for r in want]                          # key strings come back, in first-seen order
+    # PARTIAL -> FINAL over the string keys of the intermediate pages
+    partial = _gpu_agg(ctx, pages, [0], aggs[:3], step=abi.STEP_PARTIAL)
+    ppage = Page(Block.varchar([r[0] for r in partial]), Block.bigint([r[1] for r in partial]), Block.double([r[2] for r in partial]), Block.bigint([r[3] for r in partial]))
+    final = _gpu_agg(ctx, [ppage], [0], [(abi.AGG_COUNT_STAR, 1, -1), (abi.AGG_SUM, 2, -1), (abi.AGG_SUM, 3, -1)], step=abi.STEP_FINAL)
+    assert rows_equal(final, [r[:4] for r in want], rel=1e-6)
+
+
+def test_q1_with_varchar_keys_matches_oracle(ctx):
+    # the reference's Q1 groups by VARCHAR(1) l_returnflag / l_linestatus: same rows as with INT8 codes
+    cols = o.synth_lineitem_q1(300_000, 0, 0x7C01)
+    _, want = o.q1_run(cols, CUTOFF, 1)
+    flags = [chr(c) for c in cols["returnflag"]]
+    status = [chr(c) for c in cols["linestatus"]]
+    page = Page(Block.integer(cols["shipdate"]), Block.varchar(flags), Block.varchar(status), Block.double(cols["quantity"]), Block.double(cols["extendedprice"]),
+                Block.double(cols["discount"]), Block.double(cols["tax"]))
+    from q1 import q1_factory
+    for fused in (True, False):
+        if fused:
+            op = q1_factory(ctx, True).create_operator()
+            out = ops.drive(op, [page])
+            op.close()
+        else:
+            from q1 import q1_program
+            fp = ops.FilterAndProjectOperatorFactory(ctx, q1_program()).create_operator()
+            agg = q1_factory(ctx, False).create_operator()
+            fp.add_input(page)
+            o1 = fp.get_output_device()
+            agg.add_input(o1)
+            o1.release()
+            agg.finish()
+            out = [agg.get_output()]
+            fp.close(); agg.close()
+        rows = [r for p in out for r in p.rows()]
+        assert len(rows) == len(want)
+        for g_, w in zip(rows, want):
+            assert (g_[0].decode(), g_[1].decode()) == (w[0], w[1]) and g_[9] == w[9], (g_, w)
+            for a, b in zip(g_[2:9], w[2:9]):
+                assert abs(a - b) <= 1e-6 * abs(b)
+
+
+def test_global_aggregation_default_rows(ctx):
+    # HashAggregationOperator.getGlobalAggregationOutput :537-567 (TestHashAggregationOperator.testHashAggregationWithGlobals :191-230):
+    # no input, global grouping sets {42, 49}: one row per set, $group_id = id, other keys NULL, count 0, everything else NULL
+    A_ = ops.Aggregator
+    types = [abi.UTF8, abi.INT64, abi.FLOAT64, abi.INT64]
+    f = ops.HashAggregationOperatorFactory(ctx, [0, 1], abi.STEP_SINGLE, [A_(abi.AGG_COUNT_STAR), A_(abi.AGG_SUM, 2), A_(abi.AGG_AVG, 3), A_(abi.AGG_MAX, 3), A_(abi.AGG_COUNT, 2)],
+                                           expected_groups=100, global_aggregation_group_ids=[42, 49], group_id_channel=1, input_types=types)
+    op = f.create_operator()
+    out = ops.drive(op, [])
+    op.close()
+    assert [r for p in out for r in p.rows()] == [(None, 42, 0, None, None, None, 0), (None, 49, 0, None, None, None, 0)]
+    # with input the default rows do not appear; a PARTIAL step never makes them
+    op = f.create_operator()
+    out = ops.drive(op, [Page(Block.varchar(["x"]), Block.bigint([7]), Block.double([1.5]), Block.bigint([3]))])
+    op.close()
+    assert [r for p in out for r in p.rows()] == [(b"x", 7, 1, 1.5, 3.0, 3, 1)]
+    pf = ops.HashAggregationOperatorFactory(ctx, [0, 1], abi.STEP_PARTIAL, [A_(abi.AGG_COUNT_STAR)], global_aggregation_group_ids=[42], group_id_channel=1, input_types=types)
+    op = pf.create_operator()
+    assert ops.drive(op, []) == []
+    op.close()
+
+
+def test_group_keys_sharing_a_64_bit_fingerprint_are_kept_apart(ctx):
+    # wide composite keys are addressed by a 64-bit fingerprint; two tuples that share it used to fail the query, now the later one
+    # rehashes (full-key comparison on every hit, like FlatHash.valueIdentical, M/operator/FlatHash.java:445-469)
+    from helpers import colliding_groupby_pairs
+    t1 = (2**40 + 1, 2**41 + 5)
+    t2 = (2**42 + 9, colliding_groupby_pairs(t1[0], t1[1], 2**42 + 9))
+    t3 = (2**43 + 3, colliding_groupby_pairs(t1[0], t1[1], 2**43 + 3))
+    rng = np.random.default_rng(9)
+    g = ops.GroupByHash(ctx, [0, 1], 100)
+    og = o.GroupByHash(0, 100)
+    for tuples in ([t2, t1, t2, t1, t3], [t3, t3, t1], [t1]):
+        a = np.concatenate([[t[0] for t in tuples], rng.integers(2**50, 2**50 + 300, 4000)]).astype(np.int64)
+        b = np.concatenate([[t[1] for t in tuples], rng.integers(2**51, 2**51 + 300, 4000)]).astype(np.int64)
+        page = Page(Block.bigint(a), Block.bigint(b))
+        assert (g.get_group_ids(page) == og.get_group_ids(page, [0, 1])).all()
+        assert g.get_group_count() == og.group_count()
+    g.close(); og.close()
+    # and through the operator (sums per colliding tuple stay separate)
+    a = np.array([t1[0], t2[0], t1[0], t3[0], t2[0]], dtype=np.int64)
+    b = np.array([t1[1], t2[1], t1[1], t3[1], t2[1]], dtype=np.int64)
+    pages = [Page(Block.bigint(a), Block.bigint(b), Block.bigint([1, 10, 100, 1000, 10000]))]
+    aggs = [(abi.AGG_SUM, 2, -1), (abi.AGG_COUNT_STAR, -1, -1)]
+    got = _gpu_agg(ctx, pages, [0, 1], aggs)
+    assert got == _oracle_agg(pages, [0, 1], aggs) == [(t1[0], t1[1], 101, 2), (t2[0], t2[1], 10010, 2), (t3[0], t3[1], 1000, 1)]

@@ -379,3 +379,26 @@ def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
     # the operator (fused probe + payload gather, whole tiles + ragged tail) emits the oracle's rows
     got = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
     assert got == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
+
+
+def test_join_keys_sharing_a_64_bit_row_hash_are_kept_apart(ctx):
+    # round 1 answered NOT_SUPPORTED when two different key tuples shared one row hash; now the build moves one of them to its next hash
+    # function and the probe follows (DefaultPagesHash compares the values on every hash hit: M/operator/join/DefaultPagesHash.java:246-260)
+    from helpers import colliding_bigint_pairs
+    rng = np.random.default_rng(5)
+    t1 = (11, 22)
+    t2 = (33, colliding_bigint_pairs(11, 22, 33))
+    t3 = (44, colliding_bigint_pairs(11, 22, 44))            # same hash again, never built
+    base_a, base_b = rng.integers(0, 1000, 5000), rng.integers(0, 1000, 5000)
+    ba = np.concatenate([[t1[0], t2[0], t1[0]], base_a]).astype(np.int64)
+    bb = np.concatenate([[t1[1], t2[1], t1[1]], base_b]).astype(np.int64)
+    build = Page(Block.bigint(ba), Block.bigint(bb), Block.bigint(np.arange(len(ba))))
+    pa = np.concatenate([[t2[0], t3[0], t1[0], t2[0]], rng.integers(0, 1000, 20000)]).astype(np.int64)
+    pb = np.concatenate([[t2[1], t3[1], t1[1], t2[1]], rng.integers(0, 1000, 20000)]).astype(np.int64)
+    probe = Page(Block.bigint(pa), Block.bigint(pb), Block.double(np.arange(len(pa)) * 0.5))
+    for jt in (abi.JOIN_INNER, abi.JOIN_PROBE_OUTER):
+        got = gpu_join_rows(ctx, [build], [probe], [0, 1], [0, 1], [0, 1, 2], [2], jt, False)
+        want = oracle_join_rows(build, probe, [0, 1], [0, 1], [0, 1, 2], [2], jt, False)
+        assert got == want
+    inner = [r for r in want if r[3] is not None][:5]
+    assert [r[3] for r in inner[:1]] == [1] and inner[1][3] in (0, 2)       # t2 finds its own row, t1 its own chain; t3 finds nothing

@@ -106,6 +106,11 @@ class AggSpec(C.Structure):
         ("expected_groups", C.c_int64),
         ("max_partial_bytes", C.c_int64),
         ("pre", C.POINTER(ExprProgram)),
+        ("num_global_group_ids", C.c_int32),
+        ("global_group_ids", C.POINTER(C.c_int32)),
+        ("group_id_key", C.c_int32),
+        ("num_input_channels", C.c_int32),
+        ("input_channel_types", C.POINTER(C.c_int32)),
     ]
 
 

@@ -32,6 +32,7 @@
 #include "expr.cuh"
 #include "jit.cuh"
 #include "multisplit.cuh"
+#include "strdict.cuh"
 
 namespace {
 
@@ -118,8 +119,10 @@ __device__ __forceinline__ unsigned long long canonical_key_bits(long long bits,
 }
 
 // canonical packed key of a row.  Returns the special-slot index (0 NULL key, 1 sentinel-valued key) or -1.
+// `attempt` (hashed composite keys only): which of the independent 64-bit hash functions of the key tuple to use - a tuple whose
+// attempt-0 hash is already owned by a different tuple lives under its attempt-1 hash, and so on (run_general_ids)
 __device__ __forceinline__ int pack_key(const AggPlan& plan, const DColumns& cols, int64_t row, const int64_t* temps, int tstride, uint32_t nullbits,
-                                        unsigned long long* out)
+                                        unsigned long long* out, int attempt = 0)
 {
     if (plan.num_keys == 1) {
         Fetched f = fetch_src(plan.srcs[plan.key_src[0]], cols, row, temps, tstride, nullbits);
@@ -134,7 +137,7 @@ __device__ __forceinline__ int pack_key(const AggPlan& plan, const DColumns& col
         return -1;
     }
     if (plan.key_hashed) {
-        unsigned long long h = 0x9E3779B97F4A7C15ULL;
+        unsigned long long h = 0x9E3779B97F4A7C15ULL + (unsigned long long)attempt * 0xD1B54A32D192ED03ULL;
         for (int k = 0; k < plan.num_keys; k++) {
             Fetched f = fetch_src(plan.srcs[plan.key_src[k]], cols, row, temps, tstride, nullbits);
             unsigned long long u = f.is_null ? 0ULL : canonical_key_bits(f.bits, plan.key_is_double[k]);
@@ -424,15 +427,18 @@ __global__ void g_table_init_kernel(int4* table, int64_t slots)
 
 // K1: find or provisionally insert the key of every row.  slot_of_row: slot index, or -2-special.
 // `budget` new slots may be claimed (reserve-then-claim keeps the load factor bounded); exceeding it sets *overflow.
-__global__ void __launch_bounds__(256) g_insert_kernel(AggPlan plan, DColumns cols, int64_t n, GSlot* __restrict__ table, unsigned long long mask,
+// `rows` / `attempt`: nullptr = rows [0, n) at attempt 0; else the rows that have to move on to their next hash function
+__global__ void __launch_bounds__(256) g_insert_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ rows, const unsigned char* __restrict__ attempt,
+                                                      GSlot* __restrict__ table, unsigned long long mask,
                                                       GSpecial* __restrict__ special, int* __restrict__ slot_of_row, int* __restrict__ tickets, int budget,
                                                       int* __restrict__ overflow)
 {
-    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; row < n; row += stride) {
+    for (; idx < n; idx += stride) {
+        const int64_t row = rows ? rows[idx] : idx;
         unsigned long long pk = 0;
-        int sp = pack_key(plan, cols, row, nullptr, 0, 0, &pk);
+        int sp = pack_key(plan, cols, row, nullptr, 0, 0, &pk, attempt ? attempt[row] : 0);
         if (sp >= 0) {
             if (special->gid[sp] < 0) atomicMin(&special->first_row[sp], (int)row);
             slot_of_row[row] = -2 - sp;
@@ -510,21 +516,44 @@ __global__ void g_gid_kernel(int64_t n, const GSlot* __restrict__ table, const G
     }
 }
 
-// hashed keys: every row must carry the key tuple stored for its group (first-seen values), else two different tuples
-// share one 64-bit fingerprint and the GPU path must not be used for this query
-__global__ void g_verify_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ gids, AggState st, int* __restrict__ mismatch)
+// hashed composite keys: a row's slot must hold ITS key tuple - the tuple stored for the slot's group (existing groups) or the tuple
+// of the slot's lowest row in this page (new slots).  A row whose tuple differs shares a 64-bit hash with another tuple: it moves
+// on to its next hash function (attempt + 1) and is inserted again - full-key comparison and chaining by rehash, like
+// FlatHash.valueIdentical on a control-byte hit (M/operator/FlatHash.java:445-469), never a query failure.
+__device__ __forceinline__ bool g_same_tuple(const AggPlan& plan, const DColumns& cols, int64_t row, int64_t other_row)
 {
-    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = 0; k < plan.num_keys; k++) {
+        Fetched a = fetch_src(plan.srcs[plan.key_src[k]], cols, row, nullptr, 0, 0), b = fetch_src(plan.srcs[plan.key_src[k]], cols, other_row, nullptr, 0, 0);
+        if (a.is_null != b.is_null) return false;
+        if (!a.is_null && canonical_key_bits(a.bits, plan.key_is_double[k]) != canonical_key_bits(b.bits, plan.key_is_double[k])) return false;
+    }
+    return true;
+}
+
+__global__ void g_verify_kernel(AggPlan plan, DColumns cols, int64_t n, const int* __restrict__ rows, const GSlot* __restrict__ table,
+                                const int* __restrict__ slot_of_row, AggState st, unsigned char* __restrict__ attempt, int* __restrict__ retry, int* __restrict__ retry_count)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; row < n; row += stride) {
-        int gid = gids[row];
-        for (int k = 0; k < plan.num_keys; k++) {
-            Fetched f = fetch_src(plan.srcs[plan.key_src[k]], cols, row, nullptr, 0, 0);
-            bool sn = st.keynull[(size_t)k * st.cap + gid] != 0;
-            bool same = f.is_null == sn;
-            if (same && !sn)
-                same = canonical_key_bits(f.bits, plan.key_is_double[k]) == canonical_key_bits(st.keyvals[(size_t)k * st.cap + gid], plan.key_is_double[k]);
-            if (!same) *mismatch = 1;
+    for (; idx < n; idx += stride) {
+        const int64_t row = rows ? rows[idx] : idx;
+        const int s = slot_of_row[row];
+        if (s < 0) continue;                       // special groups, or no slot (table growth pending)
+        const GSlot slot = table[s];
+        bool same = true;
+        if (slot.gid >= 0) {
+            for (int k = 0; k < plan.num_keys && same; k++) {
+                Fetched f = fetch_src(plan.srcs[plan.key_src[k]], cols, row, nullptr, 0, 0);
+                bool sn = st.keynull[(size_t)k * st.cap + slot.gid] != 0;
+                same = f.is_null == sn;
+                if (same && !sn)
+                    same = canonical_key_bits(f.bits, plan.key_is_double[k]) == canonical_key_bits(st.keyvals[(size_t)k * st.cap + slot.gid], plan.key_is_double[k]);
+            }
+        }
+        else if (slot.first_row != (int)row) same = g_same_tuple(plan, cols, row, slot.first_row);
+        if (!same) {
+            attempt[row] = (unsigned char)(attempt[row] + 1);
+            retry[atomicAdd(retry_count, 1)] = (int)row;
         }
     }
 }
@@ -1204,6 +1233,13 @@ struct AggOp : tgpu_op {
     tgpu_op* inner_fp = nullptr;                      // unfused FilterAndProject feeding the general path
     int32_t prog_max_channel = -1;
     bool gids_only = false;                  // tgpu_groupby_hash_* handle
+    // variable-width keys: one string dictionary per UTF8 key column; the group-by runs on the 30-bit ids (strdict.cuh)
+    std::vector<std::shared_ptr<StringDict>> key_dicts;
+    // global aggregation default rows (HashAggregationOperator.getGlobalAggregationOutput :537-567)
+    std::vector<int32_t> global_group_ids;
+    int32_t group_id_key = -1;               // index into key_channels of the $group_id key
+    std::vector<int32_t> input_types;        // tgpu_type of every aggregation-input channel (only needed to shape the default rows)
+    bool saw_group = false;                  // a group was ever created (across PARTIAL flushes)
 
     // resolved at the first page (needs column types)
     bool planned = false;
@@ -1300,6 +1336,40 @@ struct AggOp : tgpu_op {
         return at;
     }
 
+    // channel of an ingested page that feeds group-by key k (a pass-through projection when the pre-stage is fused)
+    int key_input_channel(int k) const
+    {
+        int ch = key_channels[k];
+        if (!has_pre) return ch;
+        if (ch < 0 || ch >= (int)projections.size() || projections[ch].kind != 0) return -1;
+        return projections[ch].index;
+    }
+
+    // UTF8 key columns of the page -> INT32 dictionary ids, in place (FlatHash keeps the bytes in AppendOnlyVariableWidthData; here
+    // the dictionary does, and the group-by proper sees fixed-width keys)
+    int encode_string_keys(DevPage* pg)
+    {
+        const int nk = (int)key_channels.size();
+        if ((int)key_dicts.size() < nk) key_dicts.resize(nk);
+        std::map<int, int> done;      // channel -> first key that encoded it
+        for (int k = 0; k < nk; k++) {
+            int ch = key_input_channel(k);
+            if (ch < 0 || ch >= (int)pg->cols.size()) continue;      // reported by make_plan
+            auto first = done.find(ch);
+            if (first != done.end()) { key_dicts[k] = key_dicts[first->second]; continue; }
+            const bool is_string = pg->cols[ch].type == TGPU_UTF8;
+            if (!is_string && !key_dicts[k]) continue;
+            if (!is_string) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d was variable-width in an earlier page and is type %d now", ch, pg->cols[ch].type);
+            if (planned && !key_dicts[k]) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d became variable-width after the first page", ch);
+            if (!key_dicts[k]) key_dicts[k] = std::make_shared<StringDict>(ctx);
+            DevColumn ids;
+            TG_TRY(key_dicts[k]->encode(pg->cols[ch], &ids));
+            pg->cols[ch] = std::move(ids);
+            done[ch] = k;
+        }
+        return TGPU_OK;
+    }
+
     int make_plan(const DevPage& in)
     {
         memset(&plan, 0, sizeof(plan));
@@ -1317,7 +1387,8 @@ struct AggOp : tgpu_op {
             if (s < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d out of range", key_channels[k]);
             if (plan.srcs[s].is_temp) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "group-by keys must be pass-through channels of the fused pre-stage");
             int bits = type == TGPU_INT64 || type == TGPU_FLOAT64 ? 64 : type == TGPU_INT32 ? 32 : type == TGPU_INT16 ? 16 : type == TGPU_INT8 ? 8 : 0;
-            if (!bits) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width group-by keys are not supported on the GPU path (pass dictionary codes)");
+            if (k < (int)key_dicts.size() && key_dicts[k] && type == TGPU_INT32) bits = 30;     // dictionary ids of a variable-width key (< SD_MAX_IDS)
+            if (!bits) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "variable-width group-by key reached the planner unencoded");
             plan.key_src[k] = s;
             plan.key_bits[k] = bits;
             plan.key_is_double[k] = type == TGPU_FLOAT64;
@@ -1623,16 +1694,42 @@ struct AggOp : tgpu_op {
         TG_TRY(rank.alloc(ctx, (size_t)(n + 1) * 4));
         int* d_tickets = (int*)(ctx->d_scratch + 8);
         int* d_overflow = d_tickets + 1;
+        int* d_retry_count = (int*)(ctx->d_scratch + 18);
         int grid = tg_grid(ctx, n, 256, 8);
+        DevBuf attempt, retry_a, retry_b;
+        if (plan.key_hashed) TG_TRY(attempt.alloc(ctx, (size_t)n));
         while (true) {
-            int64_t max_fill = g_slots * 3 / 4;
-            int64_t budget = max_fill - group_count;
-            TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 8, ctx->stream));
-            TG_LAUNCH(ctx, g_insert_kernel, grid, 256, 0, plan, cols, n, g_table.as<GSlot>(), (unsigned long long)g_slots - 1, g_special.as<GSpecial>(),
-                      slot_of_row.as<int>(), d_tickets, (int)std::min<int64_t>(budget, INT32_MAX), d_overflow);
-            int64_t word = 0;
-            TG_TRY(tg_read_i64(ctx, d_tickets, &word));
-            bool overflow = (word >> 32) != 0;
+            // hashed composite keys: rows settle under the first of their hash functions whose slot holds their own key tuple
+            if (plan.key_hashed) TG_CUDA(ctx, cudaMemsetAsync(attempt.p, 0, (size_t)n, ctx->stream));
+            const int* rows = nullptr;
+            int64_t todo = n;
+            bool overflow = false;
+            int64_t claimed = 0;
+            for (int round = 0; ; round++) {
+                if (round >= 8) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "group-by keys collide under 8 independent 64-bit hashes");
+                int64_t max_fill = g_slots * 3 / 4;
+                int64_t budget = max_fill - group_count - claimed;
+                TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 8, ctx->stream));
+                TG_LAUNCH(ctx, g_insert_kernel, tg_grid(ctx, todo, 256, 8), 256, 0, plan, cols, todo, rows, plan.key_hashed ? attempt.as<unsigned char>() : nullptr,
+                          g_table.as<GSlot>(), (unsigned long long)g_slots - 1, g_special.as<GSpecial>(),
+                          slot_of_row.as<int>(), d_tickets, (int)std::min<int64_t>(std::max<int64_t>(budget, 0), INT32_MAX), d_overflow);
+                int64_t word = 0;
+                TG_TRY(tg_read_i64(ctx, d_tickets, &word));
+                overflow = (word >> 32) != 0;
+                claimed += word & 0xFFFFFFFFLL;
+                if (overflow || !plan.key_hashed) break;
+                DevBuf& retry = (round & 1) ? retry_b : retry_a;
+                TG_TRY(retry.alloc(ctx, (size_t)todo * 4));
+                TG_CUDA(ctx, cudaMemsetAsync(d_retry_count, 0, 8, ctx->stream));
+                TG_LAUNCH(ctx, g_verify_kernel, tg_grid(ctx, todo, 256, 8), 256, 0, plan, cols, todo, rows, g_table.as<GSlot>(), slot_of_row.as<int>(), state(),
+                          attempt.as<unsigned char>(), retry.as<int>(), d_retry_count);
+                int64_t left = 0;
+                TG_TRY(tg_read_i64(ctx, d_retry_count, &left));
+                left &= 0xFFFFFFFFLL;
+                if (left == 0) break;
+                rows = retry.as<int>();
+                todo = left;
+            }
             if (!overflow) break;
             // BigintGroupByHash.tryRehash :239-290: double (here: x4) and retry the page
             int64_t slots = g_slots * 4;
@@ -1658,15 +1755,6 @@ struct AggOp : tgpu_op {
                       flags.as<unsigned char>(), rank.as<int>(), (int)group_count, state());
         TG_LAUNCH(ctx, g_gid_kernel, grid, 256, 0, n, g_table.as<GSlot>(), g_special.as<GSpecial>(), slot_of_row.as<int>(), d_gids);
         group_count += total_new;
-        if (plan.key_hashed) {
-            int* d_mismatch = (int*)(ctx->d_scratch + 18);
-            TG_CUDA(ctx, cudaMemsetAsync(d_mismatch, 0, 8, ctx->stream));
-            TG_LAUNCH(ctx, g_verify_kernel, grid, 256, 0, plan, cols, n, d_gids, state(), d_mismatch);
-            int64_t bad = 0;
-            TG_TRY(tg_read_i64(ctx, d_mismatch, &bad));
-            if (bad & 0xFFFFFFFFLL)
-                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "two different group-by keys share one 64-bit fingerprint: keep the Java operator for this query");
-        }
         return TGPU_OK;
     }
 
@@ -1957,6 +2045,7 @@ struct AggOp : tgpu_op {
         if (use_general && inner_fp) return add_via_filter_project(page);
         DevPage in;
         TG_TRY(tg_ingest_page(ctx, page, &in));
+        TG_TRY(encode_string_keys(&in));
         if (!planned) {
             TG_TRY(make_plan(in));
             TG_TRY(init_state());
@@ -1993,6 +2082,7 @@ struct AggOp : tgpu_op {
             TG_TRY(inner_fp->get_output(&o));
             if (!o) break;
             std::unique_ptr<OwnedPage> guard(o);
+            TG_TRY(encode_string_keys(&o->page));       // (has_pre is false by now: the keys are the projection's output channels)
             DColumns cols;
             TG_TRY(fill_cols(o->page, &cols));
             TG_TRY(run_general(o->page, cols));
@@ -2012,6 +2102,8 @@ struct AggOp : tgpu_op {
         int64_t A = plan.num_accs > 0 ? plan.num_accs : 1;
         int64_t b = group_count * (8 + 8 * A + 9 * (int64_t)plan.num_keys);
         if (use_general) b += (int64_t)g_table.bytes + (int64_t)f_recs.bytes;
+        for (auto& d : key_dicts)
+            if (d) b += d->memory_bytes();
         return planned ? b : 0;
     }
 
@@ -2040,6 +2132,12 @@ struct AggOp : tgpu_op {
             TG_TRY(nm->alloc(ctx, (size_t)G));
             TG_LAUNCH(ctx, agg_key_output_kernel, grid, 256, 0, st_keyvals.as<long long>() + (size_t)k * st_cap, st_keynull.as<unsigned char>() + (size_t)k * st_cap,
                       G, c.elem_size(), c.own_data->p, nm->as<unsigned char>());
+            if (k < (int)key_dicts.size() && key_dicts[k]) {
+                // the key column holds dictionary ids: give the strings back (FlatHash.appendTo reads them from its variable-width data)
+                DevColumn text;
+                TG_TRY(key_dicts[k]->decode((const int32_t*)c.own_data->p, nm->as<unsigned char>(), G, &text));
+                c = std::move(text);
+            }
             nullmaps.push_back(nm);
             outp.cols.push_back(std::move(c));
         }
@@ -2135,12 +2233,89 @@ struct AggOp : tgpu_op {
         return TGPU_OK;
     }
 
+    // HashAggregationOperator.getGlobalAggregationOutput :537-567: no input row reached the operator and the plan has global grouping
+    // sets - one row per set: the $group_id key holds the set's id, the other keys are NULL, every aggregate evaluates over nothing
+    // (count -> 0, everything else -> NULL)
+    int build_default_output(OwnedPage** out)
+    {
+        *out = nullptr;
+        const int64_t G = (int64_t)global_group_ids.size();
+        if (G == 0) return TGPU_OK;
+        auto type_of = [&](int ch) -> int { return ch >= 0 && ch < (int)input_types.size() ? input_types[ch] : 0; };
+        DevPage outp;
+        outp.rows = G;
+        auto all_null = std::make_shared<DevBuf>();
+        TG_TRY(all_null->alloc(ctx, (size_t)((G + 7) / 8)));
+        TG_CUDA(ctx, cudaMemsetAsync(all_null->p, 0, (size_t)((G + 7) / 8), ctx->stream));
+        auto null_column = [&](int type, DevColumn* c) -> int {
+            if (!type) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "global aggregation default rows need tgpu_agg_spec.input_channel_types");
+            c->type = type;
+            c->length = G;
+            c->own_data = std::make_shared<DevBuf>();
+            size_t bytes = (size_t)G * (type == TGPU_UTF8 ? 1 : 8);
+            TG_TRY(c->own_data->alloc(ctx, bytes));
+            TG_CUDA(ctx, cudaMemsetAsync(c->own_data->p, 0, bytes, ctx->stream));
+            c->data = c->own_data->p;
+            if (type == TGPU_UTF8) {
+                c->own_offsets = std::make_shared<DevBuf>();
+                TG_TRY(c->own_offsets->alloc(ctx, (size_t)(G + 1) * 4));
+                TG_CUDA(ctx, cudaMemsetAsync(c->own_offsets->p, 0, (size_t)(G + 1) * 4, ctx->stream));
+                c->offsets = c->own_offsets->as<int32_t>();
+            }
+            c->own_validity = all_null;
+            c->validity = all_null->as<uint8_t>();
+            return TGPU_OK;
+        };
+        for (int k = 0; k < (int)key_channels.size(); k++) {
+            DevColumn c;
+            if (k == group_id_key) {
+                std::vector<long long> ids(global_group_ids.begin(), global_group_ids.end());
+                c.type = TGPU_INT64;
+                c.length = G;
+                c.own_data = std::make_shared<DevBuf>();
+                TG_TRY(c.own_data->alloc(ctx, (size_t)G * 8));
+                TG_CUDA(ctx, cudaMemcpyAsync(c.own_data->p, ids.data(), (size_t)G * 8, cudaMemcpyHostToDevice, ctx->stream));
+                TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                c.data = c.own_data->p;
+            }
+            else {
+                int ch = key_channels[k];
+                int type = has_pre ? (ch >= 0 && ch < (int)projections.size() && projections[ch].kind == 0 ? type_of(projections[ch].index) : 0) : type_of(ch);
+                TG_TRY(null_column(type, &c));
+            }
+            outp.cols.push_back(std::move(c));
+        }
+        const bool from_state = step == TGPU_STEP_FINAL || step == TGPU_STEP_INTERMEDIATE;
+        for (auto& f : fns) {
+            DevColumn c;
+            if (f.function == TGPU_AGG_COUNT_STAR || f.function == TGPU_AGG_COUNT) {
+                TG_TRY(null_column(TGPU_INT64, &c));
+                c.own_validity.reset();
+                c.validity = nullptr;                   // count over nothing is 0, not NULL
+            }
+            else if (f.function == TGPU_AGG_AVG) TG_TRY(null_column(TGPU_FLOAT64, &c));
+            else {
+                int ch = f.input_channel;
+                int type = has_pre ? (ch >= 0 && ch < (int)projections.size() ? (projections[ch].kind == 0 ? type_of(projections[ch].index)
+                                      : projections[ch].vtype == TGPU_V_DOUBLE ? TGPU_FLOAT64 : TGPU_INT64) : 0) : type_of(ch);
+                (void)from_state;                        // FINAL: the state column of sum / min / max has the value's type
+                if (type == TGPU_INT32 || type == TGPU_INT16 || type == TGPU_INT8) type = TGPU_INT64;   // sum / min / max of narrow integers come out as BIGINT here
+                TG_TRY(null_column(type, &c));
+            }
+            outp.cols.push_back(std::move(c));
+        }
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *out = tg_make_owned_page(std::move(outp));
+        return TGPU_OK;
+    }
+
     int get_output(OwnedPage** out) override
     {
         *out = nullptr;
         if (next_out < pending.size()) { *out = pending[next_out++]; return TGPU_OK; }
         if (flushing) {
             TG_TRY(build_output(out));
+            if (*out) saw_group = true;
             TG_TRY(reset_state());
             flushing = false;
             return TGPU_OK;
@@ -2148,6 +2323,10 @@ struct AggOp : tgpu_op {
         if (finishing && !finished) {
             TG_TRY(build_output(out));
             finished = true;
+            const bool output_partial = step == TGPU_STEP_PARTIAL || step == TGPU_STEP_INTERMEDIATE;
+            // (a group exists iff a row reached the aggregation: with a fused filter that is "a row passed the filter", which is what the
+            //  reference's totalInputRowsProcessed counts behind its separate FilterAndProjectOperator)
+            if (!*out && !saw_group && !output_partial && !global_group_ids.empty()) TG_TRY(build_default_output(out));
         }
         return TGPU_OK;
     }
@@ -2166,6 +2345,14 @@ int build_agg_op(tgpu_ctx* ctx, const tgpu_agg_spec* spec, AggOp** out)
     op->step = spec->step;
     op->expected_groups = spec->expected_groups;
     op->max_partial_bytes = spec->max_partial_bytes;
+    if (spec->num_global_group_ids > 0) {
+        if (!spec->global_group_ids || spec->group_id_key < 0 || spec->group_id_key >= spec->num_keys)
+            return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "global grouping sets need global_group_ids and a valid group_id_key");
+        op->global_group_ids.assign(spec->global_group_ids, spec->global_group_ids + spec->num_global_group_ids);
+        op->group_id_key = spec->group_id_key;
+    }
+    if (spec->num_input_channels > 0 && spec->input_channel_types)
+        op->input_types.assign(spec->input_channel_types, spec->input_channel_types + spec->num_input_channels);
     if (spec->pre) {
         if (spec->step == TGPU_STEP_FINAL || spec->step == TGPU_STEP_INTERMEDIATE)
             return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a fused pre-stage only makes sense on raw input");
@@ -2231,6 +2418,7 @@ extern "C" int tgpu_groupby_hash_get_group_ids(tgpu_op* op, const tgpu_page* pag
     if (page->num_rows == 0) return TGPU_OK;
     DevPage in;
     TG_TRY(tg_ingest_page(ctx, page, &in));
+    TG_TRY(a->encode_string_keys(&in));
     if (!a->planned) {
         TG_TRY(a->make_plan(in));
         TG_TRY(a->init_state());
@@ -2274,7 +2462,16 @@ extern "C" int tgpu_jit_selftest_agg(const tgpu_agg_spec* spec, const int32_t* c
     in.rows = 0;
     in.cols.resize(num_channels);
     int elems[TGPU_MAX_CHANNELS] = {0};
-    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) { in.cols[c].type = channel_types[c]; elems[c] = in.cols[c].elem_size(); }
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) in.cols[c].type = channel_types[c];
+    op->key_dicts.resize(op->key_channels.size());
+    for (size_t k = 0; k < op->key_channels.size(); k++) {
+        int ch = op->key_input_channel((int)k);
+        if (ch >= 0 && ch < num_channels && in.cols[ch].type == TGPU_UTF8) {     // variable-width key: the kernel sees its INT32 dictionary ids
+            op->key_dicts[k] = std::make_shared<StringDict>(&fake);
+            in.cols[ch].type = TGPU_INT32;
+        }
+    }
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) elems[c] = in.cols[c].elem_size();
     int st = op->make_plan(in);
     if (st != TGPU_OK) return st;
     AccMap map;

@@ -48,15 +48,16 @@ TG_HD int32_t process_raw_hash(uint64_t raw, int32_t count)
     return (int32_t)(((uint64_t)x * (uint64_t)(uint32_t)count) >> 32);
 }
 
-// XXH64 (io.airlift.slice.XxHash64, public algorithm) of a byte range, seed 0; unaligned-safe
-TG_HD uint64_t xxh64_bytes(const uint8_t* p, int64_t len)
+// XXH64 (io.airlift.slice.XxHash64, public algorithm) of a byte range; unaligned-safe.  The reference always hashes with seed 0; other
+// seeds give the independent hash functions the string dictionary rehashes colliding strings with (strdict.cuh)
+TG_HD uint64_t xxh64_bytes(const uint8_t* p, int64_t len, uint64_t seed = 0)
 {
     const uint8_t* end = p + len;
     uint64_t h;
     auto rd64 = [](const uint8_t* q) { uint64_t v = 0; for (int i = 7; i >= 0; i--) v = (v << 8) | q[i]; return v; };
     auto rd32 = [](const uint8_t* q) { uint32_t v = 0; for (int i = 3; i >= 0; i--) v = (v << 8) | q[i]; return v; };
     if (len >= 32) {
-        uint64_t v1 = XXP1 + XXP2, v2 = XXP2, v3 = 0, v4 = 0 - XXP1;
+        uint64_t v1 = seed + XXP1 + XXP2, v2 = seed + XXP2, v3 = seed, v4 = seed - XXP1;
         const uint8_t* limit = end - 32;
         do {
             v1 = rotl64(v1 + rd64(p) * XXP2, 31) * XXP1;
@@ -72,7 +73,7 @@ TG_HD uint64_t xxh64_bytes(const uint8_t* p, int64_t len)
         h ^= rotl64(v4 * XXP2, 31) * XXP1; h = h * XXP1 + XXP4;
     }
     else {
-        h = XXP5;
+        h = seed + XXP5;
     }
     h += (uint64_t)len;
     while (p + 8 <= end) { h ^= rotl64(rd64(p) * XXP2, 31) * XXP1; h = rotl64(h, 27) * XXP1 + XXP4; p += 8; }

@@ -374,36 +374,57 @@ __global__ void join_match_flags_kernel(const int* __restrict__ jp, int64_t n, u
 // columns: at build time every row must carry the same key as the head of its slot (a 64-bit collision between
 // different keys makes the build answer NOT_SUPPORTED so the caller keeps the Java operator), and at probe time a hit
 // is kept only when the probe row's key equals the build row's key.
-__global__ void join_fingerprint_kernel(KeyCols k, int64_t n, long long* __restrict__ fp, uint8_t* __restrict__ is_null)
+__global__ void join_fingerprint_kernel(KeyCols k, int64_t n, const uint8_t* __restrict__ attempt, long long* __restrict__ fp, uint8_t* __restrict__ is_null)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         bool ok = tg::row_joinable(k, i);
-        fp[i] = ok ? (long long)tg::row_hash(k, i) : 0;
+        fp[i] = ok ? (long long)tg::row_hash_attempt(k, i, attempt ? attempt[i] : 0) : 0;
         is_null[i] = ok ? 0 : 1;
     }
 }
 
+// build: a row whose key differs from the key of its slot's head row shares the slot's 64-bit hash with another key: it moves on to
+// its next hash function (attempt + 1); the table is then rebuilt.  Rows of one key always agree with their head, so chains stay pure.
 __global__ void join_verify_build_kernel(KeyCols k, const long long* __restrict__ fp, const uint8_t* __restrict__ fp_validity, int64_t n,
-                                         const JoinSlot* __restrict__ table, JoinGeom geo, int special_head, int* __restrict__ collision)
+                                         const JoinSlot* __restrict__ table, JoinGeom geo, int special_head, uint8_t* __restrict__ attempt, int* __restrict__ moved)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         if (!tg_valid(fp_validity, i)) continue;
         int head = join_lookup(table, geo, (unsigned long long)fp[i], special_head);
-        if (head != (int)i && head >= 0 && !tg::rows_equal_for_join(k, i, k, head)) *collision = 1;
+        if (head != (int)i && head >= 0 && !tg::rows_equal_for_join(k, i, k, head)) {
+            attempt[i] = (uint8_t)(attempt[i] + 1);
+            atomicAdd(moved, 1);
+        }
     }
 }
 
-__global__ void join_verify_probe_kernel(KeyCols probe, KeyCols build, int64_t n, int* __restrict__ jp)
+// probe, attempt 0: a hit whose key differs is a miss when the build needed one hash function only, else it stays open (-2) for the
+// next attempt
+__global__ void join_verify_probe_kernel(KeyCols probe, KeyCols build, int64_t n, int more_attempts, int* __restrict__ jp)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         int b = jp[i];
-        if (b >= 0 && !tg::rows_equal_for_join(probe, i, build, b)) jp[i] = -1;
+        if (b >= 0 && !tg::rows_equal_for_join(probe, i, build, b)) jp[i] = more_attempts ? -2 : -1;
+    }
+}
+
+// probe, attempt a >= 1 of the rows still open: look the a-th hash up; an empty slot or the last attempt closes the row as a miss
+__global__ void join_probe_retry_kernel(KeyCols probe, KeyCols build, int64_t n, const JoinSlot* __restrict__ table, JoinGeom geo, int special_head, int attempt, int last,
+                                        int* __restrict__ jp)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        if (jp[i] != -2) continue;
+        int head = join_lookup(table, geo, (unsigned long long)tg::row_hash_attempt(probe, i, attempt), special_head);
+        if (head >= 0 && tg::rows_equal_for_join(probe, i, build, head)) jp[i] = head;
+        else if (head < 0 || last) jp[i] = -1;
     }
 }
 
@@ -659,6 +680,7 @@ struct tgpu_lookup {
     int32_t num_output = 0;
     std::vector<DevBuf> by_slot;        // build output columns in table-slot order (fused probe fast path)
     bool generic = false;               // keyed by row hash + verification against build_keys
+    int attempts = 1;                   // generic only: hash functions the build needed (> 1 iff two keys shared a 64-bit hash)
     std::vector<DevColumn> build_keys;  // generic only: the real key columns of the build side
     // OuterPositionTracker (M/operator/join/OuterLookupSource.java:168-196): one byte per build position, set by the
     // LOOKUP_OUTER / FULL_OUTER probes for every build row they emit, read by the LookupOuterOperator
@@ -671,7 +693,7 @@ namespace {
 
 
 // row-hash column (+ validity: NULL / NaN keys can never match) of a set of key columns
-int make_fingerprint(tgpu_ctx* ctx, const std::vector<const DevColumn*>& keys, int64_t n, DevColumn* out)
+int make_fingerprint(tgpu_ctx* ctx, const std::vector<const DevColumn*>& keys, int64_t n, DevColumn* out, const uint8_t* d_attempt = nullptr)
 {
     KeyCols k;
     memset(&k, 0, sizeof(k));
@@ -687,7 +709,7 @@ int make_fingerprint(tgpu_ctx* ctx, const std::vector<const DevColumn*>& keys, i
     DevBuf is_null;
     TG_TRY(is_null.alloc(ctx, (size_t)std::max<int64_t>(n, 1)));
     if (n > 0) {
-        TG_LAUNCH(ctx, join_fingerprint_kernel, tg_grid(ctx, n, 256, 8), 256, 0, k, n, fp.own_data->as<long long>(), is_null.as<uint8_t>());
+        TG_LAUNCH(ctx, join_fingerprint_kernel, tg_grid(ctx, n, 256, 8), 256, 0, k, n, d_attempt, fp.own_data->as<long long>(), is_null.as<uint8_t>());
         tgpu_column bm;
         memset(&bm, 0, sizeof(bm));
         bm.type = TGPU_INT8;
@@ -764,7 +786,11 @@ int lookup_positions_generic(tgpu_ctx* ctx, const tgpu_lookup* lk, const std::ve
     memset(&pk, 0, sizeof(pk));
     pk.count = (int32_t)keys.size();
     for (size_t c = 0; c < keys.size(); c++) tg::key_cols_set(&pk, (int)c, *keys[c]);
-    TG_LAUNCH(ctx, join_verify_probe_kernel, tg_grid(ctx, n, 256, 8), 256, 0, pk, key_cols_of(lk->build_keys), n, d_out);
+    const KeyCols bk = key_cols_of(lk->build_keys);
+    TG_LAUNCH(ctx, join_verify_probe_kernel, tg_grid(ctx, n, 256, 8), 256, 0, pk, bk, n, lk->attempts > 1 ? 1 : 0, d_out);
+    for (int a = 1; a < lk->attempts; a++)
+        TG_LAUNCH(ctx, join_probe_retry_kernel, tg_grid(ctx, n, 256, 8), 256, 0, pk, bk, n, lk->table.as<JoinSlot>(), lk->geo, lk->special_head, a,
+                  a == lk->attempts - 1 ? 1 : 0, d_out);
     return TGPU_OK;
 }
 
@@ -925,68 +951,101 @@ struct JoinBuildOp : tgpu_op {
         else lk->store.cols.push_back(all.cols[0]);
         for (size_t c = nk; c < all.cols.size(); c++) lk->store.cols.push_back(all.cols[c]);
         lk->key_type = lk->store.cols[0].type;
-        // sizing: IncrementalLoadFactorHashArraySizeSupplier.getHashArraySize :40-47 (capacity is not observable)
-        double lf = rows <= (1 << 16) ? 0.25 : rows <= (1 << 20) ? 0.5 : 0.75;
-        int64_t need = (int64_t)((double)rows / lf) + 1;
-        int64_t cap = 8;   // at least one 8-slot line
-        while (cap < need) cap <<= 1;
-        // line layouts (modes 1 / 2) want lines at most about half full (measured: exp_join_summary in profiles/)
-        const char* env_mode = getenv("TGPU_JOIN_HASH");
-        const DevColumn& bkey = lk->store.cols[0];
-        const bool int_key = !lk->generic && key_kind_of(bkey.type) == KEY_INT;
-        int hash_mode = env_mode ? atoi(env_mode) : (int_key && rows > 0 ? 2 : 1);
-        if (hash_mode == 2 && !(int_key && rows > 0)) hash_mode = 1;
-        const char* env_shift = getenv("TGPU_JOIN_CAP_SHIFT");
-        int cap_shift = env_shift ? atoi(env_shift) : (hash_mode ? 1 : 0);
-        cap <<= cap_shift;
-        if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
-        lk->geo.mask = (unsigned long long)cap - 1;
-        lk->geo.kmin = 0;
-        lk->geo.shift = 0;
-        if (hash_mode == 2) {
-            // order-preserving lines: the key range [kmin, kmax] is cut into cap / 8 lines of 2^shift key values
-            long long* d_range = (long long*)(ctx->d_scratch + 24);
-            long long init_range[2] = {INT64_MAX, INT64_MIN};
-            TG_CUDA(ctx, cudaMemcpyAsync(d_range, init_range, sizeof(init_range), cudaMemcpyHostToDevice, ctx->stream));
-            TG_LAUNCH(ctx, join_key_range_kernel, tg_grid(ctx, rows, 1024, 8), 256, 0, tg_colref(bkey), rows, d_range);
-            long long h_range[2];
-            TG_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
-            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (h_range[0] > h_range[1]) hash_mode = 1;      // no insertable key at all
-            else {
-                const unsigned long long span = (unsigned long long)h_range[1] - (unsigned long long)h_range[0];   // kmax - kmin, exact in 64 bits
-                const unsigned long long lines = (unsigned long long)cap >> 3;
-                int shift = 0;
-                while (shift < 63 && (span >> shift) >= lines) shift++;
-                if ((span >> shift) >= lines) hash_mode = 1;  // a span of 2^63 or more over very few lines: not worth a special case
-                lk->geo.kmin = (unsigned long long)h_range[0];
-                lk->geo.shift = shift;
+        int64_t cap = 0;
+        auto build_table = [&]() -> int {
+            // sizing: IncrementalLoadFactorHashArraySizeSupplier.getHashArraySize :40-47 (capacity is not observable)
+            double lf = rows <= (1 << 16) ? 0.25 : rows <= (1 << 20) ? 0.5 : 0.75;
+            int64_t need = (int64_t)((double)rows / lf) + 1;
+            cap = 8;   // at least one 8-slot line
+            while (cap < need) cap <<= 1;
+            // line layouts (modes 1 / 2) want lines at most about half full (measured: exp_join_summary in profiles/)
+            const char* env_mode = getenv("TGPU_JOIN_HASH");
+            const DevColumn& bkey = lk->store.cols[0];
+            const bool int_key = !lk->generic && key_kind_of(bkey.type) == KEY_INT;
+            int hash_mode = env_mode ? atoi(env_mode) : (int_key && rows > 0 ? 2 : 1);
+            if (hash_mode == 2 && !(int_key && rows > 0)) hash_mode = 1;
+            const char* env_shift = getenv("TGPU_JOIN_CAP_SHIFT");
+            int cap_shift = env_shift ? atoi(env_shift) : (hash_mode ? 1 : 0);
+            cap <<= cap_shift;
+            if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
+            lk->geo.mask = (unsigned long long)cap - 1;
+            lk->geo.kmin = 0;
+            lk->geo.shift = 0;
+            if (hash_mode == 2) {
+                // order-preserving lines: the key range [kmin, kmax] is cut into cap / 8 lines of 2^shift key values
+                long long* d_range = (long long*)(ctx->d_scratch + 24);
+                long long init_range[2] = {INT64_MAX, INT64_MIN};
+                TG_CUDA(ctx, cudaMemcpyAsync(d_range, init_range, sizeof(init_range), cudaMemcpyHostToDevice, ctx->stream));
+                TG_LAUNCH(ctx, join_key_range_kernel, tg_grid(ctx, rows, 1024, 8), 256, 0, tg_colref(bkey), rows, d_range);
+                long long h_range[2];
+                TG_CUDA(ctx, cudaMemcpyAsync(h_range, d_range, sizeof(h_range), cudaMemcpyDeviceToHost, ctx->stream));
+                TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (h_range[0] > h_range[1]) hash_mode = 1;      // no insertable key at all
+                else {
+                    const unsigned long long span = (unsigned long long)h_range[1] - (unsigned long long)h_range[0];   // kmax - kmin, exact in 64 bits
+                    const unsigned long long lines = (unsigned long long)cap >> 3;
+                    int shift = 0;
+                    while (shift < 63 && (span >> shift) >= lines) shift++;
+                    if ((span >> shift) >= lines) hash_mode = 1;  // a span of 2^63 or more over very few lines: not worth a special case
+                    lk->geo.kmin = (unsigned long long)h_range[0];
+                    lk->geo.shift = shift;
+                }
+            }
+            TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
+            int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag, [2] rows off their home line, [3] rows more than 8 lines off
+            while (true) {
+                lk->geo.mode = hash_mode;
+                TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
+                int init[4] = {-1, 0, 0, 0};
+                TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+                if (rows > 0) {
+                    TG_LAUNCH(ctx, join_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(bkey), key_kind_of(bkey.type), rows,
+                              lk->table.as<JoinSlot>(), lk->geo, d_flags, d_flags + 1, (unsigned int*)(d_flags + 2));
+                }
+                if (hash_mode != 2) break;
+                // mode 2 relies on the keys spreading evenly over their range; clustered domains pile up in a few lines.  More than
+                // 1/8 of the rows off their home line, or any row further than 8 lines away: rebuild with scattered lines (mode 1)
+                int64_t moved = 0;
+                TG_TRY(tg_read_i64(ctx, d_flags + 2, &moved));
+                const int64_t off_home = moved & 0xFFFFFFFFLL, far = (moved >> 32) & 0xFFFFFFFFLL;
+                if (off_home * 8 <= rows && far * 1024 <= rows) break;
+                hash_mode = 1;
+            }
+            int64_t packed = 0;
+            TG_TRY(tg_read_i64(ctx, d_flags, &packed));
+            lk->special_head = (int)(packed & 0xFFFFFFFFLL);
+            lk->has_dups = (packed >> 32) != 0;
+            return TGPU_OK;
+        };
+        if (!lk->generic) TG_TRY(build_table());
+        else {
+            // the fingerprint table: every row must sit in a slot whose head row carries ITS key.  Rows that share a 64-bit hash with a
+            // different key move on to their next hash function and the table is rebuilt (never needed in practice; never a failure)
+            DevBuf attempt;
+            TG_TRY(attempt.alloc(ctx, (size_t)std::max<int64_t>(rows, 1)));
+            TG_CUDA(ctx, cudaMemsetAsync(attempt.p, 0, (size_t)std::max<int64_t>(rows, 1), ctx->stream));
+            for (int round = 0; ; round++) {
+                if (round >= 8) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "join keys collide under 8 independent 64-bit hashes");
+                if (round > 0) {
+                    std::vector<const DevColumn*> kp;
+                    for (auto& c : lk->build_keys) kp.push_back(&c);
+                    DevColumn fp;
+                    TG_TRY(make_fingerprint(ctx, kp, rows, &fp, attempt.as<uint8_t>()));
+                    lk->store.cols[0] = std::move(fp);
+                }
+                TG_TRY(build_table());
+                lk->attempts = round + 1;
+                if (rows == 0) break;
+                int* d_moved = (int*)(ctx->d_scratch + 16);
+                TG_CUDA(ctx, cudaMemsetAsync(d_moved, 0, 8, ctx->stream));
+                const DevColumn& fp = lk->store.cols[0];
+                TG_LAUNCH(ctx, join_verify_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, key_cols_of(lk->build_keys), (const long long*)fp.data, fp.validity, rows,
+                          lk->table.as<JoinSlot>(), lk->geo, lk->special_head, attempt.as<uint8_t>(), d_moved);
+                int64_t moved = 0;
+                TG_TRY(tg_read_i64(ctx, d_moved, &moved));
+                if ((moved & 0xFFFFFFFFLL) == 0) break;
             }
         }
-        TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
-        int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag, [2] rows off their home line, [3] rows more than 8 lines off
-        while (true) {
-            lk->geo.mode = hash_mode;
-            TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
-            int init[4] = {-1, 0, 0, 0};
-            TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-            if (rows > 0) {
-                TG_LAUNCH(ctx, join_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(bkey), key_kind_of(bkey.type), rows,
-                          lk->table.as<JoinSlot>(), lk->geo, d_flags, d_flags + 1, (unsigned int*)(d_flags + 2));
-            }
-            if (hash_mode != 2) break;
-            // mode 2 relies on the keys spreading evenly over their range; clustered domains pile up in a few lines.  More than
-            // 1/8 of the rows off their home line, or any row further than 8 lines away: rebuild with scattered lines (mode 1)
-            int64_t moved = 0;
-            TG_TRY(tg_read_i64(ctx, d_flags + 2, &moved));
-            const int64_t off_home = moved & 0xFFFFFFFFLL, far = (moved >> 32) & 0xFFFFFFFFLL;
-            if (off_home * 8 <= rows && far * 1024 <= rows) break;
-            hash_mode = 1;
-        }
-        int64_t packed = 0;
-        TG_TRY(tg_read_i64(ctx, d_flags, &packed));
-        lk->special_head = (int)(packed & 0xFFFFFFFFLL);
-        lk->has_dups = (packed >> 32) != 0;
         if (lk->has_dups) {
             // ArrayPositionLinks: chains in descending row order
             const DevColumn& key = lk->store.cols[0];
@@ -1002,17 +1061,6 @@ struct JoinBuildOp : tgpu_op {
             TG_TRY(lk->links.alloc(ctx, (size_t)rows * 4));
             TG_LAUNCH(ctx, join_links_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, keys_out.as<unsigned long long>(), rows, lk->links.as<int>());
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-        if (lk->generic && rows > 0) {
-            int* d_collision = (int*)(ctx->d_scratch + 16);
-            TG_CUDA(ctx, cudaMemsetAsync(d_collision, 0, 8, ctx->stream));
-            const DevColumn& fp = lk->store.cols[0];
-            TG_LAUNCH(ctx, join_verify_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, key_cols_of(lk->build_keys), (const long long*)fp.data, fp.validity, rows,
-                      lk->table.as<JoinSlot>(), lk->geo, lk->special_head, d_collision);
-            int64_t collided = 0;
-            TG_TRY(tg_read_i64(ctx, d_collision, &collided));
-            if (collided & 0xFFFFFFFFLL)
-                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "two different join keys share one 64-bit row hash: keep the Java operator for this build side");
         }
         // slot-ordered copy of the build output columns for the fused probe
         bool slot_payload = !getenv("TGPU_JOIN_PAYLOAD_BY_ROW") && rows > 0 && lk->num_output > 0 && lk->num_output <= 4;

@@ -13,7 +13,7 @@ using namespace tg;
 // ------------------------------------------------------------------------------------------------
 constexpr int XT = 256;          // threads per CTA
 constexpr int XMAXP = 64;        // partitions the fused exchange path handles (one per GPU)
-constexpr int XMAXC = 16;        // value columns + null-byte columns
+constexpr int XMAXC = 48;        // value columns + null-byte columns (lanes) of one multi-split
 constexpr int XCHG_ROW_NUMBER = 16;   // XchgCols.elem code of a lane without source: the scatter writes each row's input position (int32; CTA kernel only)
 
 // pass A: partition id per row (uint8) and a histogram per CTA chunk

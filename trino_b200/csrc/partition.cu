@@ -631,7 +631,7 @@ extern "C" int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitio
         t_last = now;
     };
     const int C = (int)in.cols.size();
-    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);
+    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);   // (every column may need a NULL-byte lane)
     // 1. partition ids + per-CTA histograms + offsets (stable multi-split, no sort)
     const XchgGeom geom = xchg_geom(ctx, n, W, W > 1);
     const int grid = geom.nchunks;
@@ -967,7 +967,7 @@ extern "C" int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tg
     for (auto& c : in.cols)
         if (c.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
     const int C = (int)in.cols.size();
-    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);
+    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);   // (every column may need a NULL-byte lane)
     // 1. partition ids, histograms, offsets.  Every destination of the scatter is LOCAL memory here (send buffers and this
     //    rank's own arena), so the warp-granular kernels apply.
     const XchgGeom geom = xchg_geom(ctx, n, W, false);

@@ -45,6 +45,31 @@ __device__ __forceinline__ uint64_t row_hash(const KeyCols& k, int64_t row)
     return h;
 }
 
+// The family of row hashes the fingerprint tables are keyed by.  attempt 0 is the reference's row hash; attempt a >= 1 is an independent
+// 64-bit hash of the same key values (strings are re-hashed from their bytes with seed a, fixed-width values are re-mixed), used only for
+// key tuples whose lower-attempt hash is already owned by a different tuple (join.cu: build / probe retries).  -0.0 hashes like +0.0.
+__device__ __forceinline__ uint64_t row_hash_attempt(const KeyCols& k, int64_t row, int attempt)
+{
+    if (attempt == 0) return row_hash(k, row);
+    uint64_t h = 0x9E3779B97F4A7C15ULL * (uint64_t)attempt;
+    for (int c = 0; c < k.count; c++) {
+        const ColRef& col = k.cols[c];
+        uint64_t t;
+        if (!tg_valid(col.validity, row)) t = 0x5851F42D4C957F2DULL;
+        else if (k.is_utf8[c]) {
+            int32_t a = k.offsets[c][row], b = k.offsets[c][row + 1];
+            t = xxh64_bytes((const uint8_t*)col.data + a, b - a, (uint64_t)attempt);
+        }
+        else {
+            uint64_t u = (uint64_t)tg_load_i64(col, row);
+            if (k.is_double[c] && (u << 1) == 0) u = 0;
+            t = murmur3_mix(u + 0xD1B54A32D192ED03ULL * (uint64_t)attempt);
+        }
+        h = murmur3_mix(h ^ t) * 31 + (uint64_t)(c + 1);
+    }
+    return h;
+}
+
 // true when the row can take part in an equi-join: no NULL key and no NaN key
 __device__ __forceinline__ bool row_joinable(const KeyCols& k, int64_t row)
 {

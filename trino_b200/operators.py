@@ -455,26 +455,35 @@ class HashAggregationOperator(Operator):
 
 
 class HashAggregationOperatorFactory(OperatorFactory):
-    def __init__(self, ctx, group_by_channels, step, aggregators, expected_groups=10_000, max_partial_memory=0, pre=None):
+    def __init__(self, ctx, group_by_channels, step, aggregators, expected_groups=10_000, max_partial_memory=0, pre=None,
+                 global_aggregation_group_ids=(), group_id_channel=None, input_types=None):
+        """global_aggregation_group_ids / group_id_channel (a group-by CHANNEL, like the reference's groupIdChannel) / input_types (tgpu_type
+        per input channel): the default rows of global grouping sets over empty input (HashAggregationOperator.java:537-567)"""
         super().__init__()
         self.ctx, self.group_by_channels, self.step, self.aggregators = ctx, list(group_by_channels), step, list(aggregators)
         self.expected_groups, self.max_partial_memory, self.pre = expected_groups, max_partial_memory, pre
+        self.global_ids, self.group_id_channel, self.input_types = list(global_aggregation_group_ids), group_id_channel, input_types
 
     def _create(self):
         keys = _i32(self.group_by_channels)
         fns = (abi.AggFn * max(1, len(self.aggregators)))()
         for i, a in enumerate(self.aggregators):
             fns[i].function, fns[i].input_channel, fns[i].mask_channel = a.function, a.input_channel, a.mask_channel
+        gids = _i32(self.global_ids)
+        types = _i32(list(self.input_types or []))
         spec = abi.AggSpec(len(self.group_by_channels), C.cast(keys, C.POINTER(C.c_int32)), self.step, len(self.aggregators),
                            C.cast(fns, C.POINTER(abi.AggFn)), self.expected_groups, self.max_partial_memory,
-                           C.pointer(self.pre.struct) if self.pre is not None else None)
+                           C.pointer(self.pre.struct) if self.pre is not None else None,
+                           len(self.global_ids), C.cast(gids, C.POINTER(C.c_int32)),
+                           self.group_by_channels.index(self.group_id_channel) if self.group_id_channel is not None else -1,
+                           len(self.input_types or []), C.cast(types, C.POINTER(C.c_int32)))
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.tgpu_agg_create(self.ctx.h, C.byref(spec), C.byref(h)))
         return HashAggregationOperator(self.ctx, h)
 
     def duplicate(self):
         return HashAggregationOperatorFactory(self.ctx, self.group_by_channels, self.step, self.aggregators, self.expected_groups,
-                                              self.max_partial_memory, self.pre)
+                                              self.max_partial_memory, self.pre, self.global_ids, self.group_id_channel, self.input_types)
 
 
 class GroupByHash:
