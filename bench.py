@@ -29,6 +29,8 @@ SEED_LINEITEM, SEED_ORDERS = 0x7C01, 0x7C02
 ALG_BYTES_PROBE_INDEX = 24          # 8 key + 12 table entry + 4 position
 ALG_BYTES_PROBE_FUSED = 40          # fused probe + gather, this workload: 24 + 8 build payload read + 8 written (probe columns pass through by reference)
 ALG_BYTES_Q1_CODES = 38             # shipdate 4 + 4 x FLOAT64 32 + 2 INT8 key codes
+ALG_BYTES_Q1_UTF8 = 46              # the reference's key types: 2 x VARCHAR(1) = 2 x (4 offset + 1 byte) instead of the 2 code bytes
+ALG_BYTES_GROUPBY_BIGINT = 36       # 8 key + 8 value + 20 table entry touched
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r01_kernels.md),
 # quoted only for the configuration they were captured on
 NCU_TRAFFIC_PROBE_FUSED_SF100 = 18.515783e9 + 7.239862e9     # 600 000 003 rows: 42.9 B/row
@@ -182,6 +184,8 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000_000)
     ap.add_argument("--e2e-rows", type=int, default=0, help="probe rows fed from host per e2e step (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-probe variant (roofline_shuffled)")
+    ap.add_argument("--no-groupby-bigint", action="store_true", help="skip the high-cardinality BIGINT GROUP BY block")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host pages) measurement: kernel experiments only")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128; 0 = leave the default)")
     args = ap.parse_args()
@@ -456,9 +460,13 @@ def main():
         peak, peak_src = measured_peak()
         kms = float(np.mean(kernel_ms))
         achieved = ALG_BYTES_PROBE_FUSED * l_count / (kms * 1e-3) / 1e9
-        roofline = {"kernel": "join_probe_lean_kernel<1,true> (fused probe + payload gather)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": NCU_TRAFFIC_PROBE_FUSED_SF100 if (args.sf == 100.0 and not args.shuffle_probe) else None,
-                    "traffic_source": "ncu --set full capture of this kernel on this configuration, profiles/r01_kernels.md (bytes per launch)",
+        traffic = NCU_TRAFFIC_PROBE_FUSED_SF100 if (args.sf == 100.0 and not args.shuffle_probe and not os.environ.get("TGPU_JOIN_HASH")) else None
+        roofline = {"kernel": "join_probe_lean_kernel<2,true> (fused probe + payload gather, order-preserving table lines)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "ncu --set full capture of this kernel on this configuration, profiles/r02_kernels.md (bytes per launch)",
+                    "frac_of_traffic": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
+                    "note": "frac can exceed 1: SURVEY §8(d)'s 40 B/row charges one table entry per probe ROW, but the ~4 rows of an order share one entry and the "
+                            "order-preserving layout reads every table line once; frac_of_traffic = measured DRAM bytes (ncu) / kernel time / peak is the physical utilisation",
                     "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "rows_per_launch": l_count,
                     "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step, "launches_timed": len(kernel_ms)}
         d_pos = ctx.malloc(l_count * 4)
@@ -471,14 +479,44 @@ def main():
             acc += ctx.last_kernel_ms()
         ims = acc / reps
         ia = ALG_BYTES_PROBE_INDEX * l_count / (ims * 1e-3) / 1e9
-        index_probe = {"kernel": "join_probe_lean_kernel<1,false> (index-only probe)", "bound": "hbm", "achieved": ia, "peak": peak, "unit": "GB/s", "frac": ia / peak,
+        index_probe = {"kernel": "join_probe_lean_kernel<2,false> (index-only probe)", "bound": "hbm", "achieved": ia, "peak": peak, "unit": "GB/s", "frac": ia / peak,
                        "algorithmic_bytes_per_row": ALG_BYTES_PROBE_INDEX, "kernel_ms": ims, "kernel_rows_per_sec": l_count / (ims * 1e-3)}
         ctx.free(d_pos)
+
+    # ---------------- variant B: the same join with uniformly shuffled probe keys - no key locality at all
+    shuffled = None
+    if world == 1 and not args.shuffle_probe and not args.no_shuffled:
+        d_skeys = ctx.malloc(l_count * 8)
+        ctx.check(lib.tgpu_synth_lineitem_keys(ctx.h, total_orders, l_first, l_count, SEED_LINEITEM, 1, C.c_void_p(d_skeys)))
+        spage = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_skeys, l_count), d_lprice_col], l_count)
+        sms = []
+        for i in range(2 + 3):
+            ctx.timer_start()
+            probe_op.add_input(spage)
+            out = probe_op.get_output_device()
+            t = ctx.timer_stop_ms()
+            assert out.rows == l_count
+            if i == 4:
+                ck = column_sum(out.column(0), 2557), column_sum(out.column(2))
+                assert ck[0] == ck[1], "shuffled probe: payload sum does not match the keys"
+            out.release()
+            if i >= 2:
+                sms.append(t)
+        sm = float(np.mean(sms))
+        sa = ALG_BYTES_PROBE_FUSED * l_count / (sm * 1e-3) / 1e9
+        shuffled = {"kernel": "LookupJoinOperator step over shuffled probe keys", "bound": "hbm", "achieved": sa, "peak": peak, "unit": "GB/s", "frac": sa / peak,
+                    "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "ms_per_step": sm, "rows_per_sec": l_count / (sm * 1e-3),
+                    "sector_floor_rows_per_sec": peak * 1e9 / (8 + 32 + 32 + 4 + 8),
+                    "note": "every probe row touches its own 32-byte table sector and its own 32-byte payload sector; sector_floor = peak / (8 key + 32 + 32 + 4 position + 8 payload written)"}
+        ctx.free(d_skeys)
 
     # ---------------- Q1 GROUP-BY side measurement (BASELINE.json configs[2]) on rank 0 at N=1
     q1 = None
     if world == 1 and args.q1_sf > 0:
         q1 = bench_q1(ctx, args)
+    gb = None
+    if world == 1 and args.q1_sf > 0 and not args.no_groupby_bigint:
+        gb = bench_groupby_bigint(ctx, args)
 
     # ---------------- end to end: host pages in, host result out, through the same operator calls
     e2e = None
@@ -507,8 +545,12 @@ def main():
             line["cpu_baseline"] = cpu
         if e2e:
             line["e2e"] = e2e
+        if shuffled:
+            line["roofline_shuffled"] = shuffled
         if q1:
             line["groupby_q1"] = q1
+        if gb:
+            line["groupby_bigint"] = gb
         print(json.dumps(line))
     probe_op.close()
     builder.close()
@@ -776,7 +818,8 @@ def bench_e2e_dist(ctx, args, dist, local, world, partitioner, probe_op, d_keys,
 
 
 def bench_q1(ctx, args):
-    """TPC-H Q1 fused scan+filter+project+GROUP BY over device-resident synthetic lineitem columns"""
+    """TPC-H Q1 fused scan+filter+project+GROUP BY over device-resident synthetic lineitem columns: with INT8 key codes (A = 38) and
+    with the reference's own key types, VARCHAR(1) l_returnflag / l_linestatus (A = 46: the keys go through the device string dictionary)"""
     from q1 import q1_factory
     from trino_b200 import abi
     from trino_b200 import operators as ops
@@ -786,38 +829,89 @@ def bench_q1(ctx, args):
     ptrs = [ctx.malloc(n * sz) for _, sz in spec]
     ctx.check(lib.tgpu_synth_lineitem_q1(ctx.h, n, 0, SEED_LINEITEM, *[C.c_void_p(p) for p in ptrs]))
     page = ops.DevicePage([ops.DeviceColumn(t, p, n) for (t, _), p in zip(spec, ptrs)], n)
+    d_off = ctx.malloc((n + 1) * 4)                      # VARCHAR(1): offsets 0..n, the bytes are the code columns themselves
+    ctx.check(lib.tgpu_synth_sequence32(ctx.h, 0, n + 1, C.c_void_p(d_off)))
+    cols_utf8 = [ops.DeviceColumn(t, p, n) for (t, _), p in zip(spec, ptrs)]
+    cols_utf8[1] = ops.DeviceColumn(abi.UTF8, ptrs[1], n, offsets=d_off)
+    cols_utf8[2] = ops.DeviceColumn(abi.UTF8, ptrs[2], n, offsets=d_off)
+    page_utf8 = ops.DevicePage(cols_utf8, n)
     factory = q1_factory(ctx, fused=True)
-
-    def run():
-        op = factory.create_operator()
-        op.add_input(page)
-        op.finish()
-        out = op.get_output()
-        op.close()
-        return out
-
-    for _ in range(2):
-        out = run()
-    reps = 5
-    kms = 0.0
-    ctx.timer_start()
-    for _ in range(reps):
-        out = run()
-        kms += ctx.last_kernel_ms()
-    ms = ctx.timer_stop_ms() / reps
-    kms /= reps
-    rows = out.rows()
     peak, peak_src = measured_peak()
-    achieved = ALG_BYTES_Q1_CODES * n / (kms * 1e-3) / 1e9
+
+    def measure(pg, alg, label, traffic):
+        def run():
+            op = factory.create_operator()
+            op.add_input(pg)
+            op.finish()
+            out = op.get_output()
+            op.close()
+            return out
+
+        for _ in range(2):
+            out = run()
+        reps = 5
+        kms = 0.0
+        ctx.timer_start()
+        for _ in range(reps):
+            out = run()
+            kms += ctx.last_kernel_ms()
+        ms = ctx.timer_stop_ms() / reps
+        kms /= reps
+        rows = out.rows()
+        achieved = alg * n / (kms * 1e-3) / 1e9
+        step_achieved = alg * n / (ms * 1e-3) / 1e9
+        return {"metric": "groupby_input_rows_per_sec", "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "rows": n, "groups": len(rows),
+                "config": f"TPC-H Q1 GROUP-BY, synthetic SF{args.q1_sf:g} lineitem, {label}, fused filter+project+aggregate (BASELINE.json configs[2])",
+                "roofline": {"kernel": "tg_agg_small_jit", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "peak_source": peak_src, "algorithmic_bytes_per_row": alg, "traffic": traffic, "kernel_ms": kms, "kernel_share_of_step": kms / ms,
+                             "step_frac": step_achieved / peak},
+                "result_count_order": [int(r[-1]) for r in rows]}
+
+    q1 = measure(page, ALG_BYTES_Q1_CODES, "INT8 key codes", NCU_TRAFFIC_Q1_SF300 if args.q1_sf == 300.0 else None)
+    q1["utf8_keys"] = measure(page_utf8, ALG_BYTES_Q1_UTF8, "VARCHAR(1) keys (the reference's types: offsets + bytes, device string dictionary)", None)
+    assert q1["utf8_keys"]["result_count_order"] == q1["result_count_order"]
+    ctx.free(d_off)
     for p in ptrs:
         ctx.free(p)
-    return {"metric": "groupby_input_rows_per_sec", "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "rows": n, "groups": len(rows),
-            "config": f"TPC-H Q1 GROUP-BY, synthetic SF{args.q1_sf:g} lineitem, INT8 key codes, fused filter+project+aggregate (BASELINE.json configs[2])",
-            "roofline": {"kernel": "tg_agg_small_jit", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_Q1_CODES,
-                         "traffic": NCU_TRAFFIC_Q1_SF300 if args.q1_sf == 300.0 else None, "kernel_ms": kms,
-                         "kernel_share_of_step": kms / ms},
-            "result_count_order": [int(r[-1]) for r in rows]}
+    return q1
+
+
+def bench_groupby_bigint(ctx, args):
+    """BIGINT-key GROUP BY with many groups (BigintGroupByHash territory, e.g. GROUP BY orderkey): 150 M rows, 10 M groups,
+    sum(bigint) + count(*), one operator per timed run (all groups are new every time)"""
+    from trino_b200 import abi
+    from trino_b200 import operators as ops
+    lib = ctx.lib
+    m, groups = 150_000_000, 10_000_000
+    d_keys, d_val = ctx.malloc(m * 8), ctx.malloc(m * 8)
+    for lo in range(0, m, groups):
+        cnt = min(groups, m - lo)
+        ctx.check(lib.tgpu_synth_orders_keys(ctx.h, groups, 0, cnt, 0x55 + lo, 1, C.c_void_p(d_keys + lo * 8)))   # every pass a fresh permutation of the keys
+    ctx.check(lib.tgpu_synth_lineitem_keys(ctx.h, m, 0, m, 1, 0, C.c_void_p(d_val)))
+    page = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_keys, m), ops.DeviceColumn(abi.INT64, d_val, m)], m)
+    f = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_SINGLE, [ops.Aggregator(abi.AGG_SUM, 1), ops.Aggregator(abi.AGG_COUNT_STAR)], expected_groups=groups)
+    got = [0]
+
+    def run():
+        op = f.create_operator()
+        op.add_input(page)
+        got[0] = op.group_count()
+        op.close()
+
+    run()
+    reps = 3
+    ctx.timer_start()
+    for _ in range(reps):
+        run()
+    ms = ctx.timer_stop_ms() / reps
+    assert got[0] == groups, got
+    peak, peak_src = measured_peak()
+    achieved = ALG_BYTES_GROUPBY_BIGINT * m / (ms * 1e-3) / 1e9
+    ctx.free(d_keys); ctx.free(d_val)
+    return {"metric": "groupby_input_rows_per_sec", "value": m / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "rows": m, "groups": groups,
+            "config": "GROUP BY a BIGINT key, 10 M groups, sum(bigint) + count(*), 150 M synthetic rows (SURVEY.md §8 a3), whole addInput incl. table set-up",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_row": ALG_BYTES_GROUPBY_BIGINT, "note": "step-level (operator call), not a single kernel"}}
 
 
 def cpu_baseline(args, n_orders, probe_rows):

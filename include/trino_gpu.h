@@ -458,6 +458,8 @@ int tgpu_synth_lineitem_q1(tgpu_ctx* ctx, int64_t n, int64_t first, uint64_t see
 int tgpu_synth_orders_custkeys(tgpu_ctx* ctx, int64_t n_total, int64_t first, int64_t count, uint64_t seed, int shuffle, int64_t n_customers,
                                uint64_t cust_seed, int64_t* out_device);
 int tgpu_synth_sequence(tgpu_ctx* ctx, int64_t first_value, int64_t count, int64_t* out_device);
+/* INT32 sequence: the offsets of a VARCHAR(1) column whose bytes are the INT8 code column itself (Q1 with the reference's key types) */
+int tgpu_synth_sequence32(tgpu_ctx* ctx, int32_t first_value, int64_t count, int32_t* out_device);
 /* star join (BASELINE.json configs[4]): rows [first, first + n) of a TPC-DS store_sales-shaped fact table: ss_sold_date_sk over a
  * 1 823-day window, ss_item_sk 1..300 000, ss_customer_sk 1..12 M and ss_store_sk 1..1 002 with 4.5 % NULLs each (Arrow validity
  * bitmaps, (n + 7) / 8 bytes), ss_net_paid FLOAT64.  *rows_with_both_keys = rows whose two nullable keys are both present. */

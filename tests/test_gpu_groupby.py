@@ -146,6 +146,7 @@ def test_aggregation_matches_oracle(ctx, card):
 def test_general_path_slice_by_slice_matches_oracle(ctx, monkeypatch):
     # tables larger than the L2 are visited slice by slice (rows regrouped by the slot index's top bits); force that path on a
     # small table: ids stay first-seen ordered across pages, growth in the middle of a page replays deferred rows
+    monkeypatch.setenv("TGPU_AGG_ROWLIST_SLICES", "1")          # the row-list form (one launch per slice), kept as the fallback for shapes the copy cannot take
     monkeypatch.setenv("TGPU_AGG_SLICE_MIN_BYTES", "0")
     monkeypatch.setenv("TGPU_AGG_SLICE_BYTES", str(256 << 10))
     rng = np.random.default_rng(77)
@@ -176,18 +177,20 @@ def test_hash_aggregation_operator_reference_case(ctx):
 
 
 def test_general_path_physical_slices_match_oracle(ctx, monkeypatch):
-    # EXPERIMENTAL (branch wip/path-g-physical): the sliced pass over a slice-ordered COPY of the page (multi-split scatter of the
-    # channels the plan reads + page row numbers for the stamps) instead of a row list
-    monkeypatch.setenv("TGPU_AGG_PHYSICAL_SLICES", "1")
+    # the default for tables beyond the L2: one pass over a slice-ordered COPY of the page (multi-split scatter of the channels the plan
+    # reads + page row numbers for the stamps); also with the interpreted kernel (hosts without NVRTC)
     monkeypatch.setenv("TGPU_AGG_SLICE_MIN_BYTES", "0")
     monkeypatch.setenv("TGPU_AGG_SLICE_BYTES", str(256 << 10))
     rng = np.random.default_rng(78)
     pages = _agg_pages(rng, 20000, (60000, 7, 90000)) + _agg_pages(rng, 400000, (150000,))
-    got = _gpu_agg(ctx, pages, [0], AGGS, expected=30000)
     want = _oracle_agg(pages, [0], AGGS)
-    assert rows_equal(got, want, rel=1e-6)
-    assert [r[0] for r in got] == [r[0] for r in want]
-    assert [(r[1], r[4], r[7], r[12]) for r in got] == [(r[1], r[4], r[7], r[12]) for r in want]
+    for interpreted in (False, True):
+        if interpreted:
+            monkeypatch.setenv("TGPU_AGG_GENERAL_INTERPRETED", "1")
+        got = _gpu_agg(ctx, pages, [0], AGGS, expected=30000)
+        assert rows_equal(got, want, rel=1e-6)
+        assert [r[0] for r in got] == [r[0] for r in want]
+        assert [(r[1], r[4], r[7], r[12]) for r in got] == [(r[1], r[4], r[7], r[12]) for r in want]
 
 
 def test_small_path_spills_into_general_path(ctx):

@@ -225,6 +225,7 @@ SIGNATURES = {
     "tgpu_column_sum": (C.c_int, [VP, VP, C.c_int64, VP]),
     "tgpu_synth_orders_custkeys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64, C.c_uint64, VP]),
     "tgpu_synth_sequence": (C.c_int, [VP, C.c_int64, C.c_int64, VP]),
+    "tgpu_synth_sequence32": (C.c_int, [VP, C.c_int32, C.c_int64, VP]),
     "tgpu_synth_store_sales": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP, VP]),
 }
 

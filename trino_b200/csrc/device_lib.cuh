@@ -424,6 +424,88 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
     }
 }
 
+// ---- general group-by, fused single pass (path G): kernel body as a template over the same row program ---------------------
+// One AoS record per table slot: {key, first-row stamp, accumulator words ...} (W 8-byte words).  A row finds or claims its key's
+// record, lowers the stamp and applies its accumulators with fire-and-forget reductions.  R rows are in flight per thread: all column
+// loads of the R rows first, then the R record heads (independent random reads), then the resolves.  Claims are budgeted through
+// TGD_TICKET_WAYS counters (tickets[way]; a way is picked by the lane) so that a page of mostly new keys does not serialise on one
+// L2 address; a row that finds its way's budget exhausted goes to the deferred list and is replayed after the table has grown.
+// tickets layout: [0, WAYS) claims per way, [WAYS] deferred rows, [WAYS + 1] special groups born.
+// P supplies, besides load() / row(): accumulate_global(unsigned long long* acc) - reductions on the record's accumulator words.
+#define TGD_TICKET_WAYS 64
+#define TGD_G_ROWS 4
+
+template <class P>
+__device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, long long n, const int* __restrict__ rows, long long first,
+                                                 const int* __restrict__ stamp_rows, long long page_base, unsigned long long* __restrict__ recs, long long cap, int W,
+                                                 int* __restrict__ tickets, int budget_per_way, int* __restrict__ deferred, unsigned int* __restrict__ err_out)
+{
+    constexpr int R = TGD_G_ROWS;
+    const unsigned long long mask = (unsigned long long)cap - 1;
+    const int way = (threadIdx.x + blockIdx.x * 7) & (TGD_TICKET_WAYS - 1);
+    unsigned int err = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * R) {
+        typename P::Regs regs[R];
+        long long row[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            long long i = base + (long long)j * stride;
+            row[j] = i < n ? (rows ? (long long)rows[i] : first + i) : -1;
+            if (row[j] >= 0) prog.load(cols, row[j], regs[j]);
+        }
+        unsigned long long pk[R], pos[R], cur[R];
+        int sp[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            pk[j] = 0;
+            sp[j] = -1;
+            if (row[j] >= 0 && !prog.row(regs[j], &pk[j], &sp[j], &err)) row[j] = -1;      // rejected by the fused filter
+            pos[j] = tgd_murmur3_mix(pk[j]) & mask;
+        }
+#pragma unroll
+        for (int j = 0; j < R; j++)
+            cur[j] = (row[j] >= 0 && sp[j] < 0) ? *((volatile unsigned long long*)(recs + (size_t)pos[j] * W)) : 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (row[j] < 0) continue;
+            long long s = -1;
+            if (sp[j] >= 0) s = cap + sp[j];
+            else {
+                unsigned long long p = pos[j], c = cur[j];
+                bool have_ticket = false;
+                while (true) {
+                    unsigned long long* kp = recs + (size_t)p * W;
+                    if (c == TGD_EMPTY_KEY) {
+                        if (!have_ticket) {
+                            if (atomicAdd(tickets + way, 1) >= budget_per_way) { atomicSub(tickets + way, 1); break; }
+                            have_ticket = true;
+                        }
+                        c = atomicCAS(kp, TGD_EMPTY_KEY, pk[j]);
+                        if (c == TGD_EMPTY_KEY) { s = (long long)p; have_ticket = false; break; }
+                    }
+                    if (c == pk[j]) { s = (long long)p; break; }
+                    p = (p + 1) & mask;
+                    c = *((volatile unsigned long long*)(recs + (size_t)p * W));
+                }
+                if (have_ticket) atomicSub(tickets + way, 1);
+            }
+            if (s < 0) { deferred[atomicAdd(tickets + TGD_TICKET_WAYS, 1)] = (int)row[j]; continue; }
+            unsigned long long* r = recs + (size_t)s * W;
+            const long long stamp = page_base + (stamp_rows ? (long long)stamp_rows[row[j]] : row[j]);
+            if (*((volatile long long*)(r + 1)) > stamp) {
+                long long old = atomicMin((long long*)(r + 1), stamp);
+                if (old == TGD_NO_ROW && s >= cap) atomicAdd(tickets + TGD_TICKET_WAYS + 1, 1);   // a special (NULL / sentinel key) group came to life
+            }
+            unsigned long long pk2;
+            int sp2;
+            prog.row(regs[j], &pk2, &sp2, &err);          // re-establish this row's values (registers only) for the accumulators
+            prog.accumulate_global(r + 2);
+        }
+    }
+    if (err) atomicOr(err_out, err);
+}
+
 // ---- FilterAndProject in two passes without a selection vector -------------------------------------------------------------
 // Every CTA owns a contiguous chunk of rows.  Pass 1 evaluates the filter (flags, 1 byte per row) and counts the selected rows
 // of the chunk; a scan of the chunk counts gives every chunk its first output row.  Pass 2 ranks the selected rows of a tile

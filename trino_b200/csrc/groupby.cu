@@ -1202,9 +1202,42 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
         if (d.kind == ACC_ROWS) appendf(s, "    if (%s) acc_update_private(%d, acc + %d * T, T, 0);\n", cond.c_str(), d.kind, map->of_plan[a]);
         else appendf(s, "    if (%s) acc_update_private(%d, acc + %d * T, T, v%d);\n", cond.c_str(), d.kind, map->of_plan[a], d.src);
     }
+    s += "  }\n";
+    // the same accumulators as reductions on a fused-G slot record (plan order, the record encoding of gf_accumulate: NONNULL counts the
+    // NULL inputs, the 128-bit integer sum is two carry-free 64-bit sums of the value's halves)
+    s += "  __device__ __forceinline__ void accumulate_global(unsigned long long* acc) {\n";
+    for (int a = 0; a < plan.num_accs; a++) {
+        const AccDesc& d = plan.accs[a];
+        if (d.kind == ACC_SUM_I64_HI) continue;
+        std::string cond = "true";
+        if (d.mask >= 0) { char b[64]; snprintf(b, sizeof(b), "(!vn%d && v%d != 0)", d.mask, d.mask); cond = b; }
+        const bool nullable = d.src >= 0 && src_nullable(d.src);
+        if (d.kind == ACC_NONNULL) {
+            if (nullable) appendf(s, "    if (%s && vn%d) atomicAdd(acc + %d, 1ULL);\n", cond.c_str(), d.src, a);
+            continue;
+        }
+        if (d.kind != ACC_ROWS && nullable) { char b[64]; snprintf(b, sizeof(b), " && !vn%d", d.src); cond += b; }
+        switch (d.kind) {
+            case ACC_ROWS: appendf(s, "    if (%s) atomicAdd(acc + %d, 1ULL);\n", cond.c_str(), a); break;
+            case ACC_SUM_F64: appendf(s, "    if (%s) atomicAdd((double*)(acc + %d), __longlong_as_double(v%d));\n", cond.c_str(), a, d.src); break;
+            case ACC_SUM_F64_FROM_I64: appendf(s, "    if (%s) atomicAdd((double*)(acc + %d), (double)v%d);\n", cond.c_str(), a, d.src); break;
+            case ACC_SUM_I64_LO:
+                appendf(s, "    if (%s) { atomicAdd(acc + %d, (unsigned long long)v%d & 0xFFFFFFFFULL); atomicAdd(acc + %d, (unsigned long long)(v%d >> 32)); }\n",
+                        cond.c_str(), a, d.src, a + 1, d.src);
+                break;
+            case ACC_MIN_F64: appendf(s, "    if (%s) atomicMin(acc + %d, f64_order_key(v%d));\n", cond.c_str(), a, d.src); break;
+            case ACC_MAX_F64: appendf(s, "    if (%s) atomicMax(acc + %d, f64_order_key_max(v%d));\n", cond.c_str(), a, d.src); break;
+            case ACC_MIN_I64: appendf(s, "    if (%s) atomicMin(acc + %d, i64_order_key(v%d));\n", cond.c_str(), a, d.src); break;
+            case ACC_MAX_I64: appendf(s, "    if (%s) atomicMax(acc + %d, i64_order_key(v%d));\n", cond.c_str(), a, d.src); break;
+            default: break;
+        }
+    }
     s += "  }\n};\n";
     appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d) tg_agg_small_jit(DColumns cols, long long n, SmallOut out) {\n", S_THREADS, min_blocks);
     s += "  extern __shared__ unsigned long long smem_u64[];\n  Prog p;\n  agg_small_body(p, cols, n, out, smem_u64);\n}\n";
+    s += "extern \"C\" __global__ void __launch_bounds__(256) tg_agg_general_jit(DColumns cols, long long n, const int* rows, long long first, const int* stamp_rows,\n"
+         "    long long page_base, unsigned long long* recs, long long cap, int W, int* tickets, int budget_per_way, int* deferred, unsigned int* err_out) {\n"
+         "  Prog p;\n  agg_general_body(p, cols, n, rows, first, stamp_rows, page_base, recs, cap, W, tickets, budget_per_way, deferred, err_out);\n}\n";
     return s;
 }
 
@@ -1257,7 +1290,9 @@ struct AggOp : tgpu_op {
     // path S scratch
     struct JitVariant { void* fn = nullptr; AccMap map; };
     std::map<uint64_t, JitVariant> jit_variants;   // keyed by (L, which channels carry a validity bitmap)
+    std::map<uint64_t, void*> jit_g_variants;      // fused general kernel, keyed by the page layout (element widths, validity bitmaps)
     std::vector<int> jit_elems;
+    DevBuf f_tickets;
     int s_L = 0, s_grid = 0;
     size_t s_smem = 0, s_per_slot = 0, s_fixed = 0;
     DevBuf blk_keys, blk_first, blk_acc, blk_ps;
@@ -1825,26 +1860,82 @@ struct AggOp : tgpu_op {
         return TGPU_OK;
     }
 
-    // one gf_page_kernel pass over `todo` rows (`rows` == nullptr: rows [0, todo) of the page), replaying deferred rows after growth
+    // the fused general kernel specialised for this plan (NVRTC; same row program as the path-S kernel), or nullptr without NVRTC
+    int general_jit_function(const DColumns& cols, void** fn)
+    {
+        *fn = nullptr;
+        if (!jit_available() || getenv("TGPU_AGG_GENERAL_INTERPRETED")) return TGPU_OK;
+        // the page layout the general path sees (the projection's output once the pre-stage was un-fused): element widths + NULL-ability
+        int elems[TGPU_MAX_CHANNELS];
+        uint64_t key = 0;
+        for (int c = 0; c < TGPU_MAX_CHANNELS; c++) {
+            elems[c] = cols.cols[c].data ? cols.cols[c].elem : 0;
+            key = key * 0x100000001B3ULL + (uint64_t)(elems[c] * 2 + (cols.cols[c].validity ? 1 : 0));
+        }
+        uint32_t nullable = 0;
+        for (int c = 0; c < TGPU_MAX_CHANNELS; c++)
+            if (cols.cols[c].validity) nullable |= 1u << c;
+        auto it = jit_g_variants.find(key);
+        if (it == jit_g_variants.end()) {
+            AccMap unused;
+            std::string src = gen_agg_small_source(plan, has_pre ? &host_prog : nullptr, elems, TGPU_MAX_CHANNELS, 4, 2, nullable, &unused);
+            void* f = nullptr;
+            TG_TRY(jit_get_function(ctx, src, "tg_agg_general_jit", &f));
+            it = jit_g_variants.emplace(key, f).first;
+        }
+        *fn = it->second;
+        return TGPU_OK;
+    }
+
+    // one pass of the fused general kernel over `todo` rows (`rows` == nullptr: rows [first, first + todo) of the page), replaying deferred
+    // rows after growth
     int run_fused_rows(const DColumns& cols, const int* rows, int64_t todo, int64_t first = 0, const int* stamp_rows = nullptr)
     {
         DevBuf deferred, replay;
         TG_TRY(deferred.alloc(ctx, (size_t)std::max<int64_t>(todo, 1) * 4));
-        int* d_tickets = (int*)(ctx->d_scratch + 20);    // [0] slots claimed by this launch, [1] deferred rows, [2] special groups born
+        void* jit_fn = nullptr;
+        TG_TRY(general_jit_function(cols, &jit_fn));
+        constexpr int WAYS = TGD_TICKET_WAYS;
+        if (!f_tickets.p) TG_TRY(f_tickets.alloc(ctx, (WAYS + 4) * 4));
+        int* d_tickets = f_tickets.as<int>();    // interpreted kernel: [0] claims, [1] deferred rows, [2] specials born; specialised: [0, WAYS) claims, [WAYS] deferred, [WAYS+1] specials, [WAYS+2] error bits
+        std::vector<int32_t> counters(WAYS + 4);
         while (true) {
             int64_t budget = f_cap * 3 / 4 - f_used;
-            TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 16, ctx->stream));
+            TG_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, (WAYS + 4) * 4, ctx->stream));
+            int grid = tg_grid(ctx, todo, 256, 8);
             TG_TIMED_BEGIN(ctx);
-            TG_LAUNCH(ctx, gf_page_kernel, tg_grid(ctx, todo, 256, 8), 256, 0, plan, cols, todo, rows, first, stamp_rows, (long long)rows_seen, f_recs.as<unsigned long long>(), f_cap,
-                      gf_words(), d_tickets, (int)std::min<int64_t>(std::max<int64_t>(budget, 0), INT32_MAX), deferred.as<int>());
+            if (jit_fn) {
+                DColumns cols_arg = cols;
+                long long n_arg = todo, first_arg = first, base_arg = (long long)rows_seen, cap_arg = f_cap;
+                const int* rows_arg = rows;
+                const int* stamps_arg = stamp_rows;
+                unsigned long long* recs_arg = f_recs.as<unsigned long long>();
+                int w_arg = gf_words(), per_way = (int)std::min<int64_t>(std::max<int64_t>(budget, 0) / WAYS, INT32_MAX);
+                int* tickets_arg = d_tickets;
+                int* deferred_arg = deferred.as<int>();
+                unsigned int* err_arg = (unsigned int*)(d_tickets + WAYS + 2);
+                void* params[13] = {&cols_arg, &n_arg, &rows_arg, &first_arg, &stamps_arg, &base_arg, &recs_arg, &cap_arg, &w_arg, &tickets_arg, &per_way, &deferred_arg, &err_arg};
+                grid = (int)std::min<int64_t>(tg_div_up(todo, 256 * TGD_G_ROWS), (int64_t)ctx->sm_count * std::max(1, jit_blocks_per_sm(jit_fn, 256, 0)));
+                TG_TRY(jit_launch(ctx, jit_fn, std::max(grid, 1), 256, 0, params));
+            }
+            else
+                TG_LAUNCH(ctx, gf_page_kernel, grid, 256, 0, plan, cols, todo, rows, first, stamp_rows, (long long)rows_seen, f_recs.as<unsigned long long>(), f_cap,
+                          gf_words(), d_tickets, (int)std::min<int64_t>(std::max<int64_t>(budget, 0), INT32_MAX), deferred.as<int>());
             TG_TIMED_END(ctx);
-            int32_t counters[4] = {0, 0, 0, 0};
-            TG_CUDA(ctx, cudaMemcpyAsync(ctx->h_scratch, d_tickets, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaMemcpyAsync(counters.data(), d_tickets, (WAYS + 4) * 4, cudaMemcpyDeviceToHost, ctx->stream));
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            memcpy(counters, ctx->h_scratch, 16);
-            f_used += counters[0];
-            f_specials += counters[2];
-            int64_t left = counters[1];
+            int64_t left;
+            if (jit_fn) {
+                for (int w = 0; w < WAYS; w++) f_used += counters[w];
+                f_specials += counters[WAYS + 1];
+                left = counters[WAYS];
+                TG_TRY(raise((uint32_t)counters[WAYS + 2]));
+            }
+            else {
+                f_used += counters[0];
+                f_specials += counters[2];
+                left = counters[1];
+            }
             if (left == 0) break;
             // BigintGroupByHash.tryRehash :239-290 (here x4), then replay the rows that found the table full
             TG_TRY(gf_grow());
@@ -1927,8 +2018,9 @@ struct AggOp : tgpu_op {
             pcols.cols[lane.col].validity = packed.validity;
             packed_keep.push_back(std::move(packed));
         }
-        for (int q = 0; q < S; q++)
-            if (counts[q]) TG_TRY(run_fused_rows(pcols, nullptr, counts[q], off[q], stamp_rows));
+        // ONE launch over the slice-ordered copy: a grid-stride pass keeps every CTA in the same neighbourhood of the row array, i.e. in
+        // the same table slice, so the slice's records stay in the L2 without a launch (and a host round trip) per slice
+        TG_TRY(run_fused_rows(pcols, nullptr, n, 0, stamp_rows));
         TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the copies are released below: the last slice launch must be done with them
         *done = true;
         return TGPU_OK;
@@ -1951,7 +2043,7 @@ struct AggOp : tgpu_op {
             const int S = 1 << log_slices;
             int log_cap = 0;
             while ((1LL << log_cap) < f_cap) log_cap++;
-            if (getenv("TGPU_AGG_PHYSICAL_SLICES")) {
+            if (!getenv("TGPU_AGG_ROWLIST_SLICES")) {
                 bool done = false;
                 TG_TRY(run_physical_slices(in, cols, n, log_slices, log_cap, &done));
                 if (done) {

@@ -99,6 +99,13 @@ __global__ void synth_orders_custkeys_kernel(int64_t n_total, int64_t first, int
     }
 }
 
+__global__ void synth_sequence32_kernel(int32_t first_value, int64_t count, int32_t* __restrict__ out)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j < count; j += stride) out[j] = first_value + (int32_t)j;
+}
+
 __global__ void synth_sequence_kernel(int64_t first_value, int64_t count, int64_t* __restrict__ out)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,5 +262,14 @@ extern "C" int tgpu_synth_store_sales(tgpu_ctx* ctx, int64_t n, int64_t first, u
     int64_t v = 0;
     TG_TRY(tg_read_i64(ctx, cnt.p, &v));
     if (rows_with_both_keys) *rows_with_both_keys = v;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_synth_sequence32(tgpu_ctx* ctx, int32_t first_value, int64_t count, int32_t* out)
+{
+    if (!ctx || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return TGPU_OK;
+    TG_LAUNCH(ctx, synth_sequence32_kernel, tg_grid(ctx, count, 1024, 8), 256, 0, first_value, count, out);
     return TGPU_OK;
 }
