@@ -12,33 +12,43 @@ import io.trino.operator.OperatorFactory;
 import io.trino.sql.planner.plan.AggregationNode.Step;
 import io.trino.sql.planner.plan.PlanNodeId;
 
+import java.lang.foreign.MemorySegment;
 import java.util.List;
+import java.util.OptionalInt;
 
 import static com.google.common.base.Preconditions.checkState;
 
 public class GpuHashAggregationOperatorFactory
         implements OperatorFactory
 {
-    /** function id + input/mask channels of one aggregate: the serialisable part of an AggregatorFactory */
+    /** function id (tgpu_agg_function) + input/mask channels of one aggregate: the serialisable part of an AggregatorFactory */
     public record GpuAggregate(int function, int inputChannel, int maskChannel) {}
 
     private final int operatorId;
     private final PlanNodeId planNodeId;
+    private final int[] inputTypes;              // tgpu_type per source channel (source.getTypes() at :4086-4089)
+    private final int[] outputTypes;             // group-by types, then one (SINGLE/FINAL) or the state columns (PARTIAL) per aggregate
     private final List<Integer> groupByChannels;
+    private final List<Integer> globalAggregationGroupIds;
     private final Step step;
     private final List<GpuAggregate> aggregates;
+    private final OptionalInt groupIdChannel;    // index among the group-by keys, as in the reference (:552)
     private final int expectedGroups;
     private final long maxPartialMemory;
     private boolean closed;
 
-    public GpuHashAggregationOperatorFactory(int operatorId, PlanNodeId planNodeId, List<Integer> groupByChannels, Step step,
-            List<GpuAggregate> aggregates, int expectedGroups, long maxPartialMemory)
+    public GpuHashAggregationOperatorFactory(int operatorId, PlanNodeId planNodeId, int[] inputTypes, int[] outputTypes, List<Integer> groupByChannels,
+            List<Integer> globalAggregationGroupIds, Step step, List<GpuAggregate> aggregates, OptionalInt groupIdChannel, int expectedGroups, long maxPartialMemory)
     {
         this.operatorId = operatorId;
         this.planNodeId = planNodeId;
+        this.inputTypes = inputTypes.clone();
+        this.outputTypes = outputTypes.clone();
         this.groupByChannels = List.copyOf(groupByChannels);
+        this.globalAggregationGroupIds = List.copyOf(globalAggregationGroupIds);
         this.step = step;
         this.aggregates = List.copyOf(aggregates);
+        this.groupIdChannel = groupIdChannel;
         this.expectedGroups = expectedGroups;
         this.maxPartialMemory = maxPartialMemory;
     }
@@ -49,8 +59,9 @@ public class GpuHashAggregationOperatorFactory
         checkState(!closed, "Factory is already closed");
         OperatorContext operatorContext = driverContext.addOperatorContext(operatorId, planNodeId, "GpuHashAggregationOperator");
         GpuContexts.Handle gpu = GpuContexts.forCurrentDriver(driverContext);
-        // fills a tgpu_agg_spec {num_keys, key_channels, step, num_aggs, aggs, expected_groups, max_partial_bytes, pre} and calls tgpu_agg_create
-        return new GpuOperator(operatorContext, gpu.context(), NativeSpecs.createAggregation(gpu, groupByChannels, step, aggregates, expectedGroups, maxPartialMemory), gpu.marshaller());
+        MemorySegment op = NativeSpecs.createAggregation(gpu, groupByChannels, step, aggregates, expectedGroups, maxPartialMemory, globalAggregationGroupIds,
+                groupIdChannel.orElse(-1), inputTypes, MemorySegment.NULL);
+        return new GpuOperator(operatorContext, gpu.context(), op, gpu.marshaller(inputTypes), outputTypes);
     }
 
     @Override
@@ -62,6 +73,7 @@ public class GpuHashAggregationOperatorFactory
     @Override
     public OperatorFactory duplicate()
     {
-        return new GpuHashAggregationOperatorFactory(operatorId, planNodeId, groupByChannels, step, aggregates, expectedGroups, maxPartialMemory);
+        return new GpuHashAggregationOperatorFactory(operatorId, planNodeId, inputTypes, outputTypes, groupByChannels, globalAggregationGroupIds, step, aggregates,
+                groupIdChannel, expectedGroups, maxPartialMemory);
     }
 }

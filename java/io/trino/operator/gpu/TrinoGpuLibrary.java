@@ -31,6 +31,11 @@ public final class TrinoGpuLibrary
     static final MethodHandle CTX_DESTROY = handle("tgpu_ctx_destroy", FunctionDescriptor.ofVoid(ADDRESS));
     static final MethodHandle LAST_ERROR = handle("tgpu_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
     static final MethodHandle STATUS_NAME = handle("tgpu_status_name", FunctionDescriptor.of(ADDRESS, JAVA_INT));
+    static final MethodHandle HOST_ALLOC_PINNED = handle("tgpu_host_alloc_pinned", FunctionDescriptor.of(JAVA_INT, JAVA_LONG, ADDRESS));
+    static final MethodHandle HOST_FREE_PINNED = handle("tgpu_host_free_pinned", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle PAGE_UTF8_BYTES = handle("tgpu_page_utf8_bytes", FunctionDescriptor.of(JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT));
+    static final MethodHandle LOOKUP_POSITION_COUNT = handle("tgpu_lookup_position_count", FunctionDescriptor.of(JAVA_LONG, ADDRESS));
+    static final MethodHandle LOOKUP_MEMORY_BYTES = handle("tgpu_lookup_memory_bytes", FunctionDescriptor.of(JAVA_LONG, ADDRESS));
     // operator factories
     static final MethodHandle FILTER_PROJECT_CREATE = handle("tgpu_filter_project_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle AGG_CREATE = handle("tgpu_agg_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));

@@ -83,7 +83,47 @@ __global__ void __launch_bounds__(256) sd_insert_kernel(const int32_t* __restric
             pos = (pos + 1) & mask;
         }
         slot_of_row[row] = found;
-        if (found >= 0 && *((volatile int*)&table[found].id) < 0) atomicMin(&table[found].first_row, row);
+        if (found >= 0 && *((volatile int*)&table[found].id) < 0) {
+            // rows of one warp that share a new slot elect their lowest row; it touches the slot only if it would lower the owner
+            // (a page of 10^9 rows over three new strings would otherwise serialise 10^9 atomics on three addresses)
+            const unsigned int peers = __match_any_sync(__activemask(), found);
+            const int lowest = __reduce_min_sync(peers, row);
+            if (row == lowest && *((volatile int*)&table[found].first_row) > row) atomicMin(&table[found].first_row, row);
+        }
+    }
+}
+
+// fast path for pages whose strings are (almost) all known: look up, write the id, flag the chunk on a miss.  One pass: offsets + bytes
+// in, ids out.  chunk_miss[row / chunk_rows] != 0 -> that chunk has to go through the insert path.
+__global__ void __launch_bounds__(256) sd_lookup_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ bytes, const uint8_t* __restrict__ validity,
+                                                       int64_t first, int64_t n, const StrSlot* __restrict__ table, unsigned long long mask,
+                                                       const uint8_t* __restrict__ dict_bytes, const long long* __restrict__ dict_start, const int* __restrict__ dict_len,
+                                                       int32_t* __restrict__ ids, int64_t chunk_rows, int* __restrict__ chunk_miss)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int64_t row = first + i;
+        if (!tg_valid(validity, row)) { ids[row] = 0; continue; }
+        const int off = offsets[row], len = offsets[row + 1] - off;
+        int id = -1;
+        for (int attempt = 0; attempt < SD_MAX_ATTEMPTS && id < 0; attempt++) {
+            const unsigned long long key = sd_key(bytes + off, len, attempt);
+            unsigned long long pos = murmur3_mix(key) & mask;
+            bool other = false;       // a slot with this key holds a different string: try the next hash function
+            while (true) {
+                const StrSlot s = table[pos];
+                if (s.key == SD_EMPTY) break;
+                if (s.key == key && s.id >= 0) {
+                    if ((len <= 7 && attempt == 0) || (dict_len[s.id] == len && sd_bytes_equal(bytes + off, dict_bytes + dict_start[s.id], len))) { id = s.id; break; }
+                    other = true;
+                }
+                pos = (pos + 1) & mask;
+            }
+            if (!other) break;
+        }
+        if (id < 0) { chunk_miss[i / chunk_rows] = 1; id = 0; }
+        ids[row] = id;
     }
 }
 
@@ -230,7 +270,9 @@ struct StringDict {
         return TGPU_OK;
     }
 
-    // UTF8 column -> INT32 id column (NULL rows keep their validity; their id is 0)
+    // UTF8 column -> INT32 id column (NULL rows keep their validity; their id is 0).  Pages are taken in chunks: the first chunk goes
+    // through the insert path (it meets the new strings), the rest through the one-pass lookup kernel; only chunks that met an
+    // unknown string are re-run through the insert path.
     int encode(const DevColumn& col, DevColumn* out)
     {
         const int64_t n = col.length;
@@ -244,6 +286,42 @@ struct StringDict {
         ids.own_validity = col.own_validity;
         ids.validity = col.validity;
         if (n == 0) { *out = std::move(ids); return TGPU_OK; }
+        constexpr int64_t CHUNK = 4 << 20;
+        int32_t* d_ids = (int32_t*)ids.own_data->p;
+        const int64_t head = count == 0 ? std::min<int64_t>(n, CHUNK) : 0;      // an empty dictionary learns from the first chunk
+        if (head > 0) TG_TRY(encode_rows(col, 0, head, d_ids));
+        if (head < n) {
+            const int64_t rest = n - head, chunks = tg_div_up(rest, CHUNK);
+            DevBuf miss;
+            TG_TRY(miss.alloc(ctx, (size_t)chunks * 4));
+            TG_CUDA(ctx, cudaMemsetAsync(miss.p, 0, (size_t)chunks * 4, ctx->stream));
+            if (cap == 0) TG_TRY(alloc_table(1 << 12));
+            TG_LAUNCH(ctx, sd_lookup_kernel, tg_grid(ctx, rest, 1024, 8), 256, 0, col.offsets, (const uint8_t*)col.data, col.validity, head, rest, table.as<StrSlot>(),
+                      (unsigned long long)cap - 1, bytes.as<uint8_t>(), start.as<long long>(), len.as<int>(), d_ids, CHUNK, miss.as<int>());
+            std::vector<int> h_miss((size_t)chunks);
+            TG_CUDA(ctx, cudaMemcpyAsync(h_miss.data(), miss.p, (size_t)chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int64_t c = 0; c < chunks; c++)
+                if (h_miss[c]) TG_TRY(encode_rows(col, head + c * CHUNK, std::min<int64_t>(CHUNK, n - (head + c * CHUNK)), d_ids));
+        }
+        *out = std::move(ids);
+        return TGPU_OK;
+    }
+
+    // insert path over rows [first, first + n) of the column: find-or-claim, verify, append the new strings, write the ids
+    int encode_rows(const DevColumn& whole, int64_t first, int64_t n, int32_t* d_ids_whole)
+    {
+        DevColumn col = whole;
+        col.offsets = whole.offsets + first;                     // row r of the slice is row first + r: offsets keep pointing into `data`
+        col.length = n;
+        const uint8_t* slice_validity = nullptr;
+        DevBuf shifted_validity;
+        if (whole.validity) {
+            if ((first & 7) == 0) slice_validity = whole.validity + (first >> 3);
+            else return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "string dictionary chunk is not byte aligned");
+        }
+        col.validity = slice_validity;
+        int32_t* d_ids = d_ids_whole + first;
         if (cap == 0) TG_TRY(alloc_table(1 << 12));
         DevBuf slot_of_row, attempt, retry_a, retry_b;
         TG_TRY(slot_of_row.alloc(ctx, (size_t)n * 4));
@@ -316,8 +394,7 @@ struct StringDict {
             count += fresh;
             bytes_used += fresh_bytes;
         }
-        TG_LAUNCH(ctx, sd_ids_kernel, grid, 256, 0, n, table.as<StrSlot>(), slot_of_row.as<int>(), (int32_t*)ids.own_data->p);
-        *out = std::move(ids);
+        TG_LAUNCH(ctx, sd_ids_kernel, grid, 256, 0, n, table.as<StrSlot>(), slot_of_row.as<int>(), d_ids);
         return TGPU_OK;
     }
 
