@@ -336,6 +336,28 @@ int tgpu_semi_join_create(tgpu_ctx* ctx, tgpu_lookup* lookup, int32_t probe_join
 int tgpu_lookup_key_domain(tgpu_ctx* ctx, tgpu_lookup* lookup, int64_t max_values, int64_t* min_out, int64_t* max_out, int64_t* distinct_out,
                            int64_t* values_out, int32_t* has_null_out);
 
+/* DynamicPageFilter (M/sql/gen/columnar/DynamicPageFilter.java:47-211): the probe-side half of dynamic filtering.  One Domain per
+ * filtered channel = `null_allowed` + a value set (Domain.includesNullableValue): ALL, NONE, one inclusive range [min, max]
+ * (integer family, and DOUBLE by value), or DISCRETE values (integer family; any order, sorted here).  Filters apply in the given order to
+ * the surviving rows (DynamicFilterEvaluator.evaluate :160-178); a filter that, after >= 2047 input positions, passes more than
+ * selectivity_threshold of them is switched off (EffectiveFilterProfiler :181-210).  A Range with an exclusive upper bound over integers is
+ * passed as max = bound - 1.  Zero domains = TupleDomain.all() (every page passes through); TupleDomain.none() = one NONE domain.
+ * Output: the input page restricted to the selected rows, in input order (all blocks pass through when every row is selected).
+ * tgpu_dynamic_filter_update installs a narrowed predicate (DynamicFilter.getCurrentPredicate after an update: a new evaluator with a
+ * fresh profiler, :100-108). */
+typedef enum tgpu_domain_kind { TGPU_DOMAIN_ALL = 0, TGPU_DOMAIN_NONE = 1, TGPU_DOMAIN_RANGE = 2, TGPU_DOMAIN_DISCRETE = 3 } tgpu_domain_kind;
+typedef struct tgpu_domain {
+    int32_t channel;
+    int32_t null_allowed;      /* Domain.isNullAllowed() */
+    int32_t kind;              /* tgpu_domain_kind */
+    int32_t num_values;        /* DISCRETE */
+    int64_t min, max;          /* RANGE (raw IEEE bits for a DOUBLE channel); derived for DISCRETE */
+    const int64_t* values;     /* DISCRETE */
+} tgpu_domain;
+int tgpu_dynamic_filter_create(tgpu_ctx* ctx, const tgpu_domain* domains, int32_t num_domains, double selectivity_threshold, tgpu_op** out);
+int tgpu_dynamic_filter_update(tgpu_op* op, const tgpu_domain* domains, int32_t num_domains);
+int tgpu_dynamic_filter_is_effective(tgpu_op* op, int32_t filter, int32_t* out);
+
 /* LookupSource.getJoinPosition(int[] positions, Page hashChannelsPage, Page allChannelsPage, long[] result)
  * (M/operator/join/JoinHash.java:100-143): for every row of `keys_page` (only the key columns, in
  * key order) the address index of the chain head or -1.  `out_positions` is int32[num_rows], host or

@@ -146,6 +146,13 @@ class PartitionSpec(C.Structure):
     ]
 
 
+class Domain(C.Structure):
+    _fields_ = [("channel", C.c_int32), ("null_allowed", C.c_int32), ("kind", C.c_int32), ("num_values", C.c_int32),
+                ("min", C.c_int64), ("max", C.c_int64), ("values", C.POINTER(C.c_int64))]
+
+
+DOMAIN_ALL, DOMAIN_NONE, DOMAIN_RANGE, DOMAIN_DISCRETE = 0, 1, 2, 3
+
 VP = C.c_void_p
 PP = C.POINTER(Page)
 
@@ -223,6 +230,9 @@ SIGNATURES = {
     "tgpu_synth_lineitem_keys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, VP]),
     "tgpu_synth_lineitem_q1": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_uint64, VP, VP, VP, VP, VP, VP, VP]),
     "tgpu_column_sum": (C.c_int, [VP, VP, C.c_int64, VP]),
+    "tgpu_dynamic_filter_create": (C.c_int, [VP, VP, C.c_int32, C.c_double, VP]),
+    "tgpu_dynamic_filter_update": (C.c_int, [VP, VP, C.c_int32]),
+    "tgpu_dynamic_filter_is_effective": (C.c_int, [VP, C.c_int32, VP]),
     "tgpu_synth_orders_custkeys": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, C.c_int64, C.c_uint64, VP]),
     "tgpu_synth_sequence": (C.c_int, [VP, C.c_int64, C.c_int64, VP]),
     "tgpu_synth_sequence32": (C.c_int, [VP, C.c_int32, C.c_int64, VP]),

@@ -95,35 +95,61 @@ __global__ void __launch_bounds__(256) sd_insert_kernel(const int32_t* __restric
 
 // fast path for pages whose strings are (almost) all known: look up, write the id, flag the chunk on a miss.  One pass: offsets + bytes
 // in, ids out.  chunk_miss[row / chunk_rows] != 0 -> that chunk has to go through the insert path.
+__device__ __forceinline__ int sd_find(const uint8_t* __restrict__ p, int len, const StrSlot* __restrict__ table, unsigned long long mask,
+                                       const uint8_t* __restrict__ dict_bytes, const long long* __restrict__ dict_start, const int* __restrict__ dict_len,
+                                       unsigned long long key0)
+{
+    for (int attempt = 0; attempt < SD_MAX_ATTEMPTS; attempt++) {
+        const unsigned long long key = attempt == 0 ? key0 : sd_key(p, len, attempt);
+        unsigned long long pos = murmur3_mix(key) & mask;
+        bool other = false;       // a slot with this key holds a different string: try the next hash function
+        while (true) {
+            const int4 raw = __ldg((const int4*)&table[pos]);
+            const unsigned long long skey = (unsigned long long)(unsigned int)raw.x | ((unsigned long long)(unsigned int)raw.y << 32);
+            if (skey == SD_EMPTY) break;
+            if (skey == key && raw.z >= 0) {
+                if ((len <= 7 && attempt == 0) || (dict_len[raw.z] == len && sd_bytes_equal(p, dict_bytes + dict_start[raw.z], len))) return raw.z;
+                other = true;
+            }
+            pos = (pos + 1) & mask;
+        }
+        if (!other) return -1;
+    }
+    return -1;
+}
+
+// R rows per thread: the offsets of the R rows first, then their (first) bytes, then the table probes - independent chains
 __global__ void __launch_bounds__(256) sd_lookup_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ bytes, const uint8_t* __restrict__ validity,
                                                        int64_t first, int64_t n, const StrSlot* __restrict__ table, unsigned long long mask,
                                                        const uint8_t* __restrict__ dict_bytes, const long long* __restrict__ dict_start, const int* __restrict__ dict_len,
                                                        int32_t* __restrict__ ids, int64_t chunk_rows, int* __restrict__ chunk_miss)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) {
-        const int64_t row = first + i;
-        if (!tg_valid(validity, row)) { ids[row] = 0; continue; }
-        const int off = offsets[row], len = offsets[row + 1] - off;
-        int id = -1;
-        for (int attempt = 0; attempt < SD_MAX_ATTEMPTS && id < 0; attempt++) {
-            const unsigned long long key = sd_key(bytes + off, len, attempt);
-            unsigned long long pos = murmur3_mix(key) & mask;
-            bool other = false;       // a slot with this key holds a different string: try the next hash function
-            while (true) {
-                const StrSlot s = table[pos];
-                if (s.key == SD_EMPTY) break;
-                if (s.key == key && s.id >= 0) {
-                    if ((len <= 7 && attempt == 0) || (dict_len[s.id] == len && sd_bytes_equal(bytes + off, dict_bytes + dict_start[s.id], len))) { id = s.id; break; }
-                    other = true;
-                }
-                pos = (pos + 1) & mask;
-            }
-            if (!other) break;
+    constexpr int R = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * R) {
+        int off[R], len[R];
+        unsigned long long key[R];
+        bool live[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int64_t i = base + (int64_t)j * stride;
+            live[j] = i < n && tg_valid(validity, first + i);
+            off[j] = 0; len[j] = 0;
+            if (live[j]) { off[j] = __ldg(offsets + first + i); len[j] = __ldg(offsets + first + i + 1) - off[j]; }
         }
-        if (id < 0) { chunk_miss[i / chunk_rows] = 1; id = 0; }
-        ids[row] = id;
+#pragma unroll
+        for (int j = 0; j < R; j++) key[j] = live[j] ? sd_key(bytes + off[j], len[j], 0) : 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int64_t i = base + (int64_t)j * stride;
+            if (i >= n) continue;
+            int id = 0;
+            if (live[j]) {
+                id = sd_find(bytes + off[j], len[j], table, mask, dict_bytes, dict_start, dict_len, key[j]);
+                if (id < 0) { chunk_miss[i / chunk_rows] = 1; id = 0; }
+            }
+            ids[first + i] = id;
+        }
     }
 }
 
@@ -296,7 +322,7 @@ struct StringDict {
             TG_TRY(miss.alloc(ctx, (size_t)chunks * 4));
             TG_CUDA(ctx, cudaMemsetAsync(miss.p, 0, (size_t)chunks * 4, ctx->stream));
             if (cap == 0) TG_TRY(alloc_table(1 << 12));
-            TG_LAUNCH(ctx, sd_lookup_kernel, tg_grid(ctx, rest, 1024, 8), 256, 0, col.offsets, (const uint8_t*)col.data, col.validity, head, rest, table.as<StrSlot>(),
+            TG_LAUNCH(ctx, sd_lookup_kernel, tg_grid(ctx, rest, 1024, 6), 256, 0, col.offsets, (const uint8_t*)col.data, col.validity, head, rest, table.as<StrSlot>(),
                       (unsigned long long)cap - 1, bytes.as<uint8_t>(), start.as<long long>(), len.as<int>(), d_ids, CHUNK, miss.as<int>());
             std::vector<int> h_miss((size_t)chunks);
             TG_CUDA(ctx, cudaMemcpyAsync(h_miss.data(), miss.p, (size_t)chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));

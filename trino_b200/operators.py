@@ -671,6 +671,82 @@ class HashSemiJoinOperatorFactory(OperatorFactory):
 
 
 # ---- partitioned output -----------------------------------------------------------------------------
+class ColumnDomain:
+    """One column's Domain of a dynamic filter's TupleDomain (S/predicate/Domain.java): nullAllowed + a value set.
+    Constructors mirror the reference's factories: all / none / only_null / single_value / multiple_values / range (end exclusive,
+    like Range.range(type, lo, true, hi, false) in the reference's tests)."""
+
+    def __init__(self, channel, kind, null_allowed=False, lo=0, hi=0, values=None):
+        self.channel, self.kind, self.null_allowed, self.lo, self.hi, self.values = channel, kind, null_allowed, lo, hi, values
+
+    @staticmethod
+    def all(channel):
+        return ColumnDomain(channel, abi.DOMAIN_ALL, True)
+
+    @staticmethod
+    def none(channel):
+        return ColumnDomain(channel, abi.DOMAIN_NONE, False)
+
+    @staticmethod
+    def only_null(channel):
+        return ColumnDomain(channel, abi.DOMAIN_NONE, True)
+
+    @staticmethod
+    def single_value(channel, value, null_allowed=False):
+        return ColumnDomain(channel, abi.DOMAIN_DISCRETE, null_allowed, values=[value])
+
+    @staticmethod
+    def multiple_values(channel, values, null_allowed=False):
+        return ColumnDomain(channel, abi.DOMAIN_DISCRETE, null_allowed, values=list(values))
+
+    @staticmethod
+    def range(channel, lo, hi_exclusive, null_allowed=False):
+        return ColumnDomain(channel, abi.DOMAIN_RANGE, null_allowed, lo=lo, hi=hi_exclusive - 1)
+
+
+class DynamicFilterOperator(Operator):
+    def update(self, domains):
+        arr, keep = _domains(domains)
+        self.ctx.check(self.ctx.lib.tgpu_dynamic_filter_update(self.h, C.cast(arr, C.c_void_p), len(domains)))
+
+    def is_effective(self, index):
+        v = C.c_int32()
+        self.ctx.check(self.ctx.lib.tgpu_dynamic_filter_is_effective(self.h, index, C.byref(v)))
+        return bool(v.value)
+
+
+def _domains(domains):
+    arr = (abi.Domain * max(1, len(domains)))()
+    keep = []
+    for i, d in enumerate(domains):
+        arr[i].channel, arr[i].null_allowed, arr[i].kind = d.channel, int(d.null_allowed), d.kind
+        arr[i].min, arr[i].max = d.lo, d.hi
+        if d.values is not None:
+            vals = (C.c_int64 * len(d.values))(*d.values)
+            keep.append(vals)
+            arr[i].num_values = len(d.values)
+            arr[i].values = C.cast(vals, C.POINTER(C.c_int64))
+    return arr, keep
+
+
+class DynamicFilterOperatorFactory(OperatorFactory):
+    """DynamicPageFilter (M/sql/gen/columnar/DynamicPageFilter.java:47-211) as an operator in front of the probe: drops the rows the
+    build side's key domain rules out.  `domains`: ColumnDomains in evaluation order; none = TupleDomain.all()."""
+
+    def __init__(self, ctx, domains, selectivity_threshold=1.0):
+        super().__init__()
+        self.ctx, self.domains, self.threshold = ctx, list(domains), selectivity_threshold
+
+    def _create(self):
+        arr, keep = _domains(self.domains)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.tgpu_dynamic_filter_create(self.ctx.h, C.cast(arr, C.c_void_p), len(self.domains), self.threshold, C.byref(h)))
+        return DynamicFilterOperator(self.ctx, h)
+
+    def duplicate(self):
+        return DynamicFilterOperatorFactory(self.ctx, self.domains, self.threshold)
+
+
 class PartitionedOutputOperator(Operator):
     def get_output_with_partition(self):
         """(partition, Page) or None — the OutputBuffer.enqueue(partition, pages) call of PagePartitioner.java:484-487"""
