@@ -7,3 +7,4 @@ python tools/bench_agg_only.py 150000000 1000000 > gpurun_out/r2i/agg_1m.log 2>&
 python tools/bench_agg_only.py 150000000 100000 > gpurun_out/r2i/agg_100k.log 2>&1; cat gpurun_out/r2i/agg_100k.log
 python bench.py --no-cpu-baseline --no-e2e --no-shuffled --no-groupby-bigint > gpurun_out/r2i/bench_q1.json 2> gpurun_out/r2i/bench_q1.err; tail -2 gpurun_out/r2i/bench_q1.err
 python -m pytest tests/test_gpu_groupby.py -m gpu -q --timeout 900 -k "varchar" > gpurun_out/r2i/pytest.log 2>&1; tail -3 gpurun_out/r2i/pytest.log
+python -m pytest tests/test_gpu_dynamic_filter.py -m gpu -q --timeout 900 > gpurun_out/r2i/pytest_df.log 2>&1; tail -15 gpurun_out/r2i/pytest_df.log | cut -c1-250

@@ -443,64 +443,83 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
     constexpr int R = TGD_G_ROWS;
     const unsigned long long mask = (unsigned long long)cap - 1;
     const int way = (threadIdx.x + blockIdx.x * 7) & (TGD_TICKET_WAYS - 1);
+    const int lane = threadIdx.x & 31;
     unsigned int err = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * R) {
+    // the loop is uniform per warp (every lane makes the same trips) so that the warp can re-converge explicitly between the phases:
+    // measured on the first version, the divergent tail of the probe loop ran the stamp + accumulator code with ~7 of 32 lanes active
+    for (long long wbase = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); wbase < n; wbase += stride * R) {
         typename P::Regs regs[R];
         long long row[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {
-            long long i = base + (long long)j * stride;
+            long long i = wbase + lane + (long long)j * stride;
             row[j] = i < n ? (rows ? (long long)rows[i] : first + i) : -1;
             if (row[j] >= 0) prog.load(cols, row[j], regs[j]);
         }
         unsigned long long pk[R], pos[R], cur[R];
-        int sp[R];
+        long long slot[R];
+        bool open[R];        // still looking for its slot
 #pragma unroll
         for (int j = 0; j < R; j++) {
             pk[j] = 0;
-            sp[j] = -1;
-            if (row[j] >= 0 && !prog.row(regs[j], &pk[j], &sp[j], &err)) row[j] = -1;      // rejected by the fused filter
+            int sp = -1;
+            if (row[j] >= 0 && !prog.row(regs[j], &pk[j], &sp, &err)) row[j] = -1;      // rejected by the fused filter
             pos[j] = tgd_murmur3_mix(pk[j]) & mask;
+            slot[j] = (row[j] >= 0 && sp >= 0) ? cap + sp : -1;
+            open[j] = row[j] >= 0 && sp < 0;
         }
 #pragma unroll
-        for (int j = 0; j < R; j++)
-            cur[j] = (row[j] >= 0 && sp[j] < 0) ? *((volatile unsigned long long*)(recs + (size_t)pos[j] * W)) : 0;
+        for (int j = 0; j < R; j++) cur[j] = open[j] ? *((volatile unsigned long long*)(recs + (size_t)pos[j] * W)) : 0;
+        // lock-step probing: one step of every open row per trip, the warp stays converged
+        while (true) {
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                if (!open[j]) continue;
+                unsigned long long c = cur[j];
+                if (c == TGD_EMPTY_KEY) {
+                    if (atomicAdd(tickets + way, 1) >= budget_per_way) { atomicSub(tickets + way, 1); open[j] = false; continue; }   // no room: deferred below
+                    c = atomicCAS(recs + (size_t)pos[j] * W, TGD_EMPTY_KEY, pk[j]);
+                    if (c == TGD_EMPTY_KEY) { slot[j] = (long long)pos[j]; open[j] = false; continue; }
+                    atomicSub(tickets + way, 1);       // lost the race for the slot: the claim was not consumed
+                }
+                if (c == pk[j]) { slot[j] = (long long)pos[j]; open[j] = false; continue; }
+                pos[j] = (pos[j] + 1) & mask;
+                cur[j] = *((volatile unsigned long long*)(recs + (size_t)pos[j] * W));
+                any = true;
+            }
+            if (!__any_sync(0xffffffffu, any)) break;
+        }
+        __syncwarp();
+        // stamps: read the R stamps first, lower the ones that need it
+        long long stamp[R], seen[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            stamp[j] = 0;
+            seen[j] = 0;
+            if (row[j] >= 0 && slot[j] >= 0) {
+                stamp[j] = page_base + (stamp_rows ? (long long)stamp_rows[row[j]] : row[j]);
+                seen[j] = *((volatile long long*)(recs + (size_t)slot[j] * W + 1));
+            }
+        }
 #pragma unroll
         for (int j = 0; j < R; j++) {
             if (row[j] < 0) continue;
-            long long s = -1;
-            if (sp[j] >= 0) s = cap + sp[j];
-            else {
-                unsigned long long p = pos[j], c = cur[j];
-                bool have_ticket = false;
-                while (true) {
-                    unsigned long long* kp = recs + (size_t)p * W;
-                    if (c == TGD_EMPTY_KEY) {
-                        if (!have_ticket) {
-                            if (atomicAdd(tickets + way, 1) >= budget_per_way) { atomicSub(tickets + way, 1); break; }
-                            have_ticket = true;
-                        }
-                        c = atomicCAS(kp, TGD_EMPTY_KEY, pk[j]);
-                        if (c == TGD_EMPTY_KEY) { s = (long long)p; have_ticket = false; break; }
-                    }
-                    if (c == pk[j]) { s = (long long)p; break; }
-                    p = (p + 1) & mask;
-                    c = *((volatile unsigned long long*)(recs + (size_t)p * W));
-                }
-                if (have_ticket) atomicSub(tickets + way, 1);
+            if (slot[j] < 0) { deferred[atomicAdd(tickets + TGD_TICKET_WAYS, 1)] = (int)row[j]; continue; }
+            if (seen[j] > stamp[j]) {
+                long long old = atomicMin((long long*)(recs + (size_t)slot[j] * W + 1), stamp[j]);
+                if (old == TGD_NO_ROW && slot[j] >= cap) atomicAdd(tickets + TGD_TICKET_WAYS + 1, 1);   // a special (NULL / sentinel key) group came to life
             }
-            if (s < 0) { deferred[atomicAdd(tickets + TGD_TICKET_WAYS, 1)] = (int)row[j]; continue; }
-            unsigned long long* r = recs + (size_t)s * W;
-            const long long stamp = page_base + (stamp_rows ? (long long)stamp_rows[row[j]] : row[j]);
-            if (*((volatile long long*)(r + 1)) > stamp) {
-                long long old = atomicMin((long long*)(r + 1), stamp);
-                if (old == TGD_NO_ROW && s >= cap) atomicAdd(tickets + TGD_TICKET_WAYS + 1, 1);   // a special (NULL / sentinel key) group came to life
-            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (row[j] < 0 || slot[j] < 0) continue;
             unsigned long long pk2;
             int sp2;
             prog.row(regs[j], &pk2, &sp2, &err);          // re-establish this row's values (registers only) for the accumulators
-            prog.accumulate_global(r + 2);
+            prog.accumulate_global(recs + (size_t)slot[j] * W + 2);
         }
     }
     if (err) atomicOr(err_out, err);
