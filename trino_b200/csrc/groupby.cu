@@ -1238,7 +1238,7 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
     {
         const char* e = getenv("TGPU_AGG_G_MINB");
         appendf(s, "extern \"C\" __global__ void __launch_bounds__(256, %d) tg_agg_general_jit(DColumns cols, long long n, const int* rows, long long first, const int* stamp_rows,\n",
-                e ? atoi(e) : 3);
+                e ? atoi(e) : 2);
     }
     s += ""
          "    long long page_base, unsigned long long* recs, long long cap, int W, int* tickets, int budget_per_way, int* deferred, unsigned int* err_out) {\n"
@@ -1840,7 +1840,7 @@ struct AggOp : tgpu_op {
         int64_t want = expected_groups > 0 ? expected_groups : 1024;
         int64_t cap = 1 << 16;
         const char* e_load = getenv("TGPU_AGG_G_SIZE_PCT");     // initial sizing only: the fill limit stays 3/4 (tryRehash)
-        const int64_t pct = e_load ? atoi(e_load) : 75;
+        const int64_t pct = e_load ? atoi(e_load) : 50;     // probe sequences (and the warp-wide lock step over them) are short at <= 1/2 full
         while (cap * pct / 100 < want + group_count) cap <<= 1;
         if (cap > (1LL << 30)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "Size of hash table cannot exceed 1 billion entries");
         TG_TRY(gf_alloc(cap, &f_recs));

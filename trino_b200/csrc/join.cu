@@ -533,6 +533,160 @@ __global__ void __launch_bounds__(256, MINB) join_probe_lean_kernel(const long l
     }
 }
 
+// ---- TMA-staged probe for order-preserving tables (mode 2) ----------------------------------------------------------------
+// With order-preserving lines a tile of probe keys that arrives in key order (TPC-H clustering; each sender's run after a stable
+// exchange) needs ONE contiguous span of table lines.  The CTA computes the span of its 1024 keys, one elected thread stages the span -
+// the 16-byte slots and, for the common single-BIGINT-payload shape, the slot-ordered payload next to them - into shared memory with
+// cp.async.bulk (TMA bulk copy, completion on an mbarrier), and every thread then resolves its four rows against shared memory:
+// one bulk copy of full 128-byte lines replaces ~2 x 1024 scattered 16 / 8-byte loads.  A tile whose span does not fit (shuffled keys, keys
+// outside the build range) takes the direct path of the lean kernel; a row whose line walk leaves the staged span falls back to global
+// loads for its remaining steps.
+constexpr int SPAN_LINES = 80;            // table lines staged per tile: 10 KB of slots + 5 KB of payload
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TG_DONE_%=;\n"
+        "bra TG_WAIT_%=;\n"
+        "TG_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(256, 6) join_probe_span_kernel(const long long* __restrict__ keys, int64_t tiles, const int4* __restrict__ table, unsigned int mask,
+                                                                unsigned long long kmin, int shift, int special_head, int* __restrict__ out, GatherCols g,
+                                                                unsigned long long* __restrict__ match_count)
+{
+    __shared__ __align__(128) int4 s_slots[SPAN_LINES * 8];
+    __shared__ __align__(128) long long s_pay[SPAN_LINES * 8];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned int s_min[8], s_max[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned int line_mask = mask >> 3;
+    // the slot-ordered single 8-byte payload is staged next to the slots; other payload shapes are read from global memory
+    const bool stage_pay = GATHER && g.by_slot && g.count == 1 && g.elem[0] == 8;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    unsigned int phase = 0;
+    unsigned int matched = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t base = t * 1024 + threadIdx.x;
+        unsigned long long k[4];
+        unsigned int pos[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = (unsigned long long)__ldg(keys + base + j * 256);
+        unsigned int lo = 0xffffffffu, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            pos[j] = lean_slot<2>(k[j], mask, kmin, shift);
+            const unsigned int line = pos[j] >> 3;
+            lo = min(lo, line);
+            hi = max(hi, line);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_min[warp] = lo; s_max[warp] = hi; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < 8; w++) { lo = min(lo, s_min[w]); hi = max(hi, s_max[w]); }
+        // one extra line behind the span for line walks that overflow their home line
+        const unsigned int first_line = lo, lines = min(hi + 1u, line_mask) - lo + 1u;
+        const bool staged = lines <= (unsigned int)SPAN_LINES;
+        if (staged) {
+            if (threadIdx.x == 0) {
+                const unsigned int slot_bytes = lines * 128u, pay_bytes = stage_pay ? lines * 64u : 0u;
+                mbar_expect_tx(&bar, slot_bytes + pay_bytes);
+                bulk_g2s(s_slots, table + (size_t)first_line * 8, slot_bytes, &bar);
+                if (stage_pay) bulk_g2s(s_pay, (const long long*)g.src[0] + (size_t)first_line * 8, pay_bytes, &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        }
+        const unsigned int first_slot = first_line << 3, staged_slots = staged ? lines << 3 : 0u;
+        int res[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned int klo = (unsigned int)k[j], khi = (unsigned int)(k[j] >> 32);
+            int r = -1;
+            unsigned int p = pos[j];
+            while (true) {
+                const unsigned int local = p - first_slot;
+                const int4 cur = local < staged_slots ? s_slots[local] : __ldg(table + p);
+                if ((unsigned int)cur.x == klo && (unsigned int)cur.y == khi) { r = cur.z; break; }
+                if (cur.x == 0 && cur.y == (int)0x80000000) break;                 // EMPTY_KEY
+                p = lean_next<2>(p, klo & 7u, mask);
+            }
+            if (k[j] == EMPTY_KEY) { r = special_head; p = mask + 1u; }
+            res[j] = r;
+            pos[j] = p;
+        }
+        if (GATHER) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (c >= g.count) break;
+                if (g.elem[c] == 8) {
+                    long long v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const unsigned int local = pos[j] - first_slot;
+                        if (res[j] < 0) v[j] = 0;
+                        else if (stage_pay && local < staged_slots) v[j] = s_pay[local];
+                        else v[j] = __ldg((const long long*)g.src[c] + (g.by_slot ? (long long)pos[j] : (long long)res[j]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ((long long*)g.dst[c])[base + j * 256] = v[j];
+                }
+                else if (g.elem[c] == 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        ((int*)g.dst[c])[base + j * 256] = res[j] >= 0 ? __ldg((const int*)g.src[c] + (g.by_slot ? (long long)pos[j] : (long long)res[j])) : 0;
+                }
+                else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        long long at = g.by_slot ? (long long)pos[j] : (long long)res[j];
+                        if (g.elem[c] == 2) ((short*)g.dst[c])[base + j * 256] = res[j] >= 0 ? ((const short*)g.src[c])[at] : (short)0;
+                        else ((signed char*)g.dst[c])[base + j * 256] = res[j] >= 0 ? ((const signed char*)g.src[c])[at] : (signed char)0;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            out[base + j * 256] = res[j];
+            if (GATHER) matched += res[j] >= 0;
+        }
+        __syncthreads();          // everyone is done with the staged span (and s_min / s_max) before the next tile overwrites them
+    }
+    if (GATHER) {
+        for (int off = 16; off > 0; off >>= 1) matched += __shfl_xor_sync(0xffffffffu, matched, off);
+        if (lane == 0 && matched) atomicAdd(match_count, (unsigned long long)matched);
+    }
+}
+
 // launch of the lean probe kernel for the table's layout mode
 template <bool GATHER>
 static int launch_lean(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys, int64_t tiles, const int4* table, int special_head, int* out, const GatherCols& g,
@@ -540,7 +694,11 @@ static int launch_lean(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys
 {
     const unsigned int mask32 = (unsigned int)geo.mask;
     // 8 CTAs per SM (32 registers): full occupancy is worth more than the registers (measured 4.9 -> 3.4 ms at SF100)
-    if (geo.mode == 2) {
+    if (geo.mode == 2 && !getenv("TGPU_JOIN_NO_SPAN")) {
+        auto k = join_probe_span_kernel<GATHER>;       // TMA-staged table spans (falls back per tile when the keys are not clustered)
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, table, mask32, geo.kmin, geo.shift, special_head, out, g, matches);
+    }
+    else if (geo.mode == 2) {
         auto k = join_probe_lean_kernel<2, GATHER, 8>;
         TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, table, mask32, geo.kmin, geo.shift, special_head, out, g, matches);
     }
@@ -958,21 +1116,20 @@ struct JoinBuildOp : tgpu_op {
             int64_t need = (int64_t)((double)rows / lf) + 1;
             cap = 8;   // at least one 8-slot line
             while (cap < need) cap <<= 1;
-            // line layouts (modes 1 / 2) want lines at most about half full (measured: exp_join_summary in profiles/)
+            // line layouts (modes 1 / 2) want lines at most about half full (measured: exp_join_summary in profiles/), unless the keys
+            // fill their lines evenly: candidates are tried in this order, each judged by the rows that had to leave their home line
+            //   mode 2, base capacity  : "dense" - e.g. TPC-H order keys: every line of 32 key values holds exactly its 8 keys
+            //   mode 2, 2 x capacity   : a line expects ~4 keys (random subsets of a dense domain: what a hash exchange leaves on a rank)
+            //   mode 1, 2 x capacity   : scattered lines, any distribution
             const char* env_mode = getenv("TGPU_JOIN_HASH");
             const DevColumn& bkey = lk->store.cols[0];
             const bool int_key = !lk->generic && key_kind_of(bkey.type) == KEY_INT;
             int hash_mode = env_mode ? atoi(env_mode) : (int_key && rows > 0 ? 2 : 1);
             if (hash_mode == 2 && !(int_key && rows > 0)) hash_mode = 1;
             const char* env_shift = getenv("TGPU_JOIN_CAP_SHIFT");
-            int cap_shift = env_shift ? atoi(env_shift) : (hash_mode ? 1 : 0);
-            cap <<= cap_shift;
-            if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
-            lk->geo.mask = (unsigned long long)cap - 1;
-            lk->geo.kmin = 0;
-            lk->geo.shift = 0;
+            const int64_t base_cap = cap;
+            unsigned long long span = 0, kmin = 0;
             if (hash_mode == 2) {
-                // order-preserving lines: the key range [kmin, kmax] is cut into cap / 8 lines of 2^shift key values
                 long long* d_range = (long long*)(ctx->d_scratch + 24);
                 long long init_range[2] = {INT64_MAX, INT64_MIN};
                 TG_CUDA(ctx, cudaMemcpyAsync(d_range, init_range, sizeof(init_range), cudaMemcpyHostToDevice, ctx->stream));
@@ -982,19 +1139,31 @@ struct JoinBuildOp : tgpu_op {
                 TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 if (h_range[0] > h_range[1]) hash_mode = 1;      // no insertable key at all
                 else {
-                    const unsigned long long span = (unsigned long long)h_range[1] - (unsigned long long)h_range[0];   // kmax - kmin, exact in 64 bits
+                    span = (unsigned long long)h_range[1] - (unsigned long long)h_range[0];   // kmax - kmin, exact in 64 bits
+                    kmin = (unsigned long long)h_range[0];
+                }
+            }
+            int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag, [2] rows off their home line, [3] rows more than 8 lines off
+            // attempt 0: dense mode 2; attempt 1: roomy mode 2; attempt 2: mode 1 (or whatever the environment pinned)
+            for (int attempt = (hash_mode == 2 && !env_shift && !getenv("TGPU_JOIN_NO_DENSE")) ? 0 : 1; ; attempt++) {
+                if (hash_mode == 2 && attempt >= 2) hash_mode = 1;
+                const int cap_shift = env_shift ? atoi(env_shift) : (hash_mode == 0 ? 0 : (hash_mode == 2 && attempt == 0) ? 0 : 1);
+                cap = base_cap << cap_shift;
+                if (cap > (1LL << 31)) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "hash array too large");
+                lk->geo.mask = (unsigned long long)cap - 1;
+                lk->geo.kmin = 0;
+                lk->geo.shift = 0;
+                if (hash_mode == 2) {
+                    // order-preserving lines: the key range [kmin, kmax] is cut into cap / 8 lines of 2^shift key values
                     const unsigned long long lines = (unsigned long long)cap >> 3;
                     int shift = 0;
                     while (shift < 63 && (span >> shift) >= lines) shift++;
-                    if ((span >> shift) >= lines) hash_mode = 1;  // a span of 2^63 or more over very few lines: not worth a special case
-                    lk->geo.kmin = (unsigned long long)h_range[0];
+                    if ((span >> shift) >= lines) { hash_mode = 1; attempt = 1; continue; }   // a span of 2^63 or more over very few lines
+                    lk->geo.kmin = kmin;
                     lk->geo.shift = shift;
                 }
-            }
-            TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
-            int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag, [2] rows off their home line, [3] rows more than 8 lines off
-            while (true) {
                 lk->geo.mode = hash_mode;
+                TG_TRY(lk->table.alloc(ctx, (size_t)cap * sizeof(JoinSlot)));
                 TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
                 int init[4] = {-1, 0, 0, 0};
                 TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
@@ -1003,13 +1172,12 @@ struct JoinBuildOp : tgpu_op {
                               lk->table.as<JoinSlot>(), lk->geo, d_flags, d_flags + 1, (unsigned int*)(d_flags + 2));
                 }
                 if (hash_mode != 2) break;
-                // mode 2 relies on the keys spreading evenly over their range; clustered domains pile up in a few lines.  More than
-                // 1/8 of the rows off their home line, or any row further than 8 lines away: rebuild with scattered lines (mode 1)
+                // mode 2 relies on the keys spreading evenly over their range; clustered domains pile up in a few lines.  Dense: at most
+                // 1/64 of the rows off their home line; roomy: at most 1/8; and (nearly) no row further than 8 lines away
                 int64_t moved = 0;
                 TG_TRY(tg_read_i64(ctx, d_flags + 2, &moved));
                 const int64_t off_home = moved & 0xFFFFFFFFLL, far = (moved >> 32) & 0xFFFFFFFFLL;
-                if (off_home * 8 <= rows && far * 1024 <= rows) break;
-                hash_mode = 1;
+                if (off_home * (attempt == 0 ? 64 : 8) <= rows && far * 1024 <= rows) break;
             }
             int64_t packed = 0;
             TG_TRY(tg_read_i64(ctx, d_flags, &packed));

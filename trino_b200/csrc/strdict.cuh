@@ -153,6 +153,43 @@ __global__ void __launch_bounds__(256) sd_lookup_kernel(const int32_t* __restric
     }
 }
 
+// first tier for columns of very short strings (VARCHAR(1) flags, status codes): strings of length <= 1 resolve through a 257-entry direct
+// map (byte value, or 256 for the empty string) held in shared memory - offsets + byte in, id out, ~20 instructions per row.  A longer
+// or yet unmapped string flags its chunk for the general lookup / insert path.
+__global__ void __launch_bounds__(256) sd_lookup_direct_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ bytes, const uint8_t* __restrict__ validity,
+                                                              int64_t first, int64_t n, const int32_t* __restrict__ direct, int32_t* __restrict__ ids,
+                                                              int64_t chunk_rows, int* __restrict__ chunk_miss)
+{
+    __shared__ int32_t map[257];
+    for (int i = threadIdx.x; i < 257; i += blockDim.x) map[i] = direct[i];
+    __syncthreads();
+    constexpr int R = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * R) {
+        int off[R], len[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int64_t i = base + (int64_t)j * stride;
+            off[j] = 0; len[j] = -1;
+            if (i < n) { off[j] = __ldg(offsets + first + i); len[j] = __ldg(offsets + first + i + 1) - off[j]; }
+        }
+        int code[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) code[j] = len[j] == 1 ? (int)__ldg(bytes + off[j]) : 256;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int64_t i = base + (int64_t)j * stride;
+            if (i >= n) continue;
+            int id = 0;
+            if (tg_valid(validity, first + i)) {
+                id = len[j] <= 1 ? map[code[j]] : -1;
+                if (id < 0) { chunk_miss[i / chunk_rows] = 1; id = 0; }
+            }
+            ids[first + i] = id;
+        }
+    }
+}
+
 // long strings only: compare the row's bytes with its slot's string; rows that differ go to `retry` with attempt + 1
 __global__ void __launch_bounds__(256) sd_verify_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ bytes, const int* __restrict__ rows, int64_t n,
                                                        uint8_t* __restrict__ attempt, const StrSlot* __restrict__ table, const int* __restrict__ slot_of_row,
@@ -201,7 +238,7 @@ __global__ void __launch_bounds__(256) sd_count_new_kernel(const int32_t* __rest
 __global__ void __launch_bounds__(256) sd_assign_kernel(const int32_t* __restrict__ offsets, const uint8_t* __restrict__ bytes, int64_t n, StrSlot* __restrict__ table,
                                                        const int* __restrict__ slot_of_row, int first_id, long long first_byte, int* __restrict__ next_id,
                                                        unsigned long long* __restrict__ next_byte, uint8_t* __restrict__ dict_bytes, long long* __restrict__ dict_start,
-                                                       int* __restrict__ dict_len, unsigned long long* __restrict__ dict_key)
+                                                       int* __restrict__ dict_len, unsigned long long* __restrict__ dict_key, int32_t* __restrict__ direct)
 {
     int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -217,6 +254,7 @@ __global__ void __launch_bounds__(256) sd_assign_kernel(const int32_t* __restric
         dict_len[id] = len;
         dict_key[id] = table[s].key;
         table[s].id = id;
+        if (len <= 1) direct[len == 1 ? (int)bytes[off] : 256] = id;
     }
 }
 
@@ -270,13 +308,19 @@ struct StringDict {
     DevBuf table;
     int64_t cap = 0;
     DevBuf bytes, start, len, key;           // the store: bytes, and per id: first byte, length, table key (for rehashing)
+    DevBuf direct;                           // int32[257]: id of every string of length <= 1 (byte value / 256 = empty), -1 = not in the dictionary
     int64_t bytes_cap = 0, bytes_used = 0, ids_cap = 0, count = 0;
+    bool has_direct = false;                 // some string of length <= 1 was ever inserted (the direct map can answer something)
 
     explicit StringDict(tgpu_ctx* c) : ctx(c) {}
     int64_t memory_bytes() const { return (int64_t)(table.bytes + bytes.bytes + start.bytes + len.bytes + key.bytes); }
 
     int alloc_table(int64_t slots)
     {
+        if (!direct.p) {
+            TG_TRY(direct.alloc(ctx, 257 * 4));
+            TG_CUDA(ctx, cudaMemsetAsync(direct.p, 0xFF, 257 * 4, ctx->stream));
+        }
         DevBuf t;
         TG_TRY(t.alloc(ctx, (size_t)slots * sizeof(StrSlot)));
         TG_LAUNCH(ctx, sd_init_kernel, tg_grid(ctx, slots, 1024, 8), 256, 0, t.as<StrSlot>(), slots);
@@ -322,9 +366,23 @@ struct StringDict {
             TG_TRY(miss.alloc(ctx, (size_t)chunks * 4));
             TG_CUDA(ctx, cudaMemsetAsync(miss.p, 0, (size_t)chunks * 4, ctx->stream));
             if (cap == 0) TG_TRY(alloc_table(1 << 12));
-            TG_LAUNCH(ctx, sd_lookup_kernel, tg_grid(ctx, rest, 1024, 6), 256, 0, col.offsets, (const uint8_t*)col.data, col.validity, head, rest, table.as<StrSlot>(),
-                      (unsigned long long)cap - 1, bytes.as<uint8_t>(), start.as<long long>(), len.as<int>(), d_ids, CHUNK, miss.as<int>());
             std::vector<int> h_miss((size_t)chunks);
+            // tier 1: the direct map of strings of length <= 1 (tried when the dictionary holds such strings at all)
+            bool tier1 = has_direct;
+            if (tier1) {
+                TG_LAUNCH(ctx, sd_lookup_direct_kernel, tg_grid(ctx, rest, 1024, 8), 256, 0, col.offsets, (const uint8_t*)col.data, col.validity, head, rest,
+                          direct.as<int32_t>(), d_ids, CHUNK, miss.as<int>());
+                TG_CUDA(ctx, cudaMemcpyAsync(h_miss.data(), miss.p, (size_t)chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            // tier 2: the table lookup, for the chunks tier 1 could not finish (all of them without tier 1); tier 3: the insert path
+            for (int64_t c = 0; c < chunks; c++) {
+                if (tier1 && !h_miss[c]) continue;
+                const int64_t lo = head + c * CHUNK, cnt = std::min<int64_t>(CHUNK, n - lo);
+                TG_CUDA(ctx, cudaMemsetAsync(miss.as<int>() + c, 0, 4, ctx->stream));
+                TG_LAUNCH(ctx, sd_lookup_kernel, tg_grid(ctx, cnt, 1024, 6), 256, 0, col.offsets, (const uint8_t*)col.data, col.validity, lo, cnt, table.as<StrSlot>(),
+                          (unsigned long long)cap - 1, bytes.as<uint8_t>(), start.as<long long>(), len.as<int>(), d_ids, CHUNK, miss.as<int>() + c);
+            }
             TG_CUDA(ctx, cudaMemcpyAsync(h_miss.data(), miss.p, (size_t)chunks * 4, cudaMemcpyDeviceToHost, ctx->stream));
             TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             for (int64_t c = 0; c < chunks; c++)
@@ -416,8 +474,14 @@ struct StringDict {
             }
             TG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
             TG_LAUNCH(ctx, sd_assign_kernel, grid, 256, 0, offs, data, n, table.as<StrSlot>(), slot_of_row.as<int>(), (int)count, (long long)bytes_used, d_cnt,
-                      (unsigned long long*)(d_cnt + 2), bytes.as<uint8_t>(), start.as<long long>(), len.as<int>(), key.as<unsigned long long>());
+                      (unsigned long long*)(d_cnt + 2), bytes.as<uint8_t>(), start.as<long long>(), len.as<int>(), key.as<unsigned long long>(), direct.as<int32_t>());
             count += fresh;
+            if (!has_direct) {      // did a string of length <= 1 arrive?  (tier 1 of encode() is only worth a pass then)
+                std::vector<int32_t> h_direct(257);
+                TG_CUDA(ctx, cudaMemcpyAsync(h_direct.data(), direct.p, 257 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (int32_t v : h_direct) has_direct = has_direct || v >= 0;
+            }
             bytes_used += fresh_bytes;
         }
         TG_LAUNCH(ctx, sd_ids_kernel, grid, 256, 0, n, table.as<StrSlot>(), slot_of_row.as<int>(), d_ids);
