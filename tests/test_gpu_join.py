@@ -346,15 +346,18 @@ def test_build_side_key_domain(ctx):
     b.close()
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2", None])
+@pytest.mark.parametrize("mode", ["0", "1", "2", None, "span", "roomy"])
 @pytest.mark.parametrize("shape", ["tpch", "every_8th", "clustered", "extremes", "shuffled_probe"])
 def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
     """Slot placement is not observable: mix(key) (mode 0, M/operator/join/PagesHash.java:35-51), line-local (1) and order-preserving
     lines (2, the default for integer keys; falls back to 1 when the keys pile up in a few lines) give the oracle's positions for dense,
     strided (what a hash exchange leaves on one rank), clustered and extreme key sets."""
-    if mode is None:
-        monkeypatch.delenv("TGPU_JOIN_HASH", raising=False)
-    else:
+    monkeypatch.delenv("TGPU_JOIN_HASH", raising=False)
+    if mode == "span":
+        monkeypatch.setenv("TGPU_JOIN_SPAN", "1")          # the TMA-staged (cp.async.bulk + mbarrier) probe kernel
+    elif mode == "roomy":
+        monkeypatch.setenv("TGPU_JOIN_NO_DENSE", "1")      # skip the dense geometry attempt
+    elif mode is not None:
         monkeypatch.setenv("TGPU_JOIN_HASH", mode)
     rng = np.random.default_rng(11)
     n_orders = 100_000

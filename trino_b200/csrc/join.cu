@@ -694,8 +694,11 @@ static int launch_lean(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys
 {
     const unsigned int mask32 = (unsigned int)geo.mask;
     // 8 CTAs per SM (32 registers): full occupancy is worth more than the registers (measured 4.9 -> 3.4 ms at SF100)
-    if (geo.mode == 2 && !getenv("TGPU_JOIN_NO_SPAN")) {
-        auto k = join_probe_span_kernel<GATHER>;       // TMA-staged table spans (falls back per tile when the keys are not clustered)
+    if (geo.mode == 2 && getenv("TGPU_JOIN_SPAN")) {
+        // TMA-staged table spans (falls back per tile when the keys are not clustered).  Opt-in: measured 9 % SLOWER than the lean kernel on
+        // the SF100 workload (2.73 vs 2.50 ms) - with the dense table the lean kernel already moves its 15.6 GB at 0.95 of the measured copy
+        // bandwidth, and the span kernel pays a block-wide span reduction plus a second dependent DRAM round trip per tile
+        auto k = join_probe_span_kernel<GATHER>;
         TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, table, mask32, geo.kmin, geo.shift, special_head, out, g, matches);
     }
     else if (geo.mode == 2) {
