@@ -248,7 +248,28 @@ typedef struct tgpu_agg_spec {
     int32_t group_id_key;
     int32_t num_input_channels;
     const int32_t* input_channel_types;
+    /* adaptive partial aggregation (PARTIAL / INTERMEDIATE steps only, else INVALID_ARGUMENT - the reference's
+       checkArgument at M/operator/HashAggregationOperator.java:296).  When the shared controller says partial aggregation is
+       disabled at the moment a new aggregation builder would be created (:358-372), the operator runs that builder as a
+       SkipAggregationBuilder (M/operator/aggregation/partial/SkipAggregationBuilder.java:103-131): add_input takes ONE page,
+       needs_input turns false, get_output returns one page of the same row count - the key channels passed through, and per
+       aggregate the intermediate state of a group that holds just that row.  NULL = no controller.  Not owned by the operator. */
+    struct tgpu_partial_agg_controller* partial_aggregation_controller;
 } tgpu_agg_spec;
+
+/* PartialAggregationController (M/operator/aggregation/partial/PartialAggregationController.java:35-103): one per plan node
+ * and task, shared by that node's drivers; thread-safe.  Partial aggregation is switched off once at least
+ * 1.5 x max_partial_memory_bytes of input were aggregated and unique rows / input rows exceeds the threshold, and switched back
+ * on (counters reset) after 300 x max_partial_memory_bytes of input.  The operators call on_flush themselves
+ * (HashAggregationOperator.closeAggregationBuilder :512-523); the entry point is public for callers that mix CPU and GPU
+ * drivers under one controller.  unique_rows_produced < 0 stands for OptionalLong.empty() (a skipped builder). Needs no GPU. */
+typedef struct tgpu_partial_agg_controller tgpu_partial_agg_controller;
+int tgpu_partial_agg_controller_create(int64_t max_partial_memory_bytes, double unique_rows_ratio_threshold, tgpu_partial_agg_controller** out);
+void tgpu_partial_agg_controller_destroy(tgpu_partial_agg_controller* controller);
+int tgpu_partial_agg_controller_is_disabled(const tgpu_partial_agg_controller* controller);
+void tgpu_partial_agg_controller_on_flush(tgpu_partial_agg_controller* controller, int64_t bytes_processed, int64_t rows_processed, int64_t unique_rows_produced);
+/* AggregationMetrics.recordInputRowsProcessedWithPartialAggregationDisabled: rows this operator passed through un-aggregated */
+int tgpu_agg_rows_with_partial_aggregation_disabled(tgpu_op* op, int64_t* out);
 
 int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op** out);
 /* diagnostics (needs no GPU): generate the kernel specialised for `spec` over input channels of the given tgpu_types

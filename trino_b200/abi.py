@@ -111,6 +111,7 @@ class AggSpec(C.Structure):
         ("group_id_key", C.c_int32),
         ("num_input_channels", C.c_int32),
         ("input_channel_types", C.POINTER(C.c_int32)),
+        ("partial_aggregation_controller", C.c_void_p),
     ]
 
 
@@ -181,6 +182,11 @@ SIGNATURES = {
     "tgpu_filter_project_create": (C.c_int, [VP, C.POINTER(ExprProgram), C.POINTER(VP)]),
     "tgpu_agg_create": (C.c_int, [VP, C.POINTER(AggSpec), C.POINTER(VP)]),
     "tgpu_agg_group_count": (C.c_int, [VP, C.POINTER(C.c_int64)]),
+    "tgpu_agg_rows_with_partial_aggregation_disabled": (C.c_int, [VP, C.POINTER(C.c_int64)]),
+    "tgpu_partial_agg_controller_create": (C.c_int, [C.c_int64, C.c_double, C.POINTER(VP)]),
+    "tgpu_partial_agg_controller_destroy": (None, [VP]),
+    "tgpu_partial_agg_controller_is_disabled": (C.c_int, [VP]),
+    "tgpu_partial_agg_controller_on_flush": (None, [VP, C.c_int64, C.c_int64, C.c_int64]),
     "tgpu_jit_selftest_filter_project": (C.c_int, [C.POINTER(ExprProgram), C.POINTER(C.c_int32), C.c_int32, C.c_uint32, C.POINTER(C.c_int64), C.c_char_p, C.c_int64]),
     "tgpu_jit_selftest_agg": (C.c_int, [C.POINTER(AggSpec), C.POINTER(C.c_int32), C.c_int32, C.c_uint32, C.POINTER(C.c_int64), C.c_char_p, C.c_int64]),
     "tgpu_groupby_hash_create": (C.c_int, [VP, C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(VP)]),

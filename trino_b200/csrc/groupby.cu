@@ -34,6 +34,19 @@
 #include "multisplit.cuh"
 #include "strdict.cuh"
 
+#include <atomic>
+#include <mutex>
+
+// PartialAggregationController (M/operator/aggregation/partial/PartialAggregationController.java:35-103), shared by the drivers of one
+// plan node: a mutex for onFlush, an atomic flag for the readers (the reference's synchronized method + volatile field)
+struct tgpu_partial_agg_controller {
+    std::mutex mu;
+    int64_t max_partial_bytes = 0;
+    double threshold = 0;
+    std::atomic<bool> disabled{false};
+    int64_t total_bytes = 0, total_rows = 0, total_unique = 0;
+};
+
 namespace {
 
 using namespace tg;
@@ -1037,6 +1050,58 @@ __global__ void nullmap_pack_kernel(const unsigned char* __restrict__ is_null, i
     if (seen && any) atomicOr(any, 1u);
 }
 
+// SkipAggregationBuilder.buildOutputPage (M/operator/aggregation/partial/SkipAggregationBuilder.java:103-131): every row is its own
+// group, so the intermediate state of an aggregate is a function of that one row - count: 0/1, sum/min/max: the value or NULL,
+// avg: (0/1, value).  One thread per row, all aggregates in one pass; null bytes are packed into bitmaps by nullmap_pack_kernel.
+#define SKIP_MAX_FNS 24
+struct SkipFn {
+    int32_t function, in_ch, mask_ch, in_is_double;
+    void* out0;
+    unsigned char* null0;      // 1 byte per row (sum / min / max), else null
+    void* out1;                // avg: the DOUBLE sum
+};
+struct SkipSpec {
+    int32_t count;
+    SkipFn f[SKIP_MAX_FNS];
+};
+
+__global__ void __launch_bounds__(256) agg_skip_kernel(DColumns cols, int64_t n, SkipSpec spec)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        for (int a = 0; a < spec.count; a++) {
+            const SkipFn& f = spec.f[a];
+            bool on = true;
+            if (f.mask_ch >= 0) {
+                const ColRef& m = cols.cols[f.mask_ch];
+                on = tg_valid(m.validity, i) && tg_load_i64(m, i) != 0;       // AggregationMask: NULL or false drops the row
+            }
+            long long bits = 0;
+            if (f.in_ch >= 0) {
+                const ColRef& c = cols.cols[f.in_ch];
+                if (!tg_valid(c.validity, i)) on = false;
+                else bits = tg_load_i64(c, i);
+            }
+            switch (f.function) {
+                case TGPU_AGG_COUNT_STAR: case TGPU_AGG_COUNT:
+                    ((long long*)f.out0)[i] = on ? 1 : 0;
+                    break;
+                case TGPU_AGG_AVG: {
+                    ((long long*)f.out0)[i] = on ? 1 : 0;
+                    double v = f.in_is_double ? __longlong_as_double(bits) : (double)bits;
+                    ((double*)f.out1)[i] = on ? v : 0.0;
+                    break;
+                }
+                default:                                                       // sum / min / max: the value itself (raw bits for DOUBLE)
+                    ((long long*)f.out0)[i] = on ? bits : 0;
+                    f.null0[i] = on ? 0 : 1;
+                    break;
+            }
+        }
+    }
+}
+
 #endif  // __CUDACC__
 
 
@@ -1313,11 +1378,19 @@ struct AggOp : tgpu_op {
     std::vector<OwnedPage*> pending;
     size_t next_out = 0;
 
+    // adaptive partial aggregation: one "builder" spans the pages between two flushes (HashAggregationOperator.aggregationBuilder)
+    tgpu_partial_agg_controller* controller = nullptr;
+    bool builder_open = false, skip_mode = false;
+    int64_t builder_bytes = 0, builder_rows = 0, builder_unique = 0;     // aggregationInputBytesProcessed / ...RowsProcessed / ...UniqueRowsProduced
+    int64_t rows_skipped = 0;                                              // AggregationMetrics: input rows processed with partial aggregation disabled
+    tgpu_op* skip_fp = nullptr;                                            // the pre-stage as its own FilterAndProject, for skipped builders of a fused operator
+
     explicit AggOp(tgpu_ctx* c) : tgpu_op(c) {}
     ~AggOp() override
     {
         for (size_t i = next_out; i < pending.size(); i++) delete pending[i];
         delete inner_fp;
+        delete skip_fp;
     }
 
     AggState state() const
@@ -1682,25 +1755,31 @@ struct AggOp : tgpu_op {
         return TGPU_OK;
     }
 
+    // the fused pre-stage as a stand-alone FilterAndProject operator (the reference's own operator chain)
+    int make_pre_filter_project(tgpu_op** out)
+    {
+        std::vector<tgpu_in_list> lists(pre_in_values.size());
+        for (size_t i = 0; i < lists.size(); i++) { lists[i].count = (int32_t)pre_in_values[i].size(); lists[i].values = pre_in_values[i].data(); }
+        tgpu_expr_program prog;
+        memset(&prog, 0, sizeof(prog));
+        prog.num_insns = (int32_t)pre_insns.size();
+        prog.insns = pre_insns.data();
+        prog.filter_temp = pre_filter_temp;
+        prog.num_filter_insns = pre_num_filter_insns;
+        prog.num_projections = (int32_t)projections.size();
+        prog.projections = projections.data();
+        prog.num_in_lists = (int32_t)lists.size();
+        prog.in_lists = lists.data();
+        return tgpu_filter_project_create(ctx, &prog, out);
+    }
+
     int switch_to_general()
     {
         use_general = true;
         if (has_pre) {
             // the general path works on materialised projection outputs: un-fuse the pre-stage into its own
             // FilterAndProject (the reference's own operator chain) and re-point every source at its output channel
-            std::vector<tgpu_in_list> lists(pre_in_values.size());
-            for (size_t i = 0; i < lists.size(); i++) { lists[i].count = (int32_t)pre_in_values[i].size(); lists[i].values = pre_in_values[i].data(); }
-            tgpu_expr_program prog;
-            memset(&prog, 0, sizeof(prog));
-            prog.num_insns = (int32_t)pre_insns.size();
-            prog.insns = pre_insns.data();
-            prog.filter_temp = pre_filter_temp;
-            prog.num_filter_insns = pre_num_filter_insns;
-            prog.num_projections = (int32_t)projections.size();
-            prog.projections = projections.data();
-            prog.num_in_lists = (int32_t)lists.size();
-            prog.in_lists = lists.data();
-            TG_TRY(tgpu_filter_project_create(ctx, &prog, &inner_fp));
+            TG_TRY(make_pre_filter_project(&inner_fp));
             for (int i = 0; i < plan.num_srcs; i++) plan.srcs[i] = SrcRef{0, src_channel[i], 0, 0};
             plan.has_pre = 0;
             has_pre = false;
@@ -2141,9 +2220,21 @@ struct AggOp : tgpu_op {
     int add_input(const tgpu_page* page) override
     {
         if (page->num_rows == 0) return TGPU_OK;
-        if (use_general && inner_fp) return add_via_filter_project(page);
+        if (!builder_open) {
+            // HashAggregationOperator.addInput :358-372: the controller is consulted when a builder is created
+            builder_open = true;
+            skip_mode = controller && controller->disabled.load(std::memory_order_acquire);
+            builder_bytes = builder_rows = builder_unique = 0;
+        }
+        builder_rows += page->num_rows;
+        if (skip_mode) return add_input_skipped(page);
+        if (use_general && inner_fp) {
+            if (controller) builder_bytes += reference_page_bytes(page);
+            return add_via_filter_project(page);
+        }
         DevPage in;
         TG_TRY(tg_ingest_page(ctx, page, &in));
+        if (controller) builder_bytes += reference_page_bytes(in);
         TG_TRY(encode_string_keys(&in));
         if (!planned) {
             TG_TRY(make_plan(in));
@@ -2171,6 +2262,182 @@ struct AggOp : tgpu_op {
         }
         TG_TRY(run_general(in, cols));
         return after_page();
+    }
+
+    // Page.getSizeInBytes() of the same page on the Java side: value bytes plus one isNull byte per position (LongArrayBlock.getSizeInBytes,
+    // S/block/LongArrayBlock.java:93-96), variable width adds the 4-byte offset (S/block/VariableWidthBlock.java:137-140)
+    static int64_t reference_column_bytes(int type, int64_t n, int64_t utf8_bytes)
+    {
+        switch (type) {
+            case TGPU_INT64: case TGPU_FLOAT64: return 9 * n;
+            case TGPU_INT32: return 5 * n;
+            case TGPU_INT16: return 3 * n;
+            case TGPU_INT8: return 2 * n;
+            case TGPU_UTF8: return utf8_bytes + 5 * n;
+            default: return 9 * n;
+        }
+    }
+    static int64_t reference_page_bytes(const DevPage& in)
+    {
+        int64_t b = 0;
+        for (auto& c : in.cols) b += reference_column_bytes(c.type, c.length, c.data_bytes);
+        return b;
+    }
+    static int64_t reference_page_bytes(const tgpu_page* page)
+    {
+        int64_t b = 0;
+        for (int c = 0; c < page->num_columns; c++) {
+            const tgpu_column& col = page->columns[c];
+            int type = col.type == TGPU_DICT32 || col.type == TGPU_RLE ? (col.dictionary ? col.dictionary->type : TGPU_INT64) : col.type;
+            // (variable-width bytes of a device page are not known without a read-back: the offsets and null bytes stand for the column)
+            b += reference_column_bytes(type, col.length, 0);
+        }
+        return b;
+    }
+
+    // One page through a skipped builder (SkipAggregationBuilder.processPage / buildResult): the output is parked in `pending`, so
+    // needs_input() is false until the caller has taken it (isFull() == currentPage != null)
+    int add_input_skipped(const tgpu_page* page)
+    {
+        const bool from_state = step == TGPU_STEP_INTERMEDIATE;
+        tgpu_op* fp = inner_fp;
+        if (has_pre) {
+            if (!skip_fp) TG_TRY(make_pre_filter_project(&skip_fp));
+            fp = skip_fp;
+        }
+        std::vector<std::unique_ptr<OwnedPage>> projected;
+        DevPage raw;
+        std::vector<const DevPage*> pages;
+        if (fp) {
+            builder_bytes += reference_page_bytes(page);
+            TG_TRY(fp->add_input(page));
+            while (true) {
+                OwnedPage* o = nullptr;
+                TG_TRY(fp->get_output(&o));
+                if (!o) break;
+                projected.emplace_back(o);
+                pages.push_back(&o->page);
+            }
+        }
+        else {
+            TG_TRY(tg_ingest_page(ctx, page, &raw));
+            builder_bytes += reference_page_bytes(raw);
+            pages.push_back(&raw);
+        }
+        rows_skipped += page->num_rows;
+        for (const DevPage* in : pages) {
+            const int64_t n = in->rows;
+            if (n == 0) continue;
+            DevPage outp;
+            outp.rows = n;
+            auto channel = [&](int ch, const DevColumn** c) -> int {
+                if (ch < 0 || ch >= (int)in->cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "aggregation channel %d out of range", ch);
+                *c = &in->cols[ch];
+                return TGPU_OK;
+            };
+            for (int ch : key_channels) {
+                const DevColumn* c = nullptr;
+                TG_TRY(channel(ch, &c));
+                outp.cols.push_back(*c);                  // the block itself (page.getBlock(hashChannels[i]))
+            }
+            SkipSpec spec;
+            memset(&spec, 0, sizeof(spec));
+            std::vector<std::pair<size_t, std::shared_ptr<DevBuf>>> nullmaps;      // (output column, byte map)
+            auto new_col = [&](int type, void** data) -> int {
+                DevColumn c;
+                c.type = type;
+                c.length = n;
+                c.own_data = std::make_shared<DevBuf>();
+                TG_TRY(c.own_data->alloc(ctx, (size_t)n * 8));
+                c.data = c.own_data->p;
+                *data = c.own_data->p;
+                outp.cols.push_back(std::move(c));
+                return TGPU_OK;
+            };
+            for (auto& f : fns) {
+                if (from_state) {
+                    // INTERMEDIATE: a one-row group's combined state is the incoming state
+                    const DevColumn* c = nullptr;
+                    TG_TRY(channel(f.input_channel, &c));
+                    outp.cols.push_back(*c);
+                    if (f.function == TGPU_AGG_AVG) {
+                        TG_TRY(channel(f.input_channel + 1, &c));
+                        outp.cols.push_back(*c);
+                    }
+                    continue;
+                }
+                if (spec.count >= SKIP_MAX_FNS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "more than %d aggregates", SKIP_MAX_FNS);
+                SkipFn& k = spec.f[spec.count++];
+                k.function = f.function;
+                k.in_ch = -1;
+                k.mask_ch = -1;
+                if (f.mask_channel >= 0) {
+                    const DevColumn* m = nullptr;
+                    TG_TRY(channel(f.mask_channel, &m));
+                    k.mask_ch = f.mask_channel;
+                }
+                int in_type = TGPU_INT64;
+                bool nullable = k.mask_ch >= 0;
+                if (f.function != TGPU_AGG_COUNT_STAR) {
+                    const DevColumn* c = nullptr;
+                    TG_TRY(channel(f.input_channel, &c));
+                    if (c->type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregates over variable-width inputs are not supported");
+                    k.in_ch = f.input_channel;
+                    in_type = c->type;
+                    nullable |= c->validity != nullptr;
+                }
+                k.in_is_double = in_type == TGPU_FLOAT64;
+                switch (f.function) {
+                    case TGPU_AGG_COUNT_STAR: case TGPU_AGG_COUNT:
+                        TG_TRY(new_col(TGPU_INT64, &k.out0));
+                        break;
+                    case TGPU_AGG_AVG:
+                        TG_TRY(new_col(TGPU_INT64, &k.out0));
+                        TG_TRY(new_col(TGPU_FLOAT64, &k.out1));
+                        break;
+                    case TGPU_AGG_SUM: case TGPU_AGG_MIN: case TGPU_AGG_MAX: {
+                        TG_TRY(new_col(k.in_is_double ? TGPU_FLOAT64 : TGPU_INT64, &k.out0));
+                        auto nm = std::make_shared<DevBuf>();
+                        TG_TRY(nm->alloc(ctx, (size_t)n));
+                        k.null0 = nm->as<unsigned char>();
+                        // (an input without NULLs and without a mask cannot produce a NULL state: no bitmap then)
+                        if (nullable) nullmaps.emplace_back(outp.cols.size() - 1, nm);
+                        else nullmaps.emplace_back((size_t)-1, nm);
+                        break;
+                    }
+                    default: return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d", f.function);
+                }
+            }
+            if (spec.count > 0) {
+                DColumns cols;
+                TG_TRY(fill_cols(*in, &cols));
+                TG_LAUNCH(ctx, agg_skip_kernel, tg_grid(ctx, n, 256, 8), 256, 0, cols, n, spec);
+                for (auto& nm : nullmaps) {
+                    if (nm.first == (size_t)-1) continue;
+                    auto bm = std::make_shared<DevBuf>();
+                    TG_TRY(bm->alloc(ctx, (size_t)((n + 7) / 8)));
+                    TG_LAUNCH(ctx, nullmap_pack_kernel, tg_grid(ctx, (n + 7) / 8, 256, 8), 256, 0, nm.second->as<unsigned char>(), n, bm->as<unsigned char>(),
+                              (unsigned int*)nullptr);
+                    outp.cols[nm.first].own_validity = bm;
+                    outp.cols[nm.first].validity = bm->as<uint8_t>();
+                }
+                // the byte maps are read by kernels queued on the stream: keep them until those ran
+                TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            pending.push_back(tg_make_owned_page(std::move(outp)));
+        }
+        if (next_out >= pending.size()) close_builder(-1);       // (a filter that drops the whole page leaves nothing to hand out)
+        return TGPU_OK;
+    }
+
+    // HashAggregationOperator.closeAggregationBuilder :512-523
+    void close_builder(int64_t unique_rows)
+    {
+        if (!builder_open) return;
+        if (controller) tgpu_partial_agg_controller_on_flush(controller, builder_bytes, builder_rows, skip_mode ? -1 : unique_rows);
+        builder_open = false;
+        skip_mode = false;
+        builder_bytes = builder_rows = builder_unique = 0;
     }
 
     int add_via_filter_project(const tgpu_page* page)
@@ -2411,16 +2678,26 @@ struct AggOp : tgpu_op {
     int get_output(OwnedPage** out) override
     {
         *out = nullptr;
-        if (next_out < pending.size()) { *out = pending[next_out++]; return TGPU_OK; }
+        if (next_out < pending.size()) {
+            *out = pending[next_out++];
+            if (next_out >= pending.size()) {
+                pending.clear();
+                next_out = 0;
+                if (skip_mode) close_builder(-1);
+            }
+            return TGPU_OK;
+        }
         if (flushing) {
             TG_TRY(build_output(out));
             if (*out) saw_group = true;
+            close_builder(*out ? (*out)->page.rows : 0);
             TG_TRY(reset_state());
             flushing = false;
             return TGPU_OK;
         }
         if (finishing && !finished) {
             TG_TRY(build_output(out));
+            close_builder(*out ? (*out)->page.rows : 0);
             finished = true;
             const bool output_partial = step == TGPU_STEP_PARTIAL || step == TGPU_STEP_INTERMEDIATE;
             // (a group exists iff a row reached the aggregation: with a fused filter that is "a row passed the filter", which is what the
@@ -2444,6 +2721,11 @@ int build_agg_op(tgpu_ctx* ctx, const tgpu_agg_spec* spec, AggOp** out)
     op->step = spec->step;
     op->expected_groups = spec->expected_groups;
     op->max_partial_bytes = spec->max_partial_bytes;
+    if (spec->partial_aggregation_controller) {
+        if (spec->step != TGPU_STEP_PARTIAL && spec->step != TGPU_STEP_INTERMEDIATE)
+            return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partialAggregationController should be present only for partial aggregation");
+        op->controller = spec->partial_aggregation_controller;
+    }
     if (spec->num_global_group_ids > 0) {
         if (!spec->global_group_ids || spec->group_id_key < 0 || spec->group_id_key >= spec->num_keys)
             return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "global grouping sets need global_group_ids and a valid group_id_key");
@@ -2480,6 +2762,53 @@ extern "C" int tgpu_agg_create(tgpu_ctx* ctx, const tgpu_agg_spec* spec, tgpu_op
     AggOp* op = nullptr;
     TG_TRY(build_agg_op(ctx, spec, &op));
     *out = op;
+    return TGPU_OK;
+}
+
+extern "C" int tgpu_partial_agg_controller_create(int64_t max_partial_memory_bytes, double unique_rows_ratio_threshold, tgpu_partial_agg_controller** out)
+{
+    if (!out || max_partial_memory_bytes < 0) return TGPU_ERR_INVALID_ARGUMENT;
+    auto* c = new tgpu_partial_agg_controller();
+    c->max_partial_bytes = max_partial_memory_bytes;
+    c->threshold = unique_rows_ratio_threshold;
+    *out = c;
+    return TGPU_OK;
+}
+
+extern "C" void tgpu_partial_agg_controller_destroy(tgpu_partial_agg_controller* controller) { delete controller; }
+
+extern "C" int tgpu_partial_agg_controller_is_disabled(const tgpu_partial_agg_controller* controller)
+{
+    return controller && controller->disabled.load(std::memory_order_acquire) ? 1 : 0;
+}
+
+// PartialAggregationController.onFlush :67-91, shouldDisablePartialAggregation :93-97
+extern "C" void tgpu_partial_agg_controller_on_flush(tgpu_partial_agg_controller* c, int64_t bytes_processed, int64_t rows_processed, int64_t unique_rows_produced)
+{
+    if (!c) return;
+    std::lock_guard<std::mutex> lock(c->mu);
+    bool disabled = c->disabled.load(std::memory_order_relaxed);
+    const bool has_unique = unique_rows_produced >= 0;
+    if (!disabled && !has_unique) return;                 // when PA is re-enabled, stats from disabled flushes are ignored
+    c->total_bytes += bytes_processed;
+    c->total_rows += rows_processed;
+    if (has_unique) c->total_unique += unique_rows_produced;
+    const double disable_factor = 1.5, enable_factor = 1.5 * 200;
+    if (!disabled && (double)c->total_bytes >= (double)c->max_partial_bytes * disable_factor
+        && ((double)c->total_unique / (double)c->total_rows) > c->threshold)
+        disabled = true;
+    if (disabled && (double)c->total_bytes >= (double)c->max_partial_bytes * enable_factor) {
+        c->total_bytes = c->total_rows = c->total_unique = 0;
+        disabled = false;
+    }
+    c->disabled.store(disabled, std::memory_order_release);
+}
+
+extern "C" int tgpu_agg_rows_with_partial_aggregation_disabled(tgpu_op* op, int64_t* out)
+{
+    AggOp* a = dynamic_cast<AggOp*>(op);
+    if (!a || !out) return TGPU_ERR_INVALID_ARGUMENT;
+    *out = a->rows_skipped;
     return TGPU_OK;
 }
 

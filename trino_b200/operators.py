@@ -453,16 +453,52 @@ class HashAggregationOperator(Operator):
         self.ctx.check(self.ctx.lib.tgpu_agg_group_count(self.h, C.byref(v)))
         return v.value
 
+    def rows_with_partial_aggregation_disabled(self):
+        """AggregationMetrics.INPUT_ROWS_WITH_PARTIAL_AGGREGATION_DISABLED_METRIC_NAME"""
+        v = C.c_int64()
+        self.ctx.check(self.ctx.lib.tgpu_agg_rows_with_partial_aggregation_disabled(self.h, C.byref(v)))
+        return v.value
+
+
+class PartialAggregationController:
+    """M/operator/aggregation/partial/PartialAggregationController.java:35-103 - the object lives in the native library (the operators
+    report their flushes to it themselves); needs no GPU."""
+
+    def __init__(self, lib, max_partial_memory, unique_rows_ratio_threshold):
+        self.lib, self.max_partial_memory, self.threshold = lib, int(max_partial_memory), float(unique_rows_ratio_threshold)
+        h = C.c_void_p()
+        rc = lib.tgpu_partial_agg_controller_create(self.max_partial_memory, self.threshold, C.byref(h))
+        if rc != 0:
+            raise abi.TrinoGpuError(rc, "INVALID_ARGUMENT", "tgpu_partial_agg_controller_create failed")
+        self.h = h
+
+    def is_partial_aggregation_disabled(self):
+        return bool(self.lib.tgpu_partial_agg_controller_is_disabled(self.h))
+
+    def on_flush(self, bytes_processed, rows_processed, unique_rows_produced=None):
+        """unique_rows_produced None = OptionalLong.empty()"""
+        self.lib.tgpu_partial_agg_controller_on_flush(self.h, int(bytes_processed), int(rows_processed),
+                                                      -1 if unique_rows_produced is None else int(unique_rows_produced))
+
+    def duplicate(self):
+        return PartialAggregationController(self.lib, self.max_partial_memory, self.threshold)
+
+    def close(self):
+        if self.h:
+            self.lib.tgpu_partial_agg_controller_destroy(self.h)
+            self.h = None
+
 
 class HashAggregationOperatorFactory(OperatorFactory):
     def __init__(self, ctx, group_by_channels, step, aggregators, expected_groups=10_000, max_partial_memory=0, pre=None,
-                 global_aggregation_group_ids=(), group_id_channel=None, input_types=None):
+                 global_aggregation_group_ids=(), group_id_channel=None, input_types=None, partial_aggregation_controller=None):
         """global_aggregation_group_ids / group_id_channel (a group-by CHANNEL, like the reference's groupIdChannel) / input_types (tgpu_type
         per input channel): the default rows of global grouping sets over empty input (HashAggregationOperator.java:537-567)"""
         super().__init__()
         self.ctx, self.group_by_channels, self.step, self.aggregators = ctx, list(group_by_channels), step, list(aggregators)
         self.expected_groups, self.max_partial_memory, self.pre = expected_groups, max_partial_memory, pre
         self.global_ids, self.group_id_channel, self.input_types = list(global_aggregation_group_ids), group_id_channel, input_types
+        self.controller = partial_aggregation_controller
 
     def _create(self):
         keys = _i32(self.group_by_channels)
@@ -476,14 +512,17 @@ class HashAggregationOperatorFactory(OperatorFactory):
                            C.pointer(self.pre.struct) if self.pre is not None else None,
                            len(self.global_ids), C.cast(gids, C.POINTER(C.c_int32)),
                            self.group_by_channels.index(self.group_id_channel) if self.group_id_channel is not None else -1,
-                           len(self.input_types or []), C.cast(types, C.POINTER(C.c_int32)))
+                           len(self.input_types or []), C.cast(types, C.POINTER(C.c_int32)),
+                           self.controller.h if self.controller is not None else None)
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.tgpu_agg_create(self.ctx.h, C.byref(spec), C.byref(h)))
         return HashAggregationOperator(self.ctx, h)
 
     def duplicate(self):
         return HashAggregationOperatorFactory(self.ctx, self.group_by_channels, self.step, self.aggregators, self.expected_groups,
-                                              self.max_partial_memory, self.pre, self.global_ids, self.group_id_channel, self.input_types)
+                                              self.max_partial_memory, self.pre, self.global_ids, self.group_id_channel, self.input_types,
+                                              # HashAggregationOperatorFactory.duplicate :238: a fresh controller for the duplicated plan node
+                                              self.controller.duplicate() if self.controller is not None else None)
 
 
 class GroupByHash:
