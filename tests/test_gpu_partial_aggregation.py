@@ -112,10 +112,15 @@ def test_skipped_pages_match_oracle(ctx, varchar_key):
     controller.close()
 
 
-def _final_aggs():
-    # state channels of AGGS behind the key: avg takes two
+# (FINAL combines counts and BIGINT sums as 128-bit pairs: a plan holds at most MAX_ACCS accumulator words, hence the shorter list)
+MIXED = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_SUM, 2, -1), (abi.AGG_MAX, 2, -1),
+         (abi.AGG_SUM, 1, 3), (abi.AGG_COUNT, 2, 3)]
+
+
+def _final_aggs(aggs=None):
+    # state channels behind the key: avg takes two
     out, ch = [], 1
-    for fn, _, _ in AGGS:
+    for fn, _, _ in (aggs or AGGS):
         out.append(A(fn, ch))
         ch += 2 if fn == abi.AGG_AVG else 1
     return out
@@ -126,18 +131,18 @@ def test_mixed_partial_pages_then_final_equals_single(ctx):
     # high-cardinality pages switch partial aggregation off, ~90 KB of skipped pages switch it back on: both kinds of page reach FINAL
     pages = _pages(rng, 5000, [600] * 40) + _pages(rng, 5, [600] * 20)
     controller = ops.PartialAggregationController(ctx.lib, 300, 0.5)
-    f = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, [A(fn, ch, m) for fn, ch, m in AGGS], 100, max_partial_memory=300,
+    f = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, [A(fn, ch, m) for fn, ch, m in MIXED], 100, max_partial_memory=300,
                                            partial_aggregation_controller=controller)
     op = f.create_operator()
     partial = ops.drive(op, pages)
     skipped = op.rows_with_partial_aggregation_disabled()
     op.close()
     assert 0 < skipped < sum(p.position_count for p in pages)
-    ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, _final_aggs(), 100)
+    ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, _final_aggs(MIXED), 100)
     fop = ff.create_operator()
     final = [r for p in ops.drive(fop, partial) for r in p.rows()]
     fop.close()
-    want = oracle_agg_rows(pages, [0], AGGS)
+    want = oracle_agg_rows(pages, [0], MIXED)
     key = lambda r: (r[0] is None, r[0])
     assert rows_equal(sorted(final, key=key), sorted(want, key=key), rel=1e-9)
     controller.close()
