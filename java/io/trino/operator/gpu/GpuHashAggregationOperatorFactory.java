@@ -35,10 +35,16 @@ public class GpuHashAggregationOperatorFactory
     private final OptionalInt groupIdChannel;    // index among the group-by keys, as in the reference (:552)
     private final int expectedGroups;
     private final long maxPartialMemory;
+    // the native PartialAggregationController shared by this plan node's drivers (MemorySegment.NULL = none).  Created by the planner hook
+    // from task.max-partial-aggregation-memory and adaptive-partial-aggregation.unique-rows-ratio-threshold where the reference creates
+    // its own (LocalExecutionPlanner.java:4101-4110), destroyed with the task.
+    private final MemorySegment partialAggregationController;
+    private final double uniqueRowsRatioThreshold;
     private boolean closed;
 
     public GpuHashAggregationOperatorFactory(int operatorId, PlanNodeId planNodeId, int[] inputTypes, int[] outputTypes, List<Integer> groupByChannels,
-            List<Integer> globalAggregationGroupIds, Step step, List<GpuAggregate> aggregates, OptionalInt groupIdChannel, int expectedGroups, long maxPartialMemory)
+            List<Integer> globalAggregationGroupIds, Step step, List<GpuAggregate> aggregates, OptionalInt groupIdChannel, int expectedGroups, long maxPartialMemory,
+            boolean adaptivePartialAggregation, double uniqueRowsRatioThreshold)
     {
         this.operatorId = operatorId;
         this.planNodeId = planNodeId;
@@ -51,6 +57,26 @@ public class GpuHashAggregationOperatorFactory
         this.groupIdChannel = groupIdChannel;
         this.expectedGroups = expectedGroups;
         this.maxPartialMemory = maxPartialMemory;
+        this.uniqueRowsRatioThreshold = uniqueRowsRatioThreshold;
+        this.partialAggregationController = adaptivePartialAggregation && step.isOutputPartial()
+                ? createController(maxPartialMemory, uniqueRowsRatioThreshold)
+                : MemorySegment.NULL;
+    }
+
+    private static MemorySegment createController(long maxPartialMemory, double uniqueRowsRatioThreshold)
+    {
+        try (java.lang.foreign.Arena arena = java.lang.foreign.Arena.ofConfined()) {
+            MemorySegment out = arena.allocate(java.lang.foreign.ValueLayout.ADDRESS);
+            int status = (int) TrinoGpuLibrary.PA_CONTROLLER_CREATE.invokeExact(maxPartialMemory, uniqueRowsRatioThreshold, out);
+            checkState(status == 0, "tgpu_partial_agg_controller_create failed: %s", status);
+            return out.get(java.lang.foreign.ValueLayout.ADDRESS, 0);
+        }
+        catch (RuntimeException e) {
+            throw e;
+        }
+        catch (Throwable e) {
+            throw new RuntimeException(e);
+        }
     }
 
     @Override
@@ -60,7 +86,7 @@ public class GpuHashAggregationOperatorFactory
         OperatorContext operatorContext = driverContext.addOperatorContext(operatorId, planNodeId, "GpuHashAggregationOperator");
         GpuContexts.Handle gpu = GpuContexts.forCurrentDriver(driverContext);
         MemorySegment op = NativeSpecs.createAggregation(gpu, groupByChannels, step, aggregates, expectedGroups, maxPartialMemory, globalAggregationGroupIds,
-                groupIdChannel.orElse(-1), inputTypes, MemorySegment.NULL);
+                groupIdChannel.orElse(-1), inputTypes, MemorySegment.NULL, partialAggregationController);
         return new GpuOperator(operatorContext, gpu.context(), op, gpu.marshaller(inputTypes), outputTypes);
     }
 
@@ -74,6 +100,8 @@ public class GpuHashAggregationOperatorFactory
     public OperatorFactory duplicate()
     {
         return new GpuHashAggregationOperatorFactory(operatorId, planNodeId, inputTypes, outputTypes, groupByChannels, globalAggregationGroupIds, step, aggregates,
-                groupIdChannel, expectedGroups, maxPartialMemory);
+                groupIdChannel, expectedGroups, maxPartialMemory,
+                // a duplicated factory gets its own controller (HashAggregationOperatorFactory.duplicate :238)
+                !partialAggregationController.equals(MemorySegment.NULL), uniqueRowsRatioThreshold);
     }
 }

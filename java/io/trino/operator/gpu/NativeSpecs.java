@@ -27,13 +27,14 @@ public final class NativeSpecs
     static final StructLayout AGG_FN = MemoryLayout.structLayout(JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT);
     // tgpu_agg_spec { int32 num_keys; (pad) ; int32* key_channels; int32 step; int32 num_aggs; tgpu_agg_fn* aggs; int64 expected_groups;
     //                 int64 max_partial_bytes; tgpu_expr_program* pre; int32 num_global_group_ids; (pad); int32* global_group_ids;
-    //                 int32 group_id_key; int32 num_input_channels; int32* input_channel_types }
+    //                 int32 group_id_key; int32 num_input_channels; int32* input_channel_types; tgpu_partial_agg_controller* controller }
     static final StructLayout AGG_SPEC = MemoryLayout.structLayout(
             JAVA_INT.withName("num_keys"), MemoryLayout.paddingLayout(4), ADDRESS.withName("key_channels"),
             JAVA_INT.withName("step"), JAVA_INT.withName("num_aggs"), ADDRESS.withName("aggs"),
             JAVA_LONG.withName("expected_groups"), JAVA_LONG.withName("max_partial_bytes"), ADDRESS.withName("pre"),
             JAVA_INT.withName("num_global_group_ids"), MemoryLayout.paddingLayout(4), ADDRESS.withName("global_group_ids"),
-            JAVA_INT.withName("group_id_key"), JAVA_INT.withName("num_input_channels"), ADDRESS.withName("input_channel_types"));
+            JAVA_INT.withName("group_id_key"), JAVA_INT.withName("num_input_channels"), ADDRESS.withName("input_channel_types"),
+            ADDRESS.withName("partial_aggregation_controller"));
     // tgpu_join_build_spec { int32 num_key_channels; int32* key_channels; int32 num_output_channels; int32* output_channels; int64 expected_positions }
     static final StructLayout JOIN_BUILD_SPEC = MemoryLayout.structLayout(
             JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_LONG);
@@ -76,7 +77,8 @@ public final class NativeSpecs
     }
 
     public static MemorySegment createAggregation(GpuContexts.Handle gpu, List<Integer> groupByChannels, Step step, List<GpuAggregate> aggregates, int expectedGroups,
-            long maxPartialMemory, List<Integer> globalAggregationGroupIds, int groupIdKey, int[] inputChannelTypes, MemorySegment preProgram)
+            long maxPartialMemory, List<Integer> globalAggregationGroupIds, int groupIdKey, int[] inputChannelTypes, MemorySegment preProgram,
+            MemorySegment partialAggregationController)
     {
         try (Arena arena = Arena.ofConfined()) {
             MemorySegment fns = arena.allocate(AGG_FN, Math.max(1, aggregates.size()));
@@ -106,6 +108,7 @@ public final class NativeSpecs
             spec.set(JAVA_INT, 72, groupIdKey);
             spec.set(JAVA_INT, 76, inputChannelTypes.length);
             spec.set(ADDRESS, 80, types);
+            spec.set(ADDRESS, 88, partialAggregationController);       // MemorySegment.NULL = Optional.empty()
             return create(gpu, TrinoGpuLibrary.AGG_CREATE, spec, arena);
         }
         catch (RuntimeException e) {

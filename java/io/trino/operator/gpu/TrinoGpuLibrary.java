@@ -13,6 +13,7 @@ import java.lang.foreign.SymbolLookup;
 import java.lang.invoke.MethodHandle;
 
 import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
 import static java.lang.foreign.ValueLayout.JAVA_INT;
 import static java.lang.foreign.ValueLayout.JAVA_LONG;
 
@@ -39,6 +40,11 @@ public final class TrinoGpuLibrary
     // operator factories
     static final MethodHandle FILTER_PROJECT_CREATE = handle("tgpu_filter_project_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle AGG_CREATE = handle("tgpu_agg_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    // PartialAggregationController lives in the library so that GPU operators report their flushes without an upcall
+    static final MethodHandle PA_CONTROLLER_CREATE = handle("tgpu_partial_agg_controller_create", FunctionDescriptor.of(JAVA_INT, JAVA_LONG, JAVA_DOUBLE, ADDRESS));
+    static final MethodHandle PA_CONTROLLER_DESTROY = handle("tgpu_partial_agg_controller_destroy", FunctionDescriptor.ofVoid(ADDRESS));
+    static final MethodHandle PA_CONTROLLER_IS_DISABLED = handle("tgpu_partial_agg_controller_is_disabled", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle AGG_ROWS_WITH_PA_DISABLED = handle("tgpu_agg_rows_with_partial_aggregation_disabled", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle JOIN_BUILD_CREATE = handle("tgpu_join_build_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     static final MethodHandle JOIN_BUILD_GET_LOOKUP = handle("tgpu_join_build_get_lookup", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle JOIN_PROBE_CREATE = handle("tgpu_join_probe_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));

@@ -71,10 +71,71 @@ public final class PageMarshaller
         this.channelTypes = channelTypes.clone();
     }
 
+    // ------------------------------------------------------------------------------------------------ ROW-typed aggregation states
+    /**
+     * Multi-field aggregation states travel between the reference's PARTIAL and FINAL steps as ONE RowBlock channel
+     * (AccumulatorCompiler.java:687-760: RowBlockBuilder.buildEntry over the state serializers); the C ABI carries the fields as
+     * consecutive flat columns (include/trino_gpu.h, "Intermediate state layout").  flattenRows() runs on every input page of a
+     * FINAL / INTERMEDIATE GPU step, composeRows() on every output page of a PARTIAL / INTERMEDIATE one; `channelTypes` of this
+     * marshaller and the channel numbers handed to NativeSpecs are those of the FLATTENED page (firstFlatChannel maps the plan's).
+     * trino_b200/page.py (RowBlock, flatten_row_blocks, compose_row_blocks) is the tested mirror of the pair.
+     */
+    public static Page flattenRows(Page page)
+    {
+        boolean any = false;
+        for (int channel = 0; channel < page.getChannelCount(); channel++) {
+            any |= flat(page.getBlock(channel)) instanceof RowBlock;
+        }
+        if (!any) {
+            return page;
+        }
+        List<Block> blocks = new ArrayList<>();
+        for (int channel = 0; channel < page.getChannelCount(); channel++) {
+            Block block = flat(page.getBlock(channel));
+            if (block instanceof RowBlock row) {
+                // a NULL row reads as NULL in every field (RowBlock.getNullSuppressedRowFieldsFromBlock, S/block/RowBlock.java:413-440)
+                blocks.addAll(RowBlock.getNullSuppressedRowFieldsFromBlock(row));
+            }
+            else {
+                blocks.add(block);
+            }
+        }
+        return new Page(page.getPositionCount(), blocks.toArray(Block[]::new));
+    }
+
+    /** first flattened channel of every plan channel; width[c] = fields of a ROW-typed channel, 1 otherwise */
+    public static int[] firstFlatChannel(int[] width)
+    {
+        int[] first = new int[width.length];
+        for (int channel = 0, at = 0; channel < width.length; channel++) {
+            first[channel] = at;
+            at += width[channel];
+        }
+        return first;
+    }
+
+    public static Page composeRows(Page flat, int[] width)
+    {
+        Block[] blocks = new Block[width.length];
+        for (int channel = 0, at = 0; channel < width.length; at += width[channel], channel++) {
+            if (width[channel] == 1) {
+                blocks[channel] = flat.getBlock(at);
+                continue;
+            }
+            Block[] fields = new Block[width[channel]];
+            for (int field = 0; field < fields.length; field++) {
+                fields[field] = flat.getBlock(at + field);
+            }
+            blocks[channel] = RowBlock.fromFieldBlocks(flat.getPositionCount(), fields);      // states are never NULL rows
+        }
+        return new Page(flat.getPositionCount(), blocks);
+    }
+
     // ------------------------------------------------------------------------------------------------ batching (Operator.addInput side)
     /** returns true when the batch should be flushed into the native operator now */
     public boolean append(Page page)
     {
+        page = flattenRows(page);
         batch.add(page);
         batchRows += page.getPositionCount();
         return batchRows >= BATCH_ROWS;

@@ -184,9 +184,13 @@ def test_general_path_physical_slices_match_oracle(ctx, monkeypatch):
     rng = np.random.default_rng(78)
     pages = _agg_pages(rng, 20000, (60000, 7, 90000)) + _agg_pages(rng, 400000, (150000,))
     want = _oracle_agg(pages, [0], AGGS)
-    for interpreted in (False, True):
+    for interpreted, stable in ((False, False), (True, False), (False, True)):
         if interpreted:
             monkeypatch.setenv("TGPU_AGG_GENERAL_INTERPRETED", "1")
+        else:
+            monkeypatch.delenv("TGPU_AGG_GENERAL_INTERPRETED", raising=False)
+        if stable:
+            monkeypatch.setenv("TGPU_AGG_STABLE_SCATTER", "1")       # the order-preserving multi-split instead of the any-order one
         got = _gpu_agg(ctx, pages, [0], AGGS, expected=30000)
         assert rows_equal(got, want, rel=1e-6)
         assert [r[0] for r in got] == [r[0] for r in want]

@@ -201,3 +201,26 @@ def test_fused_q1_partial_with_controller_off_then_final(ctx):
         for a, b in zip(g[2:9], w[2:9]):
             assert abs(a - b) <= 1e-6 * abs(b)
     controller.close()
+
+
+def test_row_typed_intermediate_states_round_trip(ctx):
+    # AccumulatorCompiler.java:687-760: a two-field state travels as ONE ROW channel between the reference's PARTIAL and FINAL steps;
+    # channel numbers on both factories are the Java plan's (key, count, sum, avg ROW, min)
+    from trino_b200.page import RowBlock
+    rng = np.random.default_rng(24)
+    pages = _pages(rng, 40, (5000, 5000))
+    aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_MIN, 2, -1)]
+    pf = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, [A(fn, ch, m) for fn, ch, m in aggs], 100, row_typed_states=True)
+    partial = []
+    for p in pages:
+        op = pf.create_operator()
+        partial += ops.drive(op, [p])
+        op.close()
+    assert all(p.channel_count == 5 and isinstance(p.get_block(3), RowBlock) and len(p.get_block(3).fields) == 2 for p in partial)
+    ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, [A(abi.AGG_COUNT_STAR, 1), A(abi.AGG_SUM, 2), A(abi.AGG_AVG, 3), A(abi.AGG_MIN, 4)], 100,
+                                            row_typed_states=True)
+    fop = ff.create_operator()
+    final = [r for p in ops.drive(fop, partial) for r in p.rows()]
+    fop.close()
+    want = oracle_agg_rows(pages, [0], aggs)
+    assert rows_equal(final, want, rel=1e-9)

@@ -227,6 +227,116 @@ __global__ void __launch_bounds__(XT, OCC) xchg_scatter_kernel(const uint8_t* __
     }
 }
 
+// ---- CTA tiles, ANY ORDER inside a partition --------------------------------------------------------------------------------
+// For callers that do not need the rows of a partition in input order (the sliced group-by: first-seen order travels in the
+// row-number lane).  Ranks come from one shared-memory counter per partition (warp-aggregated atomicAdd: one atomic per distinct
+// partition per warp), so there is no cell matrix to clear and scan; up to XU_G lanes are staged and copied out together, which
+// leaves 3 + 2 * ceil(lanes / XU_G) barriers per 2048-row tile and puts XU_G * 8 independent loads in flight per thread.
+constexpr int XU_G = 3;
+constexpr int XU_DST = 8;              // lanes whose destination pointers are cached in shared memory
+constexpr size_t XU_SMEM = (size_t)XU_G * XTILE * 8;
+
+__device__ __forceinline__ long long xchg_load_lane(int elem, const void* src, int64_t row)
+{
+    switch (elem) {
+        case 16: return (long long)row;                                           // XCHG_ROW_NUMBER
+        case 8: return ((const long long*)src)[row];
+        case 4: return ((const int*)src)[row];
+        case 2: return ((const short*)src)[row];
+        case 1: return ((const signed char*)src)[row];
+        default: return tg_valid((const uint8_t*)src, row) ? 0 : 1;              // NULL-byte pseudo lane
+    }
+}
+
+__global__ void __launch_bounds__(XT, 4) xchg_scatter_unordered_kernel(const uint8_t* __restrict__ pids, int64_t n, int64_t chunk, int32_t P,
+                                                                      const long long* __restrict__ block_off, XchgCols cols)
+{
+    extern __shared__ long long xu_stage[];          // [XU_G][XTILE]
+    __shared__ uint8_t spid[XTILE];
+    __shared__ int cnt[XMAXP];
+    __shared__ int tile_off[XMAXP];
+    __shared__ long long running[XMAXP];
+    __shared__ char* sdst[XU_DST * XMAXP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < P; i += XT) running[i] = block_off[(size_t)blockIdx.x * P + i];
+    for (int i = threadIdx.x; i < min(cols.count, XU_DST) * P; i += XT) sdst[(i / P) * XMAXP + (i % P)] = cols.dst[i];
+    const int64_t begin = (int64_t)blockIdx.x * chunk, end = min(n, begin + chunk);
+    for (int64_t tile = begin; tile < end; tile += XTILE) {
+        const int tile_rows = (int)min((int64_t)XTILE, end - tile);
+        if (threadIdx.x < XMAXP) cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int pid[XR], pos[XR];
+#pragma unroll
+        for (int i = 0; i < XR; i++) {
+            int64_t row = tile + (int64_t)i * XT + threadIdx.x;
+            pid[i] = row < end ? (int)pids[row] : -1;
+        }
+#pragma unroll
+        for (int i = 0; i < XR; i++) {
+            const bool live = pid[i] >= 0;
+            unsigned int peers = __match_any_sync(0xffffffffu, live ? pid[i] : -1 - lane);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (live && lane == leader) base = atomicAdd(&cnt[pid[i]], __popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            pos[i] = base + __popc(peers & ((1u << lane) - 1));
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
+            int incl = c0 + c1;
+            for (int off = 1; off < 32; off <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            int excl = incl - (c0 + c1);
+            tile_off[2 * lane] = excl;
+            tile_off[2 * lane + 1] = excl + c0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < XR; i++) {
+            if (pid[i] < 0) continue;
+            pos[i] += tile_off[pid[i]];
+            spid[pos[i]] = (uint8_t)pid[i];
+        }
+        for (int c0 = 0; c0 < cols.count; c0 += XU_G) {
+            const int g_count = min(XU_G, cols.count - c0);
+            for (int g = 0; g < g_count; g++) {
+                const int elem = cols.elem[c0 + g];
+                const void* src = cols.src[c0 + g];
+                long long v[XR];
+#pragma unroll
+                for (int i = 0; i < XR; i++) v[i] = pid[i] >= 0 ? xchg_load_lane(elem, src, tile + (int64_t)i * XT + threadIdx.x) : 0;
+#pragma unroll
+                for (int i = 0; i < XR; i++)
+                    if (pid[i] >= 0) xu_stage[g * XTILE + pos[i]] = v[i];
+            }
+            __syncthreads();
+            for (int g = 0; g < g_count; g++) {
+                const int c = c0 + g;
+                const int elem = cols.elem[c];
+                const long long* st = xu_stage + g * XTILE;
+                for (int j = threadIdx.x; j < tile_rows; j += XT) {
+                    const int q = spid[j];
+                    const long long d = running[q] + (j - tile_off[q]);
+                    char* base = c < XU_DST ? sdst[c * XMAXP + q] : cols.dst[(size_t)c * P + q];
+                    switch (elem) {
+                        case 8: ((long long*)base)[d] = st[j]; break;
+                        case 16:
+                        case 4: ((int*)base)[d] = (int)st[j]; break;
+                        case 2: ((short*)base)[d] = (short)st[j]; break;
+                        default: base[d] = (char)st[j]; break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < P) running[threadIdx.x] += cnt[threadIdx.x];
+        // (the barrier at the top of the next tile orders this update and the counter reset against their readers)
+    }
+}
+
 // ---- warp-granular variant for <= 8 partitions (one per GPU of a box) ------------------------------------------------------
 // Every warp owns a contiguous chunk of rows and walks it in tiles of 256 rows (8 consecutive rows per lane), with no CTA
 // barrier anywhere: warps drift apart, so the load latency of one warp hides behind the staging / copy-out of the others.
@@ -542,8 +652,17 @@ static bool xchg_ids_from_key(const XchgGeom& g, const KeyCols& k)
 }
 
 static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* pids, int64_t n, int32_t P, const long long* block_off, const XchgCols& xc,
-                               const KeyCols* key = nullptr, int32_t bucket_count = 0, const int32_t* b2p = nullptr)
+                               const KeyCols* key = nullptr, int32_t bucket_count = 0, const int32_t* b2p = nullptr, bool any_order = false)
 {
+    if (any_order && !g.warp_mode && pids) {
+        static bool attr_set = false;      // (per translation unit and process: the attribute is a property of the function)
+        if (!attr_set) {
+            TG_CUDA(ctx, cudaFuncSetAttribute(xchg_scatter_unordered_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XU_SMEM));
+            attr_set = true;
+        }
+        TG_LAUNCH(ctx, xchg_scatter_unordered_kernel, g.grid, XT, XU_SMEM, pids, n, g.chunk, P, block_off, xc);
+        return TGPU_OK;
+    }
     if (g.warp_mode) {
         const long long* key0 = pids ? nullptr : (const long long*)key->cols[0].data;
         bool vec = pids ? ((uintptr_t)pids & 7) == 0 : ((uintptr_t)key0 & 15) == 0;

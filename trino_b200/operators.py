@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .page import AbiPage, Block, Page
+from .page import AbiPage, Block, Page, RowBlock, compose_row_blocks, flatten_row_blocks
 
 _NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64}
 _ELEM = {abi.INT64: 8, abi.INT32: 4, abi.INT16: 2, abi.INT8: 1, abi.FLOAT64: 8}
@@ -448,6 +448,22 @@ class Aggregator:
 
 
 class HashAggregationOperator(Operator):
+    # ROW-typed intermediate states (AccumulatorCompiler.java:687-760): set by the factory when the neighbouring stage is a Java
+    # operator that speaks the reference's state types.  in_first: flat channel of each original input channel; out_widths: see
+    # page.compose_row_blocks
+    _out_widths = None
+
+    def add_input(self, page):
+        if hasattr(page, "blocks") and any(isinstance(b, RowBlock) for b in page.blocks):
+            page, _ = flatten_row_blocks(page)
+        super().add_input(page)
+
+    def get_output(self):
+        out = super().get_output()
+        if out is not None and self._out_widths is not None:
+            out = compose_row_blocks(out, self._out_widths)
+        return out
+
     def group_count(self):
         v = C.c_int64()
         self.ctx.check(self.ctx.lib.tgpu_agg_group_count(self.h, C.byref(v)))
@@ -491,7 +507,8 @@ class PartialAggregationController:
 
 class HashAggregationOperatorFactory(OperatorFactory):
     def __init__(self, ctx, group_by_channels, step, aggregators, expected_groups=10_000, max_partial_memory=0, pre=None,
-                 global_aggregation_group_ids=(), group_id_channel=None, input_types=None, partial_aggregation_controller=None):
+                 global_aggregation_group_ids=(), group_id_channel=None, input_types=None, partial_aggregation_controller=None,
+                 row_typed_states=False):
         """global_aggregation_group_ids / group_id_channel (a group-by CHANNEL, like the reference's groupIdChannel) / input_types (tgpu_type
         per input channel): the default rows of global grouping sets over empty input (HashAggregationOperator.java:537-567)"""
         super().__init__()
@@ -499,12 +516,30 @@ class HashAggregationOperatorFactory(OperatorFactory):
         self.expected_groups, self.max_partial_memory, self.pre = expected_groups, max_partial_memory, pre
         self.global_ids, self.group_id_channel, self.input_types = list(global_aggregation_group_ids), group_id_channel, input_types
         self.controller = partial_aggregation_controller
+        self.row_typed_states = row_typed_states
+
+    def _state_widths(self):
+        """flat columns per aggregate state: avg's LongAndDoubleState is the only two-field state of the supported functions"""
+        return [2 if a.function == abi.AGG_AVG else 1 for a in self.aggregators]
 
     def _create(self):
-        keys = _i32(self.group_by_channels)
+        from_state = self.step in (abi.STEP_FINAL, abi.STEP_INTERMEDIATE)
+        to_state = self.step in (abi.STEP_PARTIAL, abi.STEP_INTERMEDIATE)
+        keys_list, agg_inputs = list(self.group_by_channels), [a.input_channel for a in self.aggregators]
+        if self.row_typed_states and from_state:
+            # channels are numbered as the Java plan numbers them (one channel per ROW state); the library sees the flattened page
+            wide = {a.input_channel for a in self.aggregators if a.function == abi.AGG_AVG}
+            top = max(keys_list + agg_inputs + [0])
+            first, at = [], 0
+            for c in range(top + 1):
+                first.append(at)
+                at += 2 if c in wide else 1
+            keys_list = [first[c] for c in keys_list]
+            agg_inputs = [first[c] if c >= 0 else c for c in agg_inputs]
+        keys = _i32(keys_list)
         fns = (abi.AggFn * max(1, len(self.aggregators)))()
         for i, a in enumerate(self.aggregators):
-            fns[i].function, fns[i].input_channel, fns[i].mask_channel = a.function, a.input_channel, a.mask_channel
+            fns[i].function, fns[i].input_channel, fns[i].mask_channel = a.function, agg_inputs[i], a.mask_channel
         gids = _i32(self.global_ids)
         types = _i32(list(self.input_types or []))
         spec = abi.AggSpec(len(self.group_by_channels), C.cast(keys, C.POINTER(C.c_int32)), self.step, len(self.aggregators),
@@ -516,13 +551,16 @@ class HashAggregationOperatorFactory(OperatorFactory):
                            self.controller.h if self.controller is not None else None)
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.tgpu_agg_create(self.ctx.h, C.byref(spec), C.byref(h)))
-        return HashAggregationOperator(self.ctx, h)
+        op = HashAggregationOperator(self.ctx, h)
+        if self.row_typed_states and to_state:
+            op._out_widths = [1] * len(self.group_by_channels) + self._state_widths()
+        return op
 
     def duplicate(self):
         return HashAggregationOperatorFactory(self.ctx, self.group_by_channels, self.step, self.aggregators, self.expected_groups,
                                               self.max_partial_memory, self.pre, self.global_ids, self.group_id_channel, self.input_types,
                                               # HashAggregationOperatorFactory.duplicate :238: a fresh controller for the duplicated plan node
-                                              self.controller.duplicate() if self.controller is not None else None)
+                                              self.controller.duplicate() if self.controller is not None else None, self.row_typed_states)
 
 
 class GroupByHash:

@@ -146,6 +146,67 @@ class RunLengthEncodedBlock:
         return self.value.get_positions(np.zeros(self.position_count, dtype=np.int64))
 
 
+class RowBlock:
+    """S/block/RowBlock.java:37-45,91-112: equally long field blocks plus optional row-level NULL flags.  This is the shape of a
+    multi-field aggregation state on the reference's wire (AccumulatorCompiler.java:687-760 writes one ROW entry per group through
+    RowBlockBuilder.buildEntry); the C ABI carries the fields as consecutive flat columns, so ROW blocks exist only on the host side
+    of the boundary: flatten_row_blocks() before add_input, compose_row_blocks() after get_output."""
+    type = -1      # no tgpu_type: never crosses the C ABI
+
+    def __init__(self, fields, row_nulls=None):
+        assert fields, "a row block needs at least one field"
+        self.fields = list(fields)
+        self.position_count = self.fields[0].position_count
+        for f in self.fields:
+            assert f.position_count == self.position_count, "field position counts differ"
+        self.row_nulls = None if row_nulls is None else np.asarray(row_nulls, dtype=bool)
+
+    def is_null(self, i):
+        return self.row_nulls is not None and bool(self.row_nulls[i])
+
+    def get(self, i):
+        return None if self.is_null(i) else tuple(f.get(i) for f in self.fields)
+
+    def to_pylist(self):
+        return [self.get(i) for i in range(self.position_count)]
+
+    def flatten(self):
+        return self
+
+    def null_suppressed_fields(self):
+        """RowBlock.getFieldBlocks of a block with NULL rows: a NULL row reads as NULL in every field"""
+        if self.row_nulls is None or not self.row_nulls.any():
+            return [f.flatten() for f in self.fields]
+        out = []
+        for f in self.fields:
+            f = f.flatten()
+            nulls = self.row_nulls if f.nulls is None else (f.nulls | self.row_nulls)
+            out.append(Block(f.type, f.values, nulls, f.offsets) if f.type == abi.UTF8 else Block(f.type, f.values, nulls))
+        return out
+
+
+def flatten_row_blocks(page):
+    """-> (page without ROW blocks, first flat channel of every original channel)"""
+    blocks, first = [], []
+    for b in page.blocks:
+        first.append(len(blocks))
+        if isinstance(b, RowBlock):
+            blocks.extend(b.null_suppressed_fields())
+        else:
+            blocks.append(b)
+    return Page(*blocks, position_count=page.position_count), first
+
+
+def compose_row_blocks(page, widths):
+    """widths[c] = number of consecutive flat channels that make up output channel c (1 = a plain block)"""
+    assert sum(widths) == page.channel_count, "row layout does not cover the page"
+    blocks, at = [], 0
+    for w in widths:
+        blocks.append(page.blocks[at] if w == 1 else RowBlock(page.blocks[at:at + w]))
+        at += w
+    return Page(*blocks, position_count=page.position_count)
+
+
 class Page:
     """S/Page.java:31"""
 
