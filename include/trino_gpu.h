@@ -428,7 +428,11 @@ int tgpu_comm_arena_create(tgpu_ctx* ctx, size_t bytes, uint8_t handles_out[TGPU
 int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles /* world x 2 x TGPU_IPC_HANDLE_BYTES, rank-major */);
 /* Hash-partition a device-resident page into `world` partitions and exchange: partition p goes to
  * rank p.  Returns the concatenation (in rank order) of what every rank sent here, as a
- * library-owned device page.  Fixed-width columns only.                                         */
+ * library-owned device page.  Fixed-width pages of a non-replicating partitioner take the multi-split transports (peer-memory
+ * stores / copy engines / NCCL); pages with variable-width (TGPU_UTF8) columns, more than 24 columns, and partitioners that
+ * replicate rows (null_channel rows and the replicatesAnyRow row reach EVERY rank, PagePartitioner.java:229-241,401-416) take the
+ * general path: the partitioner's own per-partition pages travel buffer by buffer through ncclSend/ncclRecv and the received
+ * chunks are concatenated in rank order - same rows, same order, library-owned buffers (no arena aliasing).                    */
 int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out);
 /* Same, for a pipeline in which another context of this process (`consumer`, e.g. the one running the LookupJoinOperator)
  * reads the exchanged pages: the exchange does not enter its closing barrier - after which peers may overwrite the arena of the
@@ -438,8 +442,8 @@ int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitioner, const 
 
 /* Broadcast exchange: the REPLICATED join distribution (FIXED_BROADCAST_DISTRIBUTION, M/sql/planner/SystemPartitioningHandle.java:51;
  * BroadcastOutputBuffer hands every page to every consumer): every rank receives the concatenation, in rank order, of the pages all
- * ranks passed in - the whole (small) build side on every GPU.  Collective: every rank calls it, also with an empty page.  Fixed-width
- * columns only.  With world == 1 it returns a copy of the page. */
+ * ranks passed in - the whole (small) build side on every GPU.  Collective: every rank calls it, also with an empty page.  Pages
+ * with variable-width columns go through the general exchange's chunk transfer.  With world == 1 it returns a copy of the page. */
 int tgpu_exchange_broadcast(tgpu_ctx* ctx, const tgpu_page* page, tgpu_page** out);
 
 /* Split-phase exchange for pipelines (one context): _begin partitions the page (multi-split into per-destination send

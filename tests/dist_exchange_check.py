@@ -165,12 +165,48 @@ def main():
         assert ctx.page_to_host(pp).rows() == want_seq[done], f"split-phase exchange {done} differs"
         done += 1
     assert done == len(seq)
+    # ---- general exchange: variable-width columns and replicated rows (nullChannel rows go to EVERY rank, the first row of the first
+    # page too: PagePartitioner.java:229-241,401-416).  Every rank regenerates every sender's page and partitions it with the oracle:
+    # the received page must be the senders' parts in rank order, each in the oracle's row order.
+    def general_page(r, salt):
+        g = np.random.default_rng(1000 * salt + r)
+        m = 4000 + 137 * r
+        keys = g.integers(0, 10**6, m)
+        return Page(Block.bigint(keys, g.random(m) < 0.02),
+                    Block.varchar([None if i % 11 == 0 else "s%d-%s" % (k, "x" * int(k % 7)) for i, k in enumerate(keys)]),
+                    Block.double(keys * 0.5, g.random(m) < 0.05))
+
+    for null_channel, any_row in ((-1, False), (0, False), (0, True)):
+        gpart = ops.PartitionedOutputOperatorFactory(ctx, [0], world, None, null_channel, any_row).create_operator()
+        states = [False] * world
+        for salt, split_phase in ((1, False), (2, True), (3, False)):
+            want = []
+            for r in range(world):
+                pg = general_page(r, salt)
+                lists, states[r] = o.partition_positions(pg, [0], world, None, world, null_channel, any_row, states[r])
+                rows_r = pg.rows()
+                want += [rows_r[i] for i in lists[rank]]
+            ap = AbiPage(general_page(rank, salt))
+            pp = abi.PP()
+            if split_phase:
+                h = C.c_void_p()
+                ctx.check(lib.tgpu_exchange_begin(ctx.h, gpart.h, ap.ref(), C.byref(h)))
+                ctx.check(lib.tgpu_exchange_end(ctx.h, h, C.byref(pp)))
+            else:
+                ctx.check(lib.tgpu_exchange_partitioned(ctx.h, gpart.h, ap.ref(), C.byref(pp)))
+            got = ctx.page_to_host(pp).rows()
+            assert got == want, f"general exchange differs (null_channel={null_channel}, any_row={any_row}, page {salt}): {len(got)} vs {len(want)} rows"
+        gpart.close()
+    # broadcast of a page with a variable-width column: every rank ends up with every rank's rows, in rank order
+    pp = abi.PP()
+    ctx.check(lib.tgpu_exchange_broadcast(ctx.h, AbiPage(general_page(rank, 9)).ref(), C.byref(pp)))
+    assert ctx.page_to_host(pp).rows() == [row for r in range(world) for row in general_page(r, 9).rows()]
     part.close()
     pctx.close()
     ctx.check(lib.tgpu_comm_destroy(ctx.h))
     dist.barrier()
     if rank == 0:
-        print(f"dist_exchange_check ok (NCCL, P2P, fenced and split-phase paths): world={world} rows={total_rows}")
+        print(f"dist_exchange_check ok (NCCL, P2P, fenced, split-phase and general paths): world={world} rows={total_rows}")
     dist.destroy_process_group()
     ctx.close()
 

@@ -442,7 +442,7 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
 {
     constexpr int R = TGD_G_ROWS;
     const unsigned long long mask = (unsigned long long)cap - 1;
-    const int way = (threadIdx.x + blockIdx.x * 7) & (TGD_TICKET_WAYS - 1);
+    const int way = ((threadIdx.x >> 5) + blockIdx.x * 8) & (TGD_TICKET_WAYS - 1);      // one ticket word per warp at a time
     const int lane = threadIdx.x & 31;
     unsigned int err = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -457,7 +457,7 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
             row[j] = i < n ? (rows ? (long long)rows[i] : first + i) : -1;
             if (row[j] >= 0) prog.load(cols, row[j], regs[j]);
         }
-        unsigned long long pk[R], pos[R], cur[R];
+        unsigned long long pk[R], pos[R], cur[R], nxt[R];
         long long slot[R];
         bool open[R];        // still looking for its slot
 #pragma unroll
@@ -469,25 +469,51 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
             slot[j] = (row[j] >= 0 && sp >= 0) ? cap + sp : -1;
             open[j] = row[j] >= 0 && sp < 0;
         }
+        // the key of the home slot AND of its successor are requested together: a row that has to move on finds the next key already
+        // on its way, so the trips of the loop below overlap their L2 round trips instead of adding them up
 #pragma unroll
-        for (int j = 0; j < R; j++) cur[j] = open[j] ? *((volatile unsigned long long*)(recs + (size_t)pos[j] * W)) : 0;
-        // lock-step probing: one step of every open row per trip, the warp stays converged
+        for (int j = 0; j < R; j++) {
+            cur[j] = open[j] ? *((volatile unsigned long long*)(recs + (size_t)pos[j] * W)) : 0;
+            nxt[j] = open[j] ? *((volatile unsigned long long*)(recs + (size_t)((pos[j] + 1) & mask) * W)) : 0;
+        }
+        // lock-step probing: one step of every open row per trip, the warp stays converged.  Insertions draw their tickets (the fill
+        // limit of the table) once per warp and trip: ncu on the per-row form showed a third of all stall samples waiting for the
+        // returning atomicAdd on 64 ticket words that 10 M insertions were serialising on.
         while (true) {
             bool any = false;
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                if (!open[j]) continue;
+                bool active = open[j];
                 unsigned long long c = cur[j];
-                if (c == TGD_EMPTY_KEY) {
-                    if (atomicAdd(tickets + way, 1) >= budget_per_way) { atomicSub(tickets + way, 1); open[j] = false; continue; }   // no room: deferred below
-                    c = atomicCAS(recs + (size_t)pos[j] * W, TGD_EMPTY_KEY, pk[j]);
-                    if (c == TGD_EMPTY_KEY) { slot[j] = (long long)pos[j]; open[j] = false; continue; }
-                    atomicSub(tickets + way, 1);       // lost the race for the slot: the claim was not consumed
+                const bool want = active && c == TGD_EMPTY_KEY;
+                const unsigned int wmask = __ballot_sync(0xffffffffu, want);
+                if (wmask) {
+                    const int cnt = __popc(wmask), leader = __ffs(wmask) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(tickets + way, cnt);
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    const bool granted = want && base + __popc(wmask & ((1u << lane) - 1)) < budget_per_way;
+                    int give_back = base + cnt - budget_per_way;           // tickets drawn beyond the budget
+                    give_back = give_back < 0 ? 0 : (give_back > cnt ? cnt : give_back);
+                    bool won = false;
+                    if (granted) {
+                        c = atomicCAS(recs + (size_t)pos[j] * W, TGD_EMPTY_KEY, pk[j]);
+                        won = c == TGD_EMPTY_KEY;
+                    }
+                    give_back += __popc(__ballot_sync(0xffffffffu, granted && !won));      // lost the race for the slot: the claim was not consumed
+                    if (lane == leader && give_back) atomicSub(tickets + way, give_back);
+                    if (want && !granted) { open[j] = false; active = false; }              // no room: deferred below
+                    if (won) { slot[j] = (long long)pos[j]; open[j] = false; active = false; }
                 }
-                if (c == pk[j]) { slot[j] = (long long)pos[j]; open[j] = false; continue; }
-                pos[j] = (pos[j] + 1) & mask;
-                cur[j] = *((volatile unsigned long long*)(recs + (size_t)pos[j] * W));
-                any = true;
+                if (active) {
+                    if (c == pk[j]) { slot[j] = (long long)pos[j]; open[j] = false; }
+                    else {
+                        pos[j] = (pos[j] + 1) & mask;
+                        cur[j] = nxt[j];
+                        nxt[j] = *((volatile unsigned long long*)(recs + (size_t)((pos[j] + 1) & mask) * W));
+                        any = true;
+                    }
+                }
             }
             if (!__any_sync(0xffffffffu, any)) break;
         }

@@ -598,6 +598,193 @@ extern "C" int tgpu_comm_arena_open(tgpu_ctx* ctx, const uint8_t* all_handles)
     return TGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// General exchange: everything the PagePartitioner can emit - variable-width columns, rows replicated to every partition
+// (nullChannel rows and the single replicatesAnyRow row, PagePartitioner.java:229-241,401-416), more than XMAXC / 2 columns.  The
+// operator itself partitions the page (its sort + compose path), the per-destination pages travel as ncclSend/ncclRecv per buffer
+// (values, offsets + bytes, validity bitmap), and the chunks received from rank 0..W-1 are concatenated in rank order, which is the
+// row order the fixed-width paths produce.  Three host round trips (part sizes, the all-gathered size matrix, the final sync): this
+// is the completeness path, the multi-split paths above are the fast ones.
+// ------------------------------------------------------------------------------------------------
+namespace {
+bool exchange_needs_general_path(const PartitionOp* p, const tgpu_page* page)
+{
+    if (p->null_channel >= 0 || p->replicates_any_row) return true;
+    if (2 * page->num_columns > XMAXC) return true;
+    for (int c = 0; c < page->num_columns; c++) {
+        const tgpu_column& col = page->columns[c];
+        int type = (col.type == TGPU_DICT32 || col.type == TGPU_RLE) && col.dictionary ? col.dictionary->type : col.type;
+        if (type == TGPU_UTF8) return true;
+    }
+    return false;
+}
+
+// part[d]: the rows this rank has for rank d (nullptr = none); the parts must stay alive until this returns
+int exchange_pages(tgpu_ctx* ctx, const std::vector<const DevPage*>& part, const std::vector<int32_t>& types, tgpu_page** out)
+{
+    const int W = ctx->world, me = ctx->rank, C = (int)types.size();
+    // 2. sizes: per destination {rows, then per column: has validity, first offset, value bytes}
+    const int V = 1 + 3 * C;
+    std::vector<long long> mine((size_t)W * V, 0);
+    for (int d = 0; d < W; d++) {
+        if (!part[d]) continue;
+        const DevPage& pg = *part[d];
+        mine[(size_t)d * V] = pg.rows;
+        for (int c = 0; c < C; c++) {
+            const DevColumn& col = pg.cols[c];
+            mine[(size_t)d * V + 1 + 3 * c] = col.validity ? 1 : 0;
+            if (col.type == TGPU_UTF8 && pg.rows > 0) {
+                int32_t ends[2] = {0, 0};
+                TG_CUDA(ctx, cudaMemcpyAsync(&ends[0], col.offsets, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                TG_CUDA(ctx, cudaMemcpyAsync(&ends[1], col.offsets + pg.rows, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                mine[(size_t)d * V + 2 + 3 * c] = ends[0];
+                mine[(size_t)d * V + 3 + 3 * c] = ends[1] - ends[0];
+            }
+        }
+    }
+    std::vector<long long> all((size_t)W * W * V);
+    {
+        DevBuf d_mine, d_all;
+        TG_TRY(d_mine.alloc(ctx, mine.size() * 8));
+        TG_TRY(d_all.alloc(ctx, all.size() * 8));
+        TG_CUDA(ctx, cudaMemcpyAsync(d_mine.p, mine.data(), mine.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (W > 1) TG_NCCL(ctx, g_nccl.all_gather(d_mine.p, d_all.p, mine.size(), NCCL_INT64, ctx->comm, ctx->stream));
+        else TG_CUDA(ctx, cudaMemcpyAsync(d_all.p, d_mine.p, mine.size() * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        TG_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all.p, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    auto info = [&](int sender, int dest, int k) { return all[((size_t)sender * W + dest) * V + k]; };
+    long long total_recv = 0;
+    for (int r = 0; r < W; r++) total_recv += info(r, me, 0);
+    if (total_recv > (long long)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INSUFFICIENT_RESOURCES, "exchange output exceeds 2^31-1 rows on rank %d", me);
+    // 3. receive chunks: one DevColumn per (sender, column); this rank's own part is used in place
+    std::vector<std::vector<DevColumn>> chunk(W, std::vector<DevColumn>(C));
+    for (int r = 0; r < W; r++) {
+        const long long rows = info(r, me, 0);
+        if (r == me) {
+            if (part[me]) chunk[r] = part[me]->cols;        // (shares the buffers)
+            continue;
+        }
+        for (int c = 0; c < C && rows > 0; c++) {
+            DevColumn& col = chunk[r][c];
+            col.type = types[c];
+            col.length = rows;
+            if (types[c] == TGPU_UTF8) {
+                const long long first = info(r, me, 2 + 3 * c), bytes = info(r, me, 3 + 3 * c);
+                col.own_offsets = std::make_shared<DevBuf>();
+                TG_TRY(col.own_offsets->alloc(ctx, (size_t)(rows + 1) * 4));
+                col.offsets = col.own_offsets->as<int32_t>();
+                col.own_data = std::make_shared<DevBuf>();
+                TG_TRY(col.own_data->alloc(ctx, (size_t)std::max<long long>(bytes, 1)));
+                col.data = (const char*)col.own_data->p - first;            // the sender's offsets stay as they are
+                col.data_bytes = bytes;
+            }
+            else {
+                col.own_data = std::make_shared<DevBuf>();
+                TG_TRY(col.own_data->alloc(ctx, (size_t)rows * col.elem_size()));
+                col.data = col.own_data->p;
+            }
+            if (info(r, me, 1 + 3 * c)) {
+                col.own_validity = std::make_shared<DevBuf>();
+                TG_TRY(col.own_validity->alloc(ctx, (size_t)((rows + 7) / 8)));
+                col.validity = col.own_validity->as<uint8_t>();
+            }
+        }
+    }
+    // 4. one NCCL group: every buffer of every part to its destination, every chunk buffer from its sender (same order on both sides)
+    if (W > 1) {
+        TG_NCCL(ctx, g_nccl.group_start());
+        for (int peer = 0; peer < W; peer++) {
+            if (peer == me) continue;
+            if (part[peer] && part[peer]->rows > 0) {
+                const DevPage& pg = *part[peer];
+                for (int c = 0; c < C; c++) {
+                    const DevColumn& col = pg.cols[c];
+                    if (col.type == TGPU_UTF8) {
+                        const long long first = mine[(size_t)peer * V + 2 + 3 * c], bytes = mine[(size_t)peer * V + 3 + 3 * c];
+                        TG_NCCL(ctx, g_nccl.send(col.offsets, (size_t)(pg.rows + 1) * 4, NCCL_INT8, peer, ctx->comm, ctx->stream));
+                        if (bytes > 0) TG_NCCL(ctx, g_nccl.send((const char*)col.data + first, (size_t)bytes, NCCL_INT8, peer, ctx->comm, ctx->stream));
+                    }
+                    else TG_NCCL(ctx, g_nccl.send(col.data, (size_t)pg.rows * col.elem_size(), NCCL_INT8, peer, ctx->comm, ctx->stream));
+                    if (col.validity) TG_NCCL(ctx, g_nccl.send(col.validity, (size_t)((pg.rows + 7) / 8), NCCL_INT8, peer, ctx->comm, ctx->stream));
+                }
+            }
+            const long long rows = info(peer, me, 0);
+            for (int c = 0; c < C && rows > 0; c++) {
+                DevColumn& col = chunk[peer][c];
+                if (col.type == TGPU_UTF8) {
+                    TG_NCCL(ctx, g_nccl.recv(col.own_offsets->p, (size_t)(rows + 1) * 4, NCCL_INT8, peer, ctx->comm, ctx->stream));
+                    if (col.data_bytes > 0) TG_NCCL(ctx, g_nccl.recv(col.own_data->p, (size_t)col.data_bytes, NCCL_INT8, peer, ctx->comm, ctx->stream));
+                }
+                else TG_NCCL(ctx, g_nccl.recv(col.own_data->p, (size_t)rows * col.elem_size(), NCCL_INT8, peer, ctx->comm, ctx->stream));
+                if (col.validity) TG_NCCL(ctx, g_nccl.recv(col.own_validity->p, (size_t)((rows + 7) / 8), NCCL_INT8, peer, ctx->comm, ctx->stream));
+            }
+        }
+        TG_NCCL(ctx, g_nccl.group_end());
+    }
+    // 5. the output page: chunks in sender order
+    DevPage outp;
+    outp.rows = total_recv;
+    outp.cols.resize(C);
+    for (int c = 0; c < C; c++) {
+        std::vector<const DevColumn*> parts;
+        for (int r = 0; r < W; r++)
+            if (info(r, me, 0) > 0) parts.push_back(&chunk[r][c]);
+        if (parts.empty()) {
+            // nothing arrived: an empty column of the right type
+            DevColumn e;
+            e.type = types[c];
+            e.own_data = std::make_shared<DevBuf>();
+            TG_TRY(e.own_data->alloc(ctx, 8));
+            e.data = e.own_data->p;
+            if (types[c] == TGPU_UTF8) {
+                e.own_offsets = std::make_shared<DevBuf>();
+                TG_TRY(e.own_offsets->alloc(ctx, 4));
+                TG_CUDA(ctx, cudaMemsetAsync(e.own_offsets->p, 0, 4, ctx->stream));
+                e.offsets = e.own_offsets->as<int32_t>();
+            }
+            outp.cols[c] = std::move(e);
+        }
+        else if (parts.size() == 1) outp.cols[c] = *parts[0];
+        else TG_TRY(tg_concat_columns(ctx, parts, &outp.cols[c]));
+    }
+    TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the caller releases the parts next: the sends must have left them
+    OwnedPage* o = tg_make_owned_page(std::move(outp));
+    *out = &o->hdr;
+    return TGPU_OK;
+}
+
+std::vector<int32_t> value_types_of(const tgpu_page* page)
+{
+    std::vector<int32_t> types(page->num_columns);
+    for (int c = 0; c < page->num_columns; c++) {
+        const tgpu_column& col = page->columns[c];
+        types[c] = (col.type == TGPU_DICT32 || col.type == TGPU_RLE) && col.dictionary ? col.dictionary->type : col.type;
+    }
+    return types;
+}
+
+int exchange_general(tgpu_ctx* ctx, PartitionOp* p, const tgpu_page* page, tgpu_page** out)
+{
+    const int W = ctx->world;
+    // 1. partition locally: at most one page per destination
+    TG_TRY(p->add_input(page));
+    std::vector<std::unique_ptr<OwnedPage>> owned(W);
+    for (size_t i = p->next_out; i < p->pending.size(); i++) {
+        OwnedPage* o = p->pending[i];
+        if (o->partition < 0 || o->partition >= W || owned[o->partition]) { delete o; continue; }
+        owned[o->partition].reset(o);
+    }
+    p->pending.clear();
+    p->next_out = 0;
+    std::vector<const DevPage*> part(W, nullptr);
+    for (int d = 0; d < W; d++)
+        if (owned[d]) part[d] = &owned[d]->page;
+    return exchange_pages(ctx, part, value_types_of(page), out);
+}
+}  // namespace
+
 extern "C" int tgpu_exchange_partitioned(tgpu_ctx* ctx, tgpu_op* partitioner, const tgpu_page* page, tgpu_page** out)
 {
     return tgpu_exchange_partitioned_fenced(ctx, partitioner, page, nullptr, out);
@@ -612,14 +799,11 @@ extern "C" int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitio
     if (!ctx->comm) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "tgpu_comm_init has not been called");
     const int W = ctx->world;
     if (p->partition_count != W) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition count %d != world size %d", p->partition_count, W);
-    if (p->null_channel >= 0 || p->replicates_any_row) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "replicating partitioners are not supported by the exchange");
     int64_t n = page->num_rows;
     if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+    if (exchange_needs_general_path(p, page) || W > XMAXP) return exchange_general(ctx, p, page, out);
     DevPage in;
     TG_TRY(tg_ingest_page(ctx, page, &in));
-    for (auto& c : in.cols)
-        if (c.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
-    if (W > XMAXP) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange across more than %d ranks", XMAXP);
     // TGPU_TRACE=1: synchronise and print the wall time of every phase (diagnostics only)
     const bool trace = getenv("TGPU_TRACE") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
@@ -631,7 +815,6 @@ extern "C" int tgpu_exchange_partitioned_fenced(tgpu_ctx* ctx, tgpu_op* partitio
         t_last = now;
     };
     const int C = (int)in.cols.size();
-    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);   // (every column may need a NULL-byte lane)
     // 1. partition ids + per-CTA histograms + offsets (stable multi-split, no sort)
     const XchgGeom geom = xchg_geom(ctx, n, W, W > 1);
     const int grid = geom.nchunks;
@@ -842,8 +1025,18 @@ extern "C" int tgpu_exchange_broadcast(tgpu_ctx* ctx, const tgpu_page* page, tgp
     DevPage in;
     TG_TRY(tg_ingest_page(ctx, page, &in));
     const int C = (int)in.cols.size();
-    for (auto& c : in.cols)
-        if (c.elem_size() == 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
+    bool variable_width = false;
+    for (auto& c : in.cols) variable_width = variable_width || c.elem_size() == 0;
+    if (variable_width) {
+        // variable-width columns: every rank's page goes to every rank through the general exchange (offsets + bytes per chunk)
+        if (W == 1) {
+            OwnedPage* o = tg_make_owned_page(std::move(in));
+            *out = &o->hdr;
+            return TGPU_OK;
+        }
+        std::vector<const DevPage*> part(W, &in);
+        return exchange_pages(ctx, part, value_types_of(page), out);
+    }
     const int64_t n = in.rows;
     // count matrix: rows and one "has NULLs" flag per column from every rank
     const int V = 1 + C;
@@ -943,6 +1136,7 @@ struct tgpu_exchange {
     int arena = 0;
     long long total_recv = 0;
     cudaEvent_t done = nullptr;
+    tgpu_page* ready = nullptr;       // the general (blocking) path ran inside begin: the finished page
     ~tgpu_exchange() { if (done) cudaEventDestroy(done); }
 };
 
@@ -958,16 +1152,20 @@ extern "C" int tgpu_exchange_begin(tgpu_ctx* ctx, tgpu_op* partitioner, const tg
     if (ctx->exchanges_in_flight >= 2) return tg_fail(ctx, TGPU_ERR_ILLEGAL_STATE, "more than two exchanges in flight on one context");
     const int W = ctx->world;
     if (p->partition_count != W) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition count %d != world size %d", p->partition_count, W);
-    if (p->null_channel >= 0 || p->replicates_any_row) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "replicating partitioners are not supported by the exchange");
-    if (W > XMAXP) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange across more than %d ranks", XMAXP);
     const int64_t n = page->num_rows;
     if (n > (int64_t)INT32_MAX) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has more than 2^31-1 positions");
+    if (exchange_needs_general_path(p, page) || W > XMAXP) {
+        // shapes the copy-engine form does not carry (variable width, replicated rows): the blocking general exchange runs here, _end
+        // hands its page over.  Every rank takes this branch for the same exchange (the shape is a property of the plan, not of the data).
+        std::unique_ptr<tgpu_exchange> g(new tgpu_exchange());
+        TG_TRY(exchange_general(ctx, p, page, &g->ready));
+        ctx->exchanges_in_flight++;
+        *out = g.release();
+        return TGPU_OK;
+    }
     DevPage in;
     TG_TRY(tg_ingest_page(ctx, page, &in));
-    for (auto& c : in.cols)
-        if (c.type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "variable-width columns are not supported by the exchange yet");
     const int C = (int)in.cols.size();
-    if (2 * C > XMAXC) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "exchange of more than %d columns", XMAXC / 2);   // (every column may need a NULL-byte lane)
     // 1. partition ids, histograms, offsets.  Every destination of the scatter is LOCAL memory here (send buffers and this
     //    rank's own arena), so the warp-granular kernels apply.
     const XchgGeom geom = xchg_geom(ctx, n, W, false);
@@ -1102,6 +1300,7 @@ extern "C" int tgpu_exchange_end(tgpu_ctx* ctx, tgpu_exchange* exchange, tgpu_pa
     std::unique_ptr<tgpu_exchange> x(exchange);
     ctx->exchanges_in_flight--;
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (x->ready) { *out = x->ready; return TGPU_OK; }
     // the received rows are complete once this rank's barrier has run; everything below is ordered behind it on ctx->stream
     TG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, x->done, 0));
     DevPage outp;
