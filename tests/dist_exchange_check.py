@@ -199,7 +199,8 @@ def main():
         gpart.close()
     # broadcast of a page with a variable-width column: every rank ends up with every rank's rows, in rank order
     pp = abi.PP()
-    ctx.check(lib.tgpu_exchange_broadcast(ctx.h, AbiPage(general_page(rank, 9)).ref(), C.byref(pp)))
+    bap = AbiPage(general_page(rank, 9))          # (kept alive across the call: the descriptor points into its arrays)
+    ctx.check(lib.tgpu_exchange_broadcast(ctx.h, bap.ref(), C.byref(pp)))
     assert ctx.page_to_host(pp).rows() == [row for r in range(world) for row in general_page(r, 9).rows()]
     part.close()
     pctx.close()

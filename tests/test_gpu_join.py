@@ -384,6 +384,26 @@ def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
     assert got == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
 
 
+def test_build_over_a_random_half_of_a_dense_domain_stays_fast(ctx):
+    # what a 2-way hash exchange leaves on a rank: a hash-selected half of the order keys.  The dense trial geometry does not suit it
+    # (lines of 32 key values expect exactly 8 keys) and used to degenerate into chains thousands of lines long - 174 s for 75 M rows
+    # on a B200; trial geometries are bounded now and the build falls through to the roomy / scattered layouts in milliseconds.
+    import time
+    n_orders = 12_000_000
+    okeys = o.synth_orders_keys(n_orders, 0, n_orders, 0x7C02, True)
+    mine = okeys[o.partition_ids(Page(Block.bigint(okeys)), [0], 2) == 1]
+    build = Page(Block.bigint(mine))
+    t0 = time.time()
+    b, lk = _build_lookup(ctx, [build])
+    ctx.synchronize()
+    elapsed = time.time() - t0
+    assert elapsed < 5.0, f"build of {len(mine)} rows took {elapsed:.1f} s"
+    probe_keys = np.concatenate([mine[::7], okeys[:100_000]])
+    oj = o.Join(build, [0])
+    assert (lk.get_join_positions(Page(Block.bigint(probe_keys))) == oj.positions(Page(Block.bigint(probe_keys)), [0])).all()
+    oj.close(); b.close(); lk.close()
+
+
 def test_join_keys_sharing_a_64_bit_row_hash_are_kept_apart(ctx):
     # round 1 answered NOT_SUPPORTED when two different key tuples shared one row hash; now the build moves one of them to its next hash
     # function and the probe follows (DefaultPagesHash compares the values on every hash hit: M/operator/join/DefaultPagesHash.java:246-260)

@@ -35,6 +35,17 @@ def test_q1_kernel_compiles_and_drops_redundant_counters():
     assert "tg_agg_small_jit" in src and "vm_apply(3, 1" in src
 
 
+def test_vector_loader_variant_compiles(monkeypatch):
+    # the kernel launched for 16-byte aligned columns: four consecutive rows per thread through 16-byte loads
+    monkeypatch.setenv("TGPU_JIT_SELFTEST_VEC", "1")
+    for mask in (0, 0b1111000):
+        st, size, src = _selftest(mask)
+        if st == abi.ERR_NOT_SUPPORTED:
+            pytest.skip("NVRTC not installed")
+        assert st == 0, src
+        assert "VEC = true" in src and "load4" in src and "const longlong2* p" in src
+
+
 def test_nullable_channels_keep_their_counters():
     st, size, src = _selftest(0b1111000)      # quantity, extendedprice, discount, tax carry NULLs
     if st == abi.ERR_NOT_SUPPORTED:

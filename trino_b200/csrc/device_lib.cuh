@@ -347,17 +347,25 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
     constexpr int R = P::R;
     const int64_t stride = (int64_t)gridDim.x * T;
     bool stop = false;
-    for (int64_t base = (int64_t)blockIdx.x * T + tid; base < n && !stop; base += stride * R) {
+    // VEC: a thread owns R = 4 CONSECUTIVE rows per trip (16-byte loads, a warp reads 128 consecutive rows of every column);
+    // otherwise its R rows are a grid stride apart.  Either way the rows of one thread ascend.
+    static_assert(!P::VEC || R == 4, "the vector loader handles four rows");
+    const int64_t first = P::VEC ? ((int64_t)blockIdx.x * T + tid) * R : (int64_t)blockIdx.x * T + tid;
+    const int64_t row_step = P::VEC ? 1 : stride;
+    for (int64_t base = first; base < n && !stop; base += stride * R) {
         if (*((volatile int*)&s_overflow)) break;   // some thread of this CTA ran out of key slots: the pass is void
         typename P::Regs regs[R];
+        if (P::VEC && base + R <= n) prog.load4(cols, base, regs);
+        else {
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            int64_t row = base + (int64_t)j * stride;
-            if (row < n) prog.load(cols, row, regs[j]);
+            for (int j = 0; j < R; j++) {
+                int64_t row = base + (int64_t)j * row_step;
+                if (row < n) prog.load(cols, row, regs[j]);
+            }
         }
 #pragma unroll
         for (int j = 0; j < R; j++) {
-            int64_t row = base + (int64_t)j * stride;
+            int64_t row = base + (int64_t)j * row_step;
             if (row >= n || stop) continue;
             unsigned long long pk = 0;
             int special = -1;

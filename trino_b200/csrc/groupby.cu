@@ -1170,7 +1170,7 @@ static std::string gen_operand(const DOperand& o)
 
 // `elems[c]` = element size of input channel c (0 = not a fixed-width column); bit c of nullable_mask = channel c has a validity bitmap
 static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* prog, const int* elems, int num_channels, int L, int min_blocks,
-                                        uint32_t nullable_mask, AccMap* map)
+                                        uint32_t nullable_mask, AccMap* map, bool vec = false)
 {
     std::string s;
     bool used[TGPU_MAX_CHANNELS] = {false};
@@ -1226,7 +1226,7 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
     }
     map->compact_count = compact;
 
-    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4;\n", L, compact);
+    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4;\n  static constexpr bool VEC = %s;\n", L, compact, vec ? "true" : "false");
     s += "  __device__ static __forceinline__ int acc_kind(int a) {\n    switch (a) {\n";
     for (int a = 0; a < compact; a++) appendf(s, "      case %d: return %d;\n", a, kinds[a]);
     s += "      default: return 0;\n    }\n  }\n";
@@ -1242,6 +1242,35 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
         appendf(s, "    r.c%d = tg_load_elem<%d>(cols.cols[%d].data, row);", c, elems[c], c);
         if ((nullable_mask >> c) & 1) appendf(s, " r.c%dn = !tg_valid(cols.cols[%d].validity, row);\n", c, c);
         else appendf(s, " r.c%dn = false;\n", c);
+    }
+    s += "  }\n";
+    // the same for FOUR CONSECUTIVE rows starting at a multiple of 4 (VEC kernels: every column base is 16-byte aligned): one or two
+    // 16-byte loads per wide column, one 4-byte load per INT8 column, the four validity bits from one byte
+    s += "  __device__ __forceinline__ void load4(const DColumns& cols, long long row0, Regs (&r)[4]) {\n";
+    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) {
+        if (!used[c]) continue;
+        switch (elems[c]) {
+            case 8:
+                appendf(s, "    { const longlong2* p = (const longlong2*)((const char*)cols.cols[%d].data + row0 * 8); longlong2 a = p[0], b = p[1];"
+                           " r[0].c%d = a.x; r[1].c%d = a.y; r[2].c%d = b.x; r[3].c%d = b.y; }\n", c, c, c, c, c);
+                break;
+            case 4:
+                appendf(s, "    { int4 a = *(const int4*)((const char*)cols.cols[%d].data + row0 * 4); r[0].c%d = a.x; r[1].c%d = a.y; r[2].c%d = a.z; r[3].c%d = a.w; }\n",
+                        c, c, c, c, c);
+                break;
+            case 2:
+                appendf(s, "    { short4 a = *(const short4*)((const char*)cols.cols[%d].data + row0 * 2); r[0].c%d = a.x; r[1].c%d = a.y; r[2].c%d = a.z; r[3].c%d = a.w; }\n",
+                        c, c, c, c, c);
+                break;
+            default:
+                appendf(s, "    { char4 a = *(const char4*)((const char*)cols.cols[%d].data + row0); r[0].c%d = a.x; r[1].c%d = a.y; r[2].c%d = a.z; r[3].c%d = a.w; }\n",
+                        c, c, c, c, c);
+                break;
+        }
+        if ((nullable_mask >> c) & 1)
+            appendf(s, "    { const uint8_t* v = cols.cols[%d].validity; unsigned int b = v ? ((unsigned int)v[row0 >> 3] >> (row0 & 7)) : 0xfu;"
+                       " r[0].c%dn = !(b & 1); r[1].c%dn = !(b & 2); r[2].c%dn = !(b & 4); r[3].c%dn = !(b & 8); }\n", c, c, c, c, c);
+        else appendf(s, "    r[0].c%dn = r[1].c%dn = r[2].c%dn = r[3].c%dn = false;\n", c, c, c, c);
     }
     s += "  }\n";
     s += "  __device__ __forceinline__ bool row(const Regs& r, unsigned long long* pk, int* special, unsigned int* err) {\n";
@@ -1729,11 +1758,16 @@ struct AggOp : tgpu_op {
             if (jit_elems.empty()) jit_elems.assign(elems, elems + TGPU_MAX_CHANNELS);
             for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++)
                 if (jit_elems[c] != elems[c]) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "channel %zu changed its type between pages", c);
-            uint64_t vkey = ((uint64_t)L << 32) | nullable;
+            // four consecutive rows per thread through 16-byte loads when every column starts on a 16-byte boundary (always true for
+            // library-owned and cudaMalloc'ed columns; a caller's sliced device column may not be)
+            bool vec = !getenv("TGPU_AGG_S_NO_VEC");
+            for (size_t c = 0; c < in.cols.size() && c < TGPU_MAX_CHANNELS; c++)
+                vec = vec && ((uintptr_t)in.cols[c].data & 15) == 0;
+            uint64_t vkey = ((uint64_t)L << 32) | nullable | (vec ? 1ULL << 63 : 0);
             auto it = jit_variants.find(vkey);
             if (it == jit_variants.end()) {
                 JitVariant v;
-                std::string src = gen_agg_small_source(plan, has_pre ? &host_prog : nullptr, elems, (int)in.cols.size(), L, ctas_per_sm, nullable, &v.map);
+                std::string src = gen_agg_small_source(plan, has_pre ? &host_prog : nullptr, elems, (int)in.cols.size(), L, ctas_per_sm, nullable, &v.map, vec);
                 // a generated program that does not compile is a bug, not a fallback case
                 TG_TRY(jit_get_function(ctx, src, "tg_agg_small_jit", &v.fn));
                 it = jit_variants.emplace(vkey, v).first;
@@ -2942,7 +2976,9 @@ extern "C" int tgpu_jit_selftest_agg(const tgpu_agg_spec* spec, const int32_t* c
     int st = op->make_plan(in);
     if (st != TGPU_OK) return st;
     AccMap map;
-    std::string src = gen_agg_small_source(op->plan, op->has_pre ? &op->host_prog : nullptr, elems, num_channels, 4, 2, nullable_mask, &map);
+    // (TGPU_JIT_SELFTEST_VEC: the variant with the four-consecutive-rows loader, as launched for 16-byte aligned columns)
+    std::string src = gen_agg_small_source(op->plan, op->has_pre ? &op->host_prog : nullptr, elems, num_channels, 4, 2, nullable_mask, &map,
+                                           getenv("TGPU_JIT_SELFTEST_VEC") != nullptr);
     if (source_out && source_cap > 0) { strncpy(source_out, src.c_str(), (size_t)source_cap - 1); source_out[source_cap - 1] = 0; }
     std::string cubin;
     st = tg::jit_compile_cubin(&fake, src, &cubin);

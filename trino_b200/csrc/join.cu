@@ -100,14 +100,20 @@ __global__ void join_table_init_kernel(int4* table, int64_t slots)
 }
 
 // one thread per build row: claim/find the key's slot, head = max(row).  *dup_flag is set when a key repeats.
-// moved[0] += rows that left their home line, moved[1] += rows that went more than 8 lines away (layout quality of modes 1 / 2)
+// moved[0] += rows that left their home line, moved[1] += rows that went more than 8 lines away (layout quality of modes 1 / 2).
+// give_up_lines > 0 (a TRIAL geometry): a row that would have to move further than that many lines is not inserted and counted in
+// *gave_up, and once more than give_up_limit rows did so the whole pass stops - the host rejects the geometry, so the rest of the
+// table is never needed.  (Without the bound a geometry that does not suit the keys - e.g. the dense lines over the random half of an
+// order-key domain that a hash exchange leaves on a rank - clusters into chains thousands of lines long: 174 s for 75 M rows, measured.)
 __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, int64_t n, JoinSlot* __restrict__ table, JoinGeom geo,
-                                                         int* __restrict__ special_head, int* __restrict__ dup_flag, unsigned int* __restrict__ moved)
+                                                         int* __restrict__ special_head, int* __restrict__ dup_flag, unsigned int* __restrict__ moved,
+                                                         int give_up_lines, unsigned int give_up_limit, unsigned int* __restrict__ gave_up)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned int left_home = 0, went_far = 0;
     for (; i < n; i += stride) {
+        if (give_up_lines > 0 && *((volatile unsigned int*)gave_up) > give_up_limit) break;
         unsigned long long k;
         if (!join_key(key, kind, i, &k)) continue;
         if (k == EMPTY_KEY) {
@@ -117,6 +123,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
         }
         unsigned long long pos = join_slot_of(k, geo);
         const unsigned long long home = pos >> 3;
+        bool placed = true;
         while (true) {
             unsigned long long cur = *((volatile unsigned long long*)&table[pos].key);
             if (cur == EMPTY_KEY) cur = atomicCAS(&table[pos].key, EMPTY_KEY, k);
@@ -126,7 +133,9 @@ __global__ void __launch_bounds__(256) join_build_kernel(ColRef key, int kind, i
                 break;
             }
             pos = join_next_slot(pos, k, geo);
+            if (give_up_lines > 0 && (((pos >> 3) - home) & (geo.mask >> 3)) > (unsigned long long)give_up_lines) { placed = false; break; }
         }
+        if (!placed) { atomicAdd(gave_up, 1u); continue; }
         if (geo.mode != 0 && (pos >> 3) != home) {
             left_home++;
             went_far += (((pos >> 3) - home) & (geo.mask >> 3)) > 8;
@@ -1147,6 +1156,7 @@ struct JoinBuildOp : tgpu_op {
                 }
             }
             int* d_flags = (int*)ctx->d_scratch;   // [0] special_head, [1] dup flag, [2] rows off their home line, [3] rows more than 8 lines off
+            unsigned int* d_gave_up = (unsigned int*)(ctx->d_scratch + 22);   // rows a trial geometry could not place within its bound
             // attempt 0: dense mode 2; attempt 1: roomy mode 2; attempt 2: mode 1 (or whatever the environment pinned)
             for (int attempt = (hash_mode == 2 && !env_shift && !getenv("TGPU_JOIN_NO_DENSE")) ? 0 : 1; ; attempt++) {
                 if (hash_mode == 2 && attempt >= 2) hash_mode = 1;
@@ -1170,17 +1180,23 @@ struct JoinBuildOp : tgpu_op {
                 TG_LAUNCH(ctx, join_table_init_kernel, tg_grid(ctx, cap, 1024, 8), 256, 0, lk->table.as<int4>(), cap);
                 int init[4] = {-1, 0, 0, 0};
                 TG_CUDA(ctx, cudaMemcpyAsync(d_flags, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+                TG_CUDA(ctx, cudaMemsetAsync(d_gave_up, 0, 8, ctx->stream));
+                // mode 2 geometries are trials (the keys must suit them): bounded probing, early stop
+                const int give_up_lines = hash_mode == 2 ? 16 : 0;
+                const unsigned int give_up_limit = (unsigned int)std::min<int64_t>(rows / 1024, 1 << 20);
                 if (rows > 0) {
                     TG_LAUNCH(ctx, join_build_kernel, tg_grid(ctx, rows, 256, 8), 256, 0, tg_colref(bkey), key_kind_of(bkey.type), rows,
-                              lk->table.as<JoinSlot>(), lk->geo, d_flags, d_flags + 1, (unsigned int*)(d_flags + 2));
+                              lk->table.as<JoinSlot>(), lk->geo, d_flags, d_flags + 1, (unsigned int*)(d_flags + 2), give_up_lines, give_up_limit, d_gave_up);
                 }
                 if (hash_mode != 2) break;
                 // mode 2 relies on the keys spreading evenly over their range; clustered domains pile up in a few lines.  Dense: at most
-                // 1/64 of the rows off their home line; roomy: at most 1/8; and (nearly) no row further than 8 lines away
-                int64_t moved = 0;
+                // 1/64 of the rows off their home line; roomy: at most 1/8; and (nearly) no row further than 8 lines away, and every
+                // row placed
+                int64_t moved = 0, unplaced = 0;
                 TG_TRY(tg_read_i64(ctx, d_flags + 2, &moved));
+                TG_TRY(tg_read_i64(ctx, d_gave_up, &unplaced));
                 const int64_t off_home = moved & 0xFFFFFFFFLL, far = (moved >> 32) & 0xFFFFFFFFLL;
-                if (off_home * (attempt == 0 ? 64 : 8) <= rows && far * 1024 <= rows) break;
+                if ((unplaced & 0xFFFFFFFFLL) == 0 && off_home * (attempt == 0 ? 64 : 8) <= rows && far * 1024 <= rows) break;
             }
             int64_t packed = 0;
             TG_TRY(tg_read_i64(ctx, d_flags, &packed));
