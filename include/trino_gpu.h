@@ -60,7 +60,11 @@ typedef enum tgpu_type {
     TGPU_FLOAT64 = 5,  /* DOUBLE, raw IEEE bits in a LongArrayBlock (S/type/DoubleType.java:205) */
     TGPU_UTF8 = 7,     /* VARCHAR / CHAR / VARBINARY: int32 offsets[length+1] + bytes          */
     TGPU_DICT32 = 8,   /* DictionaryBlock: data = int32 ids[length], dictionary = value column */
-    TGPU_RLE = 9       /* RunLengthEncodedBlock: dictionary = 1-row value column, broadcast    */
+    TGPU_RLE = 9,      /* RunLengthEncodedBlock: dictionary = 1-row value column, broadcast    */
+    TGPU_INT128 = 10   /* long DECIMAL(p > 18): Int128ArrayBlock's long[] - 16 bytes per position, the HIGH (signed) word first, then the
+                          LOW word (S/block/Int128ArrayBlock.java:123-133).  Moves through every operator; hashes and compares as
+                          LongDecimalType does (S/type/LongDecimalType.java:203-247); group-by / join / partition key; sum() input and
+                          output (DecimalSumAggregation).  The expression evaluator does not compute on it.                          */
 } tgpu_type;
 
 enum {

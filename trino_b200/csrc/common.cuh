@@ -190,6 +190,7 @@ struct DevColumn {
     int elem_size() const
     {
         switch (type) {
+            case TGPU_INT128: return 16;
             case TGPU_INT64: case TGPU_FLOAT64: return 8;
             case TGPU_INT32: return 4;
             case TGPU_INT16: return 2;

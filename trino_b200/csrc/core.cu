@@ -369,6 +369,7 @@ int tg_gather_column(tgpu_ctx* ctx, const DevColumn& src, const int32_t* d_idx, 
         if (es == 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "gather: unsupported column type %d", src.type);
         TG_TRY(alloc_shared(ctx, (size_t)n * es, &r.own_data));
         switch (es) {
+            case 16: TG_LAUNCH(ctx, tg_gather_fixed_kernel<int4>, grid, threads, 0, (const int4*)src.data, d_idx, n, r.own_data->as<int4>()); break;
             case 8: TG_LAUNCH(ctx, tg_gather_fixed_kernel<int64_t>, grid, threads, 0, (const int64_t*)src.data, d_idx, n, r.own_data->as<int64_t>()); break;
             case 4: TG_LAUNCH(ctx, tg_gather_fixed_kernel<int32_t>, grid, threads, 0, (const int32_t*)src.data, d_idx, n, r.own_data->as<int32_t>()); break;
             case 2: TG_LAUNCH(ctx, tg_gather_fixed_kernel<int16_t>, grid, threads, 0, (const int16_t*)src.data, d_idx, n, r.own_data->as<int16_t>()); break;

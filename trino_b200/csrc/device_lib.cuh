@@ -443,6 +443,12 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
 #define TGD_TICKET_WAYS 64
 #define TGD_G_ROWS 4
 
+// {a, b} = the two 64-bit words at p (16-byte aligned) in one L2 transaction, never served from the L1
+__device__ __forceinline__ void tgd_ld_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
+{
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+
 template <class P>
 __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, long long n, const int* __restrict__ rows, long long first,
                                                  const int* __restrict__ stamp_rows, long long page_base, unsigned long long* __restrict__ recs, long long cap, int W,
@@ -453,6 +459,8 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
     const int way = ((threadIdx.x >> 5) + blockIdx.x * 8) & (TGD_TICKET_WAYS - 1);      // one ticket word per warp at a time
     const int lane = threadIdx.x & 31;
     unsigned int err = 0;
+    int have = 0;                                                     // tickets in hand (the same number in every lane)
+    const int batch = budget_per_way >= (32 << 8) ? 32 : (budget_per_way >> 8) > 0 ? (budget_per_way >> 8) : 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // the loop is uniform per warp (every lane makes the same trips) so that the warp can re-converge explicitly between the phases:
     // measured on the first version, the divergent tail of the probe loop ran the stamp + accumulator code with ~7 of 32 lanes active
@@ -477,16 +485,23 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
             slot[j] = (row[j] >= 0 && sp >= 0) ? cap + sp : -1;
             open[j] = row[j] >= 0 && sp < 0;
         }
-        // the key of the home slot AND of its successor are requested together: a row that has to move on finds the next key already
-        // on its way, so the trips of the loop below overlap their L2 round trips instead of adding them up
+        // one 16-byte load brings the home slot's key AND its first-row stamp; the successor's key is requested with it: a row that
+        // has to move on finds the next key already on its way, and a row that stays (most do) never reads its stamp separately
+        unsigned long long st0[R];
 #pragma unroll
         for (int j = 0; j < R; j++) {
-            cur[j] = open[j] ? *((volatile unsigned long long*)(recs + (size_t)pos[j] * W)) : 0;
-            nxt[j] = open[j] ? *((volatile unsigned long long*)(recs + (size_t)((pos[j] + 1) & mask) * W)) : 0;
+            cur[j] = 0; st0[j] = 0; nxt[j] = 0;
+            if (open[j]) {
+                tgd_ld_pair(recs + (size_t)pos[j] * W, cur[j], st0[j]);
+                nxt[j] = *((volatile unsigned long long*)(recs + (size_t)((pos[j] + 1) & mask) * W));
+            }
         }
-        // lock-step probing: one step of every open row per trip, the warp stays converged.  Insertions draw their tickets (the fill
-        // limit of the table) once per warp and trip: ncu on the per-row form showed a third of all stall samples waiting for the
-        // returning atomicAdd on 64 ticket words that 10 M insertions were serialising on.
+        bool moved[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) moved[j] = false;
+        // lock-step probing: one step of every open row per trip, the warp stays converged.  Insertions need a ticket (the fill limit
+        // of the table is a budget of tickets per way); a warp draws them in batches and keeps the remainder (`have`, warp-uniform), so
+        // the returning atomicAdd sits on the critical path of one insertion in `batch`, not of every trip that inserts.
         while (true) {
             bool any = false;
 #pragma unroll
@@ -497,19 +512,25 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
                 const unsigned int wmask = __ballot_sync(0xffffffffu, want);
                 if (wmask) {
                     const int cnt = __popc(wmask), leader = __ffs(wmask) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(tickets + way, cnt);
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    const bool granted = want && base + __popc(wmask & ((1u << lane) - 1)) < budget_per_way;
-                    int give_back = base + cnt - budget_per_way;           // tickets drawn beyond the budget
-                    give_back = give_back < 0 ? 0 : (give_back > cnt ? cnt : give_back);
+                    if (cnt > have) {
+                        int got = 0;
+                        if (lane == leader) {
+                            const int ask = cnt - have > batch ? cnt - have : batch;
+                            const int base = atomicAdd(tickets + way, ask);
+                            got = budget_per_way - base;
+                            got = got < 0 ? 0 : (got > ask ? ask : got);
+                            if (got < ask) atomicSub(tickets + way, ask - got);          // drawn beyond the budget: handed back at once
+                        }
+                        have += __shfl_sync(0xffffffffu, got, leader);
+                    }
+                    const bool granted = want && __popc(wmask & ((1u << lane) - 1)) < have;
+                    have -= cnt < have ? cnt : have;
                     bool won = false;
                     if (granted) {
                         c = atomicCAS(recs + (size_t)pos[j] * W, TGD_EMPTY_KEY, pk[j]);
                         won = c == TGD_EMPTY_KEY;
                     }
-                    give_back += __popc(__ballot_sync(0xffffffffu, granted && !won));      // lost the race for the slot: the claim was not consumed
-                    if (lane == leader && give_back) atomicSub(tickets + way, give_back);
+                    have += __popc(__ballot_sync(0xffffffffu, granted && !won));          // lost the race for the slot: the ticket stays in hand
                     if (want && !granted) { open[j] = false; active = false; }              // no room: deferred below
                     if (won) { slot[j] = (long long)pos[j]; open[j] = false; active = false; }
                 }
@@ -519,6 +540,7 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
                         pos[j] = (pos[j] + 1) & mask;
                         cur[j] = nxt[j];
                         nxt[j] = *((volatile unsigned long long*)(recs + (size_t)((pos[j] + 1) & mask) * W));
+                        moved[j] = true;
                         any = true;
                     }
                 }
@@ -534,7 +556,9 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
             seen[j] = 0;
             if (row[j] >= 0 && slot[j] >= 0) {
                 stamp[j] = page_base + (stamp_rows ? (long long)stamp_rows[row[j]] : row[j]);
-                seen[j] = *((volatile long long*)(recs + (size_t)slot[j] * W + 1));
+                // (a stamp read together with the key may be stale, i.e. too high: stamps only ever go down, so the worst case is one
+                //  atomicMin that changes nothing)
+                seen[j] = (!moved[j] && slot[j] < cap) ? (long long)st0[j] : *((volatile long long*)(recs + (size_t)slot[j] * W + 1));
             }
         }
 #pragma unroll
@@ -556,6 +580,7 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
             prog.accumulate_global(recs + (size_t)slot[j] * W + 2);
         }
     }
+    if (lane == 0 && have > 0) atomicSub(tickets + way, have);        // tickets drawn and not used
     if (err) atomicOr(err_out, err);
 }
 

@@ -141,6 +141,10 @@ class Context:
                 h.offsets = offs.ctypes.data
                 h.data = data.ctypes.data
                 keep.append((d.type, data, valid, offs))
+            elif d.type == abi.INT128:
+                data = np.empty((n, 2), dtype=np.int64)
+                h.data = data.ctypes.data
+                keep.append((d.type, data, valid, None))
             else:
                 data = np.empty(n, dtype=_NP_OF_TYPE[d.type])
                 h.data = data.ctypes.data

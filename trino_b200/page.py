@@ -43,6 +43,23 @@ class Block:
         return Block._fixed(abi.INT64, values, nulls)
 
     @staticmethod
+    def int128(values, nulls=None):
+        """Int128ArrayBlock (long DECIMAL): python ints (None = NULL) -> int64[n][2] = (high, low), the layout of the block's long[]
+        (S/block/Int128ArrayBlock.java:123-133)"""
+        v = list(values)
+        if nulls is None and any(x is None for x in v):
+            nulls = [x is None for x in v]
+        arr = np.zeros((len(v), 2), dtype=np.int64)
+        for i, x in enumerate(v):
+            x = 0 if x is None else int(x)
+            assert -(1 << 127) <= x < (1 << 127), "value does not fit 128 bits"
+            u = x & ((1 << 128) - 1)
+            hi, lo = u >> 64, u & ((1 << 64) - 1)
+            arr[i, 0] = hi - (1 << 64) if hi >= (1 << 63) else hi
+            arr[i, 1] = lo - (1 << 64) if lo >= (1 << 63) else lo
+        return Block(abi.INT128, arr, nulls)
+
+    @staticmethod
     def integer(values, nulls=None):
         return Block._fixed(abi.INT32, values, nulls)
 
@@ -86,6 +103,8 @@ class Block:
         if self.type == abi.UTF8:
             return bytes(self.values[self.offsets[i]:self.offsets[i + 1]])
         v = self.values[i]
+        if self.type == abi.INT128:
+            return (int(v[0]) << 64) | (int(v[1]) & ((1 << 64) - 1))
         return float(v) if self.type == abi.FLOAT64 else int(v)
 
     def to_pylist(self):
