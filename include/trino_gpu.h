@@ -204,7 +204,9 @@ typedef enum tgpu_agg_function {
     TGPU_AGG_SUM = 2,         /* DoubleSumAggregation.java:37-63 / BigintSumAggregation.java:38-59 (checked) */
     TGPU_AGG_AVG = 3,         /* DoubleAverageAggregations.java:37-63 (DOUBLE input) / LongAverage (BIGINT input) */
     TGPU_AGG_MIN = 4,
-    TGPU_AGG_MAX = 5
+    TGPU_AGG_MAX = 5,
+    TGPU_AGG_SUM_DECIMAL = 6  /* DecimalSumAggregation.java:44-146: input TGPU_INT64 (short decimal) or TGPU_INT128 (long decimal) -> DECIMAL(38, s)
+                                 as TGPU_INT128; "Decimal overflow" (NUMERIC_VALUE_OUT_OF_RANGE) when the sum leaves +-10^38                   */
 } tgpu_agg_function;
 
 typedef enum tgpu_agg_step {   /* M/sql/planner/plan/AggregationNode.java:361-402 */
@@ -227,6 +229,8 @@ typedef struct tgpu_agg_fn {
  *   sum            : value (INT64 or FLOAT64), NULL when no input rows (NullableDoubleState / NullableLongState)
  *   avg            : INT64 count, FLOAT64 sum (LongAndDoubleState)
  *   min/max        : value, NULL when no input rows
+ *   sum (decimal)  : TGPU_INT128 sum, INT64 overflow (LongDecimalWithOverflowState: total = sum + overflow * 2^128); the sum is NULL
+ *                    when no input rows
  * Variable-width (TGPU_UTF8) group-by keys are supported: each such key column owns a device string dictionary
  * (csrc/strdict.cuh, the AppendOnlyVariableWidthData analogue of M/operator/FlatHash.java:309-348); identity is exact
  * (full-byte comparison, colliding strings rehash), output key columns are UTF8 again.                                 */

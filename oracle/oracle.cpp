@@ -160,6 +160,9 @@ struct ColView {
             default: return 0;
         }
     }
+    // Int128ArrayBlock: long[2 * positions], the high word first (S/block/Int128ArrayBlock.java:123-133)
+    inline int64_t i128_high(int64_t i) const { return ((const int64_t*)col->data)[2 * pos(i)]; }
+    inline int64_t i128_low(int64_t i) const { return ((const int64_t*)col->data)[2 * pos(i) + 1]; }
     inline double f64(int64_t i) const { return ((const double*)col->data)[pos(i)]; }
     inline const uint8_t* bytes(int64_t i, int32_t* len) const
     {
@@ -175,6 +178,7 @@ struct ColView {
         switch (type) {
             case TGPU_FLOAT64: return hash_double(f64(i));
             case TGPU_UTF8: { int32_t len; const uint8_t* b = bytes(i, &len); return xxh64(b, len, 0); }
+            case TGPU_INT128: return xxh64_long(i128_high(i)) ^ xxh64_long(i128_low(i));   // S/type/LongDecimalType.java:203-229
             default: return hash_long(i64(i));  // integer widths sign-extend first (AbstractIntType.java:183-187)
         }
     }
@@ -193,6 +197,7 @@ struct ColView {
                 const uint8_t* b = o.bytes(j, &lb);
                 return la == lb && memcmp(a, b, la) == 0;
             }
+            case TGPU_INT128: return i128_high(i) == o.i128_high(j) && i128_low(i) == o.i128_low(j);   // LongDecimalType.java:190-201
             default: return i64(i) == o.i64(j);
         }
     }
@@ -223,7 +228,8 @@ inline bool valid_bit(const uint8_t* validity, int64_t i) { return !validity || 
 // a stored copy of one key tuple (FlatHash record; M/operator/FlatHash.java:90-96)
 struct KeyCell {
     uint8_t is_null;
-    int64_t fixed;           // raw 64-bit value for fixed-width types
+    int64_t fixed;           // raw 64-bit value for fixed-width types (INT128: the high word)
+    int64_t fixed_low;       // INT128: the low word
     std::string bytes;       // UTF8
 };
 
@@ -435,6 +441,7 @@ static int32_t flat_put(orc_groupby* g, const std::vector<ColView>& cols, int64_
                             same = (a != a && b != b) || a == b;
                             break;
                         }
+                        case TGPU_INT128: same = cols[c].i128_high(row) == k[c].fixed && cols[c].i128_low(row) == k[c].fixed_low; break;
                         default: same = cols[c].i64(row) == k[c].fixed;
                     }
                 }
@@ -455,7 +462,9 @@ static int32_t flat_put(orc_groupby* g, const std::vector<ColView>& cols, int64_
     for (size_t c = 0; c < cols.size(); c++) {
         k[c].is_null = cols[c].is_null(row);
         k[c].fixed = 0;
+        k[c].fixed_low = 0;
         if (k[c].is_null) continue;
+        if (cols[c].type == TGPU_INT128) { k[c].fixed = cols[c].i128_high(row); k[c].fixed_low = cols[c].i128_low(row); continue; }
         if (cols[c].type == TGPU_UTF8) { int32_t len; const uint8_t* b = cols[c].bytes(row, &len); k[c].bytes.assign((const char*)b, len); }
         else if (cols[c].type == TGPU_FLOAT64) { double d = cols[c].f64(row); memcpy(&k[c].fixed, &d, 8); }
         else k[c].fixed = cols[c].i64(row);
@@ -543,6 +552,60 @@ int32_t orc_agg_sum_bigint(const int32_t* gids, int64_t n, const int64_t* v, con
         sum[gids[i]] = r;
     }
     return 0;
+}
+
+// DecimalSumAggregation (M/operator/aggregation/DecimalSumAggregation.java:44-146) over LongDecimalWithOverflowState: per group
+// decimal[2] = (high, low), overflow, notNull.  `values` holds n x (high, low) pairs (long decimal input, :67-90) or, with is_short,
+// n BIGINT values sign-extended to 128 bits (:44-65).  Int128Math.addWithOverflow :192-210 word for word.
+static int64_t add_with_overflow(int64_t left_high, int64_t left_low, int64_t right_high, int64_t right_low, int64_t* out)
+{
+    int64_t low = (int64_t)((uint64_t)left_low + (uint64_t)right_low);
+    int64_t low_carry = ((uint64_t)low < (uint64_t)left_low) ? 1 : 0;              // unsignedCarry
+    int64_t high = (int64_t)((uint64_t)left_high + (uint64_t)right_high + (uint64_t)low_carry);
+    int64_t overflow = 0;
+    if (left_high >= 0 && right_high >= 0 && high < 0) overflow = 1;
+    else if (left_high < 0 && right_high < 0 && high >= 0) overflow = -1;
+    out[0] = high;
+    out[1] = low;
+    return overflow;
+}
+
+void orc_agg_sum_decimal(const int32_t* gids, int64_t n, const int64_t* values, int32_t is_short, const uint8_t* validity, const uint8_t* mask_sel,
+                         int64_t* decimal /* [groups][2] */, int64_t* overflow, uint8_t* nonnull)
+{
+    for (int64_t i = 0; i < n; i++) {
+        if (!selected(mask_sel, i) || !valid_bit(validity, i)) continue;
+        const int32_t g = gids[i];
+        nonnull[g] = 1;
+        const int64_t right_low = is_short ? values[i] : values[2 * i + 1];
+        const int64_t right_high = is_short ? (values[i] >> 63) : values[2 * i];
+        overflow[g] += add_with_overflow(decimal[2 * g], decimal[2 * g + 1], right_high, right_low, decimal + 2 * g);
+    }
+}
+
+// combine :92-120 of one other state into a group's state
+void orc_agg_sum_decimal_combine(int64_t* decimal, int64_t* overflow, uint8_t* nonnull, const int64_t* other_decimal, int64_t other_overflow)
+{
+    if (*nonnull) {
+        int64_t o = add_with_overflow(decimal[0], decimal[1], other_decimal[0], other_decimal[1], decimal);
+        *overflow += o + other_overflow;
+    }
+    else {
+        *nonnull = 1;
+        decimal[0] = other_decimal[0];
+        decimal[1] = other_decimal[1];
+        *overflow = other_overflow;
+    }
+}
+
+// outputDecimal :122-146: 0 = value ok, -4 = "Decimal overflow" (Decimals.overflows: outside +-(10^38 - 1), S/type/Decimals.java:319-323)
+int32_t orc_decimal_sum_overflows(int64_t high, int64_t low, int64_t overflow)
+{
+    if (overflow != 0) return -4;
+    const unsigned __int128 max = ((unsigned __int128)0x4B3B4CA85A86C47AULL << 64) | 0x098A224000000000ULL;    // 10^38
+    __int128 v = ((__int128)high << 64) | (unsigned __int128)(uint64_t)low;
+    unsigned __int128 a = v < 0 ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    return a >= max ? -4 : 0;
 }
 
 void orc_agg_minmax_double(const int32_t* gids, int64_t n, const double* v, const uint8_t* validity, int32_t is_max, double* acc, uint8_t* nonnull)

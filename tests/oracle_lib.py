@@ -56,6 +56,9 @@ def load():
         "orc_agg_avg_double": (None, [VP, C.c_int64, VP, VP, VP, VP, VP]),
         "orc_agg_count": (None, [VP, C.c_int64, VP, VP, VP]),
         "orc_agg_sum_bigint": (C.c_int32, [VP, C.c_int64, VP, VP, VP, VP, VP]),
+        "orc_agg_sum_decimal": (None, [VP, C.c_int64, VP, C.c_int32, VP, VP, VP, VP, VP]),
+        "orc_agg_sum_decimal_combine": (None, [VP, VP, VP, VP, C.c_int64]),
+        "orc_decimal_sum_overflows": (C.c_int32, [C.c_int64, C.c_int64, C.c_int64]),
         "orc_agg_minmax_double": (None, [VP, C.c_int64, VP, VP, C.c_int32, VP, VP]),
         "orc_agg_minmax_bigint": (None, [VP, C.c_int64, VP, VP, C.c_int32, VP, VP]),
         "orc_join_build": (VP, [PP, VP, C.c_int32, C.c_int32]),
@@ -309,3 +312,53 @@ def semi_join_bigint(set_block, probe_block):
     isnull = np.zeros(max(len(pv), 1), dtype=np.uint8)
     lib.orc_semi_join_bigint(_p(sv), _p(svalid), len(sv), _p(pv), _p(pvalid), len(pv), _p(val), _p(isnull))
     return [None if isnull[i] else bool(val[i]) for i in range(len(pv))]
+
+
+# ---- long DECIMAL sums (DecimalSumAggregation over LongDecimalWithOverflowState) --------------------------------------------------
+M64 = (1 << 64) - 1
+
+
+def int128_words(x):
+    """python int -> (high, low) as signed 64-bit words of its 128-bit two's complement"""
+    u = x & ((1 << 128) - 1)
+    hi, lo = u >> 64, u & M64
+    return (hi - (1 << 64) if hi >> 63 else hi), (lo - (1 << 64) if lo >> 63 else lo)
+
+
+def int128_value(high, low):
+    return (int(high) << 64) | (int(low) & M64)
+
+
+class DecimalSumState:
+    """one LongDecimalWithOverflowState driven through the oracle's restatement of inputLongDecimal / inputShortDecimal / combine"""
+
+    def __init__(self):
+        self.decimal = np.zeros(2, dtype=np.int64)
+        self.overflow = np.zeros(1, dtype=np.int64)
+        self.nonnull = np.zeros(1, dtype=np.uint8)
+
+    def add(self, values, short=False):
+        n = len(values)
+        gids = np.zeros(n, dtype=np.int32)
+        if short:
+            v = np.ascontiguousarray(values, dtype=np.int64)
+        else:
+            v = np.ascontiguousarray([w for x in values for w in int128_words(x)], dtype=np.int64)
+        load().orc_agg_sum_decimal(_p(gids), n, _p(v), int(short), None, None, _p(self.decimal), _p(self.overflow), _p(self.nonnull))
+        return self
+
+    def combine(self, other):
+        load().orc_agg_sum_decimal_combine(_p(self.decimal), _p(self.overflow), _p(self.nonnull), _p(other.decimal), int(other.overflow[0]))
+        return self
+
+    @property
+    def value(self):
+        return int128_value(self.decimal[0], self.decimal[1])
+
+    def output(self):
+        """outputDecimal: the value, None for an empty state, or raises OverflowError("Decimal overflow")"""
+        if not self.nonnull[0]:
+            return None
+        if load().orc_decimal_sum_overflows(int(self.decimal[0]), int(self.decimal[1]), int(self.overflow[0])) != 0:
+            raise OverflowError("Decimal overflow")
+        return self.value

@@ -235,7 +235,7 @@ static std::string gen_fp_source(const DProgram& prog, const int* elems, int num
     s += "      out.nullmap[c][j] = isn ? 1 : 0;\n      if (isn) nulls_seen |= 1u << c;\n    }\n";
     for (size_t k = 0; k < pass_channels.size(); k++) {
         int ch = pass_channels[k];
-        const char* ty = elems[ch] == 8 ? "long long" : elems[ch] == 4 ? "int" : elems[ch] == 2 ? "short" : "signed char";
+        const char* ty = elems[ch] == 16 ? "int4" : elems[ch] == 8 ? "long long" : elems[ch] == 4 ? "int" : elems[ch] == 2 ? "short" : "signed char";
         fp_appendf(s, "    ((%s*)out.pass_data[%d])[j] = ((const %s*)cols.cols[%d].data)[row];\n", ty, (int)k, ty, ch);
         if ((nullable_mask >> ch) & 1) fp_appendf(s, "    out.pass_nullmap[%d][j] = tg_valid(cols.cols[%d].validity, row) ? 0 : 1;\n", (int)k, ch);
     }
@@ -310,8 +310,8 @@ struct FilterProjectOp : tgpu_op {
         for (int i = 0; i < host_prog.num_insns; i++) {
             const DOperand* ops[3] = {&host_prog.insns[i].a, &host_prog.insns[i].b, &host_prog.insns[i].c};
             for (auto* o : ops)
-                if (o->kind == TGPU_OPND_COLUMN && in.cols[o->index].elem_size() == 0)
-                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "expressions over variable-width channel %d are not supported on the GPU path", o->index);
+                if (o->kind == TGPU_OPND_COLUMN && (in.cols[o->index].elem_size() == 0 || in.cols[o->index].elem_size() == 16))
+                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "expressions over variable-width / 128-bit channel %d are not supported on the GPU path", o->index);
         }
         unsigned int* d_err = (unsigned int*)(ctx->d_scratch + 2);
         unsigned int* d_anynull = d_err + 1;

@@ -27,6 +27,7 @@
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <algorithm>
 #include <map>
 
 #include "expr.cuh"
@@ -1005,10 +1006,67 @@ struct OutSpec {
     int32_t count;                   // output columns after the keys
     int32_t kind[48];                // 0 int64 from acc a0; 1 f64 sum nullable by count a1; 2 avg = sum a0 / count a1; 3 i128 sum (a0 lo, a0+1 hi) nullable by a1;
                                      // 4 min/max f64 decode nullable by a1; 5 min/max i64 decode nullable by a1; 6 f64 sum never null (avg partial sum)
-    int32_t a0[48], a1[48];
+                                     // 7 decimal sum -> INT128 (two words per row: high, low), 8 its overflow count (INT64): a0 = 128-bit sum of the
+                                     //   high words (or of the short-decimal values when a2 < 0), a2 / a3 = sums of the low word's upper / lower
+                                     //   32 bits, a4 = sum of the incoming overflow counts (state input) or -1; a1 = non-NULL rows;
+                                     //   9 = 7 for a FINAL / SINGLE step: raises "Decimal overflow" instead of carrying the count on
+    int32_t a0[48], a1[48], a2[48], a3[48], a4[48];
     void* data[48];
     unsigned char* nullmap[48];      // 1 = NULL
 };
+
+// ---- long DECIMAL (Int128ArrayBlock) support: the group-by proper only ever sees 64-bit channels ----------------------------------
+// An INT128 input column is split into four BIGINT columns once per page: high word, low word (as bits), and the low word's upper and
+// lower 32 bits as non-negative numbers.  Keys use (high, low); DecimalSumAggregation sums high (signed) and the two low halves with the
+// existing carry-free 128-bit accumulators, and the output kernel reassembles sum = S_high * 2^64 + S_upper * 2^32 + S_lower.
+__global__ void agg_split_int128_kernel(const long long* __restrict__ src, int64_t n, long long* __restrict__ high, long long* __restrict__ low,
+                                        long long* __restrict__ low_upper, long long* __restrict__ low_lower)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const longlong2 v = ((const longlong2*)src)[i];          // x = high, y = low (S/block/Int128ArrayBlock.java:123-133)
+        high[i] = v.x;
+        low[i] = v.y;
+        low_upper[i] = (long long)((unsigned long long)v.y >> 32);
+        low_lower[i] = (long long)((unsigned long long)v.y & 0xFFFFFFFFULL);
+    }
+}
+
+__global__ void agg_join_int128_kernel(const long long* __restrict__ high, const long long* __restrict__ low, int64_t n, long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) ((longlong2*)out)[i] = make_longlong2(high[i], low[i]);
+}
+
+// 256-bit two's complement accumulator for the reassembly (four 64-bit limbs, least significant first)
+struct Wide256 { unsigned long long w[4]; };
+__device__ __forceinline__ void wide_add_shifted(Wide256& t, unsigned long long lo, long long hi, int shift_words32)
+{
+    // the signed 128-bit value (hi:lo), sign-extended to 256 bits, shifted left by 32 * shift_words32 bits (0, 1, 2 or 4)
+    unsigned long long v[4] = {lo, (unsigned long long)hi, (unsigned long long)(hi >> 63), (unsigned long long)(hi >> 63)};
+    unsigned long long s[4];
+    const int words = shift_words32 >> 1;                 // whole 64-bit limbs
+    const bool half = (shift_words32 & 1) != 0;           // plus 32 bits
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int src = i - words;
+        unsigned long long cur = src >= 0 ? v[src] : 0, prev = src - 1 >= 0 ? v[src - 1] : 0;
+        s[i] = half ? (cur << 32) | (prev >> 32) : cur;
+    }
+    unsigned long long carry = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        unsigned long long a = t.w[i], b = s[i];
+        unsigned long long r = a + b;
+        unsigned long long c1 = r < a ? 1 : 0;
+        unsigned long long r2 = r + carry;
+        unsigned long long c2 = r2 < r ? 1 : 0;
+        t.w[i] = r2;
+        carry = c1 + c2;
+    }
+}
 
 __global__ void agg_output_kernel(AggState st, int64_t count, OutSpec spec, unsigned int* __restrict__ err_out, unsigned int* __restrict__ any_null)
 {
@@ -1038,6 +1096,42 @@ __global__ void agg_output_kernel(AggState st, int64_t count, OutSpec spec, unsi
                 }
                 case 4: isn = cnt == 0; outv = f64_from_order_key(x); break;
                 case 5: isn = cnt == 0; outv = (long long)(x ^ 0x8000000000000000ULL); break;
+                case 7: case 8: case 9: {
+                    // DecimalSumAggregation: state = (sum mod 2^128 as a signed 128-bit value, overflow) with
+                    // total = signed128(sum) + overflow * 2^128 (addWithOverflow, S/type/Int128Math.java)
+                    isn = cnt == 0;
+                    Wide256 t = {{0, 0, 0, 0}};
+                    auto pair = [&](int a, unsigned long long* lo, long long* hi) {
+                        *lo = st.acc[(size_t)a * st.cap + g];
+                        *hi = (long long)st.acc[(size_t)(a + 1) * st.cap + g];
+                    };
+                    unsigned long long lo; long long hi;
+                    pair(spec.a0[c], &lo, &hi);
+                    wide_add_shifted(t, lo, hi, spec.a2[c] >= 0 ? 2 : 0);          // short decimals: the values themselves
+                    if (spec.a2[c] >= 0) { pair(spec.a2[c], &lo, &hi); wide_add_shifted(t, lo, hi, 1); }
+                    if (spec.a3[c] >= 0) { pair(spec.a3[c], &lo, &hi); wide_add_shifted(t, lo, hi, 0); }
+                    if (spec.a4[c] >= 0) { pair(spec.a4[c], &lo, &hi); wide_add_shifted(t, lo, hi, 4); }
+                    // upper 128 bits + 1 if the low 128 bits read as a negative number
+                    long long overflow = (long long)t.w[2] + (((long long)t.w[1]) < 0 ? 1 : 0);
+                    const bool upper_fits = (long long)t.w[3] == ((long long)t.w[2] >> 63);
+                    if (!upper_fits) err |= TG_ERR_BIT_OVERFLOW;                    // (|total| >= 2^191: nothing sane gets here)
+                    if (spec.kind[c] == 8) { outv = overflow; isn = false; break; }
+                    if (!isn && spec.kind[c] == 9) {
+                        // outputDecimal :127-146: overflow != 0 or |value| >= 10^38 -> NUMERIC_VALUE_OUT_OF_RANGE "Decimal overflow"
+                        const long long vh = (long long)t.w[1];
+                        const unsigned long long vl = t.w[0];
+                        // |v| as unsigned 128 bits
+                        unsigned long long al = vl, ah = (unsigned long long)vh;
+                        if (vh < 0) { al = ~vl + 1; ah = ~(unsigned long long)vh + (al == 0 ? 1 : 0); }
+                        const unsigned long long MAXH = 0x4B3B4CA85A86C47AULL, MAXL = 0x098A224000000000ULL;    // 10^38
+                        if (overflow != 0 || ah > MAXH || (ah == MAXH && al >= MAXL)) err |= TG_ERR_BIT_OVERFLOW;
+                    }
+                    ((long long*)spec.data[c])[2 * g] = isn ? 0 : (long long)t.w[1];
+                    ((long long*)spec.data[c])[2 * g + 1] = isn ? 0 : (long long)t.w[0];
+                    spec.nullmap[c][g] = isn ? 1 : 0;
+                    if (isn) { if (c < 32) nulls0 |= 1u << c; else nulls1 |= 1u << (c - 32); }
+                    continue;
+                }
                 default: outv = (long long)x; break;
             }
             ((long long*)spec.data[c])[g] = isn ? 0 : outv;
@@ -1114,13 +1208,20 @@ __global__ void __launch_bounds__(256) agg_skip_kernel(DColumns cols, int64_t n,
                 const ColRef& m = cols.cols[f.mask_ch];
                 on = tg_valid(m.validity, i) && tg_load_i64(m, i) != 0;       // AggregationMask: NULL or false drops the row
             }
-            long long bits = 0;
+            long long bits = 0, bits_high = 0;
             if (f.in_ch >= 0) {
                 const ColRef& c = cols.cols[f.in_ch];
                 if (!tg_valid(c.validity, i)) on = false;
-                else bits = tg_load_i64(c, i);
+                else if (c.elem == 16) { bits_high = ((const long long*)c.data)[2 * i]; bits = ((const long long*)c.data)[2 * i + 1]; }
+                else { bits = tg_load_i64(c, i); bits_high = bits >> 63; }
             }
             switch (f.function) {
+                case TGPU_AGG_SUM_DECIMAL:
+                    ((long long*)f.out0)[2 * i] = on ? bits_high : 0;
+                    ((long long*)f.out0)[2 * i + 1] = on ? bits : 0;
+                    f.null0[i] = on ? 0 : 1;
+                    ((long long*)f.out1)[i] = 0;
+                    break;
                 case TGPU_AGG_COUNT_STAR: case TGPU_AGG_COUNT:
                     ((long long*)f.out0)[i] = on ? 1 : 0;
                     break;
@@ -1370,7 +1471,7 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
     {
         const char* e = getenv("TGPU_AGG_G_MINB");
         appendf(s, "extern \"C\" __global__ void __launch_bounds__(256, %d) tg_agg_general_jit(DColumns cols, long long n, const int* rows, long long first, const int* stamp_rows,\n",
-                e ? atoi(e) : 2);
+                e ? atoi(e) : 3);
     }
     s += ""
          "    long long page_base, unsigned long long* recs, long long cap, int W, int* tickets, int budget_per_way, int* deferred, unsigned int* err_out) {\n"
@@ -1385,6 +1486,7 @@ struct AggFnPlan {
     int function;
     int in_elem_is_double;
     int acc_main = -1, acc_count = -1;   // indices into plan.accs
+    int acc2 = -1, acc3 = -1, acc4 = -1; // decimal sum: the low word's upper / lower 32-bit sums, the incoming overflow counts
 };
 
 struct AggOp : tgpu_op {
@@ -1444,6 +1546,13 @@ struct AggOp : tgpu_op {
     bool finishing = false, finished = false, flushing = false;
     std::vector<OwnedPage*> pending;
     size_t next_out = 0;
+
+    // long DECIMAL channels (TGPU_INT128): split into four BIGINT channels appended behind the page's own (prepare_wide)
+    std::vector<int32_t> spec_key_channels;     // groupByChannels as the caller numbered them (key_channels is rewritten by prepare_wide)
+    bool wide_ready = false;
+    int wide_base = -1;                         // first virtual channel = number of real channels of the page
+    std::vector<int> wide_channels;             // the INT128 channels the plan reads, ascending
+    std::vector<char> wide_key_high;            // per (expanded) group-by key: 1 = the high word of an INT128 key, the next key is its low word
 
     // adaptive partial aggregation: one "builder" spans the pages between two flushes (HashAggregationOperator.aggregationBuilder)
     tgpu_partial_agg_controller* controller = nullptr;
@@ -1525,6 +1634,85 @@ struct AggOp : tgpu_op {
         return projections[ch].index;
     }
 
+    int wide_virtual(int ch, int word) const
+    {
+        for (size_t i = 0; i < wide_channels.size(); i++)
+            if (wide_channels[i] == ch) return wide_base + 4 * (int)i + word;
+        return -1;
+    }
+
+    // TGPU_INT128 channels -> four BIGINT channels each (high, low, low's upper 32 bits, low's lower 32 bits) appended behind the real
+    // channels; on the first page the group-by keys of that type become (high, low) key pairs.  The kernels never see a 128-bit value.
+    int prepare_wide(DevPage* pg)
+    {
+        const bool from_state = step == TGPU_STEP_FINAL || step == TGPU_STEP_INTERMEDIATE;
+        if (!wide_ready) {
+            std::vector<int> want;
+            auto note = [&](int ch) { if (ch >= 0 && ch < (int)pg->cols.size() && pg->cols[ch].type == TGPU_INT128) want.push_back(ch); };
+            bool any_wide = false;
+            for (auto& c : pg->cols) any_wide = any_wide || c.type == TGPU_INT128;
+            if (any_wide && has_pre)
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "a fused pre-stage over pages with 128-bit channels is not supported: run the FilterAndProject operator in front");
+            for (int ch : key_channels) note(ch);
+            for (auto& f : fns) {
+                note(f.input_channel);
+                if (f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_COUNT && f.function != TGPU_AGG_COUNT_STAR && f.input_channel >= 0 &&
+                    f.input_channel < (int)pg->cols.size() && pg->cols[f.input_channel].type == TGPU_INT128)
+                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a 128-bit channel (only count and the decimal sum are built)", f.function);
+            }
+            (void)from_state;
+            std::sort(want.begin(), want.end());
+            want.erase(std::unique(want.begin(), want.end()), want.end());
+            wide_channels = want;
+            wide_base = (int)pg->cols.size();
+            if (wide_base + 4 * (int)wide_channels.size() > TGPU_MAX_CHANNELS)
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many channels once the 128-bit ones are split (%d)", wide_base + 4 * (int)wide_channels.size());
+            // INT128 keys -> (high, low)
+            std::vector<int32_t> keys;
+            std::vector<std::shared_ptr<StringDict>> dicts;
+            wide_key_high.clear();
+            int new_group_id_key = group_id_key;
+            for (size_t k = 0; k < key_channels.size(); k++) {
+                const int ch = key_channels[k];
+                if ((int)k == group_id_key) new_group_id_key = (int)keys.size();
+                if (wide_virtual(ch, 0) >= 0) {
+                    keys.push_back(wide_virtual(ch, 0)); wide_key_high.push_back(1); dicts.push_back(nullptr);
+                    keys.push_back(wide_virtual(ch, 1)); wide_key_high.push_back(0); dicts.push_back(nullptr);
+                }
+                else {
+                    keys.push_back(ch); wide_key_high.push_back(0);
+                    dicts.push_back(k < key_dicts.size() ? key_dicts[k] : nullptr);
+                }
+            }
+            key_channels = keys;
+            key_dicts = dicts;
+            group_id_key = new_group_id_key;
+            wide_ready = true;
+        }
+        if (wide_channels.empty()) return TGPU_OK;
+        if ((int)pg->cols.size() != wide_base) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "page has %zu channels, the first one had %d", pg->cols.size(), wide_base);
+        const int64_t n = pg->rows;
+        for (int ch : wide_channels) {
+            const DevColumn src = pg->cols[ch];
+            if (src.type != TGPU_INT128) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "channel %d changed its type between pages", ch);
+            DevColumn part[4];
+            for (auto& c : part) {
+                c.type = TGPU_INT64;
+                c.length = n;
+                c.own_data = std::make_shared<DevBuf>();
+                TG_TRY(c.own_data->alloc(ctx, (size_t)std::max<int64_t>(n, 1) * 8));
+                c.data = c.own_data->p;
+                c.own_validity = src.own_validity;
+                c.validity = src.validity;
+            }
+            if (n > 0)
+                TG_LAUNCH(ctx, agg_split_int128_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, (const long long*)src.data, n, part[0].own_data->as<long long>(),
+                          part[1].own_data->as<long long>(), part[2].own_data->as<long long>(), part[3].own_data->as<long long>());
+            for (auto& c : part) pg->cols.push_back(std::move(c));
+        }
+        return TGPU_OK;
+    }
+
     // UTF8 key columns of the page -> INT32 dictionary ids, in place (FlatHash keeps the bytes in AppendOnlyVariableWidthData; here
     // the dictionary does, and the group-by proper sees fixed-width keys)
     int encode_string_keys(DevPage* pg)
@@ -1589,6 +1777,44 @@ struct AggOp : tgpu_op {
                 if (mask < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "mask channel out of range");
             }
             int type = TGPU_INT64, src = -1, src2 = -1, type2 = 0;
+            if (f.function == TGPU_AGG_SUM_DECIMAL) {
+                // DecimalSumAggregation.java:44-146.  Raw input: a short decimal (BIGINT) is summed in 128 bits as BIGINT sums are; a long
+                // decimal arrives as its four BIGINT parts (prepare_wide).  State input: the INT128 sum column likewise, plus the overflow
+                // column at input_channel + 1.
+                const bool wide = wide_virtual(f.input_channel, 0) >= 0;
+                int t = 0;
+                if (wide) {
+                    const int s_high = src_of_channel(wide_virtual(f.input_channel, 0), &t, in);
+                    const int s_upper = src_of_channel(wide_virtual(f.input_channel, 2), &t, in);
+                    const int s_lower = src_of_channel(wide_virtual(f.input_channel, 3), &t, in);
+                    if (s_high < 0 || s_upper < 0 || s_lower < 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many distinct aggregate inputs");
+                    fp.acc_main = add_acc(ACC_SUM_I64_LO, s_high, mask);
+                    fp.acc2 = add_acc(ACC_SUM_I64_LO, s_upper, mask);
+                    fp.acc3 = add_acc(ACC_SUM_I64_LO, s_lower, mask);
+                    fp.acc_count = add_acc(ACC_NONNULL, s_high, mask);
+                    if (fp.acc2 < 0 || fp.acc3 < 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
+                    type = TGPU_INT128;
+                }
+                else {
+                    if (from_state) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "the decimal sum state is an INT128 channel followed by a BIGINT overflow channel");
+                    src = src_of_channel(f.input_channel, &type, in);
+                    if (src < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "aggregate input channel %d out of range", f.input_channel);
+                    if (type != TGPU_INT64) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a decimal sum reads BIGINT (short decimal) or INT128 channels, not type %d", type);
+                    fp.acc_main = add_acc(ACC_SUM_I64_LO, src, mask);
+                    fp.acc_count = add_acc(ACC_NONNULL, src, mask);
+                }
+                if (from_state) {
+                    const int s_over = src_of_channel(f.input_channel + 1, &t, in);
+                    if (s_over < 0 || t != TGPU_INT64) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "the decimal sum state needs its BIGINT overflow channel");
+                    fp.acc4 = add_acc(ACC_SUM_I64_LO, s_over, -1);
+                    if (fp.acc4 < 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
+                }
+                fp.in_elem_is_double = 0;
+                fn_input_types.push_back(type);
+                if (fp.acc_main < 0 || fp.acc_count < 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
+                fnplans.push_back(fp);
+                continue;
+            }
             if (f.function != TGPU_AGG_COUNT_STAR || from_state) {
                 src = src_of_channel(f.input_channel, &type, in);
                 if (src < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "aggregate input channel %d out of range", f.input_channel);
@@ -2308,6 +2534,7 @@ struct AggOp : tgpu_op {
         DevPage in;
         TG_TRY(tg_ingest_page(ctx, page, &in));
         if (controller) builder_bytes += reference_page_bytes(in);
+        TG_TRY(prepare_wide(&in));
         TG_TRY(encode_string_keys(&in));
         if (!planned) {
             TG_TRY(make_plan(in));
@@ -2408,7 +2635,7 @@ struct AggOp : tgpu_op {
                 *c = &in->cols[ch];
                 return TGPU_OK;
             };
-            for (int ch : key_channels) {
+            for (int ch : spec_key_channels) {
                 const DevColumn* c = nullptr;
                 TG_TRY(channel(ch, &c));
                 outp.cols.push_back(*c);                  // the block itself (page.getBlock(hashChannels[i]))
@@ -2421,7 +2648,7 @@ struct AggOp : tgpu_op {
                 c.type = type;
                 c.length = n;
                 c.own_data = std::make_shared<DevBuf>();
-                TG_TRY(c.own_data->alloc(ctx, (size_t)n * 8));
+                TG_TRY(c.own_data->alloc(ctx, (size_t)n * (type == TGPU_INT128 ? 16 : 8)));
                 c.data = c.own_data->p;
                 *data = c.own_data->p;
                 outp.cols.push_back(std::move(c));
@@ -2433,7 +2660,7 @@ struct AggOp : tgpu_op {
                     const DevColumn* c = nullptr;
                     TG_TRY(channel(f.input_channel, &c));
                     outp.cols.push_back(*c);
-                    if (f.function == TGPU_AGG_AVG) {
+                    if (f.function == TGPU_AGG_AVG || f.function == TGPU_AGG_SUM_DECIMAL) {
                         TG_TRY(channel(f.input_channel + 1, &c));
                         outp.cols.push_back(*c);
                     }
@@ -2455,6 +2682,8 @@ struct AggOp : tgpu_op {
                     const DevColumn* c = nullptr;
                     TG_TRY(channel(f.input_channel, &c));
                     if (c->type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregates over variable-width inputs are not supported");
+                    if (c->type == TGPU_INT128 && f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_COUNT)
+                        return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a 128-bit channel (only count and the decimal sum are built)", f.function);
                     k.in_ch = f.input_channel;
                     in_type = c->type;
                     nullable |= c->validity != nullptr;
@@ -2468,6 +2697,19 @@ struct AggOp : tgpu_op {
                         TG_TRY(new_col(TGPU_INT64, &k.out0));
                         TG_TRY(new_col(TGPU_FLOAT64, &k.out1));
                         break;
+                    case TGPU_AGG_SUM_DECIMAL: {
+                        // LongDecimalWithOverflowState of one row: (the value in 128 bits, overflow 0)
+                        if (in_type != TGPU_INT64 && in_type != TGPU_INT128)
+                            return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a decimal sum reads BIGINT (short decimal) or INT128 channels, not type %d", in_type);
+                        TG_TRY(new_col(TGPU_INT128, &k.out0));
+                        auto nm = std::make_shared<DevBuf>();
+                        TG_TRY(nm->alloc(ctx, (size_t)n));
+                        k.null0 = nm->as<unsigned char>();
+                        if (nullable) nullmaps.emplace_back(outp.cols.size() - 1, nm);
+                        else nullmaps.emplace_back((size_t)-1, nm);
+                        TG_TRY(new_col(TGPU_INT64, &k.out1));
+                        break;
+                    }
                     case TGPU_AGG_SUM: case TGPU_AGG_MIN: case TGPU_AGG_MAX: {
                         TG_TRY(new_col(k.in_is_double ? TGPU_FLOAT64 : TGPU_INT64, &k.out0));
                         auto nm = std::make_shared<DevBuf>();
@@ -2521,6 +2763,7 @@ struct AggOp : tgpu_op {
             TG_TRY(inner_fp->get_output(&o));
             if (!o) break;
             std::unique_ptr<OwnedPage> guard(o);
+            TG_TRY(prepare_wide(&o->page));
             TG_TRY(encode_string_keys(&o->page));       // (has_pre is false by now: the keys are the projection's output channels)
             DColumns cols;
             TG_TRY(fill_cols(o->page, &cols));
@@ -2577,6 +2820,19 @@ struct AggOp : tgpu_op {
                 TG_TRY(key_dicts[k]->decode((const int32_t*)c.own_data->p, nm->as<unsigned char>(), G, &text));
                 c = std::move(text);
             }
+            if (k > 0 && k - 1 < (int)wide_key_high.size() && wide_key_high[k - 1]) {
+                // the low word of an INT128 key: weld it to the high word emitted just before (both carry the same NULL flags)
+                DevColumn& high = outp.cols.back();
+                DevColumn wide;
+                wide.type = TGPU_INT128;
+                wide.length = G;
+                wide.own_data = std::make_shared<DevBuf>();
+                TG_TRY(wide.own_data->alloc(ctx, (size_t)G * 16));
+                wide.data = wide.own_data->p;
+                TG_LAUNCH(ctx, agg_join_int128_kernel, grid, 256, 0, (const long long*)high.data, (const long long*)c.data, G, wide.own_data->as<long long>());
+                high = std::move(wide);
+                continue;
+            }
             nullmaps.push_back(nm);
             outp.cols.push_back(std::move(c));
         }
@@ -2585,13 +2841,13 @@ struct AggOp : tgpu_op {
         memset(&spec, 0, sizeof(spec));
         bool partial_out = step == TGPU_STEP_PARTIAL || step == TGPU_STEP_INTERMEDIATE;
         bool from_state = step == TGPU_STEP_FINAL || step == TGPU_STEP_INTERMEDIATE;
-        auto add_col = [&](int type, int kind, int a0, int a1) -> int {
+        auto add_col = [&](int type, int kind, int a0, int a1, int a2 = -1, int a3 = -1, int a4 = -1) -> int {
             if (spec.count >= 48) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many output columns");
             DevColumn c;
             c.type = type;
             c.length = G;
             c.own_data = std::make_shared<DevBuf>();
-            TG_TRY(c.own_data->alloc(ctx, (size_t)G * 8));
+            TG_TRY(c.own_data->alloc(ctx, (size_t)G * (type == TGPU_INT128 ? 16 : 8)));
             c.data = c.own_data->p;
             auto nm = std::make_shared<DevBuf>();
             TG_TRY(nm->alloc(ctx, (size_t)G));
@@ -2599,6 +2855,9 @@ struct AggOp : tgpu_op {
             spec.kind[k] = kind;
             spec.a0[k] = a0;
             spec.a1[k] = a1;
+            spec.a2[k] = a2;
+            spec.a3[k] = a3;
+            spec.a4[k] = a4;
             spec.data[k] = c.own_data->p;
             spec.nullmap[k] = nm->as<unsigned char>();
             nullmaps.push_back(nm);
@@ -2625,6 +2884,13 @@ struct AggOp : tgpu_op {
                     break;
                 case TGPU_AGG_MIN: case TGPU_AGG_MAX:
                     TG_TRY(add_col(dbl ? TGPU_FLOAT64 : TGPU_INT64, dbl ? 4 : 5, fp.acc_main, fp.acc_count));
+                    break;
+                case TGPU_AGG_SUM_DECIMAL:
+                    if (partial_out) {
+                        TG_TRY(add_col(TGPU_INT128, 7, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
+                        TG_TRY(add_col(TGPU_INT64, 8, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
+                    }
+                    else TG_TRY(add_col(TGPU_INT128, 9, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
                     break;
                 default: break;
             }
@@ -2691,7 +2957,7 @@ struct AggOp : tgpu_op {
             c->type = type;
             c->length = G;
             c->own_data = std::make_shared<DevBuf>();
-            size_t bytes = (size_t)G * (type == TGPU_UTF8 ? 1 : 8);
+            size_t bytes = (size_t)G * (type == TGPU_UTF8 ? 1 : type == TGPU_INT128 ? 16 : 8);
             TG_TRY(c->own_data->alloc(ctx, bytes));
             TG_CUDA(ctx, cudaMemsetAsync(c->own_data->p, 0, bytes, ctx->stream));
             c->data = c->own_data->p;
@@ -2733,6 +2999,7 @@ struct AggOp : tgpu_op {
                 c.validity = nullptr;                   // count over nothing is 0, not NULL
             }
             else if (f.function == TGPU_AGG_AVG) TG_TRY(null_column(TGPU_FLOAT64, &c));
+            else if (f.function == TGPU_AGG_SUM_DECIMAL) TG_TRY(null_column(TGPU_INT128, &c));
             else {
                 int ch = f.input_channel;
                 int type = has_pre ? (ch >= 0 && ch < (int)projections.size() ? (projections[ch].kind == 0 ? type_of(projections[ch].index)
@@ -2790,6 +3057,7 @@ int build_agg_op(tgpu_ctx* ctx, const tgpu_agg_spec* spec, AggOp** out)
     if (spec->step < TGPU_STEP_SINGLE || spec->step > TGPU_STEP_INTERMEDIATE) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "bad aggregation step");
     std::unique_ptr<AggOp> op(new AggOp(ctx));
     op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_keys);
+    op->spec_key_channels = op->key_channels;
     op->fns.assign(spec->aggs, spec->aggs + spec->num_aggs);
     op->step = spec->step;
     op->expected_groups = spec->expected_groups;

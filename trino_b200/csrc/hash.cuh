@@ -83,6 +83,21 @@ TG_HD uint64_t xxh64_bytes(const uint8_t* p, int64_t len, uint64_t seed = 0)
     return h;
 }
 
+// io.airlift.slice.XxHash64.hash(long) - XXH64 (seed 0) of the value's eight little-endian bytes, written out: the 8-byte input takes
+// the short-input branch and one 8-byte tail round.  (airlift slice is a dependency of the reference, not vendored in it; the
+// algorithm is the published XXH64, pinned on its test vectors in tests/test_oracle_hashes.py.)
+TG_HD uint64_t xxh64_long(int64_t v)
+{
+    uint64_t h = XXP5 + 8;
+    h ^= rotl64((uint64_t)v * XXP2, 31) * XXP1;
+    h = rotl64(h, 27) * XXP1 + XXP4;
+    h ^= h >> 33; h *= XXP2; h ^= h >> 29; h *= XXP3; h ^= h >> 32;
+    return h;
+}
+
+// long DECIMAL hash code (S/type/LongDecimalType.java:203-229): XxHash64.hash(high) ^ XxHash64.hash(low)
+TG_HD uint64_t hash_int128(int64_t high, int64_t low) { return xxh64_long(high) ^ xxh64_long(low); }
+
 // splitmix64: counter-based generator of the synthetic TPC-H-shaped columns
 TG_HD uint64_t splitmix64(uint64_t x)
 {

@@ -1108,7 +1108,7 @@ struct JoinBuildOp : tgpu_op {
             for (size_t c = 0; c < all.cols.size(); c++) all.cols[c].type = c < col_types.size() && col_types[c] ? col_types[c] : TGPU_INT64;
         }
         // one fixed-width channel -> the table is keyed by the value itself; anything else -> by the row hash + verification
-        lk->generic = nk != 1 || all.cols[0].type == TGPU_UTF8;
+        lk->generic = nk != 1 || all.cols[0].type == TGPU_UTF8 || all.cols[0].type == TGPU_INT128;      // (no 64-bit canonical key)
         lk->store.rows = rows;
         if (lk->generic) {
             for (size_t c = 0; c < nk; c++) lk->build_keys.push_back(all.cols[c]);

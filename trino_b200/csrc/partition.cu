@@ -268,7 +268,7 @@ struct PartitionOp : tgpu_op {
         if (partition_count > XMAXP || 2 * (int)in.cols.size() > XMAXC || getenv("TGPU_PARTITION_SORT")) return false;
         if (null_channel >= 0 && null_channel < (int)in.cols.size() && in.cols[null_channel].validity) return false;
         for (auto& c : in.cols)
-            if (c.type == TGPU_UTF8) return false;
+            if (c.type == TGPU_UTF8 || c.type == TGPU_INT128) return false;     // (the multi-split lanes are at most 8 bytes wide)
         return true;
     }
 
@@ -614,7 +614,7 @@ bool exchange_needs_general_path(const PartitionOp* p, const tgpu_page* page)
     for (int c = 0; c < page->num_columns; c++) {
         const tgpu_column& col = page->columns[c];
         int type = (col.type == TGPU_DICT32 || col.type == TGPU_RLE) && col.dictionary ? col.dictionary->type : col.type;
-        if (type == TGPU_UTF8) return true;
+        if (type == TGPU_UTF8 || type == TGPU_INT128) return true;
     }
     return false;
 }

@@ -34,6 +34,10 @@ __device__ __forceinline__ uint64_t type_hash(const KeyCols& k, int c, int64_t r
         int32_t a = k.offsets[c][row], b = k.offsets[c][row + 1];
         return xxh64_bytes((const uint8_t*)col.data + a, b - a);
     }
+    if (col.elem == 16) {      // Int128ArrayBlock: high word first
+        const int64_t* w = (const int64_t*)col.data + row * 2;
+        return hash_int128(w[0], w[1]);
+    }
     int64_t v = tg_load_i64(col, row);
     return k.is_double[c] ? hash_double_bits(v) : hash_long(v);
 }
@@ -59,6 +63,10 @@ __device__ __forceinline__ uint64_t row_hash_attempt(const KeyCols& k, int64_t r
         else if (k.is_utf8[c]) {
             int32_t a = k.offsets[c][row], b = k.offsets[c][row + 1];
             t = xxh64_bytes((const uint8_t*)col.data + a, b - a, (uint64_t)attempt);
+        }
+        else if (col.elem == 16) {
+            const uint64_t* w = (const uint64_t*)col.data + row * 2;
+            t = murmur3_mix(w[0] + 0xD1B54A32D192ED03ULL * (uint64_t)attempt) ^ murmur3_mix(w[1] + 0x9E3779B97F4A7C15ULL * (uint64_t)(attempt + 1));
         }
         else {
             uint64_t u = (uint64_t)tg_load_i64(col, row);
@@ -96,6 +104,11 @@ __device__ __forceinline__ bool col_value_equal(const KeyCols& a, int c, int64_t
         for (int32_t i = 0; i < la; i++)
             if (pa[i] != pb[i]) return false;
         return true;
+    }
+    if (a.cols[c].elem == 16) {
+        const int64_t* wa = (const int64_t*)a.cols[c].data + ra * 2;
+        const int64_t* wb = (const int64_t*)b.cols[c].data + rb * 2;
+        return wa[0] == wb[0] && wa[1] == wb[1];
     }
     int64_t va = tg_load_i64(a.cols[c], ra), vb = tg_load_i64(b.cols[c], rb);
     if (a.is_double[c]) {
