@@ -56,7 +56,7 @@ constexpr unsigned long long EMPTY_KEY = 0x8000000000000000ULL;
 constexpr long long NO_ROW = 0x7FFFFFFFFFFFFFFFLL;
 constexpr int MAX_KEYS = 4;
 constexpr int MAX_SRCS = 16;
-constexpr int MAX_ACCS = 24;
+constexpr int MAX_ACCS = 40;   // (a FINAL decimal sum alone takes 9: four 128-bit pairs and its non-NULL counter)
 constexpr int S_THREADS = TGD_S_THREADS;
 static_assert(TGD_MAX_CHANNELS == TGPU_MAX_CHANNELS, "channel limits differ");
 constexpr int S_GMAX = 64;             // regular groups the S path can hold (+2 special)
@@ -682,8 +682,8 @@ __device__ __forceinline__ unsigned long long* gf_rec(unsigned long long* base, 
 // per record, word by word - ran at a tenth of the copy bandwidth: 1.7 ms for a 1 GB table)
 __global__ void gf_init_kernel(unsigned long long* __restrict__ recs, int64_t cap, int W, AggPlan plan)
 {
-    __shared__ unsigned long long init[32];
-    if (threadIdx.x < 32) {
+    __shared__ unsigned long long init[64];      // W <= 64 (2 + MAX_ACCS words, padded to a power of two)
+    if (threadIdx.x < 64) {
         int w = threadIdx.x;
         init[w] = w == 0 ? EMPTY_KEY : w == 1 ? (unsigned long long)NO_ROW : (w - 2 < plan.num_accs ? acc_init(plan.accs[w - 2].kind) : 0ULL);
     }
