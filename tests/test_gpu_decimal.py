@@ -176,7 +176,7 @@ def test_int128_partition_join_and_pass_through(ctx):
     build = Page(Block.int128(keys[:2000] + [keys[5], None]), Block.int128(keys[:2000] + [1, 2]))
     probe = Page(Block.int128(keys[1000:3000] + [None]), Block.bigint(np.arange(2001)))
     rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
-    assert rows == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False) and len(rows) > 1000
+    assert rows == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False) and len(rows) >= 1000
     # FilterAndProject: a filter on a BIGINT channel, the 128-bit channel passes through
     prog = ops.PageProcessorProgram(ops.Call(abi.EX_LT, ops.Col(1, abi.V_BIGINT), ops.Const(1234, abi.V_BIGINT)), [0, 1])
     fp = ops.FilterAndProjectOperatorFactory(ctx, prog).create_operator()
