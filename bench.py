@@ -31,10 +31,10 @@ ALG_BYTES_PROBE_FUSED = 40          # fused probe + gather, this workload: 24 + 
 ALG_BYTES_Q1_CODES = 38             # shipdate 4 + 4 x FLOAT64 32 + 2 INT8 key codes
 ALG_BYTES_Q1_UTF8 = 46              # the reference's key types: 2 x VARCHAR(1) = 2 x (4 offset + 1 byte) instead of the 2 code bytes
 ALG_BYTES_GROUPBY_BIGINT = 36       # 8 key + 8 value + 20 table entry touched
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r01_kernels.md),
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r02_kernels.md),
 # quoted only for the configuration they were captured on
-NCU_TRAFFIC_PROBE_FUSED_SF100 = 18.515783e9 + 7.239862e9     # 600 000 003 rows: 42.9 B/row
-NCU_TRAFFIC_Q1_SF300 = 68.633669e9 + 4.425216e6               # 1.8 G rows: 38.1 B/row
+NCU_TRAFFIC_PROBE_FUSED_SF100 = 8.429180e9 + 7.174483e9      # 600 000 003 rows: 26.0 B/row (join_probe_lean_kernel<2,1,8>, dense order-preserving table)
+NCU_TRAFFIC_Q1_SF300 = 68.402849e9 + 4.701952e6               # 1.8 G rows: 38.0 B/row (tg_agg_small_jit, four consecutive rows per thread)
 
 
 def measured_peak():

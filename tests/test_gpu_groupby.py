@@ -247,6 +247,38 @@ def test_partial_flush_when_memory_exceeded(ctx):
     op.close()
 
 
+def test_partial_flush_with_a_fused_pre_stage_and_many_groups(ctx):
+    # The advisor's round-1 finding: a PARTIAL step with a fused filter + projection that overflows the shared-memory path un-fuses the
+    # pre-stage (the plan then reads projection OUTPUT channels); after a maxPartialMemory flush the operator must keep routing pages
+    # through that FilterAndProject instead of running the raw page through the re-pointed plan.  PARTIAL pages -> FINAL == SINGLE.
+    rng = np.random.default_rng(17)
+    n = 60_000
+    pages = [Page(Block.bigint(rng.integers(0, 5000, n)), Block.bigint(rng.integers(-50, 50, n)), Block.double(rng.normal(size=n))) for _ in range(3)]
+    keep = ops.Call(abi.EX_GE, ops.Col(1, abi.V_BIGINT), ops.Const(-10, abi.V_BIGINT))
+    doubled = ops.Call(abi.EX_MUL, ops.Col(2, abi.V_DOUBLE), ops.Const(2.0, abi.V_DOUBLE))
+
+    def program():
+        return ops.PageProcessorProgram(keep, [0, 1, doubled])          # channels of the aggregation input: key, value, 2 * x
+
+    aggs = [A(abi.AGG_COUNT_STAR), A(abi.AGG_SUM, 1), A(abi.AGG_SUM, 2)]
+    single = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_SINGLE, aggs, 16, pre=program())
+    op = single.create_operator()
+    want = [r for p in ops.drive(op, pages) for r in p.rows()]
+    op.close()
+    partial = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, aggs, 16, max_partial_memory=64 << 10, pre=program())
+    op = partial.create_operator()
+    flushed = ops.drive(op, pages)
+    op.close()
+    assert len(flushed) >= 3                                              # every page overflowed the partial memory limit
+    final = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, [A(abi.AGG_COUNT_STAR, 1), A(abi.AGG_SUM, 2), A(abi.AGG_SUM, 3)], 16)
+    op = final.create_operator()
+    got = [r for p in ops.drive(op, flushed) for r in p.rows()]
+    op.close()
+    assert [r[:3] for r in got] == [r[:3] for r in want] and rows_equal(got, want, rel=1e-9)
+    expected_rows = sum(int((np.asarray(p.get_block(1).values) >= -10).sum()) for p in pages)
+    assert sum(r[1] for r in got) == expected_rows
+
+
 def test_bigint_sum_overflow_raises(ctx):
     page = Page(Block.bigint([1, 1]), Block.bigint([2**62, 2**62]))
     with pytest.raises(abi.TrinoGpuError) as e:
