@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shuffled", action="store_true", help="skip the shuffled-probe variant (roofline_shuffled)")
     ap.add_argument("--no-groupby-bigint", action="store_true", help="skip the high-cardinality BIGINT GROUP BY block")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the FilterAndProject / PartitionedOutput blocks (secondary_operators)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host pages) measurement: kernel experiments only")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity to set (32/64/128; 0 = leave the default)")
     args = ap.parse_args()
@@ -515,6 +516,9 @@ def main():
     if world == 1 and args.q1_sf > 0:
         q1 = bench_q1(ctx, args)
     gb = None
+    secondary = None
+    if world == 1 and args.q1_sf > 0 and not args.no_secondary:
+        secondary = bench_secondary(ctx)
     if world == 1 and args.q1_sf > 0 and not args.no_groupby_bigint:
         gb = bench_groupby_bigint(ctx, args)
 
@@ -551,6 +555,8 @@ def main():
             line["groupby_q1"] = q1
         if gb:
             line["groupby_bigint"] = gb
+        if secondary is not None:
+            line["secondary_operators"] = secondary
         print(json.dumps(line))
     probe_op.close()
     builder.close()
@@ -912,6 +918,73 @@ def bench_groupby_bigint(ctx, args):
             "config": "GROUP BY a BIGINT key, 10 M groups, sum(bigint) + count(*), 150 M synthetic rows (SURVEY.md §8 a3), whole addInput incl. table set-up",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_row": ALG_BYTES_GROUPBY_BIGINT, "note": "step-level (operator call), not a single kernel"}}
+
+
+def bench_secondary(ctx):
+    """The other two operators of the path on device-resident synthetic pages, timed like the headline step:
+    FilterAndProject over the Q1 program (300 M lineitem rows) and PartitionedOutput into 8 partitions (150 M rows of BIGINT key + BIGINT payload)"""
+    from q1 import q1_program
+    from trino_b200 import abi
+    from trino_b200 import operators as ops
+    lib = ctx.lib
+    peak, peak_src = measured_peak()
+    out = {}
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ctx.timer_start()
+        for _ in range(reps):
+            fn()
+        return ctx.timer_stop_ms() / reps
+
+    n = 300_000_000
+    spec = [(abi.INT32, 4), (abi.INT8, 1), (abi.INT8, 1), (abi.FLOAT64, 8), (abi.FLOAT64, 8), (abi.FLOAT64, 8), (abi.FLOAT64, 8)]
+    ptrs = [ctx.malloc(n * sz) for _, sz in spec]
+    ctx.check(lib.tgpu_synth_lineitem_q1(ctx.h, n, 0, 0x7C01, *[C.c_void_p(p) for p in ptrs]))
+    page = ops.DevicePage([ops.DeviceColumn(t, p, n) for (t, _), p in zip(spec, ptrs)], n)
+    fp = ops.FilterAndProjectOperatorFactory(ctx, q1_program()).create_operator()
+    rows_out = [0]
+
+    def run_fp():
+        fp.add_input(page)
+        o = fp.get_output_device()
+        rows_out[0] = o.rows
+        o.release()
+    ms = timed(run_fp)
+    sel = rows_out[0] / n
+    alg = 38 + sel * (2 + 5 * 8)          # every input column read once, 2 key bytes + 5 doubles written per selected row
+    out["filter_project"] = {"config": "FilterAndProject, TPC-H Q1 filter + 7 projections, 300 M synthetic lineitem rows", "rows": n, "ms_per_step": ms,
+                             "rows_per_sec": n / (ms * 1e-3), "selectivity": sel,
+                             "roofline": {"bound": "hbm", "achieved": alg * n / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": alg * n / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "algorithmic_bytes_per_row": alg,
+                                          "note": "step-level: tg_fp_filter_chunks_jit + fp_chunk_scan_kernel + tg_fp_project_chunks_jit"}}
+    fp.close()
+    for p in ptrs:
+        ctx.free(p)
+    m = 150_000_000
+    d_keys, d_val = ctx.malloc(m * 8), ctx.malloc(m * 8)
+    ctx.check(lib.tgpu_synth_lineitem_keys(ctx.h, m, 0, m, 0x7C01, 0, C.c_void_p(d_keys)))
+    ctx.check(lib.tgpu_synth_lineitem_keys(ctx.h, m, 0, m, 1, 0, C.c_void_p(d_val)))
+    gpage = ops.DevicePage([ops.DeviceColumn(abi.INT64, d_keys, m), ops.DeviceColumn(abi.INT64, d_val, m)], m)
+    part = ops.PartitionedOutputOperatorFactory(ctx, [0], 8).create_operator()
+
+    def run_part():
+        part.add_input(gpage)
+        while True:
+            o = part.get_output_device()
+            if o is None:
+                break
+            o.release()
+    ms = timed(run_part, reps=3, warm=1)
+    out["partitioned_output"] = {"config": "PartitionedOutput (PagePartitioner), 8 partitions, BIGINT key + BIGINT payload, 150 M synthetic rows", "rows": m,
+                                 "ms_per_step": ms, "rows_per_sec": m / (ms * 1e-3),
+                                 "roofline": {"bound": "hbm", "achieved": 36 * m / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                              "frac": 36 * m / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src, "algorithmic_bytes_per_row": 36,
+                                              "note": "step-level: xchg_hist_warp_kernel + xchg_offsets_kernel + xchg_scatter_warp_kernel (SURVEY.md §8d: 8 key + 1 + 1 id + 16 in + 16 out, rounded)"}}
+    part.close()
+    ctx.free(d_keys); ctx.free(d_val)
+    return out
 
 
 def cpu_baseline(args, n_orders, probe_rows):
