@@ -596,6 +596,152 @@ __global__ void __launch_bounds__(32 * WWARPS, 4) xchg_scatter_warp_kernel(const
     }
 }
 
+// ---- lean warp-tile scatter for the exchange shape of a join: every lane is an 8-byte column without NULLs, the partition ids come from
+// a plain BIGINT key, <= 8 partitions, 16-byte aligned columns.  Same tiles, ranks and output order as xchg_scatter_warp_kernel<VEC, KEYS>,
+// with the per-row bookkeeping stripped (ncu on the generic kernel: 178 thread instructions per row, issue-bound at 59 %): 4-bit per-lane
+// counters, the destination (partition, element offset) of every staged row computed ONCE per tile and reused by all columns, no
+// element-size dispatch, no validity lanes.  A chunk's ragged last tile takes bounds-checked loads (rows beyond the end carry partition 8).
+template <int NC, int MINB>
+__global__ void __launch_bounds__(32 * WWARPS, MINB) xchg_scatter_lean8_kernel(int64_t n, int64_t wchunk, int32_t P, const long long* __restrict__ block_off, XchgCols cols,
+                                                                          const long long* __restrict__ key0, int32_t bucket_count, const int32_t* __restrict__ b2p)
+{
+    __shared__ long long stage_all[WWARPS][WTILE];
+    __shared__ long long delta_all[WWARPS][8];        // run[q] - tile offset of q: staged index j of partition q goes to element delta[q] + j
+    __shared__ uint8_t spid_all[WWARPS][WTILE];
+    __shared__ char* sdst[NC * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < NC * P; i += blockDim.x) sdst[(i / P) * 8 + (i % P)] = cols.dst[i];
+    __syncthreads();
+    const int64_t vchunk = (int64_t)blockIdx.x * WWARPS + warp;
+    const int64_t begin = vchunk * wchunk, end = min(n, begin + wchunk);
+    if (begin >= n) return;
+    long long* stage = stage_all[warp];
+    long long* delta = delta_all[warp];
+    uint8_t* spid = spid_all[warp];
+    long long run = lane < P ? block_off[(size_t)vchunk * P + lane] : 0;      // lane q < 8 keeps partition q's running element offset
+    for (int64_t tile = begin; tile < end; tile += WTILE) {
+        const int64_t row0 = tile + lane * WR;
+        const bool full = tile + WTILE <= end;
+        // partition of my 8 rows (4 bits each; 8 = no row)
+        unsigned int pid4 = 0;
+        {
+            long long k[WR];
+            if (full) {
+                const longlong2* s2 = (const longlong2*)(key0 + row0);
+#pragma unroll
+                for (int j = 0; j < WR / 2; j++) { longlong2 t = s2[j]; k[2 * j] = t.x; k[2 * j + 1] = t.y; }
+            }
+            else {
+#pragma unroll
+                for (int i = 0; i < WR; i++) k[i] = row0 + i < end ? key0[row0 + i] : 0;
+            }
+#pragma unroll
+            for (int i = 0; i < WR; i++) {
+                int32_t bucket = process_raw_hash(hash_long(k[i]), bucket_count);
+                unsigned int q = (unsigned int)(b2p ? b2p[bucket] : bucket);
+                if (!full && row0 + i >= end) q = 8u;
+                pid4 |= q << (4 * i);
+            }
+        }
+        // my rows per partition (4-bit fields, <= 8) and, per row, how many of my earlier rows share its partition
+        unsigned int c4 = 0, before4 = 0;
+        unsigned int extra = 0;        // rows without a partition (ragged tile)
+#pragma unroll
+        for (int i = 0; i < WR; i++) {
+            const unsigned int q = (pid4 >> (4 * i)) & 0xfu;
+            if (q < 8u) {
+                before4 |= ((c4 >> (4 * q)) & 0xfu) << (4 * i);
+                c4 += 1u << (4 * q);
+            }
+            else extra++;
+        }
+        (void)extra;
+        // inclusive scan over the lanes of the 8 counters as 16-bit fields in four 32-bit words (a field never exceeds 256).
+        // (c4's fields can hold 8 = 0b1000 without touching their neighbour)
+        unsigned int w0 = (c4 & 0xfu) | ((c4 & 0xf0u) << 12), w1 = ((c4 >> 8) & 0xfu) | ((c4 & 0xf000u) << 4),
+                     w2 = ((c4 >> 16) & 0xfu) | ((c4 & 0xf00000u) >> 4), w3 = ((c4 >> 24) & 0xfu) | ((c4 & 0xf0000000u) >> 12);
+        const unsigned int m0 = w0, m1 = w1, m2 = w2, m3 = w3;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned int a0 = __shfl_up_sync(0xffffffffu, w0, off), a1 = __shfl_up_sync(0xffffffffu, w1, off);
+            unsigned int a2 = __shfl_up_sync(0xffffffffu, w2, off), a3 = __shfl_up_sync(0xffffffffu, w3, off);
+            if (lane >= off) { w0 += a0; w1 += a1; w2 += a2; w3 += a3; }
+        }
+        // tile totals per partition, and where every partition starts inside the staged tile
+        const unsigned int t0 = __shfl_sync(0xffffffffu, w0, 31), t1 = __shfl_sync(0xffffffffu, w1, 31);
+        const unsigned int t2 = __shfl_sync(0xffffffffu, w2, 31), t3 = __shfl_sync(0xffffffffu, w3, 31);
+        const unsigned int tot[8] = {t0 & 0xffffu, t0 >> 16, t1 & 0xffffu, t1 >> 16, t2 & 0xffffu, t2 >> 16, t3 & 0xffffu, t3 >> 16};
+        unsigned int start[8];
+        {
+            unsigned int acc = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { start[q] = acc; acc += tot[q]; }
+        }
+        // exclusive counts of the lower lanes, per partition
+        const unsigned int e0 = w0 - m0, e1 = w1 - m1, e2 = w2 - m2, e3 = w3 - m3;
+        const unsigned int excl[8] = {e0 & 0xffffu, e0 >> 16, e1 & 0xffffu, e1 >> 16, e2 & 0xffffu, e2 >> 16, e3 & 0xffffu, e3 >> 16};
+        // staged position of my rows (8 bits each) - the selects over q fold into a handful of instructions per row
+        unsigned long long pos8 = 0;
+#pragma unroll
+        for (int i = 0; i < WR; i++) {
+            const unsigned int q = (pid4 >> (4 * i)) & 0xfu;
+            unsigned int base = 0;
+#pragma unroll
+            for (int p = 0; p < 8; p++) base = q == (unsigned int)p ? start[p] + excl[p] : base;
+            const unsigned int pos = base + ((before4 >> (4 * i)) & 0xfu);
+            if (q < 8u) {
+                pos8 |= (unsigned long long)pos << (8 * i);
+                spid[pos] = (uint8_t)q;
+            }
+        }
+        if (lane < 8) {
+            unsigned int st = 0, tt = 0;
+#pragma unroll
+            for (int p = 0; p < 8; p++) { st = lane == p ? start[p] : st; tt = lane == p ? tot[p] : tt; }
+            delta[lane] = run - (long long)st;
+            run += (long long)tt;
+        }
+        __syncwarp();
+        const int tile_rows = (int)min((int64_t)WTILE, end - tile);
+        // destination of the 8 staged rows this lane copies out (j = it * 32 + lane): partition (3 bits each) and element offset
+        unsigned int qq = 0;
+        unsigned int dd[WR];                 // (a page has at most 2^31 - 1 rows: element offsets fit 32 bits)
+#pragma unroll
+        for (int it = 0; it < WR; it++) {
+            const int j = it * 32 + lane;
+            const unsigned int q = j < tile_rows ? (unsigned int)spid[j] : 0u;
+            qq |= q << (3 * it);
+            dd[it] = (unsigned int)(delta[q] + j);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const long long* src = (const long long*)cols.src[c];
+            long long v[WR];
+            if (full) {
+                const longlong2* s2 = (const longlong2*)(src + row0);
+#pragma unroll
+                for (int j = 0; j < WR / 2; j++) { longlong2 t = s2[j]; v[2 * j] = t.x; v[2 * j + 1] = t.y; }
+            }
+            else {
+#pragma unroll
+                for (int i = 0; i < WR; i++) v[i] = row0 + i < end ? src[row0 + i] : 0;
+            }
+            if (c > 0) __syncwarp();          // the previous column's copy-out has read the stage
+#pragma unroll
+            for (int i = 0; i < WR; i++)
+                if (full || ((pid4 >> (4 * i)) & 0xfu) < 8u) stage[(pos8 >> (8 * i)) & 0xffu] = v[i];
+            __syncwarp();
+            char* const* dstc = sdst + c * 8;
+#pragma unroll
+            for (int it = 0; it < WR; it++) {
+                const int j = it * 32 + lane;
+                if (full || j < tile_rows) ((long long*)dstc[(qq >> (3 * it)) & 7u])[dd[it]] = stage[j];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // launch geometry shared by the histogram and scatter passes
 struct XchgGeom {
     bool warp_mode;     // chunks are per warp (<= 8 partitions) or per CTA
@@ -613,7 +759,8 @@ static XchgGeom xchg_geom(tgpu_ctx* ctx, int64_t n, int P, bool remote)
     n = std::max<int64_t>(n, 1);
     g.warp_mode = P <= 8 && !remote && !getenv("TGPU_XCHG_CTA");
     if (g.warp_mode) {
-        int64_t warps = (int64_t)ctx->sm_count * 4 * WWARPS;
+        // 12 CTAs per SM: whole waves for the kernels that keep 4 CTAs resident (3 waves) and for the lean scatter that keeps 3 (4 waves)
+        int64_t warps = (int64_t)ctx->sm_count * 12 * WWARPS;
         g.chunk = tg_div_up(tg_div_up(n, warps), WTILE) * WTILE;
         g.nchunks = (int)tg_div_up(n, g.chunk);
         g.grid = (int)tg_div_up(g.nchunks, WWARPS);
@@ -667,6 +814,23 @@ static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* 
         const long long* key0 = pids ? nullptr : (const long long*)key->cols[0].data;
         bool vec = pids ? ((uintptr_t)pids & 7) == 0 : ((uintptr_t)key0 & 15) == 0;
         for (int c = 0; c < xc.count; c++) vec = vec && ((uintptr_t)xc.src[c] & 15) == 0;
+        bool lean = key0 && vec && xc.count >= 1 && xc.count <= 4 && P <= 8 && !getenv("TGPU_XCHG_NO_LEAN");
+        for (int c = 0; c < xc.count; c++) lean = lean && xc.elem[c] == 8;
+        if (lean) {
+            // 3 CTAs/SM leave the kernel 80 registers (no spills); 4 CTAs/SM cap it at 64 with ~100 bytes of spills per thread
+            const bool four = getenv("TGPU_XCHG_LEAN_MINB4") != nullptr;
+#define TG_LEAN(NC_)                                                                                                                                         \
+    if (four) TG_LAUNCH(ctx, (xchg_scatter_lean8_kernel<NC_, 4>), g.grid, 32 * WWARPS, 0, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);            \
+    else TG_LAUNCH(ctx, (xchg_scatter_lean8_kernel<NC_, 3>), g.grid, 32 * WWARPS, 0, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p)
+            switch (xc.count) {
+                case 1: TG_LEAN(1); break;
+                case 2: TG_LEAN(2); break;
+                case 3: TG_LEAN(3); break;
+                default: TG_LEAN(4); break;
+            }
+#undef TG_LEAN
+            return TGPU_OK;
+        }
         if (key0) {
             if (vec) TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<true, true>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);
             else TG_LAUNCH(ctx, (xchg_scatter_warp_kernel<false, true>), g.grid, 32 * WWARPS, 0, pids, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);
