@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(32 * WWARPS) xchg_hist_warp_kernel(KeyCols key
     const int64_t begin = vchunk * wchunk, end = min(n, begin + wchunk);
     if (begin >= n) return;
     unsigned int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long packed = 0;
+    int since_flush = 0;
     const long long* __restrict__ key0 = (const long long*)keys.cols[0].data;
     for (int64_t base = begin; base < end; base += U * 32) {
         int pidv[U];
@@ -384,14 +386,22 @@ __global__ void __launch_bounds__(32 * WWARPS) xchg_hist_warp_kernel(KeyCols key
                 }
             }
         }
+        // one-hot byte counters: one add per row instead of eight compares; spilled into the 32-bit counters before a byte can wrap
 #pragma unroll
         for (int u = 0; u < U; u++) {
             int64_t row = base + u * 32 + lane;
             if (pid_out && row < end) pid_out[row] = (uint8_t)pidv[u];     // pid_out == nullptr: the scatter recomputes the ids from the key
+            if (pidv[u] >= 0) packed += 1ull << (8 * pidv[u]);
+        }
+        if (++since_flush == 31) {                                          // 31 trips x 8 rows = 248 < 256
 #pragma unroll
-            for (int q = 0; q < 8; q++) cnt[q] += (pidv[u] == q);
+            for (int q = 0; q < 8; q++) cnt[q] += (unsigned int)(packed >> (8 * q)) & 0xffu;
+            packed = 0;
+            since_flush = 0;
         }
     }
+#pragma unroll
+    for (int q = 0; q < 8; q++) cnt[q] += (unsigned int)(packed >> (8 * q)) & 0xffu;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
         unsigned int v = cnt[q];
@@ -622,19 +632,37 @@ __global__ void __launch_bounds__(32 * WWARPS, MINB) xchg_scatter_lean8_kernel(i
     for (int64_t tile = begin; tile < end; tile += WTILE) {
         const int64_t row0 = tile + lane * WR;
         const bool full = tile + WTILE <= end;
+        // every column of the tile is requested up front (two at most are held in registers; the key doubles as a column when it is one):
+        // the hash, the ranks and the staging of the first column then run under the latency of the others
+        constexpr int NPRE = NC < 2 ? NC : 2;
+        long long pre[NPRE][WR];
+        auto load8 = [&](const long long* src, long long (&v)[WR]) {
+            if (full) {
+                const longlong2* s2 = (const longlong2*)(src + row0);
+#pragma unroll
+                for (int j = 0; j < WR / 2; j++) { longlong2 t = s2[j]; v[2 * j] = t.x; v[2 * j + 1] = t.y; }
+            }
+            else {
+#pragma unroll
+                for (int i = 0; i < WR; i++) v[i] = row0 + i < end ? src[row0 + i] : 0;
+            }
+        };
+#pragma unroll
+        for (int c = 0; c < NPRE; c++) load8((const long long*)cols.src[c], pre[c]);
         // partition of my 8 rows (4 bits each; 8 = no row)
         unsigned int pid4 = 0;
         {
             long long k[WR];
-            if (full) {
-                const longlong2* s2 = (const longlong2*)(key0 + row0);
+            const int key_col = (const void*)key0 == cols.src[0] ? 0 : (NPRE > 1 && (const void*)key0 == cols.src[1]) ? 1 : -1;      // warp-uniform
+            if (key_col == 0) {
 #pragma unroll
-                for (int j = 0; j < WR / 2; j++) { longlong2 t = s2[j]; k[2 * j] = t.x; k[2 * j + 1] = t.y; }
+                for (int i = 0; i < WR; i++) k[i] = pre[0][i];
             }
-            else {
+            else if (NPRE > 1 && key_col == 1) {
 #pragma unroll
-                for (int i = 0; i < WR; i++) k[i] = row0 + i < end ? key0[row0 + i] : 0;
+                for (int i = 0; i < WR; i++) k[i] = pre[NPRE - 1][i];
             }
+            else load8(key0, k);
 #pragma unroll
             for (int i = 0; i < WR; i++) {
                 int32_t bucket = process_raw_hash(hash_long(k[i]), bucket_count);
@@ -715,17 +743,12 @@ __global__ void __launch_bounds__(32 * WWARPS, MINB) xchg_scatter_lean8_kernel(i
         }
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const long long* src = (const long long*)cols.src[c];
             long long v[WR];
-            if (full) {
-                const longlong2* s2 = (const longlong2*)(src + row0);
+            if (c < NPRE) {
 #pragma unroll
-                for (int j = 0; j < WR / 2; j++) { longlong2 t = s2[j]; v[2 * j] = t.x; v[2 * j + 1] = t.y; }
+                for (int i = 0; i < WR; i++) v[i] = pre[c < NPRE ? c : 0][i];
             }
-            else {
-#pragma unroll
-                for (int i = 0; i < WR; i++) v[i] = row0 + i < end ? src[row0 + i] : 0;
-            }
+            else load8((const long long*)cols.src[c], v);
             if (c > 0) __syncwarp();          // the previous column's copy-out has read the stage
 #pragma unroll
             for (int i = 0; i < WR; i++)
@@ -818,9 +841,11 @@ static int xchg_launch_scatter(tgpu_ctx* ctx, const XchgGeom& g, const uint8_t* 
         for (int c = 0; c < xc.count; c++) lean = lean && xc.elem[c] == 8;
         if (lean) {
             // 3 CTAs/SM leave the kernel 80 registers (no spills); 4 CTAs/SM cap it at 64 with ~100 bytes of spills per thread
-            const bool four = getenv("TGPU_XCHG_LEAN_MINB4") != nullptr;
+            const char* e_minb = getenv("TGPU_XCHG_LEAN_MINB");
+            const int minb = e_minb ? atoi(e_minb) : 3;
 #define TG_LEAN(NC_)                                                                                                                                         \
-    if (four) TG_LAUNCH(ctx, (xchg_scatter_lean8_kernel<NC_, 4>), g.grid, 32 * WWARPS, 0, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);            \
+    if (minb >= 4) TG_LAUNCH(ctx, (xchg_scatter_lean8_kernel<NC_, 4>), g.grid, 32 * WWARPS, 0, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);       \
+    else if (minb == 2) TG_LAUNCH(ctx, (xchg_scatter_lean8_kernel<NC_, 2>), g.grid, 32 * WWARPS, 0, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p);  \
     else TG_LAUNCH(ctx, (xchg_scatter_lean8_kernel<NC_, 3>), g.grid, 32 * WWARPS, 0, n, g.chunk, P, block_off, xc, key0, bucket_count, b2p)
             switch (xc.count) {
                 case 1: TG_LEAN(1); break;
