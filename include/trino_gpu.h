@@ -205,8 +205,11 @@ typedef enum tgpu_agg_function {
     TGPU_AGG_AVG = 3,         /* DoubleAverageAggregations.java:37-63 (DOUBLE input) / LongAverage (BIGINT input) */
     TGPU_AGG_MIN = 4,
     TGPU_AGG_MAX = 5,
-    TGPU_AGG_SUM_DECIMAL = 6  /* DecimalSumAggregation.java:44-146: input TGPU_INT64 (short decimal) or TGPU_INT128 (long decimal) -> DECIMAL(38, s)
+    TGPU_AGG_SUM_DECIMAL = 6, /* DecimalSumAggregation.java:44-146: input TGPU_INT64 (short decimal) or TGPU_INT128 (long decimal) -> DECIMAL(38, s)
                                  as TGPU_INT128; "Decimal overflow" (NUMERIC_VALUE_OUT_OF_RANGE) when the sum leaves +-10^38                   */
+    TGPU_AGG_AVG_DECIMAL = 7  /* DecimalAverageAggregation.java:54-176: same inputs -> DECIMAL(p, s) of the input: sum / count rounded HALF_UP, as
+                                 TGPU_INT64 for a short decimal and TGPU_INT128 for a long one (tgpu_agg_fn.reserved names the result type in a
+                                 FINAL step, where the state no longer tells)                                                                   */
 } tgpu_agg_function;
 
 typedef enum tgpu_agg_step {   /* M/sql/planner/plan/AggregationNode.java:361-402 */
@@ -220,7 +223,7 @@ typedef struct tgpu_agg_fn {
     int32_t function;          /* tgpu_agg_function */
     int32_t input_channel;     /* -1 for count(*).  For FINAL/INTERMEDIATE: first channel of the state columns */
     int32_t mask_channel;      /* -1 or a BOOLEAN channel (AggregationMask, M/operator/aggregation/AggregationMask.java:30-100) */
-    int32_t reserved;
+    int32_t reserved;          /* TGPU_AGG_AVG_DECIMAL: tgpu_type of the result (TGPU_INT64 / TGPU_INT128); 0 = as the input channel */
 } tgpu_agg_fn;
 
 /* Intermediate state layout emitted by PARTIAL and consumed by FINAL (one or two flat columns per
@@ -231,6 +234,7 @@ typedef struct tgpu_agg_fn {
  *   min/max        : value, NULL when no input rows
  *   sum (decimal)  : TGPU_INT128 sum, INT64 overflow (LongDecimalWithOverflowState: total = sum + overflow * 2^128); the sum is NULL
  *                    when no input rows
+ *   avg (decimal)  : TGPU_INT128 sum, INT64 overflow, INT64 count (LongDecimalWithOverflowAndLongState)
  * Variable-width (TGPU_UTF8) group-by keys are supported: each such key column owns a device string dictionary
  * (csrc/strdict.cuh, the AppendOnlyVariableWidthData analogue of M/operator/FlatHash.java:309-348); identity is exact
  * (full-byte comparison, colliding strings rehash), output key columns are UTF8 again.                                 */

@@ -355,6 +355,24 @@ class DecimalSumState:
     def value(self):
         return int128_value(self.decimal[0], self.decimal[1])
 
+    def average(self, rows):
+        """DecimalAverageAggregation.average :152-175 over this state and its row counter: (decimal + overflow * 2^128) / rows, HALF_UP
+        (Int128Math.divideRoundUp when overflow == 0 - then the result must stay inside +-(10^38 - 1) - else BigDecimal.divide(…, HALF_UP),
+        whose result must fit 128 bits)"""
+        if rows == 0:
+            return None
+        total = self.value + int(self.overflow[0]) * (1 << 128)
+        q, r = divmod(abs(total), rows)
+        if 2 * r >= rows:
+            q += 1
+        result = -q if total < 0 else q
+        if int(self.overflow[0]) == 0:
+            if abs(result) >= 10**38:
+                raise OverflowError("Decimal overflow")
+        elif not -(1 << 127) <= result < (1 << 127):
+            raise OverflowError("Decimal overflow")
+        return result
+
     def output(self):
         """outputDecimal: the value, None for an empty state, or raises OverflowError("Decimal overflow")"""
         if not self.nonnull[0]:

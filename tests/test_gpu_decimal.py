@@ -198,3 +198,70 @@ def test_decimal_sum_through_a_skipped_partial_builder(ctx):
     ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, [A(abi.AGG_SUM_DECIMAL, 1), A(abi.AGG_SUM_DECIMAL, 3), A(abi.AGG_SUM_DECIMAL, 5), A(abi.AGG_COUNT_STAR, 7)], 16)
     assert _rows(ctx, ff, partial) == _want_sums(pages)
     controller.close()
+
+
+def _avg(ctx, longs=None, shorts=None):
+    """avg(decimal) of one group through the SINGLE step"""
+    if longs is not None:
+        page = Page(Block.bigint([3] * len(longs)), Block.int128(longs))
+    else:
+        page = Page(Block.bigint([3] * len(shorts)), Block.bigint(shorts))
+    rows = _rows(ctx, ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_SINGLE, [A(abi.AGG_AVG_DECIMAL, 1)], 16), [page])
+    assert len(rows) == 1
+    return rows[0][1]
+
+
+def test_reference_decimal_average_cases(ctx):
+    # T/operator/aggregation/TestDecimalAverageAggregation.java:46-216 through the operator
+    MIN = -(10**38 - 1)
+    assert _avg(ctx, [TWO**126, TWO**126]) == TWO**126                                  # testOverflow (overflow != 0 branch)
+    assert _avg(ctx, [MIN, MIN]) == MIN                                                 # testUnderflow
+    assert _avg(ctx, [TWO**126, TWO**126, TWO**125] + [-(TWO**126)] * 3) == -((TWO**125) // 6)
+    for numbers, want in (([10**37, 0], 5 * 10**36), ([2, 1], 2), ([0, 1], 1), ([-2, -1], -2), ([-1, 0], -1), ([-1, 0, 0], 0), ([-2, 0, 0], -1),
+                          ([-2, 0], -1), ([200, 100], 150), ([0, 100], 50), ([-200, -100], -150), ([-100, 0], -50)):
+        assert _avg(ctx, numbers) == want, numbers
+        if all(abs(x) < 2**63 for x in numbers):
+            assert _avg(ctx, None, numbers) == want, numbers                           # the same values as a short decimal: a BIGINT result
+    assert _avg(ctx, [None, None]) is None
+
+
+def test_decimal_average_partial_final_and_skipped_builders(ctx):
+    rng = np.random.default_rng(35)
+    pages = _decimal_pages(rng, 40, (2500, 1, 3000))
+    aggs = [A(abi.AGG_AVG_DECIMAL, 1), A(abi.AGG_AVG_DECIMAL, 2), A(abi.AGG_AVG_DECIMAL, 1, 3)]
+
+    def half_up(total, n):
+        q, r = divmod(abs(total), n)
+        return (-1 if total < 0 else 1) * (q + (1 if 2 * r >= n else 0))
+
+    order, acc = [], {}
+    for p in pages:
+        for r in p.rows():
+            if r[0] not in acc:
+                acc[r[0]] = [[0, 0], [0, 0], [0, 0]]
+                order.append(r[0])
+            a = acc[r[0]]
+            if r[1] is not None:
+                a[0][0] += r[1]; a[0][1] += 1
+            if r[2] is not None:
+                a[1][0] += r[2]; a[1][1] += 1
+            if r[1] is not None and r[3]:
+                a[2][0] += r[1]; a[2][1] += 1
+    want = [(k,) + tuple(None if n == 0 else half_up(t, n) for t, n in acc[k]) for k in order]
+    single = _rows(ctx, ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_SINGLE, aggs, 16), pages)
+    assert single == want
+    finals = [A(abi.AGG_AVG_DECIMAL, 1, result_type=abi.INT128), A(abi.AGG_AVG_DECIMAL, 4, result_type=abi.INT64), A(abi.AGG_AVG_DECIMAL, 7, result_type=abi.INT128)]
+    for controller_off in (False, True):
+        controller = ops.PartialAggregationController(ctx.lib, 1 << 40, 0.0)
+        if controller_off:
+            controller.on_flush(1 << 41, 10, 10)
+        pf = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, aggs, 16, partial_aggregation_controller=controller)
+        partial = []
+        for p in pages:
+            op = pf.create_operator()
+            partial += ops.drive(op, [p])
+            op.close()
+        assert partial[0].channel_count == 1 + 3 * 3
+        ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, finals, 16)
+        assert _rows(ctx, ff, partial) == want, controller_off
+        controller.close()

@@ -76,3 +76,22 @@ def test_long_decimal_hash_is_the_xor_of_two_xxh64():
         page = Page(Block.int128([v]))
         assert int(o.row_hashes(page, [0])[0]) & o.M64 == want
         assert o.load().orc_xxh64_long(high) == o.xxh64(struct.pack("<q", high))
+
+
+def test_reference_decimal_average_cases():
+    # T/operator/aggregation/TestDecimalAverageAggregation.java:46-216
+    MIN = -(10**38 - 1)
+    assert o.DecimalSumState().add([TWO**126, TWO**126]).average(2) == TWO**126                       # testOverflow
+    s = o.DecimalSumState().add([MIN, MIN])                                                           # testUnderflow
+    assert s.overflow[0] == -1 and words(s) == (0x698966AF4AF2770B, 0xECEBBB8000000002 - (1 << 64)) and s.average(2) == MIN
+    s = o.DecimalSumState().add([TWO**126, TWO**126, TWO**125] + [-(TWO**126)] * 3)                  # testUnderflowAfterOverflow
+    assert s.average(6) == -((TWO**125) // 6)                                                         # BigInteger.divide truncates; the fraction is 1/3
+    a = o.DecimalSumState().add([TWO**125, TWO**126]).combine(o.DecimalSumState().add([TWO**125, TWO**126]))
+    assert a.average(4) == (2 * TWO**126 + 2 * TWO**125) // 4                                         # testCombineOverflow
+    a = o.DecimalSumState().add([-(TWO**125), -(TWO**126)]).combine(o.DecimalSumState().add([-(TWO**125), -(TWO**126)]))
+    assert a.overflow[0] == -1 and words(a) == (1 << 62, 0) and a.average(4) == -((2 * TWO**126 + 2 * TWO**125) // 4)
+    # testNoOverflow: HALF_UP of the exact quotient
+    for numbers, want in (([10**37, 0], 5 * 10**36), ([2, 1], 2), ([0, 1], 1), ([-2, -1], -2), ([-1, 0], -1), ([-1, 0, 0], 0), ([-2, 0, 0], -1),
+                          ([-2, 0], -1), ([200, 100], 150), ([0, 100], 50), ([-200, -100], -150), ([-100, 0], -50)):
+        assert o.DecimalSumState().add(numbers).average(len(numbers)) == want, numbers
+    assert o.DecimalSumState().average(0) is None

@@ -1010,7 +1010,9 @@ struct OutSpec {
                                      //   high words (or of the short-decimal values when a2 < 0), a2 / a3 = sums of the low word's upper / lower
                                      //   32 bits, a4 = sum of the incoming overflow counts (state input) or -1; a1 = non-NULL rows;
                                      //   9 = 7 for a FINAL / SINGLE step: raises "Decimal overflow" instead of carrying the count on
-    int32_t a0[48], a1[48], a2[48], a3[48], a4[48];
+                                     // 10 / 11 decimal average -> INT128 / INT64: the same total divided by the row count a5 (a plain counter when
+                                     //   a5 < 0: a1), rounded HALF_UP (DecimalAverageAggregation.average); NULL when the count is 0
+    int32_t a0[48], a1[48], a2[48], a3[48], a4[48], a5[48];
     void* data[48];
     unsigned char* nullmap[48];      // 1 = NULL
 };
@@ -1096,7 +1098,7 @@ __global__ void agg_output_kernel(AggState st, int64_t count, OutSpec spec, unsi
                 }
                 case 4: isn = cnt == 0; outv = f64_from_order_key(x); break;
                 case 5: isn = cnt == 0; outv = (long long)(x ^ 0x8000000000000000ULL); break;
-                case 7: case 8: case 9: {
+                case 7: case 8: case 9: case 10: case 11: {
                     // DecimalSumAggregation: state = (sum mod 2^128 as a signed 128-bit value, overflow) with
                     // total = signed128(sum) + overflow * 2^128 (addWithOverflow, S/type/Int128Math.java)
                     isn = cnt == 0;
@@ -1116,6 +1118,50 @@ __global__ void agg_output_kernel(AggState st, int64_t count, OutSpec spec, unsi
                     const bool upper_fits = (long long)t.w[3] == ((long long)t.w[2] >> 63);
                     if (!upper_fits) err |= TG_ERR_BIT_OVERFLOW;                    // (|total| >= 2^191: nothing sane gets here)
                     if (spec.kind[c] == 8) { outv = overflow; isn = false; break; }
+                    if (spec.kind[c] >= 10) {
+                        // average = total / count, HALF_UP (Int128Math.divideRoundUp; with overflow != 0 the BigDecimal path of
+                        // DecimalAverageAggregation.average :152-175 - the same exact quotient)
+                        const unsigned long long n_rows = spec.a5[c] >= 0 ? st.acc[(size_t)spec.a5[c] * st.cap + g] : cnt;
+                        isn = n_rows == 0;
+                        long long rh = 0;
+                        unsigned long long rl = 0;
+                        if (!isn) {
+                            const bool neg = ((long long)t.w[3]) < 0;
+                            unsigned long long m[4] = {t.w[0], t.w[1], t.w[2], t.w[3]};
+                            if (neg) {                                               // magnitude
+                                unsigned long long carry = 1;
+#pragma unroll
+                                for (int i = 0; i < 4; i++) { unsigned long long v = ~m[i] + carry; carry = (carry && v == 0) ? 1 : 0; m[i] = v; }
+                            }
+                            unsigned long long q[4], rem = 0;
+#pragma unroll
+                            for (int i = 3; i >= 0; i--) {
+                                unsigned __int128 cur = ((unsigned __int128)rem << 64) | m[i];
+                                q[i] = (unsigned long long)(cur / n_rows);
+                                rem = (unsigned long long)(cur % n_rows);
+                            }
+                            if ((unsigned __int128)rem * 2 >= (unsigned __int128)n_rows) {           // HALF_UP on the magnitude
+#pragma unroll
+                                for (int i = 0; i < 4; i++) { q[i] += 1; if (q[i] != 0) break; }
+                            }
+                            // the quotient must fit the result: overflow == 0 -> inside +-10^38 (overflows(result)), else 128 bits (Int128.valueOf)
+                            const unsigned long long MAXH = 0x4B3B4CA85A86C47AULL, MAXL = 0x098A224000000000ULL;
+                            bool bad = q[2] != 0 || q[3] != 0;
+                            if (overflow == 0) bad = bad || q[1] > MAXH || (q[1] == MAXH && q[0] >= MAXL);
+                            else bad = bad || (q[1] >> 63) != 0;
+                            if (spec.kind[c] == 11) bad = bad || q[1] != 0 || (q[0] >> 63) != 0;             // toLongExact
+                            if (bad) err |= TG_ERR_BIT_OVERFLOW;
+                            rl = q[0];
+                            rh = (long long)q[1];
+                            if (neg) { rl = ~rl + 1; rh = (long long)(~(unsigned long long)rh + (rl == 0 ? 1 : 0)); }
+                        }
+                        if (spec.kind[c] == 11) { outv = (long long)rl; break; }
+                        ((long long*)spec.data[c])[2 * g] = isn ? 0 : rh;
+                        ((long long*)spec.data[c])[2 * g + 1] = isn ? 0 : (long long)rl;
+                        spec.nullmap[c][g] = isn ? 1 : 0;
+                        if (isn) { if (c < 32) nulls0 |= 1u << c; else nulls1 |= 1u << (c - 32); }
+                        continue;
+                    }
                     if (!isn && spec.kind[c] == 9) {
                         // outputDecimal :127-146: overflow != 0 or |value| >= 10^38 -> NUMERIC_VALUE_OUT_OF_RANGE "Decimal overflow"
                         const long long vh = (long long)t.w[1];
@@ -1189,7 +1235,8 @@ struct SkipFn {
     int32_t function, in_ch, mask_ch, in_is_double;
     void* out0;
     unsigned char* null0;      // 1 byte per row (sum / min / max), else null
-    void* out1;                // avg: the DOUBLE sum
+    void* out1;                // avg: the DOUBLE sum; decimal sum / avg: the overflow count
+    void* out2;                // decimal avg: the row count
 };
 struct SkipSpec {
     int32_t count;
@@ -1216,11 +1263,12 @@ __global__ void __launch_bounds__(256) agg_skip_kernel(DColumns cols, int64_t n,
                 else { bits = tg_load_i64(c, i); bits_high = bits >> 63; }
             }
             switch (f.function) {
-                case TGPU_AGG_SUM_DECIMAL:
+                case TGPU_AGG_SUM_DECIMAL: case TGPU_AGG_AVG_DECIMAL:
                     ((long long*)f.out0)[2 * i] = on ? bits_high : 0;
                     ((long long*)f.out0)[2 * i + 1] = on ? bits : 0;
                     f.null0[i] = on ? 0 : 1;
                     ((long long*)f.out1)[i] = 0;
+                    if (f.function == TGPU_AGG_AVG_DECIMAL) ((long long*)f.out2)[i] = on ? 1 : 0;
                     break;
                 case TGPU_AGG_COUNT_STAR: case TGPU_AGG_COUNT:
                     ((long long*)f.out0)[i] = on ? 1 : 0;
@@ -1487,6 +1535,8 @@ struct AggFnPlan {
     int in_elem_is_double;
     int acc_main = -1, acc_count = -1;   // indices into plan.accs
     int acc2 = -1, acc3 = -1, acc4 = -1; // decimal sum: the low word's upper / lower 32-bit sums, the incoming overflow counts
+    int acc5 = -1;                       // decimal average from states: the sum of the incoming row counts
+    int result_type = 0;                 // decimal average: TGPU_INT64 (short decimal) or TGPU_INT128
 };
 
 struct AggOp : tgpu_op {
@@ -1656,7 +1706,7 @@ struct AggOp : tgpu_op {
             for (int ch : key_channels) note(ch);
             for (auto& f : fns) {
                 note(f.input_channel);
-                if (f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_COUNT && f.function != TGPU_AGG_COUNT_STAR && f.input_channel >= 0 &&
+                if (f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_AVG_DECIMAL && f.function != TGPU_AGG_COUNT && f.function != TGPU_AGG_COUNT_STAR && f.input_channel >= 0 &&
                     f.input_channel < (int)pg->cols.size() && pg->cols[f.input_channel].type == TGPU_INT128)
                     return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a 128-bit channel (only count and the decimal sum are built)", f.function);
             }
@@ -1777,7 +1827,7 @@ struct AggOp : tgpu_op {
                 if (mask < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "mask channel out of range");
             }
             int type = TGPU_INT64, src = -1, src2 = -1, type2 = 0;
-            if (f.function == TGPU_AGG_SUM_DECIMAL) {
+            if (f.function == TGPU_AGG_SUM_DECIMAL || f.function == TGPU_AGG_AVG_DECIMAL) {
                 // DecimalSumAggregation.java:44-146.  Raw input: a short decimal (BIGINT) is summed in 128 bits as BIGINT sums are; a long
                 // decimal arrives as its four BIGINT parts (prepare_wide).  State input: the INT128 sum column likewise, plus the overflow
                 // column at input_channel + 1.
@@ -1808,6 +1858,16 @@ struct AggOp : tgpu_op {
                     if (s_over < 0 || t != TGPU_INT64) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "the decimal sum state needs its BIGINT overflow channel");
                     fp.acc4 = add_acc(ACC_SUM_I64_LO, s_over, -1);
                     if (fp.acc4 < 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
+                    if (f.function == TGPU_AGG_AVG_DECIMAL) {
+                        const int s_rows = src_of_channel(f.input_channel + 2, &t, in);
+                        if (s_rows < 0 || t != TGPU_INT64) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "the decimal average state needs its BIGINT row-count channel");
+                        fp.acc5 = add_acc(ACC_SUM_I64_LO, s_rows, -1);
+                        if (fp.acc5 < 0) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
+                    }
+                }
+                if (f.function == TGPU_AGG_AVG_DECIMAL) {
+                    fp.result_type = f.reserved == TGPU_INT64 || f.reserved == TGPU_INT128 ? f.reserved : (wide && !from_state ? TGPU_INT128 : from_state ? 0 : TGPU_INT64);
+                    if (!fp.result_type) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a FINAL decimal average needs tgpu_agg_fn.reserved = TGPU_INT64 or TGPU_INT128 (the result type)");
                 }
                 fp.in_elem_is_double = 0;
                 fn_input_types.push_back(type);
@@ -2660,8 +2720,12 @@ struct AggOp : tgpu_op {
                     const DevColumn* c = nullptr;
                     TG_TRY(channel(f.input_channel, &c));
                     outp.cols.push_back(*c);
-                    if (f.function == TGPU_AGG_AVG || f.function == TGPU_AGG_SUM_DECIMAL) {
+                    if (f.function == TGPU_AGG_AVG || f.function == TGPU_AGG_SUM_DECIMAL || f.function == TGPU_AGG_AVG_DECIMAL) {
                         TG_TRY(channel(f.input_channel + 1, &c));
+                        outp.cols.push_back(*c);
+                    }
+                    if (f.function == TGPU_AGG_AVG_DECIMAL) {
+                        TG_TRY(channel(f.input_channel + 2, &c));
                         outp.cols.push_back(*c);
                     }
                     continue;
@@ -2682,7 +2746,7 @@ struct AggOp : tgpu_op {
                     const DevColumn* c = nullptr;
                     TG_TRY(channel(f.input_channel, &c));
                     if (c->type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregates over variable-width inputs are not supported");
-                    if (c->type == TGPU_INT128 && f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_COUNT)
+                    if (c->type == TGPU_INT128 && f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_AVG_DECIMAL && f.function != TGPU_AGG_COUNT)
                         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a 128-bit channel (only count and the decimal sum are built)", f.function);
                     k.in_ch = f.input_channel;
                     in_type = c->type;
@@ -2697,8 +2761,8 @@ struct AggOp : tgpu_op {
                         TG_TRY(new_col(TGPU_INT64, &k.out0));
                         TG_TRY(new_col(TGPU_FLOAT64, &k.out1));
                         break;
-                    case TGPU_AGG_SUM_DECIMAL: {
-                        // LongDecimalWithOverflowState of one row: (the value in 128 bits, overflow 0)
+                    case TGPU_AGG_SUM_DECIMAL: case TGPU_AGG_AVG_DECIMAL: {
+                        // LongDecimalWithOverflow[AndLong]State of one row: (the value in 128 bits, overflow 0[, 1 row])
                         if (in_type != TGPU_INT64 && in_type != TGPU_INT128)
                             return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a decimal sum reads BIGINT (short decimal) or INT128 channels, not type %d", in_type);
                         TG_TRY(new_col(TGPU_INT128, &k.out0));
@@ -2708,6 +2772,7 @@ struct AggOp : tgpu_op {
                         if (nullable) nullmaps.emplace_back(outp.cols.size() - 1, nm);
                         else nullmaps.emplace_back((size_t)-1, nm);
                         TG_TRY(new_col(TGPU_INT64, &k.out1));
+                        if (f.function == TGPU_AGG_AVG_DECIMAL) TG_TRY(new_col(TGPU_INT64, &k.out2));
                         break;
                     }
                     case TGPU_AGG_SUM: case TGPU_AGG_MIN: case TGPU_AGG_MAX: {
@@ -2858,6 +2923,7 @@ struct AggOp : tgpu_op {
             spec.a2[k] = a2;
             spec.a3[k] = a3;
             spec.a4[k] = a4;
+            spec.a5[k] = -1;
             spec.data[k] = c.own_data->p;
             spec.nullmap[k] = nm->as<unsigned char>();
             nullmaps.push_back(nm);
@@ -2891,6 +2957,20 @@ struct AggOp : tgpu_op {
                         TG_TRY(add_col(TGPU_INT64, 8, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
                     }
                     else TG_TRY(add_col(TGPU_INT128, 9, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
+                    break;
+                case TGPU_AGG_AVG_DECIMAL:
+                    if (partial_out) {
+                        TG_TRY(add_col(TGPU_INT128, 7, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
+                        TG_TRY(add_col(TGPU_INT64, 8, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
+                        // the row counter: non-NULL inputs of a raw step, the summed counters of a state step
+                        if (fp.acc5 >= 0) TG_TRY(add_col(TGPU_INT64, 3, fp.acc5, -1));
+                        else TG_TRY(add_col(TGPU_INT64, 0, fp.acc_count, -1));
+                    }
+                    else {
+                        const bool narrow = fp.result_type == TGPU_INT64;
+                        TG_TRY(add_col(narrow ? TGPU_INT64 : TGPU_INT128, narrow ? 11 : 10, fp.acc_main, fp.acc_count, fp.acc2, fp.acc3, fp.acc4));
+                        spec.a5[spec.count - 1] = fp.acc5;
+                    }
                     break;
                 default: break;
             }
@@ -3000,6 +3080,7 @@ struct AggOp : tgpu_op {
             }
             else if (f.function == TGPU_AGG_AVG) TG_TRY(null_column(TGPU_FLOAT64, &c));
             else if (f.function == TGPU_AGG_SUM_DECIMAL) TG_TRY(null_column(TGPU_INT128, &c));
+            else if (f.function == TGPU_AGG_AVG_DECIMAL) TG_TRY(null_column(f.reserved == TGPU_INT64 ? TGPU_INT64 : TGPU_INT128, &c));
             else {
                 int ch = f.input_channel;
                 int type = has_pre ? (ch >= 0 && ch < (int)projections.size() ? (projections[ch].kind == 0 ? type_of(projections[ch].index)

@@ -447,8 +447,9 @@ class FilterAndProjectOperatorFactory(OperatorFactory):
 class Aggregator:
     """One AggregatorFactory (M/operator/aggregation/AggregatorFactory.java:40-58): function + input/mask channels."""
 
-    def __init__(self, function, input_channel=-1, mask_channel=-1):
-        self.function, self.input_channel, self.mask_channel = function, input_channel, mask_channel
+    def __init__(self, function, input_channel=-1, mask_channel=-1, result_type=0):
+        """result_type: tgpu_type of an avg(decimal) result (INT64 short / INT128 long decimal) where the input does not tell (FINAL step)"""
+        self.function, self.input_channel, self.mask_channel, self.result_type = function, input_channel, mask_channel, result_type
 
 
 class HashAggregationOperator(Operator):
@@ -544,6 +545,7 @@ class HashAggregationOperatorFactory(OperatorFactory):
         fns = (abi.AggFn * max(1, len(self.aggregators)))()
         for i, a in enumerate(self.aggregators):
             fns[i].function, fns[i].input_channel, fns[i].mask_channel = a.function, agg_inputs[i], a.mask_channel
+            fns[i].reserved = getattr(a, "result_type", 0)
         gids = _i32(self.global_ids)
         types = _i32(list(self.input_types or []))
         spec = abi.AggSpec(len(self.group_by_channels), C.cast(keys, C.POINTER(C.c_int32)), self.step, len(self.aggregators),
