@@ -21,8 +21,14 @@ import static com.google.common.base.Preconditions.checkState;
 public class GpuHashAggregationOperatorFactory
         implements OperatorFactory
 {
-    /** function id (tgpu_agg_function) + input/mask channels of one aggregate: the serialisable part of an AggregatorFactory */
-    public record GpuAggregate(int function, int inputChannel, int maskChannel) {}
+    /** function id (tgpu_agg_function) + input/mask channels of one aggregate (+ the tgpu_type of an avg(decimal) result): the serialisable part of an AggregatorFactory */
+    public record GpuAggregate(int function, int inputChannel, int maskChannel, int resultType)
+    {
+        public GpuAggregate(int function, int inputChannel, int maskChannel)
+        {
+            this(function, inputChannel, maskChannel, 0);
+        }
+    }
 
     private final int operatorId;
     private final PlanNodeId planNodeId;

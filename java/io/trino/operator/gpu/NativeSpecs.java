@@ -88,7 +88,7 @@ public final class NativeSpecs
                 fns.set(JAVA_INT, at, aggregate.function());
                 fns.set(JAVA_INT, at + 4, aggregate.inputChannel());
                 fns.set(JAVA_INT, at + 8, aggregate.maskChannel());
-                fns.set(JAVA_INT, at + 12, 0);
+                fns.set(JAVA_INT, at + 12, aggregate.resultType());      // avg(decimal) in a FINAL step: TGPU_INT64 / TGPU_INT128, else 0
             }
             MemorySegment types = arena.allocate(JAVA_INT, Math.max(1, inputChannelTypes.length));
             for (int i = 0; i < inputChannelTypes.length; i++) {
