@@ -174,7 +174,8 @@ def main():
         keys = g.integers(0, 10**6, m)
         return Page(Block.bigint(keys, g.random(m) < 0.02),
                     Block.varchar([None if i % 11 == 0 else "s%d-%s" % (k, "x" * int(k % 7)) for i, k in enumerate(keys)]),
-                    Block.double(keys * 0.5, g.random(m) < 0.05))
+                    Block.double(keys * 0.5, g.random(m) < 0.05),
+                    Block.int128([None if i % 13 == 0 else int(k) * 10**22 - 5 for i, k in enumerate(keys)]))      # a long DECIMAL column
 
     for null_channel, any_row in ((-1, False), (0, False), (0, True)):
         gpart = ops.PartitionedOutputOperatorFactory(ctx, [0], world, None, null_channel, any_row).create_operator()

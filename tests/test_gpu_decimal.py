@@ -177,6 +177,19 @@ def test_int128_partition_join_and_pass_through(ctx):
     probe = Page(Block.int128(keys[1000:3000] + [None]), Block.bigint(np.arange(2001)))
     rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
     assert rows == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False) and len(rows) >= 1000
+    # a BIGINT-key join whose build side carries a 128-bit payload: the fused probe + gather fast path moves at most 8-byte payloads, so this
+    # shape must take the general path (count / scan / gather) and still give the oracle's rows
+    bkeys = np.arange(3000, dtype=np.int64) * 7
+    build = Page(Block.bigint(bkeys), Block.int128([int(k) * 10**20 for k in bkeys]))
+    probe = Page(Block.bigint(rng.integers(0, 21000, 4096)), Block.bigint(np.arange(4096)))
+    rows = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
+    assert rows == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False) and len(rows) > 100
+    # GroupByHash.getGroupIds over a 128-bit key
+    gb = ops.GroupByHash(ctx, [0])
+    og = o.GroupByHash(0, 16)
+    kp = Page(Block.int128([None if i % 50 == 0 else keys[i % 300] for i in range(4000)]))
+    assert (gb.get_group_ids(kp) == og.get_group_ids(kp, [0])).all() and gb.get_group_count() == og.group_count()
+    gb.close(); og.close()
     # FilterAndProject: a filter on a BIGINT channel, the 128-bit channel passes through
     prog = ops.PageProcessorProgram(ops.Call(abi.EX_LT, ops.Col(1, abi.V_BIGINT), ops.Const(1234, abi.V_BIGINT)), [0, 1])
     fp = ops.FilterAndProjectOperatorFactory(ctx, prog).create_operator()

@@ -1252,7 +1252,7 @@ struct JoinBuildOp : tgpu_op {
         // slot-ordered copy of the build output columns for the fused probe
         bool slot_payload = !getenv("TGPU_JOIN_PAYLOAD_BY_ROW") && rows > 0 && lk->num_output > 0 && lk->num_output <= 4;
         for (int32_t b = 0; b < lk->num_output && slot_payload; b++)
-            slot_payload = lk->store.cols[1 + b].elem_size() > 0 && !lk->store.cols[1 + b].validity;
+            slot_payload = lk->store.cols[1 + b].elem_size() > 0 && lk->store.cols[1 + b].elem_size() <= 8 && !lk->store.cols[1 + b].validity;
         if (slot_payload) {
             lk->by_slot.resize(lk->num_output);
             for (int32_t b = 0; b < lk->num_output; b++) {
@@ -1322,7 +1322,7 @@ struct JoinProbeOp : tgpu_op {
         if (key_kind_of(key.type) != key_kind_of(lookup->key_type)) return TGPU_OK;   // reported by the general path
         for (int32_t b = 0; b < lookup->num_output; b++) {
             const DevColumn& c = lookup->store.cols[1 + b];
-            if (c.elem_size() == 0 || c.validity) return TGPU_OK;
+            if (c.elem_size() == 0 || c.elem_size() > 8 || c.validity) return TGPU_OK;      // (the fused gather moves 1 / 2 / 4 / 8-byte payloads)
         }
         auto jp = std::make_shared<DevBuf>();
         TG_TRY(jp->alloc(ctx, (size_t)n * 4));
