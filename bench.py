@@ -466,7 +466,9 @@ def main():
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_source": "ncu --set full capture of this kernel on this configuration, profiles/r02_kernels.md (bytes per launch)",
                     "frac_of_traffic": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
-                    "note": "frac can exceed 1: SURVEY §8(d)'s 40 B/row charges one table entry per probe ROW, but the ~4 rows of an order share one entry and the "
+                    "note": "algorithmic_bytes_per_row 40 = 8 key + 12 table entry + 4 position + 8 build payload read + 8 written: SURVEY §8(d)'s 52 minus the probe columns, "
+                            "which pass through as views (LookupJoinPageBuilder.java:144-150), with an 8-byte BIGINT build payload instead of the survey's INT32.  "
+                            "frac can exceed 1: the model charges one table entry per probe ROW, but the ~4 rows of an order share one entry and the "
                             "order-preserving layout reads every table line once; frac_of_traffic = measured DRAM bytes (ncu) / kernel time / peak is the physical utilisation",
                     "peak_source": peak_src, "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "rows_per_launch": l_count,
                     "kernel_ms": kms, "kernel_share_of_step": kms / ms_per_step, "launches_timed": len(kernel_ms)}

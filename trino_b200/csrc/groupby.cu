@@ -55,7 +55,7 @@ using namespace tg;
 constexpr unsigned long long EMPTY_KEY = 0x8000000000000000ULL;
 constexpr long long NO_ROW = 0x7FFFFFFFFFFFFFFFLL;
 constexpr int MAX_KEYS = 4;
-constexpr int MAX_SRCS = 16;
+constexpr int MAX_SRCS = 32;
 constexpr int MAX_ACCS = 40;   // (a FINAL decimal sum alone takes 9: four 128-bit pairs and its non-NULL counter)
 constexpr int S_THREADS = TGD_S_THREADS;
 static_assert(TGD_MAX_CHANNELS == TGPU_MAX_CHANNELS, "channel limits differ");
@@ -868,7 +868,7 @@ __global__ void __launch_bounds__(XT) gf_slice_hist_kernel(AggPlan plan, DColumn
     int since_fold = 0;
     auto fold = [&]() {
         // my 64 counters -> the CTA totals (each thread folds its own column, rotated so that the threads of a warp hit different counters)
-        for (int k = 0; k < S; k++) {
+        for (int k = 0; k < XMAXP; k++) {
             const int q = (k + threadIdx.x) & (XMAXP - 1);
             if (q < S) {
                 const unsigned int c = priv[q * XT + threadIdx.x];
@@ -1946,7 +1946,7 @@ struct AggOp : tgpu_op {
             if (fp.acc_main < 0 || (fp.acc_count == -1 && false)) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many accumulators");
             fnplans.push_back(fp);
         }
-        if (plan.num_srcs >= MAX_SRCS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many distinct aggregate inputs");
+        if (plan.num_srcs > MAX_SRCS) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "too many distinct aggregate inputs");
         // every non-null counter can fall back on the row counter of its mask when its input has no NULLs in a page
         for (int a = 0, n0 = plan.num_accs; a < n0; a++)
             if (plan.accs[a].kind == ACC_NONNULL && add_acc(ACC_ROWS, -1, plan.accs[a].mask) < 0)
@@ -3288,6 +3288,7 @@ extern "C" int tgpu_groupby_hash_get_group_ids(tgpu_op* op, const tgpu_page* pag
     if (page->num_rows == 0) return TGPU_OK;
     DevPage in;
     TG_TRY(tg_ingest_page(ctx, page, &in));
+    TG_TRY(a->prepare_wide(&in));
     TG_TRY(a->encode_string_keys(&in));
     if (!a->planned) {
         TG_TRY(a->make_plan(in));
