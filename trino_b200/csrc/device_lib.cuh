@@ -441,7 +441,7 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
 // tickets layout: [0, WAYS) claims per way, [WAYS] deferred rows, [WAYS + 1] special groups born.
 // P supplies, besides load() / row(): accumulate_global(unsigned long long* acc) - reductions on the record's accumulator words.
 #define TGD_TICKET_WAYS 64
-#define TGD_G_ROWS 4
+#define TGD_G_ROWS 2      // (swept on B200 with __launch_bounds__(256, 4): 1 -> 8.3 ms, 2 -> 6.9, 4 -> 8.1, 8 -> 11.1 for 150 M rows / 10 M groups)
 
 // {a, b} = the two 64-bit words at p (16-byte aligned) in one L2 transaction, never served from the L1
 __device__ __forceinline__ void tgd_ld_pair(const unsigned long long* p, unsigned long long& a, unsigned long long& b)
@@ -454,7 +454,7 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
                                                  const int* __restrict__ stamp_rows, long long page_base, unsigned long long* __restrict__ recs, long long cap, int W,
                                                  int* __restrict__ tickets, int budget_per_way, int* __restrict__ deferred, unsigned int* __restrict__ err_out)
 {
-    constexpr int R = TGD_G_ROWS;
+    constexpr int R = P::GR;          // rows in flight per thread (TGD_G_ROWS unless the generator says otherwise)
     const unsigned long long mask = (unsigned long long)cap - 1;
     const int way = ((threadIdx.x >> 5) + blockIdx.x * 8) & (TGD_TICKET_WAYS - 1);      // one ticket word per warp at a time
     const int lane = threadIdx.x & 31;

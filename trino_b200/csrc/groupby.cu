@@ -1338,6 +1338,14 @@ static std::string gen_operand(const DOperand& o)
 }
 
 // `elems[c]` = element size of input channel c (0 = not a fixed-width column); bit c of nullable_mask = channel c has a validity bitmap
+// rows in flight per thread of the fused general kernel (TGPU_AGG_G_ROWS: 1, 2, 4 or 8; experiments)
+static int general_rows_per_thread()
+{
+    const char* e = getenv("TGPU_AGG_G_ROWS");
+    const int r = e ? atoi(e) : TGD_G_ROWS;
+    return r == 1 || r == 2 || r == 4 || r == 8 ? r : TGD_G_ROWS;
+}
+
 static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* prog, const int* elems, int num_channels, int L, int min_blocks,
                                         uint32_t nullable_mask, AccMap* map, bool vec = false)
 {
@@ -1395,7 +1403,8 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
     }
     map->compact_count = compact;
 
-    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4;\n  static constexpr bool VEC = %s;\n", L, compact, vec ? "true" : "false");
+    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4, GR = %d;\n  static constexpr bool VEC = %s;\n", L, compact, general_rows_per_thread(),
+            vec ? "true" : "false");
     s += "  __device__ static __forceinline__ int acc_kind(int a) {\n    switch (a) {\n";
     for (int a = 0; a < compact; a++) appendf(s, "      case %d: return %d;\n", a, kinds[a]);
     s += "      default: return 0;\n    }\n  }\n";
@@ -1539,7 +1548,7 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
     {
         const char* e = getenv("TGPU_AGG_G_MINB");
         appendf(s, "extern \"C\" __global__ void __launch_bounds__(256, %d) tg_agg_general_jit(DColumns cols, long long n, const int* rows, long long first, const int* stamp_rows,\n",
-                e ? atoi(e) : 3);
+                e ? atoi(e) : 4);
     }
     s += ""
          "    long long page_base, unsigned long long* recs, long long cap, int W, int* tickets, int budget_per_way, int* deferred, unsigned int* err_out) {\n"
@@ -2379,7 +2388,7 @@ struct AggOp : tgpu_op {
                 int* deferred_arg = deferred.as<int>();
                 unsigned int* err_arg = (unsigned int*)(d_tickets + WAYS + 2);
                 void* params[13] = {&cols_arg, &n_arg, &rows_arg, &first_arg, &stamps_arg, &base_arg, &recs_arg, &cap_arg, &w_arg, &tickets_arg, &per_way, &deferred_arg, &err_arg};
-                grid = (int)std::min<int64_t>(tg_div_up(todo, 256 * TGD_G_ROWS), (int64_t)ctx->sm_count * std::max(1, jit_blocks_per_sm(jit_fn, 256, 0)));
+                grid = (int)std::min<int64_t>(tg_div_up(todo, 256 * general_rows_per_thread()), (int64_t)ctx->sm_count * std::max(1, jit_blocks_per_sm(jit_fn, 256, 0)));
                 TG_TRY(jit_launch(ctx, jit_fn, std::max(grid, 1), 256, 0, params));
             }
             else
