@@ -37,6 +37,30 @@ NCU_TRAFFIC_PROBE_FUSED_SF100 = 8.429180e9 + 7.174483e9      # 600 000 003 rows:
 NCU_TRAFFIC_Q1_SF300 = 68.402849e9 + 4.701952e6               # 1.8 G rows: 38.0 B/row (tg_agg_small_jit, four consecutive rows per thread)
 
 
+def bind_to_gpu_numa_node(local):
+    """N > 1: run this rank's host threads (and so first-touch its pinned staging) on the NUMA node its GPU hangs off, so that the
+    end-to-end path of 8 ranks does not funnel through one socket's memory controller.  Best effort: silently a no-op when the
+    topology files are not there."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -207,6 +231,7 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = ops.Context(local)
     lib = ctx.lib
