@@ -1,5 +1,5 @@
 set -x
-O=gpurun_out/r2w
+O=gpurun_out/r3f
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > $O/pytest.log 2>&1; tail -6 $O/pytest.log
