@@ -46,7 +46,8 @@ def _allreduce_u64(dist, local, values):
     if dist is None:
         return [v & M64 for v in values]
     import torch
-    t = torch.tensor([v >> 32 for v in values] + [v & 0xFFFFFFFF for v in values], dtype=torch.int64, device=f"cuda:{local}")
+    device = f"cuda:{local}" if dist.get_backend() == "nccl" else "cpu"       # (gloo: the CPU test of this helper)
+    t = torch.tensor([v >> 32 for v in values] + [v & 0xFFFFFFFF for v in values], dtype=torch.int64, device=device)
     dist.all_reduce(t)
     t = [int(x) for x in t.tolist()]
     k = len(values)
@@ -57,7 +58,7 @@ def _max_ms(dist, local, ms):
     if dist is None:
         return ms
     import torch
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}" if dist.get_backend() == "nccl" else "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 

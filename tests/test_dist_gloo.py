@@ -64,6 +64,12 @@ def _worker(rank, world, port, out):
     stats = torch.tensor([len(mine), len(my_build), int(mine.sum() % (1 << 40))], dtype=torch.int64)
     allstats = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(allstats, stats)
+    # the checksum plumbing of bench.py --workload … (bench_workloads.py): 64-bit wrap-around sums and max-over-ranks timing
+    import bench_workloads as bw
+    big = [(1 << 63) + 12345 + rank, (1 << 64) - 1, rank]
+    tot = bw._allreduce_u64(dist, 0, big)
+    assert tot == [(sum((1 << 63) + 12345 + r for r in range(world))) & bw.M64, (world * ((1 << 64) - 1)) & bw.M64, sum(range(world))]
+    assert bw._max_ms(dist, 0, 1.5 + rank) == 1.5 + world - 1
     if rank == 0:
         assert sum(int(s[0]) for s in allstats) == total_rows
         assert sum(int(s[1]) for s in allstats) == n_orders
