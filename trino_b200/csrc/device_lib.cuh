@@ -589,7 +589,7 @@ __device__ __forceinline__ void agg_general_body(P& prog, const DColumns& cols, 
 // of the chunk; a scan of the chunk counts gives every chunk its first output row.  Pass 2 ranks the selected rows of a tile
 // (ballot + a scan over the tile's (iteration, warp) cells), evaluates the projections and copies the pass-through channels
 // straight to output row chunk_off + rank: output order = input order (PageProcessor.java:302-336).
-// P supplies: static bool filter(cols, row, err*), struct Regs, static void load(cols, row, Regs&), static void eval(Regs, j, out, err*, nulls_seen*).
+// P supplies: static bool filter(cols, row, err*), static void row(cols, row, j, out, err*, nulls_seen*).
 constexpr int FPC_R = 4;          // tile = FPC_R x 256 rows
 constexpr int FPC_T = 256;
 
@@ -600,16 +600,10 @@ __device__ __forceinline__ void fp_filter_chunks_body(const DColumns& cols, long
     __shared__ unsigned int warp_sel[FPC_T / 32];
     const long long begin = (long long)blockIdx.x * chunk, end = begin + chunk < n ? begin + chunk : n;
     unsigned int err = 0, mine = 0;
-    // four rows per trip, all four evaluated before the first flag is stored (a store between them would pin the later loads behind it)
-    for (long long row = begin + threadIdx.x; row < end; row += 4 * FPC_T) {
-        bool s[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) s[i] = row + i * FPC_T < end ? P::filter(cols, row + i * FPC_T, &err) : false;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (row + i * FPC_T < end) flags[row + i * FPC_T] = s[i] ? 1 : 0;
-            mine += s[i] ? 1u : 0u;
-        }
+    for (long long row = begin + threadIdx.x; row < end; row += FPC_T) {
+        bool s = P::filter(cols, row, &err);
+        flags[row] = s ? 1 : 0;
+        mine += s ? 1u : 0u;
     }
     for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
     if ((threadIdx.x & 31) == 0) warp_sel[threadIdx.x >> 5] = mine;
@@ -637,19 +631,10 @@ __device__ __forceinline__ void fp_project_chunks_body(const DColumns& cols, con
     for (long long tile = begin; tile < end; tile += (long long)FPC_R * FPC_T) {
         bool sel[FPC_R];
         unsigned int rank[FPC_R];
-        // every load of the tile's FPC_R rows of this thread is issued before the first row is evaluated (rows the filter rejected
-        // included: ~5 % wasted bytes on Q1 against four times the loads in flight)
-        typename P::Regs regs[FPC_R];
-        unsigned char flag[FPC_R];
 #pragma unroll
         for (int i = 0; i < FPC_R; i++) {
             long long row = tile + (long long)i * FPC_T + threadIdx.x;
-            flag[i] = row < end ? flags[row] : 0;
-            if (row < end) P::load(cols, row, regs[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < FPC_R; i++) {
-            sel[i] = flag[i] != 0;
+            sel[i] = row < end && flags[row] != 0;
             unsigned int b = __ballot_sync(0xffffffffu, sel[i]);
             rank[i] = __popc(b & ((1u << lane) - 1));
             if (lane == 0) cells[i * NW + warp] = __popc(b);
@@ -669,7 +654,8 @@ __device__ __forceinline__ void fp_project_chunks_body(const DColumns& cols, con
 #pragma unroll
         for (int i = 0; i < FPC_R; i++) {
             if (!sel[i]) continue;
-            P::eval(regs[i], running + cells[i * NW + warp] + rank[i], out, &err, &nulls_seen);
+            long long row = tile + (long long)i * FPC_T + threadIdx.x;
+            P::row(cols, row, running + cells[i * NW + warp] + rank[i], out, &err, &nulls_seen);
         }
         running += tile_total;
         __syncthreads();

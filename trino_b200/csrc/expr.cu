@@ -223,33 +223,9 @@ static std::string gen_fp_source(const DProgram& prog, const int* elems, int num
     s += loads + temps;
     fp_emit_insns(s, prog, 0, prog.num_filter_insns, "&err");
     fp_appendf(s, "    *errp |= err;\n    return !tn%d && t%d != 0;\n  }\n", prog.filter_temp, prog.filter_temp);
-    // the projection of one row in two halves - every global load of the row (operand columns and pass-through channels), then the
-    // arithmetic and the stores - so that the body can put the loads of several rows in flight before it evaluates the first
-    auto pass_type = [&](int ch) { return elems[ch] == 16 ? "int4" : elems[ch] == 8 ? "long long" : elems[ch] == 4 ? "int" : elems[ch] == 2 ? "short" : "signed char"; };
-    s += "  struct Regs {\n";
-    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++)
-        if (used[c]) fp_appendf(s, "    long long c%d; bool c%dn;\n", c, c);
-    for (size_t k = 0; k < pass_channels.size(); k++) fp_appendf(s, "    %s p%d; bool p%dn;\n", pass_type(pass_channels[k]), (int)k, (int)k);
-    s += "  };\n";
-    s += "  static __device__ __forceinline__ void load(const DColumns& cols, long long row, Regs& r) {\n";
-    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++) {
-        if (!used[c]) continue;
-        fp_appendf(s, "    r.c%d = tg_load_elem<%d>(cols.cols[%d].data, row);", c, elems[c], c);
-        if ((nullable_mask >> c) & 1) fp_appendf(s, " r.c%dn = !tg_valid(cols.cols[%d].validity, row);\n", c, c);
-        else fp_appendf(s, " r.c%dn = false;\n", c);
-    }
-    for (size_t k = 0; k < pass_channels.size(); k++) {
-        int ch = pass_channels[k];
-        fp_appendf(s, "    r.p%d = ((const %s*)cols.cols[%d].data)[row];", (int)k, pass_type(ch), ch);
-        if ((nullable_mask >> ch) & 1) fp_appendf(s, " r.p%dn = !tg_valid(cols.cols[%d].validity, row);\n", (int)k, ch);
-        else fp_appendf(s, " r.p%dn = false;\n", (int)k);
-    }
-    s += "  }\n";
-    s += "  static __device__ __forceinline__ void eval(const Regs& r, long long j, const OutCols& out, unsigned int* errp, unsigned int* nullsp) {\n";
+    s += "  static __device__ __forceinline__ void row(const DColumns& cols, long long row, long long j, const OutCols& out, unsigned int* errp, unsigned int* nullsp) {\n";
     s += "    unsigned int err = 0, ignored = 0, nulls_seen = 0;\n";
-    for (int c = 0; c < num_channels && c < TGPU_MAX_CHANNELS; c++)
-        if (used[c]) fp_appendf(s, "    const long long c%d = r.c%d; const bool c%dn = r.c%dn;\n", c, c, c, c);
-    s += temps;
+    s += loads + temps;
     fp_emit_insns(s, prog, 0, prog.num_filter_insns, "&ignored");
     fp_emit_insns(s, prog, prog.num_filter_insns, prog.num_insns, "&err");
     s += "    for (int c = 0; c < out.count; c++) {\n      long long v = 0; bool isn = true;\n      switch (out.temp[c]) {\n";
@@ -259,8 +235,9 @@ static std::string gen_fp_source(const DProgram& prog, const int* elems, int num
     s += "      out.nullmap[c][j] = isn ? 1 : 0;\n      if (isn) nulls_seen |= 1u << c;\n    }\n";
     for (size_t k = 0; k < pass_channels.size(); k++) {
         int ch = pass_channels[k];
-        fp_appendf(s, "    ((%s*)out.pass_data[%d])[j] = r.p%d;\n", pass_type(ch), (int)k, (int)k);
-        if ((nullable_mask >> ch) & 1) fp_appendf(s, "    out.pass_nullmap[%d][j] = r.p%dn ? 1 : 0;\n", (int)k, (int)k);
+        const char* ty = elems[ch] == 16 ? "int4" : elems[ch] == 8 ? "long long" : elems[ch] == 4 ? "int" : elems[ch] == 2 ? "short" : "signed char";
+        fp_appendf(s, "    ((%s*)out.pass_data[%d])[j] = ((const %s*)cols.cols[%d].data)[row];\n", ty, (int)k, ty, ch);
+        if ((nullable_mask >> ch) & 1) fp_appendf(s, "    out.pass_nullmap[%d][j] = tg_valid(cols.cols[%d].validity, row) ? 0 : 1;\n", (int)k, ch);
     }
     s += "    (void)ignored;\n    *errp |= err;\n    *nullsp |= nulls_seen;\n  }\n};\n";
     s += "extern \"C\" __global__ void __launch_bounds__(256) tg_fp_filter_chunks_jit(DColumns cols, long long n, long long chunk, unsigned char* flags, "
