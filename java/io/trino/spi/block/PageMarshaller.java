@@ -131,6 +131,114 @@ public final class PageMarshaller
         return new Page(flat.getPositionCount(), blocks);
     }
 
+    // ------------------------------------------------------------------------------------------------ decimal aggregation states
+    /**
+     * LongDecimalWithOverflowState travels as VARBINARY (LongDecimalWithOverflowStateSerializer.java:36-96): low, [high, [overflow]] as
+     * little-endian longs, NULL for an empty state.  The C ABI wants an Int128ArrayBlock (sum) and a LongArrayBlock (overflow).
+     * trino_b200/page.py (decode_decimal_sum_states / encode_decimal_sum_states, …_avg_…) is the tested mirror of these.
+     */
+    public static Block[] decodeDecimalSumStates(Block states)
+    {
+        int positions = states.getPositionCount();
+        long[] words = new long[positions * 2];
+        long[] overflow = new long[positions];
+        boolean[] isNull = new boolean[positions];
+        VariableWidthBlock flat = (VariableWidthBlock) flat(states);
+        for (int position = 0; position < positions; position++) {
+            if (flat.isNull(position)) {
+                isNull[position] = true;
+                continue;
+            }
+            Slice slice = flat.getRawSlice();
+            int at = flat.getRawSliceOffset(position);
+            int length = flat.getSliceLength(position);
+            words[2 * position + 1] = slice.getLong(at);                                   // low
+            words[2 * position] = length >= 16 ? slice.getLong(at + 8) : 0;                // high (Int128ArrayBlock: high word first)
+            overflow[position] = length == 24 ? slice.getLong(at + 16) : 0;
+        }
+        return new Block[] {new Int128ArrayBlock(positions, Optional.of(isNull), words), new LongArrayBlock(positions, Optional.empty(), overflow)};
+    }
+
+    public static Block encodeDecimalSumStates(Int128ArrayBlock sums, LongArrayBlock overflows)
+    {
+        VariableWidthBlockBuilder out = new VariableWidthBlockBuilder(null, sums.getPositionCount(), sums.getPositionCount() * 24);
+        for (int position = 0; position < sums.getPositionCount(); position++) {
+            if (sums.isNull(position)) {
+                out.appendNull();
+                continue;
+            }
+            long high = sums.getInt128High(position);
+            long low = sums.getInt128Low(position);
+            long overflow = overflows.getLong(position);
+            Slice buffer = Slices.allocate(24);
+            buffer.setLong(0, low);
+            buffer.setLong(8, high);
+            buffer.setLong(16, overflow);
+            out.writeEntry(buffer, 0, overflow != 0 ? 24 : (high != 0 ? 16 : 8));
+        }
+        return out.build();
+    }
+
+    /** LongDecimalWithOverflowAndLongStateSerializer.java:36-113: low, [high,] [count, overflow]; NULL when count == 0 */
+    public static Block[] decodeDecimalAverageStates(Block states)
+    {
+        int positions = states.getPositionCount();
+        long[] words = new long[positions * 2];
+        long[] overflow = new long[positions];
+        long[] count = new long[positions];
+        boolean[] isNull = new boolean[positions];
+        VariableWidthBlock flat = (VariableWidthBlock) flat(states);
+        for (int position = 0; position < positions; position++) {
+            if (flat.isNull(position)) {
+                isNull[position] = true;
+                continue;
+            }
+            Slice slice = flat.getRawSlice();
+            int at = flat.getRawSliceOffset(position);
+            int length = flat.getSliceLength(position);
+            words[2 * position + 1] = slice.getLong(at);
+            count[position] = 1;
+            switch (length) {
+                case 32 -> {
+                    words[2 * position] = slice.getLong(at + 8);
+                    count[position] = slice.getLong(at + 16);
+                    overflow[position] = slice.getLong(at + 24);
+                }
+                case 24 -> {
+                    count[position] = slice.getLong(at + 8);
+                    overflow[position] = slice.getLong(at + 16);
+                }
+                case 16 -> words[2 * position] = slice.getLong(at + 8);
+                default -> {}
+            }
+        }
+        return new Block[] {new Int128ArrayBlock(positions, Optional.of(isNull), words), new LongArrayBlock(positions, Optional.empty(), overflow),
+                new LongArrayBlock(positions, Optional.empty(), count)};
+    }
+
+    public static Block encodeDecimalAverageStates(Int128ArrayBlock sums, LongArrayBlock overflows, LongArrayBlock counts)
+    {
+        VariableWidthBlockBuilder out = new VariableWidthBlockBuilder(null, sums.getPositionCount(), sums.getPositionCount() * 32);
+        for (int position = 0; position < sums.getPositionCount(); position++) {
+            long count = counts.getLong(position);
+            if (count == 0) {
+                out.appendNull();
+                continue;
+            }
+            long high = sums.isNull(position) ? 0 : sums.getInt128High(position);
+            long low = sums.isNull(position) ? 0 : sums.getInt128Low(position);
+            long overflow = overflows.getLong(position);
+            Slice buffer = Slices.allocate(32);
+            buffer.setLong(0, low);
+            buffer.setLong(8, high);
+            int countOffset = high == 0 ? 1 : 2;
+            buffer.setLong(8 * countOffset, count);
+            buffer.setLong(8 * (countOffset + 1), overflow);
+            out.writeEntry(buffer, 0, 8 * (countOffset + ((overflow == 0 && count == 1) ? 0 : 2)));
+        }
+        return out.build();
+    }
+
     // ------------------------------------------------------------------------------------------------ batching (Operator.addInput side)
     /** returns true when the batch should be flushed into the native operator now */
     public boolean append(Page page)

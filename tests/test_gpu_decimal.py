@@ -278,3 +278,25 @@ def test_decimal_average_partial_final_and_skipped_builders(ctx):
         ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, finals, 16)
         assert _rows(ctx, ff, partial) == want, controller_off
         controller.close()
+
+
+def test_reference_typed_states_between_partial_and_final(ctx):
+    # a GPU PARTIAL feeding a FINAL through the reference's own state types: avg(double) as ROW(BIGINT, DOUBLE), the decimal states as
+    # VARBINARY (LongDecimalWithOverflow[AndLong]StateSerializer); channel numbers on the FINAL factory are the Java plan's
+    from trino_b200.page import RowBlock
+    rng = np.random.default_rng(36)
+    pages = _decimal_pages(rng, 30, (2000, 2500))
+    aggs = [A(abi.AGG_SUM_DECIMAL, 1), A(abi.AGG_AVG, 2), A(abi.AGG_AVG_DECIMAL, 1), A(abi.AGG_COUNT_STAR)]
+    single = _rows(ctx, ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_SINGLE, aggs, 16), pages)
+    pf = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_PARTIAL, aggs, 16, row_typed_states=True)
+    partial = []
+    for p in pages:
+        op = pf.create_operator()
+        partial += ops.drive(op, [p])
+        op.close()
+    first = partial[0]
+    assert first.channel_count == 5 and first.get_block(1).type == abi.UTF8 and isinstance(first.get_block(2), RowBlock) and first.get_block(3).type == abi.UTF8
+    finals = [A(abi.AGG_SUM_DECIMAL, 1), A(abi.AGG_AVG, 2), A(abi.AGG_AVG_DECIMAL, 3, result_type=abi.INT128), A(abi.AGG_COUNT_STAR, 4)]
+    ff = ops.HashAggregationOperatorFactory(ctx, [0], abi.STEP_FINAL, finals, 16, row_typed_states=True)
+    from helpers import rows_equal
+    assert rows_equal(_rows(ctx, ff, partial), single, rel=1e-9)

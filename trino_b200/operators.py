@@ -19,7 +19,7 @@ import ctypes as C
 import numpy as np
 
 from . import abi
-from .page import AbiPage, Block, Page, RowBlock, compose_row_blocks, flatten_row_blocks
+from .page import AbiPage, Block, Page, RowBlock, compose_row_blocks, compose_state_blocks, flatten_row_blocks, flatten_state_blocks
 
 _NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64}
 _ELEM = {abi.INT64: 8, abi.INT32: 4, abi.INT16: 2, abi.INT8: 1, abi.FLOAT64: 8}
@@ -457,16 +457,17 @@ class HashAggregationOperator(Operator):
     # operator that speaks the reference's state types.  in_first: flat channel of each original input channel; out_widths: see
     # page.compose_row_blocks
     _out_widths = None
+    _in_decimal = None            # {input channel (the plan's numbering): "decimal_sum" | "decimal_avg"}: VARBINARY decimal states to unpack
 
     def add_input(self, page):
-        if hasattr(page, "blocks") and any(isinstance(b, RowBlock) for b in page.blocks):
-            page, _ = flatten_row_blocks(page)
+        if hasattr(page, "blocks") and (self._in_decimal or any(isinstance(b, RowBlock) for b in page.blocks)):
+            page = flatten_state_blocks(page, self._in_decimal or {})
         super().add_input(page)
 
     def get_output(self):
         out = super().get_output()
         if out is not None and self._out_widths is not None:
-            out = compose_row_blocks(out, self._out_widths)
+            out = compose_state_blocks(out, self._out_widths)
         return out
 
     def group_count(self):
@@ -523,9 +524,12 @@ class HashAggregationOperatorFactory(OperatorFactory):
         self.controller = partial_aggregation_controller
         self.row_typed_states = row_typed_states
 
+    _FLAT = {abi.AGG_AVG: 2, abi.AGG_SUM_DECIMAL: 2, abi.AGG_AVG_DECIMAL: 3}           # flat state columns per function (default 1)
+    _DECIMAL = {abi.AGG_SUM_DECIMAL: "decimal_sum", abi.AGG_AVG_DECIMAL: "decimal_avg"}
+
     def _state_widths(self):
-        """flat columns per aggregate state: avg's LongAndDoubleState is the only two-field state of the supported functions"""
-        return [2 if a.function == abi.AGG_AVG else 1 for a in self.aggregators]
+        """the reference's state type per aggregate: ROW(BIGINT, DOUBLE) for avg (2 flat columns), VARBINARY for the decimal states"""
+        return [self._DECIMAL.get(a.function, self._FLAT.get(a.function, 1)) for a in self.aggregators]
 
     def _create(self):
         from_state = self.step in (abi.STEP_FINAL, abi.STEP_INTERMEDIATE)
@@ -533,12 +537,12 @@ class HashAggregationOperatorFactory(OperatorFactory):
         keys_list, agg_inputs = list(self.group_by_channels), [a.input_channel for a in self.aggregators]
         if self.row_typed_states and from_state:
             # channels are numbered as the Java plan numbers them (one channel per ROW state); the library sees the flattened page
-            wide = {a.input_channel for a in self.aggregators if a.function == abi.AGG_AVG}
+            wide = {a.input_channel: self._FLAT[a.function] for a in self.aggregators if a.function in self._FLAT}
             top = max(keys_list + agg_inputs + [0])
             first, at = [], 0
             for c in range(top + 1):
                 first.append(at)
-                at += 2 if c in wide else 1
+                at += wide.get(c, 1)
             keys_list = [first[c] for c in keys_list]
             agg_inputs = [first[c] if c >= 0 else c for c in agg_inputs]
         keys = _i32(keys_list)
@@ -560,6 +564,8 @@ class HashAggregationOperatorFactory(OperatorFactory):
         op = HashAggregationOperator(self.ctx, h)
         if self.row_typed_states and to_state:
             op._out_widths = [1] * len(self.group_by_channels) + self._state_widths()
+        if self.row_typed_states and from_state:
+            op._in_decimal = {a.input_channel: self._DECIMAL[a.function] for a in self.aggregators if a.function in self._DECIMAL}
         return op
 
     def duplicate(self):

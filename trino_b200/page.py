@@ -226,6 +226,131 @@ def compose_row_blocks(page, widths):
     return Page(*blocks, position_count=page.position_count)
 
 
+# ---- decimal aggregation states as the reference serialises them (VARBINARY) ----------------------------------------------------------
+# The C ABI carries a decimal sum state as two flat columns (INT128 sum, BIGINT overflow) and a decimal average state as three (+ BIGINT
+# row count); between a Java PARTIAL and a Java FINAL step they travel as ONE VARBINARY channel of 8 to 32 bytes per group:
+#   sum: low, [high, [overflow]]          - LongDecimalWithOverflowStateSerializer.serialize :36-60 / deserialize :62-96
+#   avg: low, [high,] [count, overflow]   - LongDecimalWithOverflowAndLongStateSerializer.serialize :36-70 / deserialize :72-113
+# (M/operator/aggregation/state/).  These four functions are the marshaller's side of that (PageMarshaller.java has the same pair).
+def _words_of(block, i):
+    v = block.values[i]
+    return int(v[0]), int(v[1])          # high, low
+
+
+def _le64(*words):
+    return b"".join(int(w & ((1 << 64) - 1)).to_bytes(8, "little") for w in words)
+
+
+def _i64(b):
+    return int.from_bytes(b, "little", signed=True)
+
+
+def encode_decimal_sum_states(sum_block, overflow_block):
+    out = []
+    for i in range(sum_block.position_count):
+        if sum_block.is_null(i):
+            out.append(None)                                              # !state.isNotNull() -> appendNull
+            continue
+        high, low = _words_of(sum_block, i)
+        overflow = int(overflow_block.values[i])
+        words = [low] + ([high] if high != 0 else [])
+        if overflow != 0:
+            words = [low, high, overflow]
+        out.append(_le64(*words))
+    return Block.varchar(out)
+
+
+def decode_decimal_sum_states(block):
+    sums, overflows = [], []
+    for i in range(block.position_count):
+        b = block.get(i)
+        if b is None:
+            sums.append(None)
+            overflows.append(0)
+            continue
+        low = _i64(b[0:8])
+        high = _i64(b[8:16]) if len(b) >= 16 else 0
+        overflow = _i64(b[16:24]) if len(b) == 24 else 0
+        sums.append((high << 64) | (low & ((1 << 64) - 1)))
+        overflows.append(overflow)
+    return Block.int128(sums), Block.bigint(overflows)
+
+
+def encode_decimal_avg_states(sum_block, overflow_block, count_block):
+    out = []
+    for i in range(sum_block.position_count):
+        count = int(count_block.values[i])
+        if count == 0:
+            out.append(None)
+            continue
+        high, low = (0, 0) if sum_block.is_null(i) else _words_of(sum_block, i)
+        overflow = int(overflow_block.values[i])
+        words = [low] + ([high] if high != 0 else [])
+        if not (overflow == 0 and count == 1):
+            words += [count, overflow]
+        out.append(_le64(*words))
+    return Block.varchar(out)
+
+
+def decode_decimal_avg_states(block):
+    sums, overflows, counts = [], [], []
+    for i in range(block.position_count):
+        b = block.get(i)
+        if b is None:
+            sums.append(None)
+            overflows.append(0)
+            counts.append(0)
+            continue
+        low, high, overflow, count = _i64(b[0:8]), 0, 0, 1
+        if len(b) == 32:
+            high, count, overflow = _i64(b[8:16]), _i64(b[16:24]), _i64(b[24:32])
+        elif len(b) == 16:
+            high = _i64(b[8:16])
+        elif len(b) == 24:
+            count, overflow = _i64(b[8:16]), _i64(b[16:24])
+        sums.append((high << 64) | (low & ((1 << 64) - 1)))
+        overflows.append(overflow)
+        counts.append(count)
+    return Block.int128(sums), Block.bigint(overflows), Block.bigint(counts)
+
+
+def compose_state_blocks(page, layout):
+    """layout[c] of output channel c: 1 (a plain block), an int k > 1 (ROW of k flat channels), "decimal_sum" (2 flat channels ->
+    VARBINARY) or "decimal_avg" (3 flat channels -> VARBINARY)"""
+    blocks, at = [], 0
+    for item in layout:
+        if item == "decimal_sum":
+            blocks.append(encode_decimal_sum_states(page.blocks[at], page.blocks[at + 1]))
+            at += 2
+        elif item == "decimal_avg":
+            blocks.append(encode_decimal_avg_states(page.blocks[at], page.blocks[at + 1], page.blocks[at + 2]))
+            at += 3
+        elif item == 1:
+            blocks.append(page.blocks[at])
+            at += 1
+        else:
+            blocks.append(RowBlock(page.blocks[at:at + item]))
+            at += item
+    assert at == page.channel_count, "state layout does not cover the page"
+    return Page(*blocks, position_count=page.position_count)
+
+
+def flatten_state_blocks(page, decimal_channels):
+    """decimal_channels: {input channel: "decimal_sum" | "decimal_avg"}; ROW blocks flatten by themselves.  -> flat page"""
+    blocks = []
+    for c, b in enumerate(page.blocks):
+        kind = decimal_channels.get(c)
+        if kind == "decimal_sum":
+            blocks.extend(decode_decimal_sum_states(b.flatten()))
+        elif kind == "decimal_avg":
+            blocks.extend(decode_decimal_avg_states(b.flatten()))
+        elif isinstance(b, RowBlock):
+            blocks.extend(b.null_suppressed_fields())
+        else:
+            blocks.append(b)
+    return Page(*blocks, position_count=page.position_count)
+
+
 class Page:
     """S/Page.java:31"""
 
