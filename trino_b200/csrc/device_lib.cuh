@@ -336,7 +336,10 @@ __device__ __forceinline__ void agg_small_body(P& prog, const DColumns& cols, in
 
     for (int i = tid; i < L; i += T) tkeys[i] = TGD_EMPTY_KEY;
     for (int i = tid; i < L + 2; i += T) lfirst[i] = TGD_NO_ROW;
-    for (int s = 0; s < L + 2; s++)
+    // the two special groups (NULL key, sentinel-valued key) exist for single-key plans only: a packed multi-column key never takes them,
+    // and without their accumulator sets a CTA needs a third less shared memory (Q1: 73.8 -> 49.2 KB, 4 CTAs per SM instead of 3)
+    constexpr int SETS = P::SPECIALS ? L + 2 : L;
+    for (int s = 0; s < SETS; s++)
         for (int a = 0; a < A; a++) acc[((size_t)s * A + a) * T + tid] = acc_init(P::acc_kind(a));
     __shared__ int s_overflow;
     if (tid == 0) s_overflow = 0;

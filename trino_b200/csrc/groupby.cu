@@ -1403,8 +1403,8 @@ static std::string gen_agg_small_source(const AggPlan& plan, const DProgram* pro
     }
     map->compact_count = compact;
 
-    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4, GR = %d;\n  static constexpr bool VEC = %s;\n", L, compact, general_rows_per_thread(),
-            vec ? "true" : "false");
+    appendf(s, "struct Prog {\n  static constexpr int L = %d, A = %d, R = 4, GR = %d;\n  static constexpr bool VEC = %s, SPECIALS = %s;\n", L, compact, general_rows_per_thread(),
+            vec ? "true" : "false", plan.num_keys == 1 ? "true" : "false");
     s += "  __device__ static __forceinline__ int acc_kind(int a) {\n    switch (a) {\n";
     for (int a = 0; a < compact; a++) appendf(s, "      case %d: return %d;\n", a, kinds[a]);
     s += "      default: return 0;\n    }\n  }\n";
@@ -2042,7 +2042,10 @@ struct AggOp : tgpu_op {
     {
         int64_t n = in.rows;
         int L = s_L, A = plan.num_accs;
-        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (smem_limit() + 2048) / (s_smem + 1024)));
+        // (the specialised kernel of a multi-key plan carries no accumulator sets for the special groups)
+        const size_t jit_smem = jit_available() && plan.num_keys > 1 ? s_smem - 2 * s_per_slot : s_smem;
+        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (smem_limit() + 2048) / (jit_smem + 1024)));
+        if (const char* e = getenv("TGPU_AGG_S_MINB")) ctas_per_sm = std::max(1, std::min(ctas_per_sm, atoi(e)));
         int grid = tg_grid(ctx, n, S_THREADS * 4, ctas_per_sm);
         if (grid != s_grid) {
             TG_TRY(blk_keys.alloc(ctx, (size_t)grid * L * 8));
@@ -2099,7 +2102,8 @@ struct AggOp : tgpu_op {
             long long n_arg = n;
             DColumns cols_arg = cols;
             void* params[3] = {&cols_arg, &n_arg, &so};
-            size_t smem = (size_t)L * 8 + (size_t)(L + 2) * 8 + (size_t)(L + 2) * map.compact_count * S_THREADS * 8;
+            const int sets = plan.num_keys == 1 ? L + 2 : L;       // (Prog::SPECIALS)
+            size_t smem = (size_t)L * 8 + (size_t)(L + 2) * 8 + (size_t)sets * map.compact_count * S_THREADS * 8;
             if (smem + 2048 > (ctx->smem_optin > 0 ? ctx->smem_optin : 227 * 1024)) { *overflowed = true; return TGPU_OK; }   // too many live accumulators for path S
             TG_TRY(jit_launch(ctx, jit_fn, grid, S_THREADS, smem, params));
         }
