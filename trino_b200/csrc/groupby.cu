@@ -2044,8 +2044,9 @@ struct AggOp : tgpu_op {
         int L = s_L, A = plan.num_accs;
         // (the specialised kernel of a multi-key plan carries no accumulator sets for the special groups)
         const size_t jit_smem = jit_available() && plan.num_keys > 1 ? s_smem - 2 * s_per_slot : s_smem;
-        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (smem_limit() + 2048) / (jit_smem + 1024)));
-        if (const char* e = getenv("TGPU_AGG_S_MINB")) ctas_per_sm = std::max(1, std::min(ctas_per_sm, atoi(e)));
+        // at most 3 CTAs per SM: the fourth would cap the kernel at 64 registers (Q1: spills, 15.9 ms instead of 11.2 ms at SF300)
+        int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (smem_limit() + 2048) / (jit_smem + 1024)));
+        if (const char* e = getenv("TGPU_AGG_S_MINB")) ctas_per_sm = std::max(1, std::min(4, atoi(e)));
         int grid = tg_grid(ctx, n, S_THREADS * 4, ctas_per_sm);
         if (grid != s_grid) {
             TG_TRY(blk_keys.alloc(ctx, (size_t)grid * L * 8));
