@@ -34,7 +34,7 @@ ALG_BYTES_GROUPBY_BIGINT = 36       # 8 key + 8 value + 20 table
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r02_kernels.md),
 # quoted only for the configuration they were captured on
 NCU_TRAFFIC_PROBE_FUSED_SF100 = 8.429180e9 + 7.174483e9      # 600 000 003 rows: 26.0 B/row (join_probe_lean_kernel<2,1,8>, dense order-preserving table)
-NCU_TRAFFIC_Q1_SF300 = 68.402849e9 + 4.701952e6               # 1.8 G rows: 38.0 B/row (tg_agg_small_jit, four consecutive rows per thread)
+NCU_TRAFFIC_Q1_SF300 = 68.400325e9 + 4.218368e6               # 1.8 G rows: 38.0 B/row (tg_agg_small_jit, profiles/r02_kernels.md, capture r3k)
 
 
 def bind_to_gpu_numa_node(local):
