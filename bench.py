@@ -532,10 +532,14 @@ def main():
                 sms.append(t)
         sm = float(np.mean(sms))
         sa = ALG_BYTES_PROBE_FUSED * l_count / (sm * 1e-3) / 1e9
-        shuffled = {"kernel": "LookupJoinOperator step over shuffled probe keys", "bound": "hbm", "achieved": sa, "peak": peak, "unit": "GB/s", "frac": sa / peak,
+        shuffled = {"kernel": "LookupJoinOperator step over shuffled probe keys: join_probe_locality_kernel picks join_probe_wide_kernel (32-byte wide slots)",
+                    "bound": "hbm", "achieved": sa, "peak": peak, "unit": "GB/s", "frac": sa / peak,
                     "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "ms_per_step": sm, "rows_per_sec": l_count / (sm * 1e-3),
-                    "sector_floor_rows_per_sec": peak * 1e9 / (8 + 32 + 32 + 4 + 8),
-                    "note": "every probe row touches its own 32-byte table sector and its own 32-byte payload sector; sector_floor = peak / (8 key + 32 + 32 + 4 position + 8 payload written)"}
+                    "sector_floor_rows_per_sec": peak * 1e9 / (8 + 32 + 4 + 8),
+                    "random_sectors_per_sec": l_count / (sm * 1e-3),
+                    "note": "every probe row reads its own random 32-byte wide slot (key, head and the payload cell in one sector; the 16-byte slots + "
+                            "slot-ordered payload array of the key-ordered case cost two random sectors per row: 33 ms); sector_floor = copy peak / "
+                            "(8 key + 32 slot + 4 position + 8 payload written), which no random 32-byte access pattern reaches on HBM"}
         ctx.free(d_skeys)
 
     # ---------------- Q1 GROUP-BY side measurement (BASELINE.json configs[2]) on rank 0 at N=1

@@ -346,7 +346,7 @@ def test_build_side_key_domain(ctx):
     b.close()
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2", None, "span", "roomy"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", None, "span", "roomy", "narrow", "wide"])
 @pytest.mark.parametrize("shape", ["tpch", "every_8th", "clustered", "extremes", "shuffled_probe"])
 def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
     """Slot placement is not observable: mix(key) (mode 0, M/operator/join/PagesHash.java:35-51), line-local (1) and order-preserving
@@ -357,6 +357,10 @@ def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
         monkeypatch.setenv("TGPU_JOIN_SPAN", "1")          # the TMA-staged (cp.async.bulk + mbarrier) probe kernel
     elif mode == "roomy":
         monkeypatch.setenv("TGPU_JOIN_NO_DENSE", "1")      # skip the dense geometry attempt
+    elif mode == "narrow":
+        monkeypatch.setenv("TGPU_JOIN_NO_WIDE", "1")       # 16-byte slots + slot-ordered payload arrays, whatever the page's key locality
+    elif mode == "wide":
+        monkeypatch.setenv("TGPU_JOIN_WIDE", "always")     # 32-byte wide slots, whatever the page's key locality (default: sampled per page)
     elif mode is not None:
         monkeypatch.setenv("TGPU_JOIN_HASH", mode)
     rng = np.random.default_rng(11)
@@ -382,6 +386,30 @@ def test_table_layout_modes_agree_with_oracle(ctx, monkeypatch, mode, shape):
     # the operator (fused probe + payload gather, whole tiles + ragged tail) emits the oracle's rows
     got = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
     assert got == oracle_join_rows(build, probe, 0, 0, [0, 1], [1], abi.JOIN_INNER, False)
+
+
+@pytest.mark.parametrize("join_type", [abi.JOIN_INNER, abi.JOIN_PROBE_OUTER])
+@pytest.mark.parametrize("payload", ["bigint+double", "integer+smallint", "tinyint", "double+integer"])
+@pytest.mark.parametrize("variant", ["auto", "always", "always-45", "always-18"])
+def test_wide_slots_carry_every_payload_width(ctx, monkeypatch, join_type, payload, variant):
+    """The fused probe reads key, head and up to two build output cells from one 32-byte wide slot (join.cu WideSlot): 8 / 4 / 2 / 1-byte
+    payloads, misses (PROBE_OUTER emits NULLs, INNER drops the row), the INT64_MIN key beside the table, shuffled probe keys, whole tiles
+    and the ragged tail give the oracle's rows; so do the other rows-in-flight x CTAs-per-SM shapes of the kernel."""
+    if variant != "auto":           # auto: the probe page below has no key locality, so the sampler picks the wide slots as well
+        monkeypatch.setenv("TGPU_JOIN_WIDE", "always")
+    if "-" in variant:
+        monkeypatch.setenv("TGPU_JOIN_WIDE_SHAPE", variant.split("-")[1])
+    rng = np.random.default_rng(5)
+    okeys = np.concatenate([[-2**63], rng.permutation(np.arange(-3000, 60_000)) * 3]).astype(np.int64)
+    cols = {"bigint": Block.bigint(okeys * 7 - 1), "double": Block.double(okeys * 0.25), "integer": Block.integer((okeys % 100_003).astype(np.int32)),
+            "smallint": Block.smallint((okeys % 30_011).astype(np.int16)), "tinyint": Block.tinyint((okeys % 113).astype(np.int8))}
+    names = payload.split("+")
+    build = Page(Block.bigint(okeys), *[cols[n] for n in names])
+    lkeys = np.concatenate([rng.integers(-10_000, 190_000, 70_000), [-2**63, 2**63 - 1, -2**63]]).astype(np.int64)     # about two thirds miss
+    probe = Page(Block.bigint(lkeys), Block.double(lkeys * 0.5))
+    build_out = list(range(1, 1 + len(names)))
+    got = gpu_join_rows(ctx, [build], [probe], 0, 0, [0, 1], build_out, join_type, False)
+    assert got == oracle_join_rows(build, probe, 0, 0, [0, 1], build_out, join_type, False)
 
 
 def test_build_over_a_random_half_of_a_dense_domain_stays_fast(ctx):

@@ -473,6 +473,8 @@ template <int MODE, bool GATHER, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB) join_probe_lean_kernel(const long long* __restrict__ keys, int64_t tiles, const int4* __restrict__ table, unsigned int mask,
                                                               unsigned long long kmin, int shift, int special_head, int* __restrict__ out, GatherCols g, unsigned long long* __restrict__ match_count)
 {
+    // the word behind the match counter holds the layout choice of the page (0 = these 16-byte slots; join_probe_locality_kernel decides)
+    if (GATHER && *(const volatile int*)(match_count + 1) != 0) return;
     unsigned int matched = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int64_t base = t * 1024 + threadIdx.x;
@@ -725,6 +727,181 @@ static int launch_lean(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys
     return TGPU_OK;
 }
 
+// ---- wide slots: key, head and the build payload of the head row in ONE 32-byte sector ------------------------------------------
+// A probe page without key locality (the survey's variant B, or any join whose probe side is not clustered on the join key) pays one
+// random DRAM sector per array it touches for a row: the 16-byte slot, then one sector per slot-ordered payload column.  The wide table
+// holds the same slots at a 32-byte stride with up to two payload cells (8 bytes each) behind key and head, so that a row costs ONE
+// random sector whatever the number of payload columns - and one 256-bit load (LDG.E.256) instead of three dependent-address loads.
+// On a key-ordered probe page the bytes are the same as slot table + slot-ordered payload arrays, read front to back.
+// Built next to the 16-byte table (which the index-only probe, the duplicate chains and every generic kernel keep using).
+struct __align__(32) WideSlot {
+    unsigned long long key;
+    int head;
+    int pad;
+    unsigned long long cell[2];
+};
+
+__device__ __forceinline__ WideSlot wide_load(const WideSlot* p)
+{
+    WideSlot w;
+    unsigned long long kh;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w.key), "=l"(kh), "=l"(w.cell[0]), "=l"(w.cell[1]) : "l"(p));
+    w.head = (int)(unsigned int)kh;
+    w.pad = 0;
+    return w;
+}
+
+__device__ __forceinline__ unsigned long long wide_cell_of(const void* src, int elem, int row)
+{
+    switch (elem) {
+        case 8: return ((const unsigned long long*)src)[row];
+        case 4: return ((const unsigned int*)src)[row];
+        case 2: return ((const unsigned short*)src)[row];
+        default: return ((const unsigned char*)src)[row];
+    }
+}
+
+__global__ void join_wide_table_kernel(const JoinSlot* __restrict__ table, int64_t slots, int special_head, const void* __restrict__ src0, int elem0,
+                                       const void* __restrict__ src1, int elem1, WideSlot* __restrict__ wide)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i <= slots; i += stride) {
+        WideSlot w;
+        w.key = i < slots ? table[i].key : EMPTY_KEY;
+        w.head = i < slots ? table[i].head : special_head;
+        w.pad = 0;
+        w.cell[0] = w.head >= 0 && src0 ? wide_cell_of(src0, elem0, w.head) : 0ULL;
+        w.cell[1] = w.head >= 0 && src1 ? wide_cell_of(src1, elem1, w.head) : 0ULL;
+        wide[i] = w;
+    }
+}
+
+// same contract as join_probe_lean_kernel<MODE, true>: whole 1024-row tiles of a BIGINT key without NULLs; ROWS rows of a thread are in
+// flight together (a tile is 4 rows per thread, taken ROWS at a time)
+template <int MODE, int ROWS, int MINB>
+__global__ void __launch_bounds__(256, MINB) join_probe_wide_kernel(const long long* __restrict__ keys, int64_t tiles, const WideSlot* __restrict__ wide, unsigned int mask,
+                                                                  unsigned long long kmin, int shift, int special_head, int* __restrict__ out, GatherCols g,
+                                                                  unsigned long long* __restrict__ match_count, const int* __restrict__ layout_choice)
+{
+    if (layout_choice && *layout_choice == 0) return;      // the page goes through the 16-byte slots
+    unsigned int matched = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+#pragma unroll
+        for (int h = 0; h < 4; h += ROWS) {
+            const int64_t base = t * 1024 + h * 256 + threadIdx.x;
+            unsigned long long k[ROWS];
+            unsigned int pos[ROWS];
+            WideSlot w[ROWS];
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) k[j] = (unsigned long long)__ldg(keys + base + j * 256);
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) pos[j] = lean_slot<MODE>(k[j], mask, kmin, shift);
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) w[j] = wide_load(wide + pos[j]);
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) {
+                unsigned int p = pos[j];
+                int r = -1;
+                while (true) {
+                    if (w[j].key == k[j]) { r = w[j].head; break; }
+                    if (w[j].key == EMPTY_KEY) break;
+                    p = lean_next<MODE>(p, (unsigned int)k[j] & 7u, mask);
+                    w[j] = wide_load(wide + p);
+                }
+                if (k[j] == EMPTY_KEY) {                       // INT64_MIN lives outside the table, in the slot behind the last one
+                    r = special_head;
+                    if (r >= 0) w[j] = wide_load(wide + (mask + 1u));
+                }
+                if (r < 0) { w[j].cell[0] = 0ULL; w[j].cell[1] = 0ULL; }
+                w[j].head = r;
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if (c >= g.count) break;
+#pragma unroll
+                for (int j = 0; j < ROWS; j++) {
+                    const unsigned long long v = w[j].cell[c];
+                    switch (g.elem[c]) {
+                        case 8: ((unsigned long long*)g.dst[c])[base + j * 256] = v; break;
+                        case 4: ((unsigned int*)g.dst[c])[base + j * 256] = (unsigned int)v; break;
+                        case 2: ((unsigned short*)g.dst[c])[base + j * 256] = (unsigned short)v; break;
+                        default: ((unsigned char*)g.dst[c])[base + j * 256] = (unsigned char)v; break;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ROWS; j++) {
+                out[base + j * 256] = w[j].head;
+                matched += w[j].head >= 0;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) matched += __shfl_xor_sync(0xffffffffu, matched, off);
+    if ((threadIdx.x & 31) == 0 && matched) atomicAdd(match_count, (unsigned long long)matched);
+}
+
+// Which layout a probe page should read.  A wide slot is 32 bytes, a 16-byte slot plus its slot-ordered payload cells 16 + (payload bytes):
+// with one payload column a probe page that arrives in key order reads fewer bytes from the narrow layout (whole lines are used either
+// way), while a page without key locality pays a 32-byte sector per ARRAY it touches and is better off with the wide slot.  256 pairs of
+// neighbouring rows, spread over the page, vote: a pair is local when its two slots lie within 8 lines of each other.
+// choice: 0 = narrow, 1 = wide.  No host round trip: both probe kernels are launched and the one not chosen returns at once.
+template <int MODE>
+__global__ void __launch_bounds__(256) join_probe_locality_kernel(const long long* __restrict__ keys, int64_t tiles, unsigned int mask, unsigned long long kmin, int shift,
+                                                                  int* __restrict__ layout_choice)
+{
+    const int64_t at = (tiles * (int64_t)threadIdx.x / 256) * 1024 + (threadIdx.x & 31) * 32;
+    const unsigned int a = lean_slot<MODE>((unsigned long long)__ldg(keys + at), mask, kmin, shift);
+    const unsigned int b = lean_slot<MODE>((unsigned long long)__ldg(keys + at + 1), mask, kmin, shift);
+    const unsigned int d = a > b ? a - b : b - a;
+    const int local = __syncthreads_count(d <= 64u);
+    if (threadIdx.x == 0) *layout_choice = local * 2 >= 256 ? 0 : 1;
+}
+
+static int launch_locality(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys, int64_t tiles, int* layout_choice)
+{
+    const unsigned int mask32 = (unsigned int)geo.mask;
+    if (geo.mode == 2) TG_LAUNCH(ctx, join_probe_locality_kernel<2>, 1, 256, 0, keys, tiles, mask32, geo.kmin, geo.shift, layout_choice);
+    else if (geo.mode == 1) TG_LAUNCH(ctx, join_probe_locality_kernel<1>, 1, 256, 0, keys, tiles, mask32, 0ULL, 0, layout_choice);
+    else TG_LAUNCH(ctx, join_probe_locality_kernel<0>, 1, 256, 0, keys, tiles, mask32, 0ULL, 0, layout_choice);
+    return TGPU_OK;
+}
+
+template <int ROWS, int MINB>
+static int launch_wide_shape(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys, int64_t tiles, const WideSlot* wide, int special_head, int* out,
+                             const GatherCols& g, unsigned long long* matches, const int* layout_choice)
+{
+    const unsigned int mask32 = (unsigned int)geo.mask;
+    if (geo.mode == 2) {
+        auto k = join_probe_wide_kernel<2, ROWS, MINB>;
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, wide, mask32, geo.kmin, geo.shift, special_head, out, g, matches, layout_choice);
+    }
+    else if (geo.mode == 1) {
+        auto k = join_probe_wide_kernel<1, ROWS, MINB>;
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, wide, mask32, 0ULL, 0, special_head, out, g, matches, layout_choice);
+    }
+    else {
+        auto k = join_probe_wide_kernel<0, ROWS, MINB>;
+        TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, wide, mask32, 0ULL, 0, special_head, out, g, matches, layout_choice);
+    }
+    return TGPU_OK;
+}
+
+// rows in flight per thread x CTAs per SM; TGPU_JOIN_WIDE_SHAPE=<rows><ctas> picks one of the built shapes (sweeps)
+static int launch_wide(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys, int64_t tiles, const WideSlot* wide, int special_head, int* out, const GatherCols& g,
+                       unsigned long long* matches, const int* layout_choice)
+{
+    const char* e = getenv("TGPU_JOIN_WIDE_SHAPE");
+    int shape = e ? atoi(e) : 28;
+    switch (shape) {
+        case 18: return launch_wide_shape<1, 8>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
+        case 26: return launch_wide_shape<2, 6>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
+        case 45: return launch_wide_shape<4, 5>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
+        case 44: return launch_wide_shape<4, 4>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
+        default: return launch_wide_shape<2, 8>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
+    }
+}
+
 // build payload re-laid out in SLOT order (one pass at build time): the fused probe then reads the payload right next
 // to where it found the key instead of chasing the row id into the (arbitrarily ordered) build pages
 __global__ void join_payload_by_slot_kernel(const JoinSlot* __restrict__ table, int64_t slots, int special_head, const void* __restrict__ src, int elem,
@@ -849,6 +1026,7 @@ struct tgpu_lookup {
     DevPage store;                      // key column first, then build output columns
     int32_t num_output = 0;
     std::vector<DevBuf> by_slot;        // build output columns in table-slot order (fused probe fast path)
+    DevBuf wide;                        // WideSlot[capacity + 1]: slots with the payload of their head row (<= 2 build output columns)
     bool generic = false;               // keyed by row hash + verification against build_keys
     int attempts = 1;                   // generic only: hash functions the build needed (> 1 iff two keys shared a 64-bit hash)
     std::vector<DevColumn> build_keys;  // generic only: the real key columns of the build side
@@ -1262,6 +1440,13 @@ struct JoinBuildOp : tgpu_op {
                           c.elem_size(), lk->by_slot[b].p);
             }
         }
+        if (slot_payload && lk->num_output <= 2 && !lk->has_dups && !lk->generic && cap + 1 < (1LL << 31) && !getenv("TGPU_JOIN_NO_WIDE")) {
+            TG_TRY(lk->wide.alloc(ctx, (size_t)(cap + 1) * sizeof(WideSlot)));
+            const DevColumn& c0 = lk->store.cols[1];
+            const DevColumn* c1 = lk->num_output > 1 ? &lk->store.cols[2] : nullptr;
+            TG_LAUNCH(ctx, join_wide_table_kernel, tg_grid(ctx, cap + 1, 1024, 8), 256, 0, lk->table.as<JoinSlot>(), cap, lk->special_head, c0.data, c0.elem_size(),
+                      c1 ? c1->data : (const void*)nullptr, c1 ? c1->elem_size() : 0, lk->wide.as<WideSlot>());
+        }
         TG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         lookup = lk.release();
         finishing = true;
@@ -1342,9 +1527,9 @@ struct JoinProbeOp : tgpu_op {
             g.dst[b] = built[b].own_data->p;
         }
         g.by_slot = lookup->by_slot.empty() ? 0 : 1;
-        if (!match_counter.p) TG_TRY(match_counter.alloc(ctx, 8));
+        if (!match_counter.p) TG_TRY(match_counter.alloc(ctx, 16));       // [0] matches of the page, [1] (int) layout choice of the page
         unsigned long long* d_matches = match_counter.as<unsigned long long>();
-        TG_CUDA(ctx, cudaMemsetAsync(d_matches, 0, 8, ctx->stream));
+        TG_CUDA(ctx, cudaMemsetAsync(d_matches, 0, 16, ctx->stream));     // no matches yet; layout choice 0 = the 16-byte slots
         constexpr int ROWS = 4;
         int grid = tg_grid(ctx, n, 256 * ROWS, 8);
         auto k_fast = join_probe_gather_kernel<ROWS, true>;
@@ -1356,7 +1541,23 @@ struct JoinProbeOp : tgpu_op {
         if (fast && !getenv("TGPU_JOIN_GENERIC_KERNELS")) {
             int64_t tiles = n / 1024;
             if (tiles > 0) {
-                TG_TRY(launch_lean<true>(ctx, lookup->geo, (const long long*)key.data, tiles, (const int4*)table, lookup->special_head, jp->as<int>(), g, d_matches));
+                // TGPU_JOIN_WIDE = always | never | auto (default): auto lets the page's key locality decide whenever the wide layout is the
+                // bigger one (payload cells < 16 bytes); with 16 bytes of payload the two layouts hold the same bytes and wide always wins
+                const char* we = getenv("TGPU_JOIN_WIDE");
+                int payload_bytes = 0;
+                for (int c = 0; c < g.count; c++) payload_bytes += g.elem[c];
+                const bool have_wide = lookup->wide.p && !getenv("TGPU_JOIN_NO_WIDE") && !getenv("TGPU_JOIN_SPAN") && !(we && !strcmp(we, "never"));
+                const bool always = have_wide && ((we && !strcmp(we, "always")) || payload_bytes >= 16 || !g.by_slot);
+                if (always)
+                    TG_TRY(launch_wide(ctx, lookup->geo, (const long long*)key.data, tiles, lookup->wide.as<WideSlot>(), lookup->special_head, jp->as<int>(), g, d_matches, nullptr));
+                else if (have_wide) {
+                    int* d_choice = (int*)(d_matches + 1);
+                    TG_TRY(launch_locality(ctx, lookup->geo, (const long long*)key.data, tiles, d_choice));
+                    TG_TRY(launch_lean<true>(ctx, lookup->geo, (const long long*)key.data, tiles, (const int4*)table, lookup->special_head, jp->as<int>(), g, d_matches));
+                    TG_TRY(launch_wide(ctx, lookup->geo, (const long long*)key.data, tiles, lookup->wide.as<WideSlot>(), lookup->special_head, jp->as<int>(), g, d_matches, d_choice));
+                }
+                else
+                    TG_TRY(launch_lean<true>(ctx, lookup->geo, (const long long*)key.data, tiles, (const int4*)table, lookup->special_head, jp->as<int>(), g, d_matches));
                 done = tiles * 1024;
             }
         }
@@ -1787,6 +1988,7 @@ extern "C" int64_t tgpu_lookup_memory_bytes(const tgpu_lookup* lookup)
     if (!lookup) return 0;
     int64_t b = (int64_t)lookup->table.bytes + (int64_t)lookup->links.bytes + lookup->store.memory_bytes();
     for (auto& s : lookup->by_slot) b += (int64_t)s.bytes;
+    b += (int64_t)lookup->wide.bytes;
     return b;
 }
 
