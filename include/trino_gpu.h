@@ -406,13 +406,25 @@ int tgpu_lookup_copy_position_links(tgpu_ctx* ctx, const tgpu_lookup* lookup, in
  * M/operator/HashGenerator.java:25-46, M/operator/BucketPartitionFunction.java:45-64).
  * get_output returns one page per non-empty partition per input page; the partition id of the
  * page returned last is read with tgpu_partition_last_output_partition.                          */
+enum {
+    TGPU_PARTITION_HASH_BUCKET = 0, /* HashBucketFunction over HashGenerator.processRawHash (the inter-stage FIXED_HASH_DISTRIBUTION)   */
+    TGPU_PARTITION_LOCAL = 1        /* LocalPartitionGenerator (M/operator/exchange/LocalPartitionGenerator.java:45-77; built by
+                                       LocalExchange.java:252 and PartitionedLookupSource.java:103): (int) XxHash64.hash(Long.reverse(raw))
+                                       & (bucket_count - 1); bucket_count must be a power of two, bucket_to_partition must be NULL     */
+};
+
 typedef struct tgpu_partition_spec {
     int32_t num_key_channels;
-    const int32_t* key_channels;          /* partitionChannels (constants not supported: TGPU_ERR_NOT_SUPPORTED) */
-    int32_t bucket_count;                 /* HashBucketFunction bucketCount */
+    const int32_t* key_channels;          /* partitionChannels; an entry < 0 takes its value from key_constants */
+    int32_t bucket_count;                 /* HashBucketFunction bucketCount / LocalPartitionGenerator partitionCount */
     const int32_t* bucket_to_partition;   /* bucket_count entries, NULL = identity */
     int32_t null_channel;                 /* -1 or channel whose NULL rows are replicated to every partition */
     int32_t replicates_any_row;           /* replicatesAnyRow */
+    int32_t partition_function;           /* TGPU_PARTITION_* */
+    const tgpu_column* key_constants;     /* partitionConstants (PagePartitioner.java:78-101,436-451): NULL, or num_key_channels host columns
+                                             of which entry i is read when key_channels[i] < 0 - ONE position holding the constant (its
+                                             NullableValue; a NULL constant hashes to 0 like every NULL).  The reference wraps it in a
+                                             RunLengthEncodedBlock per page; here its type hash is taken once, at create time.          */
 } tgpu_partition_spec;
 
 int tgpu_partition_create(tgpu_ctx* ctx, const tgpu_partition_spec* spec, tgpu_op** out);

@@ -271,11 +271,16 @@ public final class GpuJoinOperatorFactories
         private final int[] bucketToPartition;
         private final int nullChannel;
         private final boolean replicatesAnyRow;
+        private final Page partitionConstants;           // null, or ONE position: block i = NullableValue.asBlock() of partition channel i (any block where it is a real channel)
+        private final int[] partitionConstantTypes;
         private final java.util.function.BiConsumer<Integer, Page> enqueue;      // OutputBuffer.enqueue(partition, serialized pages) of the task
 
         public GpuPartitionedOutputOperatorFactory(int operatorId, PlanNodeId planNodeId, int[] types, List<Integer> partitionChannels, int bucketCount,
-                int[] bucketToPartition, int nullChannel, boolean replicatesAnyRow, java.util.function.BiConsumer<Integer, Page> enqueue)
+                int[] bucketToPartition, int nullChannel, boolean replicatesAnyRow, Page partitionConstants, int[] partitionConstantTypes,
+                java.util.function.BiConsumer<Integer, Page> enqueue)
         {
+            this.partitionConstants = partitionConstants;
+            this.partitionConstantTypes = partitionConstantTypes;
             this.operatorId = operatorId;
             this.planNodeId = planNodeId;
             this.types = types.clone();
@@ -292,7 +297,17 @@ public final class GpuJoinOperatorFactories
         {
             OperatorContext operatorContext = driverContext.addOperatorContext(operatorId, planNodeId, "GpuPartitionedOutputOperator");
             GpuContexts.Handle gpu = GpuContexts.forCurrentDriver(driverContext);
-            MemorySegment op = NativeSpecs.createPartitioner(gpu, partitionChannels, bucketCount, bucketToPartition, nullChannel, replicatesAnyRow);
+            MemorySegment op;
+            try (Arena arena = Arena.ofConfined()) {
+                MemorySegment constants = MemorySegment.NULL;
+                if (partitionConstants != null) {
+                    io.trino.spi.block.PageMarshaller constantMarshaller = gpu.marshaller(partitionConstantTypes);
+                    constantMarshaller.append(partitionConstants);
+                    constants = constantMarshaller.flush(arena).get(java.lang.foreign.ValueLayout.ADDRESS, 16);      // tgpu_page.columns
+                }
+                op = NativeSpecs.createPartitioner(gpu, partitionChannels, bucketCount, bucketToPartition, nullChannel, replicatesAnyRow,
+                        NativeSpecs.PARTITION_HASH_BUCKET, constants);
+            }
             return new GpuOperator(operatorContext, gpu.context(), op, gpu.marshaller(types), types)
             {
                 @Override

@@ -41,9 +41,13 @@ public final class NativeSpecs
     // tgpu_join_probe_spec { int32 join_type; int32 output_single_match; int32 num_key_channels; int32* key_channels; int32 num_output_channels; int32* output_channels }
     static final StructLayout JOIN_PROBE_SPEC = MemoryLayout.structLayout(
             JAVA_INT, JAVA_INT, JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS);
-    // tgpu_partition_spec { int32 num_key_channels; int32* key_channels; int32 bucket_count; int32* bucket_to_partition; int32 null_channel; int32 replicates_any_row }
+    // tgpu_partition_spec { int32 num_key_channels; int32* key_channels; int32 bucket_count; int32* bucket_to_partition; int32 null_channel; int32 replicates_any_row;
+    //                       int32 partition_function; tgpu_column* key_constants }
     static final StructLayout PARTITION_SPEC = MemoryLayout.structLayout(
-            JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_INT, JAVA_INT);
+            JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS, JAVA_INT, JAVA_INT,
+            JAVA_INT, MemoryLayout.paddingLayout(4), ADDRESS);
+    public static final int PARTITION_HASH_BUCKET = 0;    // HashBucketFunction (M/sql/planner/HashBucketFunction.java:43-46)
+    public static final int PARTITION_LOCAL = 1;          // LocalPartitionGenerator (M/operator/exchange/LocalPartitionGenerator.java:45-77)
 
     static MemorySegment ints(Arena arena, List<Integer> values)
     {
@@ -165,8 +169,13 @@ public final class NativeSpecs
         }
     }
 
+    /**
+     * keyConstants: MemorySegment.NULL, or the tgpu_column array of a ONE-position page that holds, at index i, the partition constant of
+     * partition channel i when partitionChannels.get(i) is negative (PagePartitioner.java:78-101: NullableValue.asBlock()); the library reads
+     * it inside this call only.
+     */
     public static MemorySegment createPartitioner(GpuContexts.Handle gpu, List<Integer> partitionChannels, int bucketCount, int[] bucketToPartition, int nullChannel,
-            boolean replicatesAnyRow)
+            boolean replicatesAnyRow, int partitionFunction, MemorySegment keyConstants)
     {
         try (Arena arena = Arena.ofConfined()) {
             MemorySegment spec = arena.allocate(PARTITION_SPEC);
@@ -183,6 +192,8 @@ public final class NativeSpecs
             spec.set(ADDRESS, 24, b2p);
             spec.set(JAVA_INT, 32, nullChannel);
             spec.set(JAVA_INT, 36, replicatesAnyRow ? 1 : 0);
+            spec.set(JAVA_INT, 40, partitionFunction);
+            spec.set(ADDRESS, 48, keyConstants);
             return create(gpu, TrinoGpuLibrary.PARTITION_CREATE, spec, arena);
         }
         catch (RuntimeException e) {

@@ -230,6 +230,12 @@ def partition_ids(page, key_channels, bucket_count, bucket_to_partition=None):
     return out
 
 
+def local_partition_ids(page, hash_channels, partition_count):
+    """LocalPartitionGenerator.getPartitions (M/operator/exchange/LocalPartitionGenerator.java:53-66)"""
+    lib = load()
+    return np.array([lib.orc_local_partition(int(h), partition_count) for h in row_hashes(page, hash_channels)], dtype=np.int32)
+
+
 def partition_positions(page, key_channels, bucket_count, bucket_to_partition, partition_count, null_channel, replicates_any_row, any_row_replicated):
     """returns (list of position arrays per partition, new any_row_replicated)"""
     ap = AbiPage(page)

@@ -5,7 +5,7 @@ import pytest
 import oracle_lib as o
 from trino_b200 import abi
 from trino_b200 import operators as ops
-from trino_b200.page import Block, DictionaryBlock, Page
+from trino_b200.page import Block, DictionaryBlock, Page, RunLengthEncodedBlock
 
 pytestmark = pytest.mark.gpu
 
@@ -67,6 +67,56 @@ def test_single_partition_and_dictionary_keys(ctx):
     want, _ = oracle_partition(d, [0], 4, None, 4, -1, False, False)
     assert gpu_partition(ctx, op, d) == want
     op.close()
+
+
+def test_partition_constants(ctx):
+    """A negative partition channel takes its value from partitionConstants: the reference hashes a RunLengthEncodedBlock of the constant
+    in that position of the function page (M/operator/output/PagePartitioner.java:436-451; TestPagePartitioner.java:309-379 runs the shape
+    with a test function) - so does the oracle here; the library takes the constant's type hash once."""
+    rng = np.random.default_rng(12)
+    n = 9000
+    page = Page(Block.bigint(rng.integers(-10**9, 10**9, n), rng.random(n) < 0.1), Block.double(rng.normal(size=n)))
+    constants = {"bigint": Block.bigint([1]), "null": Block.bigint([7], [True]), "double": Block.double([-0.0]), "varchar": Block.varchar(["x-ray"]),
+                 "integer": Block.integer(np.array([-5], dtype=np.int32)), "decimal": Block.int128([-(10**30)])}
+    for name, const in constants.items():
+        for channels, consts in (([-1], [const]), ([0, -1], [None, const]), ([-1, 0, 1], [const, None, None])):
+            function_page = Page(*[RunLengthEncodedBlock(consts[i], n) if ch < 0 else page.get_block(ch) for i, ch in enumerate(channels)])
+            for buckets in (2, 8, 37):
+                want = o.partition_ids(function_page, list(range(len(channels))), buckets)
+                op = ops.PartitionedOutputOperatorFactory(ctx, channels, buckets, partition_constants=consts).create_operator()
+                assert (op.get_partitions(page) == want).all(), (name, channels, buckets)
+                if len(channels) == 1:
+                    assert len(set(want.tolist())) == 1          # a lone constant sends every row to one partition (:315-330)
+                # the partitioned pages follow the same ids (rows and their order per partition)
+                got = gpu_partition(ctx, op, page)
+                rows = page.rows()
+                assert got == {p: [rows[i] for i in np.flatnonzero(want == p)] for p in sorted(set(want.tolist()))}, (name, channels, buckets)
+                op.close()
+    with pytest.raises(Exception):      # a constant channel without constants (PagePartitioner.java:111 checkArgument)
+        ops.PartitionedOutputOperatorFactory(ctx, [-1], 4).create_operator()
+
+
+@pytest.mark.parametrize("P", [1, 2, 8, 64])
+def test_local_partition_generator(ctx, P):
+    """LocalPartitionGenerator (M/operator/exchange/LocalPartitionGenerator.java:45-77): (int) XxHash64.hash(Long.reverse(rawHash)) & (P - 1)
+    over the row hash of the hash channels - ids, and the pages a PartitioningExchanger-style split makes of them."""
+    rng = np.random.default_rng(13)
+    n = 30000
+    page = Page(Block.bigint(rng.integers(-10**12, 10**12, n), rng.random(n) < 0.05), Block.double(rng.normal(size=n)), Block.integer(rng.integers(-99, 99, n)),
+                Block.varchar(["k%d" % (i % 97) if i % 13 else None for i in range(n)]))
+    for channels in ([0], [1], [3], [0, 2, 3]):
+        gen = ops.LocalPartitionGenerator(ctx, channels, P)
+        want = o.local_partition_ids(page, channels, P)
+        assert (gen.get_partitions(page) == want).all(), channels
+        gen.close()
+    op = ops.PartitionedOutputOperatorFactory(ctx, [0], P, partition_function=abi.PARTITION_LOCAL).create_operator()
+    fixed = Page(page.get_block(0), page.get_block(1))          # fixed-width: the multi-split path recomputes the id from the key
+    want = o.local_partition_ids(fixed, [0], P)
+    rows = fixed.rows()
+    assert gpu_partition(ctx, op, fixed) == {p: [rows[i] for i in np.flatnonzero(want == p)] for p in sorted(set(want.tolist()))}
+    op.close()
+    with pytest.raises(ValueError):
+        ops.LocalPartitionGenerator(ctx, [0], 6)
 
 
 @pytest.mark.parametrize("P", [2, 8, 37, 64, 100])

@@ -21,7 +21,7 @@ for (fn, reg, stack, sh), nm in zip(rows, names):
     out.append((nm, reg, stack, sh))
 print("# r02 — static resource usage (`cuobjdump -res-usage trino_b200/libtrino_gpu.so`, sm_100a, nvcc 12.9 -O3 -fmad=false)\n")
 print("Registers, local stack and static shared memory per kernel, and how many 256-thread CTAs the register file (64 K x 32-bit per SM) admits.  "
-      "NVRTC kernels (`tg_agg_small_jit`: 76 registers + 73.8 KB dynamic smem for the Q1 program; `tg_agg_general_jit`: `__launch_bounds__(256, 3)`; "
+      "NVRTC kernels (`tg_agg_small_jit`: 76 registers + 49.2 KB dynamic smem for the Q1 program; `tg_agg_general_jit`: `__launch_bounds__(256, 4)`; "
       "`tg_fp_*_jit`: 19 / 32 registers) are compiled at run time and appear in `r02_kernels.md` instead.\n")
 print("| kernel | registers | stack B | static smem B | max CTAs/SM by registers (256 thr) |\n|---|---:|---:|---:|---:|")
 seen = set()

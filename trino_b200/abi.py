@@ -17,6 +17,7 @@ ERR_DIVISION_BY_ZERO, ERR_NOT_SUPPORTED, ERR_ILLEGAL_STATE = -5, -6, -7
 
 INT64, INT32, INT16, INT8, FLOAT64, UTF8, DICT32, RLE, INT128 = 1, 2, 3, 4, 5, 7, 8, 9, 10
 COL_NULLS_BYTEMAP = 1
+PARTITION_HASH_BUCKET, PARTITION_LOCAL = 0, 1
 PAGE_DEVICE = 1
 
 EX_MOV, EX_ADD, EX_SUB, EX_MUL, EX_DIV, EX_MOD, EX_NEG = 0, 1, 2, 3, 4, 5, 6
@@ -144,6 +145,8 @@ class PartitionSpec(C.Structure):
         ("bucket_to_partition", C.POINTER(C.c_int32)),
         ("null_channel", C.c_int32),
         ("replicates_any_row", C.c_int32),
+        ("partition_function", C.c_int32),
+        ("key_constants", C.c_void_p),
     ]
 
 

@@ -41,9 +41,30 @@ TG_HD uint64_t murmur3_mix(uint64_t x)
 // CombineHashFunction.getHash (M/operator/scalar/CombineHashFunction.java:29-32)
 TG_HD uint64_t combine_hash(uint64_t prev, uint64_t v) { return 31 * prev + v; }
 
-// HashGenerator.processRawHash (M/operator/HashGenerator.java:41-46)
+TG_HD uint64_t xxh64_long(int64_t v);
+
+TG_HD uint64_t reverse_bits64(uint64_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    x = ((x >> 8) & 0x00FF00FF00FF00FFULL) | ((x & 0x00FF00FF00FF00FFULL) << 8);
+    x = ((x >> 16) & 0x0000FFFF0000FFFFULL) | ((x & 0x0000FFFF0000FFFFULL) << 16);
+    return (x >> 32) | (x << 32);
+#endif
+}
+
+// Partition of a raw row hash.
+//   count > 0: HashGenerator.processRawHash (M/operator/HashGenerator.java:41-46) - the bucket of the inter-stage hash distribution.
+//   count < 0: LocalPartitionGenerator.getPartition (M/operator/exchange/LocalPartitionGenerator.java:45-77) over -count partitions
+//              (a power of two): (int) XxHash64.hash(Long.reverse(rawHash)) & (partitionCount - 1) - the local exchange re-mixes the
+//              bits so that it does not reuse the hash the stages were distributed by.
 TG_HD int32_t process_raw_hash(uint64_t raw, int32_t count)
 {
+    if (count < 0) return (int32_t)(uint32_t)xxh64_long((int64_t)reverse_bits64(raw)) & (-count - 1);
     uint32_t x = (uint32_t)(raw ^ (raw >> 32));
     return (int32_t)(((uint64_t)x * (uint64_t)(uint32_t)count) >> 32);
 }

@@ -107,8 +107,33 @@ __global__ void shift_rows_kernel(const int32_t* __restrict__ in, int64_t n, int
 }
 
 
+// type hash of the single position of a HOST column (the value of a partition constant); same functions as the device's type_hash
+int host_type_hash(tgpu_ctx* ctx, const tgpu_column& c, uint64_t* out)
+{
+    if (c.length != 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a partition constant holds one position, not %lld", (long long)c.length);
+    if (c.validity) {
+        bool is_null = (c.flags & TGPU_COL_NULLS_BYTEMAP) ? c.validity[0] != 0 : (c.validity[0] & 1) == 0;
+        if (is_null) { *out = 0; return TGPU_OK; }
+    }
+    if (!c.data && c.type != TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition constant without a value");
+    switch (c.type) {
+        case TGPU_INT64: *out = hash_long(*(const int64_t*)c.data); return TGPU_OK;
+        case TGPU_INT32: *out = hash_long(*(const int32_t*)c.data); return TGPU_OK;
+        case TGPU_INT16: *out = hash_long(*(const int16_t*)c.data); return TGPU_OK;
+        case TGPU_INT8: *out = hash_long(*(const int8_t*)c.data); return TGPU_OK;
+        case TGPU_FLOAT64: *out = hash_double_bits(*(const int64_t*)c.data); return TGPU_OK;
+        case TGPU_INT128: *out = hash_int128(((const int64_t*)c.data)[0], ((const int64_t*)c.data)[1]); return TGPU_OK;
+        case TGPU_UTF8:
+            if (!c.offsets) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "variable-width partition constant without offsets");
+            *out = xxh64_bytes((const uint8_t*)c.data + c.offsets[0], c.offsets[1] - c.offsets[0]);
+            return TGPU_OK;
+        default: return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "partition constant of type %d", c.type);
+    }
+}
+
 struct PartitionOp : tgpu_op {
     std::vector<int32_t> key_channels;
+    std::vector<uint64_t> constant_hash;    // per partition channel; read where key_channels[c] < 0
     int32_t bucket_count = 1, partition_count = 1;
     std::vector<int32_t> bucket_to_partition;
     DevBuf d_b2p;
@@ -131,7 +156,8 @@ struct PartitionOp : tgpu_op {
         k->count = (int32_t)key_channels.size();
         for (int c = 0; c < k->count; c++) {
             int ch = key_channels[c];
-            if (ch < 0 || ch >= (int)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition channel %d out of range", ch);
+            if (ch < 0) { k->is_const[c] = 1; k->const_hash[c] = constant_hash[c]; continue; }
+            if (ch >= (int)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition channel %d out of range", ch);
             key_cols_set(k, c, in.cols[ch]);
         }
         return TGPU_OK;
@@ -485,8 +511,21 @@ extern "C" int tgpu_partition_create(tgpu_ctx* ctx, const tgpu_partition_spec* s
     if (spec->bucket_count < 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partitionCount must be at least 1");   // HashBucketFunction.java:30
     std::unique_ptr<PartitionOp> op(new PartitionOp(ctx));
     op->key_channels.assign(spec->key_channels, spec->key_channels + spec->num_key_channels);
+    op->constant_hash.assign((size_t)spec->num_key_channels, 0);
+    for (int32_t c = 0; c < spec->num_key_channels; c++) {
+        if (spec->key_channels[c] >= 0) continue;
+        if (!spec->key_constants) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partition channel %d is a constant but key_constants is NULL", c);   // PagePartitioner.java:111
+        TG_TRY(host_type_hash(ctx, spec->key_constants[c], &op->constant_hash[c]));
+    }
     op->bucket_count = spec->bucket_count;
     op->partition_count = spec->bucket_count;
+    if (spec->partition_function == TGPU_PARTITION_LOCAL) {
+        if (spec->bucket_count & (spec->bucket_count - 1)) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "partitionCount must be a power of 2");   // LocalPartitionGenerator.java:33
+        if (spec->bucket_to_partition) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "the local partition function has no bucket-to-partition map");
+        op->bucket_count = -spec->bucket_count;      // process_raw_hash (hash.cuh) reads a negative count as the local function
+    }
+    else if (spec->partition_function != TGPU_PARTITION_HASH_BUCKET)
+        return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "unknown partition function %d", spec->partition_function);
     if (spec->bucket_to_partition) {
         op->bucket_to_partition.assign(spec->bucket_to_partition, spec->bucket_to_partition + spec->bucket_count);
         int mx = 0;

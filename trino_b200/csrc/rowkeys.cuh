@@ -15,6 +15,8 @@ struct KeyCols {
     const int32_t* offsets[MAX_KEY_COLS];   // UTF8 only
     int32_t is_utf8[MAX_KEY_COLS];
     int32_t is_double[MAX_KEY_COLS];
+    int32_t is_const[MAX_KEY_COLS];         // partitionConstants (M/operator/output/PagePartitioner.java:436-451): no column, one hash for every row
+    uint64_t const_hash[MAX_KEY_COLS];
 };
 
 static inline void key_cols_set(KeyCols* k, int c, const DevColumn& col)
@@ -28,6 +30,7 @@ static inline void key_cols_set(KeyCols* k, int c, const DevColumn& col)
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint64_t type_hash(const KeyCols& k, int c, int64_t row)
 {
+    if (k.is_const[c]) return k.const_hash[c];
     const ColRef& col = k.cols[c];
     if (!tg_valid(col.validity, row)) return 0;   // NULL_HASH_CODE (S/type/TypeUtils.java:34)
     if (k.is_utf8[c]) {

@@ -854,23 +854,51 @@ class PartitionedOutputOperator(Operator):
 
 
 class PartitionedOutputOperatorFactory(OperatorFactory):
-    def __init__(self, ctx, partition_channels, bucket_count, bucket_to_partition=None, null_channel=-1, replicates_any_row=False):
+    """PartitionedOutputFactory.createOutputOperator (M/operator/output/PartitionedOutputOperator.java:69-118).
+    `partition_constants`: one entry per partition channel, None or a one-position Block - read where the channel is negative
+    (PagePartitioner.java:78-101).  `partition_function`: abi.PARTITION_HASH_BUCKET, or abi.PARTITION_LOCAL for the
+    LocalPartitionGenerator of the local exchange (M/operator/exchange/LocalPartitionGenerator.java:45-77)."""
+
+    def __init__(self, ctx, partition_channels, bucket_count, bucket_to_partition=None, null_channel=-1, replicates_any_row=False,
+                 partition_constants=None, partition_function=abi.PARTITION_HASH_BUCKET):
         super().__init__()
         self.ctx, self.partition_channels, self.bucket_count = ctx, list(partition_channels), bucket_count
         self.bucket_to_partition, self.null_channel, self.replicates_any_row = bucket_to_partition, null_channel, replicates_any_row
+        self.partition_constants, self.partition_function = partition_constants, partition_function
 
     def _create(self):
         kc = _i32(self.partition_channels)
         b2p = _i32(list(self.bucket_to_partition)) if self.bucket_to_partition is not None else None
+        constants = None
+        if self.partition_constants is not None:
+            blocks = [b if b is not None else Block.bigint(np.zeros(1, dtype=np.int64)) for b in self.partition_constants]
+            constants = AbiPage(Page(*blocks))      # alive until the create call returns: the library keeps only the hashes
         spec = abi.PartitionSpec(len(self.partition_channels), C.cast(kc, C.POINTER(C.c_int32)), self.bucket_count,
-                                 C.cast(b2p, C.POINTER(C.c_int32)) if b2p is not None else None, self.null_channel, int(self.replicates_any_row))
+                                 C.cast(b2p, C.POINTER(C.c_int32)) if b2p is not None else None, self.null_channel, int(self.replicates_any_row),
+                                 self.partition_function, C.cast(constants.columns, C.c_void_p) if constants is not None else None)
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.tgpu_partition_create(self.ctx.h, C.byref(spec), C.byref(h)))
         return PartitionedOutputOperator(self.ctx, h)
 
     def duplicate(self):
         return PartitionedOutputOperatorFactory(self.ctx, self.partition_channels, self.bucket_count, self.bucket_to_partition, self.null_channel,
-                                                self.replicates_any_row)
+                                                self.replicates_any_row, self.partition_constants, self.partition_function)
+
+
+class LocalPartitionGenerator:
+    """M/operator/exchange/LocalPartitionGenerator.java:23-77 over the library's partitioner: getPartitions of a page's hash channels."""
+
+    def __init__(self, ctx, hash_channels, partition_count):
+        if partition_count < 1 or partition_count & (partition_count - 1):
+            raise ValueError("partitionCount must be a power of 2")                 # LocalPartitionGenerator.java:33
+        self.partition_count = partition_count
+        self._op = PartitionedOutputOperatorFactory(ctx, hash_channels, partition_count, partition_function=abi.PARTITION_LOCAL).create_operator()
+
+    def get_partitions(self, page):
+        return self._op.get_partitions(page)
+
+    def close(self):
+        self._op.close()
 
 
 def drive(operator, pages):
