@@ -536,10 +536,13 @@ def main():
                     "bound": "hbm", "achieved": sa, "peak": peak, "unit": "GB/s", "frac": sa / peak,
                     "algorithmic_bytes_per_row": ALG_BYTES_PROBE_FUSED, "ms_per_step": sm, "rows_per_sec": l_count / (sm * 1e-3),
                     "sector_floor_rows_per_sec": peak * 1e9 / (8 + 32 + 4 + 8),
-                    "random_sectors_per_sec": l_count / (sm * 1e-3),
+                    "line_floor_rows_per_sec": peak * 1e9 / (8 + 128 + 4 + 8),
+                    "frac_of_line_floor": (l_count / (sm * 1e-3)) / (peak * 1e9 / (8 + 128 + 4 + 8)),
                     "note": "every probe row reads its own random 32-byte wide slot (key, head and the payload cell in one sector; the 16-byte slots + "
-                            "slot-ordered payload array of the key-ordered case cost two random sectors per row: 33 ms); sector_floor = copy peak / "
-                            "(8 key + 32 slot + 4 position + 8 payload written), which no random 32-byte access pattern reaches on HBM"}
+                            "slot-ordered payload array of the key-ordered case cost two random accesses per row: 33 ms).  ncu (profiles/r02_kernels.md): the "
+                            "L2 fills a whole 128-byte line from HBM for every random sector (134 DRAM bytes per row, whatever cudaLimitMaxL2FetchGranularity "
+                            "or the load's L2 fetch-size qualifier say), so the floor of this access pattern is line_floor = copy peak / (8 key + 128 line + "
+                            "4 position + 8 payload written), not sector_floor"}
         ctx.free(d_skeys)
 
     # ---------------- Q1 GROUP-BY side measurement (BASELINE.json configs[2]) on rank 0 at N=1

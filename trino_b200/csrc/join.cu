@@ -741,11 +741,18 @@ struct __align__(32) WideSlot {
     unsigned long long cell[2];
 };
 
+// LD: 0 = one 256-bit read-only load; 3 = the same with an explicit 64-byte L2 fetch size (LDG...LTC64B); 5 = two 128-bit loads
+template <int LD>
 __device__ __forceinline__ WideSlot wide_load(const WideSlot* p)
 {
     WideSlot w;
     unsigned long long kh;
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w.key), "=l"(kh), "=l"(w.cell[0]), "=l"(w.cell[1]) : "l"(p));
+    if (LD == 3) asm("ld.global.nc.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w.key), "=l"(kh), "=l"(w.cell[0]), "=l"(w.cell[1]) : "l"(p));
+    else if (LD == 5) {
+        asm("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(w.key), "=l"(kh) : "l"(p));
+        asm("ld.global.nc.v2.u64 {%0,%1}, [%2+16];" : "=l"(w.cell[0]), "=l"(w.cell[1]) : "l"(p));
+    }
+    else asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(w.key), "=l"(kh), "=l"(w.cell[0]), "=l"(w.cell[1]) : "l"(p));
     w.head = (int)(unsigned int)kh;
     w.pad = 0;
     return w;
@@ -779,7 +786,7 @@ __global__ void join_wide_table_kernel(const JoinSlot* __restrict__ table, int64
 
 // same contract as join_probe_lean_kernel<MODE, true>: whole 1024-row tiles of a BIGINT key without NULLs; ROWS rows of a thread are in
 // flight together (a tile is 4 rows per thread, taken ROWS at a time)
-template <int MODE, int ROWS, int MINB>
+template <int MODE, int ROWS, int MINB, int LD = 0>
 __global__ void __launch_bounds__(256, MINB) join_probe_wide_kernel(const long long* __restrict__ keys, int64_t tiles, const WideSlot* __restrict__ wide, unsigned int mask,
                                                                   unsigned long long kmin, int shift, int special_head, int* __restrict__ out, GatherCols g,
                                                                   unsigned long long* __restrict__ match_count, const int* __restrict__ layout_choice)
@@ -798,7 +805,7 @@ __global__ void __launch_bounds__(256, MINB) join_probe_wide_kernel(const long l
 #pragma unroll
             for (int j = 0; j < ROWS; j++) pos[j] = lean_slot<MODE>(k[j], mask, kmin, shift);
 #pragma unroll
-            for (int j = 0; j < ROWS; j++) w[j] = wide_load(wide + pos[j]);
+            for (int j = 0; j < ROWS; j++) w[j] = wide_load<LD>(wide + pos[j]);
 #pragma unroll
             for (int j = 0; j < ROWS; j++) {
                 unsigned int p = pos[j];
@@ -807,11 +814,11 @@ __global__ void __launch_bounds__(256, MINB) join_probe_wide_kernel(const long l
                     if (w[j].key == k[j]) { r = w[j].head; break; }
                     if (w[j].key == EMPTY_KEY) break;
                     p = lean_next<MODE>(p, (unsigned int)k[j] & 7u, mask);
-                    w[j] = wide_load(wide + p);
+                    w[j] = wide_load<LD>(wide + p);
                 }
                 if (k[j] == EMPTY_KEY) {                       // INT64_MIN lives outside the table, in the slot behind the last one
                     r = special_head;
-                    if (r >= 0) w[j] = wide_load(wide + (mask + 1u));
+                    if (r >= 0) w[j] = wide_load<LD>(wide + (mask + 1u));
                 }
                 if (r < 0) { w[j].cell[0] = 0ULL; w[j].cell[1] = 0ULL; }
                 w[j].head = r;
@@ -867,21 +874,21 @@ static int launch_locality(tgpu_ctx* ctx, const JoinGeom& geo, const long long* 
     return TGPU_OK;
 }
 
-template <int ROWS, int MINB>
+template <int ROWS, int MINB, int LD = 0>
 static int launch_wide_shape(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys, int64_t tiles, const WideSlot* wide, int special_head, int* out,
                              const GatherCols& g, unsigned long long* matches, const int* layout_choice)
 {
     const unsigned int mask32 = (unsigned int)geo.mask;
     if (geo.mode == 2) {
-        auto k = join_probe_wide_kernel<2, ROWS, MINB>;
+        auto k = join_probe_wide_kernel<2, ROWS, MINB, LD>;
         TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, wide, mask32, geo.kmin, geo.shift, special_head, out, g, matches, layout_choice);
     }
     else if (geo.mode == 1) {
-        auto k = join_probe_wide_kernel<1, ROWS, MINB>;
+        auto k = join_probe_wide_kernel<1, ROWS, MINB, LD>;
         TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, wide, mask32, 0ULL, 0, special_head, out, g, matches, layout_choice);
     }
     else {
-        auto k = join_probe_wide_kernel<0, ROWS, MINB>;
+        auto k = join_probe_wide_kernel<0, ROWS, MINB, LD>;
         TG_LAUNCH(ctx, k, lean_grid(ctx, k, tiles), 256, 0, keys, tiles, wide, mask32, 0ULL, 0, special_head, out, g, matches, layout_choice);
     }
     return TGPU_OK;
@@ -893,6 +900,10 @@ static int launch_wide(tgpu_ctx* ctx, const JoinGeom& geo, const long long* keys
 {
     const char* e = getenv("TGPU_JOIN_WIDE_SHAPE");
     int shape = e ? atoi(e) : 28;
+    const char* le = getenv("TGPU_JOIN_WIDE_LOAD");
+    int ld = le ? atoi(le) : 3;       // measured on the shuffled SF100 probe: 0 -> 17.87 ms, 3 -> 17.37 ms, 5 -> 19.5 ms
+    if (shape == 28 && ld == 3) return launch_wide_shape<2, 8, 3>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
+    if (shape == 28 && ld == 5) return launch_wide_shape<2, 8, 5>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
     switch (shape) {
         case 18: return launch_wide_shape<1, 8>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
         case 26: return launch_wide_shape<2, 6>(ctx, geo, keys, tiles, wide, special_head, out, g, matches, layout_choice);
