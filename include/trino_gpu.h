@@ -61,10 +61,15 @@ typedef enum tgpu_type {
     TGPU_UTF8 = 7,     /* VARCHAR / CHAR / VARBINARY: int32 offsets[length+1] + bytes          */
     TGPU_DICT32 = 8,   /* DictionaryBlock: data = int32 ids[length], dictionary = value column */
     TGPU_RLE = 9,      /* RunLengthEncodedBlock: dictionary = 1-row value column, broadcast    */
-    TGPU_INT128 = 10   /* long DECIMAL(p > 18): Int128ArrayBlock's long[] - 16 bytes per position, the HIGH (signed) word first, then the
+    TGPU_INT128 = 10,  /* long DECIMAL(p > 18): Int128ArrayBlock's long[] - 16 bytes per position, the HIGH (signed) word first, then the
                           LOW word (S/block/Int128ArrayBlock.java:123-133).  Moves through every operator; hashes and compares as
                           LongDecimalType does (S/type/LongDecimalType.java:203-247); group-by / join / partition key; sum() input and
                           output (DecimalSumAggregation).  The expression evaluator does not compute on it.                          */
+    TGPU_FLOAT32 = 11  /* REAL: the float's raw IEEE bits in an IntArrayBlock (S/type/RealType.java:104-121).  Moves through every
+                          operator; partition / join / group-by key with RealType's operators (hash :151-159 over floatToIntBits with
+                          -0.0 collapsed; EQUAL :145-149 - NaN matches nothing; IDENTICAL :172-185 - NaN is identical to NaN).  Join and
+                          group-by widen the key to its (exact) double internally.  Aggregates and expressions over REAL, REAL
+                          semi-join keys and REAL dynamic-filter domains answer TGPU_ERR_NOT_SUPPORTED.                              */
 } tgpu_type;
 
 enum {

@@ -46,6 +46,8 @@ public final class PageMarshaller
     public static final int UTF8 = 7;
     public static final int DICT32 = 8;
     public static final int RLE = 9;
+    public static final int INT128 = 10;      // long DECIMAL: Int128ArrayBlock, the high word first (Int128ArrayBlock.java:123-133)
+    public static final int FLOAT32 = 11;     // REAL: IntArrayBlock of raw float bits (RealType.java:104-121)
     public static final int COL_NULLS_BYTEMAP = 1;
     public static final int PAGE_DEVICE = 1;
 
@@ -324,7 +326,7 @@ public final class PageMarshaller
             }
         }
         else {
-            int width = type == INT64 || type == FLOAT64 ? 8 : type == INT32 ? 4 : type == INT16 ? 2 : 1;
+            int width = type == INT128 ? 16 : type == INT64 || type == FLOAT64 ? 8 : type == INT32 || type == FLOAT32 ? 4 : type == INT16 ? 2 : 1;
             data = reserve((long) width * batchRows);
             long row = 0;
             for (Page page : batch) {
@@ -346,6 +348,10 @@ public final class PageMarshaller
                     case ByteArrayBlock bytes -> {
                         MemorySegment.copy(bytes.getRawValues(), bytes.getRawValuesOffset(), data, JAVA_BYTE, row, count);
                         copyNulls(bytes.getRawValueIsNull(), bytes.getRawValuesOffset(), count, nulls, row);
+                    }
+                    case Int128ArrayBlock wide -> {
+                        MemorySegment.copy(wide.getRawValues(), 2 * wide.getRawOffset(), data, JAVA_LONG, row * 16, 2 * count);
+                        copyNulls(wide.getRawValueIsNull(), wide.getRawOffset(), count, nulls, row);
                     }
                     default -> throw new IllegalArgumentException("block type without a GPU mapping: " + block.getClass().getSimpleName());
                 }
@@ -408,7 +414,7 @@ public final class PageMarshaller
             MemorySegment column = columns.asSlice(channel * COLUMN.byteSize(), COLUMN.byteSize());
             int type = shape.types()[channel];
             boolean skip = passthroughChannel[channel] >= 0;
-            int width = type == INT64 || type == FLOAT64 ? 8 : type == INT32 ? 4 : type == INT16 ? 2 : 1;
+            int width = type == INT128 ? 16 : type == INT64 || type == FLOAT64 ? 8 : type == INT32 || type == FLOAT32 ? 4 : type == INT16 ? 2 : 1;
             column.set(JAVA_INT, 0, type);
             column.set(JAVA_INT, 4, 0);
             column.set(JAVA_LONG, 8, shape.rows());
@@ -465,7 +471,7 @@ public final class PageMarshaller
                 MemorySegment.copy(data.reinterpret((first + count) * 8), JAVA_LONG, first * 8, values, 0, count);
                 return new LongArrayBlock(count, nulls, values);
             }
-            case INT32 -> {
+            case INT32, FLOAT32 -> {
                 int[] values = new int[count];
                 MemorySegment.copy(data.reinterpret((first + count) * 4), JAVA_INT, first * 4, values, 0, count);
                 return new IntArrayBlock(count, nulls, values);
@@ -479,6 +485,11 @@ public final class PageMarshaller
                 byte[] values = new byte[count];
                 MemorySegment.copy(data.reinterpret(first + count), JAVA_BYTE, first, values, 0, count);
                 return new ByteArrayBlock(count, nulls, values);
+            }
+            case INT128 -> {
+                long[] values = new long[2 * count];
+                MemorySegment.copy(data.reinterpret((first + count) * 16), JAVA_LONG, first * 16, values, 0, 2 * count);
+                return new Int128ArrayBlock(count, nulls, values);
             }
             case UTF8 -> {
                 MemorySegment offsets = column.get(ADDRESS, 24).reinterpret((first + count + 1) * 4);

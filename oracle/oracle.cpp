@@ -49,6 +49,17 @@ inline uint64_t hash_double(double d)
     return hash_long(double_to_long_bits(d));
 }
 
+// S/type/RealType.java:151-159: AbstractLongType.hash(floatToIntBits(v)) with -0.0 collapsed to +0.0; Float.floatToIntBits collapses every
+// NaN to 0x7fc00000 and the int widens to long with its sign
+inline uint64_t hash_real(float f)
+{
+    if (f == 0) f = 0;
+    int32_t bits;
+    if (f != f) bits = 0x7fc00000;
+    else memcpy(&bits, &f, 4);
+    return hash_long((int64_t)bits);
+}
+
 inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
@@ -159,6 +170,7 @@ struct ColView {
             case TGPU_INT16: return ((const int16_t*)col->data)[p];
             case TGPU_INT8: return ((const int8_t*)col->data)[p];
             case TGPU_FLOAT64: return ((const int64_t*)col->data)[p];
+            case TGPU_FLOAT32: return ((const int32_t*)col->data)[p];     // REAL: the float's raw bits in an IntArrayBlock (S/type/RealType.java:104-121)
             default: return 0;
         }
     }
@@ -166,6 +178,7 @@ struct ColView {
     inline int64_t i128_high(int64_t i) const { return ((const int64_t*)col->data)[2 * pos(i)]; }
     inline int64_t i128_low(int64_t i) const { return ((const int64_t*)col->data)[2 * pos(i) + 1]; }
     inline double f64(int64_t i) const { return ((const double*)col->data)[pos(i)]; }
+    inline float f32(int64_t i) const { return ((const float*)col->data)[pos(i)]; }
     inline const uint8_t* bytes(int64_t i, int32_t* len) const
     {
         int64_t p = pos(i);
@@ -179,6 +192,7 @@ struct ColView {
         if (is_null(i)) return 0;
         switch (type) {
             case TGPU_FLOAT64: return hash_double(f64(i));
+            case TGPU_FLOAT32: return hash_real(f32(i));
             case TGPU_UTF8: { int32_t len; const uint8_t* b = bytes(i, &len); return xxh64(b, len, 0); }
             case TGPU_INT128: return xxh64_long(i128_high(i)) ^ xxh64_long(i128_low(i));   // S/type/LongDecimalType.java:203-229
             default: return hash_long(i64(i));  // integer widths sign-extend first (AbstractIntType.java:183-187)
@@ -190,6 +204,11 @@ struct ColView {
         switch (type) {
             case TGPU_FLOAT64: {
                 double a = f64(i), b = o.f64(j);
+                if (a != a && b != b) return true;
+                return a == b;
+            }
+            case TGPU_FLOAT32: {      // S/type/RealType.java:172-185
+                float a = f32(i), b = o.f32(j);
                 if (a != a && b != b) return true;
                 return a == b;
             }
@@ -207,6 +226,7 @@ struct ColView {
     inline bool equal(int64_t i, const ColView& o, int64_t j) const
     {
         if (type == TGPU_FLOAT64) return f64(i) == o.f64(j);
+        if (type == TGPU_FLOAT32) return f32(i) == o.f32(j);       // S/type/RealType.java:145-149
         return identical(i, o, j);
     }
 };
@@ -242,6 +262,7 @@ extern "C" {
 
 uint64_t orc_hash_long(int64_t v) { return hash_long(v); }
 uint64_t orc_hash_double(double d) { return hash_double(d); }
+uint64_t orc_hash_real(float f) { return hash_real(f); }
 uint64_t orc_xxh64(const void* data, int64_t len, uint64_t seed) { return xxh64((const uint8_t*)data, len, seed); }
 uint64_t orc_xxh64_long(int64_t v) { return xxh64_long(v); }
 uint64_t orc_murmur3(uint64_t x) { return murmur3(x); }
@@ -440,6 +461,11 @@ static int32_t flat_put(orc_groupby* g, const std::vector<ColView>& cols, int64_
                         }
                         case TGPU_FLOAT64: {
                             double a = cols[c].f64(row), b; memcpy(&b, &k[c].fixed, 8);
+                            same = (a != a && b != b) || a == b;
+                            break;
+                        }
+                        case TGPU_FLOAT32: {
+                            float a = cols[c].f32(row), b; int32_t bits = (int32_t)k[c].fixed; memcpy(&b, &bits, 4);
                             same = (a != a && b != b) || a == b;
                             break;
                         }

@@ -31,6 +31,7 @@ extern "C" {
 /* ---- scalar hash functions */
 uint64_t orc_hash_long(int64_t v);                 /* S/type/AbstractLongType.java:121-125 */
 uint64_t orc_hash_double(double d);                /* S/type/DoubleType.java:199-206 */
+uint64_t orc_hash_real(float f);                   /* S/type/RealType.java:151-159 */
 uint64_t orc_xxh64(const void* data, int64_t len, uint64_t seed); /* io.airlift.slice.XxHash64 (public XXH64) */
 uint64_t orc_xxh64_long(int64_t v);                /* XxHash64.hash(long) = XXH64 of the 8 LE bytes, seed 0 */
 uint64_t orc_murmur3(uint64_t x);                  /* M/operator/join/PagesHash.java:44-50 */

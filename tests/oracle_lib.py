@@ -38,6 +38,7 @@ def load():
     sig = {
         "orc_hash_long": (C.c_uint64, [C.c_int64]),
         "orc_hash_double": (C.c_uint64, [C.c_double]),
+        "orc_hash_real": (C.c_uint64, [C.c_float]),
         "orc_xxh64": (C.c_uint64, [VP, C.c_int64, C.c_uint64]),
         "orc_xxh64_long": (C.c_uint64, [C.c_int64]),
         "orc_murmur3": (C.c_uint64, [C.c_uint64]),

@@ -109,6 +109,28 @@ def test_hash_double_canonicalises_zero_and_nan():
     assert lib.orc_hash_double(1.5) == py_hash_long(int(bits))
 
 
+def test_hash_real_follows_realtype():
+    """S/type/RealType.java:151-159: AbstractLongType.hash(floatToIntBits(v)), -0.0 collapsed to +0.0; floatToIntBits makes every NaN
+    0x7fc00000 and the int widens to long WITH its sign.  The reference holds no numeric golden for it (parity of the value unpinned,
+    as for hash_long); its own test pins the property that all NaN encodings hash alike (M/test/.../type/TestRealType.java:63-79),
+    with the very bit patterns used here."""
+    lib = o.load()
+    from trino_b200.page import Block, Page
+    assert lib.orc_hash_real(0.0) == lib.orc_hash_real(-0.0) == py_hash_long(0)
+    nan_bits = [0x7FC00000, 0xFFC00000, 0x7FC00001, 0x7F800001, (-0x400000) & 0xFFFFFFFF]        # -0x400000, 0x7fc00000: TestRealType.java:70-71
+    nans = np.array(nan_bits, dtype=np.uint32).view(np.float32)
+    page = Page(Block.real(nans))
+    hashes = o.row_hashes(page, [0])
+    assert len(set(hashes.tolist())) == 1 and (int(hashes[0]) & M) == py_hash_long(0x7FC00000)
+    for v in (1.5, -1.5, 3.4028235e38, 1e-45, -2.0):
+        bits = int(np.float32(v).view(np.int32))                  # negative floats: the int is negative and sign-extends
+        assert lib.orc_hash_real(v) == py_hash_long(bits), v
+    # a REAL column hashes through the page path like the scalar does, NULL -> 0
+    vals = np.array([1.5, -0.0, 0.0, -7.25], dtype=np.float32)
+    hashes = o.row_hashes(Page(Block.real(vals, [False, False, False, True])), [0])
+    assert [int(h) & M for h in hashes] == [lib.orc_hash_real(1.5), py_hash_long(0), py_hash_long(0), 0]
+
+
 def test_array_size_and_load_factors():
     lib = o.load()
     # HashCommon.arraySize(n, f) = max(2, nextPowerOfTwo(ceil(n / f)))

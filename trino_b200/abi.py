@@ -15,7 +15,7 @@ TGPU_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_INSUFFICIENT_RESOURCES, ERR_NUMERIC_VALUE_OUT_OF_RANGE = -1, -2, -3, -4
 ERR_DIVISION_BY_ZERO, ERR_NOT_SUPPORTED, ERR_ILLEGAL_STATE = -5, -6, -7
 
-INT64, INT32, INT16, INT8, FLOAT64, UTF8, DICT32, RLE, INT128 = 1, 2, 3, 4, 5, 7, 8, 9, 10
+INT64, INT32, INT16, INT8, FLOAT64, UTF8, DICT32, RLE, INT128, FLOAT32 = 1, 2, 3, 4, 5, 7, 8, 9, 10, 11
 COL_NULLS_BYTEMAP = 1
 PARTITION_HASH_BUCKET, PARTITION_LOCAL = 0, 1
 PAGE_DEVICE = 1

@@ -192,7 +192,7 @@ struct DevColumn {
         switch (type) {
             case TGPU_INT128: return 16;
             case TGPU_INT64: case TGPU_FLOAT64: return 8;
-            case TGPU_INT32: return 4;
+            case TGPU_INT32: case TGPU_FLOAT32: return 4;
             case TGPU_INT16: return 2;
             case TGPU_INT8: return 1;
             default: return 0;

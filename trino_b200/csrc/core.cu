@@ -788,7 +788,7 @@ extern "C" int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* dp, tgpu_p
                 TG_CUDA(ctx, cudaMemcpyAsync((char*)h.data + first, (const char*)d.data + first, (size_t)(last - first), cudaMemcpyDeviceToHost, ctx->stream));
         }
         else {
-            int es = d.type == TGPU_INT128 ? 16 : d.type == TGPU_INT64 || d.type == TGPU_FLOAT64 ? 8 : d.type == TGPU_INT32 ? 4 : d.type == TGPU_INT16 ? 2 : 1;
+            int es = d.type == TGPU_INT128 ? 16 : d.type == TGPU_INT64 || d.type == TGPU_FLOAT64 ? 8 : d.type == TGPU_INT32 || d.type == TGPU_FLOAT32 ? 4 : d.type == TGPU_INT16 ? 2 : 1;
             if (n) TG_CUDA(ctx, cudaMemcpyAsync((void*)h.data, d.data, (size_t)n * es, cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (d.validity) {

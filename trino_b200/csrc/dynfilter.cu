@@ -148,6 +148,8 @@ struct DynFilterOp : tgpu_op {
             if (d.channel < 0 || d.channel >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "dynamic filter channel %d out of range", d.channel);
             const DevColumn& col = in.cols[d.channel];
             const bool dbl = col.type == TGPU_FLOAT64;
+            if (col.type == TGPU_FLOAT32 && d.kind != TGPU_DOMAIN_ALL && d.kind != TGPU_DOMAIN_NONE)
+                return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "dynamic filter domains over REAL columns stay on the Java filter");
             if (col.elem_size() == 0 && d.kind != TGPU_DOMAIN_ALL && d.kind != TGPU_DOMAIN_NONE)
                 return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "dynamic filter value sets over variable-width columns stay on the Java filter");
             if (dbl && d.kind == TGPU_DOMAIN_DISCRETE) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "discrete DOUBLE domains stay on the Java filter");

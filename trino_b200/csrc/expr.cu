@@ -310,8 +310,8 @@ struct FilterProjectOp : tgpu_op {
         for (int i = 0; i < host_prog.num_insns; i++) {
             const DOperand* ops[3] = {&host_prog.insns[i].a, &host_prog.insns[i].b, &host_prog.insns[i].c};
             for (auto* o : ops)
-                if (o->kind == TGPU_OPND_COLUMN && (in.cols[o->index].elem_size() == 0 || in.cols[o->index].elem_size() == 16))
-                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "expressions over variable-width / 128-bit channel %d are not supported on the GPU path", o->index);
+                if (o->kind == TGPU_OPND_COLUMN && (in.cols[o->index].elem_size() == 0 || in.cols[o->index].elem_size() == 16 || in.cols[o->index].type == TGPU_FLOAT32))
+                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "expressions over variable-width / 128-bit / REAL channel %d are not supported on the GPU path", o->index);
         }
         unsigned int* d_err = (unsigned int*)(ctx->d_scratch + 2);
         unsigned int* d_anynull = d_err + 1;

@@ -1037,6 +1037,30 @@ struct OutSpec {
     unsigned char* nullmap[48];      // 1 = NULL
 };
 
+// REAL group-by keys run as their exact DOUBLE widening (IDENTICAL over floats and over their doubles agree: NaN with NaN, -0.0 with +0.0,
+// S/type/RealType.java:172-185) and are narrowed back on output.  NaN payloads move by bit shifts, so the first-seen raw bits survive.
+__global__ void agg_widen_real_kernel(const unsigned int* __restrict__ in, int64_t n, unsigned long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned int b = in[i];
+        if ((b & 0x7FFFFFFFu) > 0x7F800000u) out[i] = ((unsigned long long)(b >> 31) << 63) | 0x7FF0000000000000ULL | ((unsigned long long)(b & 0x7FFFFFu) << 29);
+        else out[i] = (unsigned long long)__double_as_longlong((double)__uint_as_float(b));
+    }
+}
+
+__global__ void agg_narrow_real_kernel(const unsigned long long* __restrict__ in, int64_t n, unsigned int* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const unsigned long long b = in[i];
+        if ((b & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) out[i] = ((unsigned int)(b >> 63) << 31) | 0x7F800000u | (unsigned int)((b >> 29) & 0x7FFFFFu);
+        else out[i] = __float_as_uint((float)__longlong_as_double((long long)b));
+    }
+}
+
 // ---- long DECIMAL (Int128ArrayBlock) support: the group-by proper only ever sees 64-bit channels ----------------------------------
 // An INT128 input column is split into four BIGINT columns once per page: high word, low word (as bits), and the low word's upper and
 // lower 32 bits as non-negative numbers.  Keys use (high, low); DecimalSumAggregation sums high (signed) and the two low halves with the
@@ -1586,6 +1610,7 @@ struct AggOp : tgpu_op {
     bool gids_only = false;                  // tgpu_groupby_hash_* handle
     // variable-width keys: one string dictionary per UTF8 key column; the group-by runs on the 30-bit ids (strdict.cuh)
     std::vector<std::shared_ptr<StringDict>> key_dicts;
+    std::vector<uint8_t> key_real;       // REAL keys: the group-by runs on their DOUBLE widening (encode_string_keys), the output narrows them back
     // global aggregation default rows (HashAggregationOperator.getGlobalAggregationOutput :537-567)
     std::vector<int32_t> global_group_ids;
     int32_t group_id_key = -1;               // index into key_channels of the $group_id key
@@ -1798,12 +1823,40 @@ struct AggOp : tgpu_op {
     {
         const int nk = (int)key_channels.size();
         if ((int)key_dicts.size() < nk) key_dicts.resize(nk);
+        if ((int)key_real.size() < nk) key_real.resize(nk, 0);
+        bool any_real = false;
+        for (auto& c : pg->cols) any_real = any_real || c.type == TGPU_FLOAT32;
+        if (any_real) {
+            if (has_pre) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "a fused pre-stage over pages with REAL channels is not supported: run the FilterAndProject operator in front");
+            for (auto& f : fns)
+                if (f.function != TGPU_AGG_COUNT_STAR && f.input_channel >= 0 && f.input_channel < (int)pg->cols.size() && pg->cols[f.input_channel].type == TGPU_FLOAT32)
+                    return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a REAL channel: keep the Java accumulator", f.function);
+        }
         std::map<int, int> done;      // channel -> first key that encoded it
         for (int k = 0; k < nk; k++) {
             int ch = key_input_channel(k);
             if (ch < 0 || ch >= (int)pg->cols.size()) continue;      // reported by make_plan
             auto first = done.find(ch);
-            if (first != done.end()) { key_dicts[k] = key_dicts[first->second]; continue; }
+            if (first != done.end()) { key_dicts[k] = key_dicts[first->second]; key_real[k] = key_real[first->second]; continue; }
+            if (pg->cols[ch].type == TGPU_FLOAT32) {
+                if (planned && !key_real[k]) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d became REAL after the first page", ch);
+                const DevColumn& src = pg->cols[ch];
+                DevColumn wide;
+                wide.type = TGPU_FLOAT64;
+                wide.length = src.length;
+                wide.own_data = std::make_shared<DevBuf>();
+                TG_TRY(wide.own_data->alloc(ctx, (size_t)std::max<int64_t>(src.length, 1) * 8));
+                wide.data = wide.own_data->p;
+                wide.own_validity = src.own_validity;
+                wide.validity = src.validity;
+                if (src.length > 0)
+                    TG_LAUNCH(ctx, agg_widen_real_kernel, tg_grid(ctx, src.length, 1024, 8), 256, 0, (const unsigned int*)src.data, src.length, wide.own_data->as<unsigned long long>());
+                pg->cols[ch] = std::move(wide);
+                key_real[k] = 1;
+                done[ch] = k;
+                continue;
+            }
+            if (key_real[k]) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d was REAL in an earlier page and is type %d now", ch, pg->cols[ch].type);
             const bool is_string = pg->cols[ch].type == TGPU_UTF8;
             if (!is_string && !key_dicts[k]) continue;
             if (!is_string) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "group-by channel %d was variable-width in an earlier page and is type %d now", ch, pg->cols[ch].type);
@@ -2918,6 +2971,16 @@ struct AggOp : tgpu_op {
                 DevColumn text;
                 TG_TRY(key_dicts[k]->decode((const int32_t*)c.own_data->p, nm->as<unsigned char>(), G, &text));
                 c = std::move(text);
+            }
+            if (k < (int)key_real.size() && key_real[k]) {
+                DevColumn real;
+                real.type = TGPU_FLOAT32;
+                real.length = G;
+                real.own_data = std::make_shared<DevBuf>();
+                TG_TRY(real.own_data->alloc(ctx, (size_t)G * 4));
+                real.data = real.own_data->p;
+                TG_LAUNCH(ctx, agg_narrow_real_kernel, grid, 256, 0, (const unsigned long long*)c.own_data->p, G, real.own_data->as<unsigned int>());
+                c = std::move(real);
             }
             if (k > 0 && k - 1 < (int)wide_key_high.size() && wide_key_high[k - 1]) {
                 // the low word of an INT128 key: weld it to the high word emitted just before (both carry the same NULL flags)

@@ -30,6 +30,16 @@ TG_HD uint64_t hash_double_bits(int64_t bits)
     return hash_long((int64_t)u);
 }
 
+// REAL hash code (S/type/RealType.java:151-159): -0.0 -> +0.0, every NaN -> 0x7fc00000 (Float.floatToIntBits), the int widened with its
+// sign, then hash_long.  `bits`: the float's raw bits (any upper half is ignored)
+TG_HD uint64_t hash_real_bits(int64_t bits)
+{
+    uint32_t u = (uint32_t)bits;
+    if ((u << 1) == 0) u = 0;
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) u = 0x7FC00000u;
+    return hash_long((int64_t)(int32_t)u);
+}
+
 // murmur3 fmix64 (M/operator/join/PagesHash.java:44-50 == fastutil HashCommon.murmurHash3 used at
 // M/operator/BigintGroupByHash.java:297-300)
 TG_HD uint64_t murmur3_mix(uint64_t x)

@@ -1135,7 +1135,8 @@ int lookup_positions_generic(tgpu_ctx* ctx, const tgpu_lookup* lk, const std::ve
     if (keys.size() != lk->build_keys.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe has %zu join channels, build has %zu", keys.size(), lk->build_keys.size());
     for (size_t c = 0; c < keys.size(); c++) {
         bool pu = keys[c]->type == TGPU_UTF8, bu = lk->build_keys[c].type == TGPU_UTF8, pd = keys[c]->type == TGPU_FLOAT64, bd = lk->build_keys[c].type == TGPU_FLOAT64;
-        if (pu != bu || pd != bd) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "join channel %zu: probe type %d does not match build type %d", c, keys[c]->type, lk->build_keys[c].type);
+        bool pr = keys[c]->type == TGPU_FLOAT32, br = lk->build_keys[c].type == TGPU_FLOAT32;
+        if (pu != bu || pd != bd || pr != br) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "join channel %zu: probe type %d does not match build type %d", c, keys[c]->type, lk->build_keys[c].type);
     }
     if (n == 0) return TGPU_OK;
     DevColumn fp;
@@ -1297,7 +1298,7 @@ struct JoinBuildOp : tgpu_op {
             for (size_t c = 0; c < all.cols.size(); c++) all.cols[c].type = c < col_types.size() && col_types[c] ? col_types[c] : TGPU_INT64;
         }
         // one fixed-width channel -> the table is keyed by the value itself; anything else -> by the row hash + verification
-        lk->generic = nk != 1 || all.cols[0].type == TGPU_UTF8 || all.cols[0].type == TGPU_INT128;      // (no 64-bit canonical key)
+        lk->generic = nk != 1 || all.cols[0].type == TGPU_UTF8 || all.cols[0].type == TGPU_INT128 || all.cols[0].type == TGPU_FLOAT32;      // (no 64-bit canonical key; REAL keys compare as floats in rowkeys.cuh)
         lk->store.rows = rows;
         if (lk->generic) {
             for (size_t c = 0; c < nk; c++) lk->build_keys.push_back(all.cols[c]);
@@ -1888,8 +1889,9 @@ struct SemiJoinOp : tgpu_op {
         TG_TRY(tg_ingest_page(ctx, page, &in));
         if (probe_channel < 0 || probe_channel >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe join channel out of range");
         const DevColumn& key = in.cols[probe_channel];
-        if (key.type == TGPU_FLOAT64 || lookup->key_type == TGPU_FLOAT64)
-            return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "DOUBLE semi-join keys (NaN is IDENTICAL to NaN in a ChannelSet): keep the Java operator");
+        const bool real_set = lookup->generic && lookup->build_keys.size() == 1 && lookup->build_keys[0].type == TGPU_FLOAT32;
+        if (key.type == TGPU_FLOAT64 || lookup->key_type == TGPU_FLOAT64 || key.type == TGPU_FLOAT32 || real_set)
+            return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "DOUBLE / REAL semi-join keys (NaN is IDENTICAL to NaN in a ChannelSet): keep the Java operator");
         DevBuf pos;
         TG_TRY(pos.alloc(ctx, (size_t)n * 4));
         if (lookup->generic) {

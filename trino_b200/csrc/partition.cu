@@ -122,6 +122,7 @@ int host_type_hash(tgpu_ctx* ctx, const tgpu_column& c, uint64_t* out)
         case TGPU_INT16: *out = hash_long(*(const int16_t*)c.data); return TGPU_OK;
         case TGPU_INT8: *out = hash_long(*(const int8_t*)c.data); return TGPU_OK;
         case TGPU_FLOAT64: *out = hash_double_bits(*(const int64_t*)c.data); return TGPU_OK;
+        case TGPU_FLOAT32: *out = hash_real_bits(*(const int32_t*)c.data); return TGPU_OK;
         case TGPU_INT128: *out = hash_int128(((const int64_t*)c.data)[0], ((const int64_t*)c.data)[1]); return TGPU_OK;
         case TGPU_UTF8:
             if (!c.offsets) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "variable-width partition constant without offsets");

@@ -14,7 +14,7 @@ struct KeyCols {
     ColRef cols[MAX_KEY_COLS];
     const int32_t* offsets[MAX_KEY_COLS];   // UTF8 only
     int32_t is_utf8[MAX_KEY_COLS];
-    int32_t is_double[MAX_KEY_COLS];
+    int32_t is_double[MAX_KEY_COLS];        // 1 = DOUBLE (raw bits in 8 bytes), 2 = REAL (raw bits in 4 bytes)
     int32_t is_const[MAX_KEY_COLS];         // partitionConstants (M/operator/output/PagePartitioner.java:436-451): no column, one hash for every row
     uint64_t const_hash[MAX_KEY_COLS];
 };
@@ -24,7 +24,7 @@ static inline void key_cols_set(KeyCols* k, int c, const DevColumn& col)
     k->cols[c] = tg_colref(col);
     k->offsets[c] = col.offsets;
     k->is_utf8[c] = col.type == TGPU_UTF8;
-    k->is_double[c] = col.type == TGPU_FLOAT64;
+    k->is_double[c] = col.type == TGPU_FLOAT64 ? 1 : col.type == TGPU_FLOAT32 ? 2 : 0;
 }
 
 #if defined(__CUDACC__)
@@ -42,7 +42,7 @@ __device__ __forceinline__ uint64_t type_hash(const KeyCols& k, int c, int64_t r
         return hash_int128(w[0], w[1]);
     }
     int64_t v = tg_load_i64(col, row);
-    return k.is_double[c] ? hash_double_bits(v) : hash_long(v);
+    return k.is_double[c] == 1 ? hash_double_bits(v) : k.is_double[c] == 2 ? hash_real_bits(v) : hash_long(v);
 }
 
 __device__ __forceinline__ uint64_t row_hash(const KeyCols& k, int64_t row)
@@ -73,7 +73,9 @@ __device__ __forceinline__ uint64_t row_hash_attempt(const KeyCols& k, int64_t r
         }
         else {
             uint64_t u = (uint64_t)tg_load_i64(col, row);
-            if (k.is_double[c] && (u << 1) == 0) u = 0;
+            if (k.is_double[c] == 2) u = (uint32_t)u;
+            if (k.is_double[c] == 1 && (u << 1) == 0) u = 0;
+            if (k.is_double[c] == 2 && (u << 33) == 0) u = 0;
             t = murmur3_mix(u + 0xD1B54A32D192ED03ULL * (uint64_t)attempt);
         }
         h = murmur3_mix(h ^ t) * 31 + (uint64_t)(c + 1);
@@ -87,9 +89,13 @@ __device__ __forceinline__ bool row_joinable(const KeyCols& k, int64_t row)
     for (int c = 0; c < k.count; c++) {
         const ColRef& col = k.cols[c];
         if (!tg_valid(col.validity, row)) return false;
-        if (k.is_double[c]) {
+        if (k.is_double[c] == 1) {
             unsigned long long u = (unsigned long long)tg_load_i64(col, row);
             if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) return false;
+        }
+        else if (k.is_double[c] == 2) {
+            unsigned int u = (unsigned int)tg_load_i64(col, row);
+            if ((u & 0x7FFFFFFFu) > 0x7F800000u) return false;
         }
     }
     return true;
@@ -114,8 +120,13 @@ __device__ __forceinline__ bool col_value_equal(const KeyCols& a, int c, int64_t
         return wa[0] == wb[0] && wa[1] == wb[1];
     }
     int64_t va = tg_load_i64(a.cols[c], ra), vb = tg_load_i64(b.cols[c], rb);
-    if (a.is_double[c]) {
+    if (a.is_double[c] == 1) {
         double x = __longlong_as_double(va), y = __longlong_as_double(vb);
+        if (nan_equal && x != x && y != y) return true;
+        return x == y;
+    }
+    if (a.is_double[c] == 2) {
+        float x = __int_as_float((int)va), y = __int_as_float((int)vb);
         if (nan_equal && x != x && y != y) return true;
         return x == y;
     }

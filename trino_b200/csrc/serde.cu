@@ -90,7 +90,7 @@ const char* encoding_name(int32_t type)
 {
     switch (type) {
         case TGPU_INT64: case TGPU_FLOAT64: return "LONG_ARRAY";
-        case TGPU_INT32: return "INT_ARRAY";
+        case TGPU_INT32: case TGPU_FLOAT32: return "INT_ARRAY";
         case TGPU_INT16: return "SHORT_ARRAY";
         case TGPU_INT8: return "BYTE_ARRAY";
         case TGPU_UTF8: return "VARIABLE_WIDTH";
@@ -147,7 +147,7 @@ extern "C" int64_t tgpu_page_serialized_size_bound(const tgpu_page* page)
         int64_t n = page->num_rows;
         total += 4 + (int64_t)strlen(name) + 4 + 1 + (n + 7) / 8 + 4;
         if (col.type == TGPU_UTF8) total += 4 * n + (1LL << 31);      // the byte payload is only known on the device: see below
-        else total += n * (col.type == TGPU_INT64 || col.type == TGPU_FLOAT64 ? 8 : col.type == TGPU_INT32 ? 4 : col.type == TGPU_INT16 ? 2 : 1);
+        else total += n * (col.type == TGPU_INT64 || col.type == TGPU_FLOAT64 ? 8 : col.type == TGPU_INT32 || col.type == TGPU_FLOAT32 ? 4 : col.type == TGPU_INT16 ? 2 : 1);
     }
     return total;
 }

@@ -21,8 +21,8 @@ import numpy as np
 from . import abi
 from .page import AbiPage, Block, Page, RowBlock, compose_row_blocks, compose_state_blocks, flatten_row_blocks, flatten_state_blocks
 
-_NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64}
-_ELEM = {abi.INT64: 8, abi.INT32: 4, abi.INT16: 2, abi.INT8: 1, abi.FLOAT64: 8}
+_NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64, abi.FLOAT32: np.float32}
+_ELEM = {abi.INT64: 8, abi.INT32: 4, abi.INT16: 2, abi.INT8: 1, abi.FLOAT64: 8, abi.FLOAT32: 4}
 
 
 def _i32(values):

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import abi
 
-_NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64}
+_NP_OF_TYPE = {abi.INT64: np.int64, abi.INT32: np.int32, abi.INT16: np.int16, abi.INT8: np.int8, abi.FLOAT64: np.float64, abi.FLOAT32: np.float32}
 
 
 class Block:
@@ -83,6 +83,11 @@ class Block:
         return Block._fixed(abi.FLOAT64, values, nulls)
 
     @staticmethod
+    def real(values, nulls=None):
+        """REAL: float32 values; the buffer is the IntArrayBlock of raw float bits the reference keeps (S/type/RealType.java:104-121)"""
+        return Block._fixed(abi.FLOAT32, values, nulls)
+
+    @staticmethod
     def varchar(values):
         nulls = [v is None for v in values]
         enc = [b"" if v is None else (v.encode() if isinstance(v, str) else bytes(v)) for v in values]
@@ -105,7 +110,7 @@ class Block:
         v = self.values[i]
         if self.type == abi.INT128:
             return (int(v[0]) << 64) | (int(v[1]) & ((1 << 64) - 1))
-        return float(v) if self.type == abi.FLOAT64 else int(v)
+        return float(v) if self.type in (abi.FLOAT64, abi.FLOAT32) else int(v)
 
     def to_pylist(self):
         return [self.get(i) for i in range(self.position_count)]
