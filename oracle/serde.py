@@ -15,7 +15,7 @@ SURVEY.md §8(f) rank 1: the format GPU stages must speak to exchange pages with
   VARIABLE_WIDTH   = int32 positionCount | nulls | int32 nonNullCount | nonNullCount x int32 ending offsets (from 0) | bytes
                                                                        (S/block/VariableWidthBlockEncoding.java:57-79,112-146)
 
-All integers little-endian (Slice).  BIGINT, DOUBLE and the other 8-byte types travel as LONG_ARRAY; INTEGER/DATE/REAL as INT_ARRAY;
+All integers little-endian (Slice).  BIGINT, DOUBLE and the other 8-byte types travel as LONG_ARRAY; INTEGER/DATE/REAL as INT_ARRAY; long DECIMAL as INT128_ARRAY;
 SMALLINT as SHORT_ARRAY; TINYINT/BOOLEAN as BYTE_ARRAY; VARCHAR/VARBINARY as VARIABLE_WIDTH.  The wire carries no SQL type: the
 reader is told the channel types (the planner knows them).
 
@@ -29,7 +29,9 @@ import numpy as np
 
 HEADER_SIZE = 12
 
-_NAMES = {8: b"LONG_ARRAY", 4: b"INT_ARRAY", 2: b"SHORT_ARRAY", 1: b"BYTE_ARRAY", 0: b"VARIABLE_WIDTH"}
+# 16: Int128ArrayBlockEncoding (S/block/Int128ArrayBlockEncoding.java:52-84): the same body as LONG_ARRAY with two longs per position,
+# the high word first - values are int64[n][2] here
+_NAMES = {16: b"INT128_ARRAY", 8: b"LONG_ARRAY", 4: b"INT_ARRAY", 2: b"SHORT_ARRAY", 1: b"BYTE_ARRAY", 0: b"VARIABLE_WIDTH"}
 
 
 def pack_null_bits(nulls):
@@ -80,7 +82,7 @@ def serialize_columns(position_count, columns):
     for col in columns:
         if col[0] == "fixed":
             _, values, nulls = col
-            width = np.asarray(values).dtype.itemsize
+            width = np.asarray(values).dtype.itemsize * (2 if np.asarray(values).ndim == 2 else 1)
             name = _NAMES[width]
             body = _block_body_fixed(np.asarray(values), nulls, width)
         else:
@@ -130,16 +132,18 @@ def deserialize_columns(data):
             pos += nb
         width = widths[name]
         if width:
-            dt = np.dtype("<i%d" % width)
+            per = 2 if width == 16 else 1
+            dt = np.dtype("<i%d" % (width // per))
+            shape = (lambda rows: (rows, 2)) if per == 2 else (lambda rows: (rows,))
             if nulls is None:
-                values = np.frombuffer(data, dtype=dt, count=n, offset=pos).copy()
+                values = np.frombuffer(data, dtype=dt, count=n * per, offset=pos).reshape(shape(n)).copy()
                 pos += n * width
             else:
                 (k,) = struct.unpack_from("<i", data, pos)
                 pos += 4
-                kept = np.frombuffer(data, dtype=dt, count=k, offset=pos)
+                kept = np.frombuffer(data, dtype=dt, count=k * per, offset=pos).reshape(shape(k))
                 pos += k * width
-                values = np.zeros(n, dtype=dt)        # LongArrayBlockEncoding.expandLongsWithNulls: NULL positions read as 0
+                values = np.zeros(shape(n), dtype=dt)        # LongArrayBlockEncoding.expandLongsWithNulls: NULL positions read as 0
                 values[~nulls] = kept
             out.append((name.decode(), values, nulls))
         else:

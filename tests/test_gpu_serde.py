@@ -1,4 +1,4 @@
-"""EXPERIMENTAL (branch wip/page-serde, not yet run on hardware): the page wire format through the C ABI against oracle/serde.py
+"""The page wire format through the C ABI against oracle/serde.py
 (byte-exact for pages whose NULL-free columns carry no validity bitmap) and as a round trip."""
 import ctypes as C
 import os
@@ -53,3 +53,16 @@ def test_golden_sizes(ctx):
     # TestPagesSerde.testBigintSerializedSize / testVarcharSerializedSize
     assert len(gpu_serialize(ctx, Page(Block.bigint([123, 456])))) == 35 + 16
     assert len(gpu_serialize(ctx, Page(Block.varchar(["alice", "bob"])))) == 43 + 9 + 7
+
+
+@pytest.mark.parametrize("n", [0, 1, 9, 5000])
+def test_int128_and_real_columns(ctx, n):
+    """INT128_ARRAY (long DECIMAL, S/block/Int128ArrayBlockEncoding.java:52-84) and REAL as INT_ARRAY: byte-exact against the oracle, and back"""
+    rng = np.random.default_rng(n + 77)
+    wide = [int(x) * (1 << 70) + int(y) for x, y in zip(rng.integers(-2**50, 2**50, n), rng.integers(0, 2**62, n))]
+    page = Page(Block.int128(wide, (rng.random(n) < 0.4) if n else None), Block.int128(wide[::-1]), Block.real(rng.normal(size=n).astype(np.float32), (rng.random(n) < 0.2) if n else None),
+                position_count=n)
+    want = serde.serialize_page(page)
+    assert gpu_serialize(ctx, page) == want
+    back = gpu_deserialize(ctx, want, [abi.INT128, abi.INT128, abi.FLOAT32])
+    assert back.rows() == page.rows()

@@ -69,3 +69,27 @@ def test_round_trip_all_encodings():
         for name, values, got_nulls in cols:
             again.append(("var", values[0], values[1], got_nulls) if name == "VARIABLE_WIDTH" else ("fixed", values, got_nulls))
         assert serde.serialize_columns(count, again) == data
+
+
+def test_int128_and_real_blocks():
+    """long DECIMAL travels as INT128_ARRAY (S/block/Int128ArrayBlockEncoding.java:52-84: positionCount | nulls | [nonNullCount] | two
+    longs per non-NULL position, the high word first), REAL as INT_ARRAY of the raw float bits."""
+    import struct
+    page = Page(Block.int128([1, None, (1 << 64) + 5]), Block.real(np.array([1.5, -0.0, 2.0], dtype=np.float32)))
+    data = serde.serialize_page(page)
+    body = data[serde.HEADER_SIZE:]
+    name = b"INT128_ARRAY"
+    want = struct.pack("<i", 2) + struct.pack("<i", len(name)) + name + struct.pack("<i", 3) + b"\x01" + bytes([0b01000000]) + struct.pack("<i", 2) \
+        + struct.pack("<qqqq", 0, 1, 1, 5)
+    assert body[:len(want)] == want
+    name2 = b"INT_ARRAY"
+    want2 = struct.pack("<i", len(name2)) + name2 + struct.pack("<i", 3) + b"\x00" + np.array([1.5, -0.0, 2.0], dtype=np.float32).tobytes()
+    assert body[len(want):] == want2
+    count, cols = serde.deserialize_columns(data)
+    assert count == 3 and [c[0] for c in cols] == ["INT128_ARRAY", "INT_ARRAY"]
+    assert cols[0][1].tolist() == [[0, 1], [0, 0], [1, 5]] and cols[0][2].tolist() == [False, True, False]
+    assert serde.serialize_columns(count, [("fixed", cols[0][1], cols[0][2]), ("fixed", cols[1][1], cols[1][2])]) == data
+    # without NULLs: no count, 16 bytes per position
+    plain = serde.serialize_page(Page(Block.int128([-1, 1 << 100])))
+    assert len(plain) == serde.HEADER_SIZE + 4 + 4 + len(name) + 4 + 1 + 32
+    assert plain[-32:] == struct.pack("<qqqq", -1, -1, 1 << 36, 0)

@@ -1,6 +1,6 @@
 // serde.cu — the reference's page wire format to and from device columns.
 //
-// EXPERIMENTAL (branch wip/page-serde): written after round 1's GPU minutes were spent; not yet run on hardware.
+// (round 1 left this on a branch; merged and run on hardware in round 2: tests/test_gpu_serde.py)
 //
 // Format (uncompressed, unencrypted; all integers little-endian) — restated in oracle/serde.py with the reference lines:
 //   serialized page = int32 positionCount | int32 uncompressedSize | int32 compressedSize | raw page
@@ -61,7 +61,7 @@ __global__ void serde_expand_kernel(const T* __restrict__ compacted, const uint8
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = ((validity[i >> 3] >> (i & 7)) & 1) ? compacted[rank[i]] : T(0);
+    for (; i < n; i += stride) out[i] = ((validity[i >> 3] >> (i & 7)) & 1) ? compacted[rank[i]] : T();
 }
 
 // VARIABLE_WIDTH write: ending offset of every position relative to the first (NULL positions have zero length)
@@ -89,6 +89,7 @@ __global__ void serde_expand_offsets_kernel(const int32_t* __restrict__ ends, co
 const char* encoding_name(int32_t type)
 {
     switch (type) {
+        case TGPU_INT128: return "INT128_ARRAY";     // S/block/Int128ArrayBlockEncoding.java:52-84: LONG_ARRAY's body with two longs per position
         case TGPU_INT64: case TGPU_FLOAT64: return "LONG_ARRAY";
         case TGPU_INT32: case TGPU_FLOAT32: return "INT_ARRAY";
         case TGPU_INT16: return "SHORT_ARRAY";
@@ -147,7 +148,7 @@ extern "C" int64_t tgpu_page_serialized_size_bound(const tgpu_page* page)
         int64_t n = page->num_rows;
         total += 4 + (int64_t)strlen(name) + 4 + 1 + (n + 7) / 8 + 4;
         if (col.type == TGPU_UTF8) total += 4 * n + (1LL << 31);      // the byte payload is only known on the device: see below
-        else total += n * (col.type == TGPU_INT64 || col.type == TGPU_FLOAT64 ? 8 : col.type == TGPU_INT32 || col.type == TGPU_FLOAT32 ? 4 : col.type == TGPU_INT16 ? 2 : 1);
+        else total += n * (col.type == TGPU_INT128 ? 16 : col.type == TGPU_INT64 || col.type == TGPU_FLOAT64 ? 8 : col.type == TGPU_INT32 || col.type == TGPU_FLOAT32 ? 4 : col.type == TGPU_INT16 ? 2 : 1);
     }
     return total;
 }
@@ -220,7 +221,8 @@ extern "C" int tgpu_page_serialize(tgpu_ctx* ctx, const tgpu_page* page, uint8_t
     cub::DeviceSelect::Flagged(nullptr, tmp_bytes, (const T*)col.data, flags, compact.as<T>(), d_count, (int)n, ctx->stream);                \
     TG_TRY(tmp.alloc(ctx, tmp_bytes));                                                                                                        \
     TG_CUDA(ctx, cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, (const T*)col.data, flags, compact.as<T>(), d_count, (int)n, ctx->stream));
-                if (es == 8) { SERDE_SELECT(long long) }
+                if (es == 16) { SERDE_SELECT(longlong2) }
+                else if (es == 8) { SERDE_SELECT(long long) }
                 else if (es == 4) { SERDE_SELECT(int) }
                 else if (es == 2) { SERDE_SELECT(short) }
                 else { SERDE_SELECT(signed char) }
@@ -352,7 +354,8 @@ extern "C" int tgpu_page_deserialize(tgpu_ctx* ctx, const uint8_t* data, int64_t
                 if (k) TG_CUDA(ctx, cudaMemcpyAsync(compact.p, data + pos, (size_t)k * es, cudaMemcpyHostToDevice, ctx->stream));
                 pos += k * es;
                 int grid = tg_grid(ctx, n, 1024, 8);
-                if (es == 8) TG_LAUNCH(ctx, serde_expand_kernel<long long>, grid, 256, 0, compact.as<long long>(), col.validity, rank.as<int>(), n, col.own_data->as<long long>());
+                if (es == 16) TG_LAUNCH(ctx, serde_expand_kernel<longlong2>, grid, 256, 0, compact.as<longlong2>(), col.validity, rank.as<int>(), n, col.own_data->as<longlong2>());
+                else if (es == 8) TG_LAUNCH(ctx, serde_expand_kernel<long long>, grid, 256, 0, compact.as<long long>(), col.validity, rank.as<int>(), n, col.own_data->as<long long>());
                 else if (es == 4) TG_LAUNCH(ctx, serde_expand_kernel<int>, grid, 256, 0, compact.as<int>(), col.validity, rank.as<int>(), n, col.own_data->as<int>());
                 else if (es == 2) TG_LAUNCH(ctx, serde_expand_kernel<short>, grid, 256, 0, compact.as<short>(), col.validity, rank.as<int>(), n, col.own_data->as<short>());
                 else TG_LAUNCH(ctx, serde_expand_kernel<signed char>, grid, 256, 0, compact.as<signed char>(), col.validity, rank.as<int>(), n, col.own_data->as<signed char>());
