@@ -506,7 +506,8 @@ int tgpu_page_copy_to_host(tgpu_ctx* ctx, const tgpu_page* device_page, tgpu_pag
 /* The reference's page wire format, uncompressed and unencrypted (PagesSerdeUtil.writeRawPage / CompressingEncryptingPageSerializer
  * with CompressionCodec.NONE; M/execution/buffer/PagesSerdeUtil.java:44-76, S/block/LongArrayBlockEncoding.java:61-133,
  * S/block/EncoderUtil.java:35-70, S/block/VariableWidthBlockEncoding.java:57-146): lets a GPU stage exchange pages with Java
- * tasks over the existing HTTP exchange.  EXPERIMENTAL - not yet run on hardware (branch wip/page-serde).
+ * tasks over the existing HTTP exchange.  Block encodings: LONG_ARRAY, INT_ARRAY (also REAL), SHORT_ARRAY, BYTE_ARRAY, VARIABLE_WIDTH,
+ * INT128_ARRAY (S/block/Int128ArrayBlockEncoding.java:52-84); dictionary / RLE inputs are written flat.  Parity: tests/test_gpu_serde.py.
  * serialize: `out` is host memory of `capacity` bytes (tgpu_page_serialized_size_bound gives a bound), *bytes_out the length.
  * deserialize: `types[c]` is the tgpu_type of channel c (the wire names the block encoding, not the SQL type). */
 int64_t tgpu_page_serialized_size_bound(const tgpu_page* page);

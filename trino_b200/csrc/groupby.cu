@@ -2481,7 +2481,7 @@ struct AggOp : tgpu_op {
     // Sliced pass over a slice-ORDERED COPY of the page: the channels the plan reads (and the page row numbers, for the stamps) are
     // moved into slice order by the stable multi-split, so every slice launch streams its rows instead of gathering them through a
     // row list (which cost a 2-sector DRAM fetch per value).  *done = false: shape not handled, use the row-list form.
-    // EXPERIMENTAL (branch wip/path-g-physical): written without GPU time left in round 1, not yet run on hardware.
+    // (tests/test_gpu_groupby.py::test_general_path_physical_slices_match_oracle; the fused single-launch form below took over the default)
     int run_physical_slices(const DevPage& in, const DColumns& cols, int64_t n, int log_slices, int log_cap, bool* done)
     {
         *done = false;
