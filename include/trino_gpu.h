@@ -68,8 +68,9 @@ typedef enum tgpu_type {
     TGPU_FLOAT32 = 11  /* REAL: the float's raw IEEE bits in an IntArrayBlock (S/type/RealType.java:104-121).  Moves through every
                           operator; partition / join / group-by key with RealType's operators (hash :151-159 over floatToIntBits with
                           -0.0 collapsed; EQUAL :145-149 - NaN matches nothing; IDENTICAL :172-185 - NaN is identical to NaN).  Join and
-                          group-by widen the key to its (exact) double internally.  Aggregates and expressions over REAL, REAL
-                          semi-join keys and REAL dynamic-filter domains answer TGPU_ERR_NOT_SUPPORTED.                              */
+                          group-by widen the key to its (exact) double internally; a semi-join set over REAL or DOUBLE answers NaN
+                          probes by IDENTICAL like the ChannelSet.  Aggregates and expressions over REAL and REAL dynamic-filter
+                          domains answer TGPU_ERR_NOT_SUPPORTED.                                                                   */
 } tgpu_type;
 
 enum {
@@ -364,7 +365,8 @@ int tgpu_join_outer_create(tgpu_ctx* ctx, tgpu_lookup* lookup, const int32_t* pr
 /* HashSemiJoinOperator (M/operator/HashSemiJoinOperator.java:155-201): `lookup` is built by a hash builder over the filtering
  * source's join channel (SetBuilderOperator's ChannelSet; no output channels needed).  Output = the input page's columns + one
  * BOOLEAN (TGPU_INT8) column: NULL probe key -> false if the set is empty else NULL; otherwise contained -> true, not contained ->
- * NULL if the set holds a NULL else false.  DOUBLE keys: TGPU_ERR_NOT_SUPPORTED. */
+ * NULL if the set holds a NULL else false.  DOUBLE / REAL keys: membership is IDENTICAL as in the ChannelSet's FlatSet
+ * (M/operator/FlatSet.java:54,374) - a NaN probe key is contained iff the set holds a NaN, -0.0 and +0.0 are one member. */
 int tgpu_semi_join_create(tgpu_ctx* ctx, tgpu_lookup* lookup, int32_t probe_join_channel, tgpu_op** out);
 
 /* DynamicFilterSourceOperator / JoinDomainBuilder (M/operator/DynamicFilterSourceOperator.java, M/operator/JoinDomainBuilder.java):

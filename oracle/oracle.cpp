@@ -1497,3 +1497,41 @@ extern "C" void orc_semi_join_bigint(const int64_t* set_values, const uint8_t* s
         else { out_value[i] = contains ? 1 : 0; out_null[i] = 0; }
     }
 }
+
+// the same operator over a DOUBLE (kind 1: 8-byte raw bits) or REAL (kind 2: 4-byte raw bits) channel: the ChannelSet's FlatSet compares with
+// IDENTICAL (M/operator/FlatSet.java:54,374; S/type/DoubleType.java:218-229, S/type/RealType.java:172-185): every NaN is one member, -0.0 and +0.0 are one
+extern "C" void orc_semi_join_float(int32_t kind, const void* set_values, const uint8_t* set_validity, int64_t set_rows, const void* probe, const uint8_t* probe_validity,
+                                    int64_t probe_rows, int8_t* out_value, uint8_t* out_null)
+{
+    auto canonical = [kind](const void* base, int64_t i) -> uint64_t {
+        if (kind == 1) {
+            uint64_t u = ((const uint64_t*)base)[i];
+            if ((u << 1) == 0) return 0;
+            if ((u & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL) return 0x7FF8000000000000ULL;
+            return u;
+        }
+        uint32_t u = ((const uint32_t*)base)[i];
+        if ((u << 1) == 0) return 0;
+        if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 0x7FC00000u;
+        return u;
+    };
+    std::unordered_set<uint64_t> set;
+    bool has_null = false;
+    for (int64_t i = 0; i < set_rows; i++) {
+        bool valid = !set_validity || ((set_validity[i >> 3] >> (i & 7)) & 1);
+        if (!valid) has_null = true;
+        else set.insert(canonical(set_values, i));
+    }
+    const bool empty = set.empty() && !has_null;
+    for (int64_t i = 0; i < probe_rows; i++) {
+        bool valid = !probe_validity || ((probe_validity[i >> 3] >> (i & 7)) & 1);
+        if (!valid) {
+            out_value[i] = 0;
+            out_null[i] = empty ? 0 : 1;
+            continue;
+        }
+        bool contains = set.count(canonical(probe, i)) != 0;
+        if (!contains && has_null) { out_value[i] = 0; out_null[i] = 1; }
+        else { out_value[i] = contains ? 1 : 0; out_null[i] = 0; }
+    }
+}

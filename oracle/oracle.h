@@ -94,6 +94,9 @@ int64_t orc_join_expand(const orc_join* j, const int32_t* join_positions, int64_
  * out_value[i] = the BOOLEAN, out_null[i] = 1 when the result is NULL. */
 void orc_semi_join_bigint(const int64_t* set_values, const uint8_t* set_validity, int64_t set_rows, const int64_t* probe, const uint8_t* probe_validity,
                           int64_t probe_rows, int8_t* out_value, uint8_t* out_null);
+/* the same over a DOUBLE (kind 1) or REAL (kind 2) channel given as raw IEEE bits: IDENTICAL membership (NaN is a member like any other) */
+void orc_semi_join_float(int32_t kind, const void* set_values, const uint8_t* set_validity, int64_t set_rows, const void* probe, const uint8_t* probe_validity,
+                         int64_t probe_rows, int8_t* out_value, uint8_t* out_null);
 /* multi-threaded probe timing leg for the CPU baseline: `threads` workers each take 8192-row pages
  * (BigintPagesHash.getAddressIndex(int[],Page) 3-phase batching); returns seconds */
 double orc_join_probe_timed(const orc_join* j, const int64_t* probe_keys, int64_t n, int32_t threads, int32_t* out,

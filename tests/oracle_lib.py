@@ -70,6 +70,7 @@ def load():
         "orc_join_positions": (None, [VP, PP, VP, VP]),
         "orc_join_expand": (C.c_int64, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP, C.c_int64]),
         "orc_semi_join_bigint": (None, [VP, VP, C.c_int64, VP, VP, C.c_int64, VP, VP]),
+        "orc_semi_join_float": (None, [C.c_int32, VP, VP, C.c_int64, VP, VP, C.c_int64, VP, VP]),
         "orc_join_probe_timed": (C.c_double, [VP, VP, C.c_int64, C.c_int32, VP, VP, VP]),
         "orc_partition_ids": (None, [PP, VP, C.c_int32, C.c_int32, VP, VP]),
         "orc_partition_positions": (None, [PP, VP, C.c_int32, C.c_int32, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
@@ -318,6 +319,22 @@ def semi_join_bigint(set_block, probe_block):
     val = np.zeros(max(len(pv), 1), dtype=np.int8)
     isnull = np.zeros(max(len(pv), 1), dtype=np.uint8)
     lib.orc_semi_join_bigint(_p(sv), _p(svalid), len(sv), _p(pv), _p(pvalid), len(pv), _p(val), _p(isnull))
+    return [None if isnull[i] else bool(val[i]) for i in range(len(pv))]
+
+
+def semi_join_float(set_block, probe_block):
+    """HashSemiJoinOperator's BOOLEAN column over a DOUBLE or REAL channel (IDENTICAL membership: a NaN in the set answers NaN probes)"""
+    from trino_b200 import abi
+    lib = load()
+    kind = 1 if set_block.type == abi.FLOAT64 else 2
+    assert set_block.type == probe_block.type and set_block.type in (abi.FLOAT64, abi.FLOAT32)
+    sv = np.ascontiguousarray(set_block.values)
+    pv = np.ascontiguousarray(probe_block.values)
+    svalid = None if set_block.nulls is None else np.packbits(~set_block.nulls, bitorder="little")
+    pvalid = None if probe_block.nulls is None else np.packbits(~probe_block.nulls, bitorder="little")
+    val = np.zeros(max(len(pv), 1), dtype=np.int8)
+    isnull = np.zeros(max(len(pv), 1), dtype=np.uint8)
+    lib.orc_semi_join_float(kind, _p(sv), _p(svalid), len(sv), _p(pv), _p(pvalid), len(pv), _p(val), _p(isnull))
     return [None if isnull[i] else bool(val[i]) for i in range(len(pv))]
 
 

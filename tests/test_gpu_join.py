@@ -324,6 +324,43 @@ def test_semi_join_reference_cases_and_random(ctx):
     assert out.rows() == [(1, False), (None, False)]
 
 
+@pytest.mark.parametrize("kind", ["double", "real"])
+@pytest.mark.parametrize("set_has_nan", [False, True])
+def test_semi_join_over_floating_point_keys(ctx, kind, set_has_nan):
+    """The semi-join's ChannelSet compares with IDENTICAL (M/operator/FlatSet.java:54,374): a NaN probe key is a member iff the set holds a NaN
+    (any encoding), -0.0 and +0.0 are one member; NULLs as for BIGINT keys (HashSemiJoinOperator.java:181-199)."""
+    rng = np.random.default_rng(31 + set_has_nan)
+    ns, npr = 2000, 30000
+    def column(n, with_nan, p_null):
+        v = rng.integers(-300, 300, n) * 0.5
+        v[rng.random(n) < 0.03] = -0.0
+        if kind == "double":
+            bits = v.astype(np.float64).view(np.uint64).copy()
+            if with_nan:
+                bits[rng.random(n) < 0.02] = rng.choice(np.array([0x7FF8000000000000, 0xFFF8000000000001, 0x7FF0000000000001], dtype=np.uint64))
+            return Block.double(bits.view(np.float64), rng.random(n) < p_null if p_null else None)
+        bits = v.astype(np.float32).view(np.uint32).copy()
+        if with_nan:
+            bits[rng.random(n) < 0.02] = rng.choice(np.array([0x7FC00000, 0xFFC00001, 0x7F800001], dtype=np.uint32))
+        return Block.real(bits.view(np.float32), rng.random(n) < p_null if p_null else None)
+    for set_nulls in (0.0, 0.01):
+        sv = column(ns, set_has_nan, set_nulls)
+        pk = column(npr, True, 0.05)
+        bridge = ops.JoinBridge()
+        sb = ops.SetBuilderOperatorFactory(ctx, bridge, 0).create_operator()
+        sb.add_input(Page(sv))
+        sb.finish()
+        sj = ops.HashSemiJoinOperatorFactory(ctx, bridge, 1).create_operator()
+        sj.add_input(Page(Block.bigint(np.arange(npr)), pk))
+        out = sj.get_output()
+        sj.close(); sb.close(); bridge.lookup_source.close()
+        got = [r[2] for r in out.rows()]
+        want = o.semi_join_float(sv, pk)
+        assert got == want, (kind, set_has_nan, set_nulls)
+        nan_rows = [i for i in range(npr) if not pk.is_null(i) and pk.get(i) != pk.get(i)]
+        assert nan_rows and all(got[i] == (True if set_has_nan else (None if set_nulls else False)) for i in nan_rows)
+
+
 def test_build_side_key_domain(ctx):
     """DynamicFilterSourceOperator / JoinDomainBuilder collect the build-side key domain: the distinct values while they are few,
     else min/max.  Here it is read off the finished table."""

@@ -1046,6 +1046,7 @@ struct tgpu_lookup {
     DevBuf visited;
     std::mutex visited_lock;
     int64_t null_key_rows = -1;         // build rows whose (first) key channel is NULL; -1 = not counted yet
+    int64_t nan_key_rows = -1;          // DOUBLE / REAL key: build rows whose key is NaN (members of a semi-join's ChannelSet); -1 = not counted yet
 };
 
 namespace {
@@ -1173,14 +1174,35 @@ __global__ void join_unvisited_flags_kernel(const uint8_t* __restrict__ visited,
 }
 
 // HashSemiJoinOperator.process :181-199: value and NULL byte of the appended BOOLEAN column
+// float_kind: 0 = not a floating-point key, 1 = DOUBLE, 2 = REAL.  The ChannelSet compares with IDENTICAL (M/operator/FlatSet.java:54,374): a NaN
+// probe key is in the set iff the set holds a NaN - which the EQUAL-semantics lookup cannot answer (NaN matches nothing there) - while -0.0 / +0.0
+// are one member under both
+__device__ __forceinline__ bool key_is_nan(const ColRef& key, int float_kind, int64_t i)
+{
+    if (float_kind == 1) return ((unsigned long long)tg_load_i64(key, i) & 0x7FFFFFFFFFFFFFFFULL) > 0x7FF0000000000000ULL;
+    if (float_kind == 2) return ((unsigned int)tg_load_i64(key, i) & 0x7FFFFFFFu) > 0x7F800000u;
+    return false;
+}
+
+__global__ void count_nan_keys_kernel(ColRef key, int float_kind, int64_t n, unsigned long long* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int mine = 0;
+    for (; i < n; i += stride) mine += tg_valid(key.validity, i) && key_is_nan(key, float_kind, i);
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
+}
+
 __global__ void semi_join_kernel(const int* __restrict__ positions, const uint8_t* __restrict__ key_validity, int64_t n, int set_empty, int set_has_null,
-                                 signed char* __restrict__ value, uint8_t* __restrict__ is_null)
+                                 signed char* __restrict__ value, uint8_t* __restrict__ is_null, ColRef key, int float_kind, int set_has_nan)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         bool probe_null = !tg_valid(key_validity, i);
         bool contains = positions[i] >= 0;
+        if (float_kind && !probe_null && key_is_nan(key, float_kind, i)) contains = set_has_nan != 0;
         bool out_null, v;
         if (probe_null) { out_null = !set_empty; v = false; }
         else if (!contains && set_has_null) { out_null = true; v = false; }
@@ -1889,9 +1911,7 @@ struct SemiJoinOp : tgpu_op {
         TG_TRY(tg_ingest_page(ctx, page, &in));
         if (probe_channel < 0 || probe_channel >= (int32_t)in.cols.size()) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "probe join channel out of range");
         const DevColumn& key = in.cols[probe_channel];
-        const bool real_set = lookup->generic && lookup->build_keys.size() == 1 && lookup->build_keys[0].type == TGPU_FLOAT32;
-        if (key.type == TGPU_FLOAT64 || lookup->key_type == TGPU_FLOAT64 || key.type == TGPU_FLOAT32 || real_set)
-            return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "DOUBLE / REAL semi-join keys (NaN is IDENTICAL to NaN in a ChannelSet): keep the Java operator");
+        const int float_kind = key.type == TGPU_FLOAT64 ? 1 : key.type == TGPU_FLOAT32 ? 2 : 0;
         DevBuf pos;
         TG_TRY(pos.alloc(ctx, (size_t)n * 4));
         if (lookup->generic) {
@@ -1908,7 +1928,7 @@ struct SemiJoinOp : tgpu_op {
         DevBuf is_null;
         TG_TRY(is_null.alloc(ctx, (size_t)n));
         TG_LAUNCH(ctx, semi_join_kernel, tg_grid(ctx, n, 1024, 8), 256, 0, pos.as<int>(), key.validity, n, lookup->positions == 0 ? 1 : 0,
-                  lookup->null_key_rows > 0 ? 1 : 0, out.own_data->as<signed char>(), is_null.as<uint8_t>());
+                  lookup->null_key_rows > 0 ? 1 : 0, out.own_data->as<signed char>(), is_null.as<uint8_t>(), tg_colref(key), float_kind, lookup->nan_key_rows > 0 ? 1 : 0);
         tgpu_column bm;
         memset(&bm, 0, sizeof(bm));
         bm.type = TGPU_INT8;
@@ -1955,6 +1975,24 @@ static int lookup_count_null_keys(tgpu_ctx* ctx, tgpu_lookup* lk)
     int64_t v = 0;
     TG_TRY(tg_read_i64(ctx, cnt.p, &v));
     lk->null_key_rows = v;
+    return TGPU_OK;
+}
+
+static int lookup_count_nan_keys(tgpu_ctx* ctx, tgpu_lookup* lk)
+{
+    if (lk->nan_key_rows >= 0) return TGPU_OK;
+    lk->nan_key_rows = 0;
+    if (lk->positions == 0) return TGPU_OK;
+    const DevColumn* key = lk->generic ? (lk->build_keys.empty() ? nullptr : &lk->build_keys[0]) : (lk->store.cols.empty() ? nullptr : &lk->store.cols[0]);
+    const int float_kind = !key ? 0 : key->type == TGPU_FLOAT64 ? 1 : key->type == TGPU_FLOAT32 ? 2 : 0;
+    if (!float_kind) return TGPU_OK;
+    DevBuf cnt;
+    TG_TRY(cnt.alloc(ctx, 8));
+    TG_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, 8, ctx->stream));
+    TG_LAUNCH(ctx, count_nan_keys_kernel, tg_grid(ctx, lk->positions, 1024, 8), 256, 0, tg_colref(*key), float_kind, lk->positions, cnt.as<unsigned long long>());
+    int64_t v = 0;
+    TG_TRY(tg_read_i64(ctx, cnt.p, &v));
+    lk->nan_key_rows = v;
     return TGPU_OK;
 }
 
@@ -2047,6 +2085,7 @@ extern "C" int tgpu_semi_join_create(tgpu_ctx* ctx, tgpu_lookup* lookup, int32_t
     TG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (lookup->generic && lookup->build_keys.size() != 1) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "a semi-join set has one channel");
     TG_TRY(lookup_count_null_keys(ctx, lookup));
+    TG_TRY(lookup_count_nan_keys(ctx, lookup));
     SemiJoinOp* op = new SemiJoinOp(ctx, lookup);
     op->probe_channel = probe_join_channel;
     *out = op;
