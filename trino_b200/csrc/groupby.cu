@@ -1961,6 +1961,7 @@ struct AggOp : tgpu_op {
                 src = src_of_channel(f.input_channel, &type, in);
                 if (src < 0) return tg_fail(ctx, TGPU_ERR_INVALID_ARGUMENT, "aggregate input channel %d out of range", f.input_channel);
                 if (type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregates over variable-width inputs are not supported");
+                if (type == TGPU_FLOAT32) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a REAL channel: keep the Java accumulator", f.function);
             }
             bool dbl = type == TGPU_FLOAT64;
             fp.in_elem_is_double = dbl;
@@ -2833,6 +2834,7 @@ struct AggOp : tgpu_op {
                     const DevColumn* c = nullptr;
                     TG_TRY(channel(f.input_channel, &c));
                     if (c->type == TGPU_UTF8) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregates over variable-width inputs are not supported");
+                    if (c->type == TGPU_FLOAT32) return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a REAL channel: keep the Java accumulator", f.function);
                     if (c->type == TGPU_INT128 && f.function != TGPU_AGG_SUM_DECIMAL && f.function != TGPU_AGG_AVG_DECIMAL && f.function != TGPU_AGG_COUNT)
                         return tg_fail(ctx, TGPU_ERR_NOT_SUPPORTED, "aggregate function %d over a 128-bit channel (only count and the decimal sum are built)", f.function);
                     k.in_ch = f.input_channel;
