@@ -340,7 +340,7 @@ public final class GpuJoinOperatorFactories
         @Override
         public OperatorFactory duplicate()
         {
-            return new GpuPartitionedOutputOperatorFactory(operatorId, planNodeId, types, partitionChannels, bucketCount, bucketToPartition, nullChannel, replicatesAnyRow, enqueue);
+            return new GpuPartitionedOutputOperatorFactory(operatorId, planNodeId, types, partitionChannels, bucketCount, bucketToPartition, nullChannel, replicatesAnyRow, partitionConstants, partitionConstantTypes, enqueue);
         }
     }
 }
