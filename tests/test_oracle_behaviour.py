@@ -222,6 +222,39 @@ def test_semi_join_reference_cases():
     assert o.semi_join_bigint(Block.bigint([]), Block.bigint([1, None])) == [False, False]
 
 
+def test_semi_join_over_floats_is_identical_membership():
+    """The ChannelSet is a FlatSet compared with IDENTICAL (M/operator/FlatSet.java:54,374; DoubleType.java:218-229, RealType.java:172-185): the
+    BIGINT reference cases (TestHashSemiJoinOperator) hold verbatim over DOUBLE and REAL values, a NaN of any encoding is one member, -0.0 is +0.0."""
+    for case in reference_cases()["semi_join"]:
+        for make in (Block.double, lambda v: Block.real([None if x is None else np.float32(x) for x in v])):
+            assert o.semi_join_float(make(case["set"]), make(case["probe"])) == case["expected"], case["source"]
+    nan_a = np.array([0x7FF8000000000000], dtype=np.uint64).view(np.float64)[0]
+    nan_b = np.array([0xFFF0000000000001], dtype=np.uint64).view(np.float64)[0]
+    assert o.semi_join_float(Block.double([1.0, nan_a, -0.0]), Block.double([nan_b, 0.0, 2.0, None])) == [True, True, False, None]
+    assert o.semi_join_float(Block.double([1.0, None]), Block.double([nan_b, 1.0])) == [None, True]          # not contained + the set holds a NULL -> NULL
+    assert o.semi_join_float(Block.double([]), Block.double([nan_b, None])) == [False, False]                # empty set
+    rn = np.array([0x7FC00000, 0xFF800001], dtype=np.uint32).view(np.float32)
+    assert o.semi_join_float(Block.real(np.array([rn[0], 4.0], dtype=np.float32)), Block.real(np.array([rn[1], -4.0, 4.0], dtype=np.float32))) == [True, False, True]
+
+
+def test_local_partition_function_and_constants_follow_the_row_hash():
+    """LocalPartitionGenerator (M/operator/exchange/LocalPartitionGenerator.java:45-77) over the row hash; a partition constant is a
+    RunLengthEncodedBlock of the value in the function page (PagePartitioner.java:436-451): one partition for a lone constant."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    page = Page(Block.bigint(rng.integers(-10**9, 10**9, n)), Block.varchar(["k%d" % (i % 50) for i in range(n)]))
+    for P in (1, 2, 16):
+        ids = o.local_partition_ids(page, [0, 1], P)
+        assert ids.min() >= 0 and ids.max() < P
+        if P == 16:
+            assert len(set(ids.tolist())) == 16
+    assert (o.local_partition_ids(page, [0], 8) != o.partition_ids(page, [0], 8)).any()      # not the inter-stage function
+    const = Page(RunLengthEncodedBlock(Block.bigint([1]), n), page.get_block(0))
+    assert len(set(o.partition_ids(const, [0], 37).tolist())) == 1
+    mixed = o.partition_ids(const, [0, 1], 37)
+    assert len(set(mixed.tolist())) > 30 and (mixed != o.partition_ids(page, [0], 37)).any()
+
+
 def test_accumulator_known_answers():
     # AbstractTestAggregationFunction sequences with the expected values of TestDoubleSum/TestDoubleAverage/TestCount/TestLongSum
     aggs = [(abi.AGG_COUNT_STAR, -1, -1), (abi.AGG_COUNT, 1, -1), (abi.AGG_SUM, 1, -1), (abi.AGG_AVG, 1, -1), (abi.AGG_MIN, 1, -1), (abi.AGG_MAX, 1, -1),
